@@ -1,0 +1,136 @@
+/*
+ * nrs_b200.h -- C ABI of the B200-native hot paths of navtech-radar-slam.
+ *
+ * This is the drop-in boundary.  The reference has no FFI layer; its "operator API" is the
+ * set of C++ signatures its two ROS nodes call.  The C++ adapters in
+ * navtech-radar-slam_b200/cpp/ keep those signatures and forward to the entry points below;
+ * INTEGRATION.md shows the binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; caller owns every buffer; the library never frees a
+ *     caller buffer and never keeps a caller pointer after the call returns.
+ *   - every function returns 0 on success or a negative NRS_E* code; no exceptions cross the
+ *     ABI; nrs_last_error() returns a thread-local message for the last failure.
+ *   - "host" pointers are ordinary CPU memory (pinned is faster, not required);
+ *     "_dev" entry points take device pointers, enqueue on the context stream and do NOT
+ *     synchronise (call nrs_ctx_sync).
+ *   - matrices use the reference's in-memory layout: Eigen::MatrixXd is column-major, so a
+ *     20x60 descriptor is 60 columns of 20 doubles (ring index fastest), 9600 bytes; a 3xK
+ *     point matrix is K columns of (x,y,z).  cv::Mat images are row-major.
+ *   - there is no CPU fallback: every compute entry point fails with NRS_ENODEVICE when no
+ *     CUDA device / sm_100 kernel image is available.
+ *
+ * Paths are relative to /root/reference; ORORA/ = outlier-robust-radar-odometry/,
+ * SC/ = pgo/SC-A-LOAM/include/scancontext/.
+ */
+#ifndef NRS_B200_H
+#define NRS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRS_OK          0
+#define NRS_EINVAL     -1   /* bad argument (the reference throws std::invalid_argument) */
+#define NRS_ENODEVICE  -2   /* no CUDA device / kernel image: there is no CPU fallback     */
+#define NRS_ECUDA      -3   /* CUDA runtime error, see nrs_last_error()                    */
+#define NRS_ENOMEM     -4
+#define NRS_ECAPACITY  -5   /* caller's output buffer too small                            */
+#define NRS_ENCCL      -6
+
+#define NRS_SC_RINGS    20  /* SC/Scancontext.h:85 */
+#define NRS_SC_SECTORS  60  /* SC/Scancontext.h:86 */
+#define NRS_SC_DESC     (NRS_SC_RINGS * NRS_SC_SECTORS)
+
+typedef struct nrs_ctx   nrs_ctx;    /* one CUDA device + stream + scratch            */
+typedef struct nrs_sc_db nrs_sc_db;  /* device-resident keyframe descriptor database  */
+
+/* Result of one database search: the (min_dist, nn_idx, nn_align) triple of
+ * SCManager::detectLoopClosureID (SC/Scancontext.cpp:362-396). 16 bytes. */
+typedef struct nrs_sc_result {
+    double  dist;    /* 1e7 when nothing beat the reference's initial value */
+    int32_t idx;     /* keyframe index in [first,last) (or the candidate id); 0 when none */
+    int32_t shift;   /* column shift (sector bins) of the best alignment */
+} nrs_sc_result;
+
+/* ---- library / context -------------------------------------------------------------- */
+int         nrs_version(void);
+const char *nrs_last_error(void);
+/* number of this library's kernels launched by the calling process so far (bench.py's
+ * gpu_launches claim is a difference of two reads). */
+uint64_t    nrs_kernel_launches(void);
+
+int   nrs_ctx_create(int device, nrs_ctx **out);
+int   nrs_ctx_destroy(nrs_ctx *ctx);
+int   nrs_ctx_sync(nrs_ctx *ctx);
+void *nrs_ctx_stream(nrs_ctx *ctx);          /* the cudaStream_t all work is enqueued on */
+int   nrs_ctx_device(nrs_ctx *ctx);
+int   nrs_ctx_sm_count(nrs_ctx *ctx);
+
+/* ---- ScanContext loop detector (SC/Scancontext.{h,cpp}) ------------------------------- */
+
+/* SCManager::makeScancontext (Scancontext.cpp:151-195).  xyz = P points (x,y,z) float32,
+ * host.  desc_out = 1200 doubles column-major, host.  lidar_height/max_radius are
+ * LIDAR_HEIGHT (2.0) and PC_MAX_RADIUS (80.0) of Scancontext.h:83,87. */
+int nrs_sc_make(nrs_ctx *ctx, const float *xyz_Px3, int P, double lidar_height,
+                double max_radius, double *desc_out);
+
+/* makeRingkeyFromScancontext / makeSectorkeyFromScancontext (Scancontext.cpp:198-227).
+ * Either output may be NULL. */
+int nrs_sc_keys(nrs_ctx *ctx, const double *desc, double *ringkey20, double *sectorkey60);
+
+/* SCManager::fastAlignUsingVkey (Scancontext.cpp:93-113): argmin over 60 column shifts of
+ * ||vkey1 - shift(vkey2, s)||, strict '<' (lowest shift on ties). */
+int nrs_sc_fast_align(nrs_ctx *ctx, const double *vkey1_60, const double *vkey2_60, int32_t *shift);
+
+/* SCManager::distDirectSC (Scancontext.cpp:69-90): 1 - mean column cosine similarity over the
+ * columns where neither side is all-zero (NaN when there is none, like the reference). */
+int nrs_sc_dist_direct(nrs_ctx *ctx, const double *sc1, const double *sc2, double *dist);
+
+/* SCManager::distanceBtnScanContext(sc1, sc2) (Scancontext.cpp:116-148): sc1 is the query,
+ * sc2 the candidate whose columns are shifted. */
+int nrs_sc_pair(nrs_ctx *ctx, const double *sc1, const double *sc2, double *dist, int32_t *shift);
+
+/* The database mirrors SCManager::polarcontexts_ (Scancontext.h:111) on the device:
+ * keyframe i occupies bytes [9600*i, 9600*(i+1)).  Append is thread-safe against query;
+ * a query sees a consistent prefix (the reference's node appends and queries from two
+ * threads without a lock, SC/../src/laserPosegraphOptimization.cpp:492 vs :561). */
+int nrs_sc_db_create(nrs_ctx *ctx, int capacity_hint, nrs_sc_db **out);
+int nrs_sc_db_destroy(nrs_sc_db *db);
+int nrs_sc_db_size(nrs_sc_db *db);
+int nrs_sc_db_clear(nrs_sc_db *db);
+/* saveScancontextAndKeys (Scancontext.cpp:236-246): append `count` descriptors from host. */
+int nrs_sc_db_append(nrs_sc_db *db, const double *desc_host, int count);
+/* makeAndSaveScancontextAndKeys (Scancontext.cpp:249-260): build the descriptor from a
+ * cloud on the device and append it; desc_out (nullable, host) receives a copy so the
+ * adapter can keep the reference's public polarcontexts_ vector populated. */
+int nrs_sc_db_append_cloud(nrs_sc_db *db, const float *xyz_Px3, int P, double lidar_height,
+                           double max_radius, double *desc_out);
+/* copy descriptors [first, first+count) back to host */
+int nrs_sc_db_read(nrs_sc_db *db, int first, int count, double *desc_host);
+const double *nrs_sc_db_device_ptr(nrs_sc_db *db);
+
+/* The search loop of detectLoopClosureID (Scancontext.cpp:380-396).
+ *   candidate_idx == NULL : exhaustive over keyframes [first, last)   (north_star)
+ *   candidate_idx != NULL : exactly those n_cand ids, in that order   (reference: 3 kd-tree ids)
+ * Strict '<' everywhere: lowest shift, then first keyframe wins ties; a keyframe whose
+ * distance is NaN (no effective column) never wins; nothing found -> {1e7, 0, 0}. */
+int nrs_sc_query(nrs_sc_db *db, const double *query_host, int first, int last,
+                 const int32_t *candidate_idx, int n_cand, nrs_sc_result *result_host);
+/* Per-keyframe distanceBtnScanContext(query, db[i]) for i in [first,last):
+ * dist_out/shift_out have last-first entries (host). */
+int nrs_sc_query_all(nrs_sc_db *db, const double *query_host, int first, int last,
+                     double *dist_out, int32_t *shift_out, nrs_sc_result *result_host);
+/* Device-resident, asynchronous variant: query_dev (1200 doubles) and result_dev live in
+ * device memory; enqueued on the context stream, no host synchronisation.  idx_offset is
+ * added to the reported index (a shard's global offset). */
+int nrs_sc_query_dev(nrs_sc_db *db, const double *query_dev, int first, int last,
+                     int32_t idx_offset, nrs_sc_result *result_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRS_B200_H */

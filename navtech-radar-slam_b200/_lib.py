@@ -1,0 +1,138 @@
+"""ctypes binding of libnrs_b200.so -- fails loudly when the extension is missing."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+_SO = os.path.join(_HERE, "libnrs_b200.so")
+_HEADER = os.path.join(_ROOT, "include", "nrs_b200.h")
+
+NRS_OK, NRS_EINVAL, NRS_ENODEVICE, NRS_ECUDA, NRS_ENOMEM, NRS_ECAPACITY, NRS_ENCCL = 0, -1, -2, -3, -4, -5, -6
+
+
+class NrsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"nrs error {code}: {msg}")
+        self.code = code
+
+
+class ScResult(C.Structure):
+    _fields_ = [("dist", C.c_double), ("idx", C.c_int32), ("shift", C.c_int32)]
+
+
+def library_path():
+    return _SO
+
+
+def declared_symbols():
+    """Every function name include/nrs_b200.h declares (used by the CPU-side export test)."""
+    text = open(_HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nrs_[a-z0-9_]+)\s*\(", text)))
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library.  There is deliberately no fallback: a missing .so is an error."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise NrsError(NRS_ENODEVICE,
+                           f"{_SO} not built -- run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                           "this package has no CPU fallback")
+        _lib = C.CDLL(_SO)
+        _declare(_lib)
+    return _lib
+
+
+def _declare(L):
+    vp, i32, f64 = C.c_void_p, C.c_int, C.c_double
+    L.nrs_version.restype = i32
+    L.nrs_last_error.restype = C.c_char_p
+    L.nrs_kernel_launches.restype = C.c_uint64
+    L.nrs_ctx_create.argtypes = [i32, C.POINTER(vp)]
+    L.nrs_ctx_destroy.argtypes = [vp]
+    L.nrs_ctx_sync.argtypes = [vp]
+    L.nrs_ctx_stream.restype = vp
+    L.nrs_ctx_stream.argtypes = [vp]
+    L.nrs_ctx_device.argtypes = [vp]
+    L.nrs_ctx_sm_count.argtypes = [vp]
+    L.nrs_sc_make.argtypes = [vp, vp, i32, f64, f64, vp]
+    L.nrs_sc_keys.argtypes = [vp, vp, vp, vp]
+    L.nrs_sc_pair.argtypes = [vp, vp, vp, vp, vp]
+    L.nrs_sc_db_create.argtypes = [vp, i32, C.POINTER(vp)]
+    L.nrs_sc_db_destroy.argtypes = [vp]
+    L.nrs_sc_db_size.argtypes = [vp]
+    L.nrs_sc_db_clear.argtypes = [vp]
+    L.nrs_sc_db_append.argtypes = [vp, vp, i32]
+    L.nrs_sc_db_append_cloud.argtypes = [vp, vp, i32, f64, f64, vp]
+    L.nrs_sc_db_read.argtypes = [vp, i32, i32, vp]
+    L.nrs_sc_db_device_ptr.restype = vp
+    L.nrs_sc_db_device_ptr.argtypes = [vp]
+    L.nrs_sc_query.argtypes = [vp, vp, i32, i32, vp, i32, vp]
+    L.nrs_sc_query_all.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    L.nrs_sc_query_dev.argtypes = [vp, vp, i32, i32, i32, vp]
+    for name in declared_symbols():
+        fn = getattr(L, name, None)
+        if fn is not None and fn.restype is C.c_int and name not in ("nrs_version",):
+            pass
+
+
+def check(rc):
+    if rc < 0:
+        raise NrsError(rc, lib().nrs_last_error().decode(errors="replace"))
+    return rc
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def f64(a, n=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if n is not None and a.size != n:
+        raise ValueError(f"expected {n} doubles, got {a.size}")
+    return a
+
+
+class Context:
+    """One CUDA device + stream (nrs_ctx)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        check(lib().nrs_ctx_create(device, C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def stream(self):
+        return lib().nrs_ctx_stream(self._h)
+
+    @property
+    def sm_count(self):
+        return lib().nrs_ctx_sm_count(self._h)
+
+    @property
+    def device(self):
+        return lib().nrs_ctx_device(self._h)
+
+    def sync(self):
+        check(lib().nrs_ctx_sync(self._h))
+
+    def close(self):
+        if self._h:
+            lib().nrs_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,847 @@
+// sc_kernels.cu -- ScanContext loop detector on sm_100a.
+//
+// Replaces SCManager's makeScancontext / ring+sector keys / distanceBtnScanContext and the
+// search loop of detectLoopClosureID (reference: pgo/SC-A-LOAM/include/scancontext/
+// Scancontext.cpp:69-148,151-227,380-396) with a batched search over a device-resident
+// descriptor database.
+//
+// Arithmetic contract.  The reference computes in f64 through Eigen 3.3 built for SSE2
+// (packets of 2 doubles, no FMA).  Every reduction here follows Eigen's
+// LinearVectorizedTraversal order -- four running sums over elements i%4 == 0,1,2,3,
+// combined as (s0+s2)+(s1+s3) -- and this file is compiled with --fmad=false so that a
+// product is rounded before it is added.  Division and sqrt are IEEE in CUDA for doubles.
+// With that, distances are bit-identical to the CPU restatement in oracle/sc_ref.c for
+// binary {0,c} descriptors (every partial sum is exact) and for general-valued ones.
+//
+// Kernel sc_search_kernel (K10): one warp per keyframe, persistent grid (one 8-warp CTA per
+// SM, ~200 KB of shared memory each).  Each 9600-byte descriptor is staged into shared
+// memory by a 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) signalled on an mbarrier, two
+// stages per warp, so the next two keyframes stream in while the current one is scored.
+// Bound: HBM.  Algorithmic bytes per keyframe = 9600 (f64 20x60, the reference's
+// MatrixXd); per query = 9600*D + 9600 + 16.
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int R = NRS_SC_RINGS;      // 20
+constexpr int S = NRS_SC_SECTORS;    // 60
+constexpr int DESC = R * S;          // 1200 doubles = 9600 B
+constexpr int WARPS = 8;
+constexpr int THREADS = WARPS * 32;
+constexpr int STAGES = 2;
+constexpr int QSTRIDE = 22;          // padded query column stride (doubles): LDS.128 conflict-free
+constexpr int NSHIFT = 7;            // 2 * round(0.5 * SEARCH_RATIO * 60) + 1   (Scancontext.cpp:123)
+constexpr int RADIUS = 3;
+constexpr double SENTINEL = 10000000.0;   // Scancontext.cpp:134,362
+
+struct WarpSmem {
+    double   tile[STAGES][DESC];   // TMA destination, column-major 20x60
+    double   vk2[2 * S];           // sector key of the keyframe, stored twice (no modulo)
+    double   kn[S];                // column norms of the keyframe
+    double   sims[NSHIFT][S];      // per (shift slot, query column) cosine similarity
+    uint64_t bar[STAGES];
+};
+
+struct BlockSmem {
+    double   q[S * QSTRIDE];       // query descriptor, padded columns
+    double   qn[S];                // query column norms
+    double   qv[S];                // query sector key
+    WarpSmem w[WARPS];
+    double   red_d[WARPS];
+    int      red_pos[WARPS];
+    int      red_idx[WARPS];
+    int      red_s[WARPS];
+    int      is_last;
+};
+
+struct BlockResult {
+    double dist;
+    int    pos;
+    int    idx;
+    int    shift;
+    int    pad;
+};
+
+// Eigen redux order over 20 values held in registers.
+__device__ __forceinline__ double redux20(const double (&v)[R])
+{
+    double a0 = v[0], a1 = v[1], b0 = v[2], b1 = v[3];
+#pragma unroll
+    for (int i = 4; i < R; i += 4) {
+        a0 += v[i];
+        a1 += v[i + 1];
+        b0 += v[i + 2];
+        b1 += v[i + 3];
+    }
+    a0 += b0;
+    a1 += b1;
+    return a0 + a1;
+}
+
+__device__ __forceinline__ double redux20_dot(const double (&a)[R], const double (&b)[R])
+{
+    double a0 = a[0] * b[0], a1 = a[1] * b[1], b0 = a[2] * b[2], b1 = a[3] * b[3];
+#pragma unroll
+    for (int i = 4; i < R; i += 4) {
+        a0 += a[i] * b[i];
+        a1 += a[i + 1] * b[i + 1];
+        b0 += a[i + 2] * b[i + 2];
+        b1 += a[i + 3] * b[i + 3];
+    }
+    a0 += b0;
+    a1 += b1;
+    return a0 + a1;
+}
+
+// strict-'<' sequential scan == lexicographic min over (value, order key); NaN never wins.
+__device__ __forceinline__ bool better(double d1, int k1, double d2, int k2)
+{
+    return (d1 < d2) || (d1 == d2 && k1 < k2);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+sc_search_kernel(const double *__restrict__ db, const double *__restrict__ query,
+                 const int32_t *__restrict__ cand, int first, int n_items, int idx_offset,
+                 double *__restrict__ dist_all, int32_t *__restrict__ shift_all,
+                 BlockResult *__restrict__ block_results, unsigned int *__restrict__ ticket,
+                 nrs_sc_result *__restrict__ final_result)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BlockSmem &sm = *reinterpret_cast<BlockSmem *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpSmem &ws = sm.w[warp];
+
+    const int gw = blockIdx.x * WARPS + warp;
+    const int nw = gridDim.x * WARPS;
+
+    // ---- per-warp TMA pipeline prologue (runs while the block stages the query) ----------
+    if (lane == 0) {
+        nrs::mbar_init(&ws.bar[0], 1);
+        nrs::mbar_init(&ws.bar[1], 1);
+        nrs::fence_mbar_init();
+#pragma unroll
+        for (int st = 0; st < STAGES; ++st) {
+            const int item = gw + st * nw;
+            if (item < n_items) {
+                const int kf = cand ? cand[item] : first + item;
+                nrs::mbar_expect_tx(&ws.bar[st], DESC * 8);
+                nrs::tma_load_1d(ws.tile[st], db + (size_t)kf * DESC, DESC * 8, &ws.bar[st]);
+            }
+        }
+    }
+
+    // ---- stage the query: padded columns, column norms, sector key -----------------------
+    for (int i = threadIdx.x; i < DESC; i += THREADS) {
+        const int c = i / R, r = i - c * R;
+        sm.q[c * QSTRIDE + r] = query[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < S) {
+        double v[R], sq[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            v[r] = sm.q[threadIdx.x * QSTRIDE + r];
+            sq[r] = v[r] * v[r];
+        }
+        sm.qv[threadIdx.x] = redux20(v) / (double)R;       // Scancontext.cpp:223 mean()
+        sm.qn[threadIdx.x] = sqrt(redux20(sq));            // Scancontext.cpp:78 norm()
+    }
+    __syncthreads();
+
+    double best_d = SENTINEL;
+    int best_pos = 0x7fffffff, best_idx = 0, best_s = 0;
+
+    for (int t = 0;; ++t) {
+        const int item = gw + t * nw;
+        if (item >= n_items) break;
+        const int st = t & 1;
+        const int kf = cand ? cand[item] : first + item;
+        nrs::mbar_wait(&ws.bar[st], (t >> 1) & 1);
+
+        // ---- phase A: two adjacent keyframe columns per lane -> registers; keys; norms ----
+        const bool own = lane < S / 2;
+        const int c0 = own ? 2 * lane : 0;
+        double k0[R], k1[R];
+        {
+            const double2 *src = reinterpret_cast<const double2 *>(&ws.tile[st][c0 * R]);
+#pragma unroll
+            for (int r = 0; r < R / 2; ++r) {
+                const double2 a = src[r];
+                const double2 b = src[R / 2 + r];
+                k0[2 * r] = a.x; k0[2 * r + 1] = a.y;
+                k1[2 * r] = b.x; k1[2 * r + 1] = b.y;
+            }
+        }
+        double kn0, kn1;
+        {
+            double sq[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) sq[r] = k0[r] * k0[r];
+            kn0 = sqrt(redux20(sq));
+#pragma unroll
+            for (int r = 0; r < R; ++r) sq[r] = k1[r] * k1[r];
+            kn1 = sqrt(redux20(sq));
+            if (own) {
+                const double m0 = redux20(k0) / (double)R;
+                const double m1 = redux20(k1) / (double)R;
+                ws.vk2[c0] = m0;     ws.vk2[c0 + S] = m0;
+                ws.vk2[c0 + 1] = m1; ws.vk2[c0 + 1 + S] = m1;
+                ws.kn[c0] = kn0;
+                ws.kn[c0 + 1] = kn1;
+            }
+        }
+        __syncwarp();
+        // the tile has been consumed into registers: refill this stage two keyframes ahead
+        if (lane == 0) {
+            const int item2 = item + STAGES * nw;
+            if (item2 < n_items) {
+                const int kf2 = cand ? cand[item2] : first + item2;
+                nrs::fence_proxy_async();
+                nrs::mbar_expect_tx(&ws.bar[st], DESC * 8);
+                nrs::tma_load_1d(ws.tile[st], db + (size_t)kf2 * DESC, DESC * 8, &ws.bar[st]);
+            }
+        }
+
+        // ---- phase B: fastAlignUsingVkey (Scancontext.cpp:93-113), one shift per lane ------
+        double fa_n = SENTINEL;
+        int fa_s = 0;
+#pragma unroll
+        for (int rnd = 0; rnd < 2; ++rnd) {
+            const int s = lane + 32 * rnd;
+            if (s < S) {
+                const double *vk = &ws.vk2[S - s];     // vk[i] == key_vkey[(i - s) mod 60]
+                double acc[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double d = sm.qv[i] - vk[i];
+                    acc[i] = d * d;
+                }
+#pragma unroll
+                for (int i = 4; i < S; i += 4) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double d = sm.qv[i + j] - vk[i + j];
+                        acc[j] += d * d;
+                    }
+                }
+                const double nrm = sqrt((acc[0] + acc[2]) + (acc[1] + acc[3]));
+                if (nrm < fa_n) { fa_n = nrm; fa_s = s; }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double on = __shfl_xor_sync(0xffffffffu, fa_n, off);
+            const int os = __shfl_xor_sync(0xffffffffu, fa_s, off);
+            if (better(on, os, fa_n, fa_s)) { fa_n = on; fa_s = os; }
+        }
+        const int s0 = fa_s;
+
+        // ---- phase C: 7 shifts x 60 columns of cosine similarity ---------------------------
+        // key column k at shift (s0 + d) meets query column (k + s0 + d) mod 60.  A lane owns
+        // key columns c0, c0+1 and walks the 8 query columns (c0 + s0 - 3 + t), t = 0..7:
+        // column t serves c0 at d = t-3 (t <= 6) and c0+1 at d = t-4 (t >= 1).
+        if (own) {
+            int qc = c0 + s0 - RADIUS + S;
+            qc = qc >= S ? qc - S : qc;
+            qc = qc >= S ? qc - S : qc;
+#pragma unroll
+            for (int tt = 0; tt < NSHIFT + 1; ++tt) {
+                double qcol[R];
+                const double2 *src = reinterpret_cast<const double2 *>(&sm.q[qc * QSTRIDE]);
+#pragma unroll
+                for (int r = 0; r < R / 2; ++r) {
+                    const double2 a = src[r];
+                    qcol[2 * r] = a.x; qcol[2 * r + 1] = a.y;
+                }
+                const double qnorm = sm.qn[qc];
+                if (tt <= NSHIFT - 1)
+                    ws.sims[tt][qc] = redux20_dot(qcol, k0) / (qnorm * kn0);        // :81
+                if (tt >= 1)
+                    ws.sims[tt - 1][qc] = redux20_dot(qcol, k1) / (qnorm * kn1);
+                qc = (qc + 1 == S) ? 0 : qc + 1;
+            }
+        }
+        __syncwarp();
+
+        // ---- phase C2: distDirectSC's sequential column sum per shift (:73-88) -------------
+        double dd = SENTINEL;
+        int ds = 0;
+        if (lane < NSHIFT) {
+            int s = s0 + lane - RADIUS + S;
+            s = s >= S ? s - S : s;
+            s = s >= S ? s - S : s;
+            const double *knv = &ws.kn[0];
+            double sum = 0.0;
+            int cnt = 0;
+            int kc = S - s;                 // key column paired with query column 0
+            kc = kc == S ? 0 : kc;
+            for (int c = 0; c < S; ++c) {
+                if (!((sm.qn[c] == 0) | (knv[kc] == 0))) {
+                    sum = sum + ws.sims[lane][c];
+                    cnt = cnt + 1;
+                }
+                kc = (kc + 1 == S) ? 0 : kc + 1;
+            }
+            const double dist = 1.0 - sum / (double)cnt;     // 0/0 -> NaN, never '<'
+            if (dist < SENTINEL) { dd = dist; ds = s; }
+        }
+        // min over the 7 shifts in ascending shift order with strict '<' (:135-144)
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, dd, off);
+            const int os = __shfl_xor_sync(0xffffffffu, ds, off);
+            if (better(od, os, dd, ds)) { dd = od; ds = os; }
+        }
+        if (lane == 0) {
+            if (dist_all) dist_all[item] = dd;
+            if (shift_all) shift_all[item] = ds;
+            if (dd < best_d) { best_d = dd; best_pos = item; best_idx = kf; best_s = ds; }
+        }
+        __syncwarp();
+    }
+
+    // ---- block reduce, then last-block-done grid reduce ------------------------------------
+    if (lane == 0) {
+        sm.red_d[warp] = best_d;
+        sm.red_pos[warp] = best_pos;
+        sm.red_idx[warp] = best_idx;
+        sm.red_s[warp] = best_s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double d = sm.red_d[0];
+        int p = sm.red_pos[0], ix = sm.red_idx[0], sh = sm.red_s[0];
+        for (int w = 1; w < WARPS; ++w)
+            if (better(sm.red_d[w], sm.red_pos[w], d, p)) {
+                d = sm.red_d[w]; p = sm.red_pos[w]; ix = sm.red_idx[w]; sh = sm.red_s[w];
+            }
+        BlockResult br;
+        br.dist = d; br.pos = p; br.idx = ix; br.shift = sh; br.pad = 0;
+        block_results[blockIdx.x] = br;
+        __threadfence();
+        const unsigned int tk = atomicAdd(ticket, 1u);
+        sm.is_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (sm.is_last && warp == 0) {
+        __threadfence();
+        double d = SENTINEL;
+        int p = 0x7fffffff, ix = 0, sh = 0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) {
+            const volatile BlockResult *br = block_results + b;
+            const double bd = br->dist;
+            const int bp = br->pos;
+            if (better(bd, bp, d, p)) { d = bd; p = bp; ix = br->idx; sh = br->shift; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, d, off);
+            const int op = __shfl_xor_sync(0xffffffffu, p, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, ix, off);
+            const int os = __shfl_xor_sync(0xffffffffu, sh, off);
+            if (better(od, op, d, p)) { d = od; p = op; ix = oi; sh = os; }
+        }
+        if (lane == 0) {
+            nrs_sc_result res;
+            res.dist = d;
+            res.idx = (d < SENTINEL) ? ix + idx_offset : 0;
+            res.shift = sh;
+            *final_result = res;
+            *ticket = 0u;      // ready for the next launch on this stream
+        }
+    }
+}
+
+// ---- makeScancontext (Scancontext.cpp:151-195) ---------------------------------------------
+__device__ __forceinline__ int enc_f32(float f)
+{
+    const int b = __float_as_int(f);
+    return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float dec_f32(int k)
+{
+    return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff);
+}
+
+__device__ __forceinline__ float xy2theta(float x, float y)      // Scancontext.cpp:23-36
+{
+    const double k = 180 / 3.14159265358979323846;
+    if ((x >= 0) & (y >= 0)) return (float)(k * atanf(y / x));
+    if ((x < 0) & (y >= 0)) return (float)(180 - (k * atanf(y / (-x))));
+    if ((x < 0) & (y < 0)) return (float)(180 + (k * atanf(y / x)));
+    if ((x >= 0) & (y < 0)) return (float)(360 - (k * atanf((-y) / x)));
+    return 0.0f;
+}
+
+__global__ void __launch_bounds__(256)
+sc_make_kernel(const float *__restrict__ xyz, int P, double lidar_height, double max_radius,
+               double *__restrict__ desc)
+{
+    __shared__ int bins[DESC];
+    const int empty = enc_f32(-1000.0f);                          // NO_POINT :158
+    for (int i = threadIdx.x; i < DESC; i += blockDim.x) bins[i] = empty;
+    __syncthreads();
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+        const float px = xyz[3 * p], py = xyz[3 * p + 1];
+        const float pz = (float)((double)xyz[3 * p + 2] + lidar_height);   // :168
+        if (px != px || py != py || pz != pz) continue;           // NaN: reference is UB
+        const float azim_range = sqrtf(px * px + py * py);        // :171
+        const float azim_angle = xy2theta(px, py);                // :172
+        if ((double)azim_range > max_radius) continue;            // :175
+        int ring = (int)ceil(((double)azim_range / max_radius) * R);     // :178
+        ring = max(min(R, ring), 1);
+        int sect = (int)ceil(((double)azim_angle / 360.0) * S);          // :179
+        sect = max(min(S, sect), 1);
+        atomicMax(&bins[(sect - 1) * R + (ring - 1)], enc_f32(pz));      // :182-183
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < DESC; i += blockDim.x)
+        desc[i] = (bins[i] == empty) ? 0.0 : (double)dec_f32(bins[i]);   // :187-190
+}
+
+// ---- ring key / sector key (Scancontext.cpp:198-227) ------------------------------------------
+__global__ void __launch_bounds__(96)
+sc_keys_kernel(const double *__restrict__ desc, double *__restrict__ ringkey,
+               double *__restrict__ sectorkey)
+{
+    const int t = threadIdx.x;
+    if (t < S) {                     // column means
+        double v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = desc[t * R + r];
+        if (sectorkey) sectorkey[t] = redux20(v) / (double)R;
+    } else if (t - S < R) {          // row means over 60 columns, Eigen order
+        const int r = t - S;
+        double acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = desc[i * R + r];
+        for (int i = 4; i < S; i += 4)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] += desc[(i + j) * R + r];
+        if (ringkey) ringkey[r] = ((acc[0] + acc[2]) + (acc[1] + acc[3])) / (double)S;
+    }
+}
+
+// ---- fastAlignUsingVkey (Scancontext.cpp:93-113) as a stand-alone operator: one warp ----------
+__global__ void __launch_bounds__(32)
+sc_fast_align_kernel(const double *__restrict__ vk1, const double *__restrict__ vk2,
+                     int32_t *__restrict__ out)
+{
+    __shared__ double a[S], b2[2 * S];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < S; i += 32) { a[i] = vk1[i]; b2[i] = vk2[i]; b2[i + S] = vk2[i]; }
+    __syncwarp();
+    double fa_n = SENTINEL;
+    int fa_s = 0;
+    for (int s = lane; s < S; s += 32) {
+        const double *vk = &b2[S - s];
+        double acc[4];
+        for (int i = 0; i < 4; ++i) { const double d = a[i] - vk[i]; acc[i] = d * d; }
+        for (int i = 4; i < S; i += 4)
+            for (int j = 0; j < 4; ++j) { const double d = a[i + j] - vk[i + j]; acc[j] += d * d; }
+        const double nrm = sqrt((acc[0] + acc[2]) + (acc[1] + acc[3]));
+        if (nrm < fa_n) { fa_n = nrm; fa_s = s; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double on = __shfl_xor_sync(0xffffffffu, fa_n, off);
+        const int os = __shfl_xor_sync(0xffffffffu, fa_s, off);
+        if (better(on, os, fa_n, fa_s)) { fa_n = on; fa_s = os; }
+    }
+    if (lane == 0) *out = fa_s;
+}
+
+// ---- distDirectSC (Scancontext.cpp:69-90) as a stand-alone operator ---------------------------
+__global__ void __launch_bounds__(64)
+sc_dist_direct_kernel(const double *__restrict__ sc1, const double *__restrict__ sc2,
+                      double *__restrict__ out)
+{
+    __shared__ double sim[S];
+    __shared__ int eff[S];
+    const int c = threadIdx.x;
+    if (c < S) {
+        double x[R], y[R], sq[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { x[r] = sc1[c * R + r]; y[r] = sc2[c * R + r]; }
+#pragma unroll
+        for (int r = 0; r < R; ++r) sq[r] = x[r] * x[r];
+        const double nx = sqrt(redux20(sq));
+#pragma unroll
+        for (int r = 0; r < R; ++r) sq[r] = y[r] * y[r];
+        const double ny = sqrt(redux20(sq));
+        eff[c] = !((nx == 0) | (ny == 0));
+        sim[c] = redux20_dot(x, y) / (nx * ny);
+    }
+    __syncthreads();
+    if (c == 0) {
+        double sum = 0.0;
+        int cnt = 0;
+        for (int i = 0; i < S; ++i)
+            if (eff[i]) { sum = sum + sim[i]; cnt = cnt + 1; }
+        *out = 1.0 - sum / (double)cnt;
+    }
+}
+
+}  // namespace
+
+// =================================================================================================
+// host side
+// =================================================================================================
+struct nrs_sc_db {
+    nrs_ctx     *ctx = nullptr;
+    std::mutex   mu;
+    double      *d_desc = nullptr;       // capacity * 1200 doubles
+    int          size = 0;
+    int          capacity = 0;
+    // per-db search scratch
+    BlockResult   *d_block = nullptr;
+    unsigned int  *d_ticket = nullptr;
+    nrs_sc_result *d_result = nullptr;
+    double        *d_query = nullptr;
+    nrs_sc_result *h_result = nullptr;   // pinned
+    double        *h_query = nullptr;    // pinned
+    int            max_blocks = 0;
+};
+
+namespace {
+
+int search_smem_bytes() { return (int)sizeof(BlockSmem); }
+
+int configure_search_kernel()
+{
+    static int done = 0;
+    if (!done) {
+        NRS_CUDA(cudaFuncSetAttribute(sc_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      search_smem_bytes()));
+        done = 1;
+    }
+    return NRS_OK;
+}
+
+// enqueue one search on the ctx stream
+int launch_search(nrs_ctx *ctx, const double *d_db, const double *d_query, const int32_t *d_cand,
+                  int first, int n_items, int idx_offset, double *d_dist_all, int32_t *d_shift_all,
+                  BlockResult *d_block, unsigned int *d_ticket, nrs_sc_result *d_result,
+                  int max_blocks)
+{
+    int rc = configure_search_kernel();
+    if (rc) return rc;
+    int blocks = (n_items + WARPS - 1) / WARPS;
+    blocks = std::max(1, std::min(blocks, max_blocks));
+    sc_search_kernel<<<blocks, THREADS, search_smem_bytes(), ctx->stream>>>(
+        d_db, d_query, d_cand, first, n_items, idx_offset, d_dist_all, d_shift_all, d_block,
+        d_ticket, d_result);
+    NRS_LAUNCHED();
+    return NRS_OK;
+}
+
+int db_reserve(nrs_sc_db *db, int want)
+{
+    if (want <= db->capacity) return NRS_OK;
+    int cap = db->capacity ? db->capacity : 1024;
+    while (cap < want) cap *= 2;
+    double *np = nullptr;
+    NRS_CUDA(cudaMalloc(&np, (size_t)cap * DESC * sizeof(double)));
+    if (db->d_desc) {
+        // in-flight searches read the old buffer: drain the stream before swapping it out
+        NRS_CUDA(cudaStreamSynchronize(db->ctx->stream));
+        NRS_CUDA(cudaMemcpyAsync(np, db->d_desc, (size_t)db->size * DESC * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, db->ctx->stream));
+        NRS_CUDA(cudaStreamSynchronize(db->ctx->stream));
+        cudaFree(db->d_desc);
+    }
+    db->d_desc = np;
+    db->capacity = cap;
+    return NRS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nrs_sc_make(nrs_ctx *ctx, const float *xyz, int P, double lidar_height, double max_radius,
+                double *desc_out)
+{
+    NRS_CHECK_ARG(ctx && desc_out && P >= 0 && (xyz || P == 0), "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    NRS_CUDA(cudaSetDevice(ctx->device));
+    int rc = ctx->scratch[0].reserve((size_t)std::max(P, 1) * 3 * sizeof(float) + DESC * sizeof(double));
+    if (rc) return rc;
+    double *d_desc = ctx->scratch[0].as<double>();
+    float *d_xyz = reinterpret_cast<float *>(d_desc + DESC);
+    if (P) NRS_CUDA(cudaMemcpyAsync(d_xyz, xyz, (size_t)P * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    sc_make_kernel<<<1, 256, 0, ctx->stream>>>(d_xyz, P, lidar_height, max_radius, d_desc);
+    NRS_LAUNCHED();
+    NRS_CUDA(cudaMemcpyAsync(desc_out, d_desc, DESC * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NRS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NRS_OK;
+}
+
+int nrs_sc_keys(nrs_ctx *ctx, const double *desc, double *ringkey20, double *sectorkey60)
+{
+    NRS_CHECK_ARG(ctx && desc, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    NRS_CUDA(cudaSetDevice(ctx->device));
+    int rc = ctx->scratch[0].reserve((DESC + R + S) * sizeof(double));
+    if (rc) return rc;
+    double *d = ctx->scratch[0].as<double>();
+    NRS_CUDA(cudaMemcpyAsync(d, desc, DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    sc_keys_kernel<<<1, 96, 0, ctx->stream>>>(d, d + DESC, d + DESC + R);
+    NRS_LAUNCHED();
+    if (ringkey20) NRS_CUDA(cudaMemcpyAsync(ringkey20, d + DESC, R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sectorkey60) NRS_CUDA(cudaMemcpyAsync(sectorkey60, d + DESC + R, S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NRS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NRS_OK;
+}
+
+int nrs_sc_db_create(nrs_ctx *ctx, int capacity_hint, nrs_sc_db **out)
+{
+    NRS_CHECK_ARG(ctx && out, "bad argument");
+    *out = nullptr;
+    NRS_CUDA(cudaSetDevice(ctx->device));
+    nrs_sc_db *db = new nrs_sc_db();
+    db->ctx = ctx;
+    db->max_blocks = ctx->sm_count;            // persistent: one 200 KB CTA per SM
+    cudaError_t e = cudaSuccess;
+    if ((e = cudaMalloc(&db->d_block, sizeof(BlockResult) * db->max_blocks)) != cudaSuccess ||
+        (e = cudaMalloc(&db->d_ticket, sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMalloc(&db->d_result, sizeof(nrs_sc_result))) != cudaSuccess ||
+        (e = cudaMalloc(&db->d_query, DESC * sizeof(double))) != cudaSuccess ||
+        (e = cudaMallocHost(&db->h_result, sizeof(nrs_sc_result))) != cudaSuccess ||
+        (e = cudaMallocHost(&db->h_query, DESC * sizeof(double))) != cudaSuccess ||
+        (e = cudaMemset(db->d_ticket, 0, sizeof(unsigned int))) != cudaSuccess) {
+        nrs::set_error("nrs_sc_db_create: %s", cudaGetErrorString(e));
+        nrs_sc_db_destroy(db);
+        return NRS_ECUDA;
+    }
+    int rc = db_reserve(db, std::max(capacity_hint, 1));
+    if (rc) { nrs_sc_db_destroy(db); return rc; }
+    *out = db;
+    return NRS_OK;
+}
+
+int nrs_sc_db_destroy(nrs_sc_db *db)
+{
+    if (!db) return NRS_OK;
+    cudaSetDevice(db->ctx->device);
+    cudaStreamSynchronize(db->ctx->stream);
+    cudaFree(db->d_desc); cudaFree(db->d_block); cudaFree(db->d_ticket);
+    cudaFree(db->d_result); cudaFree(db->d_query);
+    if (db->h_result) cudaFreeHost(db->h_result);
+    if (db->h_query) cudaFreeHost(db->h_query);
+    delete db;
+    return NRS_OK;
+}
+
+int nrs_sc_db_size(nrs_sc_db *db)
+{
+    if (!db) return NRS_EINVAL;
+    std::lock_guard<std::mutex> lk(db->mu);
+    return db->size;
+}
+
+int nrs_sc_db_clear(nrs_sc_db *db)
+{
+    NRS_CHECK_ARG(db, "db is NULL");
+    std::lock_guard<std::mutex> lk(db->mu);
+    db->size = 0;
+    return NRS_OK;
+}
+
+int nrs_sc_db_append(nrs_sc_db *db, const double *desc_host, int count)
+{
+    NRS_CHECK_ARG(db && desc_host && count >= 0, "bad argument");
+    std::lock_guard<std::mutex> lk(db->mu);
+    NRS_CUDA(cudaSetDevice(db->ctx->device));
+    int rc = db_reserve(db, db->size + count);
+    if (rc) return rc;
+    NRS_CUDA(cudaMemcpyAsync(db->d_desc + (size_t)db->size * DESC, desc_host,
+                             (size_t)count * DESC * sizeof(double), cudaMemcpyHostToDevice,
+                             db->ctx->stream));
+    NRS_CUDA(cudaStreamSynchronize(db->ctx->stream));
+    db->size += count;
+    return NRS_OK;
+}
+
+int nrs_sc_db_append_cloud(nrs_sc_db *db, const float *xyz, int P, double lidar_height,
+                           double max_radius, double *desc_out)
+{
+    NRS_CHECK_ARG(db && P >= 0 && (xyz || P == 0), "bad argument");
+    std::lock_guard<std::mutex> lk(db->mu);
+    nrs_ctx *ctx = db->ctx;
+    std::lock_guard<std::mutex> lk2(ctx->mu);
+    NRS_CUDA(cudaSetDevice(ctx->device));
+    int rc = db_reserve(db, db->size + 1);
+    if (rc) return rc;
+    rc = ctx->scratch[0].reserve((size_t)std::max(P, 1) * 3 * sizeof(float));
+    if (rc) return rc;
+    float *d_xyz = ctx->scratch[0].as<float>();
+    double *d_slot = db->d_desc + (size_t)db->size * DESC;
+    if (P) NRS_CUDA(cudaMemcpyAsync(d_xyz, xyz, (size_t)P * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    sc_make_kernel<<<1, 256, 0, ctx->stream>>>(d_xyz, P, lidar_height, max_radius, d_slot);
+    NRS_LAUNCHED();
+    if (desc_out) NRS_CUDA(cudaMemcpyAsync(desc_out, d_slot, DESC * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NRS_CUDA(cudaStreamSynchronize(ctx->stream));
+    db->size += 1;
+    return NRS_OK;
+}
+
+int nrs_sc_db_read(nrs_sc_db *db, int first, int count, double *desc_host)
+{
+    NRS_CHECK_ARG(db && desc_host && first >= 0 && count >= 0, "bad argument");
+    std::lock_guard<std::mutex> lk(db->mu);
+    NRS_CHECK_ARG(first + count <= db->size, "range exceeds database size");
+    NRS_CUDA(cudaSetDevice(db->ctx->device));
+    NRS_CUDA(cudaMemcpyAsync(desc_host, db->d_desc + (size_t)first * DESC,
+                             (size_t)count * DESC * sizeof(double), cudaMemcpyDeviceToHost,
+                             db->ctx->stream));
+    NRS_CUDA(cudaStreamSynchronize(db->ctx->stream));
+    return NRS_OK;
+}
+
+const double *nrs_sc_db_device_ptr(nrs_sc_db *db) { return db ? db->d_desc : nullptr; }
+
+static int sc_query_impl(nrs_sc_db *db, const double *query_host, int first, int last,
+                         const int32_t *cand, int n_cand, double *dist_out, int32_t *shift_out,
+                         nrs_sc_result *result_host)
+{
+    NRS_CHECK_ARG(db && query_host && result_host, "bad argument");
+    std::lock_guard<std::mutex> lk(db->mu);
+    nrs_ctx *ctx = db->ctx;
+    NRS_CUDA(cudaSetDevice(ctx->device));
+    int n_items;
+    if (cand) {
+        NRS_CHECK_ARG(n_cand >= 0, "n_cand < 0");
+        for (int i = 0; i < n_cand; ++i)
+            NRS_CHECK_ARG(cand[i] >= 0 && cand[i] < db->size, "candidate id out of range");
+        n_items = n_cand;
+        first = 0;
+    } else {
+        NRS_CHECK_ARG(first >= 0 && last <= db->size, "search range outside the database");
+        n_items = std::max(0, last - first);
+    }
+    std::lock_guard<std::mutex> lk2(ctx->mu);
+    const bool want_all = dist_out || shift_out;
+    size_t scratch = (size_t)std::max(n_items, 1) * (sizeof(double) + 2 * sizeof(int32_t));
+    int rc = ctx->scratch[1].reserve(scratch);
+    if (rc) return rc;
+    double *d_dist = ctx->scratch[1].as<double>();
+    int32_t *d_shift = reinterpret_cast<int32_t *>(d_dist + std::max(n_items, 1));
+    int32_t *d_cand = d_shift + std::max(n_items, 1);
+    memcpy(db->h_query, query_host, DESC * sizeof(double));
+    NRS_CUDA(cudaMemcpyAsync(db->d_query, db->h_query, DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (cand && n_items)
+        NRS_CUDA(cudaMemcpyAsync(d_cand, cand, (size_t)n_items * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_search(ctx, db->d_desc, db->d_query, cand ? d_cand : nullptr, first, n_items, 0,
+                       want_all ? d_dist : nullptr, want_all ? d_shift : nullptr, db->d_block,
+                       db->d_ticket, db->d_result, db->max_blocks);
+    if (rc) return rc;
+    NRS_CUDA(cudaMemcpyAsync(db->h_result, db->d_result, sizeof(nrs_sc_result), cudaMemcpyDeviceToHost, ctx->stream));
+    if (dist_out && n_items)
+        NRS_CUDA(cudaMemcpyAsync(dist_out, d_dist, (size_t)n_items * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (shift_out && n_items)
+        NRS_CUDA(cudaMemcpyAsync(shift_out, d_shift, (size_t)n_items * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    NRS_CUDA(cudaStreamSynchronize(ctx->stream));
+    *result_host = *db->h_result;
+    return NRS_OK;
+}
+
+int nrs_sc_query(nrs_sc_db *db, const double *query_host, int first, int last,
+                 const int32_t *candidate_idx, int n_cand, nrs_sc_result *result_host)
+{
+    return sc_query_impl(db, query_host, first, last, candidate_idx, n_cand, nullptr, nullptr, result_host);
+}
+
+int nrs_sc_query_all(nrs_sc_db *db, const double *query_host, int first, int last,
+                     double *dist_out, int32_t *shift_out, nrs_sc_result *result_host)
+{
+    nrs_sc_result tmp;
+    return sc_query_impl(db, query_host, first, last, nullptr, 0, dist_out, shift_out,
+                         result_host ? result_host : &tmp);
+}
+
+int nrs_sc_query_dev(nrs_sc_db *db, const double *query_dev, int first, int last,
+                     int32_t idx_offset, nrs_sc_result *result_dev)
+{
+    NRS_CHECK_ARG(db && query_dev && result_dev, "bad argument");
+    std::lock_guard<std::mutex> lk(db->mu);
+    NRS_CHECK_ARG(first >= 0 && last <= db->size, "search range outside the database");
+    NRS_CUDA(cudaSetDevice(db->ctx->device));
+    return launch_search(db->ctx, db->d_desc, query_dev, nullptr, first, std::max(0, last - first),
+                         idx_offset, nullptr, nullptr, db->d_block, db->d_ticket, result_dev,
+                         db->max_blocks);
+}
+
+int nrs_sc_fast_align(nrs_ctx *ctx, const double *vkey1, const double *vkey2, int32_t *shift)
+{
+    NRS_CHECK_ARG(ctx && vkey1 && vkey2 && shift, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    NRS_CUDA(cudaSetDevice(ctx->device));
+    int rc = ctx->scratch[2].reserve((2 * S + 2) * sizeof(double));
+    if (rc) return rc;
+    double *d = ctx->scratch[2].as<double>();
+    NRS_CUDA(cudaMemcpyAsync(d, vkey1, S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NRS_CUDA(cudaMemcpyAsync(d + S, vkey2, S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    sc_fast_align_kernel<<<1, 32, 0, ctx->stream>>>(d, d + S, reinterpret_cast<int32_t *>(d + 2 * S));
+    NRS_LAUNCHED();
+    int32_t h = 0;
+    NRS_CUDA(cudaMemcpyAsync(&h, d + 2 * S, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    NRS_CUDA(cudaStreamSynchronize(ctx->stream));
+    *shift = h;
+    return NRS_OK;
+}
+
+int nrs_sc_dist_direct(nrs_ctx *ctx, const double *sc1, const double *sc2, double *dist)
+{
+    NRS_CHECK_ARG(ctx && sc1 && sc2 && dist, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    NRS_CUDA(cudaSetDevice(ctx->device));
+    int rc = ctx->scratch[2].reserve((2 * DESC + 2) * sizeof(double));
+    if (rc) return rc;
+    double *d = ctx->scratch[2].as<double>();
+    NRS_CUDA(cudaMemcpyAsync(d, sc1, DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NRS_CUDA(cudaMemcpyAsync(d + DESC, sc2, DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    sc_dist_direct_kernel<<<1, 64, 0, ctx->stream>>>(d, d + DESC, d + 2 * DESC);
+    NRS_LAUNCHED();
+    double h = 0;
+    NRS_CUDA(cudaMemcpyAsync(&h, d + 2 * DESC, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NRS_CUDA(cudaStreamSynchronize(ctx->stream));
+    *dist = h;
+    return NRS_OK;
+}
+
+int nrs_sc_pair(nrs_ctx *ctx, const double *sc1, const double *sc2, double *dist, int32_t *shift)
+{
+    NRS_CHECK_ARG(ctx && sc1 && sc2 && dist && shift, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    NRS_CUDA(cudaSetDevice(ctx->device));
+    const size_t bytes = 2 * DESC * sizeof(double) + sizeof(BlockResult) + 16 + sizeof(nrs_sc_result) +
+                         sizeof(double) + sizeof(int32_t) + 64;
+    int rc = ctx->scratch[2].reserve(bytes);
+    if (rc) return rc;
+    unsigned char *base = ctx->scratch[2].as<unsigned char>();
+    double *d_q = reinterpret_cast<double *>(base);
+    double *d_k = d_q + DESC;
+    BlockResult *d_block = reinterpret_cast<BlockResult *>(d_k + DESC);
+    unsigned int *d_ticket = reinterpret_cast<unsigned int *>(d_block + 1);
+    nrs_sc_result *d_res = reinterpret_cast<nrs_sc_result *>(reinterpret_cast<unsigned char *>(d_ticket) + 16);
+    double *d_dist = reinterpret_cast<double *>(d_res + 1);
+    int32_t *d_shift = reinterpret_cast<int32_t *>(d_dist + 1);
+    NRS_CUDA(cudaMemsetAsync(d_ticket, 0, sizeof(unsigned int), ctx->stream));
+    NRS_CUDA(cudaMemcpyAsync(d_q, sc1, DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NRS_CUDA(cudaMemcpyAsync(d_k, sc2, DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_search(ctx, d_k, d_q, nullptr, 0, 1, 0, d_dist, d_shift, d_block, d_ticket, d_res, 1);
+    if (rc) return rc;
+    double h_dist; int32_t h_shift;
+    NRS_CUDA(cudaMemcpyAsync(&h_dist, d_dist, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NRS_CUDA(cudaMemcpyAsync(&h_shift, d_shift, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    NRS_CUDA(cudaStreamSynchronize(ctx->stream));
+    *dist = h_dist;
+    *shift = h_shift;
+    return NRS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,67 @@
+"""Seeded synthetic workloads.  numpy only; shared by tests and bench.py.
+
+There is no network and the reference ships no data, so every benchmark and parity input is
+generated here from a seed and described in bench.py's ``data`` field.
+"""
+import numpy as np
+
+RINGS, SECTORS, DESC = 20, 60, 1200
+
+
+def shift_desc(desc_flat, s):
+    """circshift (SC/Scancontext.cpp:39-59) on a flat column-major descriptor:
+    out.col((c + s) % 60) = in.col(c)."""
+    m = np.asarray(desc_flat).reshape(SECTORS, RINGS)      # row c of this view == column c
+    return np.roll(m, s, axis=0).reshape(-1)
+
+
+def sc_database(D, n_revisits, seed=42, binary=True, flip=0.05):
+    """D descriptors, 20x60 f64 column-major, flat (D,1200).
+
+    binary=True : occupancy Bernoulli(p_ring), p decaying 0.45 -> 0.10 with the ring index,
+                  occupied bins = 3.0 -- the {0, 3.0} descriptors this pipeline produces
+                  (ORORA publishes z = 1.0, SCManager adds LIDAR_HEIGHT = 2.0).
+    binary=False: occupied bins get a height U(0.5, 4) (exercises inexact f64 arithmetic).
+    n_revisits planted loop closures: entry j is an earlier entry i circularly shifted by a
+    random s with `flip` of its bins toggled.  Returns (db, revisits[(j, i, s)]).
+    """
+    rng = np.random.default_rng(seed)
+    p = np.linspace(0.45, 0.10, RINGS)
+    occ = rng.random((D, SECTORS, RINGS)) < p[None, None, :]
+    if binary:
+        db = np.where(occ, 3.0, 0.0)
+    else:
+        db = np.where(occ, rng.uniform(0.5, 4.0, size=occ.shape), 0.0)
+    db = db.reshape(D, DESC)
+    revisits = []
+    if n_revisits and D > 64:
+        js = rng.choice(np.arange(D // 2, D), size=min(n_revisits, D // 2), replace=False)
+        for j in sorted(js.tolist()):
+            i = int(rng.integers(0, max(1, j - 40)))
+            s = int(rng.integers(0, SECTORS))
+            d = shift_desc(db[i], s).copy()
+            tog = rng.random(DESC) < flip
+            if binary:
+                d = np.where(tog, np.where(d > 0, 0.0, 3.0), d)
+            else:
+                d = np.where(tog, np.where(d > 0, 0.0, rng.uniform(0.5, 4.0, DESC)), d)
+            db[j] = d
+            revisits.append((j, i, s))
+    return np.ascontiguousarray(db), revisits
+
+
+def feature_cloud(n_points, seed, max_range=100.0, z=1.0):
+    """A 2-D radar feature cloud as /orora/cloud_local carries it: (x, y, z = 1.0) float32
+    (ORORA/src/odometry.cpp:305-316).  Points cluster along a few walls plus clutter."""
+    rng = np.random.default_rng(seed)
+    n_wall = n_points // 2
+    segs = rng.uniform(-max_range * 0.7, max_range * 0.7, size=(12, 4))
+    which = rng.integers(0, 12, n_wall)
+    t = rng.random(n_wall)
+    wx = segs[which, 0] + t * (segs[which, 2] - segs[which, 0]) + rng.normal(0, 0.2, n_wall)
+    wy = segs[which, 1] + t * (segs[which, 3] - segs[which, 1]) + rng.normal(0, 0.2, n_wall)
+    r = max_range * np.sqrt(rng.random(n_points - n_wall))
+    a = rng.uniform(0, 2 * np.pi, n_points - n_wall)
+    x = np.concatenate([wx, r * np.cos(a)])
+    y = np.concatenate([wy, r * np.sin(a)])
+    return np.stack([x, y, np.full(n_points, z)], axis=1).astype(np.float32)

@@ -1,0 +1,185 @@
+"""ctypes bindings of oracle/_build/liboracle.so (our CPU restatement of the reference) and,
+when present, oracle/_ref/libref_kdtree.so (the reference's own vendored nanoflann).
+
+TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "liboracle.so")
+_REF = os.path.join(_HERE, "_ref", "libref_kdtree.so")
+
+RINGS, SECTORS, DESC = 20, 60, 1200
+
+
+def build(force=False):
+    """Compile the C restatement (gcc, seconds).  Also builds oracle/_ref when /root/reference
+    exists (this container); on the GPU box the prebuilt files are used as they travelled."""
+    if force or not os.path.exists(_LIB) or any(
+            os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB)
+            for f in os.listdir(_HERE) if f.endswith(".c")):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "all"])
+    if os.path.isdir("/root/reference/pgo/SC-A-LOAM/include/scancontext"):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            build()
+        _lib = C.CDLL(_LIB)
+        _declare(_lib)
+    return _lib
+
+
+def ref_kdtree():
+    """The reference's real nanoflann kd-tree, or None when oracle/_ref was not built."""
+    global _ref
+    if _ref is None and os.path.exists(_REF):
+        _ref = C.CDLL(_REF)
+        _ref.ref_kdtree_knn.restype = C.c_int
+        _ref.ref_kdtree_knn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                        C.c_void_p, C.c_void_p]
+    return _ref
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _declare(L):
+    vp, i32, f64, f32 = C.c_void_p, C.c_int, C.c_double, C.c_float
+    L.sc_xy2theta.restype = f32
+    L.sc_xy2theta.argtypes = [f32, f32]
+    L.sc_make.restype = None
+    L.sc_make.argtypes = [vp, i32, f64, f64, vp]
+    L.sc_ringkey.restype = None
+    L.sc_ringkey.argtypes = [vp, vp]
+    L.sc_sectorkey.restype = None
+    L.sc_sectorkey.argtypes = [vp, vp]
+    L.sc_ringkey_f32.restype = None
+    L.sc_ringkey_f32.argtypes = [vp, vp]
+    L.sc_fast_align.restype = i32
+    L.sc_fast_align.argtypes = [vp, vp]
+    L.sc_dist_direct.restype = f64
+    L.sc_dist_direct.argtypes = [vp, vp]
+    L.sc_distance.restype = None
+    L.sc_distance.argtypes = [vp, vp, vp, vp]
+    L.sc_search_range.restype = None
+    L.sc_search_range.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
+    L.sc_detect_from_candidates.restype = None
+    L.sc_detect_from_candidates.argtypes = [vp, vp, vp, i32, f64, vp, vp, vp, vp]
+    L.sc_knn_bruteforce.restype = None
+    L.sc_knn_bruteforce.argtypes = [vp, i32, i32, vp, i32, vp, vp]
+
+
+# ---------------------------------------------------------------------------------------------
+# ScanContext
+# ---------------------------------------------------------------------------------------------
+def sc_make(xyz, lidar_height=2.0, max_radius=80.0):
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+    desc = np.empty(DESC, dtype=np.float64)
+    lib().sc_make(_p(xyz), xyz.shape[0], lidar_height, max_radius, _p(desc))
+    return desc
+
+
+def sc_ringkey(desc):
+    desc = np.ascontiguousarray(desc, dtype=np.float64)
+    out = np.empty(RINGS, dtype=np.float64)
+    lib().sc_ringkey(_p(desc), _p(out))
+    return out
+
+
+def sc_ringkey_f32(desc):
+    desc = np.ascontiguousarray(desc, dtype=np.float64)
+    out = np.empty(RINGS, dtype=np.float32)
+    lib().sc_ringkey_f32(_p(desc), _p(out))
+    return out
+
+
+def sc_sectorkey(desc):
+    desc = np.ascontiguousarray(desc, dtype=np.float64)
+    out = np.empty(SECTORS, dtype=np.float64)
+    lib().sc_sectorkey(_p(desc), _p(out))
+    return out
+
+
+def sc_fast_align(vk1, vk2):
+    vk1 = np.ascontiguousarray(vk1, dtype=np.float64)
+    vk2 = np.ascontiguousarray(vk2, dtype=np.float64)
+    return int(lib().sc_fast_align(_p(vk1), _p(vk2)))
+
+
+def sc_dist_direct(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    return float(lib().sc_dist_direct(_p(a), _p(b)))
+
+
+def sc_distance(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    d = C.c_double()
+    s = C.c_int()
+    lib().sc_distance(_p(a), _p(b), C.byref(d), C.byref(s))
+    return d.value, s.value
+
+
+def sc_search(query, db, first=0, last=None, want_all=True, threads=None):
+    """Exhaustive distanceBtnScanContext(query, db[i]) for i in [first,last).
+    Returns (dist_all, shift_all, (best_dist, best_idx, best_shift))."""
+    query = np.ascontiguousarray(query, dtype=np.float64)
+    db = np.ascontiguousarray(db, dtype=np.float64).reshape(-1, DESC)
+    last = db.shape[0] if last is None else last
+    dist = np.full(db.shape[0], np.nan) if want_all else None
+    shift = np.zeros(db.shape[0], dtype=np.int32) if want_all else None
+    bd, bi, bs = C.c_double(), C.c_int(), C.c_int()
+    if threads is not None:
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+    lib().sc_search_range(_p(query), _p(db), first, last,
+                          _p(dist) if want_all else None, _p(shift) if want_all else None,
+                          C.byref(bd), C.byref(bi), C.byref(bs))
+    if want_all:
+        return dist[first:last], shift[first:last], (bd.value, bi.value, bs.value)
+    return None, None, (bd.value, bi.value, bs.value)
+
+
+def sc_detect_from_candidates(query, db, cand, thres):
+    query = np.ascontiguousarray(query, dtype=np.float64)
+    db = np.ascontiguousarray(db, dtype=np.float64).reshape(-1, DESC)
+    cand = np.ascontiguousarray(cand, dtype=np.int32)
+    loop, yaw, md, nn = C.c_int(), C.c_float(), C.c_double(), C.c_int()
+    lib().sc_detect_from_candidates(_p(query), _p(db), _p(cand), len(cand), thres,
+                                    C.byref(loop), C.byref(yaw), C.byref(md), C.byref(nn))
+    return loop.value, yaw.value, md.value, nn.value
+
+
+def sc_knn_bruteforce(keys, query, k):
+    keys = np.ascontiguousarray(keys, dtype=np.float32)
+    query = np.ascontiguousarray(query, dtype=np.float32)
+    idx = np.empty(k, dtype=np.int32)
+    d2 = np.empty(k, dtype=np.float32)
+    lib().sc_knn_bruteforce(_p(keys), keys.shape[0], keys.shape[1], _p(query), k, _p(idx), _p(d2))
+    return idx, d2
+
+
+def ref_knn(keys, query, k):
+    """kNN through the reference's real nanoflann tree (SC/Scancontext.cpp:356,371-373)."""
+    R = ref_kdtree()
+    if R is None:
+        return None
+    keys = np.ascontiguousarray(keys, dtype=np.float32)
+    query = np.ascontiguousarray(query, dtype=np.float32)
+    idx = np.empty(k, dtype=np.int32)
+    d2 = np.empty(k, dtype=np.float32)
+    R.ref_kdtree_knn(_p(keys), keys.shape[0], keys.shape[1], _p(query), k, _p(idx), _p(d2))
+    return idx, d2

@@ -1,0 +1,215 @@
+"""GPU parity tests of the ScanContext path: CUDA (through the C ABI) vs the CPU oracle on the
+same seeded inputs, vs the committed golden vectors, and size-independent properties at the
+full 10k-keyframe size.  Bar: shift / index exact, distance bit-exact (binary descriptors: all
+partial sums exact; general values: same summation order, no FMA), tolerance 1e-12 stated."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "sc_golden.npz")
+TOL = 1e-12
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+@pytest.fixture(scope="module")
+def sc(nrs, ctx):
+    return nrs.scancontext
+
+
+def test_pair_parity(sc, nrs, ctx, oracle, synth):
+    m = sc.SCManager(ctx)
+    for binary in (True, False):
+        db, _ = synth.sc_database(120, 20, seed=21, binary=binary)
+        rng = np.random.default_rng(1)
+        for _ in range(120):
+            i, j = rng.integers(0, 120, 2)
+            d, s = m.distanceBtnScanContext(sc.as_desc(db[i]), sc.as_desc(db[j]))
+            od, os_ = oracle.sc_distance(db[i], db[j])
+            assert s == os_
+            assert abs(d - od) <= TOL
+            assert bits([d])[0] == bits([od])[0]
+
+
+def test_operators_parity(sc, ctx, oracle, synth):
+    m = sc.SCManager(ctx)
+    db, _ = synth.sc_database(12, 0, seed=22, binary=False)
+    for i in range(0, 12, 2):
+        a, b = db[i], db[i + 1]
+        rk, sk = m.makeRingkeyFromScancontext(sc.as_desc(a)), m.makeSectorkeyFromScancontext(sc.as_desc(a))
+        assert rk.shape == (20, 1) and sk.shape == (1, 60)
+        assert np.array_equal(bits(rk), bits(oracle.sc_ringkey(a)))
+        assert np.array_equal(bits(sk), bits(oracle.sc_sectorkey(a)))
+        vb = oracle.sc_sectorkey(b)
+        assert m.fastAlignUsingVkey(sk, vb) == oracle.sc_fast_align(sk.reshape(-1), vb)
+        assert bits([m.distDirectSC(sc.as_desc(a), sc.as_desc(b))])[0] == bits([oracle.sc_dist_direct(a, b)])[0]
+    zero = np.zeros(1200)
+    assert np.isnan(m.distDirectSC(sc.as_desc(zero), sc.as_desc(db[0])))
+    assert m.distanceBtnScanContext(sc.as_desc(zero), sc.as_desc(db[0])) == (1e7, 0)
+
+
+@pytest.mark.parametrize("binary", [True, False])
+def test_query_all_1k(sc, ctx, oracle, synth, binary):
+    """BASELINE config 2: 1 query vs 1k-keyframe DB."""
+    db, _ = synth.sc_database(1000, 50, seed=42, binary=binary)
+    d = sc.SCDatabase(ctx)
+    d.append(db)
+    assert len(d) == 1000
+    q = db[-1]
+    dist, shift, best = d.query_all(q, 0, 999)
+    odist, oshift, obest = oracle.sc_search(q, db, 0, 999)
+    assert np.array_equal(shift, oshift)
+    assert np.max(np.abs(dist - odist)) <= TOL
+    assert np.array_equal(bits(dist), bits(odist))
+    assert best == obest
+    assert d.query(q, 0, 999) == obest
+    # sub-ranges, including empty and single
+    for a, b in ((0, 0), (5, 6), (100, 731), (998, 999), (0, 1000)):
+        _, _, ob = oracle.sc_search(q, db, a, b)
+        assert d.query(q, a, b) == ob
+    assert np.array_equal(bits(d.read(10, 3)), bits(db[10:13]))
+    d.close()
+
+
+def test_candidates_mode_and_golden(sc, ctx, oracle):
+    g = np.load(GOLD)
+    for tag in ("bin", "gen"):
+        db, q = g[f"{tag}_db"], g[f"{tag}_query"]
+        d = sc.SCDatabase(ctx, capacity_hint=4)      # forces growth
+        for k in range(0, 96, 7):
+            d.append(db[k:k + 7])
+        dist, shift, best = d.query_all(q, 0, 95)
+        assert np.array_equal(shift, g[f"{tag}_shift"])
+        assert np.array_equal(bits(dist), bits(g[f"{tag}_dist"]))
+        assert tuple(best) == tuple(g[f"{tag}_best"])
+        if f"{tag}_ref_knn_idx" in g:
+            cand = g[f"{tag}_ref_knn_idx"]
+            loop, yaw, md, nn = oracle.sc_detect_from_candidates(q, db, cand, 0.45)
+            gd, gi, gs = d.query(q, candidates=cand)
+            assert (gd, gi) == (md, nn)
+        # candidate order decides ties: duplicates of the same keyframe
+        gd, gi, gs = d.query(q, candidates=[40, 12, 40, 12])
+        od = [oracle.sc_distance(q, db[c]) for c in (40, 12)]
+        exp = 40 if od[0][0] <= od[1][0] else 12
+        assert gi == exp
+        d.close()
+
+
+def test_edge_cases(sc, ctx, oracle, synth):
+    db, _ = synth.sc_database(40, 0, seed=23)
+    zero = np.zeros(1200)
+    d = sc.SCDatabase(ctx)
+    d.append(np.stack([zero, zero, db[3], zero]))
+    assert d.query(db[3]) == (oracle.sc_distance(db[3], db[3])[0], 2, 0)
+    assert d.query(zero) == (1e7, 0, 0)                 # NaN distances never win
+    assert d.query(db[3], 0, 2) == (1e7, 0, 0)
+    dist, shift, _ = d.query_all(db[3])
+    assert dist[0] == 1e7 and shift[0] == 0
+    # ties: lowest index wins
+    d.clear()
+    d.append(np.stack([db[5], db[7], db[5], db[7]]))
+    assert d.query(db[7])[1] == 1 and d.query(db[5])[1] == 0
+    # sparse descriptors with many empty columns
+    sp = db[9].copy().reshape(60, 20)
+    sp[::2] = 0
+    sp = sp.reshape(-1)
+    d.clear()
+    d.append(db)
+    assert d.query(sp) == oracle.sc_search(sp, db)[2]
+    with pytest.raises(Exception):
+        d.query(db[0], 0, 41)
+    d.close()
+
+
+def test_make_scancontext_parity(sc, ctx, oracle, synth):
+    m = sc.SCManager(ctx)
+    g = np.load(GOLD)
+    assert np.array_equal(sc.flat(m.makeScancontext(g["cloud"])), g["cloud_desc"])
+    for seed in range(6):
+        cloud = synth.feature_cloud(500 + 700 * seed, seed=100 + seed, max_range=60 + 20 * seed)
+        if seed == 5:
+            cloud[:, 2] = np.random.default_rng(0).uniform(-3, 3, cloud.shape[0]).astype(np.float32)
+        assert np.array_equal(sc.flat(m.makeScancontext(cloud)), oracle.sc_make(cloud)), seed
+    axes = np.array([[1, 0, 1], [0, 1, 1], [-1, 0, 1], [0, -1, 1], [0, 0, 1], [80, 0, 1], [56.5685, 56.5685, 1],
+                     [100, 0, 1], [3, 3, -5000]], dtype=np.float32)
+    assert np.array_equal(sc.flat(m.makeScancontext(axes)), oracle.sc_make(axes))
+    assert np.array_equal(sc.flat(m.makeScancontext(np.zeros((0, 3), np.float32))), np.zeros(1200))
+
+
+def test_manager_flow_matches_reference_flow(sc, ctx, oracle, synth):
+    """makeAndSaveScancontextAndKeys + detectLoopClosureID, keyframe by keyframe, against the
+    reference flow restated with the oracle (kd-tree candidates from the reference's own
+    nanoflann when oracle/_ref is present)."""
+    knn = (lambda keys, q, k: oracle.ref_knn(keys, q, min(k, len(keys)))[0]) if oracle.ref_kdtree() \
+        else (lambda keys, q, k: oracle.sc_knn_bruteforce(keys, q, min(k, len(keys)))[0])
+    m_ex = sc.SCManager(ctx)                      # exhaustive (north_star)
+    m_cd = sc.SCManager(ctx, candidate_fn=knn)    # reference candidate set
+    m_ex.setSCdistThres(0.45)
+    m_cd.setSCdistThres(0.45)
+    rng = np.random.default_rng(5)
+    clouds = [synth.feature_cloud(900, seed=200 + i, max_range=75) for i in range(20)]
+    seq = [clouds[i % 20] if i < 20 or i % 3 else
+           (clouds[(i * 7) % 20] + rng.normal(0, 0.05, clouds[0].shape).astype(np.float32) * [1, 1, 0])
+           for i in range(75)]
+    o_descs, o_keys, counter, search_end = [], [], 0, 0
+    for i, cl in enumerate(seq):
+        cl = cl.astype(np.float32)
+        m_ex.makeAndSaveScancontextAndKeys(cl)
+        m_cd.makeAndSaveScancontextAndKeys(cl)
+        o_descs.append(oracle.sc_make(cl))
+        o_keys.append(oracle.sc_ringkey_f32(o_descs[-1]))
+        assert np.array_equal(sc.flat(m_ex.polarcontexts_[-1]), o_descs[-1])
+        assert np.array_equal(m_ex.polarcontext_invkeys_mat_[-1], o_keys[-1])
+        r_ex, r_cd = m_ex.detectLoopClosureID(), m_cd.detectLoopClosureID()
+        if len(o_descs) < 31:
+            assert r_ex == (-1, 0.0) and r_cd == (-1, 0.0)
+            continue
+        if counter % 30 == 0:
+            search_end = len(o_descs) - 30
+        counter += 1
+        db = np.stack(o_descs)
+        cand = knn(np.stack(o_keys[:search_end]), o_keys[-1], 3)
+        loop, yaw, md, nn = oracle.sc_detect_from_candidates(o_descs[-1], db, cand, 0.45)
+        assert r_cd == (loop, yaw)
+        _, _, (bd, bi, bs) = oracle.sc_search(o_descs[-1], db, 0, search_end)
+        assert r_ex[0] == (bi if bd < 0.45 else -1)
+        assert m_ex.last_min_dist == bd and m_ex.last_nn_idx == bi
+        assert bd <= md          # exhaustive is never worse than the 3 candidates
+
+
+def test_full_size_properties_10k(sc, ctx, oracle, synth):
+    """BASELINE config 4 size (10k keyframes) through size-independent properties: planted
+    revisits are recovered with the planted shift, self-queries return distance ~0 at the
+    lowest duplicate index, a split search merges to the same answer, and a sample of
+    per-keyframe results is bit-identical to the oracle."""
+    db, rev = synth.sc_database(10000, 500, seed=42)
+    d = sc.SCDatabase(ctx)
+    d.append(db)
+    hits = 0
+    for j, i, s in rev[::25]:
+        gd, gi, gs = d.query(db[j], 0, j - 30)
+        od, os_ = oracle.sc_distance(db[j], db[i])
+        assert gd <= od
+        if gi == i:
+            assert gs == os_ == s
+            hits += 1
+    assert hits >= 15
+    for i in (0, 4999, 9999):
+        gd, gi, gs = d.query(db[i])
+        assert gi <= i and gd < 1e-12 and (gi != i or gs == 0)
+    q = db[rev[3][0]]
+    whole = d.query(q, 0, 9000)
+    parts = [d.query(q, a, b) for a, b in ((0, 1234), (1234, 5000), (5000, 9000))]
+    assert sc.best_of(parts) == whole
+    dist, shift, best = d.query_all(q, 0, 10000)
+    assert best == d.query(q, 0, 10000)
+    idx = np.random.default_rng(0).choice(10000, 300, replace=False)
+    for k in idx:
+        od, os_ = oracle.sc_distance(q, db[k])
+        assert shift[k] == os_ and bits([dist[k]])[0] == bits([od])[0]
+    assert np.argmin(np.where(np.isnan(dist), 1e9, dist)) == best[1]
+    d.close()
