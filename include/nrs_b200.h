@@ -130,6 +130,58 @@ int nrs_sc_query_all(nrs_sc_db *db, const double *query_host, int first, int las
 int nrs_sc_query_dev(nrs_sc_db *db, const double *query_dev, int first, int last,
                      int32_t idx_offset, nrs_sc_result *result_dev);
 
+/* ---- ORORA solver (ORORA/include/ORORA.hpp, ORORA/include/solver/nonminimal_solver.hpp) ---- */
+
+/* NonMinimalSolver::Params (nonminimal_solver.hpp:104-162) + the ORORA ctor arguments
+ * (ORORA.hpp:15-28); defaults = ORORA/config/orora_params.yaml as loaded by odometry.cpp:79-135. */
+typedef struct nrs_solver_params {
+    double  noise_bound;                  /* 0.75 */
+    double  cbar2;                        /* noise_bound_coeff, 1.0 */
+    int32_t rotation_max_iterations;      /* 100 */
+    double  rotation_gnc_factor;          /* 1.4 */
+    double  rotation_cost_threshold;      /* 1e-6 */
+    double  noise_bound_radial;           /* 0.1 m */
+    double  noise_bound_tangential;       /* radians (9 deg) */
+    int32_t use_doppler_compensation;     /* 1 */
+    double  doppler_beta;                 /* 0.049, odometry.cpp:109 */
+    int32_t check_stop_motion;            /* 1 */
+    int32_t num_feat_thr_for_stop_motion; /* 700 */
+    int64_t clique_node_limit;            /* 0 = default (2e6 branch-and-bound nodes) */
+} nrs_solver_params;
+
+typedef struct nrs_solver_info {
+    int32_t valid;              /* solution_.valid (nonminimal_solver.hpp:718,820) */
+    int32_t stop_motion;        /* 1: skipped by the stop-motion gate (ORORA.hpp:74-79) -> Identity */
+    int32_t n_edges;            /* scale-consistent TIMs = edges of the inlier graph */
+    int32_t M;                  /* getNumMaxCliqueInliers() */
+    int32_t gnc_iters;
+    int32_t gnc_early_return;   /* GNC-TLS returned at initialisation (:348-352) */
+    int32_t n_rot_inliers;      /* getNumRotaionInliers() */
+    int32_t n_final_inliers;    /* getFinalInliersIndices().size() */
+    int32_t clique_exact;       /* 0 when the node limit stopped the exact search early */
+    int32_t pad_;
+    int64_t clique_nodes;
+    double  R[4];               /* 2x2 rotation, column-major */
+    double  t[2];
+    double  cost;
+} nrs_solver_info;
+
+void nrs_solver_default_params(nrs_solver_params *p);
+
+/* ORORA::calcTransform (ORORA.hpp:37-93) minus the velocity bookkeeping the caller keeps:
+ * Doppler compensation of both point sets with |vel_x| (:56-61,139-151), stop-motion gate
+ * (:74-79), then NonMinimalSolver::computeTransformation with source = curr, target = prev
+ * (:83-85; nonminimal_solver.hpp:678-825): TIMs + scale consistency -> inlier graph ->
+ * exact maximum clique -> chain TIMs -> GNC-TLS rotation -> anisotropic COTE translation.
+ *   prev_2xN, curr_2xN : matched points, column-major 2xN doubles (host)
+ *   vel_x              : curr_vel_se3_(0) of the previous call = T(0,3)/delta_t
+ *   T_out              : 4x4 column-major; Identity when the solver fails or the gate fires
+ *   clique_out, final_inliers_out : nullable, room for N int32 (sorted correspondence ids)
+ * N is limited to 1024 correspondences (NRS_ECAPACITY above). */
+int nrs_orora_solve(nrs_ctx *ctx, const double *prev_2xN, const double *curr_2xN, int N,
+                    const nrs_solver_params *p, double vel_x, double T_out[16],
+                    int32_t *clique_out, int32_t *final_inliers_out, nrs_solver_info *info_out);
+
 #ifdef __cplusplus
 }
 #endif

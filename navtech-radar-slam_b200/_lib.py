@@ -23,6 +23,24 @@ class ScResult(C.Structure):
     _fields_ = [("dist", C.c_double), ("idx", C.c_int32), ("shift", C.c_int32)]
 
 
+class SolverParams(C.Structure):
+    """nrs_solver_params (include/nrs_b200.h)."""
+    _fields_ = [("noise_bound", C.c_double), ("cbar2", C.c_double), ("rotation_max_iterations", C.c_int32),
+                ("rotation_gnc_factor", C.c_double), ("rotation_cost_threshold", C.c_double),
+                ("noise_bound_radial", C.c_double), ("noise_bound_tangential", C.c_double),
+                ("use_doppler_compensation", C.c_int32), ("doppler_beta", C.c_double),
+                ("check_stop_motion", C.c_int32), ("num_feat_thr_for_stop_motion", C.c_int32),
+                ("clique_node_limit", C.c_int64)]
+
+
+class SolverInfo(C.Structure):
+    """nrs_solver_info (include/nrs_b200.h)."""
+    _fields_ = [("valid", C.c_int32), ("stop_motion", C.c_int32), ("n_edges", C.c_int32), ("M", C.c_int32),
+                ("gnc_iters", C.c_int32), ("gnc_early_return", C.c_int32), ("n_rot_inliers", C.c_int32),
+                ("n_final_inliers", C.c_int32), ("clique_exact", C.c_int32), ("pad_", C.c_int32),
+                ("clique_nodes", C.c_int64), ("R", C.c_double * 4), ("t", C.c_double * 2), ("cost", C.c_double)]
+
+
 def library_path():
     return _SO
 
@@ -77,6 +95,9 @@ def _declare(L):
     L.nrs_sc_query.argtypes = [vp, vp, i32, i32, vp, i32, vp]
     L.nrs_sc_query_all.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     L.nrs_sc_query_dev.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.nrs_solver_default_params.restype = None
+    L.nrs_solver_default_params.argtypes = [vp]
+    L.nrs_orora_solve.argtypes = [vp, vp, vp, i32, vp, f64, vp, vp, vp, vp]
     for name in declared_symbols():
         fn = getattr(L, name, None)
         if fn is not None and fn.restype is C.c_int and name not in ("nrs_version",):
@@ -105,7 +126,13 @@ class Context:
 
     def __init__(self, device=0):
         self._h = C.c_void_p()
+        self._children = []          # weakrefs of objects whose native handles hang off this ctx
         check(lib().nrs_ctx_create(device, C.byref(self._h)))
+
+    def adopt(self, obj):
+        """Register a dependent (database, frame, ...) so close() tears it down first."""
+        import weakref
+        self._children.append(weakref.ref(obj))
 
     @property
     def handle(self):
@@ -128,6 +155,11 @@ class Context:
 
     def close(self):
         if self._h:
+            for ref in self._children:
+                obj = ref()
+                if obj is not None:
+                    obj.close()
+            self._children = []
             lib().nrs_ctx_destroy(self._h)
             self._h = C.c_void_p()
 

@@ -1,0 +1,752 @@
+// solver_kernels.cu -- ORORA non-minimal solver on sm_100a.
+//
+// Replaces NonMinimalSolver::computeTransformation and the part of ORORA::calcTransform around
+// it (reference: outlier-robust-radar-odometry/include/solver/nonminimal_solver.hpp:171-264,
+// 266-440, 480-661, 678-825, 844-859; include/ORORA.hpp:37-93,139-151; src/graph.cc:12-130).
+//
+//   K7  orora_adjacency_kernel   all N(N-1)/2 translation-invariant measurements (TIMs) and the
+//                                scale-consistency test of solveForScale, written directly as an
+//                                N x 32-word bit adjacency matrix (replaces computeTIMs' 3 x N^2/2
+//                                f64 temporaries and Graph::addEdge's O(N^3) linear finds).
+//   K8  orora_order_kernel /     degree ordering, permuted adjacency, then an exact maximum-clique
+//       orora_permute_kernel /   search (greedy bound + bitset branch and bound with greedy
+//       orora_clique_kernel      colouring) by ONE warp: lane l owns word l of every vertex set, the
+//                                adjacency matrix sits in shared memory.  PMC (un-vendored in the
+//                                reference) is replaced by this exact solver.
+//   K9  orora_tail_kernel        one 1024-thread CTA: clique sort, chain TIMs + initial weights,
+//                                GNC-TLS rotation (warp-shuffle reduced weighted 2x2 correlation,
+//                                closed-form 2-D Kabsch), anisotropic COTE translation (bitonic
+//                                sort of the 2M interval endpoints + block scan + argmin).
+//
+// All of it is latency-bound on <= 1024 correspondences (22 KB of input): it sits far below the
+// HBM roofline by construction and DESIGN.md reports it that way.  Built with --fmad=false so the
+// scale-consistency comparisons round exactly like the CPU restatement (oracle/solver_ref.c).
+#include <string.h>
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAXN = 1024;      // one 32-bit adjacency word per lane
+constexpr int WORDS = 32;
+
+struct SolverInfoDev {
+    int    valid, n_edges, M, gnc_iters, gnc_early_return, n_rot_inliers, n_final_inliers, clique_exact;
+    double R[4], t[2], cost;
+    long long nodes;
+};
+
+// ---- K7 ---------------------------------------------------------------------------------------
+// ORORA.hpp:139-151 Doppler compensation fused in front: p.x += beta*v*x*x/rsq; p.y += beta*v*x'*y/rsq
+__global__ void orora_prep_kernel(const double *__restrict__ prev, const double *__restrict__ curr,
+                                  int N, double beta_v, int use_doppler, double *__restrict__ src,
+                                  double *__restrict__ tgt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    // src = curr frame (setInputSource), tgt = prev frame (setInputTarget): ORORA.hpp:83-84
+    double cx = curr[2 * i], cy = curr[2 * i + 1], px = prev[2 * i], py = prev[2 * i + 1];
+    if (use_doppler) {
+        double rsq = cx * cx + cy * cy;
+        cx += beta_v * cx * cx / rsq;
+        cy += beta_v * cx * cy / rsq;
+        rsq = px * px + py * py;
+        px += beta_v * px * px / rsq;
+        py += beta_v * px * py / rsq;
+    }
+    src[2 * i] = cx; src[2 * i + 1] = cy;
+    tgt[2 * i] = px; tgt[2 * i + 1] = py;
+}
+
+__global__ void __launch_bounds__(256)
+orora_adjacency_kernel(const double *__restrict__ src, const double *__restrict__ tgt, int N,
+                       double beta, uint32_t *__restrict__ adj)
+{
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gid / WORDS, w = gid % WORDS;
+    if (i >= N) return;
+    uint32_t bits = 0;
+    const double six = src[2 * i], siy = src[2 * i + 1], tix = tgt[2 * i], tiy = tgt[2 * i + 1];
+    for (int b = 0; b < 32; ++b) {
+        const int j = w * 32 + b;
+        if (j >= N || j == i) continue;
+        // nonminimal_solver.hpp:185-222 TIM (sign is irrelevant for the norms), :233-264 test
+        const double sx = src[2 * j] - six, sy = src[2 * j + 1] - siy;
+        const double tx = tgt[2 * j] - tix, ty = tgt[2 * j + 1] - tiy;
+        const double v1 = sqrt(sx * sx + sy * sy + 0.0);
+        const double v2 = sqrt(tx * tx + ty * ty + 0.0);
+        const bool in_f = fabs(v2 / v1 - 1.0) <= beta * (1.0 / v1);
+        const bool in_r = fabs(v1 / v2 - 1.0) <= beta * (1.0 / v2);
+        if (in_f && in_r) bits |= 1u << b;
+    }
+    adj[i * WORDS + w] = bits;
+}
+
+// ---- K8 ---------------------------------------------------------------------------------------
+// search order: non-increasing degree, ties by index (oracle/solver_ref.c orora_max_clique)
+__global__ void __launch_bounds__(1024)
+orora_order_kernel(const uint32_t *__restrict__ adj, int N, int *__restrict__ perm,
+                   int *__restrict__ inv, int *__restrict__ n_edges)
+{
+    __shared__ int deg[MAXN];
+    __shared__ int esum;
+    const int i = threadIdx.x;
+    if (i == 0) esum = 0;
+    int d = 0;
+    if (i < N)
+        for (int w = 0; w < WORDS; ++w) d += __popc(adj[i * WORDS + w]);
+    if (i < N) deg[i] = d;
+    __syncthreads();
+    if (i < N) {
+        int rank = 0;
+        for (int j = 0; j < N; ++j) rank += (deg[j] > d) || (deg[j] == d && j < i);
+        perm[rank] = i;
+        inv[i] = rank;
+        atomicAdd(&esum, d);
+    }
+    __syncthreads();
+    if (i == 0) *n_edges = esum / 2;
+}
+
+__global__ void __launch_bounds__(256)
+orora_permute_kernel(const uint32_t *__restrict__ adj, const int *__restrict__ perm, int N,
+                     uint32_t *__restrict__ adjp)
+{
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ip = gid / WORDS, w = gid % WORDS;
+    if (ip >= N) return;
+    const int i = perm[ip];
+    uint32_t bits = 0;
+    for (int b = 0; b < 32; ++b) {
+        const int jp = w * 32 + b;
+        if (jp >= N) break;
+        const int j = perm[jp];
+        bits |= ((adj[i * WORDS + (j >> 5)] >> (j & 31)) & 1u) << b;
+    }
+    adjp[ip * WORDS + w] = bits;
+}
+
+// greedy sequential colouring of the vertex set P (one word per lane); vertices are emitted
+// class by class in increasing index: order[n], color[n] (BBMC / oracle mc_expand).
+__device__ int warp_color_sort(uint32_t Pw, uint16_t *__restrict__ ord, uint16_t *__restrict__ col,
+                               const uint32_t *sadj, int lane)
+{
+    uint32_t Q = Pw;
+    int n = 0, k = 0;
+    while (__ballot_sync(0xffffffffu, Q != 0)) {
+        ++k;
+        uint32_t Qc = Q;
+        unsigned int b;
+        while ((b = __ballot_sync(0xffffffffu, Qc != 0)) != 0) {
+            const int f = __ffs(b) - 1;
+            const uint32_t wd = __shfl_sync(0xffffffffu, Qc, f);
+            const int bit = __ffs(wd) - 1;
+            const int v = f * 32 + bit;
+            if (lane == f) { Qc &= ~(1u << bit); Q &= ~(1u << bit); }
+            Qc &= ~sadj[v * WORDS + lane];
+            if (lane == 0) { ord[n] = (uint16_t)v; col[n] = (uint16_t)k; }
+            ++n;
+        }
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(32)
+orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restrict__ stackP,
+                    uint16_t *__restrict__ ordS, uint16_t *__restrict__ colS, int *__restrict__ cur,
+                    int *__restrict__ best, int *__restrict__ idxS, SolverInfoDev *__restrict__ info,
+                    long long node_limit)
+{
+    extern __shared__ uint32_t sadj[];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < N * WORDS; i += 32) sadj[i] = adjp[i];
+    __syncwarp();
+    // all-vertices mask, word `lane`
+    uint32_t full = 0;
+    {
+        const int lo = lane * 32;
+        if (N >= lo + 32) full = 0xffffffffu;
+        else if (N > lo) full = (1u << (N - lo)) - 1u;
+    }
+    // ---- greedy lower bound -----------------------------------------------------------------
+    int best_n = 0;
+    {
+        uint32_t P = full;
+        unsigned int b;
+        while ((b = __ballot_sync(0xffffffffu, P != 0)) != 0) {
+            const int f = __ffs(b) - 1;
+            const uint32_t wd = __shfl_sync(0xffffffffu, P, f);
+            const int v = f * 32 + __ffs(wd) - 1;
+            if (lane == 0) best[best_n] = v;
+            ++best_n;
+            P &= sadj[v * WORDS + lane];
+        }
+    }
+    // ---- branch and bound, explicit stack ---------------------------------------------------
+    long long nodes = 0;
+    int exact = 1;
+    int depth = 0, cur_n = 0;
+    uint32_t P = full;                          // vertex set of the current depth (word `lane`)
+    stackP[lane] = P;
+    int n = warp_color_sort(P, ordS, colS, sadj, lane);
+    int idx = n - 1;
+    ++nodes;
+    __syncwarp();
+    for (;;) {
+        bool pop = false;
+        if (idx < 0) pop = true;
+        else {
+            int c = 0, v = 0;
+            if (lane == 0) { c = colS[(size_t)depth * N + idx]; v = ordS[(size_t)depth * N + idx]; }
+            c = __shfl_sync(0xffffffffu, c, 0);
+            v = __shfl_sync(0xffffffffu, v, 0);
+            if (cur_n + c <= best_n) pop = true;
+            else {
+                if (lane == 0) cur[cur_n] = v;
+                ++cur_n;
+                const uint32_t Pn = P & sadj[v * WORDS + lane];
+                if (__ballot_sync(0xffffffffu, Pn != 0) == 0) {
+                    if (cur_n > best_n) {
+                        __syncwarp();
+                        for (int i = lane; i < cur_n; i += 32) best[i] = cur[i];
+                        best_n = cur_n;
+                        __syncwarp();
+                    }
+                    --cur_n;
+                    if (lane == (v >> 5)) P &= ~(1u << (v & 31));
+                    --idx;
+                } else {
+                    if (nodes >= node_limit) { exact = 0; break; }
+                    // push
+                    stackP[(size_t)depth * WORDS + lane] = P;
+                    if (lane == 0) idxS[depth] = idx;
+                    ++depth;
+                    P = Pn;
+                    n = warp_color_sort(P, ordS + (size_t)depth * N, colS + (size_t)depth * N, sadj, lane);
+                    idx = n - 1;
+                    ++nodes;
+                    __syncwarp();
+                }
+            }
+        }
+        if (pop) {
+            if (depth == 0) break;
+            --depth;
+            P = stackP[(size_t)depth * WORDS + lane];
+            int pi = 0;
+            if (lane == 0) pi = idxS[depth];
+            idx = __shfl_sync(0xffffffffu, pi, 0);
+            int v = 0;
+            if (lane == 0) v = ordS[(size_t)depth * N + idx];
+            v = __shfl_sync(0xffffffffu, v, 0);
+            --cur_n;
+            if (lane == (v >> 5)) P &= ~(1u << (v & 31));
+            --idx;
+        }
+    }
+    if (lane == 0) {
+        info->M = best_n;
+        info->nodes = nodes;
+        info->clique_exact = exact;
+    }
+}
+
+// ---- K9 ---------------------------------------------------------------------------------------
+constexpr int TT = 1024;   // tail kernel threads
+
+struct TailSmem {
+    double a[MAXN];          // general per-element scratch (ps.x / X)
+    double b[MAXN];          //                              (ps.y / alpha)
+    double c[MAXN];          //                              (pd.x)
+    double d[MAXN];          //                              (pd.y)
+    double w[MAXN];          // GNC weights
+    double key[2 * MAXN];    // COTE endpoints
+    int    tag[2 * MAXN];
+    double s1[2 * MAXN], s2[2 * MAXN], s3[2 * MAXN], s4[2 * MAXN], s5[2 * MAXN];
+    int    si[2 * MAXN];
+    double red[32 * 6];
+    int    redi[32];
+    int    clique[MAXN];
+    unsigned char inl[MAXN];
+    unsigned char rot_inl[MAXN];
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// block-wide sum of up to 4 values per thread; result broadcast to all threads
+__device__ void block_sum4(double &x0, double &x1, double &x2, double &x3, double *red)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    x0 = warp_sum(x0); x1 = warp_sum(x1); x2 = warp_sum(x2); x3 = warp_sum(x3);
+    __syncthreads();
+    if (lane == 0) { red[warp * 4] = x0; red[warp * 4 + 1] = x1; red[warp * 4 + 2] = x2; red[warp * 4 + 3] = x3; }
+    __syncthreads();
+    if (warp == 0) {
+        double y0 = red[lane * 4], y1 = red[lane * 4 + 1], y2 = red[lane * 4 + 2], y3 = red[lane * 4 + 3];
+        y0 = warp_sum(y0); y1 = warp_sum(y1); y2 = warp_sum(y2); y3 = warp_sum(y3);
+        if (lane == 0) { red[128] = y0; red[129] = y1; red[130] = y2; red[131] = y3; }
+    }
+    __syncthreads();
+    x0 = red[128]; x1 = red[129]; x2 = red[130]; x3 = red[131];
+}
+__device__ double block_max(double x, double *red)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    x = warp_max(x);
+    __syncthreads();
+    if (lane == 0) red[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        double y = warp_max(red[lane]);
+        if (lane == 0) red[128] = y;
+    }
+    __syncthreads();
+    return red[128];
+}
+
+// svdRot2d (nonminimal_solver.hpp:844-859): R = V U^T with the determinant fix == the rotation
+// maximising trace(R H), H = X diag(w) Y^T; in 2-D that is (cos, sin) ~ (H00 + H11, H01 - H10).
+__device__ void rot_from_H(double h00, double h10, double h01, double h11, double R[4])
+{
+    const double cc = h00 + h11, ss = h01 - h10;
+    const double nrm = sqrt(cc * cc + ss * ss);
+    double c = 1.0, s = 0.0;
+    if (nrm > 0) { c = cc / nrm; s = ss / nrm; }
+    R[0] = c; R[1] = s; R[2] = -s; R[3] = c;      // column-major [[c,-s],[s,c]]
+}
+
+// COTE on one axis (nonminimal_solver.hpp:532-661): X, alpha in sm.a / sm.b, M elements.
+__device__ double cote_axis(TailSmem &sm, int M, unsigned char *inl_and)
+{
+    const int t = threadIdx.x;
+    const int n2 = 2 * M;
+    int P2 = 1;
+    while (P2 < n2) P2 <<= 1;
+    // endpoints (:548-552); pad with +inf so they sort to the end
+    for (int e = t; e < P2; e += TT) {
+        if (e < n2) {
+            const int i = e >> 1;
+            const bool lo = (e & 1) == 0;
+            sm.key[e] = lo ? sm.a[i] - sm.b[i] : sm.a[i] + sm.b[i];
+            sm.tag[e] = lo ? (i + 1) : -(i + 1);
+            sm.si[e] = e;                 // original order = stable tie-break
+        } else {
+            sm.key[e] = INFINITY; sm.tag[e] = 0; sm.si[e] = e;
+        }
+    }
+    __syncthreads();
+    // bitonic sort ascending on (key, original order) (:555 std::sort, restated stable)
+    for (int k = 2; k <= P2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int e = t; e < P2; e += TT) {
+                const int p = e ^ j;
+                if (p > e) {
+                    const bool up = (e & k) == 0;
+                    const double ke = sm.key[e], kp = sm.key[p];
+                    const int oe = sm.si[e], op = sm.si[p];
+                    const bool gt = (ke > kp) || (ke == kp && oe > op);
+                    if (gt == up) {
+                        sm.key[e] = kp; sm.key[p] = ke;
+                        sm.si[e] = op; sm.si[p] = oe;
+                        const int te = sm.tag[e]; sm.tag[e] = sm.tag[p]; sm.tag[p] = te;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    // per-endpoint increments (:604-612), then an inclusive block scan
+    double tot = 0.0;
+    {
+        double x0 = (t < M) ? sm.b[t] : 0.0, x1 = 0, x2 = 0, x3 = 0;
+        block_sum4(x0, x1, x2, x3, sm.red);
+        tot = x0;                         // ranges.sum() (:566)
+    }
+    for (int e = t; e < P2; e += TT) {
+        double i1 = 0, i2 = 0, i3 = 0, i4 = 0, i5 = 0;
+        int ic = 0;
+        if (e < n2) {
+            const int tg = sm.tag[e];
+            const int idx = abs(tg) - 1;
+            const double eps = tg > 0 ? 1.0 : -1.0;
+            const double r = sm.b[idx], x = sm.a[idx];
+            const double wgt = 1.0 / (r * r);
+            ic = tg > 0 ? 1 : -1;
+            i1 = eps * wgt;               // dot_weights_consensus
+            i2 = eps * wgt * x;           // dot_X_weights
+            i3 = eps * r;                 // subtracted from ranges_inverse_sum
+            i4 = eps * x;                 // sum_xi
+            i5 = eps * x * x;             // sum_xi_square
+        }
+        sm.s1[e] = i1; sm.s2[e] = i2; sm.s3[e] = i3; sm.s4[e] = i4; sm.s5[e] = i5; sm.si[e] = ic;
+    }
+    __syncthreads();
+    // Hillis-Steele inclusive scan over P2 <= 2048 elements (2 per thread)
+    for (int off = 1; off < P2; off <<= 1) {
+        double v1[2], v2[2], v3[2], v4[2], v5[2];
+        int vi[2];
+        int cnt = 0;
+        for (int e = t; e < P2; e += TT, ++cnt) {
+            const bool has = e >= off;
+            v1[cnt] = has ? sm.s1[e - off] : 0.0; v2[cnt] = has ? sm.s2[e - off] : 0.0;
+            v3[cnt] = has ? sm.s3[e - off] : 0.0; v4[cnt] = has ? sm.s4[e - off] : 0.0;
+            v5[cnt] = has ? sm.s5[e - off] : 0.0; vi[cnt] = has ? sm.si[e - off] : 0;
+        }
+        __syncthreads();
+        cnt = 0;
+        for (int e = t; e < P2; e += TT, ++cnt) {
+            sm.s1[e] += v1[cnt]; sm.s2[e] += v2[cnt]; sm.s3[e] += v3[cnt];
+            sm.s4[e] += v4[cnt]; sm.s5[e] += v5[cnt]; sm.si[e] += vi[cnt];
+        }
+        __syncthreads();
+    }
+    // x_hat, cost (:618-622) and the first minimum (:626)
+    double bc = INFINITY, bh = 0.0;
+    int bi = 0x7fffffff;
+    for (int e = t; e < n2; e += TT) {
+        const double x_hat = sm.s2[e] / sm.s1[e];
+        const double residual = sm.si[e] * x_hat * x_hat + sm.s5[e] - 2 * sm.s4[e] * x_hat;
+        const double cost = residual + (tot - sm.s3[e]);
+        if (cost < bc || (e == 0 && !(cost >= cost))) { bc = cost; bh = x_hat; bi = e; }
+    }
+    // block argmin on (cost, index)
+    {
+        const int lane = t & 31, warp = t >> 5;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double oc = __shfl_xor_sync(0xffffffffu, bc, o);
+            const double oh = __shfl_xor_sync(0xffffffffu, bh, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oc < bc || (oc == bc && oi < bi)) { bc = oc; bh = oh; bi = oi; }
+        }
+        __syncthreads();
+        if (lane == 0) { sm.red[warp] = bc; sm.red[32 + warp] = bh; sm.redi[warp] = bi; }
+        __syncthreads();
+        if (warp == 0) {
+            bc = sm.red[lane]; bh = sm.red[32 + lane]; bi = sm.redi[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double oc = __shfl_xor_sync(0xffffffffu, bc, o);
+                const double oh = __shfl_xor_sync(0xffffffffu, bh, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (oc < bc || (oc == bc && oi < bi)) { bc = oc; bh = oh; bi = oi; }
+            }
+            if (lane == 0) sm.red[160] = bh;
+        }
+        __syncthreads();
+    }
+    const double est = sm.red[160];
+    if (t < M) inl_and[t] = inl_and[t] && (fabs(sm.a[t] - est) <= sm.b[t]);   // :658
+    __syncthreads();
+    return est;
+}
+
+__global__ void __launch_bounds__(TT)
+orora_tail_kernel(const double *__restrict__ src, const double *__restrict__ tgt, int N,
+                  const int *__restrict__ perm, const int *__restrict__ best,
+                  double noise_bound, int max_iter, double gnc_factor, double cost_thr,
+                  double nb_radial, double nb_tangential, SolverInfoDev *__restrict__ info,
+                  double *__restrict__ T_out, int *__restrict__ clique_out,
+                  int *__restrict__ final_out)
+{
+    extern __shared__ __align__(16) unsigned char tail_raw[];
+    TailSmem &sm = *reinterpret_cast<TailSmem *>(tail_raw);
+    const int t = threadIdx.x;
+    const int M = info->M;
+    if (t < 16) T_out[t] = (t % 5 == 0) ? 1.0 : 0.0;           // :681 identity on failure
+    if (M <= 1) {                                             // :715-720
+        if (t == 0) { info->valid = 0; info->R[0] = 1; info->R[1] = 0; info->R[2] = 0; info->R[3] = 1; info->t[0] = info->t[1] = 0; }
+        return;
+    }
+    // ---- clique in original ids, sorted ascending (:712) ------------------------------------------
+    int my = (t < M) ? perm[best[t]] : 0x7fffffff;
+    sm.clique[t] = my;
+    __syncthreads();
+    int pos = 0;
+    if (t < M) for (int j = 0; j < M; ++j) pos += sm.clique[j] < my;
+    __syncthreads();
+    if (t < M) { sm.clique[pos] = my; clique_out[pos] = my; }
+    __syncthreads();
+    // ---- chain TIMs + initial weights (:735-760) --------------------------------------------------
+    double w0 = 0.0;
+    if (t < M) {
+        const int root = sm.clique[t], leaf = sm.clique[(t + 1 == M) ? 0 : t + 1];
+        sm.a[t] = src[2 * leaf] - src[2 * root];  sm.b[t] = src[2 * leaf + 1] - src[2 * root + 1];
+        sm.c[t] = tgt[2 * leaf] - tgt[2 * root];  sm.d[t] = tgt[2 * leaf + 1] - tgt[2 * root + 1];
+        const double rl = tgt[2 * leaf] * tgt[2 * leaf] + tgt[2 * leaf + 1] * tgt[2 * leaf + 1] + 1.0;
+        const double rr = tgt[2 * root] * tgt[2 * root] + tgt[2 * root + 1] * tgt[2 * root + 1] + 1.0;
+        w0 = 1.0 / sqrt(rl + rr);
+    }
+    const double max_w = block_max(t < M ? w0 : 0.0, sm.red);
+    w0 = w0 / max_w;
+    // ---- GNC-TLS (:292-440) ------------------------------------------------------------------------
+    const double sx = t < M ? sm.a[t] : 0.0, sy = t < M ? sm.b[t] : 0.0;
+    const double dx = t < M ? sm.c[t] : 0.0, dy = t < M ? sm.d[t] : 0.0;
+    double R[4];
+    double nb2 = noise_bound * noise_bound;
+    if (nb2 < 1e-16) nb2 = 1e-2;
+    double wgt = 1.0, res;
+    int iters = 0, early = 0;
+    double cost = INFINITY, prev_cost = INFINITY;
+    {
+        double h00 = sx * w0 * dx, h10 = sy * w0 * dx, h01 = sx * w0 * dy, h11 = sy * w0 * dy;
+        block_sum4(h00, h10, h01, h11, sm.red);
+        rot_from_H(h00, h10, h01, h11, R);                    // :333
+    }
+    {
+        const double ex = dx - (R[0] * sx + R[2] * sy), ey = dy - (R[1] * sx + R[3] * sy);
+        res = ex * ex + ey * ey;
+    }
+    const double max_res = block_max(t < M ? res : -INFINITY, sm.red);
+    if (max_res < nb2) nb2 = 0.01;                            // :342-344
+    double mu = 1 / (2 * max_res / nb2 - 1);
+    if (mu <= 0) {
+        early = 1;                                            // :348-352
+    } else {
+        {
+            const double th1 = (mu + 1) / mu * nb2, th2 = mu / (mu + 1) * nb2;
+            if (res >= th1) wgt = 0;
+            else if (res <= th2) wgt = 1;
+            else wgt = sqrt(nb2 * mu * (mu + 1) / res + 0.00000000000001) - mu;   // :368
+            mu = mu * gnc_factor;
+        }
+        for (int it = 0; it < max_iter; ++it) {               // :376-433
+            double h00 = (t < M) ? sx * wgt * dx : 0.0, h10 = (t < M) ? sy * wgt * dx : 0.0;
+            double h01 = (t < M) ? sx * wgt * dy : 0.0, h11 = (t < M) ? sy * wgt * dy : 0.0;
+            block_sum4(h00, h10, h01, h11, sm.red);
+            rot_from_H(h00, h10, h01, h11, R);
+            const double ex = dx - (R[0] * sx + R[2] * sy), ey = dy - (R[1] * sx + R[3] * sy);
+            res = ex * ex + ey * ey;
+            double c0 = (t < M) ? wgt * res : 0.0, c1 = 0, c2 = 0, c3 = 0;
+            block_sum4(c0, c1, c2, c3, sm.red);
+            cost = c0;
+            const double th1 = (mu + 1) / mu * nb2, th2 = mu / (mu + 1) * nb2;
+            if (res >= th1) wgt = 0;
+            else if (res <= th2) wgt = 1;
+            else wgt = sqrt(nb2 * mu * (mu + 1) / res) - mu;  // :406
+            const double cost_diff = fabs(cost - prev_cost);
+            mu = mu * gnc_factor;
+            prev_cost = cost;
+            iters = it + 1;
+            if (cost_diff < cost_thr) break;
+        }
+    }
+    if (t < M) sm.rot_inl[t] = early ? 0 : (wgt >= 0.4);      // :435-439
+    __syncthreads();
+    double nrot = 0.0;
+    if (t < M) nrot = (sm.rot_inl[t == 0 ? M - 1 : t - 1] && sm.rot_inl[t]) ? 1.0 : 0.0;   // :776-789
+    {
+        double z1 = 0, z2 = 0, z3 = 0;
+        block_sum4(nrot, z1, z2, z3, sm.red);
+    }
+    // ---- translation (:480-529): rotate the clique's source points, anisotropic bounds, COTE ------
+    double ax = 0, ay = 0, X0 = 0, X1 = 0;
+    if (t < M) {
+        const int cidx = sm.clique[t];
+        const double x = src[2 * cidx], y = src[2 * cidx + 1];
+        const double rx = R[0] * x + R[2] * y, ry = R[1] * x + R[3] * y;
+        const double px = tgt[2 * cidx], py = tgt[2 * cidx + 1];
+        const double var_r = nb_radial * nb_radial, var_t = nb_tangential * nb_tangential;
+        const double as = atan2(ry, rx), ad = atan2(py, px);
+        const double c_s = cos(as), s_s = sin(as), c_d = cos(ad), s_d = sin(ad);
+        const double r2s = rx * rx + ry * ry + 1.0, r2d = px * px + py * py + 1.0;   // (x,y,1): :513-514
+        ax = sqrt((c_s * c_s * var_r + s_s * s_s * r2s * var_t) + (c_d * c_d * var_r + s_d * s_d * r2d * var_t));
+        ay = sqrt((s_s * s_s * var_r + c_s * c_s * r2s * var_t) + (s_d * s_d * var_r + c_d * c_d * r2d * var_t));
+        X0 = px - rx;
+        X1 = py - ry;
+        sm.inl[t] = 1;
+    }
+    __syncthreads();
+    if (t < M) { sm.a[t] = X0; sm.b[t] = ax; }
+    __syncthreads();
+    const double tx = cote_axis(sm, M, sm.inl);
+    if (t < M) { sm.a[t] = X1; sm.b[t] = ay; }
+    __syncthreads();
+    const double ty = cote_axis(sm, M, sm.inl);
+    // ---- final inliers (:807-818), compose (:820-824) -------------------------------------------
+    if (t == 0) {
+        int nf = 0;
+        for (int i = 0; i < M; ++i) if (sm.inl[i]) final_out[nf++] = sm.clique[i];
+        info->n_final_inliers = nf;
+        info->valid = 1;
+        info->gnc_iters = iters;
+        info->gnc_early_return = early;
+        info->n_rot_inliers = (int)nrot;
+        info->cost = cost;
+        info->R[0] = R[0]; info->R[1] = R[1]; info->R[2] = R[2]; info->R[3] = R[3];
+        info->t[0] = tx; info->t[1] = ty;
+        T_out[0] = R[0]; T_out[1] = R[1]; T_out[4] = R[2]; T_out[5] = R[3];
+        T_out[12] = tx; T_out[13] = ty; T_out[14] = 0.0;
+    }
+}
+
+}  // namespace
+
+// =================================================================================================
+// host side
+// =================================================================================================
+namespace {
+
+struct SolverBufs {
+    double *d_prev, *d_curr, *d_src, *d_tgt, *d_T;
+    uint32_t *d_adj, *d_adjp, *d_stackP;
+    uint16_t *d_ord, *d_col;
+    int *d_perm, *d_inv, *d_cur, *d_best, *d_idx, *d_clique, *d_final, *d_edges;
+    SolverInfoDev *d_info;
+};
+
+size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+int carve(nrs_ctx *ctx, int N, SolverBufs &b)
+{
+    const size_t n = std::max(N, 1);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+    const size_t o_prev = take(2 * n * 8), o_curr = take(2 * n * 8), o_src = take(2 * n * 8), o_tgt = take(2 * n * 8);
+    const size_t o_T = take(16 * 8), o_adj = take(n * WORDS * 4), o_adjp = take(n * WORDS * 4);
+    const size_t o_stack = take((n + 2) * WORDS * 4), o_ord = take((n + 2) * n * 2), o_col = take((n + 2) * n * 2);
+    const size_t o_perm = take(n * 4), o_inv = take(n * 4), o_cur = take(n * 4), o_best = take(n * 4), o_idx = take((n + 2) * 4);
+    const size_t o_clique = take(n * 4), o_final = take(n * 4), o_edges = take(4), o_info = take(sizeof(SolverInfoDev));
+    int rc = ctx->scratch[3].reserve(off);
+    if (rc) return rc;
+    unsigned char *p = ctx->scratch[3].as<unsigned char>();
+    b.d_prev = (double *)(p + o_prev); b.d_curr = (double *)(p + o_curr);
+    b.d_src = (double *)(p + o_src); b.d_tgt = (double *)(p + o_tgt); b.d_T = (double *)(p + o_T);
+    b.d_adj = (uint32_t *)(p + o_adj); b.d_adjp = (uint32_t *)(p + o_adjp); b.d_stackP = (uint32_t *)(p + o_stack);
+    b.d_ord = (uint16_t *)(p + o_ord); b.d_col = (uint16_t *)(p + o_col);
+    b.d_perm = (int *)(p + o_perm); b.d_inv = (int *)(p + o_inv); b.d_cur = (int *)(p + o_cur);
+    b.d_best = (int *)(p + o_best); b.d_idx = (int *)(p + o_idx); b.d_clique = (int *)(p + o_clique);
+    b.d_final = (int *)(p + o_final); b.d_edges = (int *)(p + o_edges); b.d_info = (SolverInfoDev *)(p + o_info);
+    return NRS_OK;
+}
+
+int configure_solver_kernels()
+{
+    static int done = 0;
+    if (!done) {
+        NRS_CUDA(cudaFuncSetAttribute(orora_clique_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      MAXN * WORDS * 4));
+        NRS_CUDA(cudaFuncSetAttribute(orora_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(TailSmem)));
+        done = 1;
+    }
+    return NRS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nrs_orora_solve(nrs_ctx *ctx, const double *prev_2xN, const double *curr_2xN, int N,
+                    const nrs_solver_params *p, double vel_x, double T_out[16], int32_t *clique_out,
+                    int32_t *final_inliers_out, nrs_solver_info *info_out)
+{
+    NRS_CHECK_ARG(ctx && p && T_out && info_out && N >= 0 && (N == 0 || (prev_2xN && curr_2xN)), "bad argument");
+    if (N > MAXN) {
+        nrs::set_error("nrs_orora_solve: N = %d exceeds the %d correspondences one warp-wide bitset holds "
+                       "(the reference skips estimation above num_feat_thr_for_stop_motion = 700)", N, MAXN);
+        return NRS_ECAPACITY;
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    NRS_CUDA(cudaSetDevice(ctx->device));
+    memset(info_out, 0, sizeof(*info_out));
+    for (int i = 0; i < 16; ++i) T_out[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    info_out->R[0] = info_out->R[3] = 1.0;
+    info_out->clique_exact = 1;
+    // stop-motion gate (ORORA.hpp:74-79) and the degenerate sizes are host decisions
+    if ((p->check_stop_motion && N > p->num_feat_thr_for_stop_motion) || N < 2) {
+        info_out->stop_motion = (p->check_stop_motion && N > p->num_feat_thr_for_stop_motion) ? 1 : 0;
+        return NRS_OK;
+    }
+    int rc = configure_solver_kernels();
+    if (rc) return rc;
+    SolverBufs b;
+    rc = carve(ctx, N, b);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    NRS_CUDA(cudaMemcpyAsync(b.d_prev, prev_2xN, 2 * (size_t)N * 8, cudaMemcpyHostToDevice, st));
+    NRS_CUDA(cudaMemcpyAsync(b.d_curr, curr_2xN, 2 * (size_t)N * 8, cudaMemcpyHostToDevice, st));
+    NRS_CUDA(cudaMemsetAsync(b.d_info, 0, sizeof(SolverInfoDev), st));
+    const double beta_v = p->doppler_beta * fabs(vel_x);
+    orora_prep_kernel<<<(N + 255) / 256, 256, 0, st>>>(b.d_prev, b.d_curr, N, beta_v, p->use_doppler_compensation,
+                                                      b.d_src, b.d_tgt);
+    NRS_LAUNCHED();
+    const double beta = 2 * p->noise_bound * sqrt(p->cbar2);
+    const int nthreads = N * WORDS;
+    orora_adjacency_kernel<<<(nthreads + 255) / 256, 256, 0, st>>>(b.d_src, b.d_tgt, N, beta, b.d_adj);
+    NRS_LAUNCHED();
+    orora_order_kernel<<<1, 1024, 0, st>>>(b.d_adj, N, b.d_perm, b.d_inv, b.d_edges);
+    NRS_LAUNCHED();
+    orora_permute_kernel<<<(nthreads + 255) / 256, 256, 0, st>>>(b.d_adj, b.d_perm, N, b.d_adjp);
+    NRS_LAUNCHED();
+    const long long node_limit = p->clique_node_limit > 0 ? p->clique_node_limit : 2000000;
+    orora_clique_kernel<<<1, 32, (size_t)N * WORDS * 4, st>>>(b.d_adjp, N, b.d_stackP, b.d_ord, b.d_col, b.d_cur,
+                                                             b.d_best, b.d_idx, b.d_info, node_limit);
+    NRS_LAUNCHED();
+    orora_tail_kernel<<<1, TT, sizeof(TailSmem), st>>>(b.d_src, b.d_tgt, N, b.d_perm, b.d_best, p->noise_bound,
+                                                       p->rotation_max_iterations, p->rotation_gnc_factor,
+                                                       p->rotation_cost_threshold, p->noise_bound_radial,
+                                                       p->noise_bound_tangential, b.d_info, b.d_T, b.d_clique,
+                                                       b.d_final);
+    NRS_LAUNCHED();
+    int rcp = ctx->pin[0].reserve(sizeof(SolverInfoDev) + 16 * 8 + 2 * (size_t)N * 4 + 64);
+    if (rcp) return rcp;
+    unsigned char *h = ctx->pin[0].as<unsigned char>();
+    SolverInfoDev *h_info = (SolverInfoDev *)h;
+    double *h_T = (double *)(h + align_up(sizeof(SolverInfoDev)));
+    int *h_clique = (int *)(h_T + 16);
+    int *h_final = h_clique + N;
+    int h_edges = 0;
+    NRS_CUDA(cudaMemcpyAsync(h_info, b.d_info, sizeof(SolverInfoDev), cudaMemcpyDeviceToHost, st));
+    NRS_CUDA(cudaMemcpyAsync(h_T, b.d_T, 16 * 8, cudaMemcpyDeviceToHost, st));
+    NRS_CUDA(cudaMemcpyAsync(&h_edges, b.d_edges, 4, cudaMemcpyDeviceToHost, st));
+    if (clique_out) NRS_CUDA(cudaMemcpyAsync(h_clique, b.d_clique, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+    if (final_inliers_out) NRS_CUDA(cudaMemcpyAsync(h_final, b.d_final, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+    NRS_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < 16; ++i) T_out[i] = h_T[i];
+    info_out->valid = h_info->valid;
+    info_out->n_edges = h_edges;
+    info_out->M = h_info->M;
+    info_out->gnc_iters = h_info->gnc_iters;
+    info_out->gnc_early_return = h_info->gnc_early_return;
+    info_out->n_rot_inliers = h_info->n_rot_inliers;
+    info_out->n_final_inliers = h_info->n_final_inliers;
+    info_out->clique_exact = h_info->clique_exact;
+    info_out->clique_nodes = h_info->nodes;
+    for (int i = 0; i < 4; ++i) info_out->R[i] = h_info->R[i];
+    info_out->t[0] = h_info->t[0]; info_out->t[1] = h_info->t[1];
+    info_out->cost = h_info->cost;
+    if (clique_out) memcpy(clique_out, h_clique, (size_t)h_info->M * 4);
+    if (final_inliers_out) memcpy(final_inliers_out, h_final, (size_t)h_info->n_final_inliers * 4);
+    return NRS_OK;
+}
+
+void nrs_solver_default_params(nrs_solver_params *p)
+{
+    if (!p) return;
+    p->noise_bound = 0.75;                         // ORORA/config/orora_params.yaml:10
+    p->cbar2 = 1.0;                                // noise_bound_coeff :31
+    p->rotation_max_iterations = 100;              // :36
+    p->rotation_gnc_factor = 1.4;                  // :39
+    p->rotation_cost_threshold = 1e-6;             // :42
+    p->noise_bound_radial = 0.1;                   // :12
+    p->noise_bound_tangential = 9.0 * 3.14159265358979323846 / 180.0;   // :14, DEG2RAD at odometry.cpp:128
+    p->use_doppler_compensation = 1;               // :2
+    p->doppler_beta = 0.049;                       // odometry.cpp:109
+    p->check_stop_motion = 1;                      // :25
+    p->num_feat_thr_for_stop_motion = 700;         // :26
+    p->clique_node_limit = 0;
+}
+
+}  // extern "C"

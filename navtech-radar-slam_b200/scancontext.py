@@ -63,6 +63,7 @@ class SCDatabase:
         self.ctx = ctx
         self._h = C.c_void_p()
         check(lib().nrs_sc_db_create(ctx.handle, capacity_hint, C.byref(self._h)))
+        ctx.adopt(self)
 
     def __len__(self):
         return check(lib().nrs_sc_db_size(self._h))

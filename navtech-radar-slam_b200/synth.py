@@ -65,3 +65,31 @@ def feature_cloud(n_points, seed, max_range=100.0, z=1.0):
     x = np.concatenate([wx, r * np.cos(a)])
     y = np.concatenate([wy, r * np.sin(a)])
     return np.stack([x, y, np.full(n_points, z)], axis=1).astype(np.float32)
+
+
+def se2(theta, tx, ty):
+    c, s = np.cos(theta), np.sin(theta)
+    T = np.eye(4)
+    T[0, 0], T[0, 1], T[1, 0], T[1, 1], T[0, 3], T[1, 3] = c, -s, s, c, tx, ty
+    return T
+
+
+def correspondences(N, inlier_ratio, seed, theta=np.deg2rad(1.0), tx=2.5, ty=0.1, noise=0.05,
+                    max_range=100.0):
+    """Matched point pairs as RadarLoader::matchFeatures hands them to ORORA::calcTransform:
+    prev (2xN) and curr (2xN) with prev ~= R * curr + t for inliers (so the solver, called
+    with src = curr and tgt = prev, should recover (theta, tx, ty)); outliers are random.
+    Returns (prev, curr, inlier_mask, T_true)."""
+    rng = np.random.default_rng(seed)
+    r = rng.uniform(6.0, max_range, N)
+    a = rng.uniform(0, 2 * np.pi, N)
+    curr = np.stack([r * np.cos(a), r * np.sin(a)])
+    c, s = np.cos(theta), np.sin(theta)
+    R = np.array([[c, -s], [s, c]])
+    prev = R @ curr + np.array([[tx], [ty]]) + rng.normal(0, noise, (2, N))
+    inl = rng.random(N) < inlier_ratio
+    n_out = int((~inl).sum())
+    ro = rng.uniform(6.0, max_range, n_out)
+    ao = rng.uniform(0, 2 * np.pi, n_out)
+    prev[:, ~inl] = np.stack([ro * np.cos(ao), ro * np.sin(ao)])
+    return np.ascontiguousarray(prev), np.ascontiguousarray(curr), inl, se2(theta, tx, ty)

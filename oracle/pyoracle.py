@@ -183,3 +183,127 @@ def ref_knn(keys, query, k):
     d2 = np.empty(k, dtype=np.float32)
     R.ref_kdtree_knn(_p(keys), keys.shape[0], keys.shape[1], _p(query), k, _p(idx), _p(d2))
     return idx, d2
+
+
+# ---------------------------------------------------------------------------------------------
+# ORORA solver (oracle/solver_ref.c)
+# ---------------------------------------------------------------------------------------------
+class OroraParams(C.Structure):
+    _fields_ = [("noise_bound", C.c_double), ("cbar2", C.c_double), ("max_iter", C.c_int),
+                ("gnc_factor", C.c_double), ("cost_thr", C.c_double), ("nb_radial", C.c_double),
+                ("nb_tangential", C.c_double)]
+
+
+class OroraInfo(C.Structure):
+    _fields_ = [("valid", C.c_int), ("n_edges", C.c_int), ("M", C.c_int), ("gnc_iters", C.c_int),
+                ("gnc_early_return", C.c_int), ("R", C.c_double * 4), ("t", C.c_double * 2),
+                ("cost", C.c_double), ("n_rot_inliers", C.c_int), ("n_final_inliers", C.c_int)]
+
+
+def default_params():
+    """ORORA/config/orora_params.yaml + odometry.cpp:79-135 effective values."""
+    return OroraParams(0.75, 1.0, 100, 1.4, 1e-6, 0.1, np.deg2rad(9.0))
+
+
+def _cols(a):
+    """2xN matrix (numpy (2,N) or (N,2)-as-columns) -> flat column-major doubles."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 2 and a.shape[0] == 2:
+        return np.ascontiguousarray(a.T).reshape(-1)
+    return np.ascontiguousarray(a).reshape(-1)
+
+
+def orora_doppler(p2d, vel_x, beta=0.049):
+    p = _cols(p2d)
+    out = np.empty_like(p)
+    lib().orora_doppler.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p]
+    lib().orora_doppler.restype = None
+    lib().orora_doppler(_p(p), p.size // 2, vel_x, beta, _p(out))
+    return out.reshape(-1, 2).T
+
+
+def orora_adjacency(src, tgt, noise_bound=0.75, cbar2=1.0):
+    s, t = _cols(src), _cols(tgt)
+    N = s.size // 2
+    W = (N + 63) // 64
+    adj = np.zeros((N, W), dtype=np.uint64)
+    L = lib()
+    L.orora_build_adjacency.restype = C.c_int
+    L.orora_build_adjacency.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_int]
+    e = L.orora_build_adjacency(_p(s), _p(t), N, noise_bound, cbar2, _p(adj), W)
+    return adj, e
+
+
+def orora_max_clique(adj):
+    adj = np.ascontiguousarray(adj, dtype=np.uint64)
+    N, W = adj.shape
+    out = np.zeros(max(N, 1), dtype=np.int32)
+    nodes = C.c_longlong()
+    L = lib()
+    L.orora_max_clique.restype = C.c_int
+    L.orora_max_clique.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    n = L.orora_max_clique(_p(adj), N, W, _p(out), C.byref(nodes))
+    return out[:n].copy(), nodes.value
+
+
+def orora_svd_rot2d(X, Y, Wt):
+    x, y = _cols(X), _cols(Y)
+    w = np.ascontiguousarray(Wt, dtype=np.float64)
+    R = np.zeros(4)
+    L = lib()
+    L.orora_svd_rot2d.restype = None
+    L.orora_svd_rot2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.orora_svd_rot2d(_p(x), _p(y), _p(w), w.size, _p(R))
+    return R.reshape(2, 2).T     # column-major -> numpy
+
+
+def orora_cote_axis(X, ranges):
+    x = np.ascontiguousarray(X, dtype=np.float64)
+    r = np.ascontiguousarray(ranges, dtype=np.float64)
+    est = C.c_double()
+    inl = np.zeros(x.size, dtype=np.uint8)
+    L = lib()
+    L.orora_cote_axis.restype = None
+    L.orora_cote_axis.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.orora_cote_axis(_p(x), _p(r), x.size, C.byref(est), _p(inl))
+    return est.value, inl.astype(bool)
+
+
+def orora_solve(src, tgt, params=None):
+    """NonMinimalSolver::computeTransformation: src = curr matches, tgt = prev matches (2xN).
+    Returns dict(T (4,4), clique, final_inliers, info)."""
+    params = params or default_params()
+    s, t = _cols(src), _cols(tgt)
+    N = s.size // 2
+    T = np.zeros(16)
+    clique = np.zeros(max(N, 1), dtype=np.int32)
+    fin = np.zeros(max(N, 1), dtype=np.int32)
+    info = OroraInfo()
+    L = lib()
+    L.orora_solve.restype = C.c_int
+    L.orora_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orora_solve(_p(s), _p(t), N, C.byref(params), _p(T), _p(clique), _p(fin), C.byref(info))
+    return {"T": T.reshape(4, 4).T.copy(), "clique": clique[:info.M].copy(),
+            "final_inliers": fin[:info.n_final_inliers].copy(), "info": info, "valid": bool(info.valid)}
+
+
+def orora_calc_transform(prev, curr, vel_x, params=None, delta_t=0.25, beta=0.049, use_doppler=True,
+                         check_stop_motion=True, stop_thr=700):
+    """ORORA::calcTransform.  Returns (result dict, new vel_x)."""
+    params = params or default_params()
+    pv, cv = _cols(prev), _cols(curr)
+    N = pv.size // 2
+    T = np.zeros(16)
+    clique = np.zeros(max(N, 1), dtype=np.int32)
+    fin = np.zeros(max(N, 1), dtype=np.int32)
+    info = OroraInfo()
+    v = C.c_double(vel_x)
+    L = lib()
+    L.orora_calc_transform.restype = C.c_int
+    L.orora_calc_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double,
+                                       C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]
+    L.orora_calc_transform(_p(pv), _p(cv), N, C.byref(params), delta_t, beta, int(use_doppler),
+                           int(check_stop_motion), stop_thr, C.byref(v), _p(T), _p(clique), _p(fin), C.byref(info))
+    return ({"T": T.reshape(4, 4).T.copy(), "clique": clique[:info.M].copy(),
+             "final_inliers": fin[:info.n_final_inliers].copy(), "info": info, "valid": bool(info.valid)}, v.value)

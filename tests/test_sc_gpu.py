@@ -42,8 +42,8 @@ def test_operators_parity(sc, ctx, oracle, synth):
         a, b = db[i], db[i + 1]
         rk, sk = m.makeRingkeyFromScancontext(sc.as_desc(a)), m.makeSectorkeyFromScancontext(sc.as_desc(a))
         assert rk.shape == (20, 1) and sk.shape == (1, 60)
-        assert np.array_equal(bits(rk), bits(oracle.sc_ringkey(a)))
-        assert np.array_equal(bits(sk), bits(oracle.sc_sectorkey(a)))
+        assert np.array_equal(bits(rk.reshape(-1)), bits(oracle.sc_ringkey(a)))
+        assert np.array_equal(bits(sk.reshape(-1)), bits(oracle.sc_sectorkey(a)))
         vb = oracle.sc_sectorkey(b)
         assert m.fastAlignUsingVkey(sk, vb) == oracle.sc_fast_align(sk.reshape(-1), vb)
         assert bits([m.distDirectSC(sc.as_desc(a), sc.as_desc(b))])[0] == bits([oracle.sc_dist_direct(a, b)])[0]
