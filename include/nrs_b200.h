@@ -182,6 +182,78 @@ int nrs_orora_solve(nrs_ctx *ctx, const double *prev_2xN, const double *curr_2xN
                     const nrs_solver_params *p, double vel_x, double T_out[16],
                     int32_t *clique_out, int32_t *final_inliers_out, nrs_solver_info *info_out);
 
+/* ---- ORORA front-end (ORORA/include/radar_loader.hpp, src/features.cpp, src/radar_utils.cpp) ---- */
+
+typedef struct nrs_frame nrs_frame;   /* device-resident RadarFeature (radar_loader.hpp:16-33) */
+
+/* RadarLoader's dataset constants (radar_loader.hpp:48-62) and extractor knobs (:283-297). */
+typedef struct nrs_extract_params {
+    int32_t navtech_version;        /* 0 = CIR204 (MulRan, 3360 bins), 1 = CTS350 (Oxford, 3768 bins) */
+    int32_t range_bins;
+    float   radar_resolution;       /* m / bin: 0.05952 (mulran), 0.0432 (oxford) */
+    float   cart_resolution;        /* 0.2592 m / px */
+    int32_t cart_pixel_width;       /* 964 */
+    int32_t min_range;              /* 58 bins */
+    int32_t max_points;             /* 10000 */
+    int32_t patch_size;             /* 21 */
+    int32_t use_voxelization;       /* 1 */
+    int32_t interpolate_crossover;  /* 1 */
+    double  voxel_size;             /* 0.6 m */
+    float   nndr;                   /* 0.8 */
+    int32_t pad_;
+} nrs_extract_params;
+
+/* counts and scalars of one extraction, for callers and stage-parity tests */
+typedef struct nrs_frame_info {
+    int32_t n_candidates;   /* pixels with h > mean_h (features.cpp:217-223) */
+    int32_t j_consumed;     /* candidates consumed by the marking loop (:231-249) */
+    int32_t l_regions;      /* regions counted, <= max_points */
+    int32_t K_polar;        /* cen2019 keypoints = feat_in_polar_.cols() */
+    int32_t K_voxel;        /* after voxelisation */
+    int32_t K;              /* after the BEV border filter = kp_.size() = desc_.rows */
+    float   maxg, mean, mean_h, cart_max;
+    int64_t t_criteria;
+} nrs_frame_info;
+
+/* dataset = "mulran" | "oxford" (anything else -> NRS_EINVAL, the reference throws
+ * std::invalid_argument, radar_loader.hpp:62) */
+int nrs_extract_default_params(const char *dataset, nrs_extract_params *p);
+
+/* cen2019features (features.hpp:36, features.cpp:197-299) as a stand-alone operator.
+ * fft = R x C float32 row-major (host).  targets_3xKcap receives K columns (azimuth, range, 1),
+ * column-major doubles; *K is always set; NRS_ECAPACITY if K > Kcap. */
+int nrs_cen2019(nrs_ctx *ctx, const float *fft_RxC, int R, int C, int max_points, int min_range,
+                double *targets_3xKcap, int Kcap, int *K);
+
+/* RadarLoader::extractFeature (radar_loader.hpp:74-141) on the decoded 8-bit rows of one
+ * "oxford-form" polar PNG (what cv::imread hands load_radar, radar_utils.cpp:104-129):
+ * row i = [int64 stamp | uint16 encoder | valid | R bins of power ...], row_pitch bytes apart.
+ * load_radar -> cen2019features -> polar_to_cartesian_radar_img -> polar_to_cartesian_points ->
+ * voxelize -> convert_to_bev -> ORB compute.  t_criteria = the stamp in the file name. */
+int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw_rows, int R, int row_pitch,
+                      const nrs_extract_params *p, int64_t t_criteria, nrs_frame **out);
+int nrs_frame_destroy(nrs_frame *f);
+int nrs_frame_info_get(const nrs_frame *f, nrs_frame_info *info);
+/* copy products to host; any pointer may be NULL.  Sizes: polar 3 x K_polar doubles (col-major),
+ * feat_in_cart 3 x K doubles (row 2 = 0 with voxelisation, 1 without), kp K x 2 float (u, v),
+ * t K int64, t_norm K doubles, desc K x 32 bytes, img W x W bytes. */
+int nrs_frame_get(nrs_frame *f, double *polar_3xK0, double *feat_in_cart_3xK, float *kp_Kx2,
+                  int64_t *t_K, double *t_norm_K, uint8_t *desc_Kx32, uint8_t *img_WxW);
+/* stage outputs for parity tests: fft (R x C float), R mask (R x C bytes), pre-voxel Cartesian
+ * points (2 x K_polar doubles); any pointer may be NULL.  Valid until the next extraction on
+ * the same context. */
+int nrs_frame_get_stages(nrs_frame *f, float *fft_RxC, uint8_t *marked_RxC, double *cart_pre_2xK0,
+                         float *cart_f32_WxW);
+
+/* RadarLoader::matchFeatures (radar_loader.hpp:143-205): brute-force Hamming kNN(2) of
+ * prev (query) against curr (train), ratio test d0 < nndr * d1, ties -> lowest train index.
+ * Outputs (host, capacity cap): query_idx/train_idx of the good matches in query order and the
+ * gathered 2 x N matched points (prev_matched.feat_in_cart_, curr_matched.feat_in_cart_);
+ * stamps prev_t/curr_t (nullable).  NRS_ECAPACITY if N > cap (N is still reported). */
+int nrs_match(nrs_ctx *ctx, const nrs_frame *prev, const nrs_frame *curr, float nndr, int cap,
+              int32_t *query_idx, int32_t *train_idx, double *prev_2xN, double *curr_2xN,
+              int64_t *prev_t, int64_t *curr_t, int *N);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,22 @@ class SolverInfo(C.Structure):
                 ("clique_nodes", C.c_int64), ("R", C.c_double * 4), ("t", C.c_double * 2), ("cost", C.c_double)]
 
 
+class ExtractParams(C.Structure):
+    """nrs_extract_params (include/nrs_b200.h)."""
+    _fields_ = [("navtech_version", C.c_int32), ("range_bins", C.c_int32), ("radar_resolution", C.c_float),
+                ("cart_resolution", C.c_float), ("cart_pixel_width", C.c_int32), ("min_range", C.c_int32),
+                ("max_points", C.c_int32), ("patch_size", C.c_int32), ("use_voxelization", C.c_int32),
+                ("interpolate_crossover", C.c_int32), ("voxel_size", C.c_double), ("nndr", C.c_float),
+                ("pad_", C.c_int32)]
+
+
+class FrameInfo(C.Structure):
+    """nrs_frame_info (include/nrs_b200.h)."""
+    _fields_ = [("n_candidates", C.c_int32), ("j_consumed", C.c_int32), ("l_regions", C.c_int32),
+                ("K_polar", C.c_int32), ("K_voxel", C.c_int32), ("K", C.c_int32), ("maxg", C.c_float),
+                ("mean", C.c_float), ("mean_h", C.c_float), ("cart_max", C.c_float), ("t_criteria", C.c_int64)]
+
+
 def library_path():
     return _SO
 
@@ -98,6 +114,14 @@ def _declare(L):
     L.nrs_solver_default_params.restype = None
     L.nrs_solver_default_params.argtypes = [vp]
     L.nrs_orora_solve.argtypes = [vp, vp, vp, i32, vp, f64, vp, vp, vp, vp]
+    L.nrs_extract_default_params.argtypes = [C.c_char_p, vp]
+    L.nrs_cen2019.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, vp]
+    L.nrs_frame_extract.argtypes = [vp, vp, i32, i32, vp, C.c_int64, C.POINTER(vp)]
+    L.nrs_frame_destroy.argtypes = [vp]
+    L.nrs_frame_info_get.argtypes = [vp, vp]
+    L.nrs_frame_get.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.nrs_frame_get_stages.argtypes = [vp, vp, vp, vp, vp]
+    L.nrs_match.argtypes = [vp, vp, vp, C.c_float, i32, vp, vp, vp, vp, vp, vp, vp]
     for name in declared_symbols():
         fn = getattr(L, name, None)
         if fn is not None and fn.restype is C.c_int and name not in ("nrs_version",):

@@ -1,0 +1,86 @@
+// frontend.cuh -- shared state of the ORORA front-end kernels (cen2019, polar->Cartesian, ORB,
+// matcher).  One FrontendState hangs off a context per dataset parameter set; one nrs_frame holds
+// the device-resident products of RadarLoader::extractFeature for one scan.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace nrs {
+
+constexpr int FE_MAX_AZ = 1024;          // azimuth rows supported (Navtech: 400)
+constexpr int FE_KP_CAP = 16384;         // >= max_points (10000): one keypoint per marked region at most
+constexpr int FE_PATTERN = 512;          // rBRIEF sample points (256 pairs)
+
+struct FrameCounts {
+    int   n_cand;        // pixels with h > mean_h
+    int   j_star;        // last candidate rank consumed by the marking loop
+    int   l_regions;     // regions counted (<= max_points)
+    int   K0;            // cen2019 keypoints (polar)
+    int   Kv;            // after voxelisation
+    int   K;             // after the BEV border filter (== descriptor rows)
+    float maxg;
+    float mean;
+    float mean_h;
+    float cart_max;
+    int   overflow;      // a capacity was exceeded (reported as NRS_ECAPACITY)
+    int   pad;
+};
+
+struct FrontendState {
+    nrs_extract_params p;
+    // static maps of polar_to_cartesian_radar_img (radar_utils.cpp:257-291), host libm, uploaded once
+    float *d_theta = nullptr;            // W*W, atan2f(y, x) wrapped to [0, 2pi)
+    int   *d_sx = nullptr;               // W*W, cvRound(range * 32)
+    // rBRIEF sample offsets for angle = -1 deg (cv::ORB with supplied keypoints), 512 x (dx, dy)
+    signed char *d_pattern = nullptr;
+    // big per-frame scratch (reused by every frame of this context)
+    unsigned char *d_raw = nullptr;      // R * pitch
+    float *d_fft = nullptr;              // R * C
+    float *d_h = nullptr;                // R * C
+    float *d_keys[2] = {nullptr, nullptr};       // sort keys (double buffer)
+    unsigned int *d_vals[2] = {nullptr, nullptr};// sort values
+    unsigned int *d_claim = nullptr;     // R * C
+    unsigned int *d_incr = nullptr;      // R * C (flags then inclusive scan)
+    double *d_partial = nullptr;         // block partial sums
+    float *d_cart = nullptr;             // W * W float image
+    float *d_rowbuf = nullptr;           // W * W blur row pass
+    unsigned char *d_blur = nullptr;     // W * W blurred u8
+    void *d_cub = nullptr;               // CUB temp storage
+    size_t cub_bytes = 0;
+    // per-frame small tables
+    double *d_az = nullptr;              // azimuths (R)
+    double *d_azsort = nullptr;          // sorted distinct azimuth values
+    int    *d_azidx = nullptr;           // their (lowest) original index
+    double *d_cossin = nullptr;          // 2 * R
+    long long *d_times = nullptr;        // R
+    FrameCounts *d_counts = nullptr;
+    FrameCounts *h_counts = nullptr;     // pinned
+    // voxel scratch
+    unsigned int *d_vkey[2] = {nullptr, nullptr};
+    unsigned int *d_vval[2] = {nullptr, nullptr};
+    float *d_pts32 = nullptr;            // 2 * KP_CAP float x,y
+    int   *d_rowcount = nullptr;         // per-row keypoint counts / offsets
+    int    R = 0, C = 0, pitch = 0;
+};
+
+}  // namespace nrs
+
+struct nrs_frame {
+    nrs_ctx *ctx = nullptr;
+    unsigned char *d_block = nullptr;    // one allocation holding everything below
+    size_t block_bytes = 0;
+    // products of extractFeature (radar_loader.hpp:74-141)
+    int    *d_polar = nullptr;           // 2 * KP_CAP (azimuth row, range bin)  feat_in_polar_
+    double *d_cart_pre = nullptr;        // 2 * KP_CAP x,y before voxelisation
+    long long *d_t_pre = nullptr;        // KP_CAP stamps before voxelisation
+    double *d_feat = nullptr;            // 2 * KP_CAP feat_in_cart_ (x, y) after voxel + BEV
+    long long *d_t = nullptr;            // KP_CAP  t_
+    float  *d_kp = nullptr;              // 2 * KP_CAP keypoints (u, v)
+    unsigned char *d_desc = nullptr;     // KP_CAP * 32
+    unsigned char *d_img = nullptr;      // W * W u8 Cartesian image  img_
+    nrs::FrameCounts counts;
+    int W = 0;
+    long long t_criteria = 0;
+    long long t_min = 0, t_max = 0;
+};

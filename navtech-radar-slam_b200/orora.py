@@ -134,3 +134,143 @@ class ORORA:
     @property
     def last_result(self):
         return self._last[0] if self._last else None
+
+
+# =================================================================================================
+# front-end: RadarLoader (ORORA/include/radar_loader.hpp:35-308)
+# =================================================================================================
+from ._lib import ExtractParams, FrameInfo  # noqa: E402
+
+
+def extract_params(dataset):
+    p = ExtractParams()
+    check(lib().nrs_extract_default_params(dataset.encode(), C.byref(p)))
+    return p
+
+
+def cen2019features(ctx, fft_data, max_points, min_range):
+    """features.hpp:36 cen2019features(fft, max_points, min_range, targets) -> targets (3, K)."""
+    fft = np.ascontiguousarray(fft_data, dtype=np.float32)
+    R, Cc = fft.shape
+    cap = 16384
+    out = np.zeros(3 * cap, dtype=np.float64)
+    K = C.c_int()
+    check(lib().nrs_cen2019(ctx.handle, ptr(fft), R, Cc, int(max_points), int(min_range), ptr(out), cap, C.byref(K)))
+    return out[: 3 * K.value].reshape(-1, 3).T.copy()
+
+
+class Frame:
+    """nrs_frame: the device-resident products of one extractFeature call."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self._h = ctx, handle
+        ctx.adopt(self)
+        self.info = FrameInfo()
+        check(lib().nrs_frame_info_get(self._h, C.byref(self.info)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def get(self, want_img=True):
+        i = self.info
+        W = 964
+        polar = np.zeros(3 * max(i.K_polar, 1))
+        feat = np.zeros(3 * max(i.K, 1))
+        kp = np.zeros(2 * max(i.K, 1), dtype=np.float32)
+        t = np.zeros(max(i.K, 1), dtype=np.int64)
+        tn = np.zeros(max(i.K, 1))
+        desc = np.zeros(32 * max(i.K, 1), dtype=np.uint8)
+        img = np.zeros(W * W, dtype=np.uint8) if want_img else None
+        check(lib().nrs_frame_get(self._h, ptr(polar), ptr(feat), ptr(kp), ptr(t), ptr(tn), ptr(desc), ptr(img)))
+        return {"polar": polar[: 3 * i.K_polar].reshape(-1, 3).T.copy(),
+                "feat_in_cart": feat[: 3 * i.K].reshape(-1, 3).T.copy(),
+                "kp": kp[: 2 * i.K].reshape(-1, 2).copy(), "t": t[: i.K].copy(), "t_norm": tn[: i.K].copy(),
+                "desc": desc[: 32 * i.K].reshape(-1, 32).copy(),
+                "img": img.reshape(W, W) if want_img else None}
+
+    def stages(self, R, Cc, W=964):
+        fft = np.zeros((R, Cc), dtype=np.float32)
+        marked = np.zeros((R, Cc), dtype=np.uint8)
+        pre = np.zeros(2 * max(self.info.K_polar, 1))
+        cart = np.zeros((W, W), dtype=np.float32)
+        check(lib().nrs_frame_get_stages(self._h, ptr(fft), ptr(marked), ptr(pre), ptr(cart)))
+        return {"fft": fft, "R": marked, "cart_pre": pre[: 2 * self.info.K_polar].reshape(-1, 2).T.copy(), "cart_f32": cart}
+
+    def close(self):
+        if self._h:
+            lib().nrs_frame_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class RadarLoader:
+    """RadarLoader (radar_loader.hpp:35-308): extractFeature + matchFeatures on the GPU."""
+
+    def __init__(self, dataset, keypoint_extraction="cen2019", voxel_size=0.6, use_voxelization=True,
+                 viz_extraction=False, ctx=None):
+        if dataset not in ("oxford", "mulran"):
+            raise ValueError("Note implemented!")                                  # radar_loader.hpp:62
+        if keypoint_extraction not in ("cen2018", "cen2019"):
+            raise ValueError("Keypoint extraction method seems to be wrong!")      # :64-66
+        if keypoint_extraction != "cen2019":
+            raise ValueError("cen2018 is listed as 'next' in SURVEY.md 8(f); this build implements cen2019")
+        self.ctx = ctx if ctx is not None else _lib.Context(0)
+        self.dataset_ = dataset
+        self.params = extract_params(dataset)
+        self.params.voxel_size = voxel_size
+        self.params.use_voxelization = int(bool(use_voxelization))
+        self.time_unit_denominator_ = 1000000.0 if dataset == "oxford" else 1000000000.0
+
+    def extractFeatureFromRows(self, raw_rows, t_criteria=0):
+        """raw_rows: the decoded 8-bit PNG (what cv::imread gives load_radar)."""
+        raw = np.ascontiguousarray(raw_rows, dtype=np.uint8)
+        h = C.c_void_p()
+        check(lib().nrs_frame_extract(self.ctx.handle, ptr(raw), raw.shape[0], raw.shape[1], C.byref(self.params),
+                                      int(t_criteria), C.byref(h)))
+        fr = Frame(self.ctx, h)
+        d = fr.get()
+        return RadarFeature(img_=d["img"], t_=d["t"], time_unit_denominator_=self.time_unit_denominator_,
+                            desc_=d["desc"], kp_=d["kp"], feat_in_cart_=d["feat_in_cart"],
+                            feat_in_polar_=d["polar"], t_crietria_=int(t_criteria), t_norm_=d["t_norm"], handle=fr)
+
+    def extractFeature(self, datadir, radar_file_path):
+        """radar_loader.hpp:74: reads datadir/radar_file_path (8-bit PNG) and extracts."""
+        import cv2
+        import os
+        raw = cv2.imread(os.path.join(datadir, radar_file_path), cv2.IMREAD_GRAYSCALE)
+        if raw is None:
+            raise FileNotFoundError(os.path.join(datadir, radar_file_path))
+        return self.extractFeatureFromRows(raw, int(radar_file_path.split(".")[0]))
+
+    def matchFeatures(self, prev_feat, curr_feat):
+        """radar_loader.hpp:143-205 -> (prev_matched, curr_matched) with 2xN feat_in_cart_."""
+        cap = max(prev_feat.handle.info.K, 1)
+        q = np.zeros(cap, dtype=np.int32)
+        t = np.zeros(cap, dtype=np.int32)
+        pxy = np.zeros(2 * cap)
+        cxy = np.zeros(2 * cap)
+        pt = np.zeros(cap, dtype=np.int64)
+        ct = np.zeros(cap, dtype=np.int64)
+        n = C.c_int()
+        check(lib().nrs_match(self.ctx.handle, prev_feat.handle.handle, curr_feat.handle.handle,
+                              float(self.params.nndr), cap, ptr(q), ptr(t), ptr(pxy), ptr(cxy), ptr(pt), ptr(ct),
+                              C.byref(n)))
+        N = n.value
+        q, t = q[:N].copy(), t[:N].copy()
+        pm = RadarFeature(img_=prev_feat.img_, t_=pt[:N].copy(), time_unit_denominator_=prev_feat.time_unit_denominator_,
+                          desc_=prev_feat.desc_, kp_=prev_feat.kp_[q], feat_in_cart_=pxy[: 2 * N].reshape(-1, 2).T.copy(),
+                          feat_in_polar_=prev_feat.feat_in_polar_, t_crietria_=prev_feat.t_crietria_,
+                          t_norm_=prev_feat.t_norm_[q], handle=prev_feat.handle)
+        cm = RadarFeature(img_=curr_feat.img_, t_=ct[:N].copy(), time_unit_denominator_=curr_feat.time_unit_denominator_,
+                          desc_=curr_feat.desc_, kp_=prev_feat.kp_[np.minimum(t, len(prev_feat.kp_) - 1)] if len(prev_feat.kp_) else curr_feat.kp_[t],
+                          feat_in_cart_=cxy[: 2 * N].reshape(-1, 2).T.copy(),
+                          feat_in_polar_=curr_feat.feat_in_polar_, t_crietria_=curr_feat.t_crietria_,
+                          t_norm_=curr_feat.t_norm_[t], handle=curr_feat.handle)
+        pm.query_idx, pm.train_idx = q, t
+        return pm, cm

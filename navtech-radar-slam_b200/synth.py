@@ -93,3 +93,71 @@ def correspondences(N, inlier_ratio, seed, theta=np.deg2rad(1.0), tx=2.5, ty=0.1
     ao = rng.uniform(0, 2 * np.pi, n_out)
     prev[:, ~inl] = np.stack([ro * np.cos(ao), ro * np.sin(ao)])
     return np.ascontiguousarray(prev), np.ascontiguousarray(curr), inl, se2(theta, tx, ty)
+
+
+# -------------------------------------------------------------------------------------------------
+# synthetic Navtech polar frames in the "oxford-form" PNG row layout load_radar decodes
+# (ORORA/src/radar_utils.cpp:104-129): bytes 0-7 int64 stamp, 8-9 uint16 encoder, 10 valid,
+# 11.. one byte of power per range bin.
+# -------------------------------------------------------------------------------------------------
+RADAR = {"mulran": dict(range_bins=3360, res=0.05952, stamp_step=625000, jitter=True),
+         "oxford": dict(range_bins=3768, res=0.0432, stamp_step=625, jitter=False)}
+
+
+def radar_world(seed=1234, n_points=300, n_walls=20, extent=200.0):
+    """Static scene: point scatterers + wall segments (sampled every 0.25 m) with a peak power."""
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(-extent / 2, extent / 2, size=(n_points, 2))
+    pw = rng.uniform(120, 250, n_points)
+    xs, ps = [pts], [pw]
+    for _ in range(n_walls):
+        a = rng.uniform(-extent / 2, extent / 2, 2)
+        d = rng.uniform(0, 2 * np.pi)
+        ln = rng.uniform(8, 40)
+        n = int(ln / 0.25)
+        seg = a[None, :] + np.linspace(0, ln, n)[:, None] * np.array([np.cos(d), np.sin(d)])[None, :]
+        xs.append(seg)
+        ps.append(np.full(n, rng.uniform(140, 240)))
+    return np.concatenate(xs), np.concatenate(ps)
+
+
+def radar_frame(world, pose=(0.0, 0.0, 0.0), seed=1234, dataset="mulran", t0=1_560_000_000_000_000_000,
+                n_azimuths=400):
+    """Render the world as seen from pose (x, y, yaw) into uint8 rows (n_azimuths, 11 + bins).
+    A scatterer at sensor-frame polar (range, azimuth) lights a 3-5 bin range blob over 1-3
+    azimuths; background is clip(N(30, 8))."""
+    cfg = RADAR[dataset]
+    bins, res = cfg["range_bins"], cfg["res"]
+    rng = np.random.default_rng(seed)
+    pts, pw = world
+    x0, y0, yaw = pose
+    c, s = np.cos(yaw), np.sin(yaw)
+    dx, dy = pts[:, 0] - x0, pts[:, 1] - y0
+    lx, ly = c * dx + s * dy, -s * dx + c * dy                      # world -> sensor frame
+    rngm = np.hypot(lx, ly)
+    az = np.arctan2(ly, lx) % (2 * np.pi)
+    jit = rng.integers(0, 2, n_azimuths) if cfg["jitter"] else np.zeros(n_azimuths, dtype=np.int64)
+    enc = ((np.arange(n_azimuths) * 14 + jit) % 5600).astype(np.uint16)
+    az_table = enc.astype(np.float64) * 2 * np.pi / 5600.0
+    img = np.clip(rng.normal(30, 8, size=(n_azimuths, bins)), 0, 255)
+    rbin = np.round(rngm / res - 0.5).astype(np.int64)
+    arow = np.round(az / (2 * np.pi) * n_azimuths).astype(np.int64) % n_azimuths
+    half_w = rng.integers(1, 3, len(pts))                           # range blob half width 1..2 -> 3..5 bins
+    half_a = rng.integers(0, 2, len(pts))                           # azimuth half width 0..1 -> 1..3 rows
+    for k in range(len(pts)):
+        if rbin[k] < 60 or rbin[k] >= bins - 3:
+            continue
+        for da in range(-half_a[k], half_a[k] + 1):
+            r_ = (arow[k] + da) % n_azimuths
+            for dr in range(-half_w[k], half_w[k] + 1):
+                v = pw[k] * np.exp(-0.5 * (dr / 1.2) ** 2) * (1.0 if da == 0 else 0.8)
+                b = rbin[k] + dr
+                if img[r_, b] < v:
+                    img[r_, b] = v
+    raw = np.zeros((n_azimuths, 11 + bins), dtype=np.uint8)
+    stamps = (t0 + np.arange(n_azimuths, dtype=np.int64) * cfg["stamp_step"]).astype("<i8")
+    raw[:, 0:8] = stamps.view(np.uint8).reshape(n_azimuths, 8)
+    raw[:, 8:10] = enc.astype("<u2").view(np.uint8).reshape(n_azimuths, 2)
+    raw[:, 10] = 255
+    raw[:, 11:] = np.round(img).astype(np.uint8)
+    return raw

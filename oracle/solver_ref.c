@@ -241,8 +241,10 @@ static void svd2x2(const double H[4], double U[4], double sv[2], double V[4])
     }
     sv[0] = s0; sv[1] = s1;
     if (s0 > 0) { U[0] = hv00 / s0; U[1] = hv10 / s0; } else { U[0] = 1; U[1] = 0; }
-    if (s1 > 1e-300 * (s0 > 1 ? s0 : 1) && s1 > 0) { U[2] = hv01 / s1; U[3] = hv11 / s1; }
-    else { U[2] = -U[1]; U[3] = U[0]; }
+    /* second left singular vector: +-perp(u1), signed so that H v2 = s1 u2 with s1 >= 0; this stays
+     * orthonormal when H is rank deficient (JacobiSVD always returns orthogonal factors) */
+    U[2] = -U[1]; U[3] = U[0];
+    if (U[2] * hv01 + U[3] * hv11 < 0) { U[2] = -U[2]; U[3] = -U[3]; }
 }
 
 void orora_svd_rot2d(const double *X, const double *Y, const double *Wt, int M, double R[4])

@@ -1,0 +1,111 @@
+"""GPU stage-parity of the ORORA front-end against the cv2-driven oracle (oracle/frontend_ref.py):
+every stage up to the matcher is compared exactly (keypoint list, image bytes, descriptor bytes,
+match list), the pose within north_star's 1e-4 m / 1e-5 rad."""
+import importlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def F(oracle):
+    return importlib.import_module("oracle.frontend_ref")
+
+
+@pytest.fixture(scope="module")
+def world(synth):
+    return synth.radar_world(seed=1234)
+
+
+def check_frame(nrs, F, raw, dataset, loader):
+    o = F.extract_feature(raw, dataset)
+    g = loader.extractFeatureFromRows(raw, 1234)
+    info = g.handle.info
+    st = o["stages"]
+    R, C = o["fft"].shape
+    gs = g.handle.stages(R, C)
+    assert np.array_equal(gs["fft"], o["fft"])                                  # load_radar
+    assert info.maxg == np.float32(st["maxg"]) and info.mean == st["mean"]
+    assert info.mean_h == st["mean_h"]
+    assert info.n_candidates == st["n_cand"]
+    assert info.j_consumed == st["j_consumed"] and info.l_regions == st["l_regions"]
+    assert np.array_equal(gs["R"], st["R"])                                     # marked matrix
+    assert np.array_equal(g.feat_in_polar_, o["polar"])                         # cen2019 keypoints
+    cart_o = F.polar_to_cartesian_radar_img(o["azimuths"], o["fft"], loader.params.radar_resolution,
+                                            loader.params.cart_resolution, 964, True,
+                                            loader.params.navtech_version, as_u8=False)
+    assert np.array_equal(gs["cart_f32"], cart_o)                               # cv::remap
+    assert np.array_equal(g.img_, o["img"])                                     # convertTo u8
+    assert np.array_equal(gs["cart_pre"], o["cart_pre_voxel"][:2])              # polar_to_cartesian_points
+    assert info.K == o["feat_in_cart"].shape[1]
+    assert np.array_equal(g.feat_in_cart_, o["feat_in_cart"])                   # voxelize + convert_to_bev
+    assert np.array_equal(g.kp_, o["kp"])
+    assert np.array_equal(g.t_, o["t"])
+    assert np.array_equal(g.desc_, o["desc"])                                   # ORB
+    return o, g
+
+
+@pytest.mark.parametrize("dataset", ["mulran", "oxford"])
+def test_extract_match_solve_parity(nrs, ctx, oracle, synth, F, world, dataset):
+    """BASELINE configs[0] (MulRan 400x3360) and configs[2] (Oxford-format 400x3768): two frames of the
+    same world related by a known SE(2); every stage vs the oracle, then the pose."""
+    loader = nrs.orora.RadarLoader(dataset, "cen2019", 0.6, True, False, ctx=ctx)
+    raw0 = synth.radar_frame(world, (0, 0, 0), seed=1234, dataset=dataset)
+    raw1 = synth.radar_frame(world, (2.5, 0.1, np.deg2rad(1.0)), seed=1235, dataset=dataset)
+    o0, g0 = check_frame(nrs, F, raw0, dataset, loader)
+    o1, g1 = check_frame(nrs, F, raw1, dataset, loader)
+    assert g0.handle.info.K > 300
+    pm_o, cm_o, q_o, t_o = F.match_frames(o0, o1)
+    pm, cm = loader.matchFeatures(g0, g1)
+    assert np.array_equal(pm.query_idx, q_o) and np.array_equal(pm.train_idx, t_o)     # match list
+    assert np.array_equal(pm.feat_in_cart_, pm_o) and np.array_equal(cm.feat_in_cart_, cm_o)
+    est = nrs.orora.ORORA(dataset, "rot", True, False, True, 700, 0.049, 0.1, np.deg2rad(9.0), ctx=ctx)
+    params = nrs.orora.setParams(0.75, 1.0, False, 100, 1.4, 1e-6)
+    T = est.calcTransform(params, 0.25, pm, cm)
+    ro, _ = oracle.orora_calc_transform(pm_o, cm_o, 0.0)
+    assert np.array_equal(est.last_result["clique"], ro["clique"])
+    dth = np.arctan2(T[1, 0], T[0, 0]) - np.arctan2(ro["T"][1, 0], ro["T"][0, 0])
+    assert np.hypot(T[0, 3] - ro["T"][0, 3], T[1, 3] - ro["T"][1, 3]) <= 1e-4 and abs(dth) <= 1e-5
+    # and the answer is the planted motion
+    assert abs(np.arctan2(T[1, 0], T[0, 0]) - np.deg2rad(1.0)) < 5e-3
+    assert abs(T[0, 3] - 2.5) < 0.3 and abs(T[1, 3] - 0.1) < 0.3
+
+
+def test_cen2019_operator_small_and_adversarial(nrs, ctx, F):
+    """cen2019features as a stand-alone operator on small frames: random, heavily tied (few grey
+    levels), nearly empty, and one where fewer than max_points regions exist."""
+    rng = np.random.default_rng(7)
+    cases = []
+    cases.append(((rng.integers(0, 256, (40, 500)) / 255.0).astype(np.float32), 300, 58))
+    cases.append(((rng.integers(0, 4, (64, 700)) * 60 / 255.0).astype(np.float32), 500, 58))      # ties
+    f = np.zeros((32, 450), dtype=np.float32)
+    f[5, 100:104] = 0.9
+    f[6, 101:103] = 0.8
+    f[20, 449] = 1.0
+    cases.append((f, 10000, 58))
+    cases.append(((rng.random((400, 600)) ** 3).astype(np.float32), 2000, 10))                      # cols > rows quirk
+    cases.append(((rng.integers(0, 256, (16, 3360)) / 255.0).astype(np.float32), 10000, 58))
+    for fft, mp, mr in cases:
+        fft[:, :42] = 0
+        want = F.cen2019features(fft, mp, mr)
+        got = nrs.orora.cen2019features(ctx, fft, mp, mr)
+        assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_matcher_ties_and_edges(nrs, ctx, F, synth, world):
+    loader = nrs.orora.RadarLoader("mulran", "cen2019", 0.6, False, False, ctx=ctx)     # no voxelisation
+    raw0 = synth.radar_frame(world, (0, 0, 0), seed=99)
+    o = F.extract_feature(raw0, "mulran", use_voxelization=False)
+    g = loader.extractFeatureFromRows(raw0, 7)
+    assert np.array_equal(g.feat_in_cart_, o["feat_in_cart"]) and g.feat_in_cart_[2].min() == 1.0
+    assert np.array_equal(g.desc_, o["desc"])
+    # a frame matched against itself: every keypoint's best is itself (distance 0); duplicates tie -> lowest index
+    pm, cm = loader.matchFeatures(g, g)
+    q_o, t_o = F.match_features(o["desc"], o["desc"])
+    assert np.array_equal(pm.query_idx, q_o) and np.array_equal(pm.train_idx, t_o)
+    with pytest.raises(ValueError):
+        nrs.orora.RadarLoader("kitti", "cen2019")
+    with pytest.raises(ValueError):
+        nrs.orora.RadarLoader("mulran", "orb")
