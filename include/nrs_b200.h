@@ -210,7 +210,9 @@ typedef struct nrs_frame_info {
     int32_t l_regions;      /* regions counted, <= max_points */
     int32_t K_polar;        /* cen2019 keypoints = feat_in_polar_.cols() */
     int32_t K_voxel;        /* after voxelisation */
-    int32_t K;              /* after the BEV border filter = kp_.size() = desc_.rows */
+    int32_t K;              /* after the BEV border filter = feat_in_cart_.cols() = t_.size() */
+    int32_t K_desc;         /* kp_.size() = desc_.rows after cv::ORB::compute's own border filter (<= K) */
+    int32_t pad_;
     float   maxg, mean, mean_h, cart_max;
     int64_t t_criteria;
 } nrs_frame_info;
@@ -235,8 +237,10 @@ int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw_rows, int R, int row_pitc
 int nrs_frame_destroy(nrs_frame *f);
 int nrs_frame_info_get(const nrs_frame *f, nrs_frame_info *info);
 /* copy products to host; any pointer may be NULL.  Sizes: polar 3 x K_polar doubles (col-major),
- * feat_in_cart 3 x K doubles (row 2 = 0 with voxelisation, 1 without), kp K x 2 float (u, v),
- * t K int64, t_norm K doubles, desc K x 32 bytes, img W x W bytes. */
+ * feat_in_cart 3 x K doubles (row 2 = 0 with voxelisation, 1 without), t K int64, t_norm K doubles,
+ * kp K_desc x 2 float (u, v), desc K_desc x 32 bytes, img W x W bytes.  K_desc < K happens when
+ * cv::ORB drops a keypoint whose rounded coordinate hits the image border band; the reference then
+ * indexes feat_in_cart_ with descriptor rows (radar_loader.hpp:181-182) and so does nrs_match. */
 int nrs_frame_get(nrs_frame *f, double *polar_3xK0, double *feat_in_cart_3xK, float *kp_Kx2,
                   int64_t *t_K, double *t_norm_K, uint8_t *desc_Kx32, uint8_t *img_WxW);
 /* stage outputs for parity tests: fft (R x C float), R mask (R x C bytes), pre-voxel Cartesian

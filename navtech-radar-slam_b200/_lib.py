@@ -53,7 +53,8 @@ class ExtractParams(C.Structure):
 class FrameInfo(C.Structure):
     """nrs_frame_info (include/nrs_b200.h)."""
     _fields_ = [("n_candidates", C.c_int32), ("j_consumed", C.c_int32), ("l_regions", C.c_int32),
-                ("K_polar", C.c_int32), ("K_voxel", C.c_int32), ("K", C.c_int32), ("maxg", C.c_float),
+                ("K_polar", C.c_int32), ("K_voxel", C.c_int32), ("K", C.c_int32), ("K_desc", C.c_int32),
+                ("pad_", C.c_int32), ("maxg", C.c_float),
                 ("mean", C.c_float), ("mean_h", C.c_float), ("cart_max", C.c_float), ("t_criteria", C.c_int64)]
 
 

@@ -18,13 +18,13 @@ struct FrameCounts {
     int   l_regions;     // regions counted (<= max_points)
     int   K0;            // cen2019 keypoints (polar)
     int   Kv;            // after voxelisation
-    int   K;             // after the BEV border filter (== descriptor rows)
+    int   K;             // after the BEV border filter (feat_in_cart_ columns)
+    int   Kd;            // keypoints cv::ORB keeps (runByImageBorder on rounded coords) == descriptor rows
     float maxg;
     float mean;
     float mean_h;
     float cart_max;
     int   overflow;      // a capacity was exceeded (reported as NRS_ECAPACITY)
-    int   pad;
 };
 
 struct FrontendState {
@@ -76,7 +76,8 @@ struct nrs_frame {
     long long *d_t_pre = nullptr;        // KP_CAP stamps before voxelisation
     double *d_feat = nullptr;            // 2 * KP_CAP feat_in_cart_ (x, y) after voxel + BEV
     long long *d_t = nullptr;            // KP_CAP  t_
-    float  *d_kp = nullptr;              // 2 * KP_CAP keypoints (u, v)
+    float  *d_kp = nullptr;              // 2 * KP_CAP keypoints (u, v) from convert_to_bev
+    float  *d_kp_orb = nullptr;          // 2 * KP_CAP keypoints cv::ORB::compute keeps (kp_ after :126)
     unsigned char *d_desc = nullptr;     // KP_CAP * 32
     unsigned char *d_img = nullptr;      // W * W u8 Cartesian image  img_
     nrs::FrameCounts counts;

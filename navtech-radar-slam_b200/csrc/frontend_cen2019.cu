@@ -398,7 +398,8 @@ fe_vox_centroid_kernel(const unsigned int *__restrict__ skeys, const unsigned in
 __global__ void __launch_bounds__(1024)
 fe_bev_kernel(const double *__restrict__ pts_xy, const long long *__restrict__ t_pre,
               FrameCounts *__restrict__ cnt, int use_vox, float cart_resolution, int width, int patch,
-              int cap, double *__restrict__ feat, float *__restrict__ kp, long long *__restrict__ t_out)
+              int cap, double *__restrict__ feat, float *__restrict__ kp, long long *__restrict__ t_out,
+              float *__restrict__ kp_orb)
 {
     typedef cub::BlockScan<int, 1024> BS;
     __shared__ typename BS::TempStorage tmp;
@@ -432,7 +433,33 @@ fe_bev_kernel(const double *__restrict__ pts_xy, const long long *__restrict__ t
         if (t == 0) carry = c0 + total;
         __syncthreads();
     }
-    if (t == 0) cnt->K = carry;
+    __syncthreads();
+    const int K = carry;
+    __syncthreads();
+    if (t == 0) { cnt->K = K; carry = 0; }
+    __syncthreads();
+    // cv::ORB::compute (radar_loader.hpp:126) first runs KeyPointsFilter::runByImageBorder(kps, size,
+    // edgeThreshold = patch): Rect(Point(b,b), Point(W-b,W-b)).contains(Point(cvRound(u), cvRound(v))).
+    // Keypoints with cvRound(u|v) == W - patch are dropped from kp_/desc_ while feat_in_cart_ keeps its
+    // columns -- the reference's index misalignment is reproduced, not repaired.
+    for (int base = 0; base < K; base += 1024) {
+        const int j = base + t;
+        bool keep = false;
+        float u = 0.f, v = 0.f;
+        if (j < K) {
+            u = kp[2 * j]; v = kp[2 * j + 1];
+            const int ru = __float2int_rn(u), rv = __float2int_rn(v);
+            keep = ru >= patch && ru < width - patch && rv >= patch && rv < width - patch;
+        }
+        int ex, total;
+        BS(tmp).ExclusiveSum(keep ? 1 : 0, ex, total);
+        const int c0 = carry;
+        if (keep) { kp_orb[2 * (c0 + ex)] = u; kp_orb[2 * (c0 + ex) + 1] = v; }
+        __syncthreads();
+        if (t == 0) carry = c0 + total;
+        __syncthreads();
+    }
+    if (t == 0) cnt->Kd = carry;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -511,7 +538,7 @@ int fe_points_voxel_bev_device(nrs_ctx *ctx, FrontendState &S, nrs_frame *f)
         pts = vox;
     }
     fe_bev_kernel<<<1, 1024, 0, st>>>(pts, f->d_t_pre, cnt, p.use_voxelization, p.cart_resolution,
-                                      p.cart_pixel_width, p.patch_size, FE_KP_CAP, f->d_feat, f->d_kp, f->d_t);
+                                      p.cart_pixel_width, p.patch_size, FE_KP_CAP, f->d_feat, f->d_kp, f->d_t, f->d_kp_orb);
     NRS_LAUNCHED();
     return NRS_OK;
 }

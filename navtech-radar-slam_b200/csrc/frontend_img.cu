@@ -176,7 +176,7 @@ __global__ void fe_brief_kernel(const unsigned char *__restrict__ blur, int W, c
 {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = gid >> 5, byte = gid & 31;
-    if (k >= cnt->K) return;
+    if (k >= cnt->Kd) return;
     const int cx = __float2int_rn(kp[2 * k]), cy = __float2int_rn(kp[2 * k + 1]);
     const unsigned char *center = blur + (size_t)cy * W + cx;
     unsigned int val = 0;
@@ -390,6 +390,7 @@ static int alloc_frame(nrs_ctx *ctx, int W, nrs_frame **out)
     const size_t o_polar = take(2 * FE_KP_CAP * sizeof(int)), o_pre = take(2 * FE_KP_CAP * sizeof(double));
     const size_t o_tpre = take(FE_KP_CAP * sizeof(long long)), o_feat = take(2 * FE_KP_CAP * sizeof(double));
     const size_t o_t = take(FE_KP_CAP * sizeof(long long)), o_kp = take(2 * FE_KP_CAP * sizeof(float));
+    const size_t o_kpo = take(2 * FE_KP_CAP * sizeof(float));
     const size_t o_desc = take((size_t)FE_KP_CAP * 32), o_img = take((size_t)W * W);
     cudaError_t e = cudaMalloc((void **)&f->d_block, off);
     if (e != cudaSuccess) { delete f; set_error("frame allocation: %s", cudaGetErrorString(e)); return NRS_ENOMEM; }
@@ -397,7 +398,7 @@ static int alloc_frame(nrs_ctx *ctx, int W, nrs_frame **out)
     unsigned char *b = f->d_block;
     f->d_polar = (int *)(b + o_polar); f->d_cart_pre = (double *)(b + o_pre); f->d_t_pre = (long long *)(b + o_tpre);
     f->d_feat = (double *)(b + o_feat); f->d_t = (long long *)(b + o_t); f->d_kp = (float *)(b + o_kp);
-    f->d_desc = b + o_desc; f->d_img = b + o_img;
+    f->d_desc = b + o_desc; f->d_img = b + o_img; f->d_kp_orb = (float *)(b + o_kpo);
     *out = f;
     return NRS_OK;
 }
@@ -532,7 +533,7 @@ int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw, int R, int row_pitch, co
     NRS_LAUNCHED();
     fe_blur_col_kernel<<<bg, 256, 0, st>>>(S->d_rowbuf, W, S->d_blur);
     NRS_LAUNCHED();
-    fe_brief_kernel<<<(FE_KP_CAP * 32 + 255) / 256, 256, 0, st>>>(S->d_blur, W, f->d_kp, S->d_counts, S->d_pattern, f->d_desc);
+    fe_brief_kernel<<<(FE_KP_CAP * 32 + 255) / 256, 256, 0, st>>>(S->d_blur, W, f->d_kp_orb, S->d_counts, S->d_pattern, f->d_desc);
     NRS_LAUNCHED();
     NRS_CUDA(cudaMemcpyAsync(S->h_counts, S->d_counts, sizeof(FrameCounts), cudaMemcpyDeviceToHost, st));
     NRS_CUDA(cudaStreamSynchronize(st));
@@ -565,6 +566,7 @@ int nrs_frame_info_get(const nrs_frame *f, nrs_frame_info *info)
     info->K_polar = f->counts.K0;
     info->K_voxel = f->counts.Kv;
     info->K = f->counts.K;
+    info->K_desc = f->counts.Kd;
     info->maxg = f->counts.maxg; info->mean = f->counts.mean; info->mean_h = f->counts.mean_h;
     info->cart_max = f->counts.cart_max;
     info->t_criteria = f->t_criteria;
@@ -578,15 +580,15 @@ int nrs_frame_get(nrs_frame *f, double *polar, double *feat, float *kp, int64_t 
     nrs_ctx *ctx = f->ctx;
     std::lock_guard<std::mutex> lk(ctx->mu);
     NRS_CUDA(cudaSetDevice(ctx->device));
-    const int K0 = f->counts.K0, K = f->counts.K;
+    const int K0 = f->counts.K0, K = f->counts.K, Kd = f->counts.Kd;
     std::vector<int> hp;
     std::vector<double> hf;
     std::vector<long long> ht;
     if (polar && K0) { hp.resize(2 * (size_t)K0); NRS_CUDA(cudaMemcpyAsync(hp.data(), f->d_polar, hp.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)); }
     if (feat && K) { hf.resize(2 * (size_t)K); NRS_CUDA(cudaMemcpyAsync(hf.data(), f->d_feat, hf.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)); }
     if ((t || t_norm) && K) { ht.resize(K); NRS_CUDA(cudaMemcpyAsync(ht.data(), f->d_t, (size_t)K * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream)); }
-    if (kp && K) NRS_CUDA(cudaMemcpyAsync(kp, f->d_kp, 2 * (size_t)K * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    if (desc && K) NRS_CUDA(cudaMemcpyAsync(desc, f->d_desc, (size_t)K * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    if (kp && Kd) NRS_CUDA(cudaMemcpyAsync(kp, f->d_kp_orb, 2 * (size_t)Kd * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (desc && Kd) NRS_CUDA(cudaMemcpyAsync(desc, f->d_desc, (size_t)Kd * 32, cudaMemcpyDeviceToHost, ctx->stream));
     if (img) NRS_CUDA(cudaMemcpyAsync(img, f->d_img, (size_t)f->W * f->W, cudaMemcpyDeviceToHost, ctx->stream));
     NRS_CUDA(cudaStreamSynchronize(ctx->stream));
     if (polar) for (int i = 0; i < K0; ++i) { polar[3 * i] = hp[2 * i]; polar[3 * i + 1] = hp[2 * i + 1]; polar[3 * i + 2] = 1.0; }
@@ -640,7 +642,7 @@ int nrs_match(nrs_ctx *ctx, const nrs_frame *prev, const nrs_frame *curr, float 
     NRS_CHECK_ARG(ctx && prev && curr && N && cap >= 0, "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     NRS_CUDA(cudaSetDevice(ctx->device));
-    const int nq = prev->counts.K, nt = curr->counts.K;
+    const int nq = prev->counts.Kd, nt = curr->counts.Kd;   // desc_ rows; indices address feat_in_cart_ as-is
     *N = 0;
     if (nq == 0 || nt == 0) return NRS_OK;
     const size_t c = (size_t)std::max(cap, 1);

@@ -177,16 +177,16 @@ class Frame:
         W = 964
         polar = np.zeros(3 * max(i.K_polar, 1))
         feat = np.zeros(3 * max(i.K, 1))
-        kp = np.zeros(2 * max(i.K, 1), dtype=np.float32)
+        kp = np.zeros(2 * max(i.K_desc, 1), dtype=np.float32)
         t = np.zeros(max(i.K, 1), dtype=np.int64)
         tn = np.zeros(max(i.K, 1))
-        desc = np.zeros(32 * max(i.K, 1), dtype=np.uint8)
+        desc = np.zeros(32 * max(i.K_desc, 1), dtype=np.uint8)
         img = np.zeros(W * W, dtype=np.uint8) if want_img else None
         check(lib().nrs_frame_get(self._h, ptr(polar), ptr(feat), ptr(kp), ptr(t), ptr(tn), ptr(desc), ptr(img)))
         return {"polar": polar[: 3 * i.K_polar].reshape(-1, 3).T.copy(),
                 "feat_in_cart": feat[: 3 * i.K].reshape(-1, 3).T.copy(),
-                "kp": kp[: 2 * i.K].reshape(-1, 2).copy(), "t": t[: i.K].copy(), "t_norm": tn[: i.K].copy(),
-                "desc": desc[: 32 * i.K].reshape(-1, 32).copy(),
+                "kp": kp[: 2 * i.K_desc].reshape(-1, 2).copy(), "t": t[: i.K].copy(), "t_norm": tn[: i.K].copy(),
+                "desc": desc[: 32 * i.K_desc].reshape(-1, 32).copy(),
                 "img": img.reshape(W, W) if want_img else None}
 
     def stages(self, R, Cc, W=964):
@@ -250,7 +250,7 @@ class RadarLoader:
 
     def matchFeatures(self, prev_feat, curr_feat):
         """radar_loader.hpp:143-205 -> (prev_matched, curr_matched) with 2xN feat_in_cart_."""
-        cap = max(prev_feat.handle.info.K, 1)
+        cap = max(prev_feat.handle.info.K_desc, 1)
         q = np.zeros(cap, dtype=np.int32)
         t = np.zeros(cap, dtype=np.int32)
         pxy = np.zeros(2 * cap)
@@ -266,7 +266,7 @@ class RadarLoader:
         pm = RadarFeature(img_=prev_feat.img_, t_=pt[:N].copy(), time_unit_denominator_=prev_feat.time_unit_denominator_,
                           desc_=prev_feat.desc_, kp_=prev_feat.kp_[q], feat_in_cart_=pxy[: 2 * N].reshape(-1, 2).T.copy(),
                           feat_in_polar_=prev_feat.feat_in_polar_, t_crietria_=prev_feat.t_crietria_,
-                          t_norm_=prev_feat.t_norm_[q], handle=prev_feat.handle)
+                          t_norm_=prev_feat.t_norm_[q], handle=prev_feat.handle)   # :187: indexed by descriptor row, like the reference
         cm = RadarFeature(img_=curr_feat.img_, t_=ct[:N].copy(), time_unit_denominator_=curr_feat.time_unit_denominator_,
                           desc_=curr_feat.desc_, kp_=prev_feat.kp_[np.minimum(t, len(prev_feat.kp_) - 1)] if len(prev_feat.kp_) else curr_feat.kp_[t],
                           feat_in_cart_=cxy[: 2 * N].reshape(-1, 2).T.copy(),

@@ -247,7 +247,8 @@ def orb_compute(img_u8, kp_uv, patch_size=21):
     kps2, desc = orb.compute(img_u8, kps)
     if desc is None:
         desc = np.zeros((0, 32), dtype=np.uint8)
-    return desc, len(kps2)
+    kept = np.array([k.pt for k in kps2], dtype=np.float32).reshape(-1, 2)
+    return desc, kept
 
 
 def match_features(desc_prev, desc_curr, nndr=np.float32(0.8)):
@@ -279,10 +280,12 @@ def extract_feature(raw, dataset="mulran", voxel_size=0.6, use_voxelization=True
     if use_voxelization:
         cart = voxelize(voxel_size, cart)
     cart, kp, t = convert_to_bev(cart, P.cart_resolution, P.cart_pixel_width, P.patch_size, t)
-    desc, n_kept = orb_compute(img, kp, P.patch_size)
-    assert n_kept == len(kp), "cv::ORB dropped keypoints: the reference would misalign kp_/feat_in_cart_"
+    # cv::ORB::compute filters kp_ in place (runByImageBorder on rounded coordinates): kp_/desc_ can
+    # end up shorter than feat_in_cart_/t_, and matchFeatures indexes the latter with descriptor rows
+    # (radar_loader.hpp:181-187).  Kept as is.
+    desc, kp_orb = orb_compute(img, kp, P.patch_size)
     return {"fft": fft, "azimuths": azimuths, "times": times, "polar": polar, "img": img,
-            "cart_pre_voxel": cart_pre_voxel, "feat_in_cart": cart, "kp": kp, "t": t, "desc": desc,
+            "cart_pre_voxel": cart_pre_voxel, "feat_in_cart": cart, "kp_bev": kp, "kp": kp_orb, "t": t, "desc": desc,
             "stages": st}
 
 

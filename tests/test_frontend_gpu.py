@@ -41,7 +41,7 @@ def check_frame(nrs, F, raw, dataset, loader):
     assert np.array_equal(gs["cart_pre"], o["cart_pre_voxel"][:2])              # polar_to_cartesian_points
     assert info.K == o["feat_in_cart"].shape[1]
     assert np.array_equal(g.feat_in_cart_, o["feat_in_cart"])                   # voxelize + convert_to_bev
-    assert np.array_equal(g.kp_, o["kp"])
+    assert np.array_equal(g.kp_, o["kp"]) and info.K_desc == len(o["kp"])     # kp_ after cv::ORB's border filter
     assert np.array_equal(g.t_, o["t"])
     assert np.array_equal(g.desc_, o["desc"])                                   # ORB
     return o, g

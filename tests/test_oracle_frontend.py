@@ -1,0 +1,195 @@
+"""CPU tests of the front-end oracle: the OpenCV arithmetic the CUDA kernels restate is pinned
+against the real cv2 calls, the exact parallel form of the cen2019 marking loop is checked against
+the sequential loop, and the whole chain recovers a planted motion."""
+import importlib
+import math
+
+import cv2
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def F(oracle):
+    return importlib.import_module("oracle.frontend_ref")
+
+
+def test_remap_restatement_matches_cv2():
+    rng = np.random.default_rng(0)
+    H, W = 50, 300
+    src = rng.random((H, W)).astype(np.float32)
+    mx = (rng.random((64, 64)) * (W + 20) - 10).astype(np.float32)
+    my = (rng.random((64, 64)) * (H + 6) - 3).astype(np.float32)
+    ref = cv2.remap(src, mx, my, cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+    sx = np.rint(mx * np.float32(32)).astype(np.int64)
+    sy = np.rint(my * np.float32(32)).astype(np.int64)
+    ix, iy = sx >> 5, sy >> 5
+    fx = (sx & 31).astype(np.float32) * np.float32(1 / 32)
+    fy = (sy & 31).astype(np.float32) * np.float32(1 / 32)
+
+    def tap(y, x):
+        ok = (x >= 0) & (x < W) & (y >= 0) & (y < H)
+        return np.where(ok, src[np.clip(y, 0, H - 1), np.clip(x, 0, W - 1)], np.float32(0))
+    one = np.float32(1)
+    out = ((tap(iy, ix) * ((one - fy) * (one - fx)) + tap(iy, ix + 1) * ((one - fy) * fx))
+           + tap(iy + 1, ix) * (fy * (one - fx))) + tap(iy + 1, ix + 1) * (fy * fx)
+    assert np.array_equal(out, ref)
+
+
+def test_u8_conversion_and_prewitt_and_mean():
+    rng = np.random.default_rng(1)
+    v = (rng.random((200, 200)) * 3).astype(np.float32)
+    mxv = float(v.max())
+    assert np.array_equal(cv2.convertScaleAbs(v, alpha=255.0 / mxv),
+                          np.clip(np.rint(v * np.float32(255.0 / mxv)), 0, 255).astype(np.uint8))
+    f = (rng.integers(0, 256, (40, 100)) / 255.0).astype(np.float32)
+    pw = np.zeros((1, 3), np.float32)
+    pw[0, 0], pw[0, 2] = -1, 1
+    g = cv2.filter2D(f, -1, pw, borderType=cv2.BORDER_REFLECT101)
+    fp = np.pad(f, ((0, 0), (1, 1)), mode="reflect")
+    assert np.array_equal(g, fp[:, 2:] - fp[:, :-2])
+    s = float(f.astype(np.float64).sum())            # exact for k/255 data in any order
+    assert cv2.mean(f)[0] == s * (1.0 / f.size)
+
+
+GAUSS_BITS = np.array([1032826801, 1040595070, 1044597305, 1046301408, 1044597305, 1040595070, 1032826801],
+                      dtype=np.uint32)
+
+
+def blur_restated(img):
+    """ORB's blur: sepFilter2D float path.  row: k0*S0 then FMA chain; column: k3*c then FMA of
+    symmetric pairs; rounded to u8.  (FMA emulated in float64: product exact, one rounding.)"""
+    k = GAUSS_BITS.view(np.float32)
+    H, W = img.shape
+
+    def fma(a, b, c):
+        return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+    pad = np.pad(img, ((0, 0), (3, 3)), mode="reflect").astype(np.float32)
+    s = (k[0] * pad[:, 0:W]).astype(np.float32)
+    for t in range(1, 7):
+        s = fma(np.full_like(s, k[t]), pad[:, t:t + W], s)
+    pv = np.pad(s, ((3, 3), (0, 0)), mode="reflect")
+    o = (k[3] * pv[3:3 + H]).astype(np.float32)
+    for t in range(1, 4):
+        o = fma(np.full_like(o, k[3 + t]), (pv[3 + t:3 + t + H] + pv[3 - t:3 - t + H]).astype(np.float32), o)
+    return np.clip(np.rint(o), 0, 255).astype(np.uint8)
+
+
+def brief_pattern(patch=21):
+    state = 0x34985739
+
+    def nxt():
+        nonlocal state
+        state = ((state & 0xffffffff) * 4164903690 + (state >> 32)) & 0xffffffffffffffff
+        return state & 0xffffffff
+    half = patch // 2
+    angle = np.float32(-1.0) * np.float32(math.pi / 180.0)
+    a, b = np.float32(math.cos(float(angle))), np.float32(math.sin(float(angle)))
+    out = []
+    for _ in range(512):
+        px = np.float32(-half + nxt() % (2 * half + 1))
+        py = np.float32(-half + nxt() % (2 * half + 1))
+        out.append((int(np.rint(px * a - py * b)), int(np.rint(px * b + py * a))))
+    return out
+
+
+def test_orb_restatement_matches_cv2():
+    """The kernel constants (Gaussian taps), the blur arithmetic, the RNG pattern at angle -1 degree and
+    the bit order, all against cv2.ORB.compute on 600 keypoints incl. x.5 coordinates."""
+    assert np.array_equal(cv2.getGaussianKernel(7, 2, cv2.CV_32F).ravel().view(np.uint32), GAUSS_BITS)
+    rng = np.random.default_rng(2)
+    for smooth in (False, True):
+        img = rng.integers(0, 256, (320, 320), dtype=np.uint8)
+        if smooth:
+            img = cv2.GaussianBlur(img, (9, 9), 3)
+        blur = blur_restated(img)
+        ref8 = cv2.sepFilter2D(img, cv2.CV_8U, cv2.getGaussianKernel(7, 2, cv2.CV_32F),
+                               cv2.getGaussianKernel(7, 2, cv2.CV_32F), borderType=cv2.BORDER_REFLECT_101)
+        assert (blur[:, :-4] != ref8[:, :-4]).sum() == 0      # last W%8 columns take cv2's scalar tail
+        pts = rng.uniform(22, 297, (300, 2))
+        pts[:60] = np.floor(pts[:60]) + 0.5
+        orb = cv2.ORB_create()
+        orb.setPatchSize(21)
+        orb.setEdgeThreshold(21)
+        kps, desc = orb.compute(img, [cv2.KeyPoint(float(x), float(y), 21) for x, y in pts])
+        assert len(kps) == 300
+        pat = brief_pattern()
+        for i, kp in enumerate(kps):
+            cx, cy = int(np.rint(np.float32(kp.pt[0]))), int(np.rint(np.float32(kp.pt[1])))
+            d = np.zeros(32, dtype=np.uint8)
+            for n in range(32):
+                byte = 0
+                for kb in range(8):
+                    (x0, y0), (x1, y1) = pat[2 * (8 * n + kb)], pat[2 * (8 * n + kb) + 1]
+                    byte |= int(blur[cy + y0, cx + x0] < blur[cy + y1, cx + x1]) << kb
+                d[n] = byte
+            assert np.array_equal(d, desc[i]), i
+
+
+def parallel_mark(s, h, mean_h, rows, cols, max_points):
+    """The claim formulation the CUDA kernels use (csrc/frontend_cen2019.cu), in numpy."""
+    ca, cr = np.nonzero(h > mean_h)
+    order = np.argsort(-h[ca, cr], kind="stable")
+    ca, cr = ca[order], cr[order]
+    claim = np.full((rows, cols), np.iinfo(np.int64).max)
+    regions = []
+    for k, (a, r) in enumerate(zip(ca, cr)):
+        lo = r
+        while lo - 1 >= 0 and s[a, lo - 1] < 0:
+            lo -= 1
+        hi = r
+        if r < rows - 1:
+            while hi + 1 < cols and s[a, hi + 1] < 0:
+                hi += 1
+        regions.append((a, lo, hi))
+        claim[a, lo:hi + 1] = np.minimum(claim[a, lo:hi + 1], k)
+    incr = np.array([int(np.all(claim[a, lo:hi + 1] == k)) for k, (a, lo, hi) in enumerate(regions)], dtype=np.int64)
+    cums = np.cumsum(incr)
+    hit = np.nonzero((cums == max_points) & (incr == 1))[0]
+    J = int(hit[0]) if len(hit) else len(regions) - 1
+    return (claim <= J).astype(np.uint8), J + 1, int(min(cums[-1], max_points)) if len(cums) else 0
+
+
+def test_parallel_marking_equals_sequential_loop(F):
+    """Exactness of the claim/atomicMin formulation against features.cpp:226-249, incl. heavy ties,
+    the `r < s.rows - 1` column quirk regime (cols > rows) and cut-offs in the middle of ties."""
+    rng = np.random.default_rng(3)
+    for trial in range(40):
+        rows, cols = int(rng.integers(4, 24)), int(rng.integers(30, 90))
+        levels = int(rng.choice([3, 8, 256]))
+        fft = (rng.integers(0, levels, (rows, cols)) * (255 // max(levels - 1, 1)) / 255.0).astype(np.float32)
+        mp = int(rng.choice([3, 10, 40, 10000]))
+        st = F.cen2019_stages(fft, mp, min_range=int(rng.integers(0, 8)))
+        Rm, consumed, l = parallel_mark(st["s"], st["h"], st["mean_h"], rows, cols, mp)
+        assert np.array_equal(Rm, st["R"]), trial
+        assert l == st["l_regions"]
+        if st["l_regions"] == mp:
+            assert consumed == st["j_consumed"]
+
+
+def test_voxelize_and_bev(F):
+    rng = np.random.default_rng(4)
+    pts = np.vstack([rng.uniform(-150, 150, (2, 3000)), np.ones((1, 3000))])
+    v = F.voxelize(0.6, pts)
+    assert v.shape[0] == 3 and v.shape[1] < 3000 and np.all(v[2] == 0)
+    # every centroid lies in its own voxel, voxels are distinct and ordered y-major
+    inv = np.float32(1) / np.float32(0.6)
+    ij = np.floor(v[:2].astype(np.float32) * inv).astype(np.int64)
+    assert len({(a, b) for a, b in ij.T}) == v.shape[1]
+    key = ij[1] * 100000 + ij[0]
+    assert np.all(np.diff(key) > 0)
+    cart, kp, t = F.convert_to_bev(v, 0.2592, 964, 21, np.arange(3000, dtype=np.int64))
+    assert np.all(kp > 21) and np.all(kp < 943) and cart.shape[1] == len(kp) == len(t)
+
+
+def test_chain_recovers_planted_motion(F, oracle, synth):
+    w = synth.radar_world(seed=1234)
+    f0 = F.extract_feature(synth.radar_frame(w, (0, 0, 0), seed=1234), "mulran")
+    f1 = F.extract_feature(synth.radar_frame(w, (2.5, 0.1, np.deg2rad(1.0)), seed=1235), "mulran")
+    assert f0["stages"]["l_regions"] == 10000 and f0["feat_in_cart"].shape[1] > 500
+    pm, cm, q, t = F.match_frames(f0, f1)
+    assert pm.shape[1] > 100
+    r, _ = oracle.orora_calc_transform(pm, cm, 0.0)
+    assert r["valid"] and r["info"].M > 50
+    assert abs(np.arctan2(r["T"][1, 0], r["T"][0, 0]) - np.deg2rad(1.0)) < 5e-3
+    assert abs(r["T"][0, 3] - 2.5) < 0.3 and abs(r["T"][1, 3] - 0.1) < 0.3
