@@ -117,7 +117,7 @@ def cen2019_stages(fft, max_points=10000, min_range=58):
     s = np.ascontiguousarray(s)
     h = np.ascontiguousarray(h)
     l = L.fe_cen2019_mark(_p(s), rows, cols, _p(ca), _p(cr), len(ca), max_points, _p(R), C.byref(j))
-    cap = rows * 64
+    cap = rows * (cols // 2 + 1)
     oa = np.zeros(cap, dtype=np.int32)
     orr = np.zeros(cap, dtype=np.int32)
     k = L.fe_cen2019_scan(_p(R), _p(h), rows, cols, min_range, _p(oa), _p(orr), cap)
