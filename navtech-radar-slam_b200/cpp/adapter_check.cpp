@@ -1,0 +1,84 @@
+// adapter_check.cpp -- instantiates every adapter in nrs_adapters.hpp with minimal stand-ins for
+// Eigen::MatrixXd and pcl::PointCloud (neither library is in the build container) and, when a GPU
+// is present, runs a small end-to-end exercise through the C++ host side:
+//     g++ -std=c++17 -Iinclude -Inavtech-radar-slam_b200/cpp adapter_check.cpp -Lnavtech-radar-slam_b200 -lnrs_b200
+// Prints one line per check; exit code 0 = all good, 77 = no GPU (compile/link check only).
+#include <cstdio>
+#include <random>
+
+#include "nrs_adapters.hpp"
+
+struct MiniMatrix {                      // the slice of Eigen::MatrixXd's interface the adapters use
+    MiniMatrix() = default;
+    MiniMatrix(long r, long c) : r_(r), c_(c), d_((size_t)r * c, 0.0) {}
+    double *data() { return d_.data(); }
+    const double *data() const { return d_.data(); }
+    long rows() const { return r_; }
+    long cols() const { return c_; }
+    void resize(long r, long c) { r_ = r; c_ = c; d_.assign((size_t)r * c, 0.0); }
+    double &operator()(long i, long j) { return d_[(size_t)j * r_ + i]; }      // column-major
+    double operator()(long i, long j) const { return d_[(size_t)j * r_ + i]; }
+    long r_ = 0, c_ = 0;
+    std::vector<double> d_;
+};
+struct MiniPoint { float x, y, z, intensity; };
+struct MiniCloud { std::vector<MiniPoint> points; };
+
+using SCManager = nrs::SCManagerT<MiniMatrix, MiniCloud>;
+using RadarLoader = nrs::RadarLoaderT<MiniMatrix>;
+using ORORA = nrs::ORORAT<MiniMatrix>;
+
+int main()
+{
+    nrs_ctx *ctx = nullptr;
+    if (nrs_ctx_create(0, &ctx) != NRS_OK) {
+        std::printf("no GPU: %s (adapters compiled and linked)\n", nrs_last_error());
+        return 77;
+    }
+    int rc = 0;
+    {
+    std::mt19937 rng(1);
+    std::uniform_real_distribution<float> U(-70.f, 70.f);
+    SCManager sc(ctx);
+    sc.setSCdistThres(0.45);
+    std::vector<MiniCloud> clouds(8);
+    for (auto &c : clouds) for (int i = 0; i < 600; ++i) c.points.push_back({U(rng), U(rng), 1.0f, 0.f});
+    int found = 0;
+    for (int k = 0; k < 70; ++k) {
+        sc.makeAndSaveScancontextAndKeys(clouds[k % 8]);
+        auto r = sc.detectLoopClosureID();
+        if (k >= 40 && r.first >= 0) { ++found; if (r.first % 8 != k % 8) { std::printf("wrong loop %d for %d\n", r.first, k); return 1; } }
+    }
+    std::printf("SCManager: %zu keyframes, %d loops found\n", sc.polarcontexts_.size(), found);
+    if (found < 20) return 1;
+    auto d = sc.distanceBtnScanContext(sc.polarcontexts_[3], sc.polarcontexts_[11]);
+    std::printf("distanceBtnScanContext(3,11) = %.3g shift %d\n", d.first, d.second);
+    if (!(d.first < 1e-12) || d.second != 0) return 1;
+
+    // solver through ORORA::calcTransform
+    const int N = 300;
+    MiniMatrix prev(2, N), curr(2, N);
+    const double th = 0.02, tx = 1.5, ty = -0.2;
+    std::uniform_real_distribution<double> P(-80., 80.);
+    for (int j = 0; j < N; ++j) {
+        curr(0, j) = P(rng); curr(1, j) = P(rng);
+        if (j % 3) { prev(0, j) = std::cos(th) * curr(0, j) - std::sin(th) * curr(1, j) + tx; prev(1, j) = std::sin(th) * curr(0, j) + std::cos(th) * curr(1, j) + ty; }
+        else { prev(0, j) = P(rng); prev(1, j) = P(rng); }
+    }
+    ORORA est("mulran", "rot", true, false, true, 700, 0.049, 0.1, 9.0 * M_PI / 180.0, ctx);
+    nrs_solver_params params;
+    nrs::setParams(0.75, 1.0, false, 100, 1.4, 1e-6, params);
+    ORORA::RadarFeature pm, cm;
+    pm.feat_in_cart_ = prev; cm.feat_in_cart_ = curr;
+    MiniMatrix T = est.calcTransform(params, 0.25, pm, cm);
+    std::printf("ORORA: M = %d, yaw = %.5f (true %.5f), t = (%.3f, %.3f)\n", est.getNumMaxCliqueInliers(),
+                std::atan2(T(1, 0), T(0, 0)), th, T(0, 3), T(1, 3));
+    if (std::fabs(std::atan2(T(1, 0), T(0, 0)) - th) > 1e-3 || std::fabs(T(0, 3) - tx) > 0.05) return 1;
+    try { RadarLoader bad("kitti", "cen2019", 0.6, true, false, ctx); return 1; } catch (const std::invalid_argument &) {}
+    RadarLoader loader("mulran", "cen2019", 0.6, true, false, ctx);
+    (void)loader;
+    std::printf("adapters ok\n");
+    }
+    nrs_ctx_destroy(ctx);
+    return rc;
+}

@@ -45,3 +45,18 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dp, f), errors="replace").read()
                 assert "pyoracle" not in text and "oracle/" not in text.replace("oracle/sc_ref.c", "").replace(
                     "oracle/solver_ref", "").replace("oracle/frontend", ""), f
+
+
+def test_cpp_adapters_compile_and_link(nrs):
+    """The header-only C++ host side (nrs_adapters.hpp) instantiated with minimal Eigen/PCL
+    stand-ins and linked against the library; without a GPU it must refuse loudly (exit 77)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "navtech-radar-slam_b200", "cpp", "adapter_check")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    import torch
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+    else:
+        assert r.returncode == 77 and "no CPU fallback" in r.stdout

@@ -68,9 +68,13 @@ def test_extract_match_solve_parity(nrs, ctx, oracle, synth, F, world, dataset):
     assert np.array_equal(est.last_result["clique"], ro["clique"])
     dth = np.arctan2(T[1, 0], T[0, 0]) - np.arctan2(ro["T"][1, 0], ro["T"][0, 0])
     assert np.hypot(T[0, 3] - ro["T"][0, 3], T[1, 3] - ro["T"][1, 3]) <= 1e-4 and abs(dth) <= 1e-5
-    # and the answer is the planted motion
-    assert abs(np.arctan2(T[1, 0], T[0, 0]) - np.deg2rad(1.0)) < 5e-3
-    assert abs(T[0, 3] - 2.5) < 0.3 and abs(T[1, 3] - 0.1) < 0.3
+    # and the answer is close to the planted motion (loose: on the oxford frame cv::ORB drops one
+    # border keypoint, and the reference's kp_/feat_in_cart_ misalignment that follows -- reproduced
+    # here on purpose -- turns the later matches into 0.6 m-level outliers)
+    assert abs(np.arctan2(T[1, 0], T[0, 0]) - np.deg2rad(1.0)) < 2e-2
+    assert abs(T[0, 3] - 2.5) < 0.5 and abs(T[1, 3] - 0.1) < 0.5
+    if dataset == "oxford":
+        assert g0.handle.info.K_desc < g0.handle.info.K or g1.handle.info.K_desc < g1.handle.info.K
 
 
 def test_cen2019_operator_small_and_adversarial(nrs, ctx, F):

@@ -213,3 +213,13 @@ def test_full_size_properties_10k(sc, ctx, oracle, synth):
         assert shift[k] == os_ and bits([dist[k]])[0] == bits([od])[0]
     assert np.argmin(np.where(np.isnan(dist), 1e9, dist)) == best[1]
     d.close()
+
+
+def test_cpp_adapters_end_to_end():
+    """SCManager / ORORA through the C++ adapters (navtech-radar-slam_b200/cpp/nrs_adapters.hpp)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "navtech-radar-slam_b200", "cpp", "adapter_check")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "adapters ok" in r.stdout
