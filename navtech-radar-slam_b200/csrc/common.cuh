@@ -6,6 +6,8 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/nrs_b200.h"
 
@@ -71,6 +73,7 @@ struct nrs_ctx {
     nrs::DevBuf  scratch[8];           // per-subsystem device scratch (indexed by users)
     nrs::PinBuf  pin[4];               // pinned staging
     void        *frontend = nullptr;   // lazily created front-end static state (maps, tables)
+    std::vector<std::pair<void *, size_t>> frame_pool;   // recycled nrs_frame device blocks (cudaMalloc/cudaFree cost ms)
     void       (*frontend_free)(void *) = nullptr;
 };
 

@@ -102,6 +102,8 @@ int nrs_ctx_destroy(nrs_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->frontend && ctx->frontend_free) ctx->frontend_free(ctx->frontend);
+    for (auto &fb : ctx->frame_pool) cudaFree(fb.first);
+    ctx->frame_pool.clear();
     for (auto &b : ctx->scratch) b.release();
     for (auto &b : ctx->pin) b.release();
     cudaStreamDestroy(ctx->stream);

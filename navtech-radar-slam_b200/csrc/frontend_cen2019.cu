@@ -91,11 +91,11 @@ fe_stats_kernel(const float *__restrict__ fft, int R, int C, double *__restrict_
 __global__ void fe_mean_kernel(const double *__restrict__ partial, int nblocks, double inv_n,
                                float *__restrict__ mean_out)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double s = 0.0;
-        for (int b = 0; b < nblocks; ++b) s += partial[b];
-        *mean_out = (float)(s * inv_n);
-    }
+    // one warp, fixed order: lane l sums partial[l], partial[l+32], ... then a fixed shuffle tree
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 32) s += partial[b];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) *mean_out = (float)(s * inv_n);
 }
 
 // h = s .* (1 - g / maxg) (features.cpp:206-213), all f32; Mat /= double multiplies by (float)(1/maxg)

@@ -392,15 +392,35 @@ static int alloc_frame(nrs_ctx *ctx, int W, nrs_frame **out)
     const size_t o_t = take(FE_KP_CAP * sizeof(long long)), o_kp = take(2 * FE_KP_CAP * sizeof(float));
     const size_t o_kpo = take(2 * FE_KP_CAP * sizeof(float));
     const size_t o_desc = take((size_t)FE_KP_CAP * 32), o_img = take((size_t)W * W);
-    cudaError_t e = cudaMalloc((void **)&f->d_block, off);
-    if (e != cudaSuccess) { delete f; set_error("frame allocation: %s", cudaGetErrorString(e)); return NRS_ENOMEM; }
-    f->block_bytes = off;
+    // recycle a block of a destroyed frame: cudaMalloc / cudaFree synchronise and cost milliseconds
+    for (size_t i = 0; i < ctx->frame_pool.size(); ++i)
+        if (ctx->frame_pool[i].second >= off) {
+            f->d_block = (unsigned char *)ctx->frame_pool[i].first;
+            f->block_bytes = ctx->frame_pool[i].second;
+            ctx->frame_pool.erase(ctx->frame_pool.begin() + i);
+            break;
+        }
+    if (!f->d_block) {
+        cudaError_t e = cudaMalloc((void **)&f->d_block, off);
+        if (e != cudaSuccess) { delete f; set_error("frame allocation: %s", cudaGetErrorString(e)); return NRS_ENOMEM; }
+        f->block_bytes = off;
+    }
     unsigned char *b = f->d_block;
     f->d_polar = (int *)(b + o_polar); f->d_cart_pre = (double *)(b + o_pre); f->d_t_pre = (long long *)(b + o_tpre);
     f->d_feat = (double *)(b + o_feat); f->d_t = (long long *)(b + o_t); f->d_kp = (float *)(b + o_kp);
     f->d_desc = b + o_desc; f->d_img = b + o_img; f->d_kp_orb = (float *)(b + o_kpo);
     *out = f;
     return NRS_OK;
+}
+
+// called with ctx->mu held
+static void frame_release_locked(nrs_frame *f)
+{
+    if (f->d_block) {
+        if (f->ctx->frame_pool.size() < 8) f->ctx->frame_pool.emplace_back(f->d_block, f->block_bytes);
+        else cudaFree(f->d_block);
+    }
+    delete f;
 }
 
 }  // namespace nrs
@@ -518,8 +538,8 @@ int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw, int R, int row_pitch, co
     NRS_CUDA(cudaMemcpyAsync(S->d_times, times, R * sizeof(long long), cudaMemcpyHostToDevice, st));
 
     // ---- device pipeline ------------------------------------------------------------------------
-    if ((rc = fe_decode_device(ctx, *S, R, C, row_pitch))) { nrs_frame_destroy(f); return rc; }
-    if ((rc = fe_cen2019_device(ctx, *S, R, C, p->max_points, p->min_range, f->d_polar))) { nrs_frame_destroy(f); return rc; }
+    if ((rc = fe_decode_device(ctx, *S, R, C, row_pitch))) { frame_release_locked(f); return rc; }
+    if ((rc = fe_cen2019_device(ctx, *S, R, C, p->max_points, p->min_range, f->d_polar))) { frame_release_locked(f); return rc; }
     fe_remap_kernel<<<(W * W + 255) / 256, 256, 0, st>>>(S->d_fft, R, C, S->d_theta, S->d_sx, S->d_az, S->d_azsort,
                                                         S->d_azidx, n_sorted, p->navtech_version == 0,
                                                         p->interpolate_crossover, W, S->d_cart,
@@ -527,7 +547,7 @@ int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw, int R, int row_pitch, co
     NRS_LAUNCHED();
     fe_to_u8_kernel<<<(W * W + 255) / 256, 256, 0, st>>>(S->d_cart, W * W, S->d_counts, f->d_img);
     NRS_LAUNCHED();
-    if ((rc = fe_points_voxel_bev_device(ctx, *S, f))) { nrs_frame_destroy(f); return rc; }
+    if ((rc = fe_points_voxel_bev_device(ctx, *S, f))) { frame_release_locked(f); return rc; }
     dim3 bg((W + 255) / 256, W);
     fe_blur_row_kernel<<<bg, 256, 0, st>>>(f->d_img, W, S->d_rowbuf);
     NRS_LAUNCHED();
@@ -539,7 +559,7 @@ int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw, int R, int row_pitch, co
     NRS_CUDA(cudaStreamSynchronize(st));
     f->counts = *S->h_counts;
     if (f->counts.overflow) {
-        nrs_frame_destroy(f);
+        frame_release_locked(f);
         set_error("nrs_frame_extract: more than %d keypoints", FE_KP_CAP);
         return NRS_ECAPACITY;
     }
@@ -550,9 +570,13 @@ int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw, int R, int row_pitch, co
 int nrs_frame_destroy(nrs_frame *f)
 {
     if (!f) return NRS_OK;
-    cudaSetDevice(f->ctx->device);
-    cudaStreamSynchronize(f->ctx->stream);
-    if (f->d_block) cudaFree(f->d_block);
+    // every consumer of a frame's buffers runs on the context stream and the entry points that
+    // enqueue them synchronise before returning, so the block can be recycled immediately
+    if (f->d_block) {
+        std::lock_guard<std::mutex> lk(f->ctx->mu);
+        if (f->ctx->frame_pool.size() < 8) f->ctx->frame_pool.emplace_back(f->d_block, f->block_bytes);
+        else { cudaSetDevice(f->ctx->device); cudaFree(f->d_block); }
+    }
     delete f;
     return NRS_OK;
 }

@@ -19,6 +19,7 @@
 // stages per warp, so the next two keyframes stream in while the current one is scored.
 // Bound: HBM.  Algorithmic bytes per keyframe = 9600 (f64 20x60, the reference's
 // MatrixXd); per query = 9600*D + 9600 + 16.
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
@@ -356,6 +357,377 @@ sc_search_kernel(const double *__restrict__ db, const double *__restrict__ query
     }
 }
 
+
+// =================================================================================================
+// K10 v2: f32 filter + f64 certification
+// =================================================================================================
+// The reference's arithmetic is f64, but both of its decisions per keyframe are arg-mins:
+//   (B) s0 = argmin_s ||vq - shift(vk, s)||            over 60 shifts   (fastAlignUsingVkey)
+//   (C) argmin over the 7 shifts around s0 of distDirectSC              (distanceBtnScanContext)
+// v2 evaluates every candidate of both arg-mins in f32 (FFMA, 2x the FP64 rate, half the shared
+// memory traffic), keeps the ones within a rigorous error bound of the f32 minimum, and re-evaluates
+// ONLY those in the reference's exact f64 order.  The winner and its value are therefore bit-identical
+// to v1 / the oracle; the FP64 pipe does ~1/4 of the work.
+//   bound B: |n32_s - n64_s| <= 2^-16.8 (|vq|^2+|vk|^2)  (inputs rounded to f32, 60 fused terms);
+//            kept: n32_s <= min + 2^-11 (|vq|^2 + |vk|^2)                     (28x margin over 2e)
+//   bound C: |d32 - d64| <= 2^-17.2                      (unit-norm cosine terms, <= 60 of them);
+//            kept: d32 <= min + 2^-13                                          (9x margin over 2e)
+// A non-finite f32 intermediate (inputs beyond ~1e18) keeps every candidate, i.e. falls back to f64.
+constexpr int W2 = 16;                   // warps per CTA
+constexpr int THREADS2 = W2 * 32;
+constexpr int QS32 = 24;                 // padded f32 query column stride (floats): LDS.128 conflict-free
+constexpr float EPS_B = 4.8828125e-4f;   // 2^-11
+constexpr float EPS_C = 1.220703125e-4f; // 2^-13
+
+struct Warp2Smem {
+    double   tile[DESC];                 // TMA destination (kept until the keyframe is finished)
+    double   vk2[2 * S];                 // keyframe sector key, doubled (f64, for certification)
+    double   kn[S];                      // keyframe column norms (f64)
+    double   scr[S];                     // certification scratch (squared diffs / similarities)
+    float    vk2f[2 * S];                // f32 copy, doubled
+    uint64_t bar;
+    uint64_t pad;
+};
+
+struct Block2Smem {
+    double q64[S * QSTRIDE];             // query, f64, padded columns (certification)
+    float  q32[S * QS32];                // query, f32, padded columns (filter)
+    double qn[S], qv[S];
+    float  qnf[S], qvf[S];
+    Warp2Smem w[W2];
+    double red_d[W2];
+    int    red_pos[W2], red_idx[W2], red_s[W2];
+    int    is_last;
+    float  qv_norm2;                     // |vq|^2 (f32)
+    unsigned long long qzero;            // bit c set <=> query column c has zero norm
+};
+
+__device__ __forceinline__ float warp_min_f(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__global__ void __launch_bounds__(THREADS2, 1)
+sc_search2_kernel(const double *__restrict__ db, const double *__restrict__ query,
+                  const int32_t *__restrict__ cand, int first, int n_items, int idx_offset,
+                  double *__restrict__ dist_all, int32_t *__restrict__ shift_all,
+                  BlockResult *__restrict__ block_results, unsigned int *__restrict__ ticket,
+                  nrs_sc_result *__restrict__ final_result)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Block2Smem &sm = *reinterpret_cast<Block2Smem *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Warp2Smem &ws = sm.w[warp];
+    const int gw = blockIdx.x * W2 + warp;
+    const int nw = gridDim.x * W2;
+
+    if (lane == 0) {
+        nrs::mbar_init(&ws.bar, 1);
+        nrs::fence_mbar_init();
+        if (gw < n_items) {
+            const int kf = cand ? cand[gw] : first + gw;
+            nrs::mbar_expect_tx(&ws.bar, DESC * 8);
+            nrs::tma_load_1d(ws.tile, db + (size_t)kf * DESC, DESC * 8, &ws.bar);
+        }
+    }
+    // ---- stage the query in f64 and f32 ---------------------------------------------------------
+    for (int i = threadIdx.x; i < DESC; i += THREADS2) {
+        const int c = i / R, r = i - c * R;
+        const double v = query[i];
+        sm.q64[c * QSTRIDE + r] = v;
+        sm.q32[c * QS32 + r] = (float)v;
+    }
+    if (threadIdx.x == 0) sm.qzero = 0ull;
+    __syncthreads();
+    if (threadIdx.x < S) {
+        double v[R], sq[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { v[r] = sm.q64[threadIdx.x * QSTRIDE + r]; sq[r] = v[r] * v[r]; }
+        const double mean = redux20(v) / (double)R, nrm = sqrt(redux20(sq));
+        sm.qv[threadIdx.x] = mean;  sm.qvf[threadIdx.x] = (float)mean;
+        sm.qn[threadIdx.x] = nrm;   sm.qnf[threadIdx.x] = (float)nrm;
+        if (nrm == 0) atomicOr(&sm.qzero, 1ull << threadIdx.x);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a2 = 0.f;
+        for (int c = 0; c < S; ++c) a2 = fmaf(fabsf(sm.qvf[c]), fabsf(sm.qvf[c]), a2);
+        sm.qv_norm2 = a2 * 1.0001f;
+    }
+    __syncthreads();
+    const unsigned long long qzero = sm.qzero;
+    const float A2 = sm.qv_norm2;
+
+    double best_d = SENTINEL;
+    int best_pos = 0x7fffffff, best_idx = 0, best_s = 0;
+    const bool own = lane < S / 2;
+    const int c0 = own ? 2 * lane : 0;
+
+    for (int t = 0;; ++t) {
+        const int item = gw + t * nw;
+        if (item >= n_items) break;
+        const int kf = cand ? cand[item] : first + item;
+        nrs::mbar_wait(&ws.bar, t & 1);
+
+        // ---- phase A (f64): column means and norms; f32 copies of this lane's two columns -------
+        float kf0[R], kf1[R];
+        float knf0, knf1;
+        {
+            double k0[R], k1[R];
+            const double2 *src = reinterpret_cast<const double2 *>(&ws.tile[c0 * R]);
+#pragma unroll
+            for (int r = 0; r < R / 2; ++r) {
+                const double2 a = src[r], b = src[R / 2 + r];
+                k0[2 * r] = a.x; k0[2 * r + 1] = a.y; k1[2 * r] = b.x; k1[2 * r + 1] = b.y;
+            }
+            double sq[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) sq[r] = k0[r] * k0[r];
+            const double kn0 = sqrt(redux20(sq));
+#pragma unroll
+            for (int r = 0; r < R; ++r) sq[r] = k1[r] * k1[r];
+            const double kn1 = sqrt(redux20(sq));
+            const double m0 = redux20(k0) / (double)R, m1 = redux20(k1) / (double)R;
+            if (own) {
+                ws.vk2[c0] = m0; ws.vk2[c0 + S] = m0; ws.vk2[c0 + 1] = m1; ws.vk2[c0 + 1 + S] = m1;
+                ws.vk2f[c0] = (float)m0; ws.vk2f[c0 + S] = (float)m0;
+                ws.vk2f[c0 + 1] = (float)m1; ws.vk2f[c0 + 1 + S] = (float)m1;
+                ws.kn[c0] = kn0; ws.kn[c0 + 1] = kn1;
+            }
+            knf0 = (float)kn0; knf1 = (float)kn1;
+#pragma unroll
+            for (int r = 0; r < R; ++r) { kf0[r] = (float)k0[r]; kf1[r] = (float)k1[r]; }
+        }
+        // zero-norm key columns as a 60-bit mask (exact: from the f64 norms)
+        __syncwarp();
+        unsigned long long kzero = 0ull;
+        {
+            const bool za = own && (knf0 == 0.0f) && (ws.kn[c0] == 0);
+            const bool zb = own && (knf1 == 0.0f) && (ws.kn[c0 + 1] == 0);
+            const unsigned int ma = __ballot_sync(0xffffffffu, za), mb = __ballot_sync(0xffffffffu, zb);
+            // lane l owns columns 2l, 2l+1: interleave the two 30-bit masks
+            for (int l = 0; l < S / 2; ++l) {
+                kzero |= (unsigned long long)((ma >> l) & 1u) << (2 * l);
+                kzero |= (unsigned long long)((mb >> l) & 1u) << (2 * l + 1);
+            }
+        }
+
+        // ---- phase B filter (f32): one shift per lane, two rounds -----------------------------------
+        float nB[2];
+        float B2 = 0.f;
+#pragma unroll
+        for (int rnd = 0; rnd < 2; ++rnd) {
+            const int s = lane + 32 * rnd;
+            float acc0 = 0.f, acc1 = 0.f, b2 = 0.f;
+            if (s < S) {
+                const float *vk = &ws.vk2f[S - s];
+#pragma unroll 10
+                for (int i = 0; i < S; i += 2) {
+                    const float d0 = sm.qvf[i] - vk[i], d1 = sm.qvf[i + 1] - vk[i + 1];
+                    acc0 = fmaf(d0, d0, acc0);
+                    acc1 = fmaf(d1, d1, acc1);
+                    if (rnd == 0) b2 = fmaf(vk[i], vk[i], fmaf(vk[i + 1], vk[i + 1], b2));
+                }
+            }
+            nB[rnd] = (s < S) ? acc0 + acc1 : INFINITY;
+            if (rnd == 0) B2 = b2;
+        }
+        B2 = __shfl_sync(0xffffffffu, B2, 0) * 1.0001f;          // |vk|^2 (lane 0: shift 0 sees all of vk)
+        const float mB = warp_min_f(fminf(nB[0], nB[1]));
+        const float thrB = mB + EPS_B * (A2 + B2);
+        const bool finiteB = (mB == mB) && (thrB < INFINITY);
+        unsigned int candB[2];
+        candB[0] = __ballot_sync(0xffffffffu, !finiteB || nB[0] <= thrB);
+        candB[1] = __ballot_sync(0xffffffffu, (lane + 32 < S) && (!finiteB || nB[1] <= thrB));
+        if (!finiteB) { candB[0] = 0xffffffffu; candB[1] = 0x0fffffffu; }
+
+        // ---- phase B certification (f64, reference order): candidates in ascending shift ---------------
+        double fa_n = SENTINEL;
+        int s0 = 0;
+#pragma unroll
+        for (int rnd = 0; rnd < 2; ++rnd) {
+            unsigned int m = candB[rnd];
+            while (m) {
+                const int s = __ffs(m) - 1 + 32 * rnd;
+                m &= m - 1;
+                const double *vk = &ws.vk2[S - s];
+                __syncwarp();
+                for (int i = lane; i < S; i += 32) { const double d = sm.qv[i] - vk[i]; ws.scr[i] = d * d; }
+                __syncwarp();
+                double acc = 0.0;
+                if (lane < 4) {
+                    acc = ws.scr[lane];
+#pragma unroll
+                    for (int i = 4; i < S; i += 4) acc += ws.scr[lane + i];
+                }
+                const double a2 = __shfl_sync(0xffffffffu, acc, 2), a3 = __shfl_sync(0xffffffffu, acc, 3);
+                const double a1 = __shfl_sync(0xffffffffu, acc, 1), a0 = __shfl_sync(0xffffffffu, acc, 0);
+                const double nrm = sqrt((a0 + a2) + (a1 + a3));
+                if (nrm < fa_n) { fa_n = nrm; s0 = s; }          // ascending s + strict '<' == reference scan
+            }
+        }
+
+        // ---- phase C filter (f32): 7 shifts x 60 columns ------------------------------------------------
+        float part[NSHIFT];
+#pragma unroll
+        for (int d = 0; d < NSHIFT; ++d) part[d] = 0.f;
+        if (own) {
+            int qc = c0 + s0 - RADIUS + S;
+            qc = qc >= S ? qc - S : qc;
+            qc = qc >= S ? qc - S : qc;
+#pragma unroll
+            for (int tt = 0; tt < NSHIFT + 1; ++tt) {
+                float qcol[R];
+                const float4 *src = reinterpret_cast<const float4 *>(&sm.q32[qc * QS32]);
+#pragma unroll
+                for (int r = 0; r < R / 4; ++r) {
+                    const float4 a = src[r];
+                    qcol[4 * r] = a.x; qcol[4 * r + 1] = a.y; qcol[4 * r + 2] = a.z; qcol[4 * r + 3] = a.w;
+                }
+                const float qn_ = sm.qnf[qc];
+                if (tt <= NSHIFT - 1) {
+                    float dot = 0.f;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) dot = fmaf(qcol[r], kf0[r], dot);
+                    const float den = qn_ * knf0;
+                    part[tt] += (den > 0.f) ? __fdividef(dot, den) : 0.f;
+                }
+                if (tt >= 1) {
+                    float dot = 0.f;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) dot = fmaf(qcol[r], kf1[r], dot);
+                    const float den = qn_ * knf1;
+                    part[tt - 1] += (den > 0.f) ? __fdividef(dot, den) : 0.f;
+                }
+                qc = (qc + 1 == S) ? 0 : qc + 1;
+            }
+        }
+        float dC = INFINITY;       // lane d (< 7) ends up with the approximate distance of shift slot d
+        int cntC = 0;
+#pragma unroll
+        for (int d = 0; d < NSHIFT; ++d) {
+            float v = part[d];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == d) {
+                int s = s0 + d - RADIUS + S;
+                s = s >= S ? s - S : s;
+                s = s >= S ? s - S : s;
+                // key column paired with query column c is (c - s) mod 60: rotate the key mask up by s
+                const unsigned long long mask60 = (1ull << S) - 1ull;
+                const unsigned long long krot = ((kzero << s) | (kzero >> (S - s))) & mask60;
+                cntC = S - __popcll((qzero | (s ? krot : kzero)) & mask60);
+                dC = cntC ? 1.0f - v / (float)cntC : INFINITY;
+            }
+        }
+        float mC = (lane < NSHIFT) ? dC : INFINITY;
+        const bool finC = !(lane < NSHIFT) || (dC == dC);
+        const bool allfin = __all_sync(0xffffffffu, finC);
+        mC = warp_min_f(mC);
+        unsigned int candC = __ballot_sync(0xffffffffu, lane < NSHIFT && cntC > 0 && (!allfin || dC <= mC + EPS_C));
+
+        // ---- phase C certification (f64, reference order) -------------------------------------------------
+        double dd = SENTINEL;
+        int ds = 0;
+        while (candC) {
+            const int d = __ffs(candC) - 1;
+            candC &= candC - 1;
+            int s = s0 + d - RADIUS + S;
+            s = s >= S ? s - S : s;
+            s = s >= S ? s - S : s;
+            __syncwarp();
+            for (int c = lane; c < S; c += 32) {
+                int kc = c - s;
+                kc = kc < 0 ? kc + S : kc;
+                double a[R], b[R];
+                const double2 *qa = reinterpret_cast<const double2 *>(&sm.q64[c * QSTRIDE]);
+                const double2 *kb = reinterpret_cast<const double2 *>(&ws.tile[kc * R]);
+#pragma unroll
+                for (int r = 0; r < R / 2; ++r) {
+                    const double2 x = qa[r], y = kb[r];
+                    a[2 * r] = x.x; a[2 * r + 1] = x.y; b[2 * r] = y.x; b[2 * r + 1] = y.y;
+                }
+                ws.scr[c] = redux20_dot(a, b) / (sm.qn[c] * ws.kn[kc]);
+            }
+            __syncwarp();
+            double dist = SENTINEL;
+            if (lane == 0) {
+                double sum = 0.0;
+                int cnt = 0;
+                int kc = S - s;
+                kc = kc == S ? 0 : kc;
+                for (int c = 0; c < S; ++c) {
+                    if (!((sm.qn[c] == 0) | (ws.kn[kc] == 0))) { sum = sum + ws.scr[c]; cnt = cnt + 1; }
+                    kc = (kc + 1 == S) ? 0 : kc + 1;
+                }
+                dist = 1.0 - sum / (double)cnt;
+            }
+            dist = __shfl_sync(0xffffffffu, dist, 0);
+            if (better(dist, s, dd, ds)) { dd = dist; ds = s; }   // lexicographic (dist, shift) == ascending-shift scan
+        }
+        __syncwarp();
+        // the tile is no longer needed: stream in this warp's next keyframe
+        if (lane == 0) {
+            const int item2 = item + nw;
+            if (item2 < n_items) {
+                const int kf2 = cand ? cand[item2] : first + item2;
+                nrs::fence_proxy_async();
+                nrs::mbar_expect_tx(&ws.bar, DESC * 8);
+                nrs::tma_load_1d(ws.tile, db + (size_t)kf2 * DESC, DESC * 8, &ws.bar);
+            }
+            if (dist_all) dist_all[item] = dd;
+            if (shift_all) shift_all[item] = ds;
+            if (dd < best_d) { best_d = dd; best_pos = item; best_idx = kf; best_s = ds; }
+        }
+    }
+
+    // ---- block reduce, then last-block-done grid reduce (same as v1) --------------------------------
+    if (lane == 0) { sm.red_d[warp] = best_d; sm.red_pos[warp] = best_pos; sm.red_idx[warp] = best_idx; sm.red_s[warp] = best_s; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double d = sm.red_d[0];
+        int p = sm.red_pos[0], ix = sm.red_idx[0], sh = sm.red_s[0];
+        for (int w = 1; w < W2; ++w)
+            if (better(sm.red_d[w], sm.red_pos[w], d, p)) { d = sm.red_d[w]; p = sm.red_pos[w]; ix = sm.red_idx[w]; sh = sm.red_s[w]; }
+        BlockResult br;
+        br.dist = d; br.pos = p; br.idx = ix; br.shift = sh; br.pad = 0;
+        block_results[blockIdx.x] = br;
+        __threadfence();
+        const unsigned int tk = atomicAdd(ticket, 1u);
+        sm.is_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (sm.is_last && warp == 0) {
+        __threadfence();
+        double d = SENTINEL;
+        int p = 0x7fffffff, ix = 0, sh = 0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) {
+            const volatile BlockResult *br = block_results + b;
+            const double bd = br->dist;
+            const int bp = br->pos;
+            if (better(bd, bp, d, p)) { d = bd; p = bp; ix = br->idx; sh = br->shift; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, d, off);
+            const int op = __shfl_xor_sync(0xffffffffu, p, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, ix, off);
+            const int os = __shfl_xor_sync(0xffffffffu, sh, off);
+            if (better(od, op, d, p)) { d = od; p = op; ix = oi; sh = os; }
+        }
+        if (lane == 0) {
+            nrs_sc_result res;
+            res.dist = d;
+            res.idx = (d < SENTINEL) ? ix + idx_offset : 0;
+            res.shift = sh;
+            *final_result = res;
+            *ticket = 0u;
+        }
+    }
+}
+
 // ---- makeScancontext (Scancontext.cpp:151-195) ---------------------------------------------
 __device__ __forceinline__ int enc_f32(float f)
 {
@@ -509,6 +881,18 @@ struct nrs_sc_db {
 namespace {
 
 int search_smem_bytes() { return (int)sizeof(BlockSmem); }
+int search2_smem_bytes() { return (int)sizeof(Block2Smem); }
+
+// NRS_SC_KERNEL=1 selects the all-f64 v1 kernel (kept for A/B measurements); default is v2
+int search_version()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("NRS_SC_KERNEL");
+        v = (e && e[0] == '1') ? 1 : 2;
+    }
+    return v;
+}
 
 int configure_search_kernel()
 {
@@ -516,6 +900,8 @@ int configure_search_kernel()
     if (!done) {
         NRS_CUDA(cudaFuncSetAttribute(sc_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       search_smem_bytes()));
+        NRS_CUDA(cudaFuncSetAttribute(sc_search2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      search2_smem_bytes()));
         done = 1;
     }
     return NRS_OK;
@@ -529,11 +915,19 @@ int launch_search(nrs_ctx *ctx, const double *d_db, const double *d_query, const
 {
     int rc = configure_search_kernel();
     if (rc) return rc;
-    int blocks = (n_items + WARPS - 1) / WARPS;
-    blocks = std::max(1, std::min(blocks, max_blocks));
-    sc_search_kernel<<<blocks, THREADS, search_smem_bytes(), ctx->stream>>>(
-        d_db, d_query, d_cand, first, n_items, idx_offset, d_dist_all, d_shift_all, d_block,
-        d_ticket, d_result);
+    if (search_version() == 1) {
+        int blocks = (n_items + WARPS - 1) / WARPS;
+        blocks = std::max(1, std::min(blocks, max_blocks));
+        sc_search_kernel<<<blocks, THREADS, search_smem_bytes(), ctx->stream>>>(
+            d_db, d_query, d_cand, first, n_items, idx_offset, d_dist_all, d_shift_all, d_block,
+            d_ticket, d_result);
+    } else {
+        int blocks = (n_items + W2 - 1) / W2;
+        blocks = std::max(1, std::min(blocks, max_blocks));
+        sc_search2_kernel<<<blocks, THREADS2, search2_smem_bytes(), ctx->stream>>>(
+            d_db, d_query, d_cand, first, n_items, idx_offset, d_dist_all, d_shift_all, d_block,
+            d_ticket, d_result);
+    }
     NRS_LAUNCHED();
     return NRS_OK;
 }

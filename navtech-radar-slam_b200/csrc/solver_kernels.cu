@@ -188,10 +188,29 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restri
     int exact = 1;
     int depth = 0, cur_n = 0;
     uint32_t P = full;                          // vertex set of the current depth (word `lane`)
+    // peel to the best_n-core: a clique larger than the greedy one only contains vertices with at
+    // least best_n neighbours inside the surviving set (same pruning as oracle/solver_ref.c)
+    for (bool changed = true; changed;) {
+        changed = false;
+        for (int v = 0; v < N; ++v) {
+            const uint32_t pw = __shfl_sync(0xffffffffu, P, v >> 5);
+            if (!((pw >> (v & 31)) & 1u)) continue;
+            int c = __popc(sadj[v * WORDS + lane] & P);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (c < best_n) {
+                if (lane == (v >> 5)) P &= ~(1u << (v & 31));
+                changed = true;
+            }
+        }
+    }
     stackP[lane] = P;
-    int n = warp_color_sort(P, ordS, colS, sadj, lane);
-    int idx = n - 1;
-    ++nodes;
+    int n = 0, idx = -1;
+    if (__ballot_sync(0xffffffffu, P != 0)) {
+        n = warp_color_sort(P, ordS, colS, sadj, lane);
+        idx = n - 1;
+        ++nodes;
+    }
     __syncwarp();
     for (;;) {
         bool pop = false;

@@ -202,7 +202,20 @@ int orora_max_clique(const uint64_t *adj_in, int N, int W, int *clique, long lon
         S.best_n = n;
         for (int w = 0; w < W; ++w) P[w] = 0;
         for (int i = 0; i < N; ++i) P[i >> 6] |= 1ull << (i & 63);
-        mc_expand(&S, 0, P);
+        /* a clique larger than the greedy one only contains vertices with >= best_n neighbours inside
+         * the surviving set: peel everything else off (the best_n-core; unique whatever the order) */
+        for (int changed = 1; changed;) {
+            changed = 0;
+            for (int v = 0; v < N; ++v) {
+                if (!(P[v >> 6] >> (v & 63) & 1ull)) continue;
+                int c = 0;
+                for (int w = 0; w < W; ++w) c += __builtin_popcountll(adj[(size_t)v * W + w] & P[w]);
+                if (c < S.best_n) { P[v >> 6] &= ~(1ull << (v & 63)); changed = 1; }
+            }
+        }
+        int any = 0;
+        for (int w = 0; w < W; ++w) any |= (P[w] != 0);
+        if (any) mc_expand(&S, 0, P);
         free(P);
     }
     int n = S.best_n;
