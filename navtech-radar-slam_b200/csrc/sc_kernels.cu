@@ -369,14 +369,14 @@ sc_search_kernel(const double *__restrict__ db, const double *__restrict__ query
 // ONLY those in the reference's exact f64 order.  The winner and its value are therefore bit-identical
 // to v1 / the oracle; the FP64 pipe does ~1/4 of the work.
 //   bound B: |n32_s - n64_s| <= 2^-16.8 (|vq|^2+|vk|^2)  (inputs rounded to f32, 60 fused terms);
-//            kept: n32_s <= min + 2^-11 (|vq|^2 + |vk|^2)                     (28x margin over 2e)
+//            kept: n32_s <= min + 2^-13 (|vq|^2 + |vk|^2)                     (5x margin over 2e)
 //   bound C: |d32 - d64| <= 2^-17.2                      (unit-norm cosine terms, <= 60 of them);
 //            kept: d32 <= min + 2^-13                                          (9x margin over 2e)
 // A non-finite f32 intermediate (inputs beyond ~1e18) keeps every candidate, i.e. falls back to f64.
 constexpr int W2 = 16;                   // warps per CTA
 constexpr int THREADS2 = W2 * 32;
 constexpr int QS32 = 24;                 // padded f32 query column stride (floats): LDS.128 conflict-free
-constexpr float EPS_B = 4.8828125e-4f;   // 2^-11
+constexpr float EPS_B = 1.220703125e-4f; // 2^-13
 constexpr float EPS_C = 1.220703125e-4f; // 2^-13
 
 struct Warp2Smem {
@@ -384,7 +384,8 @@ struct Warp2Smem {
     double   vk2[2 * S];                 // keyframe sector key, doubled (f64, for certification)
     double   kn[S];                      // keyframe column norms (f64)
     double   scr[S];                     // certification scratch (squared diffs / similarities)
-    float    vk2f[2 * S];                // f32 copy, doubled
+    float    vkf[4][2 * S + 4];          // f32 copies, doubled; copy m holds vk[(j + m) mod 60] so that every
+                                         // lane's window starts 16-byte aligned (LDS.128)
     uint64_t bar;
     uint64_t pad;
 };
@@ -393,7 +394,8 @@ struct Block2Smem {
     double q64[S * QSTRIDE];             // query, f64, padded columns (certification)
     float  q32[S * QS32];                // query, f32, padded columns (filter)
     double qn[S], qv[S];
-    float  qnf[S], qvf[S];
+    float  qnf[S];
+    __align__(16) float qvf[S];
     Warp2Smem w[W2];
     double red_d[W2];
     int    red_pos[W2], red_idx[W2], red_s[W2];
@@ -492,8 +494,18 @@ sc_search2_kernel(const double *__restrict__ db, const double *__restrict__ quer
             const double m0 = redux20(k0) / (double)R, m1 = redux20(k1) / (double)R;
             if (own) {
                 ws.vk2[c0] = m0; ws.vk2[c0 + S] = m0; ws.vk2[c0 + 1] = m1; ws.vk2[c0 + 1 + S] = m1;
-                ws.vk2f[c0] = (float)m0; ws.vk2f[c0 + S] = (float)m0;
-                ws.vk2f[c0 + 1] = (float)m1; ws.vk2f[c0 + 1 + S] = (float)m1;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    // copy m, index j holds vk[(j + m) mod 60]  =>  vk[c] lands at j = c - m (+60, +120)
+                    const float f0 = (float)m0, f1 = (float)m1;
+                    int j0 = c0 - m, j1 = c0 + 1 - m;
+                    if (j0 < 0) j0 += S;
+                    if (j1 < 0) j1 += S;
+                    ws.vkf[m][j0] = f0; ws.vkf[m][j0 + S] = f0;
+                    ws.vkf[m][j1] = f1; ws.vkf[m][j1 + S] = f1;
+                    if (j0 + 2 * S < 2 * S + 4) ws.vkf[m][j0 + 2 * S] = f0;
+                    if (j1 + 2 * S < 2 * S + 4) ws.vkf[m][j1 + 2 * S] = f1;
+                }
                 ws.kn[c0] = kn0; ws.kn[c0 + 1] = kn1;
             }
             knf0 = (float)kn0; knf1 = (float)kn1;
@@ -514,27 +526,33 @@ sc_search2_kernel(const double *__restrict__ db, const double *__restrict__ quer
             }
         }
 
-        // ---- phase B filter (f32): one shift per lane, two rounds -----------------------------------
+        // ---- phase B filter (f32): one shift per lane, two rounds; ||a - shift(b,s)||^2 =
+        //      |a|^2 + |b|^2 - 2 corr(s), corr by FFMA over 16-byte aligned windows -----------------------
         float nB[2];
-        float B2 = 0.f;
+        float B2;
+        {
+            float b2 = own ? fmaf(ws.vkf[0][c0], ws.vkf[0][c0], ws.vkf[0][c0 + 1] * ws.vkf[0][c0 + 1]) : 0.f;
 #pragma unroll
-        for (int rnd = 0; rnd < 2; ++rnd) {
-            const int s = lane + 32 * rnd;
-            float acc0 = 0.f, acc1 = 0.f, b2 = 0.f;
-            if (s < S) {
-                const float *vk = &ws.vk2f[S - s];
-#pragma unroll 10
-                for (int i = 0; i < S; i += 2) {
-                    const float d0 = sm.qvf[i] - vk[i], d1 = sm.qvf[i + 1] - vk[i + 1];
-                    acc0 = fmaf(d0, d0, acc0);
-                    acc1 = fmaf(d1, d1, acc1);
-                    if (rnd == 0) b2 = fmaf(vk[i], vk[i], fmaf(vk[i + 1], vk[i + 1], b2));
-                }
+            for (int o = 16; o > 0; o >>= 1) b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+            B2 = b2;
+            // window of shift s starts at vk index (60 - s): copy m = (60 - s) & 3, aligned index (60 - s) - m
+            const int o0 = S - lane, o1 = S - (lane + 32 < S ? lane + 32 : lane);
+            const float4 *w0 = reinterpret_cast<const float4 *>(&ws.vkf[o0 & 3][o0 & ~3]);
+            const float4 *w1 = reinterpret_cast<const float4 *>(&ws.vkf[o1 & 3][o1 & ~3]);
+            const float4 *qa = reinterpret_cast<const float4 *>(&sm.qvf[0]);
+            float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
+#pragma unroll
+            for (int i = 0; i < S / 4; ++i) {
+                const float4 a = qa[i], x = w0[i], y = w1[i];
+                c00 = fmaf(a.x, x.x, c00); c01 = fmaf(a.y, x.y, c01);
+                c00 = fmaf(a.z, x.z, c00); c01 = fmaf(a.w, x.w, c01);
+                c10 = fmaf(a.x, y.x, c10); c11 = fmaf(a.y, y.y, c11);
+                c10 = fmaf(a.z, y.z, c10); c11 = fmaf(a.w, y.w, c11);
             }
-            nB[rnd] = (s < S) ? acc0 + acc1 : INFINITY;
-            if (rnd == 0) B2 = b2;
+            nB[0] = (A2 + B2) - 2.0f * (c00 + c01);
+            nB[1] = (lane + 32 < S) ? (A2 + B2) - 2.0f * (c10 + c11) : INFINITY;
         }
-        B2 = __shfl_sync(0xffffffffu, B2, 0) * 1.0001f;          // |vk|^2 (lane 0: shift 0 sees all of vk)
+        B2 = B2 * 1.0001f;
         const float mB = warp_min_f(fminf(nB[0], nB[1]));
         const float thrB = mB + EPS_B * (A2 + B2);
         const bool finiteB = (mB == mB) && (thrB < INFINITY);
@@ -638,7 +656,12 @@ sc_search2_kernel(const double *__restrict__ db, const double *__restrict__ quer
             s = s >= S ? s - S : s;
             s = s >= S ? s - S : s;
             __syncwarp();
+            // effective columns (both norms non-zero), in column order, packed densely into scr[]
+            const unsigned long long mask60 = (1ull << S) - 1ull;
+            const unsigned long long krot = s ? (((kzero << s) | (kzero >> (S - s))) & mask60) : kzero;
+            const unsigned long long eff = ~(qzero | krot) & mask60;
             for (int c = lane; c < S; c += 32) {
+                if (!((eff >> c) & 1ull)) continue;
                 int kc = c - s;
                 kc = kc < 0 ? kc + S : kc;
                 double a[R], b[R];
@@ -649,19 +672,21 @@ sc_search2_kernel(const double *__restrict__ db, const double *__restrict__ quer
                     const double2 x = qa[r], y = kb[r];
                     a[2 * r] = x.x; a[2 * r + 1] = x.y; b[2 * r] = y.x; b[2 * r + 1] = y.y;
                 }
-                ws.scr[c] = redux20_dot(a, b) / (sm.qn[c] * ws.kn[kc]);
+                const int pos = __popcll(eff & ((1ull << c) - 1ull));
+                ws.scr[pos] = redux20_dot(a, b) / (sm.qn[c] * ws.kn[kc]);
             }
             __syncwarp();
             double dist = SENTINEL;
             if (lane == 0) {
-                double sum = 0.0;
-                int cnt = 0;
-                int kc = S - s;
-                kc = kc == S ? 0 : kc;
-                for (int c = 0; c < S; ++c) {
-                    if (!((sm.qn[c] == 0) | (ws.kn[kc] == 0))) { sum = sum + ws.scr[c]; cnt = cnt + 1; }
-                    kc = (kc + 1 == S) ? 0 : kc + 1;
+                const int cnt = __popcll(eff);
+                double sum = 0.0;                       // distDirectSC's left-to-right sum (:83)
+                int i = 0;
+                for (; i + 1 < cnt; i += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(&ws.scr[i]);
+                    sum = sum + v.x;
+                    sum = sum + v.y;
                 }
+                if (i < cnt) sum = sum + ws.scr[i];
                 dist = 1.0 - sum / (double)cnt;
             }
             dist = __shfl_sync(0xffffffffu, dist, 0);

@@ -130,7 +130,7 @@ orora_permute_kernel(const uint32_t *__restrict__ adj, const int *__restrict__ p
 // greedy sequential colouring of the vertex set P (one word per lane); vertices are emitted
 // class by class in increasing index: order[n], color[n] (BBMC / oracle mc_expand).
 __device__ int warp_color_sort(uint32_t Pw, uint16_t *__restrict__ ord, uint16_t *__restrict__ col,
-                               const uint32_t *sadj, int lane)
+                               const uint32_t *sadj, int lane, int &k_out)
 {
     uint32_t Q = Pw;
     int n = 0, k = 0;
@@ -149,7 +149,21 @@ __device__ int warp_color_sort(uint32_t Pw, uint16_t *__restrict__ ord, uint16_t
             ++n;
         }
     }
+    k_out = k;
     return n;
+}
+
+// P (n vertices, each in its own colour class) is a clique: the best leaf below is cur + P
+__device__ void take_clique(const uint16_t *__restrict__ ord, int n, int *__restrict__ cur, int cur_n,
+                            int *__restrict__ best, int &best_n, int lane)
+{
+    if (cur_n + n > best_n) {
+        __syncwarp();
+        for (int i = lane; i < cur_n; i += 32) best[i] = cur[i];
+        for (int i = lane; i < n; i += 32) best[cur_n + i] = ord[i];
+        best_n = cur_n + n;
+        __syncwarp();
+    }
 }
 
 __global__ void __launch_bounds__(32)
@@ -205,11 +219,13 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restri
         }
     }
     stackP[lane] = P;
-    int n = 0, idx = -1;
+    int n = 0, idx = -1, kcol = 0;
     if (__ballot_sync(0xffffffffu, P != 0)) {
-        n = warp_color_sort(P, ordS, colS, sadj, lane);
+        n = warp_color_sort(P, ordS, colS, sadj, lane, kcol);
         idx = n - 1;
         ++nodes;
+        __syncwarp();
+        if (kcol == n) { take_clique(ordS, n, cur, 0, best, best_n, lane); idx = -1; }
     }
     __syncwarp();
     for (;;) {
@@ -242,10 +258,11 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restri
                     if (lane == 0) idxS[depth] = idx;
                     ++depth;
                     P = Pn;
-                    n = warp_color_sort(P, ordS + (size_t)depth * N, colS + (size_t)depth * N, sadj, lane);
+                    n = warp_color_sort(P, ordS + (size_t)depth * N, colS + (size_t)depth * N, sadj, lane, kcol);
                     idx = n - 1;
                     ++nodes;
                     __syncwarp();
+                    if (kcol == n) { take_clique(ordS + (size_t)depth * N, n, cur, cur_n, best, best_n, lane); idx = -1; }
                 }
             }
         }

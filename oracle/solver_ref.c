@@ -142,6 +142,15 @@ static void mc_expand(mc_state *S, int depth, uint64_t *P)
             order[n] = v; color[n] = k; ++n;
         }
     }
+    if (k == n && n > 0) {
+        /* every vertex got its own colour: P is a clique, the best leaf of this subtree is cur + P */
+        if (S->cur_n + n > S->best_n) {
+            memcpy(S->best, S->cur, S->cur_n * sizeof(int));
+            for (int i = 0; i < n; ++i) S->best[S->cur_n + i] = order[i];
+            S->best_n = S->cur_n + n;
+        }
+        return;
+    }
     for (int idx = n - 1; idx >= 0; --idx) {
         if (S->cur_n + color[idx] <= S->best_n) return;
         int v = order[idx];
