@@ -223,20 +223,22 @@ fe_scan_rows_kernel(const unsigned int *__restrict__ claim, const float *__restr
                     int min_range, const FrameCounts *__restrict__ cnt, int *__restrict__ rowcount,
                     int *__restrict__ polar, int cap)
 {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= R) return;
-    const int i = warp;
+    // one 256-thread block per azimuth, one column per thread per step; emission stays ordered by
+    // column through per-warp ballots and a running base
+    __shared__ int wsum[8];
+    __shared__ int running;
+    const int i = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int J = (unsigned int)cnt->j_star;
     const bool none = cnt->j_star < 0;
     const unsigned int *crow = claim + (size_t)i * C;
     const int below = (i == 0) ? R - 1 : i - 1, above = (i + 1 >= R) ? 0 : i + 1;     // :173-178
     const unsigned int *cb = claim + (size_t)below * C, *ca = claim + (size_t)above * C;
     const float *hrow = h + (size_t)i * C;
-    int count = 0;
-    const int base = EMIT ? rowcount[i] : 0;
-    for (int j0 = min_range; j0 < C; j0 += 32) {
-        const int j = j0 + lane;
+    if (threadIdx.x == 0) running = EMIT ? rowcount[i] : 0;
+    __syncthreads();
+    for (int j0 = min_range; j0 < C; j0 += 256) {
+        const int j = j0 + threadIdx.x;
         bool emit = false;
         int max_r = 0;
         if (j < C && !none) {
@@ -263,13 +265,21 @@ fe_scan_rows_kernel(const unsigned int *__restrict__ claim, const float *__restr
             }
         }
         const unsigned int mask = __ballot_sync(0xffffffffu, emit);
+        if (lane == 0) wsum[warp] = __popc(mask);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const int c = wsum[w]; if (w < warp) before += c; total += c; }
+        const int base = running;
         if (EMIT && emit) {
-            const int pos = base + count + __popc(mask & ((1u << lane) - 1u));
+            const int pos = base + before + __popc(mask & ((1u << lane) - 1u));
             if (pos < cap) { polar[2 * pos] = i; polar[2 * pos + 1] = max_r; }
         }
-        count += __popc(mask);
+        __syncthreads();
+        if (threadIdx.x == 0) running = base + total;
+        __syncthreads();
     }
-    if (!EMIT && lane == 0) rowcount[i] = count;
+    if (!EMIT && threadIdx.x == 0) rowcount[i] = running;
 }
 
 // exclusive scan of the per-azimuth counts (R <= 1024), total -> K0
@@ -503,8 +513,7 @@ int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_poin
     NRS_LAUNCHED();
     fe_jstar_fix_kernel<<<1, 32, 0, st>>>(cnt);
     NRS_LAUNCHED();
-    const int warps_per_block = 8;
-    const int sb = (R + warps_per_block - 1) / warps_per_block;
+    const int sb = R;
     fe_scan_rows_kernel<false><<<sb, 256, 0, st>>>(S.d_claim, S.d_h, R, C, min_range, cnt, S.d_rowcount, nullptr, 0);
     NRS_LAUNCHED();
     fe_rowscan_kernel<<<1, 1024, 0, st>>>(S.d_rowcount, R, cnt, FE_KP_CAP);

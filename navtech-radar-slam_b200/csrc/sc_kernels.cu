@@ -381,7 +381,7 @@ constexpr float EPS_C = 1.220703125e-4f; // 2^-13
 
 struct Warp2Smem {
     double   tile[DESC];                 // TMA destination (kept until the keyframe is finished)
-    double   vk2[2 * S];                 // keyframe sector key, doubled (f64, for certification)
+    double   vk[S];                      // keyframe sector key (f64, for certification)
     double   kn[S];                      // keyframe column norms (f64)
     double   scr[S];                     // certification scratch (squared diffs / similarities)
     float    vkf[4][2 * S + 4];          // f32 copies, doubled; copy m holds vk[(j + m) mod 60] so that every
@@ -493,7 +493,7 @@ sc_search2_kernel(const double *__restrict__ db, const double *__restrict__ quer
             const double kn1 = sqrt(redux20(sq));
             const double m0 = redux20(k0) / (double)R, m1 = redux20(k1) / (double)R;
             if (own) {
-                ws.vk2[c0] = m0; ws.vk2[c0 + S] = m0; ws.vk2[c0 + 1] = m1; ws.vk2[c0 + 1 + S] = m1;
+                ws.vk[c0] = m0; ws.vk[c0 + 1] = m1;
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
                     // copy m, index j holds vk[(j + m) mod 60]  =>  vk[c] lands at j = c - m (+60, +120)
@@ -570,9 +570,13 @@ sc_search2_kernel(const double *__restrict__ db, const double *__restrict__ quer
             while (m) {
                 const int s = __ffs(m) - 1 + 32 * rnd;
                 m &= m - 1;
-                const double *vk = &ws.vk2[S - s];
                 __syncwarp();
-                for (int i = lane; i < S; i += 32) { const double d = sm.qv[i] - vk[i]; ws.scr[i] = d * d; }
+                for (int i = lane; i < S; i += 32) {
+                    int j = i - s;
+                    j = j < 0 ? j + S : j;
+                    const double d = sm.qv[i] - ws.vk[j];
+                    ws.scr[i] = d * d;
+                }
                 __syncwarp();
                 double acc = 0.0;
                 if (lane < 4) {

@@ -166,16 +166,20 @@ __device__ void take_clique(const uint16_t *__restrict__ ord, int n, int *__rest
     }
 }
 
-__global__ void __launch_bounds__(32)
+constexpr int CLQ_THREADS = 1024;
+
+__global__ void __launch_bounds__(CLQ_THREADS)
 orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restrict__ stackP,
                     uint16_t *__restrict__ ordS, uint16_t *__restrict__ colS, int *__restrict__ cur,
                     int *__restrict__ best, int *__restrict__ idxS, SolverInfoDev *__restrict__ info,
                     long long node_limit)
 {
     extern __shared__ uint32_t sadj[];
-    const int lane = threadIdx.x;
-    for (int i = lane; i < N * WORDS; i += 32) sadj[i] = adjp[i];
-    __syncwarp();
+    __shared__ uint32_t sP[WORDS];          // current vertex set, one word per entry
+    __shared__ int s_cnt[32], s_idx[32];
+    __shared__ int s_pick, s_changed;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < N * WORDS; i += CLQ_THREADS) sadj[i] = adjp[i];
     // all-vertices mask, word `lane`
     uint32_t full = 0;
     {
@@ -183,41 +187,67 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restri
         if (N >= lo + 32) full = 0xffffffffu;
         else if (N > lo) full = (1u << (N - lo)) - 1u;
     }
-    // ---- greedy lower bound -----------------------------------------------------------------
+    if (warp == 0) sP[lane] = full;
+    __syncthreads();
+    // ---- greedy lower bound, whole block: take the vertex with the most neighbours inside the current
+    //      set (ties: lowest index), shrink the set to its neighbourhood (oracle/solver_ref.c) --------
     int best_n = 0;
-    {
-        uint32_t P = full;
-        unsigned int b;
-        while ((b = __ballot_sync(0xffffffffu, P != 0)) != 0) {
-            const int f = __ffs(b) - 1;
-            const uint32_t wd = __shfl_sync(0xffffffffu, P, f);
-            const int v = f * 32 + __ffs(wd) - 1;
-            if (lane == 0) best[best_n] = v;
-            ++best_n;
-            P &= sadj[v * WORDS + lane];
+    for (;;) {
+        // thread u scores vertex u
+        int c = -1;
+        if (tid < N && ((sP[tid >> 5] >> (tid & 31)) & 1u)) {
+            c = 0;
+            for (int w = 0; w < WORDS; ++w) c += __popc(sadj[tid * WORDS + w] & sP[w]);
         }
+        int bi = tid;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int oc = __shfl_xor_sync(0xffffffffu, c, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oc > c || (oc == c && oi < bi)) { c = oc; bi = oi; }
+        }
+        if (lane == 0) { s_cnt[warp] = c; s_idx[warp] = bi; }
+        __syncthreads();
+        if (warp == 0) {
+            c = s_cnt[lane]; bi = s_idx[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const int oc = __shfl_xor_sync(0xffffffffu, c, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (oc > c || (oc == c && oi < bi)) { c = oc; bi = oi; }
+            }
+            if (lane == 0) s_pick = (c >= 0) ? bi : -1;
+        }
+        __syncthreads();
+        const int v = s_pick;
+        if (v < 0) break;
+        if (tid == 0) best[best_n] = v;
+        ++best_n;
+        if (warp == 0) sP[lane] &= sadj[v * WORDS + lane];
+        __syncthreads();
     }
-    // ---- branch and bound, explicit stack ---------------------------------------------------
+    // ---- peel to the best_n-core (Jacobi sweeps; the fixpoint does not depend on the order) ---------
+    if (warp == 0) sP[lane] = full;
+    __syncthreads();
+    for (;;) {
+        if (tid == 0) s_changed = 0;
+        __syncthreads();
+        bool drop = false;
+        if (tid < N && ((sP[tid >> 5] >> (tid & 31)) & 1u)) {
+            int c = 0;
+            for (int w = 0; w < WORDS; ++w) c += __popc(sadj[tid * WORDS + w] & sP[w]);
+            drop = c < best_n;
+        }
+        __syncthreads();
+        const unsigned int dm = __ballot_sync(0xffffffffu, drop);
+        if (lane == 0 && dm) { sP[warp] &= ~dm; s_changed = 1; }
+        __syncthreads();
+        if (!s_changed) break;
+    }
+    if (warp != 0) return;
+    // ---- warp 0: exact branch and bound on the surviving set ------------------------------------------
+    uint32_t P = sP[lane];
     long long nodes = 0;
     int exact = 1;
     int depth = 0, cur_n = 0;
-    uint32_t P = full;                          // vertex set of the current depth (word `lane`)
-    // peel to the best_n-core: a clique larger than the greedy one only contains vertices with at
-    // least best_n neighbours inside the surviving set (same pruning as oracle/solver_ref.c)
-    for (bool changed = true; changed;) {
-        changed = false;
-        for (int v = 0; v < N; ++v) {
-            const uint32_t pw = __shfl_sync(0xffffffffu, P, v >> 5);
-            if (!((pw >> (v & 31)) & 1u)) continue;
-            int c = __popc(sadj[v * WORDS + lane] & P);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-            if (c < best_n) {
-                if (lane == (v >> 5)) P &= ~(1u << (v & 31));
-                changed = true;
-            }
-        }
-    }
     stackP[lane] = P;
     int n = 0, idx = -1, kcol = 0;
     if (__ballot_sync(0xffffffffu, P != 0)) {
@@ -727,7 +757,7 @@ int nrs_orora_solve(nrs_ctx *ctx, const double *prev_2xN, const double *curr_2xN
     orora_permute_kernel<<<(nthreads + 255) / 256, 256, 0, st>>>(b.d_adj, b.d_perm, N, b.d_adjp);
     NRS_LAUNCHED();
     const long long node_limit = p->clique_node_limit > 0 ? p->clique_node_limit : 2000000;
-    orora_clique_kernel<<<1, 32, (size_t)N * WORDS * 4, st>>>(b.d_adjp, N, b.d_stackP, b.d_ord, b.d_col, b.d_cur,
+    orora_clique_kernel<<<1, CLQ_THREADS, (size_t)N * WORDS * 4, st>>>(b.d_adjp, N, b.d_stackP, b.d_ord, b.d_col, b.d_cur,
                                                              b.d_best, b.d_idx, b.d_info, node_limit);
     NRS_LAUNCHED();
     orora_tail_kernel<<<1, TT, sizeof(TailSmem), st>>>(b.d_src, b.d_tgt, N, b.d_perm, b.d_best, p->noise_bound,

@@ -195,15 +195,21 @@ int orora_max_clique(const uint64_t *adj_in, int N, int W, int *clique, long lon
     S.pool = (uint64_t *)malloc((size_t)3 * (N + 1) * W * sizeof(uint64_t));
     S.ord_pool = (int *)malloc((size_t)(N + 1) * N * sizeof(int));
     S.col_pool = (int *)malloc((size_t)(N + 1) * N * sizeof(int));
-    /* greedy lower bound: from vertex 0 (max degree) keep adding the first compatible vertex */
+    /* greedy lower bound: repeatedly take the vertex with the most neighbours inside the current
+     * candidate set (ties: lowest index in search order), shrink the set to its neighbourhood */
     {
         uint64_t *P = (uint64_t *)malloc(W * sizeof(uint64_t));
         for (int w = 0; w < W; ++w) P[w] = 0;
         for (int i = 0; i < N; ++i) P[i >> 6] |= 1ull << (i & 63);
         int n = 0;
         for (;;) {
-            int v = -1;
-            for (int w = 0; w < W; ++w) if (P[w]) { v = w * 64 + __builtin_ctzll(P[w]); break; }
+            int v = -1, bestc = -1;
+            for (int u = 0; u < N; ++u) {
+                if (!(P[u >> 6] >> (u & 63) & 1ull)) continue;
+                int c = 0;
+                for (int w = 0; w < W; ++w) c += __builtin_popcountll(adj[(size_t)u * W + w] & P[w]);
+                if (c > bestc) { bestc = c; v = u; }
+            }
             if (v < 0) break;
             S.best[n++] = v;
             for (int w = 0; w < W; ++w) P[w] &= adj[(size_t)v * W + w];

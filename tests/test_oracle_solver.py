@@ -128,3 +128,19 @@ def test_doppler_and_gates(oracle, synth):
     # fewer than two mutually consistent pairs -> Identity, valid = false
     r = oracle.orora_solve(np.array([[0.0, 50.0], [0.0, 0.0]]), np.array([[0.0, 5.0], [0.0, 0.0]]))
     assert (not r["valid"]) and np.array_equal(r["T"], np.eye(4))
+
+
+def test_orora_golden(oracle):
+    import importlib
+    import os
+    F = importlib.import_module("oracle.frontend_ref")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "orora_golden.npz"))
+    for tag in ("a", "b"):
+        r = oracle.orora_solve(g[f"sol_{tag}_curr"], g[f"sol_{tag}_prev"])
+        assert np.array_equal(r["clique"], g[f"sol_{tag}_clique"])
+        assert np.array_equal(r["final_inliers"], g[f"sol_{tag}_final"])
+        assert np.allclose(r["T"], g[f"sol_{tag}_T"], rtol=0, atol=1e-12)
+        i = r["info"]
+        assert [i.n_edges, i.M, i.gnc_iters, i.n_rot_inliers] == list(g[f"sol_{tag}_meta"])
+    fft = (g["cen_fft_u8"].astype(np.float64) / 255.0).astype(np.float32)
+    assert np.array_equal(F.cen2019features(fft, 400, 58), g["cen_targets"])

@@ -90,3 +90,22 @@ def test_degenerate_inputs(nrs, ctx, oracle):
     o = oracle.orora_solve(pts, pts)
     assert g["info"].gnc_early_return == o["info"].gnc_early_return
     assert np.allclose(g["T"], o["T"], atol=1e-9)
+
+
+def test_golden_vectors(nrs, ctx):
+    """CUDA path against the committed golden vectors (tests/golden/orora_golden.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "orora_golden.npz"))
+    p = nrs.orora.default_params()
+    p.check_stop_motion = 0
+    p.use_doppler_compensation = 0
+    for tag in ("a", "b"):
+        r = nrs.orora.solve(ctx, g[f"sol_{tag}_prev"], g[f"sol_{tag}_curr"], p)
+        assert np.array_equal(r["clique"], g[f"sol_{tag}_clique"])
+        assert np.array_equal(r["final_inliers"], g[f"sol_{tag}_final"])
+        dm, dr = pose_err(r["T"], g[f"sol_{tag}_T"])
+        assert dm <= TOL_M and dr <= TOL_RAD
+        i = r["info"]
+        assert [i.n_edges, i.M, i.gnc_iters, i.n_rot_inliers] == list(g[f"sol_{tag}_meta"])
+    fft = (g["cen_fft_u8"].astype(np.float64) / 255.0).astype(np.float32)
+    assert np.array_equal(nrs.orora.cen2019features(ctx, fft, 400, 58), g["cen_targets"])
