@@ -113,7 +113,7 @@ def run_reference(args, rank, world):
     O.build()
     db, queries, _ = workload()
     cores = os.cpu_count() or 1
-    os.environ["OMP_NUM_THREADS"] = str(cores)
+    O.lib().oracle_set_threads(cores)
     # a step = one query over a bounded sample of D_s keyframes (cost is uniform per keyframe);
     # D_s is sized so K steps take about a minute, and the rate is scaled back to the 10k DB
     O.sc_search(queries[0], db, want_all=False)
@@ -274,7 +274,7 @@ def run_ours(args, rank, world, local_rank):
                 traffic = None
         # bounded CPU baseline on this box's host cores (oracle port, all threads)
         cores = os.cpu_count() or 1
-        os.environ["OMP_NUM_THREADS"] = str(cores)
+        O.lib().oracle_set_threads(cores)
         O.sc_search(queries[0], db, want_all=False)
         n_cpu, t0 = 0, time.perf_counter()
         while time.perf_counter() - t0 < 10.0 and n_cpu < 2000:

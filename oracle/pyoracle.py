@@ -144,7 +144,7 @@ def sc_search(query, db, first=0, last=None, want_all=True, threads=None):
     shift = np.zeros(db.shape[0], dtype=np.int32) if want_all else None
     bd, bi, bs = C.c_double(), C.c_int(), C.c_int()
     if threads is not None:
-        os.environ["OMP_NUM_THREADS"] = str(threads)
+        lib().oracle_set_threads(int(threads))
     lib().sc_search_range(_p(query), _p(db), first, last,
                           _p(dist) if want_all else None, _p(shift) if want_all else None,
                           C.byref(bd), C.byref(bi), C.byref(bs))

@@ -276,3 +276,13 @@ void sc_knn_bruteforce(const float *keys, int n, int dim, const float *query, in
         if (j < k) { out_d2[j] = d; out_idx[j] = i; }
     }
 }
+
+/* torchrun exports OMP_NUM_THREADS=1; the timed CPU baseline asks for its thread count explicitly */
+#ifdef _OPENMP
+#include <omp.h>
+void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int oracle_max_threads(void) { return omp_get_max_threads(); }
+#else
+void oracle_set_threads(int n) { (void)n; }
+int oracle_max_threads(void) { return 1; }
+#endif
