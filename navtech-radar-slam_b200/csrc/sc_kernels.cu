@@ -404,6 +404,17 @@ struct Block2Smem {
     unsigned long long qzero;            // bit c set <=> query column c has zero norm
 };
 
+// f64 -> f32 for the filter by integer ops (truncation, relative error < 2^-23, covered by the bounds):
+// F2F.F32.F64 runs on the XU pipe at a small fraction of the ALU rate and was the top stall of v2
+__device__ __forceinline__ float d2f_trunc(double x)
+{
+    const unsigned int hi = (unsigned int)__double2hiint(x), lo = (unsigned int)__double2loint(x);
+    const int ef = (int)((hi >> 20) & 0x7ffu) - 1023 + 127;
+    const unsigned int m = ((hi & 0xfffffu) << 3) | (lo >> 29);
+    const unsigned int r = (ef <= 0) ? 0u : (ef >= 255 ? 0x7f800000u : (((unsigned int)ef << 23) | m));
+    return __uint_as_float((hi & 0x80000000u) | r);
+}
+
 __device__ __forceinline__ float warp_min_f(float v)
 {
 #pragma unroll
@@ -497,7 +508,7 @@ sc_search2_kernel(const double *__restrict__ db, const double *__restrict__ quer
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
                     // copy m, index j holds vk[(j + m) mod 60]  =>  vk[c] lands at j = c - m (+60, +120)
-                    const float f0 = (float)m0, f1 = (float)m1;
+                    const float f0 = d2f_trunc(m0), f1 = d2f_trunc(m1);
                     int j0 = c0 - m, j1 = c0 + 1 - m;
                     if (j0 < 0) j0 += S;
                     if (j1 < 0) j1 += S;
@@ -508,9 +519,9 @@ sc_search2_kernel(const double *__restrict__ db, const double *__restrict__ quer
                 }
                 ws.kn[c0] = kn0; ws.kn[c0 + 1] = kn1;
             }
-            knf0 = (float)kn0; knf1 = (float)kn1;
+            knf0 = d2f_trunc(kn0); knf1 = d2f_trunc(kn1);
 #pragma unroll
-            for (int r = 0; r < R; ++r) { kf0[r] = (float)k0[r]; kf1[r] = (float)k1[r]; }
+            for (int r = 0; r < R; ++r) { kf0[r] = d2f_trunc(k0[r]); kf1[r] = d2f_trunc(k1[r]); }
         }
         // zero-norm key columns as a 60-bit mask (exact: from the f64 norms)
         __syncwarp();
@@ -1379,7 +1390,7 @@ int search_version()
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("NRS_SC_KERNEL");
-        v = (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 3;
+        v = (e && e[0] == '1') ? 1 : (e && e[0] == '3') ? 3 : 2;
     }
     return v;
 }
