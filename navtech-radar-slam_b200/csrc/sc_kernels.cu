@@ -19,6 +19,7 @@
 // stages per warp, so the next two keyframes stream in while the current one is scored.
 // Bound: HBM.  Algorithmic bytes per keyframe = 9600 (f64 20x60, the reference's
 // MatrixXd); per query = 9600*D + 9600 + 16.
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -390,18 +391,29 @@ struct Warp2Smem {
     uint64_t pad;
 };
 
-struct Block2Smem {
+// Everything a CTA needs of the query, prepared ONCE per search by sc_prep_query_kernel and
+// pulled into shared memory with a single TMA bulk copy (it used to be recomputed by every CTA:
+// 14 % of the kernel's warp samples).
+struct QPrep {
     double q64[S * QSTRIDE];             // query, f64, padded columns (certification)
     float  q32[S * QS32];                // query, f32, padded columns (filter)
     double qn[S], qv[S];
     float  qnf[S];
-    __align__(16) float qvf[S];
+    float  qvf[S];
+    unsigned long long qzero;            // bit c set <=> query column c has zero norm
+    float  qv_norm2;                     // |vq|^2 (f32), inflated
+    float  pad_[1];
+};
+static_assert(sizeof(QPrep) % 16 == 0, "QPrep must be a multiple of 16 bytes for the bulk copy");
+static_assert(offsetof(QPrep, qvf) % 16 == 0 && offsetof(QPrep, q32) % 16 == 0, "LDS.128 alignment");
+
+struct Block2Smem {
+    QPrep  q;
     Warp2Smem w[W2];
     double red_d[W2];
     int    red_pos[W2], red_idx[W2], red_s[W2];
     int    is_last;
-    float  qv_norm2;                     // |vq|^2 (f32)
-    unsigned long long qzero;            // bit c set <=> query column c has zero norm
+    uint64_t qbar;
 };
 
 // f64 -> f32 for the filter by integer ops (truncation, relative error < 2^-23, covered by the bounds):
@@ -422,8 +434,42 @@ __device__ __forceinline__ float warp_min_f(float v)
     return v;
 }
 
+// one small CTA per search: query -> QPrep (global), same arithmetic as v1's per-CTA staging
+__global__ void __launch_bounds__(64)
+sc_prep_query_kernel(const double *__restrict__ query, QPrep *__restrict__ out)
+{
+    __shared__ float sq2[S];
+    const int t = threadIdx.x;
+    if (t == 0) out->qzero = 0ull;
+    for (int i = t; i < S * QSTRIDE; i += 64) out->q64[i] = 0.0;
+    for (int i = t; i < S * QS32; i += 64) out->q32[i] = 0.f;
+    __syncthreads();
+    if (t < S) {
+        double v[R], sq[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            v[r] = query[t * R + r];
+            sq[r] = v[r] * v[r];
+            out->q64[t * QSTRIDE + r] = v[r];
+            out->q32[t * QS32 + r] = d2f_trunc(v[r]);
+        }
+        const double mean = redux20(v) / (double)R, nrm = sqrt(redux20(sq));   // Scancontext.cpp:223, :78
+        const float mf = d2f_trunc(mean);
+        out->qv[t] = mean; out->qvf[t] = mf;
+        out->qn[t] = nrm;  out->qnf[t] = d2f_trunc(nrm);
+        sq2[t] = mf * mf;
+        if (nrm == 0) atomicOr(&out->qzero, 1ull << t);
+    }
+    __syncthreads();
+    if (t == 0) {
+        float a2 = 0.f;
+        for (int c = 0; c < S; ++c) a2 += sq2[c];
+        out->qv_norm2 = a2 * 1.0001f;
+    }
+}
+
 __global__ void __launch_bounds__(THREADS2, 1)
-sc_search2_kernel(const double *__restrict__ db, const double *__restrict__ query,
+sc_search2_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep,
                   const int32_t *__restrict__ cand, int first, int n_items, int idx_offset,
                   double *__restrict__ dist_all, int32_t *__restrict__ shift_all,
                   BlockResult *__restrict__ block_results, unsigned int *__restrict__ ticket,
@@ -445,33 +491,17 @@ sc_search2_kernel(const double *__restrict__ db, const double *__restrict__ quer
             nrs::tma_load_1d(ws.tile, db + (size_t)kf * DESC, DESC * 8, &ws.bar);
         }
     }
-    // ---- stage the query in f64 and f32 ---------------------------------------------------------
-    for (int i = threadIdx.x; i < DESC; i += THREADS2) {
-        const int c = i / R, r = i - c * R;
-        const double v = query[i];
-        sm.q64[c * QSTRIDE + r] = v;
-        sm.q32[c * QS32 + r] = (float)v;
-    }
-    if (threadIdx.x == 0) sm.qzero = 0ull;
-    __syncthreads();
-    if (threadIdx.x < S) {
-        double v[R], sq[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) { v[r] = sm.q64[threadIdx.x * QSTRIDE + r]; sq[r] = v[r] * v[r]; }
-        const double mean = redux20(v) / (double)R, nrm = sqrt(redux20(sq));
-        sm.qv[threadIdx.x] = mean;  sm.qvf[threadIdx.x] = (float)mean;
-        sm.qn[threadIdx.x] = nrm;   sm.qnf[threadIdx.x] = (float)nrm;
-        if (nrm == 0) atomicOr(&sm.qzero, 1ull << threadIdx.x);
-    }
-    __syncthreads();
+    // ---- the prepared query arrives by one bulk copy -------------------------------------------------
     if (threadIdx.x == 0) {
-        float a2 = 0.f;
-        for (int c = 0; c < S; ++c) a2 = fmaf(fabsf(sm.qvf[c]), fabsf(sm.qvf[c]), a2);
-        sm.qv_norm2 = a2 * 1.0001f;
+        nrs::mbar_init(&sm.qbar, 1);
+        nrs::fence_mbar_init();
+        nrs::mbar_expect_tx(&sm.qbar, (uint32_t)sizeof(QPrep));
+        nrs::tma_load_1d(&sm.q, qprep, (uint32_t)sizeof(QPrep), &sm.qbar);
     }
     __syncthreads();
-    const unsigned long long qzero = sm.qzero;
-    const float A2 = sm.qv_norm2;
+    nrs::mbar_wait(&sm.qbar, 0);
+    const unsigned long long qzero = sm.q.qzero;
+    const float A2 = sm.q.qv_norm2;
 
     double best_d = SENTINEL;
     int best_pos = 0x7fffffff, best_idx = 0, best_s = 0;
@@ -525,16 +555,14 @@ sc_search2_kernel(const double *__restrict__ db, const double *__restrict__ quer
         }
         // zero-norm key columns as a 60-bit mask (exact: from the f64 norms)
         __syncwarp();
-        unsigned long long kzero = 0ull;
+        unsigned long long kzero;
         {
-            const bool za = own && (knf0 == 0.0f) && (ws.kn[c0] == 0);
-            const bool zb = own && (knf1 == 0.0f) && (ws.kn[c0 + 1] == 0);
-            const unsigned int ma = __ballot_sync(0xffffffffu, za), mb = __ballot_sync(0xffffffffu, zb);
-            // lane l owns columns 2l, 2l+1: interleave the two 30-bit masks
-            for (int l = 0; l < S / 2; ++l) {
-                kzero |= (unsigned long long)((ma >> l) & 1u) << (2 * l);
-                kzero |= (unsigned long long)((mb >> l) & 1u) << (2 * l + 1);
-            }
+            // zero-norm key columns as a 60-bit mask (exact: from the f64 norms), OR-reduced over the warp
+            const bool za = own && (ws.kn[c0] == 0), zb = own && (ws.kn[c0 + 1] == 0);
+            const unsigned long long mine = (za ? 1ull << c0 : 0ull) | (zb ? 1ull << (c0 + 1) : 0ull);
+            const unsigned int lo = __reduce_or_sync(0xffffffffu, (unsigned int)mine);
+            const unsigned int hi = __reduce_or_sync(0xffffffffu, (unsigned int)(mine >> 32));
+            kzero = ((unsigned long long)hi << 32) | lo;
         }
 
         // ---- phase B filter (f32): one shift per lane, two rounds; ||a - shift(b,s)||^2 =
@@ -550,7 +578,7 @@ sc_search2_kernel(const double *__restrict__ db, const double *__restrict__ quer
             const int o0 = S - lane, o1 = S - (lane + 32 < S ? lane + 32 : lane);
             const float4 *w0 = reinterpret_cast<const float4 *>(&ws.vkf[o0 & 3][o0 & ~3]);
             const float4 *w1 = reinterpret_cast<const float4 *>(&ws.vkf[o1 & 3][o1 & ~3]);
-            const float4 *qa = reinterpret_cast<const float4 *>(&sm.qvf[0]);
+            const float4 *qa = reinterpret_cast<const float4 *>(&sm.q.qvf[0]);
             float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
 #pragma unroll
             for (int i = 0; i < S / 4; ++i) {
@@ -585,7 +613,7 @@ sc_search2_kernel(const double *__restrict__ db, const double *__restrict__ quer
                 for (int i = lane; i < S; i += 32) {
                     int j = i - s;
                     j = j < 0 ? j + S : j;
-                    const double d = sm.qv[i] - ws.vk[j];
+                    const double d = sm.q.qv[i] - ws.vk[j];
                     ws.scr[i] = d * d;
                 }
                 __syncwarp();
@@ -613,13 +641,13 @@ sc_search2_kernel(const double *__restrict__ db, const double *__restrict__ quer
 #pragma unroll
             for (int tt = 0; tt < NSHIFT + 1; ++tt) {
                 float qcol[R];
-                const float4 *src = reinterpret_cast<const float4 *>(&sm.q32[qc * QS32]);
+                const float4 *src = reinterpret_cast<const float4 *>(&sm.q.q32[qc * QS32]);
 #pragma unroll
                 for (int r = 0; r < R / 4; ++r) {
                     const float4 a = src[r];
                     qcol[4 * r] = a.x; qcol[4 * r + 1] = a.y; qcol[4 * r + 2] = a.z; qcol[4 * r + 3] = a.w;
                 }
-                const float qn_ = sm.qnf[qc];
+                const float qn_ = sm.q.qnf[qc];
                 if (tt <= NSHIFT - 1) {
                     float dot = 0.f;
 #pragma unroll
@@ -637,21 +665,44 @@ sc_search2_kernel(const double *__restrict__ db, const double *__restrict__ quer
                 qc = (qc + 1 == S) ? 0 : qc + 1;
             }
         }
+        // reduce the 7 per-lane partial sums over the warp by recursive halving (9 shuffles instead of 35):
+        // after the xor-16/8/4 exchanges lane l holds slot (l >> 2) & 7 summed over 8 lanes, two butterflies finish
         float dC = INFINITY;       // lane d (< 7) ends up with the approximate distance of shift slot d
         int cntC = 0;
+        {
+            float v8[8];
 #pragma unroll
-        for (int d = 0; d < NSHIFT; ++d) {
-            float v = part[d];
+            for (int d = 0; d < NSHIFT; ++d) v8[d] = part[d];
+            v8[7] = 0.f;
+            float v4[4], v2[2], v1;
+            const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == d) {
-                int s = s0 + d - RADIUS + S;
+            for (int i = 0; i < 4; ++i) {
+                const float send = up16 ? v8[i] : v8[4 + i], keep = up16 ? v8[4 + i] : v8[i];
+                v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float send = up8 ? v4[i] : v4[2 + i], keep = up8 ? v4[2 + i] : v4[i];
+                v2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            {
+                const float send = up4 ? v2[0] : v2[1], keep = up4 ? v2[1] : v2[0];
+                v1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+            // slot d lives in lanes with (bit4, bit3, bit2) = (d >> 2, (d >> 1) & 1, d & 1)
+            const int srcl = (lane < 8) ? (((lane >> 2) & 1) << 4 | ((lane >> 1) & 1) << 3 | (lane & 1) << 2) : 0;
+            const float v = __shfl_sync(0xffffffffu, v1, srcl);
+            if (lane < NSHIFT) {
+                int s = s0 + lane - RADIUS + S;
                 s = s >= S ? s - S : s;
                 s = s >= S ? s - S : s;
                 // key column paired with query column c is (c - s) mod 60: rotate the key mask up by s
                 const unsigned long long mask60 = (1ull << S) - 1ull;
-                const unsigned long long krot = ((kzero << s) | (kzero >> (S - s))) & mask60;
-                cntC = S - __popcll((qzero | (s ? krot : kzero)) & mask60);
+                const unsigned long long krot = s ? (((kzero << s) | (kzero >> (S - s))) & mask60) : kzero;
+                cntC = S - __popcll((qzero | krot) & mask60);
                 dC = cntC ? 1.0f - v / (float)cntC : INFINITY;
             }
         }
@@ -680,7 +731,7 @@ sc_search2_kernel(const double *__restrict__ db, const double *__restrict__ quer
                 int kc = c - s;
                 kc = kc < 0 ? kc + S : kc;
                 double a[R], b[R];
-                const double2 *qa = reinterpret_cast<const double2 *>(&sm.q64[c * QSTRIDE]);
+                const double2 *qa = reinterpret_cast<const double2 *>(&sm.q.q64[c * QSTRIDE]);
                 const double2 *kb = reinterpret_cast<const double2 *>(&ws.tile[kc * R]);
 #pragma unroll
                 for (int r = 0; r < R / 2; ++r) {
@@ -688,7 +739,7 @@ sc_search2_kernel(const double *__restrict__ db, const double *__restrict__ quer
                     a[2 * r] = x.x; a[2 * r + 1] = x.y; b[2 * r] = y.x; b[2 * r + 1] = y.y;
                 }
                 const int pos = __popcll(eff & ((1ull << c) - 1ull));
-                ws.scr[pos] = redux20_dot(a, b) / (sm.qn[c] * ws.kn[kc]);
+                ws.scr[pos] = redux20_dot(a, b) / (sm.q.qn[c] * ws.kn[kc]);
             }
             __syncwarp();
             double dist = SENTINEL;
@@ -768,465 +819,6 @@ sc_search2_kernel(const double *__restrict__ db, const double *__restrict__ quer
     }
 }
 
-
-// =================================================================================================
-// K10 v3: CTA-batched filter + certification
-// =================================================================================================
-// Same arithmetic as v2 (f32 filter with rigorous bounds, f64 certification in reference order), but
-// the work of G = 8 keyframes is spread over all 256 threads of a CTA in bulk-synchronous phases, so
-// that every phase runs with ~94 % of the lanes busy and no per-warp serial tail:
-//   TMA   one thread issues G bulk copies (9600 B each) onto one mbarrier; two CTAs per SM alternate
-//         between "tiles in flight" and "scoring", which is the double buffering
-//   A     thread (kf, column pair): f64 column sums / norms (Eigen order), f32 copies stay in registers
-//   B     thread (kf, 2 shifts): f32 correlation over a sliding window; per-keyframe min by atomicMin
-//   B*    certified candidates: 4 threads per (kf, shift), one Eigen accumulator each, exact f64
-//   C     thread (kf, column pair): 8 query columns x 2 key columns, f32 similarities -> atomicAdd
-//   C*    certified (kf, shift) pairs: thread per column (exact f64 dot / norms), then one thread per
-//         pair performs distDirectSC's left-to-right sum
-constexpr int G3 = 8;
-constexpr int T3 = 256;
-constexpr int CB_CAP = 8;                 // certified fast-align candidates per keyframe before the slow path
-constexpr int CC_TASKS = 8;               // (kf, shift) certification tasks scored per round
-
-struct Smem3 {
-    double tile[G3][DESC];                // 76800
-    double q64[DESC];                     // query f64, unpadded (certification only)
-    float  q32[S * QS32];                 // query f32, padded columns
-    double qn[S], qv[S];
-    float  qnf[S];
-    __align__(16) float qvf[S];
-    double kvk[G3][S];                    // keyframe sector keys (f64)
-    double kkn[G3][S];                    // keyframe column norms (f64)
-    float  kvkf[G3][2 * S];               // f32, doubled
-    double sims[CC_TASKS][S];             // certification scratch
-    double cb_norm[G3][CB_CAP];
-    int    cb_shift[G3][CB_CAP];
-    int    cb_n[G3];
-    float  B2[G3];
-    int    nBmin[G3];                     // f32 bits (values clamped >= 0)
-    int    s0[G3];
-    float  partC[G3][8];
-    int    dCmin[G3];                     // orderable f32 bits
-    int    ccand[G3];                     // 7-bit masks
-    double cc_dist[G3][NSHIFT];
-    unsigned long long kzero[G3];
-    unsigned long long qzero;
-    double res_d[G3];
-    int    res_s[G3];
-    int    task_kf[G3 * NSHIFT], task_slot[G3 * NSHIFT];
-    int    n_tasks;
-    float  A2;
-    int    batch;                         // current batch index (dynamic scheduling)
-    int    is_last;
-    uint64_t bar;
-    double red_d[G3];
-    int    red_pos[G3], red_idx[G3], red_s[G3];
-};
-
-__device__ __forceinline__ int f32_orderable(float f)
-{
-    const int b = __float_as_int(f);
-    return b >= 0 ? b : b ^ 0x7fffffff;
-}
-__device__ __forceinline__ float f32_from_orderable(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
-
-__global__ void __launch_bounds__(T3, 2)
-sc_search3_kernel(const double *__restrict__ db, const double *__restrict__ query,
-                  const int32_t *__restrict__ cand, int first, int n_items, int idx_offset,
-                  double *__restrict__ dist_all, int32_t *__restrict__ shift_all,
-                  BlockResult *__restrict__ block_results, unsigned int *__restrict__ ticket,
-                  unsigned int *__restrict__ work_counter, nrs_sc_result *__restrict__ final_result)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem3 &sm = *reinterpret_cast<Smem3 *>(smem_raw);
-    const int t = threadIdx.x;
-    const int n_batches = (n_items + G3 - 1) / G3;
-
-    auto issue_tiles = [&](int batch) {            // one thread: G bulk copies onto one mbarrier
-        const int base = batch * G3;
-        const int nk = min(G3, n_items - base);
-        nrs::mbar_expect_tx(&sm.bar, (uint32_t)nk * DESC * 8);
-        for (int g = 0; g < nk; ++g) {
-            const int item = base + g;
-            const int kf = cand ? cand[item] : first + item;
-            nrs::tma_load_1d(sm.tile[g], db + (size_t)kf * DESC, DESC * 8, &sm.bar);
-        }
-    };
-
-    if (t == 0) {
-        nrs::mbar_init(&sm.bar, 1);
-        nrs::fence_mbar_init();
-        sm.batch = blockIdx.x;
-        if ((int)blockIdx.x < n_batches) issue_tiles(blockIdx.x);
-        sm.qzero = 0ull;
-    }
-    // ---- stage the query ------------------------------------------------------------------------
-    for (int i = t; i < DESC; i += T3) {
-        const int c = i / R, r = i - c * R;
-        const double v = query[i];
-        sm.q64[i] = v;
-        sm.q32[c * QS32 + r] = (float)v;
-    }
-    __syncthreads();
-    if (t < S) {
-        double v[R], sq[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) { v[r] = sm.q64[t * R + r]; sq[r] = v[r] * v[r]; }
-        const double mean = redux20(v) / (double)R, nrm = sqrt(redux20(sq));
-        sm.qv[t] = mean; sm.qvf[t] = (float)mean;
-        sm.qn[t] = nrm;  sm.qnf[t] = (float)nrm;
-        if (nrm == 0) atomicOr(&sm.qzero, 1ull << t);
-    }
-    __syncthreads();
-    if (t == 0) {
-        float a2 = 0.f;
-        for (int c = 0; c < S; ++c) a2 = fmaf(sm.qvf[c], sm.qvf[c], a2);
-        sm.A2 = a2 * 1.0001f;
-    }
-    __syncthreads();
-    const unsigned long long qzero = sm.qzero;
-    const float A2 = sm.A2;
-    const unsigned long long mask60 = (1ull << S) - 1ull;
-
-    // thread roles
-    const int g_own = t / 30, pair = t - g_own * 30;       // phases A, B, C: t < 240
-    const bool act = t < G3 * 30;
-    const int c0 = 2 * pair;
-
-    double best_d = SENTINEL;                               // thread g < G3 tracks slot g's running best
-    int best_pos = 0x7fffffff, best_idx = 0, best_s = 0;
-    int phase = 0;
-
-    for (;;) {
-        const int batch = sm.batch;
-        if (batch >= n_batches) break;
-        const int base = batch * G3;
-        const int nk = min(G3, n_items - base);
-        const bool mine = act && g_own < nk;
-        nrs::mbar_wait(&sm.bar, phase);
-        phase ^= 1;
-        if (t < G3) { sm.B2[t] = 0.f; sm.nBmin[t] = 0x7f800000; sm.cb_n[t] = 0; sm.kzero[t] = 0ull; sm.dCmin[t] = 0x7f800000;
-                      sm.ccand[t] = 0; }
-        if (t < G3 * 8) (&sm.partC[0][0])[t] = 0.f;
-        __syncthreads();
-
-        // ---- phase A --------------------------------------------------------------------------------
-        float kf0[R], kf1[R];
-        float knf0 = 0.f, knf1 = 0.f;
-        if (mine) {
-            double k0[R], k1[R];
-            const double2 *src = reinterpret_cast<const double2 *>(&sm.tile[g_own][c0 * R]);
-#pragma unroll
-            for (int r = 0; r < R / 2; ++r) {
-                const double2 a = src[r], b = src[R / 2 + r];
-                k0[2 * r] = a.x; k0[2 * r + 1] = a.y; k1[2 * r] = b.x; k1[2 * r + 1] = b.y;
-            }
-            double sq[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) sq[r] = k0[r] * k0[r];
-            const double kn0 = sqrt(redux20(sq));
-#pragma unroll
-            for (int r = 0; r < R; ++r) sq[r] = k1[r] * k1[r];
-            const double kn1 = sqrt(redux20(sq));
-            const double m0 = redux20(k0) / (double)R, m1 = redux20(k1) / (double)R;
-            sm.kvk[g_own][c0] = m0; sm.kvk[g_own][c0 + 1] = m1;
-            sm.kkn[g_own][c0] = kn0; sm.kkn[g_own][c0 + 1] = kn1;
-            const float f0 = (float)m0, f1 = (float)m1;
-            sm.kvkf[g_own][c0] = f0; sm.kvkf[g_own][c0 + S] = f0;
-            sm.kvkf[g_own][c0 + 1] = f1; sm.kvkf[g_own][c0 + 1 + S] = f1;
-            atomicAdd(&sm.B2[g_own], fmaf(f0, f0, f1 * f1));
-            knf0 = (float)kn0; knf1 = (float)kn1;
-            unsigned long long z = 0ull;
-            if (kn0 == 0) z |= 1ull << c0;
-            if (kn1 == 0) z |= 1ull << (c0 + 1);
-            if (z) atomicOr(&sm.kzero[g_own], z);
-#pragma unroll
-            for (int r = 0; r < R; ++r) { kf0[r] = (float)k0[r]; kf1[r] = (float)k1[r]; }
-        }
-        __syncthreads();
-
-        // ---- phase B filter: thread (kf, shifts 2*pair, 2*pair+1) -----------------------------------------
-        float nB0 = INFINITY, nB1 = INFINITY;
-        if (mine) {
-            const int s = c0;                                   // shifts s and s + 1
-            const float *vk = &sm.kvkf[g_own][S - s];           // vk[i] = key_vkey[(i - s) mod 60]
-            float corr0 = 0.f, corr1 = 0.f;
-            float prevb = vk[-1];                               // key_vkey[(-1 - s) mod 60], index S-s-1 >= 0
-#pragma unroll 12
-            for (int i = 0; i < S; ++i) {
-                const float a = sm.qvf[i], b = vk[i];
-                corr0 = fmaf(a, b, corr0);                      // shift s
-                corr1 = fmaf(a, prevb, corr1);                  // shift s + 1 : key_vkey[(i - s - 1) mod 60]
-                prevb = b;
-            }
-            const float ab = A2 + sm.B2[g_own] * 1.0001f;
-            nB0 = fmaxf(ab - 2.0f * corr0, 0.f);
-            nB1 = fmaxf(ab - 2.0f * corr1, 0.f);
-            if (!(nB0 == nB0) || !(nB1 == nB1)) { nB0 = 0.f; nB1 = 0.f; }     // NaN -> forces the slow path
-            atomicMin(&sm.nBmin[g_own], __float_as_int(fminf(nB0, nB1)));
-        }
-        __syncthreads();
-        if (mine) {
-            const float ab = A2 + sm.B2[g_own] * 1.0001f;
-            const float mB = __int_as_float(sm.nBmin[g_own]);
-            const float thr = mB + EPS_B * ab;
-            const bool fin = thr < INFINITY;
-            if (!fin || nB0 <= thr) { const int k = atomicAdd(&sm.cb_n[g_own], 1); if (k < CB_CAP) sm.cb_shift[g_own][k] = c0; }
-            if (!fin || nB1 <= thr) { const int k = atomicAdd(&sm.cb_n[g_own], 1); if (k < CB_CAP) sm.cb_shift[g_own][k] = c0 + 1; }
-        }
-        __syncthreads();
-        // ---- phase B certification: 4 threads per (kf, candidate), one Eigen accumulator each ---------------
-        {
-            // slow path (more than CB_CAP candidates, e.g. constant keys): certify all 60 shifts
-            for (int g = 0; g < nk; ++g) {
-                const int ncand = sm.cb_n[g];                   // stable: written before the last barrier
-                const bool all = ncand > CB_CAP;
-                const int n = all ? S : ncand;
-                double bn = SENTINEL;
-                int bs = 0;
-                for (int k0_ = 0; k0_ < n; k0_ += T3 / 4) {
-                    const int k = k0_ + (t >> 2);
-                    const int acc_id = t & 3;
-                    double acc = 0.0;
-                    int s = 0;
-                    if (k < n) {
-                        s = all ? k : sm.cb_shift[g][k];
-                        int j = acc_id - s;
-                        j = j < 0 ? j + S : j;
-                        double d = sm.qv[acc_id] - sm.kvk[g][j];
-                        acc = d * d;
-#pragma unroll
-                        for (int i = 4; i < S; i += 4) {
-                            j += 4;
-                            j = j >= S ? j - S : j;
-                            d = sm.qv[acc_id + i] - sm.kvk[g][j];
-                            acc += d * d;
-                        }
-                    }
-                    // (a0 + a2) + (a1 + a3) within each group of 4 lanes
-                    const double o2 = __shfl_xor_sync(0xffffffffu, acc, 2);
-                    const double pairsum = (acc_id & 2) ? o2 + acc : acc + o2;       // a0+a2 on lanes 0/2, a1+a3 on 1/3
-                    const double o1 = __shfl_xor_sync(0xffffffffu, pairsum, 1);
-                    const double tot = (acc_id & 1) ? o1 + pairsum : pairsum + o1;   // (a0+a2)+(a1+a3)
-                    if (k < n && acc_id == 0) {
-                        const double nrm = sqrt(tot);
-                        if (all) { if (better(nrm, s, bn, bs)) { bn = nrm; bs = s; } }
-                        else { sm.cb_norm[g][k] = nrm; }
-                    }
-                }
-                if (all) {
-                    // reduce the per-thread bests of the slow path through shared memory (64 leaders)
-                    __syncthreads();
-                    if ((t & 3) == 0) { sm.sims[0][t >> 2] = bn; (reinterpret_cast<int *>(&sm.sims[1][0]))[t >> 2] = bs; }
-                    __syncthreads();
-                    if (t == 0) {
-                        double fn = SENTINEL; int fs = 0;
-                        for (int q = 0; q < T3 / 4; ++q) {
-                            const double v = sm.sims[0][q];
-                            const int sv = (reinterpret_cast<int *>(&sm.sims[1][0]))[q];
-                            if (better(v, sv, fn, fs)) { fn = v; fs = sv; }
-                        }
-                        sm.s0[g] = fs;
-                    }
-                    __syncthreads();
-                }
-            }
-        }
-        __syncthreads();
-        if (t < nk && sm.cb_n[t] <= CB_CAP) {                    // fast path: lexicographic min over <= 8 entries
-            double fn = SENTINEL; int fs = 0;
-            for (int k = 0; k < sm.cb_n[t]; ++k)
-                if (better(sm.cb_norm[t][k], sm.cb_shift[t][k], fn, fs)) { fn = sm.cb_norm[t][k]; fs = sm.cb_shift[t][k]; }
-            sm.s0[t] = fs;
-        }
-        __syncthreads();
-
-        // ---- phase C filter: thread (kf, column pair) -------------------------------------------------------
-        if (mine) {
-            const int s0 = sm.s0[g_own];
-            int qc = c0 + s0 - RADIUS + S;
-            qc = qc >= S ? qc - S : qc;
-            qc = qc >= S ? qc - S : qc;
-            float part[NSHIFT];
-#pragma unroll
-            for (int d = 0; d < NSHIFT; ++d) part[d] = 0.f;
-#pragma unroll
-            for (int tt = 0; tt < NSHIFT + 1; ++tt) {
-                float qcol[R];
-                const float4 *src = reinterpret_cast<const float4 *>(&sm.q32[qc * QS32]);
-#pragma unroll
-                for (int r = 0; r < R / 4; ++r) {
-                    const float4 a = src[r];
-                    qcol[4 * r] = a.x; qcol[4 * r + 1] = a.y; qcol[4 * r + 2] = a.z; qcol[4 * r + 3] = a.w;
-                }
-                const float qn_ = sm.qnf[qc];
-                if (tt <= NSHIFT - 1) {
-                    float dot = 0.f;
-#pragma unroll
-                    for (int r = 0; r < R; ++r) dot = fmaf(qcol[r], kf0[r], dot);
-                    const float den = qn_ * knf0;
-                    part[tt] += (den > 0.f) ? __fdividef(dot, den) : 0.f;
-                }
-                if (tt >= 1) {
-                    float dot = 0.f;
-#pragma unroll
-                    for (int r = 0; r < R; ++r) dot = fmaf(qcol[r], kf1[r], dot);
-                    const float den = qn_ * knf1;
-                    part[tt - 1] += (den > 0.f) ? __fdividef(dot, den) : 0.f;
-                }
-                qc = (qc + 1 == S) ? 0 : qc + 1;
-            }
-#pragma unroll
-            for (int d = 0; d < NSHIFT; ++d) atomicAdd(&sm.partC[g_own][d], part[d]);
-        }
-        __syncthreads();
-        float dC = INFINITY;
-        int cntC = 0;
-        const int gk = t / NSHIFT, slot = t - gk * NSHIFT;        // t < nk * 7
-        if (t < nk * NSHIFT) {
-            int s = sm.s0[gk] + slot - RADIUS + S;
-            s = s >= S ? s - S : s;
-            s = s >= S ? s - S : s;
-            const unsigned long long kz = sm.kzero[gk];
-            const unsigned long long krot = s ? (((kz << s) | (kz >> (S - s))) & mask60) : kz;
-            cntC = S - __popcll((qzero | krot) & mask60);
-            if (cntC) {
-                dC = 1.0f - sm.partC[gk][slot] / (float)cntC;
-                if (!(dC == dC)) dC = -INFINITY;                 // NaN -> everything becomes a candidate
-                atomicMin(&sm.dCmin[gk], f32_orderable(dC));
-            }
-        }
-        __syncthreads();
-        if (t < nk * NSHIFT && cntC) {
-            const float mC = f32_from_orderable(sm.dCmin[gk]);
-            if (!(mC > -INFINITY) || dC <= mC + EPS_C) atomicOr(&sm.ccand[gk], 1 << slot);
-        }
-        __syncthreads();
-        if (t == 0) {                                            // task list (kf, slot), ascending
-            int n = 0;
-            for (int g = 0; g < nk; ++g)
-                for (int d = 0; d < NSHIFT; ++d)
-                    if ((sm.ccand[g] >> d) & 1) { sm.task_kf[n] = g; sm.task_slot[n] = d; ++n; }
-            sm.n_tasks = n;
-        }
-        __syncthreads();
-        // ---- phase C certification -----------------------------------------------------------------------------
-        const int n_tasks = sm.n_tasks;
-        for (int tb = 0; tb < n_tasks; tb += CC_TASKS) {
-            const int nt = min(CC_TASKS, n_tasks - tb);
-            for (int w = t; w < nt * S; w += T3) {
-                const int ti = w / S, c = w - ti * S;
-                const int g = sm.task_kf[tb + ti];
-                int s = sm.s0[g] + sm.task_slot[tb + ti] - RADIUS + S;
-                s = s >= S ? s - S : s;
-                s = s >= S ? s - S : s;
-                const unsigned long long kz = sm.kzero[g];
-                const unsigned long long krot = s ? (((kz << s) | (kz >> (S - s))) & mask60) : kz;
-                const unsigned long long eff = ~(qzero | krot) & mask60;
-                if ((eff >> c) & 1ull) {
-                    int kc = c - s;
-                    kc = kc < 0 ? kc + S : kc;
-                    double a[R], b[R];
-                    const double2 *qa = reinterpret_cast<const double2 *>(&sm.q64[c * R]);
-                    const double2 *kb = reinterpret_cast<const double2 *>(&sm.tile[g][kc * R]);
-#pragma unroll
-                    for (int r = 0; r < R / 2; ++r) {
-                        const double2 x = qa[r], y = kb[r];
-                        a[2 * r] = x.x; a[2 * r + 1] = x.y; b[2 * r] = y.x; b[2 * r + 1] = y.y;
-                    }
-                    const int pos = __popcll(eff & ((1ull << c) - 1ull));
-                    sm.sims[ti][pos] = redux20_dot(a, b) / (sm.qn[c] * sm.kkn[g][kc]);
-                }
-            }
-            __syncthreads();
-            if (t < nt) {
-                const int g = sm.task_kf[tb + t];
-                int s = sm.s0[g] + sm.task_slot[tb + t] - RADIUS + S;
-                s = s >= S ? s - S : s;
-                s = s >= S ? s - S : s;
-                const unsigned long long kz = sm.kzero[g];
-                const unsigned long long krot = s ? (((kz << s) | (kz >> (S - s))) & mask60) : kz;
-                const int cnt = __popcll(~(qzero | krot) & mask60);
-                double sum = 0.0;                               // distDirectSC's left-to-right sum (:83)
-                for (int i = 0; i < cnt; ++i) sum = sum + sm.sims[t][i];
-                sm.cc_dist[g][sm.task_slot[tb + t]] = 1.0 - sum / (double)cnt;
-            }
-            __syncthreads();
-        }
-        // ---- per keyframe: min over certified shifts in ascending shift order, strict '<' ------------------------
-        if (t < nk) {
-            double dd = SENTINEL;
-            int ds = 0;
-            for (int d = 0; d < NSHIFT; ++d)
-                if ((sm.ccand[t] >> d) & 1) {
-                    int s = sm.s0[t] + d - RADIUS + S;
-                    s = s >= S ? s - S : s;
-                    s = s >= S ? s - S : s;
-                    const double v = sm.cc_dist[t][d];
-                    if (better(v, s, dd, ds)) { dd = v; ds = s; }
-                }
-            const int item = base + t;
-            if (dist_all) dist_all[item] = dd;
-            if (shift_all) shift_all[item] = ds;
-            if (better(dd, item, best_d, best_pos)) {
-                best_d = dd; best_pos = item; best_idx = cand ? cand[item] : first + item; best_s = ds;
-            }
-        }
-        __syncthreads();                                         // tiles and scratch are free again
-        if (t == 0) {
-            const int nb = (int)atomicAdd(work_counter, 1u) + (int)gridDim.x;
-            sm.batch = nb;
-            if (nb < n_batches) { nrs::fence_proxy_async(); issue_tiles(nb); }
-        }
-        __syncthreads();
-    }
-
-    // ---- block reduce, last-block-done grid reduce -------------------------------------------------------
-    if (t < G3) { sm.red_d[t] = best_d; sm.red_pos[t] = best_pos; sm.red_idx[t] = best_idx; sm.red_s[t] = best_s; }
-    __syncthreads();
-    if (t == 0) {
-        double d = sm.red_d[0];
-        int p = sm.red_pos[0], ix = sm.red_idx[0], sh = sm.red_s[0];
-        for (int w = 1; w < G3; ++w)
-            if (better(sm.red_d[w], sm.red_pos[w], d, p)) { d = sm.red_d[w]; p = sm.red_pos[w]; ix = sm.red_idx[w]; sh = sm.red_s[w]; }
-        BlockResult br;
-        br.dist = d; br.pos = p; br.idx = ix; br.shift = sh; br.pad = 0;
-        block_results[blockIdx.x] = br;
-        __threadfence();
-        const unsigned int tk = atomicAdd(ticket, 1u);
-        sm.is_last = (tk == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (sm.is_last && t < 32) {
-        __threadfence();
-        const int lane = t;
-        double d = SENTINEL;
-        int p = 0x7fffffff, ix = 0, sh = 0;
-        for (int b = lane; b < (int)gridDim.x; b += 32) {
-            const volatile BlockResult *br = block_results + b;
-            const double bd = br->dist;
-            const int bp = br->pos;
-            if (better(bd, bp, d, p)) { d = bd; p = bp; ix = br->idx; sh = br->shift; }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double od = __shfl_xor_sync(0xffffffffu, d, off);
-            const int op = __shfl_xor_sync(0xffffffffu, p, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, ix, off);
-            const int os = __shfl_xor_sync(0xffffffffu, sh, off);
-            if (better(od, op, d, p)) { d = od; p = op; ix = oi; sh = os; }
-        }
-        if (lane == 0) {
-            nrs_sc_result res;
-            res.dist = d;
-            res.idx = (d < SENTINEL) ? ix + idx_offset : 0;
-            res.shift = sh;
-            *final_result = res;
-            *ticket = 0u;
-            *work_counter = 0u;
-        }
-    }
-}
 
 // ---- makeScancontext (Scancontext.cpp:151-195) ---------------------------------------------
 __device__ __forceinline__ int enc_f32(float f)
@@ -1373,6 +965,7 @@ struct nrs_sc_db {
     unsigned int  *d_ticket = nullptr;
     nrs_sc_result *d_result = nullptr;
     double        *d_query = nullptr;
+    QPrep         *d_qprep = nullptr;      // prepared query (v2 kernel)
     nrs_sc_result *h_result = nullptr;   // pinned
     double        *h_query = nullptr;    // pinned
     int            max_blocks = 0;
@@ -1382,15 +975,14 @@ namespace {
 
 int search_smem_bytes() { return (int)sizeof(BlockSmem); }
 int search2_smem_bytes() { return (int)sizeof(Block2Smem); }
-int search3_smem_bytes() { return (int)sizeof(Smem3); }
 
-// NRS_SC_KERNEL=1 / 2 select the earlier kernels (kept for A/B measurements); default is v3
+// NRS_SC_KERNEL=1 selects the all-f64 v1 kernel (kept for A/B measurements); default is v2
 int search_version()
 {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("NRS_SC_KERNEL");
-        v = (e && e[0] == '1') ? 1 : (e && e[0] == '3') ? 3 : 2;
+        v = (e && e[0] == '1') ? 1 : 2;
     }
     return v;
 }
@@ -1403,15 +995,13 @@ int configure_search_kernel()
                                       search_smem_bytes()));
         NRS_CUDA(cudaFuncSetAttribute(sc_search2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       search2_smem_bytes()));
-        NRS_CUDA(cudaFuncSetAttribute(sc_search3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      search3_smem_bytes()));
         done = 1;
     }
     return NRS_OK;
 }
 
 // enqueue one search on the ctx stream
-int launch_search(nrs_ctx *ctx, const double *d_db, const double *d_query, const int32_t *d_cand,
+int launch_search(nrs_ctx *ctx, const double *d_db, const double *d_query, QPrep *d_qprep, const int32_t *d_cand,
                   int first, int n_items, int idx_offset, double *d_dist_all, int32_t *d_shift_all,
                   BlockResult *d_block, unsigned int *d_ticket, nrs_sc_result *d_result,
                   int max_blocks)
@@ -1424,18 +1014,14 @@ int launch_search(nrs_ctx *ctx, const double *d_db, const double *d_query, const
         sc_search_kernel<<<blocks, THREADS, search_smem_bytes(), ctx->stream>>>(
             d_db, d_query, d_cand, first, n_items, idx_offset, d_dist_all, d_shift_all, d_block,
             d_ticket, d_result);
-    } else if (search_version() == 2) {
+    } else {
+        sc_prep_query_kernel<<<1, 64, 0, ctx->stream>>>(d_query, d_qprep);
+        NRS_LAUNCHED();
         int blocks = (n_items + W2 - 1) / W2;
         blocks = std::max(1, std::min(blocks, max_blocks));
         sc_search2_kernel<<<blocks, THREADS2, search2_smem_bytes(), ctx->stream>>>(
-            d_db, d_query, d_cand, first, n_items, idx_offset, d_dist_all, d_shift_all, d_block,
+            d_db, d_qprep, d_cand, first, n_items, idx_offset, d_dist_all, d_shift_all, d_block,
             d_ticket, d_result);
-    } else {
-        int blocks = (n_items + G3 - 1) / G3;
-        blocks = std::max(1, std::min(blocks, 2 * max_blocks));      // two CTAs per SM
-        sc_search3_kernel<<<blocks, T3, search3_smem_bytes(), ctx->stream>>>(
-            d_db, d_query, d_cand, first, n_items, idx_offset, d_dist_all, d_shift_all, d_block,
-            d_ticket, d_ticket + 1, d_result);
     }
     NRS_LAUNCHED();
     return NRS_OK;
@@ -1513,6 +1099,7 @@ int nrs_sc_db_create(nrs_ctx *ctx, int capacity_hint, nrs_sc_db **out)
         (e = cudaMalloc(&db->d_ticket, 2 * sizeof(unsigned int))) != cudaSuccess ||
         (e = cudaMalloc(&db->d_result, sizeof(nrs_sc_result))) != cudaSuccess ||
         (e = cudaMalloc(&db->d_query, DESC * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&db->d_qprep, sizeof(QPrep))) != cudaSuccess ||
         (e = cudaMallocHost(&db->h_result, sizeof(nrs_sc_result))) != cudaSuccess ||
         (e = cudaMallocHost(&db->h_query, DESC * sizeof(double))) != cudaSuccess ||
         (e = cudaMemset(db->d_ticket, 0, 2 * sizeof(unsigned int))) != cudaSuccess) {
@@ -1532,7 +1119,7 @@ int nrs_sc_db_destroy(nrs_sc_db *db)
     cudaSetDevice(db->ctx->device);
     cudaStreamSynchronize(db->ctx->stream);
     cudaFree(db->d_desc); cudaFree(db->d_block); cudaFree(db->d_ticket);
-    cudaFree(db->d_result); cudaFree(db->d_query);
+    cudaFree(db->d_result); cudaFree(db->d_query); cudaFree(db->d_qprep);
     if (db->h_result) cudaFreeHost(db->h_result);
     if (db->h_query) cudaFreeHost(db->h_query);
     delete db;
@@ -1638,7 +1225,7 @@ static int sc_query_impl(nrs_sc_db *db, const double *query_host, int first, int
     NRS_CUDA(cudaMemcpyAsync(db->d_query, db->h_query, DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     if (cand && n_items)
         NRS_CUDA(cudaMemcpyAsync(d_cand, cand, (size_t)n_items * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    rc = launch_search(ctx, db->d_desc, db->d_query, cand ? d_cand : nullptr, first, n_items, 0,
+    rc = launch_search(ctx, db->d_desc, db->d_query, db->d_qprep, cand ? d_cand : nullptr, first, n_items, 0,
                        want_all ? d_dist : nullptr, want_all ? d_shift : nullptr, db->d_block,
                        db->d_ticket, db->d_result, db->max_blocks);
     if (rc) return rc;
@@ -1673,7 +1260,7 @@ int nrs_sc_query_dev(nrs_sc_db *db, const double *query_dev, int first, int last
     std::lock_guard<std::mutex> lk(db->mu);
     NRS_CHECK_ARG(first >= 0 && last <= db->size, "search range outside the database");
     NRS_CUDA(cudaSetDevice(db->ctx->device));
-    return launch_search(db->ctx, db->d_desc, query_dev, nullptr, first, std::max(0, last - first),
+    return launch_search(db->ctx, db->d_desc, query_dev, db->d_qprep, nullptr, first, std::max(0, last - first),
                          idx_offset, nullptr, nullptr, db->d_block, db->d_ticket, result_dev,
                          db->max_blocks);
 }
@@ -1721,12 +1308,13 @@ int nrs_sc_pair(nrs_ctx *ctx, const double *sc1, const double *sc2, double *dist
     NRS_CHECK_ARG(ctx && sc1 && sc2 && dist && shift, "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     NRS_CUDA(cudaSetDevice(ctx->device));
-    const size_t bytes = 2 * DESC * sizeof(double) + sizeof(BlockResult) + 16 + sizeof(nrs_sc_result) +
+    const size_t bytes = sizeof(QPrep) + 2 * DESC * sizeof(double) + sizeof(BlockResult) + 16 + sizeof(nrs_sc_result) +
                          sizeof(double) + sizeof(int32_t) + 64;
     int rc = ctx->scratch[2].reserve(bytes);
     if (rc) return rc;
     unsigned char *base = ctx->scratch[2].as<unsigned char>();
-    double *d_q = reinterpret_cast<double *>(base);
+    QPrep *d_qprep = reinterpret_cast<QPrep *>(base);
+    double *d_q = reinterpret_cast<double *>(base + sizeof(QPrep));
     double *d_k = d_q + DESC;
     BlockResult *d_block = reinterpret_cast<BlockResult *>(d_k + DESC);
     unsigned int *d_ticket = reinterpret_cast<unsigned int *>(d_block + 1);
@@ -1736,7 +1324,7 @@ int nrs_sc_pair(nrs_ctx *ctx, const double *sc1, const double *sc2, double *dist
     NRS_CUDA(cudaMemsetAsync(d_ticket, 0, 2 * sizeof(unsigned int), ctx->stream));
     NRS_CUDA(cudaMemcpyAsync(d_q, sc1, DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     NRS_CUDA(cudaMemcpyAsync(d_k, sc2, DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    rc = launch_search(ctx, d_k, d_q, nullptr, 0, 1, 0, d_dist, d_shift, d_block, d_ticket, d_res, 1);
+    rc = launch_search(ctx, d_k, d_q, d_qprep, nullptr, 0, 1, 0, d_dist, d_shift, d_block, d_ticket, d_res, 1);
     if (rc) return rc;
     double h_dist; int32_t h_shift;
     NRS_CUDA(cudaMemcpyAsync(&h_dist, d_dist, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
