@@ -13,12 +13,15 @@
 // With that, distances are bit-identical to the CPU restatement in oracle/sc_ref.c for
 // binary {0,c} descriptors (every partial sum is exact) and for general-valued ones.
 //
-// Kernel sc_search_kernel (K10): one warp per keyframe, persistent grid (one 8-warp CTA per
-// SM, ~200 KB of shared memory each).  Each 9600-byte descriptor is staged into shared
-// memory by a 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) signalled on an mbarrier, two
-// stages per warp, so the next two keyframes stream in while the current one is scored.
-// Bound: HBM.  Algorithmic bytes per keyframe = 9600 (f64 20x60, the reference's
-// MatrixXd); per query = 9600*D + 9600 + 16.
+// Kernel sc_search2_kernel (K10): one warp per keyframe, persistent grid (one 16-warp CTA per SM,
+// ~220 KB of shared memory).  Each keyframe record (10080 B: 30 column pairs padded to 336 B so the
+// tile is bank-conflict free as it lands) is staged by ONE 1-D TMA bulk copy (cp.async.bulk ->
+// UBLKCP) onto a per-warp mbarrier; the prepared query arrives the same way.  Both arg-mins of the
+// reference are filtered in f32 and certified in f64 (see the K10 v2 block below); certification of
+// the 7-shift distance is skipped for keyframes that provably cannot beat the best distance found so
+// far anywhere on the GPU (exact pruning; disabled when per-keyframe results are requested).
+// Bound: HBM.  Algorithmic bytes per keyframe = 9600 (f64 20x60, the reference's MatrixXd);
+// per query = 9600*D + 9600 + 16.
 #include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
@@ -31,34 +34,17 @@ namespace {
 
 constexpr int R = NRS_SC_RINGS;      // 20
 constexpr int S = NRS_SC_SECTORS;    // 60
-constexpr int DESC = R * S;          // 1200 doubles = 9600 B
-constexpr int WARPS = 8;
-constexpr int THREADS = WARPS * 32;
-constexpr int STAGES = 2;
+constexpr int DESC = R * S;          // 1200 doubles = 9600 B (the reference's MatrixXd)
+// Device-side keyframe record: the 30 column pairs of a descriptor, each padded from 320 to 336
+// bytes, so that the record lands in shared memory by ONE bulk copy already free of bank conflicts
+// for the lane-per-column-pair reads (336 = 21 x 16 B, 21 mod 8 = 5).  10080 B per keyframe.
+constexpr int PAIR_D = 42;           // doubles per padded column pair
+constexpr int KREC = (S / 2) * PAIR_D;   // 1260 doubles
+__host__ __device__ constexpr int col_off(int c) { return (c >> 1) * PAIR_D + (c & 1) * R; }
 constexpr int QSTRIDE = 22;          // padded query column stride (doubles): LDS.128 conflict-free
 constexpr int NSHIFT = 7;            // 2 * round(0.5 * SEARCH_RATIO * 60) + 1   (Scancontext.cpp:123)
 constexpr int RADIUS = 3;
 constexpr double SENTINEL = 10000000.0;   // Scancontext.cpp:134,362
-
-struct WarpSmem {
-    double   tile[STAGES][DESC];   // TMA destination, column-major 20x60
-    double   vk2[2 * S];           // sector key of the keyframe, stored twice (no modulo)
-    double   kn[S];                // column norms of the keyframe
-    double   sims[NSHIFT][S];      // per (shift slot, query column) cosine similarity
-    uint64_t bar[STAGES];
-};
-
-struct BlockSmem {
-    double   q[S * QSTRIDE];       // query descriptor, padded columns
-    double   qn[S];                // query column norms
-    double   qv[S];                // query sector key
-    WarpSmem w[WARPS];
-    double   red_d[WARPS];
-    int      red_pos[WARPS];
-    int      red_idx[WARPS];
-    int      red_s[WARPS];
-    int      is_last;
-};
 
 struct BlockResult {
     double dist;
@@ -105,260 +91,6 @@ __device__ __forceinline__ bool better(double d1, int k1, double d2, int k2)
     return (d1 < d2) || (d1 == d2 && k1 < k2);
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
-sc_search_kernel(const double *__restrict__ db, const double *__restrict__ query,
-                 const int32_t *__restrict__ cand, int first, int n_items, int idx_offset,
-                 double *__restrict__ dist_all, int32_t *__restrict__ shift_all,
-                 BlockResult *__restrict__ block_results, unsigned int *__restrict__ ticket,
-                 nrs_sc_result *__restrict__ final_result)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    BlockSmem &sm = *reinterpret_cast<BlockSmem *>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpSmem &ws = sm.w[warp];
-
-    const int gw = blockIdx.x * WARPS + warp;
-    const int nw = gridDim.x * WARPS;
-
-    // ---- per-warp TMA pipeline prologue (runs while the block stages the query) ----------
-    if (lane == 0) {
-        nrs::mbar_init(&ws.bar[0], 1);
-        nrs::mbar_init(&ws.bar[1], 1);
-        nrs::fence_mbar_init();
-#pragma unroll
-        for (int st = 0; st < STAGES; ++st) {
-            const int item = gw + st * nw;
-            if (item < n_items) {
-                const int kf = cand ? cand[item] : first + item;
-                nrs::mbar_expect_tx(&ws.bar[st], DESC * 8);
-                nrs::tma_load_1d(ws.tile[st], db + (size_t)kf * DESC, DESC * 8, &ws.bar[st]);
-            }
-        }
-    }
-
-    // ---- stage the query: padded columns, column norms, sector key -----------------------
-    for (int i = threadIdx.x; i < DESC; i += THREADS) {
-        const int c = i / R, r = i - c * R;
-        sm.q[c * QSTRIDE + r] = query[i];
-    }
-    __syncthreads();
-    if (threadIdx.x < S) {
-        double v[R], sq[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            v[r] = sm.q[threadIdx.x * QSTRIDE + r];
-            sq[r] = v[r] * v[r];
-        }
-        sm.qv[threadIdx.x] = redux20(v) / (double)R;       // Scancontext.cpp:223 mean()
-        sm.qn[threadIdx.x] = sqrt(redux20(sq));            // Scancontext.cpp:78 norm()
-    }
-    __syncthreads();
-
-    double best_d = SENTINEL;
-    int best_pos = 0x7fffffff, best_idx = 0, best_s = 0;
-
-    for (int t = 0;; ++t) {
-        const int item = gw + t * nw;
-        if (item >= n_items) break;
-        const int st = t & 1;
-        const int kf = cand ? cand[item] : first + item;
-        nrs::mbar_wait(&ws.bar[st], (t >> 1) & 1);
-
-        // ---- phase A: two adjacent keyframe columns per lane -> registers; keys; norms ----
-        const bool own = lane < S / 2;
-        const int c0 = own ? 2 * lane : 0;
-        double k0[R], k1[R];
-        {
-            const double2 *src = reinterpret_cast<const double2 *>(&ws.tile[st][c0 * R]);
-#pragma unroll
-            for (int r = 0; r < R / 2; ++r) {
-                const double2 a = src[r];
-                const double2 b = src[R / 2 + r];
-                k0[2 * r] = a.x; k0[2 * r + 1] = a.y;
-                k1[2 * r] = b.x; k1[2 * r + 1] = b.y;
-            }
-        }
-        double kn0, kn1;
-        {
-            double sq[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) sq[r] = k0[r] * k0[r];
-            kn0 = sqrt(redux20(sq));
-#pragma unroll
-            for (int r = 0; r < R; ++r) sq[r] = k1[r] * k1[r];
-            kn1 = sqrt(redux20(sq));
-            if (own) {
-                const double m0 = redux20(k0) / (double)R;
-                const double m1 = redux20(k1) / (double)R;
-                ws.vk2[c0] = m0;     ws.vk2[c0 + S] = m0;
-                ws.vk2[c0 + 1] = m1; ws.vk2[c0 + 1 + S] = m1;
-                ws.kn[c0] = kn0;
-                ws.kn[c0 + 1] = kn1;
-            }
-        }
-        __syncwarp();
-        // the tile has been consumed into registers: refill this stage two keyframes ahead
-        if (lane == 0) {
-            const int item2 = item + STAGES * nw;
-            if (item2 < n_items) {
-                const int kf2 = cand ? cand[item2] : first + item2;
-                nrs::fence_proxy_async();
-                nrs::mbar_expect_tx(&ws.bar[st], DESC * 8);
-                nrs::tma_load_1d(ws.tile[st], db + (size_t)kf2 * DESC, DESC * 8, &ws.bar[st]);
-            }
-        }
-
-        // ---- phase B: fastAlignUsingVkey (Scancontext.cpp:93-113), one shift per lane ------
-        double fa_n = SENTINEL;
-        int fa_s = 0;
-#pragma unroll
-        for (int rnd = 0; rnd < 2; ++rnd) {
-            const int s = lane + 32 * rnd;
-            if (s < S) {
-                const double *vk = &ws.vk2[S - s];     // vk[i] == key_vkey[(i - s) mod 60]
-                double acc[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const double d = sm.qv[i] - vk[i];
-                    acc[i] = d * d;
-                }
-#pragma unroll
-                for (int i = 4; i < S; i += 4) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const double d = sm.qv[i + j] - vk[i + j];
-                        acc[j] += d * d;
-                    }
-                }
-                const double nrm = sqrt((acc[0] + acc[2]) + (acc[1] + acc[3]));
-                if (nrm < fa_n) { fa_n = nrm; fa_s = s; }
-            }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double on = __shfl_xor_sync(0xffffffffu, fa_n, off);
-            const int os = __shfl_xor_sync(0xffffffffu, fa_s, off);
-            if (better(on, os, fa_n, fa_s)) { fa_n = on; fa_s = os; }
-        }
-        const int s0 = fa_s;
-
-        // ---- phase C: 7 shifts x 60 columns of cosine similarity ---------------------------
-        // key column k at shift (s0 + d) meets query column (k + s0 + d) mod 60.  A lane owns
-        // key columns c0, c0+1 and walks the 8 query columns (c0 + s0 - 3 + t), t = 0..7:
-        // column t serves c0 at d = t-3 (t <= 6) and c0+1 at d = t-4 (t >= 1).
-        if (own) {
-            int qc = c0 + s0 - RADIUS + S;
-            qc = qc >= S ? qc - S : qc;
-            qc = qc >= S ? qc - S : qc;
-#pragma unroll
-            for (int tt = 0; tt < NSHIFT + 1; ++tt) {
-                double qcol[R];
-                const double2 *src = reinterpret_cast<const double2 *>(&sm.q[qc * QSTRIDE]);
-#pragma unroll
-                for (int r = 0; r < R / 2; ++r) {
-                    const double2 a = src[r];
-                    qcol[2 * r] = a.x; qcol[2 * r + 1] = a.y;
-                }
-                const double qnorm = sm.qn[qc];
-                if (tt <= NSHIFT - 1)
-                    ws.sims[tt][qc] = redux20_dot(qcol, k0) / (qnorm * kn0);        // :81
-                if (tt >= 1)
-                    ws.sims[tt - 1][qc] = redux20_dot(qcol, k1) / (qnorm * kn1);
-                qc = (qc + 1 == S) ? 0 : qc + 1;
-            }
-        }
-        __syncwarp();
-
-        // ---- phase C2: distDirectSC's sequential column sum per shift (:73-88) -------------
-        double dd = SENTINEL;
-        int ds = 0;
-        if (lane < NSHIFT) {
-            int s = s0 + lane - RADIUS + S;
-            s = s >= S ? s - S : s;
-            s = s >= S ? s - S : s;
-            const double *knv = &ws.kn[0];
-            double sum = 0.0;
-            int cnt = 0;
-            int kc = S - s;                 // key column paired with query column 0
-            kc = kc == S ? 0 : kc;
-            for (int c = 0; c < S; ++c) {
-                if (!((sm.qn[c] == 0) | (knv[kc] == 0))) {
-                    sum = sum + ws.sims[lane][c];
-                    cnt = cnt + 1;
-                }
-                kc = (kc + 1 == S) ? 0 : kc + 1;
-            }
-            const double dist = 1.0 - sum / (double)cnt;     // 0/0 -> NaN, never '<'
-            if (dist < SENTINEL) { dd = dist; ds = s; }
-        }
-        // min over the 7 shifts in ascending shift order with strict '<' (:135-144)
-#pragma unroll
-        for (int off = 4; off > 0; off >>= 1) {
-            const double od = __shfl_xor_sync(0xffffffffu, dd, off);
-            const int os = __shfl_xor_sync(0xffffffffu, ds, off);
-            if (better(od, os, dd, ds)) { dd = od; ds = os; }
-        }
-        if (lane == 0) {
-            if (dist_all) dist_all[item] = dd;
-            if (shift_all) shift_all[item] = ds;
-            if (dd < best_d) { best_d = dd; best_pos = item; best_idx = kf; best_s = ds; }
-        }
-        __syncwarp();
-    }
-
-    // ---- block reduce, then last-block-done grid reduce ------------------------------------
-    if (lane == 0) {
-        sm.red_d[warp] = best_d;
-        sm.red_pos[warp] = best_pos;
-        sm.red_idx[warp] = best_idx;
-        sm.red_s[warp] = best_s;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double d = sm.red_d[0];
-        int p = sm.red_pos[0], ix = sm.red_idx[0], sh = sm.red_s[0];
-        for (int w = 1; w < WARPS; ++w)
-            if (better(sm.red_d[w], sm.red_pos[w], d, p)) {
-                d = sm.red_d[w]; p = sm.red_pos[w]; ix = sm.red_idx[w]; sh = sm.red_s[w];
-            }
-        BlockResult br;
-        br.dist = d; br.pos = p; br.idx = ix; br.shift = sh; br.pad = 0;
-        block_results[blockIdx.x] = br;
-        __threadfence();
-        const unsigned int tk = atomicAdd(ticket, 1u);
-        sm.is_last = (tk == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (sm.is_last && warp == 0) {
-        __threadfence();
-        double d = SENTINEL;
-        int p = 0x7fffffff, ix = 0, sh = 0;
-        for (int b = lane; b < (int)gridDim.x; b += 32) {
-            const volatile BlockResult *br = block_results + b;
-            const double bd = br->dist;
-            const int bp = br->pos;
-            if (better(bd, bp, d, p)) { d = bd; p = bp; ix = br->idx; sh = br->shift; }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double od = __shfl_xor_sync(0xffffffffu, d, off);
-            const int op = __shfl_xor_sync(0xffffffffu, p, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, ix, off);
-            const int os = __shfl_xor_sync(0xffffffffu, sh, off);
-            if (better(od, op, d, p)) { d = od; p = op; ix = oi; sh = os; }
-        }
-        if (lane == 0) {
-            nrs_sc_result res;
-            res.dist = d;
-            res.idx = (d < SENTINEL) ? ix + idx_offset : 0;
-            res.shift = sh;
-            *final_result = res;
-            *ticket = 0u;      // ready for the next launch on this stream
-        }
-    }
-}
-
-
 // =================================================================================================
 // K10 v2: f32 filter + f64 certification
 // =================================================================================================
@@ -381,12 +113,12 @@ constexpr float EPS_B = 1.220703125e-4f; // 2^-13
 constexpr float EPS_C = 1.220703125e-4f; // 2^-13
 
 struct Warp2Smem {
-    double   tile[DESC];                 // TMA destination (kept until the keyframe is finished)
+    double   tile[KREC];                 // TMA destination: padded keyframe record, kept until the keyframe is finished
     double   vk[S];                      // keyframe sector key (f64, for certification)
     double   kn[S];                      // keyframe column norms (f64)
-    double   scr[S];                     // certification scratch (squared diffs / similarities)
     float    vkf[4][2 * S + 4];          // f32 copies, doubled; copy m holds vk[(j + m) mod 60] so that every
-                                         // lane's window starts 16-byte aligned (LDS.128)
+                                         // lane's window starts 16-byte aligned (LDS.128).  Once the filter
+                                         // is done the first 480 bytes double as certification scratch.
     uint64_t bar;
     uint64_t pad;
 };
@@ -436,11 +168,12 @@ __device__ __forceinline__ float warp_min_f(float v)
 
 // one small CTA per search: query -> QPrep (global), same arithmetic as v1's per-CTA staging
 __global__ void __launch_bounds__(64)
-sc_prep_query_kernel(const double *__restrict__ query, QPrep *__restrict__ out)
+sc_prep_query_kernel(const double *__restrict__ query, QPrep *__restrict__ out,
+                     unsigned long long *__restrict__ gbest)
 {
     __shared__ float sq2[S];
     const int t = threadIdx.x;
-    if (t == 0) out->qzero = 0ull;
+    if (t == 0) { out->qzero = 0ull; *gbest = (unsigned long long)__double_as_longlong(SENTINEL); }
     for (int i = t; i < S * QSTRIDE; i += 64) out->q64[i] = 0.0;
     for (int i = t; i < S * QS32; i += 64) out->q32[i] = 0.f;
     __syncthreads();
@@ -473,12 +206,14 @@ sc_search2_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep
                   const int32_t *__restrict__ cand, int first, int n_items, int idx_offset,
                   double *__restrict__ dist_all, int32_t *__restrict__ shift_all,
                   BlockResult *__restrict__ block_results, unsigned int *__restrict__ ticket,
-                  nrs_sc_result *__restrict__ final_result)
+                  unsigned long long *__restrict__ gbest, nrs_sc_result *__restrict__ final_result)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Block2Smem &sm = *reinterpret_cast<Block2Smem *>(smem_raw);
+    const bool prune = (dist_all == nullptr) && (shift_all == nullptr);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Warp2Smem &ws = sm.w[warp];
+    double *scr = reinterpret_cast<double *>(&ws.vkf[0][0]);     // certification scratch (60 doubles)
     const int gw = blockIdx.x * W2 + warp;
     const int nw = gridDim.x * W2;
 
@@ -487,8 +222,8 @@ sc_search2_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep
         nrs::fence_mbar_init();
         if (gw < n_items) {
             const int kf = cand ? cand[gw] : first + gw;
-            nrs::mbar_expect_tx(&ws.bar, DESC * 8);
-            nrs::tma_load_1d(ws.tile, db + (size_t)kf * DESC, DESC * 8, &ws.bar);
+            nrs::mbar_expect_tx(&ws.bar, KREC * 8);
+            nrs::tma_load_1d(ws.tile, db + (size_t)kf * KREC, KREC * 8, &ws.bar);
         }
     }
     // ---- the prepared query arrives by one bulk copy -------------------------------------------------
@@ -512,6 +247,9 @@ sc_search2_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep
         const int item = gw + t * nw;
         if (item >= n_items) break;
         const int kf = cand ? cand[item] : first + item;
+        // best exact distance found so far by any warp of the grid (an upper bound of the final minimum)
+        unsigned long long gb = 0;
+        if (prune && lane == 0) gb = *reinterpret_cast<volatile unsigned long long *>(gbest);
         nrs::mbar_wait(&ws.bar, t & 1);
 
         // ---- phase A (f64): column means and norms; f32 copies of this lane's two columns -------
@@ -519,7 +257,7 @@ sc_search2_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep
         float knf0, knf1;
         {
             double k0[R], k1[R];
-            const double2 *src = reinterpret_cast<const double2 *>(&ws.tile[c0 * R]);
+            const double2 *src = reinterpret_cast<const double2 *>(&ws.tile[(own ? lane : 0) * PAIR_D]);
 #pragma unroll
             for (int r = 0; r < R / 2; ++r) {
                 const double2 a = src[r], b = src[R / 2 + r];
@@ -614,14 +352,14 @@ sc_search2_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep
                     int j = i - s;
                     j = j < 0 ? j + S : j;
                     const double d = sm.q.qv[i] - ws.vk[j];
-                    ws.scr[i] = d * d;
+                    scr[i] = d * d;
                 }
                 __syncwarp();
                 double acc = 0.0;
                 if (lane < 4) {
-                    acc = ws.scr[lane];
+                    acc = scr[lane];
 #pragma unroll
-                    for (int i = 4; i < S; i += 4) acc += ws.scr[lane + i];
+                    for (int i = 4; i < S; i += 4) acc += scr[lane + i];
                 }
                 const double a2 = __shfl_sync(0xffffffffu, acc, 2), a3 = __shfl_sync(0xffffffffu, acc, 3);
                 const double a1 = __shfl_sync(0xffffffffu, acc, 1), a0 = __shfl_sync(0xffffffffu, acc, 0);
@@ -711,6 +449,14 @@ sc_search2_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep
         const bool allfin = __all_sync(0xffffffffu, finC);
         mC = warp_min_f(mC);
         unsigned int candC = __ballot_sync(0xffffffffu, lane < NSHIFT && cntC > 0 && (!allfin || dC <= mC + EPS_C));
+        if (prune) {
+            // every exact distance of this keyframe is >= mC - e_C; if that already exceeds the best
+            // exact distance known (this warp's or the grid's), the keyframe can neither win nor tie
+            const double mine_best = __shfl_sync(0xffffffffu, best_d, 0);
+            const double grid_best = __longlong_as_double((long long)__shfl_sync(0xffffffffu, gb, 0));
+            const double bound = fmin(mine_best, grid_best);
+            if (allfin && (double)(mC - EPS_C) > bound) candC = 0u;
+        }
 
         // ---- phase C certification (f64, reference order) -------------------------------------------------
         double dd = SENTINEL;
@@ -732,14 +478,14 @@ sc_search2_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep
                 kc = kc < 0 ? kc + S : kc;
                 double a[R], b[R];
                 const double2 *qa = reinterpret_cast<const double2 *>(&sm.q.q64[c * QSTRIDE]);
-                const double2 *kb = reinterpret_cast<const double2 *>(&ws.tile[kc * R]);
+                const double2 *kb = reinterpret_cast<const double2 *>(&ws.tile[col_off(kc)]);
 #pragma unroll
                 for (int r = 0; r < R / 2; ++r) {
                     const double2 x = qa[r], y = kb[r];
                     a[2 * r] = x.x; a[2 * r + 1] = x.y; b[2 * r] = y.x; b[2 * r + 1] = y.y;
                 }
                 const int pos = __popcll(eff & ((1ull << c) - 1ull));
-                ws.scr[pos] = redux20_dot(a, b) / (sm.q.qn[c] * ws.kn[kc]);
+                scr[pos] = redux20_dot(a, b) / (sm.q.qn[c] * ws.kn[kc]);
             }
             __syncwarp();
             double dist = SENTINEL;
@@ -748,11 +494,11 @@ sc_search2_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep
                 double sum = 0.0;                       // distDirectSC's left-to-right sum (:83)
                 int i = 0;
                 for (; i + 1 < cnt; i += 2) {
-                    const double2 v = *reinterpret_cast<const double2 *>(&ws.scr[i]);
+                    const double2 v = *reinterpret_cast<const double2 *>(&scr[i]);
                     sum = sum + v.x;
                     sum = sum + v.y;
                 }
-                if (i < cnt) sum = sum + ws.scr[i];
+                if (i < cnt) sum = sum + scr[i];
                 dist = 1.0 - sum / (double)cnt;
             }
             dist = __shfl_sync(0xffffffffu, dist, 0);
@@ -765,12 +511,15 @@ sc_search2_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep
             if (item2 < n_items) {
                 const int kf2 = cand ? cand[item2] : first + item2;
                 nrs::fence_proxy_async();
-                nrs::mbar_expect_tx(&ws.bar, DESC * 8);
-                nrs::tma_load_1d(ws.tile, db + (size_t)kf2 * DESC, DESC * 8, &ws.bar);
+                nrs::mbar_expect_tx(&ws.bar, KREC * 8);
+                nrs::tma_load_1d(ws.tile, db + (size_t)kf2 * KREC, KREC * 8, &ws.bar);
             }
             if (dist_all) dist_all[item] = dd;
             if (shift_all) shift_all[item] = ds;
-            if (dd < best_d) { best_d = dd; best_pos = item; best_idx = kf; best_s = ds; }
+            if (dd < best_d) {
+                best_d = dd; best_pos = item; best_idx = kf; best_s = ds;
+                if (prune) atomicMin(gbest, (unsigned long long)__double_as_longlong(dd));   // dd >= 0: bit order == value order
+            }
         }
     }
 
@@ -949,6 +698,23 @@ sc_dist_direct_kernel(const double *__restrict__ sc1, const double *__restrict__
     }
 }
 
+// canonical 20x60 column-major descriptor(s) <-> padded device record(s)
+__global__ void sc_pack_kernel(const double *__restrict__ canon, double *__restrict__ rec, int count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count * KREC) return;
+    const int k = i / KREC, o = i - k * KREC;
+    const int pair = o / PAIR_D, w = o - pair * PAIR_D;
+    rec[i] = (w < 2 * R) ? canon[(size_t)k * DESC + pair * 2 * R + w] : 0.0;
+}
+__global__ void sc_unpack_kernel(const double *__restrict__ rec, double *__restrict__ canon, int count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count * DESC) return;
+    const int k = i / DESC, e = i - k * DESC;
+    canon[i] = rec[(size_t)k * KREC + col_off(e / R) + (e % R)];
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -957,15 +723,15 @@ sc_dist_direct_kernel(const double *__restrict__ sc1, const double *__restrict__
 struct nrs_sc_db {
     nrs_ctx     *ctx = nullptr;
     std::mutex   mu;
-    double      *d_desc = nullptr;       // capacity * 1200 doubles
+    double      *d_desc = nullptr;       // capacity padded records (KREC doubles each)
     int          size = 0;
     int          capacity = 0;
     // per-db search scratch
     BlockResult   *d_block = nullptr;
-    unsigned int  *d_ticket = nullptr;
+    unsigned int  *d_ticket = nullptr;   // [0] last-block ticket, [2..3] grid-wide best distance (u64)
     nrs_sc_result *d_result = nullptr;
     double        *d_query = nullptr;
-    QPrep         *d_qprep = nullptr;      // prepared query (v2 kernel)
+    QPrep         *d_qprep = nullptr;    // prepared query
     nrs_sc_result *h_result = nullptr;   // pinned
     double        *h_query = nullptr;    // pinned
     int            max_blocks = 0;
@@ -973,26 +739,12 @@ struct nrs_sc_db {
 
 namespace {
 
-int search_smem_bytes() { return (int)sizeof(BlockSmem); }
 int search2_smem_bytes() { return (int)sizeof(Block2Smem); }
-
-// NRS_SC_KERNEL=1 selects the all-f64 v1 kernel (kept for A/B measurements); default is v2
-int search_version()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("NRS_SC_KERNEL");
-        v = (e && e[0] == '1') ? 1 : 2;
-    }
-    return v;
-}
 
 int configure_search_kernel()
 {
     static int done = 0;
     if (!done) {
-        NRS_CUDA(cudaFuncSetAttribute(sc_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      search_smem_bytes()));
         NRS_CUDA(cudaFuncSetAttribute(sc_search2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       search2_smem_bytes()));
         done = 1;
@@ -1000,7 +752,8 @@ int configure_search_kernel()
     return NRS_OK;
 }
 
-// enqueue one search on the ctx stream
+// enqueue one search on the ctx stream: prepare the query, then the persistent search kernel.
+// d_ticket points at 4 words: [0] ticket (zero between launches), [2..3] grid-wide best (reset here)
 int launch_search(nrs_ctx *ctx, const double *d_db, const double *d_query, QPrep *d_qprep, const int32_t *d_cand,
                   int first, int n_items, int idx_offset, double *d_dist_all, int32_t *d_shift_all,
                   BlockResult *d_block, unsigned int *d_ticket, nrs_sc_result *d_result,
@@ -1008,21 +761,14 @@ int launch_search(nrs_ctx *ctx, const double *d_db, const double *d_query, QPrep
 {
     int rc = configure_search_kernel();
     if (rc) return rc;
-    if (search_version() == 1) {
-        int blocks = (n_items + WARPS - 1) / WARPS;
-        blocks = std::max(1, std::min(blocks, max_blocks));
-        sc_search_kernel<<<blocks, THREADS, search_smem_bytes(), ctx->stream>>>(
-            d_db, d_query, d_cand, first, n_items, idx_offset, d_dist_all, d_shift_all, d_block,
-            d_ticket, d_result);
-    } else {
-        sc_prep_query_kernel<<<1, 64, 0, ctx->stream>>>(d_query, d_qprep);
-        NRS_LAUNCHED();
-        int blocks = (n_items + W2 - 1) / W2;
-        blocks = std::max(1, std::min(blocks, max_blocks));
-        sc_search2_kernel<<<blocks, THREADS2, search2_smem_bytes(), ctx->stream>>>(
-            d_db, d_qprep, d_cand, first, n_items, idx_offset, d_dist_all, d_shift_all, d_block,
-            d_ticket, d_result);
-    }
+    unsigned long long *d_gbest = reinterpret_cast<unsigned long long *>(d_ticket + 2);
+    sc_prep_query_kernel<<<1, 64, 0, ctx->stream>>>(d_query, d_qprep, d_gbest);
+    NRS_LAUNCHED();
+    int blocks = (n_items + W2 - 1) / W2;
+    blocks = std::max(1, std::min(blocks, max_blocks));
+    sc_search2_kernel<<<blocks, THREADS2, search2_smem_bytes(), ctx->stream>>>(
+        d_db, d_qprep, d_cand, first, n_items, idx_offset, d_dist_all, d_shift_all, d_block,
+        d_ticket, d_gbest, d_result);
     NRS_LAUNCHED();
     return NRS_OK;
 }
@@ -1033,17 +779,25 @@ int db_reserve(nrs_sc_db *db, int want)
     int cap = db->capacity ? db->capacity : 1024;
     while (cap < want) cap *= 2;
     double *np = nullptr;
-    NRS_CUDA(cudaMalloc(&np, (size_t)cap * DESC * sizeof(double)));
+    NRS_CUDA(cudaMalloc(&np, (size_t)cap * KREC * sizeof(double)));
     if (db->d_desc) {
         // in-flight searches read the old buffer: drain the stream before swapping it out
         NRS_CUDA(cudaStreamSynchronize(db->ctx->stream));
-        NRS_CUDA(cudaMemcpyAsync(np, db->d_desc, (size_t)db->size * DESC * sizeof(double),
+        NRS_CUDA(cudaMemcpyAsync(np, db->d_desc, (size_t)db->size * KREC * sizeof(double),
                                  cudaMemcpyDeviceToDevice, db->ctx->stream));
         NRS_CUDA(cudaStreamSynchronize(db->ctx->stream));
         cudaFree(db->d_desc);
     }
     db->d_desc = np;
     db->capacity = cap;
+    return NRS_OK;
+}
+
+int pack_records(nrs_ctx *ctx, const double *d_canon, double *d_rec, int count)
+{
+    const int n = count * KREC;
+    sc_pack_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_canon, d_rec, count);
+    NRS_LAUNCHED();
     return NRS_OK;
 }
 
@@ -1093,16 +847,16 @@ int nrs_sc_db_create(nrs_ctx *ctx, int capacity_hint, nrs_sc_db **out)
     NRS_CUDA(cudaSetDevice(ctx->device));
     nrs_sc_db *db = new nrs_sc_db();
     db->ctx = ctx;
-    db->max_blocks = ctx->sm_count;            // persistent: one 200 KB CTA per SM
+    db->max_blocks = ctx->sm_count;            // persistent: one ~220 KB CTA per SM
     cudaError_t e = cudaSuccess;
-    if ((e = cudaMalloc(&db->d_block, sizeof(BlockResult) * 2 * db->max_blocks)) != cudaSuccess ||
-        (e = cudaMalloc(&db->d_ticket, 2 * sizeof(unsigned int))) != cudaSuccess ||
+    if ((e = cudaMalloc(&db->d_block, sizeof(BlockResult) * db->max_blocks)) != cudaSuccess ||
+        (e = cudaMalloc(&db->d_ticket, 4 * sizeof(unsigned int))) != cudaSuccess ||
         (e = cudaMalloc(&db->d_result, sizeof(nrs_sc_result))) != cudaSuccess ||
         (e = cudaMalloc(&db->d_query, DESC * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&db->d_qprep, sizeof(QPrep))) != cudaSuccess ||
         (e = cudaMallocHost(&db->h_result, sizeof(nrs_sc_result))) != cudaSuccess ||
         (e = cudaMallocHost(&db->h_query, DESC * sizeof(double))) != cudaSuccess ||
-        (e = cudaMemset(db->d_ticket, 0, 2 * sizeof(unsigned int))) != cudaSuccess) {
+        (e = cudaMemset(db->d_ticket, 0, 4 * sizeof(unsigned int))) != cudaSuccess) {
         nrs::set_error("nrs_sc_db_create: %s", cudaGetErrorString(e));
         nrs_sc_db_destroy(db);
         return NRS_ECUDA;
@@ -1144,14 +898,26 @@ int nrs_sc_db_clear(nrs_sc_db *db)
 int nrs_sc_db_append(nrs_sc_db *db, const double *desc_host, int count)
 {
     NRS_CHECK_ARG(db && desc_host && count >= 0, "bad argument");
+    if (count == 0) return NRS_OK;
     std::lock_guard<std::mutex> lk(db->mu);
-    NRS_CUDA(cudaSetDevice(db->ctx->device));
+    nrs_ctx *ctx = db->ctx;
+    std::lock_guard<std::mutex> lk2(ctx->mu);
+    NRS_CUDA(cudaSetDevice(ctx->device));
     int rc = db_reserve(db, db->size + count);
     if (rc) return rc;
-    NRS_CUDA(cudaMemcpyAsync(db->d_desc + (size_t)db->size * DESC, desc_host,
-                             (size_t)count * DESC * sizeof(double), cudaMemcpyHostToDevice,
-                             db->ctx->stream));
-    NRS_CUDA(cudaStreamSynchronize(db->ctx->stream));
+    // stage the canonical 9600-byte descriptors, then rewrite them as padded device records
+    const int chunk = 4096;
+    rc = ctx->scratch[6].reserve((size_t)std::min(count, chunk) * DESC * sizeof(double));
+    if (rc) return rc;
+    double *d_stage = ctx->scratch[6].as<double>();
+    for (int done = 0; done < count; done += chunk) {
+        const int n = std::min(chunk, count - done);
+        NRS_CUDA(cudaMemcpyAsync(d_stage, desc_host + (size_t)done * DESC, (size_t)n * DESC * sizeof(double),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+        rc = pack_records(ctx, d_stage, db->d_desc + (size_t)(db->size + done) * KREC, n);
+        if (rc) return rc;
+        NRS_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     db->size += count;
     return NRS_OK;
 }
@@ -1166,14 +932,16 @@ int nrs_sc_db_append_cloud(nrs_sc_db *db, const float *xyz, int P, double lidar_
     NRS_CUDA(cudaSetDevice(ctx->device));
     int rc = db_reserve(db, db->size + 1);
     if (rc) return rc;
-    rc = ctx->scratch[0].reserve((size_t)std::max(P, 1) * 3 * sizeof(float));
+    rc = ctx->scratch[0].reserve((size_t)std::max(P, 1) * 3 * sizeof(float) + DESC * sizeof(double));
     if (rc) return rc;
-    float *d_xyz = ctx->scratch[0].as<float>();
-    double *d_slot = db->d_desc + (size_t)db->size * DESC;
+    double *d_canon = ctx->scratch[0].as<double>();
+    float *d_xyz = reinterpret_cast<float *>(d_canon + DESC);
     if (P) NRS_CUDA(cudaMemcpyAsync(d_xyz, xyz, (size_t)P * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    sc_make_kernel<<<1, 256, 0, ctx->stream>>>(d_xyz, P, lidar_height, max_radius, d_slot);
+    sc_make_kernel<<<1, 256, 0, ctx->stream>>>(d_xyz, P, lidar_height, max_radius, d_canon);
     NRS_LAUNCHED();
-    if (desc_out) NRS_CUDA(cudaMemcpyAsync(desc_out, d_slot, DESC * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    rc = pack_records(ctx, d_canon, db->d_desc + (size_t)db->size * KREC, 1);
+    if (rc) return rc;
+    if (desc_out) NRS_CUDA(cudaMemcpyAsync(desc_out, d_canon, DESC * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     NRS_CUDA(cudaStreamSynchronize(ctx->stream));
     db->size += 1;
     return NRS_OK;
@@ -1184,11 +952,22 @@ int nrs_sc_db_read(nrs_sc_db *db, int first, int count, double *desc_host)
     NRS_CHECK_ARG(db && desc_host && first >= 0 && count >= 0, "bad argument");
     std::lock_guard<std::mutex> lk(db->mu);
     NRS_CHECK_ARG(first + count <= db->size, "range exceeds database size");
-    NRS_CUDA(cudaSetDevice(db->ctx->device));
-    NRS_CUDA(cudaMemcpyAsync(desc_host, db->d_desc + (size_t)first * DESC,
-                             (size_t)count * DESC * sizeof(double), cudaMemcpyDeviceToHost,
-                             db->ctx->stream));
-    NRS_CUDA(cudaStreamSynchronize(db->ctx->stream));
+    if (count == 0) return NRS_OK;
+    nrs_ctx *ctx = db->ctx;
+    std::lock_guard<std::mutex> lk2(ctx->mu);
+    NRS_CUDA(cudaSetDevice(ctx->device));
+    const int chunk = 4096;
+    int rc = ctx->scratch[6].reserve((size_t)std::min(count, chunk) * DESC * sizeof(double));
+    if (rc) return rc;
+    double *d_stage = ctx->scratch[6].as<double>();
+    for (int done = 0; done < count; done += chunk) {
+        const int n = std::min(chunk, count - done);
+        sc_unpack_kernel<<<(n * DESC + 255) / 256, 256, 0, ctx->stream>>>(db->d_desc + (size_t)(first + done) * KREC, d_stage, n);
+        NRS_LAUNCHED();
+        NRS_CUDA(cudaMemcpyAsync(desc_host + (size_t)done * DESC, d_stage, (size_t)n * DESC * sizeof(double),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+        NRS_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     return NRS_OK;
 }
 
@@ -1249,6 +1028,7 @@ int nrs_sc_query_all(nrs_sc_db *db, const double *query_host, int first, int las
                      double *dist_out, int32_t *shift_out, nrs_sc_result *result_host)
 {
     nrs_sc_result tmp;
+    NRS_CHECK_ARG(dist_out || shift_out, "nrs_sc_query_all needs dist_out or shift_out");
     return sc_query_impl(db, query_host, first, last, nullptr, 0, dist_out, shift_out,
                          result_host ? result_host : &tmp);
 }
@@ -1308,23 +1088,28 @@ int nrs_sc_pair(nrs_ctx *ctx, const double *sc1, const double *sc2, double *dist
     NRS_CHECK_ARG(ctx && sc1 && sc2 && dist && shift, "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     NRS_CUDA(cudaSetDevice(ctx->device));
-    const size_t bytes = sizeof(QPrep) + 2 * DESC * sizeof(double) + sizeof(BlockResult) + 16 + sizeof(nrs_sc_result) +
-                         sizeof(double) + sizeof(int32_t) + 64;
-    int rc = ctx->scratch[2].reserve(bytes);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+    const size_t o_prep = take(sizeof(QPrep)), o_q = take(DESC * 8), o_k = take(DESC * 8), o_rec = take(KREC * 8);
+    const size_t o_blk = take(sizeof(BlockResult)), o_tk = take(16), o_res = take(sizeof(nrs_sc_result));
+    const size_t o_d = take(8), o_s = take(4);
+    int rc = ctx->scratch[2].reserve(off);
     if (rc) return rc;
     unsigned char *base = ctx->scratch[2].as<unsigned char>();
-    QPrep *d_qprep = reinterpret_cast<QPrep *>(base);
-    double *d_q = reinterpret_cast<double *>(base + sizeof(QPrep));
-    double *d_k = d_q + DESC;
-    BlockResult *d_block = reinterpret_cast<BlockResult *>(d_k + DESC);
-    unsigned int *d_ticket = reinterpret_cast<unsigned int *>(d_block + 1);
-    nrs_sc_result *d_res = reinterpret_cast<nrs_sc_result *>(reinterpret_cast<unsigned char *>(d_ticket) + 16);
-    double *d_dist = reinterpret_cast<double *>(d_res + 1);
-    int32_t *d_shift = reinterpret_cast<int32_t *>(d_dist + 1);
-    NRS_CUDA(cudaMemsetAsync(d_ticket, 0, 2 * sizeof(unsigned int), ctx->stream));
+    QPrep *d_qprep = reinterpret_cast<QPrep *>(base + o_prep);
+    double *d_q = reinterpret_cast<double *>(base + o_q), *d_k = reinterpret_cast<double *>(base + o_k);
+    double *d_rec = reinterpret_cast<double *>(base + o_rec);
+    BlockResult *d_block = reinterpret_cast<BlockResult *>(base + o_blk);
+    unsigned int *d_ticket = reinterpret_cast<unsigned int *>(base + o_tk);
+    nrs_sc_result *d_res = reinterpret_cast<nrs_sc_result *>(base + o_res);
+    double *d_dist = reinterpret_cast<double *>(base + o_d);
+    int32_t *d_shift = reinterpret_cast<int32_t *>(base + o_s);
+    NRS_CUDA(cudaMemsetAsync(d_ticket, 0, 16, ctx->stream));
     NRS_CUDA(cudaMemcpyAsync(d_q, sc1, DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     NRS_CUDA(cudaMemcpyAsync(d_k, sc2, DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    rc = launch_search(ctx, d_k, d_q, d_qprep, nullptr, 0, 1, 0, d_dist, d_shift, d_block, d_ticket, d_res, 1);
+    rc = pack_records(ctx, d_k, d_rec, 1);
+    if (rc) return rc;
+    rc = launch_search(ctx, d_rec, d_q, d_qprep, nullptr, 0, 1, 0, d_dist, d_shift, d_block, d_ticket, d_res, 1);
     if (rc) return rc;
     double h_dist; int32_t h_shift;
     NRS_CUDA(cudaMemcpyAsync(&h_dist, d_dist, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
