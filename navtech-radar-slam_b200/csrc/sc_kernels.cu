@@ -108,12 +108,15 @@ __device__ __forceinline__ bool better(double d1, int k1, double d2, int k2)
 // A non-finite f32 intermediate (inputs beyond ~1e18) keeps every candidate, i.e. falls back to f64.
 constexpr int W2 = 16;                   // warps per CTA
 constexpr int THREADS2 = W2 * 32;
-constexpr int QS32 = 24;                 // padded f32 query column stride (floats): LDS.128 conflict-free
+// f32 query columns are stored as pairs padded to 176 B (44 floats): lanes read columns 2l + const, i.e.
+// one pair apart, and 176 B = 11 x 16 B makes those eight 16-byte accesses hit eight different banks
+constexpr int QPAIR32 = 44;
+__host__ __device__ constexpr int q32_off(int c) { return (c >> 1) * QPAIR32 + (c & 1) * R; }
 constexpr float EPS_B = 1.220703125e-4f; // 2^-13
 constexpr float EPS_C = 1.220703125e-4f; // 2^-13
 
 struct Warp2Smem {
-    double   tile[KREC];                 // TMA destination: padded keyframe record, kept until the keyframe is finished
+    double   tile[KREC];                 // TMA destination: padded keyframe record, consumed by phase A and re-armed at once
     double   vk[S];                      // keyframe sector key (f64, for certification)
     double   kn[S];                      // keyframe column norms (f64)
     float    vkf[4][2 * S + 4];          // f32 copies, doubled; copy m holds vk[(j + m) mod 60] so that every
@@ -128,7 +131,7 @@ struct Warp2Smem {
 // 14 % of the kernel's warp samples).
 struct QPrep {
     double q64[S * QSTRIDE];             // query, f64, padded columns (certification)
-    float  q32[S * QS32];                // query, f32, padded columns (filter)
+    float  q32[(S / 2) * QPAIR32];       // query, f32, padded column pairs (filter)
     double qn[S], qv[S];
     float  qnf[S];
     float  qvf[S];
@@ -148,17 +151,6 @@ struct Block2Smem {
     uint64_t qbar;
 };
 
-// f64 -> f32 for the filter by integer ops (truncation, relative error < 2^-23, covered by the bounds):
-// F2F.F32.F64 runs on the XU pipe at a small fraction of the ALU rate and was the top stall of v2
-__device__ __forceinline__ float d2f_trunc(double x)
-{
-    const unsigned int hi = (unsigned int)__double2hiint(x), lo = (unsigned int)__double2loint(x);
-    const int ef = (int)((hi >> 20) & 0x7ffu) - 1023 + 127;
-    const unsigned int m = ((hi & 0xfffffu) << 3) | (lo >> 29);
-    const unsigned int r = (ef <= 0) ? 0u : (ef >= 255 ? 0x7f800000u : (((unsigned int)ef << 23) | m));
-    return __uint_as_float((hi & 0x80000000u) | r);
-}
-
 __device__ __forceinline__ float warp_min_f(float v)
 {
 #pragma unroll
@@ -175,7 +167,7 @@ sc_prep_query_kernel(const double *__restrict__ query, QPrep *__restrict__ out,
     const int t = threadIdx.x;
     if (t == 0) { out->qzero = 0ull; *gbest = (unsigned long long)__double_as_longlong(SENTINEL); }
     for (int i = t; i < S * QSTRIDE; i += 64) out->q64[i] = 0.0;
-    for (int i = t; i < S * QS32; i += 64) out->q32[i] = 0.f;
+    for (int i = t; i < (S / 2) * QPAIR32; i += 64) out->q32[i] = 0.f;
     __syncthreads();
     if (t < S) {
         double v[R], sq[R];
@@ -184,12 +176,12 @@ sc_prep_query_kernel(const double *__restrict__ query, QPrep *__restrict__ out,
             v[r] = query[t * R + r];
             sq[r] = v[r] * v[r];
             out->q64[t * QSTRIDE + r] = v[r];
-            out->q32[t * QS32 + r] = d2f_trunc(v[r]);
+            out->q32[q32_off(t) + r] = (float)v[r];
         }
         const double mean = redux20(v) / (double)R, nrm = sqrt(redux20(sq));   // Scancontext.cpp:223, :78
-        const float mf = d2f_trunc(mean);
+        const float mf = (float)mean;
         out->qv[t] = mean; out->qvf[t] = mf;
-        out->qn[t] = nrm;  out->qnf[t] = d2f_trunc(nrm);
+        out->qn[t] = nrm;  out->qnf[t] = (float)nrm;
         sq2[t] = mf * mf;
         if (nrm == 0) atomicOr(&out->qzero, 1ull << t);
     }
@@ -276,7 +268,7 @@ sc_search2_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
                     // copy m, index j holds vk[(j + m) mod 60]  =>  vk[c] lands at j = c - m (+60, +120)
-                    const float f0 = d2f_trunc(m0), f1 = d2f_trunc(m1);
+                    const float f0 = (float)m0, f1 = (float)m1;
                     int j0 = c0 - m, j1 = c0 + 1 - m;
                     if (j0 < 0) j0 += S;
                     if (j1 < 0) j1 += S;
@@ -287,12 +279,22 @@ sc_search2_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep
                 }
                 ws.kn[c0] = kn0; ws.kn[c0 + 1] = kn1;
             }
-            knf0 = d2f_trunc(kn0); knf1 = d2f_trunc(kn1);
+            knf0 = (float)kn0; knf1 = (float)kn1;
 #pragma unroll
-            for (int r = 0; r < R; ++r) { kf0[r] = d2f_trunc(k0[r]); kf1[r] = d2f_trunc(k1[r]); }
+            for (int r = 0; r < R; ++r) { kf0[r] = (float)k0[r]; kf1[r] = (float)k1[r]; }
         }
         // zero-norm key columns as a 60-bit mask (exact: from the f64 norms)
         __syncwarp();
+        // the record now lives in registers (f32) and vk/kn: stream in this warp's next keyframe already
+        if (lane == 0) {
+            const int item2 = item + nw;
+            if (item2 < n_items) {
+                const int kf2 = cand ? cand[item2] : first + item2;
+                nrs::fence_proxy_async();
+                nrs::mbar_expect_tx(&ws.bar, KREC * 8);
+                nrs::tma_load_1d(ws.tile, db + (size_t)kf2 * KREC, KREC * 8, &ws.bar);
+            }
+        }
         unsigned long long kzero;
         {
             // zero-norm key columns as a 60-bit mask (exact: from the f64 norms), OR-reduced over the warp
@@ -379,7 +381,7 @@ sc_search2_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep
 #pragma unroll
             for (int tt = 0; tt < NSHIFT + 1; ++tt) {
                 float qcol[R];
-                const float4 *src = reinterpret_cast<const float4 *>(&sm.q.q32[qc * QS32]);
+                const float4 *src = reinterpret_cast<const float4 *>(&sm.q.q32[q32_off(qc)]);
 #pragma unroll
                 for (int r = 0; r < R / 4; ++r) {
                     const float4 a = src[r];
@@ -387,16 +389,18 @@ sc_search2_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep
                 }
                 const float qn_ = sm.q.qnf[qc];
                 if (tt <= NSHIFT - 1) {
-                    float dot = 0.f;
+                    float dot = 0.f, dot2 = 0.f;
 #pragma unroll
-                    for (int r = 0; r < R; ++r) dot = fmaf(qcol[r], kf0[r], dot);
+                    for (int r = 0; r < R; r += 2) { dot = fmaf(qcol[r], kf0[r], dot); dot2 = fmaf(qcol[r + 1], kf0[r + 1], dot2); }
+                    dot += dot2;
                     const float den = qn_ * knf0;
                     part[tt] += (den > 0.f) ? __fdividef(dot, den) : 0.f;
                 }
                 if (tt >= 1) {
-                    float dot = 0.f;
+                    float dot = 0.f, dot2 = 0.f;
 #pragma unroll
-                    for (int r = 0; r < R; ++r) dot = fmaf(qcol[r], kf1[r], dot);
+                    for (int r = 0; r < R; r += 2) { dot = fmaf(qcol[r], kf1[r], dot); dot2 = fmaf(qcol[r + 1], kf1[r + 1], dot2); }
+                    dot += dot2;
                     const float den = qn_ * knf1;
                     part[tt - 1] += (den > 0.f) ? __fdividef(dot, den) : 0.f;
                 }
@@ -478,7 +482,8 @@ sc_search2_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep
                 kc = kc < 0 ? kc + S : kc;
                 double a[R], b[R];
                 const double2 *qa = reinterpret_cast<const double2 *>(&sm.q.q64[c * QSTRIDE]);
-                const double2 *kb = reinterpret_cast<const double2 *>(&ws.tile[col_off(kc)]);
+                // the f64 record is re-read from global memory (it was streamed moments ago: L2 hit)
+                const double2 *kb = reinterpret_cast<const double2 *>(db + (size_t)kf * KREC + col_off(kc));
 #pragma unroll
                 for (int r = 0; r < R / 2; ++r) {
                     const double2 x = qa[r], y = kb[r];
@@ -505,15 +510,7 @@ sc_search2_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep
             if (better(dist, s, dd, ds)) { dd = dist; ds = s; }   // lexicographic (dist, shift) == ascending-shift scan
         }
         __syncwarp();
-        // the tile is no longer needed: stream in this warp's next keyframe
         if (lane == 0) {
-            const int item2 = item + nw;
-            if (item2 < n_items) {
-                const int kf2 = cand ? cand[item2] : first + item2;
-                nrs::fence_proxy_async();
-                nrs::mbar_expect_tx(&ws.bar, KREC * 8);
-                nrs::tma_load_1d(ws.tile, db + (size_t)kf2 * KREC, KREC * 8, &ws.bar);
-            }
             if (dist_all) dist_all[item] = dd;
             if (shift_all) shift_all[item] = ds;
             if (dd < best_d) {
