@@ -112,6 +112,9 @@ constexpr int THREADS2 = W2 * 32;
 // one pair apart, and 176 B = 11 x 16 B makes those eight 16-byte accesses hit eight different banks
 constexpr int QPAIR32 = 44;
 __host__ __device__ constexpr int q32_off(int c) { return (c >> 1) * QPAIR32 + (c & 1) * R; }
+// row stride of the four aligned sector-key copies: 136 floats = 34 x 16 B, 34 mod 8 = 2, so that the
+// eight lanes of a quarter-warp (two window bases x four copies) hit eight different banks
+constexpr int VKF_STRIDE = 136;
 constexpr float EPS_B = 1.220703125e-4f; // 2^-13
 constexpr float EPS_C = 1.220703125e-4f; // 2^-13
 
@@ -119,7 +122,7 @@ struct Warp2Smem {
     double   tile[KREC];                 // TMA destination: padded keyframe record, consumed by phase A and re-armed at once
     double   vk[S];                      // keyframe sector key (f64, for certification)
     double   kn[S];                      // keyframe column norms (f64)
-    float    vkf[4][2 * S + 4];          // f32 copies, doubled; copy m holds vk[(j + m) mod 60] so that every
+    float    vkf[4][VKF_STRIDE];         // f32 copies, doubled; copy m holds vk[(j + m) mod 60] so that every
                                          // lane's window starts 16-byte aligned (LDS.128).  Once the filter
                                          // is done the first 480 bytes double as certification scratch.
     uint64_t bar;
@@ -165,6 +168,10 @@ sc_prep_query_kernel(const double *__restrict__ query, QPrep *__restrict__ out,
 {
     __shared__ float sq2[S];
     const int t = threadIdx.x;
+    // programmatic dependent launch: let the search kernel start its prologue (mbarrier init, first TMA
+    // tile loads) while this CTA prepares the query; the search waits on griddepcontrol.wait before it
+    // touches anything written here
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (t == 0) { out->qzero = 0ull; *gbest = (unsigned long long)__double_as_longlong(SENTINEL); }
     for (int i = t; i < S * QSTRIDE; i += 64) out->q64[i] = 0.0;
     for (int i = t; i < (S / 2) * QPAIR32; i += 64) out->q32[i] = 0.f;
@@ -218,7 +225,8 @@ sc_search2_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep
             nrs::tma_load_1d(ws.tile, db + (size_t)kf * KREC, KREC * 8, &ws.bar);
         }
     }
-    // ---- the prepared query arrives by one bulk copy -------------------------------------------------
+    // ---- the prepared query arrives by one bulk copy (after the prep grid has completed) -------------
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x == 0) {
         nrs::mbar_init(&sm.qbar, 1);
         nrs::fence_mbar_init();
@@ -763,9 +771,19 @@ int launch_search(nrs_ctx *ctx, const double *d_db, const double *d_query, QPrep
     NRS_LAUNCHED();
     int blocks = (n_items + W2 - 1) / W2;
     blocks = std::max(1, std::min(blocks, max_blocks));
-    sc_search2_kernel<<<blocks, THREADS2, search2_smem_bytes(), ctx->stream>>>(
-        d_db, d_qprep, d_cand, first, n_items, idx_offset, d_dist_all, d_shift_all, d_block,
-        d_ticket, d_gbest, d_result);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(THREADS2);
+    cfg.dynamicSmemBytes = search2_smem_bytes();
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const QPrep *c_qprep = d_qprep;
+    NRS_CUDA(cudaLaunchKernelEx(&cfg, sc_search2_kernel, d_db, c_qprep, d_cand, first, n_items, idx_offset,
+                                d_dist_all, d_shift_all, d_block, d_ticket, d_gbest, d_result));
     NRS_LAUNCHED();
     return NRS_OK;
 }
