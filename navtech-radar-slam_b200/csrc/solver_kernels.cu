@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(CLQ_THREADS)
 orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restrict__ stackP,
                     uint16_t *__restrict__ ordS, uint16_t *__restrict__ colS, int *__restrict__ cur,
                     int *__restrict__ best, int *__restrict__ idxS, SolverInfoDev *__restrict__ info,
-                    long long node_limit)
+                    long long node_limit, uint32_t *__restrict__ misStack)
 {
     extern __shared__ uint32_t sadj[];
     __shared__ uint32_t sP[WORDS];          // current vertex set, one word per entry
@@ -241,6 +241,181 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restri
         if (lane == 0 && dm) { sP[warp] &= ~dm; s_changed = 1; }
         __syncthreads();
         if (!s_changed) break;
+    }
+    // ---- method selection: complement edges inside the core (oracle/solver_ref.c orora_max_clique) ------
+    __shared__ int s_ncore, s_mh2;
+    if (tid == 0) { s_ncore = 0; s_mh2 = 0; }
+    __syncthreads();
+    {
+        int hc = 0;
+        const bool in = tid < N && ((sP[tid >> 5] >> (tid & 31)) & 1u);
+        if (in) {
+            for (int w = 0; w < WORDS; ++w) hc += __popc(~sadj[tid * WORDS + w] & sP[w]);
+            hc -= 1;
+        }
+        const unsigned int bm = __ballot_sync(0xffffffffu, in);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) hc += __shfl_xor_sync(0xffffffffu, hc, o);
+        if (lane == 0 && bm) { atomicAdd(&s_ncore, __popc(bm)); atomicAdd(&s_mh2, hc); }
+    }
+    __syncthreads();
+    const bool use_mis = s_ncore > 0 && (s_mh2 / 2 <= 3 * s_ncore);
+    if (use_mis) {
+        // ---- maximum independent set on the sparse complement of the core, one thread per vertex ----------
+        // stack entry e: words [0,32) P, [32,64) C, [64] size, [65] stage, [66] branch vertex
+        constexpr int ENT = 2 * WORDS + 4;
+        __shared__ uint32_t sCore[WORDS], curP[WORDS], curC[WORDS], sTake[WORDS], sRem[WORDS], bestC[WORDS];
+        __shared__ int sd[MAXN];
+        __shared__ int s_size, s_depth, s_np, s_m2, s_md, s_vstar, s_improved, s_exact;
+        __shared__ long long s_nodes;
+        if (warp == 0) { sCore[lane] = sP[lane]; bestC[lane] = 0u; }
+        if (tid == 0) { s_depth = 0; s_improved = 0; s_exact = 1; s_nodes = 0; }
+        if (tid < WORDS) { misStack[tid] = sP[tid]; misStack[WORDS + tid] = 0u; }
+        if (tid == 0) { misStack[2 * WORDS] = 0u; misStack[2 * WORDS + 1] = 0u; misStack[2 * WORDS + 2] = 0u; }
+        __syncthreads();
+        while (s_depth >= 0) {
+            uint32_t *ent = misStack + (size_t)s_depth * ENT;
+            const int stage = (int)ent[2 * WORDS + 1];
+            __syncthreads();
+            if (stage == 0) {
+                if (warp == 0) { curP[lane] = ent[lane]; curC[lane] = ent[WORDS + lane]; }
+                if (tid == 0) { s_size = (int)ent[2 * WORDS]; s_nodes += 1; }
+                __syncthreads();
+                int d = -1;
+                for (;;) {                                       // Jacobi reduction rounds
+                    const bool inP = tid < N && ((curP[tid >> 5] >> (tid & 31)) & 1u);
+                    d = -1;
+                    if (inP) {
+                        d = 0;
+                        for (int w = 0; w < WORDS; ++w) d += __popc(~sadj[tid * WORDS + w] & sCore[w] & curP[w]);
+                        d -= 1;                                  // the complement row includes the vertex itself
+                    }
+                    if (tid < MAXN) sd[tid] = d;
+                    if (warp == 0) sRem[lane] = 0u;
+                    __syncthreads();
+                    bool takev = false;
+                    if (d == 0) takev = true;
+                    else if (d == 1) {
+                        int u = -1;
+                        for (int w = 0; w < WORDS && u < 0; ++w) {
+                            uint32_t x = ~sadj[tid * WORDS + w] & sCore[w] & curP[w];
+                            if ((tid >> 5) == w) x &= ~(1u << (tid & 31));
+                            if (x) u = w * 32 + __ffs(x) - 1;
+                        }
+                        if (sd[u] == 1) { if (tid < u) { takev = true; atomicOr(&sRem[u >> 5], 1u << (u & 31)); } }
+                        else { takev = true; atomicOr(&sRem[u >> 5], 1u << (u & 31)); }
+                    }
+                    const unsigned int tm = __ballot_sync(0xffffffffu, takev);
+                    if (lane == 0) sTake[warp] = tm;
+                    const int changed = __syncthreads_or(takev ? 1 : 0);
+                    if (!changed) break;
+                    if (warp == 0) {
+                        const uint32_t tk = sTake[lane];
+                        curC[lane] |= tk;
+                        curP[lane] &= ~(tk | sRem[lane]);
+                        int c = __popc(tk);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                        if (lane == 0) s_size += c;
+                    }
+                    __syncthreads();
+                }
+                // np, sum of degrees, max degree and its lowest-index vertex (d is from the last round)
+                if (tid == 0) { s_np = 0; s_m2 = 0; s_md = 0; s_vstar = 0x7fffffff; }
+                __syncthreads();
+                {
+                    int c = d >= 0 ? 1 : 0, m2 = d > 0 ? d : 0, md = d, vi = tid;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        c += __shfl_xor_sync(0xffffffffu, c, o);
+                        m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+                        const int om = __shfl_xor_sync(0xffffffffu, md, o), oi = __shfl_xor_sync(0xffffffffu, vi, o);
+                        if (om > md || (om == md && oi < vi)) { md = om; vi = oi; }
+                    }
+                    if (lane == 0 && c) {
+                        atomicAdd(&s_np, c); atomicAdd(&s_m2, m2);
+                        atomicMax(&s_md, md);
+                    }
+                    __syncthreads();
+                    if (lane == 0 && c && md == s_md) atomicMin(&s_vstar, vi);
+                }
+                __syncthreads();
+                const int np = s_np;
+                bool descend = false;
+                if (np == 0) {
+                    if (s_size > best_n) {
+                        if (warp == 0) bestC[lane] = curC[lane];
+                        if (tid == 0) s_improved = 1;
+                        best_n = s_size;
+                    }
+                } else {
+                    const int md = s_md, m = s_m2 / 2;
+                    const int ub = s_size + np - (m + md - 1) / md;
+                    if (ub > best_n) {
+                        if (s_nodes >= node_limit) { if (tid == 0) s_exact = 0; }
+                        else descend = true;
+                    }
+                }
+                __syncthreads();
+                if (descend) {
+                    const int v = s_vstar;
+                    uint32_t *child = ent + ENT;
+                    if (warp == 0) {
+                        ent[lane] = curP[lane]; ent[WORDS + lane] = curC[lane];          // reduced state for the exclude branch
+                        uint32_t cw = curC[lane];
+                        if (lane == (v >> 5)) cw |= 1u << (v & 31);
+                        child[lane] = curP[lane] & sadj[v * WORDS + lane];                // P \ H[v] \ {v}
+                        child[WORDS + lane] = cw;
+                    }
+                    if (tid == 0) {
+                        ent[2 * WORDS] = (uint32_t)s_size; ent[2 * WORDS + 1] = 1u; ent[2 * WORDS + 2] = (uint32_t)v;
+                        child[2 * WORDS] = (uint32_t)(s_size + 1); child[2 * WORDS + 1] = 0u; child[2 * WORDS + 2] = 0u;
+                        s_depth += 1;
+                    }
+                } else if (tid == 0) s_depth -= 1;
+            } else if (stage == 1) {                             // include branch done: exclude the vertex
+                uint32_t *child = ent + ENT;
+                const int v = (int)ent[2 * WORDS + 2];
+                if (warp == 0) {
+                    uint32_t pw = ent[lane];
+                    if (lane == (v >> 5)) pw &= ~(1u << (v & 31));
+                    child[lane] = pw;
+                    child[WORDS + lane] = ent[WORDS + lane];
+                }
+                if (tid == 0) {
+                    child[2 * WORDS] = ent[2 * WORDS]; child[2 * WORDS + 1] = 0u; child[2 * WORDS + 2] = 0u;
+                    ent[2 * WORDS + 1] = 2u;
+                    s_depth += 1;
+                }
+            } else {
+                if (tid == 0) s_depth -= 1;
+            }
+            __threadfence_block();
+            __syncthreads();
+        }
+        // result: greedy clique stands unless a strictly larger independent set was found
+        if (s_improved) {
+            __shared__ int s_base;
+            if (tid == 0) s_base = 0;
+            __syncthreads();
+            for (int w0 = 0; w0 < WORDS; ++w0) {                 // ordered compaction, one word (32 vertices) per step
+                if (warp == 0) {
+                    const uint32_t bw = bestC[w0];
+                    const bool on = (bw >> lane) & 1u;
+                    const int pos = s_base + __popc(bw & ((1u << lane) - 1u));
+                    if (on) best[pos] = w0 * 32 + lane;
+                    __syncwarp();
+                    if (lane == 0) s_base += __popc(bw);
+                }
+                __syncthreads();
+            }
+        }
+        if (tid == 0) {
+            info->M = best_n;
+            info->nodes = s_nodes;
+            info->clique_exact = s_exact;
+        }
+        return;
     }
     if (warp != 0) return;
     // ---- warp 0: exact branch and bound on the surviving set ------------------------------------------
@@ -666,7 +841,7 @@ namespace {
 
 struct SolverBufs {
     double *d_prev, *d_curr, *d_src, *d_tgt, *d_T;
-    uint32_t *d_adj, *d_adjp, *d_stackP;
+    uint32_t *d_adj, *d_adjp, *d_stackP, *d_mis;
     uint16_t *d_ord, *d_col;
     int *d_perm, *d_inv, *d_cur, *d_best, *d_idx, *d_clique, *d_final, *d_edges;
     SolverInfoDev *d_info;
@@ -682,6 +857,7 @@ int carve(nrs_ctx *ctx, int N, SolverBufs &b)
     const size_t o_prev = take(2 * n * 8), o_curr = take(2 * n * 8), o_src = take(2 * n * 8), o_tgt = take(2 * n * 8);
     const size_t o_T = take(16 * 8), o_adj = take(n * WORDS * 4), o_adjp = take(n * WORDS * 4);
     const size_t o_stack = take((n + 2) * WORDS * 4), o_ord = take((n + 2) * n * 2), o_col = take((n + 2) * n * 2);
+    const size_t o_mis = take((n + 3) * (2 * WORDS + 4) * 4);
     const size_t o_perm = take(n * 4), o_inv = take(n * 4), o_cur = take(n * 4), o_best = take(n * 4), o_idx = take((n + 2) * 4);
     const size_t o_clique = take(n * 4), o_final = take(n * 4), o_edges = take(4), o_info = take(sizeof(SolverInfoDev));
     int rc = ctx->scratch[3].reserve(off);
@@ -689,7 +865,7 @@ int carve(nrs_ctx *ctx, int N, SolverBufs &b)
     unsigned char *p = ctx->scratch[3].as<unsigned char>();
     b.d_prev = (double *)(p + o_prev); b.d_curr = (double *)(p + o_curr);
     b.d_src = (double *)(p + o_src); b.d_tgt = (double *)(p + o_tgt); b.d_T = (double *)(p + o_T);
-    b.d_adj = (uint32_t *)(p + o_adj); b.d_adjp = (uint32_t *)(p + o_adjp); b.d_stackP = (uint32_t *)(p + o_stack);
+    b.d_adj = (uint32_t *)(p + o_adj); b.d_adjp = (uint32_t *)(p + o_adjp); b.d_stackP = (uint32_t *)(p + o_stack); b.d_mis = (uint32_t *)(p + o_mis);
     b.d_ord = (uint16_t *)(p + o_ord); b.d_col = (uint16_t *)(p + o_col);
     b.d_perm = (int *)(p + o_perm); b.d_inv = (int *)(p + o_inv); b.d_cur = (int *)(p + o_cur);
     b.d_best = (int *)(p + o_best); b.d_idx = (int *)(p + o_idx); b.d_clique = (int *)(p + o_clique);
@@ -758,7 +934,7 @@ int nrs_orora_solve(nrs_ctx *ctx, const double *prev_2xN, const double *curr_2xN
     NRS_LAUNCHED();
     const long long node_limit = p->clique_node_limit > 0 ? p->clique_node_limit : 2000000;
     orora_clique_kernel<<<1, CLQ_THREADS, (size_t)N * WORDS * 4, st>>>(b.d_adjp, N, b.d_stackP, b.d_ord, b.d_col, b.d_cur,
-                                                             b.d_best, b.d_idx, b.d_info, node_limit);
+                                                             b.d_best, b.d_idx, b.d_info, node_limit, b.d_mis);
     NRS_LAUNCHED();
     orora_tail_kernel<<<1, TT, sizeof(TailSmem), st>>>(b.d_src, b.d_tgt, N, b.d_perm, b.d_best, p->noise_bound,
                                                        p->rotation_max_iterations, p->rotation_gnc_factor,

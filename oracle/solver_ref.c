@@ -168,6 +168,94 @@ static void mc_expand(mc_state *S, int depth, uint64_t *P)
     }
 }
 
+
+/* ---- maximum independent set on the complement of the pruned core ---------------------------
+ * Inlier graphs are near-cliques: inside the best_n-core almost every pair is adjacent, so the
+ * complement H is sparse and a vertex-cover style search closes in a handful of nodes where the
+ * colouring branch and bound needs thousands.  Deterministic, order-free ("Jacobi") reductions so
+ * that the CUDA kernel (one thread per vertex) follows exactly the same tree:
+ *   round: degrees d(v) = |H(v) & P| from ONE snapshot of P;
+ *          d = 0           -> v joins the set;
+ *          d = 1, nbr u    -> if d(u) = 1 (isolated edge) the lower index joins and the other leaves,
+ *                             else v joins and u leaves;
+ *   repeat until nothing changes; bound size + |P| - ceil(m / maxdeg) (m = edges of H[P]);
+ *   branch on the vertex of maximum degree (lowest index on ties): include it first, then exclude. */
+typedef struct {
+    int N, W;
+    const uint64_t *adj;      /* search-order adjacency */
+    const uint64_t *core;     /* W words */
+    int best_n;
+    uint64_t *bestC;          /* W words; valid when improved */
+    int improved;
+    long long nodes, limit;
+    int exact;
+} mis_state;
+
+static inline int bit_get(const uint64_t *b, int v) { return (int)((b[v >> 6] >> (v & 63)) & 1ull); }
+
+static void mis_rec(mis_state *S, const uint64_t *Pin, const uint64_t *Cin, int size)
+{
+    const int N = S->N, W = S->W;
+    S->nodes++;
+    uint64_t *P = (uint64_t *)malloc(4 * (size_t)W * sizeof(uint64_t));
+    uint64_t *C = P + W, *take = C + W, *rem = take + W;
+    int *d = (int *)malloc((size_t)N * sizeof(int));
+    memcpy(P, Pin, W * sizeof(uint64_t));
+    memcpy(C, Cin, W * sizeof(uint64_t));
+    for (;;) {
+        for (int v = 0; v < N; ++v) {
+            if (!bit_get(P, v)) { d[v] = -1; continue; }
+            int c = 0;
+            for (int w = 0; w < W; ++w) c += __builtin_popcountll(~S->adj[(size_t)v * W + w] & S->core[w] & P[w]);
+            d[v] = c - 1;                                   /* the complement row includes v itself */
+        }
+        memset(take, 0, 2 * (size_t)W * sizeof(uint64_t));
+        int changed = 0;
+        for (int v = 0; v < N; ++v) {
+            if (d[v] == 0) { take[v >> 6] |= 1ull << (v & 63); changed = 1; }
+            else if (d[v] == 1) {
+                int u = -1;
+                for (int w = 0; w < W && u < 0; ++w) {
+                    uint64_t x = ~S->adj[(size_t)v * W + w] & S->core[w] & P[w];
+                    if ((v >> 6) == w) x &= ~(1ull << (v & 63));
+                    if (x) u = w * 64 + __builtin_ctzll(x);
+                }
+                if (d[u] == 1) { if (v < u) { take[v >> 6] |= 1ull << (v & 63); rem[u >> 6] |= 1ull << (u & 63); changed = 1; } }
+                else { take[v >> 6] |= 1ull << (v & 63); rem[u >> 6] |= 1ull << (u & 63); changed = 1; }
+            }
+        }
+        if (!changed) break;
+        for (int w = 0; w < W; ++w) {
+            size += __builtin_popcountll(take[w]);
+            C[w] |= take[w];
+            P[w] &= ~(take[w] | rem[w]);
+        }
+    }
+    int np = 0, m2 = 0, md = 0, vstar = -1;
+    for (int v = 0; v < N; ++v)
+        if (d[v] >= 0) { ++np; m2 += d[v]; if (d[v] > md) { md = d[v]; vstar = v; } }
+    if (np == 0) {
+        if (size > S->best_n) { S->best_n = size; memcpy(S->bestC, C, W * sizeof(uint64_t)); S->improved = 1; }
+    } else {
+        const int m = m2 / 2;
+        const int ub = size + np - (m + md - 1) / md;
+        if (ub > S->best_n) {
+            if (S->nodes >= S->limit) S->exact = 0;
+            else {
+                uint64_t *Q = (uint64_t *)malloc(2 * (size_t)W * sizeof(uint64_t)), *QC = Q + W;
+                for (int w = 0; w < W; ++w) { Q[w] = P[w] & S->adj[(size_t)vstar * W + w]; QC[w] = C[w]; }   /* P \ H[v] \ {v} */
+                QC[vstar >> 6] |= 1ull << (vstar & 63);
+                mis_rec(S, Q, QC, size + 1);
+                for (int w = 0; w < W; ++w) Q[w] = P[w];
+                Q[vstar >> 6] &= ~(1ull << (vstar & 63));
+                mis_rec(S, Q, C, size);
+                free(Q);
+            }
+        }
+    }
+    free(d); free(P);
+}
+
 /* Returns clique size; clique[] holds ORIGINAL vertex ids sorted ascending
  * (nonminimal_solver.hpp:712 sorts the solver's output). */
 int orora_max_clique(const uint64_t *adj_in, int N, int W, int *clique, long long *nodes_out)
@@ -228,9 +316,37 @@ int orora_max_clique(const uint64_t *adj_in, int N, int W, int *clique, long lon
                 if (c < S.best_n) { P[v >> 6] &= ~(1ull << (v & 63)); changed = 1; }
             }
         }
-        int any = 0;
-        for (int w = 0; w < W; ++w) any |= (P[w] != 0);
-        if (any) mc_expand(&S, 0, P);
+        int any = 0, n_core = 0;
+        for (int w = 0; w < W; ++w) { any |= (P[w] != 0); n_core += __builtin_popcountll(P[w]); }
+        if (any) {
+            /* complement edges inside the core decide the exact method (both are exact) */
+            long long mh2 = 0;
+            for (int v = 0; v < N; ++v)
+                if (P[v >> 6] >> (v & 63) & 1ull) {
+                    int c = 0;
+                    for (int w = 0; w < W; ++w) c += __builtin_popcountll(~adj[(size_t)v * W + w] & P[w]);
+                    mh2 += c - 1;
+                }
+            if (mh2 / 2 <= 3LL * n_core) {
+                mis_state M;
+                M.N = N; M.W = W; M.adj = adj; M.core = P; M.best_n = S.best_n; M.improved = 0;
+                M.bestC = (uint64_t *)calloc(W, sizeof(uint64_t));
+                M.nodes = 0; M.limit = 2000000; M.exact = 1;
+                uint64_t *C0 = (uint64_t *)calloc(W, sizeof(uint64_t));
+                uint64_t *P0 = (uint64_t *)malloc(W * sizeof(uint64_t));
+                memcpy(P0, P, W * sizeof(uint64_t));
+                mis_rec(&M, P0, C0, 0);
+                if (M.improved) {
+                    int k = 0;
+                    for (int v = 0; v < N; ++v) if (M.bestC[v >> 6] >> (v & 63) & 1ull) S.best[k++] = v;
+                    S.best_n = k;
+                }
+                S.nodes = M.nodes;
+                free(M.bestC); free(C0); free(P0);
+            } else {
+                mc_expand(&S, 0, P);
+            }
+        }
         free(P);
     }
     int n = S.best_n;
