@@ -112,7 +112,7 @@ def run_reference(args, rank, world):
     from oracle import pyoracle as O
     O.build()
     db, queries, _ = workload()
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0))
     O.lib().oracle_set_threads(cores)
     # a step = one query over a bounded sample of D_s keyframes (cost is uniform per keyframe);
     # D_s is sized so K steps take about a minute, and the rate is scaled back to the 10k DB
@@ -273,7 +273,7 @@ def run_ours(args, rank, world, local_rank):
             except Exception:
                 traffic = None
         # bounded CPU baseline on this box's host cores (oracle port, all threads)
-        cores = os.cpu_count() or 1
+        cores = len(os.sched_getaffinity(0))
         O.lib().oracle_set_threads(cores)
         O.sc_search(queries[0], db, want_all=False)
         n_cpu, t0 = 0, time.perf_counter()
@@ -398,7 +398,7 @@ def orora_block(pkg, ctx, n_pairs=40, cpu_pairs=3):
             "gpu_launches_per_pair": launches / n_pairs,
             "roofline": {"bound": "hbm (latency-bound in practice)", "algorithmic_bytes_per_pair": alg_bytes,
                          "achieved_GBps": alg_bytes / (dt / n_pairs) / 1e9, "frac_of_measured_peak": alg_bytes / (dt / n_pairs) / 1e9 / load_peaks()[0]},
-            "cpu_baseline": {"value": 1.0 / cpu_dt, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+            "cpu_baseline": {"value": 1.0 / cpu_dt, "unit": "pairs/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
                              "cv2_threads": cv2.getNumThreads(),
                              "sample": f"{cpu_pairs} pairs, oracle/frontend_ref.py (real cv2) + oracle/solver_ref.c"}}
 

@@ -95,7 +95,9 @@ int nrs_sc_dist_direct(nrs_ctx *ctx, const double *sc1, const double *sc2, doubl
 int nrs_sc_pair(nrs_ctx *ctx, const double *sc1, const double *sc2, double *dist, int32_t *shift);
 
 /* The database mirrors SCManager::polarcontexts_ (Scancontext.h:111) on the device:
- * keyframe i occupies bytes [9600*i, 9600*(i+1)).  Append is thread-safe against query;
+ * through this ABI every descriptor is the reference's 9600-byte column-major layout; on the
+ * device keyframe i is a 10080-byte record (30 column pairs of 320 B, each padded to 336 B
+ * for conflict-free shared-memory reads).  Append is thread-safe against query;
  * a query sees a consistent prefix (the reference's node appends and queries from two
  * threads without a lock, SC/../src/laserPosegraphOptimization.cpp:492 vs :561). */
 int nrs_sc_db_create(nrs_ctx *ctx, int capacity_hint, nrs_sc_db **out);
@@ -111,6 +113,8 @@ int nrs_sc_db_append_cloud(nrs_sc_db *db, const float *xyz_Px3, int P, double li
                            double max_radius, double *desc_out);
 /* copy descriptors [first, first+count) back to host */
 int nrs_sc_db_read(nrs_sc_db *db, int first, int count, double *desc_host);
+/* base of the packed device records (10080 B per keyframe, see above); for diagnostics and
+ * peer-memory exchange only -- use nrs_sc_db_read for the reference layout */
 const double *nrs_sc_db_device_ptr(nrs_sc_db *db);
 
 /* The search loop of detectLoopClosureID (Scancontext.cpp:380-396).

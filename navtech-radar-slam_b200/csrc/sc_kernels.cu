@@ -13,11 +13,11 @@
 // With that, distances are bit-identical to the CPU restatement in oracle/sc_ref.c for
 // binary {0,c} descriptors (every partial sum is exact) and for general-valued ones.
 //
-// Kernel sc_search2_kernel (K10): one warp per keyframe, persistent grid (one 16-warp CTA per SM,
+// Kernel sc_search_kernel (K10): one warp per keyframe, persistent grid (one 16-warp CTA per SM,
 // ~220 KB of shared memory).  Each keyframe record (10080 B: 30 column pairs padded to 336 B so the
 // tile is bank-conflict free as it lands) is staged by ONE 1-D TMA bulk copy (cp.async.bulk ->
 // UBLKCP) onto a per-warp mbarrier; the prepared query arrives the same way.  Both arg-mins of the
-// reference are filtered in f32 and certified in f64 (see the K10 v2 block below); certification of
+// reference are filtered in f32 and certified in f64 (see the K10 block below); certification of
 // the 7-shift distance is skipped for keyframes that provably cannot beat the best distance found so
 // far anywhere on the GPU (exact pruning; disabled when per-keyframe results are requested).
 // Bound: HBM.  Algorithmic bytes per keyframe = 9600 (f64 20x60, the reference's MatrixXd);
@@ -92,22 +92,23 @@ __device__ __forceinline__ bool better(double d1, int k1, double d2, int k2)
 }
 
 // =================================================================================================
-// K10 v2: f32 filter + f64 certification
+// K10: f32 filter + f64 certification
 // =================================================================================================
 // The reference's arithmetic is f64, but both of its decisions per keyframe are arg-mins:
 //   (B) s0 = argmin_s ||vq - shift(vk, s)||            over 60 shifts   (fastAlignUsingVkey)
 //   (C) argmin over the 7 shifts around s0 of distDirectSC              (distanceBtnScanContext)
-// v2 evaluates every candidate of both arg-mins in f32 (FFMA, 2x the FP64 rate, half the shared
+// The kernel evaluates every candidate of both arg-mins in f32 (FFMA, 2x the FP64 rate, half the shared
 // memory traffic), keeps the ones within a rigorous error bound of the f32 minimum, and re-evaluates
 // ONLY those in the reference's exact f64 order.  The winner and its value are therefore bit-identical
-// to v1 / the oracle; the FP64 pipe does ~1/4 of the work.
+// to an all-f64 evaluation / the oracle (round 1's first kernel was all-f64: 110 us per 10k query,
+// FP64 pipe 27 %; this one is at ~53 us with the FP64 pipe at 9 %).
 //   bound B: |n32_s - n64_s| <= 2^-16.8 (|vq|^2+|vk|^2)  (inputs rounded to f32, 60 fused terms);
 //            kept: n32_s <= min + 2^-13 (|vq|^2 + |vk|^2)                     (5x margin over 2e)
 //   bound C: |d32 - d64| <= 2^-17.2                      (unit-norm cosine terms, <= 60 of them);
 //            kept: d32 <= min + 2^-13                                          (9x margin over 2e)
 // A non-finite f32 intermediate (inputs beyond ~1e18) keeps every candidate, i.e. falls back to f64.
-constexpr int W2 = 16;                   // warps per CTA
-constexpr int THREADS2 = W2 * 32;
+constexpr int WARPS = 16;                   // warps per CTA
+constexpr int THREADS = WARPS * 32;
 // f32 query columns are stored as pairs padded to 176 B (44 floats): lanes read columns 2l + const, i.e.
 // one pair apart, and 176 B = 11 x 16 B makes those eight 16-byte accesses hit eight different banks
 constexpr int QPAIR32 = 44;
@@ -118,7 +119,7 @@ constexpr int VKF_STRIDE = 136;
 constexpr float EPS_B = 1.220703125e-4f; // 2^-13
 constexpr float EPS_C = 1.220703125e-4f; // 2^-13
 
-struct Warp2Smem {
+struct WarpSmem {
     double   tile[KREC];                 // TMA destination: padded keyframe record, consumed by phase A and re-armed at once
     double   vk[S];                      // keyframe sector key (f64, for certification)
     double   kn[S];                      // keyframe column norms (f64)
@@ -145,11 +146,11 @@ struct QPrep {
 static_assert(sizeof(QPrep) % 16 == 0, "QPrep must be a multiple of 16 bytes for the bulk copy");
 static_assert(offsetof(QPrep, qvf) % 16 == 0 && offsetof(QPrep, q32) % 16 == 0, "LDS.128 alignment");
 
-struct Block2Smem {
+struct BlockSmem {
     QPrep  q;
-    Warp2Smem w[W2];
-    double red_d[W2];
-    int    red_pos[W2], red_idx[W2], red_s[W2];
+    WarpSmem w[WARPS];
+    double red_d[WARPS];
+    int    red_pos[WARPS], red_idx[WARPS], red_s[WARPS];
     int    is_last;
     uint64_t qbar;
 };
@@ -161,7 +162,7 @@ __device__ __forceinline__ float warp_min_f(float v)
     return v;
 }
 
-// one small CTA per search: query -> QPrep (global), same arithmetic as v1's per-CTA staging
+// one small CTA per search: query -> QPrep (global), the reference's sector key / column norm arithmetic
 __global__ void __launch_bounds__(64)
 sc_prep_query_kernel(const double *__restrict__ query, QPrep *__restrict__ out,
                      unsigned long long *__restrict__ gbest)
@@ -200,21 +201,21 @@ sc_prep_query_kernel(const double *__restrict__ query, QPrep *__restrict__ out,
     }
 }
 
-__global__ void __launch_bounds__(THREADS2, 1)
-sc_search2_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep,
+__global__ void __launch_bounds__(THREADS, 1)
+sc_search_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep,
                   const int32_t *__restrict__ cand, int first, int n_items, int idx_offset,
                   double *__restrict__ dist_all, int32_t *__restrict__ shift_all,
                   BlockResult *__restrict__ block_results, unsigned int *__restrict__ ticket,
                   unsigned long long *__restrict__ gbest, nrs_sc_result *__restrict__ final_result)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Block2Smem &sm = *reinterpret_cast<Block2Smem *>(smem_raw);
+    BlockSmem &sm = *reinterpret_cast<BlockSmem *>(smem_raw);
     const bool prune = (dist_all == nullptr) && (shift_all == nullptr);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    Warp2Smem &ws = sm.w[warp];
+    WarpSmem &ws = sm.w[warp];
     double *scr = reinterpret_cast<double *>(&ws.vkf[0][0]);     // certification scratch (60 doubles)
-    const int gw = blockIdx.x * W2 + warp;
-    const int nw = gridDim.x * W2;
+    const int gw = blockIdx.x * WARPS + warp;
+    const int nw = gridDim.x * WARPS;
 
     if (lane == 0) {
         nrs::mbar_init(&ws.bar, 1);
@@ -528,13 +529,13 @@ sc_search2_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep
         }
     }
 
-    // ---- block reduce, then last-block-done grid reduce (same as v1) --------------------------------
+    // ---- block reduce, then last-block-done grid reduce ---------------------------------------------
     if (lane == 0) { sm.red_d[warp] = best_d; sm.red_pos[warp] = best_pos; sm.red_idx[warp] = best_idx; sm.red_s[warp] = best_s; }
     __syncthreads();
     if (threadIdx.x == 0) {
         double d = sm.red_d[0];
         int p = sm.red_pos[0], ix = sm.red_idx[0], sh = sm.red_s[0];
-        for (int w = 1; w < W2; ++w)
+        for (int w = 1; w < WARPS; ++w)
             if (better(sm.red_d[w], sm.red_pos[w], d, p)) { d = sm.red_d[w]; p = sm.red_pos[w]; ix = sm.red_idx[w]; sh = sm.red_s[w]; }
         BlockResult br;
         br.dist = d; br.pos = p; br.idx = ix; br.shift = sh; br.pad = 0;
@@ -744,14 +745,14 @@ struct nrs_sc_db {
 
 namespace {
 
-int search2_smem_bytes() { return (int)sizeof(Block2Smem); }
+int search_smem_bytes() { return (int)sizeof(BlockSmem); }
 
 int configure_search_kernel()
 {
     static int done = 0;
     if (!done) {
-        NRS_CUDA(cudaFuncSetAttribute(sc_search2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      search2_smem_bytes()));
+        NRS_CUDA(cudaFuncSetAttribute(sc_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      search_smem_bytes()));
         done = 1;
     }
     return NRS_OK;
@@ -769,12 +770,12 @@ int launch_search(nrs_ctx *ctx, const double *d_db, const double *d_query, QPrep
     unsigned long long *d_gbest = reinterpret_cast<unsigned long long *>(d_ticket + 2);
     sc_prep_query_kernel<<<1, 64, 0, ctx->stream>>>(d_query, d_qprep, d_gbest);
     NRS_LAUNCHED();
-    int blocks = (n_items + W2 - 1) / W2;
+    int blocks = (n_items + WARPS - 1) / WARPS;
     blocks = std::max(1, std::min(blocks, max_blocks));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(blocks);
-    cfg.blockDim = dim3(THREADS2);
-    cfg.dynamicSmemBytes = search2_smem_bytes();
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = search_smem_bytes();
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -782,7 +783,7 @@ int launch_search(nrs_ctx *ctx, const double *d_db, const double *d_query, QPrep
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const QPrep *c_qprep = d_qprep;
-    NRS_CUDA(cudaLaunchKernelEx(&cfg, sc_search2_kernel, d_db, c_qprep, d_cand, first, n_items, idx_offset,
+    NRS_CUDA(cudaLaunchKernelEx(&cfg, sc_search_kernel, d_db, c_qprep, d_cand, first, n_items, idx_offset,
                                 d_dist_all, d_shift_all, d_block, d_ticket, d_gbest, d_result));
     NRS_LAUNCHED();
     return NRS_OK;
