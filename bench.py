@@ -159,7 +159,8 @@ def run_ours(args, rank, world, local_rank):
     # ---- shard (round-robin) and replicate so that consecutive steps never re-read L2-resident data
     mine = np.arange(rank, D_KEYFRAMES, world)
     local = np.ascontiguousarray(db[mine])
-    slice_bytes = local.shape[0] * DESC_BYTES
+    stream_bytes = L.nrs_sc_filter_record_bytes()                  # bytes per keyframe a query actually streams
+    slice_bytes = local.shape[0] * stream_bytes
     n_rep = max(4, int(np.ceil(300e6 / slice_bytes)))
     reps = []
     for r in range(n_rep):
@@ -173,9 +174,16 @@ def run_ours(args, rank, world, local_rank):
     allrec = torch.zeros(16 * world, dtype=torch.uint8, device=dev)
     cur = torch.cuda.current_stream(dev)
 
+    # N > 1: the per-shard records are exchanged and merged inside the search kernel over peer memory
+    # (NVLink); if CUDA IPC is unavailable on this box the NCCL all_gather path is used and reported
+    peer = world > 1 and sc.enable_peer_exchange(reps, rank, world, dev)
+
     def step_device(i):
         """inputs resident in HBM; result record(s) stay on the device"""
         q = q_dev[i % 64]
+        if peer:
+            reps[i % n_rep].query_dev_sharded(q.data_ptr(), 0, n_local, rec.data_ptr())
+            return
         reps[i % n_rep].query_dev(q.data_ptr(), 0, n_local, 0, rec.data_ptr())
         if world > 1:
             cur.wait_stream(nrs_stream)
@@ -188,7 +196,9 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
 
     # ---- correctness gate before timing: the sharded answer equals the oracle's on 2 queries
-    sharded = sc.ShardedSCDatabase(rank, world, ctx=ctx)
+    sharded = sc.ShardedSCDatabase(rank, world, ctx=ctx, exchange="nccl")
+    if peer:
+        sharded.exchange = "peer"
     sharded.db.close()
     sharded.db = reps[0]
     sharded._local_n = n_local
@@ -212,6 +222,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
         time.sleep(0.12)
+    barrier()          # every rank enters the timed region together (the exchange makes them lock-step anyway)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = L.nrs_kernel_launches()
     t0 = time.perf_counter()
@@ -285,12 +296,13 @@ def run_ours(args, rank, world, local_rank):
             "metric": "sc_loop_queries_per_s_10k_db", "value": value, "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(CONFIG, parallelism=f"keyframe-sharded x{world} (round-robin), 1 all_gather of 16 B/rank",
+            "config": dict(CONFIG, parallelism=f"keyframe-sharded x{world} (round-robin), records exchanged "
+                                           + ("in-kernel over peer memory (NVLink)" if peer else "by 1 all_gather of 16 B/rank" if world > 1 else "n/a"),
                            l2=f"inputs larger than L2: {n_rep} database replicas rotated per step "
                               f"({n_rep * slice_bytes / 1e6:.0f} MB per GPU > 126 MB L2)",
                            parity_gate=parity),
             "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": DESC_BYTES, "d2h_bytes_per_step": 16 * world,
-                    "api": "ShardedSCDatabase.query -> nrs_sc_query_dev (+all_gather), host query in, host result out"},
+                    "api": "ShardedSCDatabase.query -> nrs_sc_query_dev" + ("_sharded" if peer else "") + ", host query in, host result out"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "sc_search_kernel", "achieved": achieved, "peak": peak,

@@ -95,9 +95,10 @@ int nrs_sc_dist_direct(nrs_ctx *ctx, const double *sc1, const double *sc2, doubl
 int nrs_sc_pair(nrs_ctx *ctx, const double *sc1, const double *sc2, double *dist, int32_t *shift);
 
 /* The database mirrors SCManager::polarcontexts_ (Scancontext.h:111) on the device:
- * through this ABI every descriptor is the reference's 9600-byte column-major layout; on the
- * device keyframe i is a 10080-byte record (30 column pairs of 320 B, each padded to 336 B
- * for conflict-free shared-memory reads).  Append is thread-safe against query;
+ * keyframe i occupies bytes [9600*i, 9600*(i+1)) of the descriptor array, verbatim.  Beside it
+ * the database keeps, per keyframe, the f64 sector key and column norms (960 B) and the
+ * f32 filter record the search streams (nrs_sc_filter_record_bytes() bytes), both derived
+ * on the device at append time.  Append is thread-safe against query;
  * a query sees a consistent prefix (the reference's node appends and queries from two
  * threads without a lock, SC/../src/laserPosegraphOptimization.cpp:492 vs :561). */
 int nrs_sc_db_create(nrs_ctx *ctx, int capacity_hint, nrs_sc_db **out);
@@ -113,9 +114,30 @@ int nrs_sc_db_append_cloud(nrs_sc_db *db, const float *xyz_Px3, int P, double li
                            double max_radius, double *desc_out);
 /* copy descriptors [first, first+count) back to host */
 int nrs_sc_db_read(nrs_sc_db *db, int first, int count, double *desc_host);
-/* base of the packed device records (10080 B per keyframe, see above); for diagnostics and
- * peer-memory exchange only -- use nrs_sc_db_read for the reference layout */
+/* device base of the descriptor array (9600 B per keyframe, the reference's layout) */
 const double *nrs_sc_db_device_ptr(nrs_sc_db *db);
+/* bytes per keyframe that an exhaustive query streams from HBM (the f32 filter record) */
+int nrs_sc_filter_record_bytes(void);
+
+/* Multi-GPU (one process per GPU, keyframe g stored on rank g % world as local slot g / world):
+ * result exchange through peer memory instead of a collective.  Each rank creates its slot array
+ * and exports a CUDA IPC handle (NRS_SC_XCHG_HANDLE_BYTES bytes); the host program gathers the
+ * world's handles any way it likes (MPI, torch.distributed, a file) and hands them to _open in
+ * rank order.  nrs_sc_query_dev_sharded then searches local slots [first, last) and the search
+ * kernel's last CTA writes this rank's record into every peer's HBM over NVLink, waits for the
+ * world's records and merges them: *result_dev holds the GLOBAL (dist, idx, shift) on every
+ * rank, ties to the lowest global index like the sequential scan (Scancontext.cpp:380-396).
+ * All ranks must issue the same sequence of sharded queries on a database.  A peer that does
+ * not answer within ~3 s yields idx == -2 (dist 1e7) instead of a hang. */
+#define NRS_SC_XCHG_HANDLE_BYTES 64
+int nrs_sc_xchg_create(nrs_sc_db *db, int world, int rank, unsigned char *handle_out);
+int nrs_sc_xchg_open(nrs_sc_db *db, const unsigned char *handles_world_x_64);
+int nrs_sc_query_dev_sharded(nrs_sc_db *db, const double *query_dev, int first, int last,
+                             nrs_sc_result *result_dev);
+/* diagnostics: %globaltimer (ns) stamps of the database's most recent search, taken by its last
+ * CTA: [0] tail entered, [1] local result ready, [2] record + flag written to the peers
+ * (sharded queries only), [3] result written.  Synchronises the stream. */
+int nrs_sc_db_tail_times(nrs_sc_db *db, uint64_t *t_ns4);
 
 /* The search loop of detectLoopClosureID (Scancontext.cpp:380-396).
  *   candidate_idx == NULL : exhaustive over keyframes [first, last)   (north_star)

@@ -14,14 +14,13 @@
 // binary {0,c} descriptors (every partial sum is exact) and for general-valued ones.
 //
 // Kernel sc_search_kernel (K10): one warp per keyframe, persistent grid (one 16-warp CTA per SM,
-// ~220 KB of shared memory).  Each keyframe record (10080 B: 30 column pairs padded to 336 B so the
-// tile is bank-conflict free as it lands) is staged by ONE 1-D TMA bulk copy (cp.async.bulk ->
-// UBLKCP) onto a per-warp mbarrier; the prepared query arrives the same way.  Both arg-mins of the
-// reference are filtered in f32 and certified in f64 (see the K10 block below); certification of
-// the 7-shift distance is skipped for keyframes that provably cannot beat the best distance found so
-// far anywhere on the GPU (exact pruning; disabled when per-keyframe results are requested).
+// ~205 KB of shared memory).  Each keyframe's 5536-byte f32 filter record (written at append time)
+// is staged by ONE 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) onto a per-warp mbarrier, two
+// records in flight per warp; the prepared query arrives the same way.  All three arg-mins of the
+// reference are filtered in f32 and certified in f64 from the canonical 9600-byte descriptor (see
+// the K10 block below); only keyframes the filter cannot rule out are ever read in f64.
 // Bound: HBM.  Algorithmic bytes per keyframe = 9600 (f64 20x60, the reference's MatrixXd);
-// per query = 9600*D + 9600 + 16.
+// per query = 9600*D + 9600 + 16; bytes actually streamed = 5536*D + survivors.
 #include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
@@ -35,13 +34,6 @@ namespace {
 constexpr int R = NRS_SC_RINGS;      // 20
 constexpr int S = NRS_SC_SECTORS;    // 60
 constexpr int DESC = R * S;          // 1200 doubles = 9600 B (the reference's MatrixXd)
-// Device-side keyframe record: the 30 column pairs of a descriptor, each padded from 320 to 336
-// bytes, so that the record lands in shared memory by ONE bulk copy already free of bank conflicts
-// for the lane-per-column-pair reads (336 = 21 x 16 B, 21 mod 8 = 5).  10080 B per keyframe.
-constexpr int PAIR_D = 42;           // doubles per padded column pair
-constexpr int KREC = (S / 2) * PAIR_D;   // 1260 doubles
-__host__ __device__ constexpr int col_off(int c) { return (c >> 1) * PAIR_D + (c & 1) * R; }
-constexpr int QSTRIDE = 22;          // padded query column stride (doubles): LDS.128 conflict-free
 constexpr int NSHIFT = 7;            // 2 * round(0.5 * SEARCH_RATIO * 60) + 1   (Scancontext.cpp:123)
 constexpr int RADIUS = 3;
 constexpr double SENTINEL = 10000000.0;   // Scancontext.cpp:134,362
@@ -92,328 +84,443 @@ __device__ __forceinline__ bool better(double d1, int k1, double d2, int k2)
 }
 
 // =================================================================================================
-// K10: f32 filter + f64 certification
+// K10: f32 filter over a compact filter record + f64 certification of the survivors
 // =================================================================================================
-// The reference's arithmetic is f64, but both of its decisions per keyframe are arg-mins:
+// The reference's arithmetic is f64, but everything it decides per query is an arg-min:
 //   (B) s0 = argmin_s ||vq - shift(vk, s)||            over 60 shifts   (fastAlignUsingVkey)
 //   (C) argmin over the 7 shifts around s0 of distDirectSC              (distanceBtnScanContext)
-// The kernel evaluates every candidate of both arg-mins in f32 (FFMA, 2x the FP64 rate, half the shared
-// memory traffic), keeps the ones within a rigorous error bound of the f32 minimum, and re-evaluates
-// ONLY those in the reference's exact f64 order.  The winner and its value are therefore bit-identical
-// to an all-f64 evaluation / the oracle (round 1's first kernel was all-f64: 110 us per 10k query,
-// FP64 pipe 27 %; this one is at ~53 us with the FP64 pipe at 9 %).
-//   bound B: |n32_s - n64_s| <= 2^-16.8 (|vq|^2+|vk|^2)  (inputs rounded to f32, 60 fused terms);
-//            kept: n32_s <= min + 2^-13 (|vq|^2 + |vk|^2)                     (5x margin over 2e)
-//   bound C: |d32 - d64| <= 2^-17.2                      (unit-norm cosine terms, <= 60 of them);
-//            kept: d32 <= min + 2^-13                                          (9x margin over 2e)
-// A non-finite f32 intermediate (inputs beyond ~1e18) keeps every candidate, i.e. falls back to f64.
-constexpr int WARPS = 16;                   // warps per CTA
+//   (D) argmin over keyframes of (C)                                     (detectLoopClosureID)
+// The search streams, per keyframe, a 5536-byte FILTER RECORD written once at append time
+// (sc_pack_kernel): the 60 columns normalised to unit length in f64 and rounded to f32 (column
+// pairs padded to 176 B so the tile lands bank-conflict free), the sector key in f32, its squared
+// norm, and the 60-bit mask of zero-norm columns (exact, from the f64 norms).  Every candidate of
+// (B) and (C) is evaluated in f32 from that record; candidates that a rigorous error bound cannot
+// separate from the f32 minimum are re-evaluated in the reference's exact f64 order from the
+// canonical 9600-byte descriptor (and the f64 keys stored beside it), so winner and value are
+// bit-identical to an all-f64 evaluation / the oracle.  (D) is pruned the same way: a keyframe
+// whose f32 lower bound exceeds the smallest f32 upper bound seen anywhere on the GPU can neither
+// win nor tie; the rest (a handful) go on a survivor list that the last CTA certifies.
+//   bound B: n_s = |vq|^2 + |vk|^2 - 2 corr(s); the first two terms are common to all shifts and
+//            cancel in comparisons, corr(s) is two 30-term FFMA chains over inputs rounded to
+//            f32: |err| <= 33 * 2^-24 * (|vq|^2 + |vk|^2) = 2^-18.9 (..), + final rounding
+//            2^-23 (..)  =>  e_B <= 2^-18.8 (|vq|^2 + |vk|^2);
+//            kept: n32_s <= min + 2^-15 (|vq|^2 + |vk|^2)                  (7x margin over 2 e_B)
+//   bound C: unit columns rounded to f32 (2 * 2^-24), two 10-term FFMA chains + 1 add
+//            (11 * 2^-24), 6 adds on the path of the column sum (6 * 2^-24 per unit of |term|),
+//            v / cnt and 1 - x (3 * 2^-24): e_C <= 22 * 2^-24 = 2^-19.5;
+//            kept within a keyframe: d32 <= min + 2^-17 (2.8x over 2 e_C); across keyframes X is
+//            dropped when min32_X - 2^-17 > min32_Y + 2^-17 for some Y (5.7x over e_C each side).
+// Inputs outside the range where those bounds hold (non-finite entries, column magnitudes beyond
+// 1e150 or below 1e-140, sector keys beyond 1e15 or below 1e-15) are flagged at pack time / query
+// preparation (HAZ_B, HAZ_C): flagged keyframes keep every candidate, always survive and never
+// tighten the bound, i.e. they fall back to the all-f64 evaluation.
+constexpr int WARPS = 24;                   // warps per CTA (768 threads, <= 85 registers each)
 constexpr int THREADS = WARPS * 32;
-// f32 query columns are stored as pairs padded to 176 B (44 floats): lanes read columns 2l + const, i.e.
-// one pair apart, and 176 B = 11 x 16 B makes those eight 16-byte accesses hit eight different banks
-constexpr int QPAIR32 = 44;
-__host__ __device__ constexpr int q32_off(int c) { return (c >> 1) * QPAIR32 + (c & 1) * R; }
-// row stride of the four aligned sector-key copies: 136 floats = 34 x 16 B, 34 mod 8 = 2, so that the
-// eight lanes of a quarter-warp (two window bases x four copies) hit eight different banks
-constexpr int VKF_STRIDE = 136;
-constexpr float EPS_B = 1.220703125e-4f; // 2^-13
-constexpr float EPS_C = 1.220703125e-4f; // 2^-13
+// f32 columns are stored as pairs padded to 176 B (44 floats): lanes read columns 2l + const, i.e.
+// one pair apart, and 176 B = 11 x 16 B makes the eight 16-byte accesses of a quarter-warp hit
+// eight different banks
+constexpr int FPAIR = 44;
+__host__ __device__ constexpr int f32_off(int c) { return (c >> 1) * FPAIR + (c & 1) * R; }
+constexpr int F_VK = (S / 2) * FPAIR;       // float index of the f32 sector key inside a filter record
+constexpr int F_B2 = F_VK + S;              // |vk|^2 (f32), one pad float, then the 64-bit flag word
+constexpr int FREC_F = F_B2 + 4;            // 1384 floats
+constexpr int FREC_BYTES = FREC_F * 4;      // 5536 B per keyframe
+static_assert(FREC_BYTES % 16 == 0 && (F_VK * 4) % 16 == 0 && ((F_B2 + 2) * 4) % 8 == 0, "filter record alignment");
+constexpr int KEYS_D = 2 * S;               // f64 side record: vk[60], kn[60]
+constexpr unsigned long long MASK60 = (1ull << S) - 1ull;
+constexpr unsigned long long HAZ_B = 1ull << 62, HAZ_C = 1ull << 63;
+// Filter B: lane l scores the shifts 2l and 2l+1 from ONE sliding window of the doubled query key that
+// starts at index 2l.  Two copies (copy m holds vq[(j + 2m) mod 60] at j) make every window start 16-byte
+// aligned: lane l reads copy l & 1 from float index 4 (l >> 1).  Copy stride 144 floats = 36 x 16 B,
+// 36 mod 8 = 4: the eight lanes of a quarter-warp (four bases x two copies) hit eight different banks.
+constexpr int QW_STRIDE = 144;
+constexpr float EPS_B = 3.0517578125e-5f;   // 2^-15
+constexpr float EPS_C = 7.62939453125e-6f;  // 2^-17
+
+struct __align__(16) Survivor {          // 16 bytes, one per keyframe the filter could not rule out
+    int   item;                          // position in the searched range / candidate list
+    int   code;                          // s0 | candC << 8 | certain << 16
+    float lo;                            // f32 minimum of the 7 distances
+    int   pad;
+};
 
 struct WarpSmem {
-    double   tile[KREC];                 // TMA destination: padded keyframe record, consumed by phase A and re-armed at once
-    double   vk[S];                      // keyframe sector key (f64, for certification)
-    double   kn[S];                      // keyframe column norms (f64)
-    float    vkf[4][VKF_STRIDE];         // f32 copies, doubled; copy m holds vk[(j + m) mod 60] so that every
-                                         // lane's window starts 16-byte aligned (LDS.128).  Once the filter
-                                         // is done the first 480 bytes double as certification scratch.
+    float    tile[FREC_F];               // TMA destination: the warp's filter record; consumed into registers
+                                         // half way through the keyframe and re-armed at once
+    double   scr[S + 4];                 // certification scratch
+    Survivor first;                      // the warp's first keyframe: judged after the loop, when a bound exists
     uint64_t bar;
     uint64_t pad;
 };
 
-// Everything a CTA needs of the query, prepared ONCE per search by sc_prep_query_kernel and
-// pulled into shared memory with a single TMA bulk copy (it used to be recomputed by every CTA:
-// 14 % of the kernel's warp samples).
-struct QPrep {
-    double q64[S * QSTRIDE];             // query, f64, padded columns (certification)
-    float  q32[(S / 2) * QPAIR32];       // query, f32, padded column pairs (filter)
-    double qn[S], qv[S];
-    float  qnf[S];
-    float  qvf[S];
-    unsigned long long qzero;            // bit c set <=> query column c has zero norm
+// What the filter needs of the query; every CTA derives it from the 9600-byte query in its prologue,
+// while its first keyframe records are still in flight (prepare_query) ...
+constexpr int QH_PAIRS = 64;                // pair p holds columns (2p) mod 60, (2p + 1) mod 60: a lane's eight
+                                            // consecutive columns never wrap, so its reads stay conflict-free
+struct QHot {
+    float  qh[QH_PAIRS * FPAIR];         // unit query columns, f32, padded pairs, doubled (filter C)
+    float  qw[2][QW_STRIDE];             // f32 sector key, doubled, two aligned copies (filter B)
+    unsigned long long qflags;           // bit c <=> query column c has zero norm; HAZ_B / HAZ_C
     float  qv_norm2;                     // |vq|^2 (f32), inflated
     float  pad_[1];
 };
-static_assert(sizeof(QPrep) % 16 == 0, "QPrep must be a multiple of 16 bytes for the bulk copy");
-static_assert(offsetof(QPrep, qvf) % 16 == 0 && offsetof(QPrep, q32) % 16 == 0, "LDS.128 alignment");
+// ... and the f64 side for the (rare) certification: keys and norms here, the columns straight from the query
+struct QCold {
+    const double *q64;                   // the query itself (global memory, the reference's layout)
+    double qn[S], qv[S];
+};
+static_assert(offsetof(QHot, qh) % 16 == 0 && offsetof(QHot, qw) % 16 == 0, "LDS.128 alignment");
+
+// search state shared by the launches of one database (device memory, 32 bytes)
+struct SearchState {
+    unsigned int ticket;                 // last-block-done counter (zero between launches)
+    unsigned int gub;                    // smallest f32 upper bound of any keyframe's distance (order-preserving bits)
+    unsigned int n_surv;                 // survivor list length
+    unsigned int pad;
+    unsigned long long t_ns[4];          // %globaltimer of the last launch: tail entered, local result ready,
+                                         // record + flag written to the peers, world's records merged
+};
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Result exchange between the ranks of a keyframe-sharded database (one process per GPU): every
+// rank owns a slot array in its own HBM, slot[parity][source rank], mapped into all peers (CUDA IPC over
+// NVLink).  The last CTA of the search writes the rank's 16-byte record straight into every peer's
+// array (payload, fence.sys, epoch flag), waits until the world's records of this epoch have arrived
+// in its own array and merges them -- no collective call, no host round trip.  Slots are reused every
+// second query: a rank can only start writing epoch e+2 after it has seen every peer's e+1 flag, and a
+// peer raises that flag only after it has finished reading epoch e.
+struct XchgSlot {
+    double dist;
+    int    idx;
+    int    shift;
+    unsigned int epoch;
+    unsigned int pad[3];
+};
+struct XchgView {
+    XchgSlot *const *peers;              // device array of `world` base pointers (entry `rank` = local array)
+    int world, rank;
+    unsigned int epoch;
+};
+constexpr int XCHG_MAX_WORLD = 32;       // one lane per peer
+constexpr long long XCHG_TIMEOUT_CYCLES = 6000000000ll;   // ~3 s: a peer that never answers must not hang the GPU
 
 struct BlockSmem {
-    QPrep  q;
+    QHot   q;
+    QCold  qc;
     WarpSmem w[WARPS];
     double red_d[WARPS];
     int    red_pos[WARPS], red_idx[WARPS], red_s[WARPS];
+    unsigned int ub;                     // smallest upper bound produced by this CTA (order-preserving bits)
     int    is_last;
-    uint64_t qbar;
+    unsigned long long prep_flags;
+    float  prep_sq[S];
+    float  prep_vf[S];
+    double prep_am[S];
+    double prep_inv[S];
 };
 
+// warp-wide f32 minimum in one instruction (sm_100a: CREDUX.MIN.F32)
 __device__ __forceinline__ float warp_min_f(float v)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
+    float r;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+// order-preserving f32 -> u32 (atomicMin on the result == min on the floats)
+__device__ __forceinline__ unsigned int ord_f32(float f)
+{
+    const unsigned int b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float unord_f32(unsigned int u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__device__ __forceinline__ int wrap60(int s)          // s in [-60, 120) -> [0, 60)
+{
+    s = s < 0 ? s + S : s;
+    return s >= S ? s - S : s;
 }
 
-// one small CTA per search: query -> QPrep (global), the reference's sector key / column norm arithmetic
-__global__ void __launch_bounds__(64)
-sc_prep_query_kernel(const double *__restrict__ query, QPrep *__restrict__ out,
-                     unsigned long long *__restrict__ gbest)
+// magnitude window in which the f32 filter's error bounds hold (see the K10 header)
+__device__ __forceinline__ bool hazard_col(double mx) { return !(mx <= 1e150) || (mx != 0.0 && mx < 1e-140); }
+__device__ __forceinline__ bool hazard_key(double mx) { return !(mx <= 1e15) || (mx != 0.0 && mx < 1e-15); }
+
+// Query preparation, once per CTA (threads 0..59 take one column each; the rest of the CTA is waiting for its
+// first records anyway): the reference's sector key / column norm arithmetic (Scancontext.cpp:223, :78) in
+// Eigen's reduction order, then the f32 copies the filter reads.  Ends with a CTA barrier.
+__device__ __forceinline__ void prepare_query(BlockSmem &sm, const double *__restrict__ query)
 {
-    __shared__ float sq2[S];
     const int t = threadIdx.x;
-    // programmatic dependent launch: let the search kernel start its prologue (mbarrier init, first TMA
-    // tile loads) while this CTA prepares the query; the search waits on griddepcontrol.wait before it
-    // touches anything written here
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (t == 0) { out->qzero = 0ull; *gbest = (unsigned long long)__double_as_longlong(SENTINEL); }
-    for (int i = t; i < S * QSTRIDE; i += 64) out->q64[i] = 0.0;
-    for (int i = t; i < (S / 2) * QPAIR32; i += 64) out->q32[i] = 0.f;
+    if (t == 0) { sm.prep_flags = 0ull; sm.ub = ord_f32(INFINITY); sm.qc.q64 = query; }
     __syncthreads();
     if (t < S) {
-        double v[R], sq[R];
+        // one column per thread; redux20 order: four running sums over i % 4, combined (s0 + s2) + (s1 + s3)
+        const double2 *col = reinterpret_cast<const double2 *>(query + t * R);
+        double v[R];
+#pragma unroll
+        for (int i = 0; i < R / 2; ++i) { const double2 x = col[i]; v[2 * i] = x.x; v[2 * i + 1] = x.y; }
+        double sq[R];
+        double mx = 0.0;
+        bool bad = false;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            v[r] = query[t * R + r];
             sq[r] = v[r] * v[r];
-            out->q64[t * QSTRIDE + r] = v[r];
-            out->q32[q32_off(t) + r] = (float)v[r];
+            bad |= !(fabs(v[r]) <= 1e300);
+            mx = fmax(mx, fabs(v[r]));
         }
-        const double mean = redux20(v) / (double)R, nrm = sqrt(redux20(sq));   // Scancontext.cpp:223, :78
+        const double mean = redux20(v) / (double)R, nrm = sqrt(redux20(sq));
         const float mf = (float)mean;
-        out->qv[t] = mean; out->qvf[t] = mf;
-        out->qn[t] = nrm;  out->qnf[t] = (float)nrm;
-        sq2[t] = mf * mf;
-        if (nrm == 0) atomicOr(&out->qzero, 1ull << t);
+        sm.qc.qv[t] = mean;
+        sm.qc.qn[t] = nrm;
+        sm.prep_inv[t] = (nrm > 0) ? 1.0 / nrm : 0.0;
+        sm.prep_vf[t] = mf;
+        sm.prep_sq[t] = mf * mf;
+        sm.prep_am[t] = fabs(mean);
+        unsigned long long f = 0ull;
+        if (nrm == 0) f |= 1ull << t;
+        if (bad || hazard_col(mx)) f |= HAZ_C;
+        if (bad) f |= HAZ_B;
+        if (f) atomicOr(&sm.prep_flags, f);
     }
     __syncthreads();
-    if (t == 0) {
-        float a2 = 0.f;
-        for (int c = 0; c < S; ++c) a2 += sq2[c];
-        out->qv_norm2 = a2 * 1.0001f;
+    // unit columns in f32, all threads: |u - v / |v|| <= (2^-24 + 2^-51) |u|
+    for (int e = t; e < DESC; e += THREADS) {
+        const int c = e / R, r = e - c * R;
+        const float u = (float)(query[e] * sm.prep_inv[c]);
+        sm.q.qh[f32_off(c) + r] = u;
+        sm.q.qh[f32_off(c + S) + r] = u;
+        if (c + 2 * S < 2 * QH_PAIRS) sm.q.qh[f32_off(c + 2 * S) + r] = u;
     }
+    for (int i = t; i < 2 * QW_STRIDE; i += THREADS) {
+        const int m = i / QW_STRIDE, j = i - m * QW_STRIDE;
+        sm.q.qw[m][j] = sm.prep_vf[(j + 2 * m) % S];
+    }
+    if (t == THREADS - 32) {
+        float a2 = 0.f;
+        double mk = 0.0;
+        for (int c = 0; c < S; ++c) { a2 += sm.prep_sq[c]; mk = fmax(mk, sm.prep_am[c]); }
+        sm.q.qv_norm2 = a2 * 1.0001f;
+        sm.q.qflags = sm.prep_flags | (hazard_key(mk) ? HAZ_B : 0ull);
+    }
+    __syncthreads();
+}
+
+// ---- exact f64 evaluation, the reference's order -----------------------------------------------------
+// fastAlignUsingVkey over the candidate shifts (bit l of even <=> shift 2l, of odd <=> shift 2l + 1),
+// ascending; one warp.
+__device__ __noinline__ int certify_shift(const QCold *__restrict__ qc, double *scr, const double *__restrict__ vk,
+                                          unsigned int even, unsigned int odd, int lane)
+{
+    double fa_n = SENTINEL;
+    int s0 = 0;
+    while (even | odd) {
+        const int se = even ? 2 * (__ffs(even) - 1) : 2 * S, so = odd ? 2 * (__ffs(odd) - 1) + 1 : 2 * S;
+        const int s = min(se, so);
+        if (se < so) even &= even - 1; else odd &= odd - 1;
+        __syncwarp();
+        for (int i = lane; i < S; i += 32) {
+            const double d = qc->qv[i] - vk[wrap60(i - s)];
+            scr[i] = d * d;
+        }
+        __syncwarp();
+        double acc = 0.0;
+        if (lane < 4) {
+            acc = scr[lane];
+#pragma unroll
+            for (int i = 4; i < S; i += 4) acc += scr[lane + i];
+        }
+        const double a2 = __shfl_sync(0xffffffffu, acc, 2), a3 = __shfl_sync(0xffffffffu, acc, 3);
+        const double a1 = __shfl_sync(0xffffffffu, acc, 1), a0 = __shfl_sync(0xffffffffu, acc, 0);
+        const double nrm = sqrt((a0 + a2) + (a1 + a3));
+        if (nrm < fa_n) { fa_n = nrm; s0 = s; }          // ascending s + strict '<' == reference scan
+    }
+    __syncwarp();
+    return s0;
+}
+
+// distDirectSC for the shift slots in candC (bit d <=> shift s0 + d - 3); one warp; returns on all lanes
+// the lexicographic (dist, shift) minimum, (SENTINEL, 0) when no slot has an effective column.
+__device__ __noinline__ void certify_dist(const QCold *__restrict__ qc, unsigned long long qzero, double *scr,
+                                          const double *__restrict__ desc, const double *__restrict__ kn,
+                                          unsigned long long kzero, int s0, unsigned int candC, int lane,
+                                          double &dd, int &ds)
+{
+    dd = SENTINEL;
+    ds = 0;
+    while (candC) {
+        const int d = __ffs(candC) - 1;
+        candC &= candC - 1;
+        const int s = wrap60(s0 + d - RADIUS);
+        __syncwarp();
+        // key column paired with query column c is (c - s) mod 60: rotate the key mask up by s;
+        // effective columns (both norms non-zero), in column order, packed densely into scr[]
+        const unsigned long long krot = s ? (((kzero << s) | (kzero >> (S - s))) & MASK60) : kzero;
+        const unsigned long long eff = ~(qzero | krot) & MASK60;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                 // both columns' loads in flight together
+            const int c = lane + 32 * h;
+            if (c >= S || !((eff >> c) & 1ull)) continue;
+            const int kc = wrap60(c - s);
+            double a[R], b[R];
+            const double2 *qa = reinterpret_cast<const double2 *>(qc->q64 + c * R);
+            const double2 *kb = reinterpret_cast<const double2 *>(desc + kc * R);
+#pragma unroll
+            for (int r = 0; r < R / 2; ++r) {
+                const double2 x = qa[r], y = kb[r];
+                a[2 * r] = x.x; a[2 * r + 1] = x.y; b[2 * r] = y.x; b[2 * r + 1] = y.y;
+            }
+            const int pos = __popcll(eff & ((1ull << c) - 1ull));
+            scr[pos] = redux20_dot(a, b) / (qc->qn[c] * kn[kc]);
+        }
+        __syncwarp();
+        double dist = SENTINEL;
+        if (lane == 0) {
+            const int cnt = __popcll(eff);
+            double sum = 0.0;                       // distDirectSC's left-to-right sum (:83)
+            for (int i = 0; i < cnt; ++i) sum = sum + scr[i];
+            dist = 1.0 - sum / (double)cnt;
+        }
+        dist = __shfl_sync(0xffffffffu, dist, 0);
+        if (better(dist, s, dd, ds)) { dd = dist; ds = s; }   // lexicographic (dist, shift) == ascending-shift scan
+    }
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-sc_search_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep,
-                  const int32_t *__restrict__ cand, int first, int n_items, int idx_offset,
-                  double *__restrict__ dist_all, int32_t *__restrict__ shift_all,
-                  BlockResult *__restrict__ block_results, unsigned int *__restrict__ ticket,
-                  unsigned long long *__restrict__ gbest, nrs_sc_result *__restrict__ final_result)
+sc_search_kernel(const float *__restrict__ frec, const double *__restrict__ desc, const double *__restrict__ keys,
+                 const double *__restrict__ query, const int32_t *__restrict__ cand, int first, int n_items,
+                 int idx_scale, int idx_offset, double *__restrict__ dist_all, int32_t *__restrict__ shift_all,
+                 BlockResult *__restrict__ block_results, Survivor *__restrict__ surv,
+                 SearchState *__restrict__ st, nrs_sc_result *__restrict__ final_result, XchgView xv)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BlockSmem &sm = *reinterpret_cast<BlockSmem *>(smem_raw);
-    const bool prune = (dist_all == nullptr) && (shift_all == nullptr);
+    const bool inline_cert = (dist_all != nullptr) || (shift_all != nullptr);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpSmem &ws = sm.w[warp];
-    double *scr = reinterpret_cast<double *>(&ws.vkf[0][0]);     // certification scratch (60 doubles)
     const int gw = blockIdx.x * WARPS + warp;
     const int nw = gridDim.x * WARPS;
+    const QCold *qc = &sm.qc;
 
+    // start streaming this warp's first record, then prepare the query while it is in flight
     if (lane == 0) {
         nrs::mbar_init(&ws.bar, 1);
         nrs::fence_mbar_init();
         if (gw < n_items) {
             const int kf = cand ? cand[gw] : first + gw;
-            nrs::mbar_expect_tx(&ws.bar, KREC * 8);
-            nrs::tma_load_1d(ws.tile, db + (size_t)kf * KREC, KREC * 8, &ws.bar);
+            nrs::mbar_expect_tx(&ws.bar, FREC_BYTES);
+            nrs::tma_load_1d(ws.tile, frec + (size_t)kf * FREC_F, FREC_BYTES, &ws.bar);
         }
     }
-    // ---- the prepared query arrives by one bulk copy (after the prep grid has completed) -------------
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (threadIdx.x == 0) {
-        nrs::mbar_init(&sm.qbar, 1);
-        nrs::fence_mbar_init();
-        nrs::mbar_expect_tx(&sm.qbar, (uint32_t)sizeof(QPrep));
-        nrs::tma_load_1d(&sm.q, qprep, (uint32_t)sizeof(QPrep), &sm.qbar);
-    }
-    __syncthreads();
-    nrs::mbar_wait(&sm.qbar, 0);
-    const unsigned long long qzero = sm.q.qzero;
+    prepare_query(sm, query);
+    const unsigned long long qflags = sm.q.qflags;
+    const unsigned long long qzero = qflags & MASK60;
     const float A2 = sm.q.qv_norm2;
 
     double best_d = SENTINEL;
     int best_pos = 0x7fffffff, best_idx = 0, best_s = 0;
+    float my_ub = INFINITY;                       // smallest upper bound this warp has produced
     const bool own = lane < S / 2;
     const int c0 = own ? 2 * lane : 0;
+    // sliding query window of this lane's two shifts (2 lane, 2 lane + 1); lanes 30, 31 idle along on lane 0's
+    const int lb = own ? lane : 0;
+    const float4 *wq = reinterpret_cast<const float4 *>(&sm.q.qw[lb & 1][4 * (lb >> 1)]);
+    const float *T = ws.tile;
 
     for (int t = 0;; ++t) {
         const int item = gw + t * nw;
         if (item >= n_items) break;
         const int kf = cand ? cand[item] : first + item;
-        // best exact distance found so far by any warp of the grid (an upper bound of the final minimum)
-        unsigned long long gb = 0;
-        if (prune && lane == 0) gb = *reinterpret_cast<volatile unsigned long long *>(gbest);
         nrs::mbar_wait(&ws.bar, t & 1);
 
-        // ---- phase A (f64): column means and norms; f32 copies of this lane's two columns -------
-        float kf0[R], kf1[R];
-        float knf0, knf1;
+        const unsigned long long kflags = *reinterpret_cast<const unsigned long long *>(T + F_B2 + 2);
+        const unsigned long long kzero = kflags & MASK60;
+
+        // ---- filter B (f32): ||a - shift(b,s)||^2 = |a|^2 + |b|^2 - 2 corr(s),
+        //      corr(s) = sum_j vk[j] * vq[(j + s) mod 60];  lane l: s = 2l and 2l + 1 ------------------------
+        float nB0, nB1;
+        float B2 = T[F_B2];
         {
-            double k0[R], k1[R];
-            const double2 *src = reinterpret_cast<const double2 *>(&ws.tile[(own ? lane : 0) * PAIR_D]);
+            const float4 *kv = reinterpret_cast<const float4 *>(T + F_VK);     // same address on every lane: broadcast
+            float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
+            float4 x = wq[0];
 #pragma unroll
-            for (int r = 0; r < R / 2; ++r) {
-                const double2 a = src[r], b = src[R / 2 + r];
-                k0[2 * r] = a.x; k0[2 * r + 1] = a.y; k1[2 * r] = b.x; k1[2 * r + 1] = b.y;
+            for (int i = 0; i < S / 4; ++i) {
+                const float4 a = kv[i], xn = wq[i + 1];
+                c00 = fmaf(a.x, x.x, c00); c01 = fmaf(a.y, x.y, c01);
+                c00 = fmaf(a.z, x.z, c00); c01 = fmaf(a.w, x.w, c01);
+                c10 = fmaf(a.x, x.y, c10); c11 = fmaf(a.y, x.z, c11);
+                c10 = fmaf(a.z, x.w, c10); c11 = fmaf(a.w, xn.x, c11);
+                x = xn;
             }
-            double sq[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) sq[r] = k0[r] * k0[r];
-            const double kn0 = sqrt(redux20(sq));
-#pragma unroll
-            for (int r = 0; r < R; ++r) sq[r] = k1[r] * k1[r];
-            const double kn1 = sqrt(redux20(sq));
-            const double m0 = redux20(k0) / (double)R, m1 = redux20(k1) / (double)R;
-            if (own) {
-                ws.vk[c0] = m0; ws.vk[c0 + 1] = m1;
-#pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    // copy m, index j holds vk[(j + m) mod 60]  =>  vk[c] lands at j = c - m (+60, +120)
-                    const float f0 = (float)m0, f1 = (float)m1;
-                    int j0 = c0 - m, j1 = c0 + 1 - m;
-                    if (j0 < 0) j0 += S;
-                    if (j1 < 0) j1 += S;
-                    ws.vkf[m][j0] = f0; ws.vkf[m][j0 + S] = f0;
-                    ws.vkf[m][j1] = f1; ws.vkf[m][j1 + S] = f1;
-                    if (j0 + 2 * S < 2 * S + 4) ws.vkf[m][j0 + 2 * S] = f0;
-                    if (j1 + 2 * S < 2 * S + 4) ws.vkf[m][j1 + 2 * S] = f1;
-                }
-                ws.kn[c0] = kn0; ws.kn[c0 + 1] = kn1;
-            }
-            knf0 = (float)kn0; knf1 = (float)kn1;
-#pragma unroll
-            for (int r = 0; r < R; ++r) { kf0[r] = (float)k0[r]; kf1[r] = (float)k1[r]; }
+            nB0 = own ? (A2 + B2) - 2.0f * (c00 + c01) : INFINITY;
+            nB1 = own ? (A2 + B2) - 2.0f * (c10 + c11) : INFINITY;
         }
-        // zero-norm key columns as a 60-bit mask (exact: from the f64 norms)
+        B2 = B2 * 1.0001f;
+        const float mB = warp_min_f(fminf(nB0, nB1));
+        const float thrB = mB + EPS_B * (A2 + B2);
+        const bool finiteB = (mB == mB) && (thrB < INFINITY) && !((qflags | kflags) & HAZ_B);
+        const unsigned int candB0 = __ballot_sync(0xffffffffu, own && (!finiteB || nB0 <= thrB));
+        const unsigned int candB1 = __ballot_sync(0xffffffffu, own && (!finiteB || nB1 <= thrB));
+        int s0;
+        if (__popc(candB0) + __popc(candB1) == 1) s0 = candB0 ? 2 * (__ffs(candB0) - 1) : 2 * (__ffs(candB1) - 1) + 1;
+        else s0 = certify_shift(qc, ws.scr, keys + (size_t)kf * KEYS_D, candB0, candB1, lane);
+
+        // ---- filter C (f32): 7 shifts x 60 unit columns ------------------------------------------------
+        float part[NSHIFT];
+#pragma unroll
+        for (int d = 0; d < NSHIFT; ++d) part[d] = 0.f;
+        float kf0[R], kf1[R];
+        {
+            const float4 *src = reinterpret_cast<const float4 *>(T + lb * FPAIR);
+#pragma unroll
+            for (int r = 0; r < R / 4; ++r) {
+                const float4 a = src[r], b = src[R / 4 + r];
+                kf0[4 * r] = a.x; kf0[4 * r + 1] = a.y; kf0[4 * r + 2] = a.z; kf0[4 * r + 3] = a.w;
+                kf1[4 * r] = b.x; kf1[4 * r + 1] = b.y; kf1[4 * r + 2] = b.z; kf1[4 * r + 3] = b.w;
+            }
+        }
+        // the record now lives in registers: stream in this warp's next keyframe already
         __syncwarp();
-        // the record now lives in registers (f32) and vk/kn: stream in this warp's next keyframe already
         if (lane == 0) {
             const int item2 = item + nw;
             if (item2 < n_items) {
                 const int kf2 = cand ? cand[item2] : first + item2;
                 nrs::fence_proxy_async();
-                nrs::mbar_expect_tx(&ws.bar, KREC * 8);
-                nrs::tma_load_1d(ws.tile, db + (size_t)kf2 * KREC, KREC * 8, &ws.bar);
+                nrs::mbar_expect_tx(&ws.bar, FREC_BYTES);
+                nrs::tma_load_1d(ws.tile, frec + (size_t)kf2 * FREC_F, FREC_BYTES, &ws.bar);
             }
         }
-        unsigned long long kzero;
-        {
-            // zero-norm key columns as a 60-bit mask (exact: from the f64 norms), OR-reduced over the warp
-            const bool za = own && (ws.kn[c0] == 0), zb = own && (ws.kn[c0 + 1] == 0);
-            const unsigned long long mine = (za ? 1ull << c0 : 0ull) | (zb ? 1ull << (c0 + 1) : 0ull);
-            const unsigned int lo = __reduce_or_sync(0xffffffffu, (unsigned int)mine);
-            const unsigned int hi = __reduce_or_sync(0xffffffffu, (unsigned int)(mine >> 32));
-            kzero = ((unsigned long long)hi << 32) | lo;
-        }
-
-        // ---- phase B filter (f32): one shift per lane, two rounds; ||a - shift(b,s)||^2 =
-        //      |a|^2 + |b|^2 - 2 corr(s), corr by FFMA over 16-byte aligned windows -----------------------
-        float nB[2];
-        float B2;
-        {
-            float b2 = own ? fmaf(ws.vkf[0][c0], ws.vkf[0][c0], ws.vkf[0][c0 + 1] * ws.vkf[0][c0 + 1]) : 0.f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) b2 += __shfl_xor_sync(0xffffffffu, b2, o);
-            B2 = b2;
-            // window of shift s starts at vk index (60 - s): copy m = (60 - s) & 3, aligned index (60 - s) - m
-            const int o0 = S - lane, o1 = S - (lane + 32 < S ? lane + 32 : lane);
-            const float4 *w0 = reinterpret_cast<const float4 *>(&ws.vkf[o0 & 3][o0 & ~3]);
-            const float4 *w1 = reinterpret_cast<const float4 *>(&ws.vkf[o1 & 3][o1 & ~3]);
-            const float4 *qa = reinterpret_cast<const float4 *>(&sm.q.qvf[0]);
-            float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
-#pragma unroll
-            for (int i = 0; i < S / 4; ++i) {
-                const float4 a = qa[i], x = w0[i], y = w1[i];
-                c00 = fmaf(a.x, x.x, c00); c01 = fmaf(a.y, x.y, c01);
-                c00 = fmaf(a.z, x.z, c00); c01 = fmaf(a.w, x.w, c01);
-                c10 = fmaf(a.x, y.x, c10); c11 = fmaf(a.y, y.y, c11);
-                c10 = fmaf(a.z, y.z, c10); c11 = fmaf(a.w, y.w, c11);
-            }
-            nB[0] = (A2 + B2) - 2.0f * (c00 + c01);
-            nB[1] = (lane + 32 < S) ? (A2 + B2) - 2.0f * (c10 + c11) : INFINITY;
-        }
-        B2 = B2 * 1.0001f;
-        const float mB = warp_min_f(fminf(nB[0], nB[1]));
-        const float thrB = mB + EPS_B * (A2 + B2);
-        const bool finiteB = (mB == mB) && (thrB < INFINITY);
-        unsigned int candB[2];
-        candB[0] = __ballot_sync(0xffffffffu, !finiteB || nB[0] <= thrB);
-        candB[1] = __ballot_sync(0xffffffffu, (lane + 32 < S) && (!finiteB || nB[1] <= thrB));
-        if (!finiteB) { candB[0] = 0xffffffffu; candB[1] = 0x0fffffffu; }
-
-        // ---- phase B certification (f64, reference order): candidates in ascending shift ---------------
-        double fa_n = SENTINEL;
-        int s0 = 0;
-#pragma unroll
-        for (int rnd = 0; rnd < 2; ++rnd) {
-            unsigned int m = candB[rnd];
-            while (m) {
-                const int s = __ffs(m) - 1 + 32 * rnd;
-                m &= m - 1;
-                __syncwarp();
-                for (int i = lane; i < S; i += 32) {
-                    int j = i - s;
-                    j = j < 0 ? j + S : j;
-                    const double d = sm.q.qv[i] - ws.vk[j];
-                    scr[i] = d * d;
-                }
-                __syncwarp();
-                double acc = 0.0;
-                if (lane < 4) {
-                    acc = scr[lane];
-#pragma unroll
-                    for (int i = 4; i < S; i += 4) acc += scr[lane + i];
-                }
-                const double a2 = __shfl_sync(0xffffffffu, acc, 2), a3 = __shfl_sync(0xffffffffu, acc, 3);
-                const double a1 = __shfl_sync(0xffffffffu, acc, 1), a0 = __shfl_sync(0xffffffffu, acc, 0);
-                const double nrm = sqrt((a0 + a2) + (a1 + a3));
-                if (nrm < fa_n) { fa_n = nrm; s0 = s; }          // ascending s + strict '<' == reference scan
-            }
-        }
-
-        // ---- phase C filter (f32): 7 shifts x 60 columns ------------------------------------------------
-        float part[NSHIFT];
-#pragma unroll
-        for (int d = 0; d < NSHIFT; ++d) part[d] = 0.f;
         if (own) {
-            int qc = c0 + s0 - RADIUS + S;
-            qc = qc >= S ? qc - S : qc;
-            qc = qc >= S ? qc - S : qc;
+            // un-wrapped query column of (key column c0, shift slot 0); at most 59 + 58 + 8 < 2 * QH_PAIRS
+            const int qc_ = c0 + wrap60(s0 - RADIUS);
 #pragma unroll
             for (int tt = 0; tt < NSHIFT + 1; ++tt) {
                 float qcol[R];
-                const float4 *src = reinterpret_cast<const float4 *>(&sm.q.q32[q32_off(qc)]);
+                const float4 *src = reinterpret_cast<const float4 *>(&sm.q.qh[f32_off(qc_ + tt)]);
 #pragma unroll
                 for (int r = 0; r < R / 4; ++r) {
                     const float4 a = src[r];
                     qcol[4 * r] = a.x; qcol[4 * r + 1] = a.y; qcol[4 * r + 2] = a.z; qcol[4 * r + 3] = a.w;
                 }
-                const float qn_ = sm.q.qnf[qc];
                 if (tt <= NSHIFT - 1) {
                     float dot = 0.f, dot2 = 0.f;
 #pragma unroll
                     for (int r = 0; r < R; r += 2) { dot = fmaf(qcol[r], kf0[r], dot); dot2 = fmaf(qcol[r + 1], kf0[r + 1], dot2); }
-                    dot += dot2;
-                    const float den = qn_ * knf0;
-                    part[tt] += (den > 0.f) ? __fdividef(dot, den) : 0.f;
+                    part[tt] += dot + dot2;
                 }
                 if (tt >= 1) {
                     float dot = 0.f, dot2 = 0.f;
 #pragma unroll
                     for (int r = 0; r < R; r += 2) { dot = fmaf(qcol[r], kf1[r], dot); dot2 = fmaf(qcol[r + 1], kf1[r + 1], dot2); }
-                    dot += dot2;
-                    const float den = qn_ * knf1;
-                    part[tt - 1] += (den > 0.f) ? __fdividef(dot, den) : 0.f;
+                    part[tt - 1] += dot + dot2;
                 }
-                qc = (qc + 1 == S) ? 0 : qc + 1;
             }
         }
         // reduce the 7 per-lane partial sums over the warp by recursive halving (9 shuffles instead of 35):
@@ -421,15 +528,12 @@ sc_search_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep,
         float dC = INFINITY;       // lane d (< 7) ends up with the approximate distance of shift slot d
         int cntC = 0;
         {
-            float v8[8];
-#pragma unroll
-            for (int d = 0; d < NSHIFT; ++d) v8[d] = part[d];
-            v8[7] = 0.f;
             float v4[4], v2[2], v1;
             const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float send = up16 ? v8[i] : v8[4 + i], keep = up16 ? v8[4 + i] : v8[i];
+                const float hi = (i == 3) ? 0.f : part[4 + i];
+                const float send = up16 ? part[i] : hi, keep = up16 ? hi : part[i];
                 v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
             }
 #pragma unroll
@@ -447,114 +551,129 @@ sc_search_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep,
             const int srcl = (lane < 8) ? (((lane >> 2) & 1) << 4 | ((lane >> 1) & 1) << 3 | (lane & 1) << 2) : 0;
             const float v = __shfl_sync(0xffffffffu, v1, srcl);
             if (lane < NSHIFT) {
-                int s = s0 + lane - RADIUS + S;
-                s = s >= S ? s - S : s;
-                s = s >= S ? s - S : s;
+                const int s = wrap60(s0 + lane - RADIUS);
                 // key column paired with query column c is (c - s) mod 60: rotate the key mask up by s
-                const unsigned long long mask60 = (1ull << S) - 1ull;
-                const unsigned long long krot = s ? (((kzero << s) | (kzero >> (S - s))) & mask60) : kzero;
-                cntC = S - __popcll((qzero | krot) & mask60);
+                const unsigned long long krot = s ? (((kzero << s) | (kzero >> (S - s))) & MASK60) : kzero;
+                cntC = S - __popcll((qzero | krot) & MASK60);
                 dC = cntC ? 1.0f - v / (float)cntC : INFINITY;
             }
         }
-        float mC = (lane < NSHIFT) ? dC : INFINITY;
         const bool finC = !(lane < NSHIFT) || (dC == dC);
-        const bool allfin = __all_sync(0xffffffffu, finC);
-        mC = warp_min_f(mC);
-        unsigned int candC = __ballot_sync(0xffffffffu, lane < NSHIFT && cntC > 0 && (!allfin || dC <= mC + EPS_C));
-        if (prune) {
-            // every exact distance of this keyframe is >= mC - e_C; if that already exceeds the best
-            // exact distance known (this warp's or the grid's), the keyframe can neither win nor tie
-            const double mine_best = __shfl_sync(0xffffffffu, best_d, 0);
-            const double grid_best = __longlong_as_double((long long)__shfl_sync(0xffffffffu, gb, 0));
-            const double bound = fmin(mine_best, grid_best);
-            if (allfin && (double)(mC - EPS_C) > bound) candC = 0u;
-        }
+        const bool certain = __all_sync(0xffffffffu, finC) && !((qflags | kflags) & HAZ_C);
+        const float mC = warp_min_f((lane < NSHIFT && dC == dC) ? dC : INFINITY);
+        const unsigned int candC = __ballot_sync(0xffffffffu, lane < NSHIFT && cntC > 0 && (!certain || dC <= mC + 2.0f * EPS_C));
 
-        // ---- phase C certification (f64, reference order) -------------------------------------------------
-        double dd = SENTINEL;
-        int ds = 0;
-        while (candC) {
-            const int d = __ffs(candC) - 1;
-            candC &= candC - 1;
-            int s = s0 + d - RADIUS + S;
-            s = s >= S ? s - S : s;
-            s = s >= S ? s - S : s;
-            __syncwarp();
-            // effective columns (both norms non-zero), in column order, packed densely into scr[]
-            const unsigned long long mask60 = (1ull << S) - 1ull;
-            const unsigned long long krot = s ? (((kzero << s) | (kzero >> (S - s))) & mask60) : kzero;
-            const unsigned long long eff = ~(qzero | krot) & mask60;
-            for (int c = lane; c < S; c += 32) {
-                if (!((eff >> c) & 1ull)) continue;
-                int kc = c - s;
-                kc = kc < 0 ? kc + S : kc;
-                double a[R], b[R];
-                const double2 *qa = reinterpret_cast<const double2 *>(&sm.q.q64[c * QSTRIDE]);
-                // the f64 record is re-read from global memory (it was streamed moments ago: L2 hit)
-                const double2 *kb = reinterpret_cast<const double2 *>(db + (size_t)kf * KREC + col_off(kc));
-#pragma unroll
-                for (int r = 0; r < R / 2; ++r) {
-                    const double2 x = qa[r], y = kb[r];
-                    a[2 * r] = x.x; a[2 * r + 1] = x.y; b[2 * r] = y.x; b[2 * r + 1] = y.y;
-                }
-                const int pos = __popcll(eff & ((1ull << c) - 1ull));
-                scr[pos] = redux20_dot(a, b) / (sm.q.qn[c] * ws.kn[kc]);
-            }
-            __syncwarp();
-            double dist = SENTINEL;
+        if (inline_cert) {
+            // per-keyframe results requested: every keyframe is certified on the spot
+            double dd;
+            int ds;
+            certify_dist(qc, qzero, ws.scr, desc + (size_t)kf * DESC, keys + (size_t)kf * KEYS_D + S, kzero, s0, candC, lane, dd, ds);
             if (lane == 0) {
-                const int cnt = __popcll(eff);
-                double sum = 0.0;                       // distDirectSC's left-to-right sum (:83)
-                int i = 0;
-                for (; i + 1 < cnt; i += 2) {
-                    const double2 v = *reinterpret_cast<const double2 *>(&scr[i]);
-                    sum = sum + v.x;
-                    sum = sum + v.y;
+                if (dist_all) dist_all[item] = dd;
+                if (shift_all) shift_all[item] = ds;
+                if (dd < best_d) { best_d = dd; best_pos = item; best_idx = kf; best_s = ds; }
+            }
+        } else if (lane == 0) {
+            // every exact distance of this keyframe is >= mC - e_C, and its best one is <= mC + e_C:
+            // it survives unless that lower bound already exceeds an upper bound seen by this CTA
+            Survivor sv;
+            sv.item = item; sv.code = 1 << 16; sv.lo = INFINITY; sv.pad = 0;        // "ruled out"
+            bool push = false;
+            if (candC) {
+                const float bound = fminf(my_ub, unord_f32(*reinterpret_cast<volatile unsigned int *>(&sm.ub)));
+                push = !certain || mC - EPS_C <= bound;
+                if (push) { sv.code = s0 | (int)(candC << 8) | (certain ? 1 << 16 : 0); sv.lo = mC; }
+                if (certain && mC + EPS_C < bound) {
+                    my_ub = mC + EPS_C;
+                    atomicMin(&sm.ub, ord_f32(my_ub));
+                    atomicMin(&st->gub, ord_f32(my_ub));
                 }
-                if (i < cnt) sum = sum + scr[i];
-                dist = 1.0 - sum / (double)cnt;
             }
-            dist = __shfl_sync(0xffffffffu, dist, 0);
-            if (better(dist, s, dd, ds)) { dd = dist; ds = s; }   // lexicographic (dist, shift) == ascending-shift scan
-        }
-        __syncwarp();
-        if (lane == 0) {
-            if (dist_all) dist_all[item] = dd;
-            if (shift_all) shift_all[item] = ds;
-            if (dd < best_d) {
-                best_d = dd; best_pos = item; best_idx = kf; best_s = ds;
-                if (prune) atomicMin(gbest, (unsigned long long)__double_as_longlong(dd));   // dd >= 0: bit order == value order
-            }
+            // the first keyframe of a warp meets no bound yet: park it and judge it after the loop
+            if (t == 0) ws.first = sv;
+            else if (push) surv[atomicAdd(&st->n_surv, 1u)] = sv;
         }
     }
+    if (!inline_cert && lane == 0 && gw < n_items) {
+        const Survivor sv = ws.first;
+        const float bound = fminf(my_ub, unord_f32(*reinterpret_cast<volatile unsigned int *>(&sm.ub)));
+        if (!(sv.code & (1 << 16)) || sv.lo - EPS_C <= bound) surv[atomicAdd(&st->n_surv, 1u)] = sv;
+    }
 
-    // ---- block reduce, then last-block-done grid reduce ---------------------------------------------
-    if (lane == 0) { sm.red_d[warp] = best_d; sm.red_pos[warp] = best_pos; sm.red_idx[warp] = best_idx; sm.red_s[warp] = best_s; }
+    // ---- last-block-done: the last CTA certifies the survivors (or, with per-keyframe results, reduces
+    //      the per-block minima) and writes the result ---------------------------------------------------
+    if (inline_cert && lane == 0) { sm.red_d[warp] = best_d; sm.red_pos[warp] = best_pos; sm.red_idx[warp] = best_idx; sm.red_s[warp] = best_s; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double d = sm.red_d[0];
-        int p = sm.red_pos[0], ix = sm.red_idx[0], sh = sm.red_s[0];
-        for (int w = 1; w < WARPS; ++w)
-            if (better(sm.red_d[w], sm.red_pos[w], d, p)) { d = sm.red_d[w]; p = sm.red_pos[w]; ix = sm.red_idx[w]; sh = sm.red_s[w]; }
-        BlockResult br;
-        br.dist = d; br.pos = p; br.idx = ix; br.shift = sh; br.pad = 0;
-        block_results[blockIdx.x] = br;
+        if (inline_cert) {
+            double d = sm.red_d[0];
+            int p = sm.red_pos[0], ix = sm.red_idx[0], sh = sm.red_s[0];
+            for (int w = 1; w < WARPS; ++w)
+                if (better(sm.red_d[w], sm.red_pos[w], d, p)) { d = sm.red_d[w]; p = sm.red_pos[w]; ix = sm.red_idx[w]; sh = sm.red_s[w]; }
+            BlockResult br;
+            br.dist = d; br.pos = p; br.idx = ix; br.shift = sh; br.pad = 0;
+            block_results[blockIdx.x] = br;
+        }
+        // release: the barrier above ordered every warp's list entries before this fence (cumulativity)
         __threadfence();
-        const unsigned int tk = atomicAdd(ticket, 1u);
+        const unsigned int tk = atomicAdd(&st->ticket, 1u);
         sm.is_last = (tk == gridDim.x - 1);
     }
     __syncthreads();
-    if (sm.is_last && warp == 0) {
-        __threadfence();
-        double d = SENTINEL;
-        int p = 0x7fffffff, ix = 0, sh = 0;
-        for (int b = lane; b < (int)gridDim.x; b += 32) {
-            const volatile BlockResult *br = block_results + b;
-            const double bd = br->dist;
-            const int bp = br->pos;
-            if (better(bd, bp, d, p)) { d = bd; p = bp; ix = br->idx; sh = br->shift; }
+    if (!sm.is_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) st->t_ns[0] = globaltimer_ns();
+
+    double d = SENTINEL;
+    int p = 0x7fffffff, ix = 0, sh = 0;
+    if (inline_cert) {
+        if (warp == 0) {
+            for (int b = lane; b < (int)gridDim.x; b += 32) {
+                const volatile BlockResult *br = block_results + b;
+                const double bd = br->dist;
+                const int bp = br->pos;
+                if (better(bd, bp, d, p)) { d = bd; p = bp; ix = br->idx; sh = br->shift; }
+            }
         }
+    } else {
+        const unsigned int n_list = *reinterpret_cast<volatile unsigned int *>(&st->n_surv);
+        const float bound = unord_f32(*reinterpret_cast<volatile unsigned int *>(&st->gub));
+        // four coalesced list entries per lane in flight; the few the final bound cannot rule out are certified
+        constexpr int U = 4;
+        for (unsigned int base = warp * (32 * U); base < n_list; base += WARPS * 32 * U) {
+            int4 e[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const unsigned int i = base + u * 32 + lane;
+                e[u] = (i < n_list) ? __ldcg(reinterpret_cast<const int4 *>(surv + i)) : make_int4(0, 1 << 16, 0x7f800000, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool need = !(e[u].y & (1 << 16)) || !(__int_as_float(e[u].z) - EPS_C > bound);
+                unsigned int todo = __ballot_sync(0xffffffffu, need);
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int it = __shfl_sync(0xffffffffu, e[u].x, src), cd = __shfl_sync(0xffffffffu, e[u].y, src);
+                    const int kf = cand ? cand[it] : first + it;
+                    const unsigned long long kzero =
+                        *reinterpret_cast<const unsigned long long *>(frec + (size_t)kf * FREC_F + F_B2 + 2) & MASK60;
+                    double dd;
+                    int ds;
+                    certify_dist(qc, qzero, ws.scr, desc + (size_t)kf * DESC, keys + (size_t)kf * KEYS_D + S, kzero, cd & 0xff,
+                                 (unsigned int)(cd >> 8) & 0x7fu, lane, dd, ds);
+                    if (better(dd, it, d, p)) { d = dd; p = it; ix = kf; sh = ds; }
+                }
+            }
+        }
+        if (lane == 0) { sm.red_d[warp] = d; sm.red_pos[warp] = p; sm.red_idx[warp] = ix; sm.red_s[warp] = sh; }
+        __syncthreads();
+        if (warp == 0) {
+            d = SENTINEL; p = 0x7fffffff; ix = 0; sh = 0;
+            if (lane < WARPS) { d = sm.red_d[lane]; p = sm.red_pos[lane]; ix = sm.red_idx[lane]; sh = sm.red_s[lane]; }
+        }
+    }
+    if (warp == 0) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             const double od = __shfl_xor_sync(0xffffffffu, d, off);
@@ -563,17 +682,60 @@ sc_search_kernel(const double *__restrict__ db, const QPrep *__restrict__ qprep,
             const int os = __shfl_xor_sync(0xffffffffu, sh, off);
             if (better(od, op, d, p)) { d = od; p = op; ix = oi; sh = os; }
         }
+        ix = (d < SENTINEL) ? ix * idx_scale + idx_offset : 0;
+        if (lane == 0) st->t_ns[1] = globaltimer_ns();
+        if (xv.world > 1) {
+            // ---- fused exchange: this rank's record to every peer, then merge the world's records ----------
+            d = __shfl_sync(0xffffffffu, d, 0);
+            ix = __shfl_sync(0xffffffffu, ix, 0);
+            sh = __shfl_sync(0xffffffffu, sh, 0);
+            const int par = (int)(xv.epoch & 1u);
+            bool ok = true;
+            if (lane < xv.world) {
+                XchgSlot *dst = xv.peers[lane] + par * xv.world + xv.rank;
+                *reinterpret_cast<volatile double *>(&dst->dist) = d;
+                *reinterpret_cast<volatile int *>(&dst->idx) = ix;
+                *reinterpret_cast<volatile int *>(&dst->shift) = sh;
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned int *>(&dst->epoch) = xv.epoch;
+                if (lane == 0) st->t_ns[2] = globaltimer_ns();
+                const XchgSlot *src = xv.peers[xv.rank] + par * xv.world + lane;
+                const long long t0 = clock64();
+                while (*reinterpret_cast<const volatile unsigned int *>(&src->epoch) != xv.epoch)
+                    if (clock64() - t0 > XCHG_TIMEOUT_CYCLES) { ok = false; break; }
+                __threadfence_system();
+                d = *reinterpret_cast<const volatile double *>(&src->dist);
+                ix = *reinterpret_cast<const volatile int *>(&src->idx);
+                sh = *reinterpret_cast<const volatile int *>(&src->shift);
+            } else {
+                d = SENTINEL;
+            }
+            p = (d < SENTINEL) ? ix : 0x7fffffff;            // order key across ranks: the global index
+            ok = __all_sync(0xffffffffu, ok);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, d, off);
+                const int op = __shfl_xor_sync(0xffffffffu, p, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, ix, off);
+                const int os = __shfl_xor_sync(0xffffffffu, sh, off);
+                if (better(od, op, d, p)) { d = od; p = op; ix = oi; sh = os; }
+            }
+            if (!(d < SENTINEL)) { ix = 0; sh = 0; }
+            if (!ok) { d = SENTINEL; ix = -2; sh = 0; }      // a peer did not answer: reported, never silent
+        }
         if (lane == 0) {
+            st->t_ns[3] = globaltimer_ns();
             nrs_sc_result res;
             res.dist = d;
-            res.idx = (d < SENTINEL) ? ix + idx_offset : 0;
+            res.idx = ix;
             res.shift = sh;
             *final_result = res;
-            *ticket = 0u;
+            st->ticket = 0u;                       // leave the state ready for the next launch
+            st->n_surv = 0u;
+            st->gub = ord_f32(INFINITY);
         }
     }
 }
-
 
 // ---- makeScancontext (Scancontext.cpp:151-195) ---------------------------------------------
 __device__ __forceinline__ int enc_f32(float f)
@@ -704,21 +866,60 @@ sc_dist_direct_kernel(const double *__restrict__ sc1, const double *__restrict__
     }
 }
 
-// canonical 20x60 column-major descriptor(s) <-> padded device record(s)
-__global__ void sc_pack_kernel(const double *__restrict__ canon, double *__restrict__ rec, int count)
+// canonical 20x60 column-major descriptor(s) -> the three device records of a keyframe:
+// desc (the reference's 9600 bytes, verbatim), keys (f64 sector key + column norms, the reference's
+// arithmetic) and the f32 filter record (layout: K10 header).  One 64-thread CTA per keyframe.
+__global__ void __launch_bounds__(64)
+sc_pack_kernel(const double *__restrict__ canon, double *__restrict__ desc, double *__restrict__ keys,
+               float *__restrict__ frec, int count)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count * KREC) return;
-    const int k = i / KREC, o = i - k * KREC;
-    const int pair = o / PAIR_D, w = o - pair * PAIR_D;
-    rec[i] = (w < 2 * R) ? canon[(size_t)k * DESC + pair * 2 * R + w] : 0.0;
-}
-__global__ void sc_unpack_kernel(const double *__restrict__ rec, double *__restrict__ canon, int count)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count * DESC) return;
-    const int k = i / DESC, e = i - k * DESC;
-    canon[i] = rec[(size_t)k * KREC + col_off(e / R) + (e % R)];
+    __shared__ float sq2[S];
+    __shared__ double am[S];
+    __shared__ unsigned long long flags;
+    const int k = blockIdx.x, t = threadIdx.x;
+    if (k >= count) return;
+    const double *src = canon + (size_t)k * DESC;
+    double *dk = keys + (size_t)k * KEYS_D;
+    float *fr = frec + (size_t)k * FREC_F;
+    if (t == 0) flags = 0ull;
+    for (int i = t; i < F_VK; i += 64) fr[i] = 0.f;          // pair padding included
+    __syncthreads();
+    if (t < S) {
+        double v[R], sq[R];
+        double mx = 0.0;
+        bool bad = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            v[r] = src[t * R + r];
+            desc[(size_t)k * DESC + t * R + r] = v[r];
+            sq[r] = v[r] * v[r];
+            bad |= !(fabs(v[r]) <= 1e300);
+            mx = fmax(mx, fabs(v[r]));
+        }
+        const double mean = redux20(v) / (double)R, nrm = sqrt(redux20(sq));   // Scancontext.cpp:223, :78
+        dk[t] = mean;
+        dk[S + t] = nrm;
+#pragma unroll
+        for (int r = 0; r < R; ++r) fr[f32_off(t) + r] = (nrm > 0) ? (float)(v[r] / nrm) : 0.f;
+        const float mf = (float)mean;
+        fr[F_VK + t] = mf;
+        sq2[t] = mf * mf;
+        am[t] = fabs(mean);
+        unsigned long long f = 0ull;
+        if (nrm == 0) f |= 1ull << t;
+        if (bad || hazard_col(mx)) f |= HAZ_C;
+        if (bad) f |= HAZ_B;
+        if (f) atomicOr(&flags, f);
+    }
+    __syncthreads();
+    if (t == 0) {
+        float b2 = 0.f;
+        double mk = 0.0;
+        for (int c = 0; c < S; ++c) { b2 += sq2[c]; mk = fmax(mk, am[c]); }
+        fr[F_B2] = b2;
+        fr[F_B2 + 1] = 0.f;
+        *reinterpret_cast<unsigned long long *>(fr + F_B2 + 2) = flags | (hazard_key(mk) ? HAZ_B : 0ull);
+    }
 }
 
 }  // namespace
@@ -729,21 +930,40 @@ __global__ void sc_unpack_kernel(const double *__restrict__ rec, double *__restr
 struct nrs_sc_db {
     nrs_ctx     *ctx = nullptr;
     std::mutex   mu;
-    double      *d_desc = nullptr;       // capacity padded records (KREC doubles each)
+    double      *d_desc = nullptr;       // capacity x 1200 doubles: polarcontexts_ verbatim (Scancontext.h:111)
+    double      *d_keys = nullptr;       // capacity x 120 doubles: sector key, column norms (f64)
+    float       *d_frec = nullptr;       // capacity x FREC_F floats: filter records
+    Survivor    *d_surv = nullptr;       // capacity entries
     int          size = 0;
     int          capacity = 0;
     // per-db search scratch
     BlockResult   *d_block = nullptr;
-    unsigned int  *d_ticket = nullptr;   // [0] last-block ticket, [2..3] grid-wide best distance (u64)
+    SearchState   *d_state = nullptr;
     nrs_sc_result *d_result = nullptr;
     double        *d_query = nullptr;
-    QPrep         *d_qprep = nullptr;    // prepared query
     nrs_sc_result *h_result = nullptr;   // pinned
     double        *h_query = nullptr;    // pinned
     int            max_blocks = 0;
+    // peer-memory result exchange (keyframe-sharded databases)
+    XchgSlot      *x_local = nullptr;    // 2 x world slots in this GPU's HBM, exported by CUDA IPC
+    XchgSlot     **x_peers_dev = nullptr;   // device array of world base pointers
+    void          *x_opened[XCHG_MAX_WORLD] = {};   // peer mappings to close
+    int            x_world = 0, x_rank = 0;
+    unsigned int   x_epoch = 0;
+    bool           x_ready = false;
 };
 
 namespace {
+
+constexpr int SURV_EXTRA = 64;
+
+// device-side view of a set of keyframes
+struct DbView {
+    const float  *frec;
+    const double *desc;
+    const double *keys;
+    Survivor     *surv;
+};
 
 int search_smem_bytes() { return (int)sizeof(BlockSmem); }
 
@@ -758,61 +978,72 @@ int configure_search_kernel()
     return NRS_OK;
 }
 
-// enqueue one search on the ctx stream: prepare the query, then the persistent search kernel.
-// d_ticket points at 4 words: [0] ticket (zero between launches), [2..3] grid-wide best (reset here)
-int launch_search(nrs_ctx *ctx, const double *d_db, const double *d_query, QPrep *d_qprep, const int32_t *d_cand,
+constexpr unsigned int GUB_INIT = 0xff800000u;     // ord_f32(+inf)
+
+int init_state(SearchState *d_state, cudaStream_t stream)
+{
+    SearchState h = {};
+    h.gub = GUB_INIT;
+    NRS_CUDA(cudaMemcpyAsync(d_state, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
+    NRS_CUDA(cudaStreamSynchronize(stream));
+    return NRS_OK;
+}
+
+// enqueue one search on the ctx stream: ONE persistent kernel per query
+int launch_search(nrs_ctx *ctx, const DbView &v, const double *d_query, const int32_t *d_cand,
                   int first, int n_items, int idx_offset, double *d_dist_all, int32_t *d_shift_all,
-                  BlockResult *d_block, unsigned int *d_ticket, nrs_sc_result *d_result,
-                  int max_blocks)
+                  BlockResult *d_block, SearchState *d_state, nrs_sc_result *d_result, int max_blocks,
+                  int idx_scale = 1, XchgView xv = XchgView{nullptr, 0, 0, 0u})
 {
     int rc = configure_search_kernel();
     if (rc) return rc;
-    unsigned long long *d_gbest = reinterpret_cast<unsigned long long *>(d_ticket + 2);
-    sc_prep_query_kernel<<<1, 64, 0, ctx->stream>>>(d_query, d_qprep, d_gbest);
-    NRS_LAUNCHED();
     int blocks = (n_items + WARPS - 1) / WARPS;
     blocks = std::max(1, std::min(blocks, max_blocks));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(blocks);
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = search_smem_bytes();
-    cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    const QPrep *c_qprep = d_qprep;
-    NRS_CUDA(cudaLaunchKernelEx(&cfg, sc_search_kernel, d_db, c_qprep, d_cand, first, n_items, idx_offset,
-                                d_dist_all, d_shift_all, d_block, d_ticket, d_gbest, d_result));
+    sc_search_kernel<<<blocks, THREADS, search_smem_bytes(), ctx->stream>>>(
+        v.frec, v.desc, v.keys, d_query, d_cand, first, n_items, idx_scale, idx_offset, d_dist_all, d_shift_all,
+        d_block, v.surv, d_state, d_result, xv);
     NRS_LAUNCHED();
     return NRS_OK;
 }
+
+DbView view_of(const nrs_sc_db *db) { return DbView{db->d_frec, db->d_desc, db->d_keys, db->d_surv}; }
 
 int db_reserve(nrs_sc_db *db, int want)
 {
     if (want <= db->capacity) return NRS_OK;
     int cap = db->capacity ? db->capacity : 1024;
     while (cap < want) cap *= 2;
-    double *np = nullptr;
-    NRS_CUDA(cudaMalloc(&np, (size_t)cap * KREC * sizeof(double)));
-    if (db->d_desc) {
-        // in-flight searches read the old buffer: drain the stream before swapping it out
-        NRS_CUDA(cudaStreamSynchronize(db->ctx->stream));
-        NRS_CUDA(cudaMemcpyAsync(np, db->d_desc, (size_t)db->size * KREC * sizeof(double),
-                                 cudaMemcpyDeviceToDevice, db->ctx->stream));
-        NRS_CUDA(cudaStreamSynchronize(db->ctx->stream));
-        cudaFree(db->d_desc);
+    double *nd = nullptr, *nk = nullptr;
+    float *nf = nullptr;
+    Survivor *ns = nullptr;
+    cudaError_t e = cudaSuccess;
+    if ((e = cudaMalloc(&nd, (size_t)cap * DESC * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&nk, (size_t)cap * KEYS_D * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&nf, (size_t)cap * FREC_BYTES)) != cudaSuccess ||
+        (e = cudaMalloc(&ns, ((size_t)cap + SURV_EXTRA) * sizeof(Survivor))) != cudaSuccess) {
+        cudaFree(nd); cudaFree(nk); cudaFree(nf); cudaFree(ns);
+        nrs::set_error("nrs_sc_db: growing to %d keyframes: %s", cap, cudaGetErrorString(e));
+        return NRS_ECUDA;
     }
-    db->d_desc = np;
+    // in-flight searches read the old buffers: drain the stream before swapping them out
+    NRS_CUDA(cudaStreamSynchronize(db->ctx->stream));
+    if (db->size) {
+        NRS_CUDA(cudaMemcpyAsync(nd, db->d_desc, (size_t)db->size * DESC * sizeof(double), cudaMemcpyDeviceToDevice, db->ctx->stream));
+        NRS_CUDA(cudaMemcpyAsync(nk, db->d_keys, (size_t)db->size * KEYS_D * sizeof(double), cudaMemcpyDeviceToDevice, db->ctx->stream));
+        NRS_CUDA(cudaMemcpyAsync(nf, db->d_frec, (size_t)db->size * FREC_BYTES, cudaMemcpyDeviceToDevice, db->ctx->stream));
+        NRS_CUDA(cudaStreamSynchronize(db->ctx->stream));
+    }
+    cudaFree(db->d_desc); cudaFree(db->d_keys); cudaFree(db->d_frec); cudaFree(db->d_surv);
+    db->d_desc = nd; db->d_keys = nk; db->d_frec = nf; db->d_surv = ns;
     db->capacity = cap;
     return NRS_OK;
 }
 
-int pack_records(nrs_ctx *ctx, const double *d_canon, double *d_rec, int count)
+// canonical descriptors (device) -> records of keyframes [at, at + count)
+int pack_records(nrs_ctx *ctx, const double *d_canon, double *d_desc, double *d_keys, float *d_frec, int at, int count)
 {
-    const int n = count * KREC;
-    sc_pack_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_canon, d_rec, count);
+    sc_pack_kernel<<<count, 64, 0, ctx->stream>>>(d_canon, d_desc + (size_t)at * DESC, d_keys + (size_t)at * KEYS_D,
+                                                  d_frec + (size_t)at * FREC_F, count);
     NRS_LAUNCHED();
     return NRS_OK;
 }
@@ -863,16 +1094,15 @@ int nrs_sc_db_create(nrs_ctx *ctx, int capacity_hint, nrs_sc_db **out)
     NRS_CUDA(cudaSetDevice(ctx->device));
     nrs_sc_db *db = new nrs_sc_db();
     db->ctx = ctx;
-    db->max_blocks = ctx->sm_count;            // persistent: one ~220 KB CTA per SM
+    db->max_blocks = ctx->sm_count;            // persistent: one ~205 KB CTA per SM
     cudaError_t e = cudaSuccess;
     if ((e = cudaMalloc(&db->d_block, sizeof(BlockResult) * db->max_blocks)) != cudaSuccess ||
-        (e = cudaMalloc(&db->d_ticket, 4 * sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMalloc(&db->d_state, sizeof(SearchState))) != cudaSuccess ||
         (e = cudaMalloc(&db->d_result, sizeof(nrs_sc_result))) != cudaSuccess ||
         (e = cudaMalloc(&db->d_query, DESC * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc(&db->d_qprep, sizeof(QPrep))) != cudaSuccess ||
         (e = cudaMallocHost(&db->h_result, sizeof(nrs_sc_result))) != cudaSuccess ||
         (e = cudaMallocHost(&db->h_query, DESC * sizeof(double))) != cudaSuccess ||
-        (e = cudaMemset(db->d_ticket, 0, 4 * sizeof(unsigned int))) != cudaSuccess) {
+        init_state(db->d_state, ctx->stream) != NRS_OK) {
         nrs::set_error("nrs_sc_db_create: %s", cudaGetErrorString(e));
         nrs_sc_db_destroy(db);
         return NRS_ECUDA;
@@ -888,8 +1118,11 @@ int nrs_sc_db_destroy(nrs_sc_db *db)
     if (!db) return NRS_OK;
     cudaSetDevice(db->ctx->device);
     cudaStreamSynchronize(db->ctx->stream);
-    cudaFree(db->d_desc); cudaFree(db->d_block); cudaFree(db->d_ticket);
-    cudaFree(db->d_result); cudaFree(db->d_query); cudaFree(db->d_qprep);
+    cudaFree(db->d_desc); cudaFree(db->d_keys); cudaFree(db->d_frec); cudaFree(db->d_surv);
+    cudaFree(db->d_block); cudaFree(db->d_state);
+    for (void *m : db->x_opened) if (m) cudaIpcCloseMemHandle(m);
+    cudaFree(db->x_local); cudaFree(db->x_peers_dev);
+    cudaFree(db->d_result); cudaFree(db->d_query);
     if (db->h_result) cudaFreeHost(db->h_result);
     if (db->h_query) cudaFreeHost(db->h_query);
     delete db;
@@ -921,7 +1154,7 @@ int nrs_sc_db_append(nrs_sc_db *db, const double *desc_host, int count)
     NRS_CUDA(cudaSetDevice(ctx->device));
     int rc = db_reserve(db, db->size + count);
     if (rc) return rc;
-    // stage the canonical 9600-byte descriptors, then rewrite them as padded device records
+    // stage the canonical 9600-byte descriptors, then derive the device records from them
     const int chunk = 4096;
     rc = ctx->scratch[6].reserve((size_t)std::min(count, chunk) * DESC * sizeof(double));
     if (rc) return rc;
@@ -930,7 +1163,7 @@ int nrs_sc_db_append(nrs_sc_db *db, const double *desc_host, int count)
         const int n = std::min(chunk, count - done);
         NRS_CUDA(cudaMemcpyAsync(d_stage, desc_host + (size_t)done * DESC, (size_t)n * DESC * sizeof(double),
                                  cudaMemcpyHostToDevice, ctx->stream));
-        rc = pack_records(ctx, d_stage, db->d_desc + (size_t)(db->size + done) * KREC, n);
+        rc = pack_records(ctx, d_stage, db->d_desc, db->d_keys, db->d_frec, db->size + done, n);
         if (rc) return rc;
         NRS_CUDA(cudaStreamSynchronize(ctx->stream));
     }
@@ -955,7 +1188,7 @@ int nrs_sc_db_append_cloud(nrs_sc_db *db, const float *xyz, int P, double lidar_
     if (P) NRS_CUDA(cudaMemcpyAsync(d_xyz, xyz, (size_t)P * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     sc_make_kernel<<<1, 256, 0, ctx->stream>>>(d_xyz, P, lidar_height, max_radius, d_canon);
     NRS_LAUNCHED();
-    rc = pack_records(ctx, d_canon, db->d_desc + (size_t)db->size * KREC, 1);
+    rc = pack_records(ctx, d_canon, db->d_desc, db->d_keys, db->d_frec, db->size, 1);
     if (rc) return rc;
     if (desc_out) NRS_CUDA(cudaMemcpyAsync(desc_out, d_canon, DESC * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     NRS_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -972,22 +1205,15 @@ int nrs_sc_db_read(nrs_sc_db *db, int first, int count, double *desc_host)
     nrs_ctx *ctx = db->ctx;
     std::lock_guard<std::mutex> lk2(ctx->mu);
     NRS_CUDA(cudaSetDevice(ctx->device));
-    const int chunk = 4096;
-    int rc = ctx->scratch[6].reserve((size_t)std::min(count, chunk) * DESC * sizeof(double));
-    if (rc) return rc;
-    double *d_stage = ctx->scratch[6].as<double>();
-    for (int done = 0; done < count; done += chunk) {
-        const int n = std::min(chunk, count - done);
-        sc_unpack_kernel<<<(n * DESC + 255) / 256, 256, 0, ctx->stream>>>(db->d_desc + (size_t)(first + done) * KREC, d_stage, n);
-        NRS_LAUNCHED();
-        NRS_CUDA(cudaMemcpyAsync(desc_host + (size_t)done * DESC, d_stage, (size_t)n * DESC * sizeof(double),
-                                 cudaMemcpyDeviceToHost, ctx->stream));
-        NRS_CUDA(cudaStreamSynchronize(ctx->stream));
-    }
+    NRS_CUDA(cudaMemcpyAsync(desc_host, db->d_desc + (size_t)first * DESC, (size_t)count * DESC * sizeof(double),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    NRS_CUDA(cudaStreamSynchronize(ctx->stream));
     return NRS_OK;
 }
 
 const double *nrs_sc_db_device_ptr(nrs_sc_db *db) { return db ? db->d_desc : nullptr; }
+
+int nrs_sc_filter_record_bytes(void) { return FREC_BYTES; }
 
 static int sc_query_impl(nrs_sc_db *db, const double *query_host, int first, int last,
                          const int32_t *cand, int n_cand, double *dist_out, int32_t *shift_out,
@@ -1020,9 +1246,16 @@ static int sc_query_impl(nrs_sc_db *db, const double *query_host, int first, int
     NRS_CUDA(cudaMemcpyAsync(db->d_query, db->h_query, DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     if (cand && n_items)
         NRS_CUDA(cudaMemcpyAsync(d_cand, cand, (size_t)n_items * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    rc = launch_search(ctx, db->d_desc, db->d_query, db->d_qprep, cand ? d_cand : nullptr, first, n_items, 0,
+    DbView view = view_of(db);
+    if (n_items > db->capacity) {
+        // a candidate list may repeat keyframes and outgrow the database's own survivor list
+        rc = ctx->scratch[7].reserve(((size_t)n_items + SURV_EXTRA) * sizeof(Survivor));
+        if (rc) return rc;
+        view.surv = ctx->scratch[7].as<Survivor>();
+    }
+    rc = launch_search(ctx, view, db->d_query, cand ? d_cand : nullptr, first, n_items, 0,
                        want_all ? d_dist : nullptr, want_all ? d_shift : nullptr, db->d_block,
-                       db->d_ticket, db->d_result, db->max_blocks);
+                       db->d_state, db->d_result, db->max_blocks);
     if (rc) return rc;
     NRS_CUDA(cudaMemcpyAsync(db->h_result, db->d_result, sizeof(nrs_sc_result), cudaMemcpyDeviceToHost, ctx->stream));
     if (dist_out && n_items)
@@ -1056,9 +1289,79 @@ int nrs_sc_query_dev(nrs_sc_db *db, const double *query_dev, int first, int last
     std::lock_guard<std::mutex> lk(db->mu);
     NRS_CHECK_ARG(first >= 0 && last <= db->size, "search range outside the database");
     NRS_CUDA(cudaSetDevice(db->ctx->device));
-    return launch_search(db->ctx, db->d_desc, query_dev, db->d_qprep, nullptr, first, std::max(0, last - first),
-                         idx_offset, nullptr, nullptr, db->d_block, db->d_ticket, result_dev,
+    return launch_search(db->ctx, view_of(db), query_dev, nullptr, first, std::max(0, last - first),
+                         idx_offset, nullptr, nullptr, db->d_block, db->d_state, result_dev,
                          db->max_blocks);
+}
+
+int nrs_sc_xchg_create(nrs_sc_db *db, int world, int rank, unsigned char *handle_out)
+{
+    NRS_CHECK_ARG(db && handle_out, "bad argument");
+    NRS_CHECK_ARG(world >= 2 && world <= XCHG_MAX_WORLD && rank >= 0 && rank < world, "world must be 2..32, 0 <= rank < world");
+    static_assert(sizeof(cudaIpcMemHandle_t) == NRS_SC_XCHG_HANDLE_BYTES, "IPC handle size");
+    std::lock_guard<std::mutex> lk(db->mu);
+    NRS_CHECK_ARG(db->x_local == nullptr, "exchange already created for this database");
+    NRS_CUDA(cudaSetDevice(db->ctx->device));
+    const size_t bytes = (size_t)2 * world * sizeof(XchgSlot);
+    NRS_CUDA(cudaMalloc(&db->x_local, bytes));
+    NRS_CUDA(cudaMemset(db->x_local, 0, bytes));
+    NRS_CUDA(cudaMalloc(&db->x_peers_dev, world * sizeof(XchgSlot *)));
+    cudaIpcMemHandle_t h;
+    NRS_CUDA(cudaIpcGetMemHandle(&h, db->x_local));
+    memcpy(handle_out, &h, sizeof(h));
+    db->x_world = world;
+    db->x_rank = rank;
+    return NRS_OK;
+}
+
+int nrs_sc_xchg_open(nrs_sc_db *db, const unsigned char *handles)
+{
+    NRS_CHECK_ARG(db && handles, "bad argument");
+    std::lock_guard<std::mutex> lk(db->mu);
+    NRS_CHECK_ARG(db->x_local != nullptr && !db->x_ready, "call nrs_sc_xchg_create first (once)");
+    NRS_CUDA(cudaSetDevice(db->ctx->device));
+    XchgSlot *peers[XCHG_MAX_WORLD] = {};
+    for (int r = 0; r < db->x_world; ++r) {
+        if (r == db->x_rank) { peers[r] = db->x_local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * sizeof(h), sizeof(h));
+        void *m = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&m, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            nrs::set_error("nrs_sc_xchg_open: mapping rank %d: %s", r, cudaGetErrorString(e));
+            return NRS_ECUDA;
+        }
+        db->x_opened[r] = m;
+        peers[r] = static_cast<XchgSlot *>(m);
+    }
+    NRS_CUDA(cudaMemcpy(db->x_peers_dev, peers, db->x_world * sizeof(XchgSlot *), cudaMemcpyHostToDevice));
+    db->x_ready = true;
+    return NRS_OK;
+}
+
+int nrs_sc_query_dev_sharded(nrs_sc_db *db, const double *query_dev, int first, int last, nrs_sc_result *result_dev)
+{
+    NRS_CHECK_ARG(db && query_dev && result_dev, "bad argument");
+    std::lock_guard<std::mutex> lk(db->mu);
+    NRS_CHECK_ARG(db->x_ready, "exchange not opened (nrs_sc_xchg_create / nrs_sc_xchg_open)");
+    NRS_CHECK_ARG(first >= 0 && last <= db->size, "search range outside the database");
+    NRS_CUDA(cudaSetDevice(db->ctx->device));
+    const XchgView xv{db->x_peers_dev, db->x_world, db->x_rank, ++db->x_epoch};
+    return launch_search(db->ctx, view_of(db), query_dev, nullptr, first, std::max(0, last - first),
+                         db->x_rank, nullptr, nullptr, db->d_block, db->d_state, result_dev, db->max_blocks,
+                         db->x_world, xv);
+}
+
+int nrs_sc_db_tail_times(nrs_sc_db *db, uint64_t *t_ns4)
+{
+    NRS_CHECK_ARG(db && t_ns4, "bad argument");
+    std::lock_guard<std::mutex> lk(db->mu);
+    NRS_CUDA(cudaSetDevice(db->ctx->device));
+    NRS_CUDA(cudaStreamSynchronize(db->ctx->stream));
+    SearchState h;
+    NRS_CUDA(cudaMemcpy(&h, db->d_state, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; ++i) t_ns4[i] = h.t_ns[i];
+    return NRS_OK;
 }
 
 int nrs_sc_fast_align(nrs_ctx *ctx, const double *vkey1, const double *vkey2, int32_t *shift)
@@ -1106,26 +1409,29 @@ int nrs_sc_pair(nrs_ctx *ctx, const double *sc1, const double *sc2, double *dist
     NRS_CUDA(cudaSetDevice(ctx->device));
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
-    const size_t o_prep = take(sizeof(QPrep)), o_q = take(DESC * 8), o_k = take(DESC * 8), o_rec = take(KREC * 8);
-    const size_t o_blk = take(sizeof(BlockResult)), o_tk = take(16), o_res = take(sizeof(nrs_sc_result));
+    const size_t o_q = take(DESC * 8), o_k = take(DESC * 8), o_desc = take(DESC * 8);
+    const size_t o_keys = take(KEYS_D * 8), o_frec = take(FREC_BYTES), o_surv = take(sizeof(Survivor) * (WARPS + 1));
+    const size_t o_blk = take(sizeof(BlockResult)), o_st = take(sizeof(SearchState)), o_res = take(sizeof(nrs_sc_result));
     const size_t o_d = take(8), o_s = take(4);
     int rc = ctx->scratch[2].reserve(off);
     if (rc) return rc;
     unsigned char *base = ctx->scratch[2].as<unsigned char>();
-    QPrep *d_qprep = reinterpret_cast<QPrep *>(base + o_prep);
     double *d_q = reinterpret_cast<double *>(base + o_q), *d_k = reinterpret_cast<double *>(base + o_k);
-    double *d_rec = reinterpret_cast<double *>(base + o_rec);
+    double *d_desc = reinterpret_cast<double *>(base + o_desc), *d_keys = reinterpret_cast<double *>(base + o_keys);
+    float *d_frec = reinterpret_cast<float *>(base + o_frec);
     BlockResult *d_block = reinterpret_cast<BlockResult *>(base + o_blk);
-    unsigned int *d_ticket = reinterpret_cast<unsigned int *>(base + o_tk);
+    SearchState *d_state = reinterpret_cast<SearchState *>(base + o_st);
     nrs_sc_result *d_res = reinterpret_cast<nrs_sc_result *>(base + o_res);
     double *d_dist = reinterpret_cast<double *>(base + o_d);
     int32_t *d_shift = reinterpret_cast<int32_t *>(base + o_s);
-    NRS_CUDA(cudaMemsetAsync(d_ticket, 0, 16, ctx->stream));
+    rc = init_state(d_state, ctx->stream);
+    if (rc) return rc;
     NRS_CUDA(cudaMemcpyAsync(d_q, sc1, DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     NRS_CUDA(cudaMemcpyAsync(d_k, sc2, DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    rc = pack_records(ctx, d_k, d_rec, 1);
+    rc = pack_records(ctx, d_k, d_desc, d_keys, d_frec, 0, 1);
     if (rc) return rc;
-    rc = launch_search(ctx, d_rec, d_q, d_qprep, nullptr, 0, 1, 0, d_dist, d_shift, d_block, d_ticket, d_res, 1);
+    const DbView v{d_frec, d_desc, d_keys, reinterpret_cast<Survivor *>(base + o_surv)};
+    rc = launch_search(ctx, v, d_q, nullptr, 0, 1, 0, d_dist, d_shift, d_block, d_state, d_res, 1);
     if (rc) return rc;
     double h_dist; int32_t h_shift;
     NRS_CUDA(cudaMemcpyAsync(&h_dist, d_dist, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -87,6 +87,29 @@ class SCDatabase:
         check(lib().nrs_sc_db_read(self._h, first, count, ptr(out)))
         return out
 
+    # -- peer-memory result exchange (keyframe-sharded, one process per GPU) -------------------------
+    def xchg_create(self, world, rank):
+        """-> this rank's 64-byte CUDA IPC handle (bytes)"""
+        buf = (C.c_ubyte * 64)()
+        check(lib().nrs_sc_xchg_create(self._h, world, rank, buf))
+        return bytes(buf)
+
+    def xchg_open(self, handles):
+        """handles: the world's handles concatenated in rank order (world x 64 bytes)"""
+        raw = bytes(handles)
+        buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+        check(lib().nrs_sc_xchg_open(self._h, buf))
+
+    def query_dev_sharded(self, query_dev_ptr, first, last, result_dev_ptr):
+        """local slots [first,last); *result_dev = GLOBAL (dist, idx, shift) after the in-kernel exchange"""
+        check(lib().nrs_sc_query_dev_sharded(self._h, C.c_void_p(query_dev_ptr), first, last, C.c_void_p(result_dev_ptr)))
+
+    def tail_times(self):
+        """%globaltimer ns stamps of the most recent search's last CTA (see nrs_sc_db_tail_times)"""
+        t = (C.c_uint64 * 4)()
+        check(lib().nrs_sc_db_tail_times(self._h, t))
+        return [int(x) for x in t]
+
     def device_ptr(self):
         return lib().nrs_sc_db_device_ptr(self._h)
 
@@ -287,19 +310,42 @@ def local_range(first, last, rank, world):
     return lo, hi
 
 
+def enable_peer_exchange(dbs, rank, world, dev, group=None):
+    """Set up the peer-memory result exchange (nrs_sc_xchg_*) on every database in `dbs` (same list
+    length on every rank).  The IPC handles travel through one all_gather on the process group --
+    plumbing, done once.  Returns True when every rank mapped every peer; False leaves the
+    databases usable with the collective exchange."""
+    import torch
+    import torch.distributed as dist
+    ok = True
+    for db in dbs:
+        mine = torch.frombuffer(bytearray(db.xchg_create(world, rank)), dtype=torch.uint8).to(dev)
+        allh = torch.empty(64 * world, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        try:
+            db.xchg_open(allh.cpu().numpy().tobytes())
+        except Exception:
+            ok = False
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(flag.item())
+
+
 class ShardedSCDatabase:
     """Keyframe database sharded across the ranks of a torch.distributed group.
 
     Every rank calls append()/query() with identical arguments (SPMD).  Rank r stores
-    keyframes g with g % world == r.  query() = local search on each rank's slice + ONE
-    all_gather of the 16-byte (dist, idx, shift) records + the exact merge of best_of().
+    keyframes g with g % world == r.  query() = local search on each rank's slice, then the
+    exchange of the 16-byte (dist, idx, shift) records and their exact merge: on GPUs inside the
+    search kernel over peer memory (exchange == "peer", nrs_sc_query_dev_sharded), else ONE
+    all_gather + best_of() on the host (exchange == "nccl"; the CPU tests use gloo).
     ``local_search(query, lo, hi) -> (dist, local_idx, shift)`` defaults to the CUDA library;
     the CPU tests of this host logic inject a test double (gloo backend, no GPU).
     """
 
     RECORD = 16
 
-    def __init__(self, rank, world, ctx=None, group=None, local_search=None, device=None):
+    def __init__(self, rank, world, ctx=None, group=None, local_search=None, device=None, exchange="auto"):
         import torch
         import torch.distributed as dist
         self._torch, self._dist = torch, dist
@@ -317,10 +363,17 @@ class ShardedSCDatabase:
             self._rec_dev = torch.zeros(self.RECORD, dtype=torch.uint8, device=self.dev)
             self._all_dev = torch.zeros(self.RECORD * world, dtype=torch.uint8, device=self.dev)
             self._all_pin = torch.zeros(self.RECORD * world, dtype=torch.uint8).pin_memory()
+            self.exchange = "none" if world == 1 else "nccl"
+            if world > 1 and exchange in ("auto", "peer"):
+                if enable_peer_exchange([self.db], rank, world, self.dev, group):
+                    self.exchange = "peer"
+                elif exchange == "peer":
+                    raise RuntimeError("peer-memory exchange requested but CUDA IPC mapping failed on some rank")
         else:
             self.ctx = self.db = None
             self.dev = torch.device("cpu")
             self._store = []
+            self.exchange = "collective"
 
     def __len__(self):
         return self.n_total
@@ -360,6 +413,21 @@ class ShardedSCDatabase:
         torch, dist = self._torch, self._dist
         last = self.n_total if last is None else last
         q = f64(query, DESC)
+        if self.exchange == "peer":
+            # local search + in-kernel exchange over peer memory: the record that comes back is global
+            lo, hi = local_range(first, last, self.rank, self.world)
+            hi = min(hi, self._local_n)
+            self._q_pin.copy_(torch.from_numpy(q))
+            with torch.cuda.stream(self._nrs_stream):
+                self._q_dev.copy_(self._q_pin, non_blocking=True)
+                self.db.query_dev_sharded(self._q_dev.data_ptr(), lo, hi, self._rec_dev.data_ptr())
+                pin = self._all_pin[: self.RECORD]
+                pin.copy_(self._rec_dev, non_blocking=True)
+            self._nrs_stream.synchronize()
+            r = pin.numpy().view([("dist", "<f8"), ("idx", "<i4"), ("shift", "<i4")])[0]
+            if int(r["idx"]) == -2:
+                raise RuntimeError("sharded ScanContext query: a peer rank did not answer within the exchange timeout")
+            return float(r["dist"]), int(r["idx"]), int(r["shift"])
         rec = self._local_record(q, first, last)
         if self.world == 1:
             gathered = rec

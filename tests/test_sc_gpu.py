@@ -122,6 +122,88 @@ def test_edge_cases(sc, ctx, oracle, synth):
     assert d.query(sp) == oracle.sc_search(sp, db)[2]
     with pytest.raises(Exception):
         d.query(db[0], 0, 41)
+    # a candidate list far longer than the database (repeats): first occurrence wins
+    cand = np.tile(np.arange(40, dtype=np.int32)[::-1], 200)
+    assert d.query(db[3], candidates=cand) == (oracle.sc_distance(db[3], db[3])[0], 3, 0)
+    d.close()
+
+
+def same_result(a, b):
+    """(dist, idx, shift) equality where NaN never appears (the search returns 1e7 instead)."""
+    return bits([a[0]])[0] == bits([b[0]])[0] and a[1] == b[1] and a[2] == b[2]
+
+
+def test_filter_cannot_separate_near_duplicates(sc, ctx, oracle, synth):
+    """Hundreds of keyframes within 1e-14 .. 1e-7 of the query: far below the f32 filter's
+    resolution, so every one of them must reach the f64 certification and the exact arg-min
+    (lowest index on ties) must come out."""
+    rng = np.random.default_rng(7)
+    base, _ = synth.sc_database(64, 0, seed=11, binary=False)
+    q = base[5]
+    rel = 10.0 ** rng.uniform(-14, -7, size=400)
+    near = q[None, :] * (1.0 + rel[:, None] * rng.standard_normal((400, 1200)))
+    near[37] = near[311]                                   # exact tie: the lower index must win
+    db = np.concatenate([base, near, base[:16]])
+    d = sc.SCDatabase(ctx)
+    d.append(db)
+    odist, oshift, obest = oracle.sc_search(q, db)
+    assert same_result(d.query(q), obest)
+    dist, shift, best = d.query_all(q)
+    assert np.array_equal(bits(dist), bits(odist)) and np.array_equal(shift, oshift) and best == obest
+    # the same with the query itself absent from the range (all survivors are near-ties)
+    _, _, ob = oracle.sc_search(q, db, 64, 464)
+    assert same_result(d.query(q, 64, 464), ob)
+    # rotated near-duplicates: the alignment arg-min is decided in f64 as well
+    rot = np.stack([synth.shift_desc(near[k], int(s)) for k, s in enumerate(rng.integers(0, 60, 400))])
+    d.clear()
+    d.append(rot)
+    odist, oshift, obest = oracle.sc_search(q, rot)
+    assert same_result(d.query(q), obest)
+    dist, shift, _ = d.query_all(q)
+    assert np.array_equal(bits(dist), bits(odist)) and np.array_equal(shift, oshift)
+    d.close()
+
+
+@pytest.mark.parametrize("scale_db,scale_q", [(1e-200, 1e-200), (1e-160, 1.0), (1e-30, 1e-30), (1e-12, 1e9),
+                                               (1e20, 1e20), (1e30, 1e-30), (1e160, 1e160), (1e200, 1.0)])
+def test_filter_magnitude_hazards(sc, ctx, oracle, synth, scale_db, scale_q):
+    """Magnitudes at which the f32 filter's error bounds do not hold (or f32 over/underflows) must
+    fall back to the f64 evaluation: results stay identical to the oracle's."""
+    db, rev = synth.sc_database(300, 40, seed=3, binary=False)
+    db = db * scale_db
+    q = db[rev[0][0]] / scale_db * scale_q
+    d = sc.SCDatabase(ctx)
+    d.append(db)
+    with np.errstate(all="ignore"):
+        odist, oshift, obest = oracle.sc_search(q, db)
+    dist, shift, best = d.query_all(q)
+    assert np.array_equal(dist, odist, equal_nan=True) and np.array_equal(shift, oshift)
+    assert same_result(best, obest)
+    assert same_result(d.query(q), obest)
+    d.close()
+
+
+def test_filter_mixed_hazards(sc, ctx, oracle, synth):
+    """A few poisoned keyframes (NaN / inf entries, one column 1e-170, one column 1e170, tiny sector
+    means) inside an otherwise ordinary database must neither win wrongly nor mask the winner."""
+    db, rev = synth.sc_database(400, 60, seed=9, binary=False)
+    j, i, s = rev[1]
+    db = db.copy()
+    db[2, 7] = np.nan
+    db[3, 100] = np.inf
+    db[4].reshape(60, 20)[11] *= 1e-170
+    db[6].reshape(60, 20)[40] *= 1e170
+    db[8] *= 1e-18
+    db[9] = db[j] * (1 + 1e-13)                            # near-duplicate of the query keyframe at a low index
+    d = sc.SCDatabase(ctx)
+    d.append(db)
+    for q in (db[j], db[4], db[6], db[8], db[2]):
+        with np.errstate(all="ignore"):
+            odist, oshift, obest = oracle.sc_search(q, db, 0, 390)
+        dist, shift, best = d.query_all(q, 0, 390)
+        assert np.array_equal(dist, odist, equal_nan=True) and np.array_equal(shift, oshift)
+        assert same_result(best, obest)
+        assert same_result(d.query(q, 0, 390), obest)
     d.close()
 
 
