@@ -116,6 +116,20 @@ int nrs_sc_db_append_cloud(nrs_sc_db *db, const float *xyz_Px3, int P, double li
 int nrs_sc_db_read(nrs_sc_db *db, int first, int count, double *desc_host);
 /* device base of the descriptor array (9600 B per keyframe, the reference's layout) */
 const double *nrs_sc_db_device_ptr(nrs_sc_db *db);
+/* The candidate step of detectLoopClosureID (Scancontext.cpp:361-377): the k ring keys of
+ * keyframes [first, last) nearest to `ringkey20` in nanoflann's L2_Adaptor arithmetic
+ * (nanoflann.hpp:375-412, float, groups of four) -- what the reference's kd-tree returns,
+ * without a tree: ascending distance, equal distances by ascending index, NaN distances never
+ * listed; idx_out[j] = -1 where fewer than k exist.  The database keeps every keyframe's ring
+ * key (polarcontext_invkeys_mat_, Scancontext.h:114) since append.  1 <= k <= 16. */
+int nrs_sc_knn(nrs_sc_db *db, const float *ringkey20_host, int first, int last, int k,
+               int32_t *idx_out, float *d2_out);
+/* detectLoopClosureID exactly as the reference runs it (Scancontext.cpp:331-399): ring key of the
+ * query, its k nearest ring keys among keyframes [first, last) (the set the kd-tree holds), then
+ * distanceBtnScanContext over those k in tree order, strict '<'.  Everything stays on the
+ * device; cand_out (nullable, k ids) reports the candidates. */
+int nrs_sc_detect_knn(nrs_sc_db *db, const double *query_host, int first, int last, int k,
+                      int32_t *cand_out, nrs_sc_result *result_host);
 /* bytes per keyframe that an exhaustive query streams from HBM (the f32 filter record) */
 int nrs_sc_filter_record_bytes(void);
 

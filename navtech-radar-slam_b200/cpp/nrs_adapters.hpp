@@ -117,15 +117,27 @@ public:
             searchable_end_ = (int)polarcontext_invkeys_mat_.size() - NUM_EXCLUDE_RECENT;
         tree_making_period_conter = tree_making_period_conter + 1;
         nrs_sc_result r;
-        check(nrs_sc_query(db_, polarcontexts_.back().data(), 0, searchable_end_, nullptr, 0, &r));
+        if (use_tree_candidates)      // the reference's own flow: ring-key k-NN, then its 3 candidates (:361-396)
+            check(nrs_sc_detect_knn(db_, polarcontexts_.back().data(), 0, searchable_end_, NUM_CANDIDATES_FROM_TREE,
+                                    nullptr, &r));
+        else                          // exhaustive over the set the tree would hold (north_star)
+            check(nrs_sc_query(db_, polarcontexts_.back().data(), 0, searchable_end_, nullptr, 0, &r));
         if (r.dist < SC_DIST_THRES) loop_id = r.idx;
         return {loop_id, yaw(r.shift)};
     }
-    std::pair<int, float> detectLoopClosureIDBetweenSession(std::vector<float> & /*curr_key*/, MatrixXd &curr_desc)
+    std::pair<int, float> detectLoopClosureIDBetweenSession(std::vector<float> &curr_key, MatrixXd &curr_desc)
     {
         is_tree_batch_made = true;
         nrs_sc_result r;
-        check(nrs_sc_query(db_, curr_desc.data(), 0, (int)polarcontexts_.size(), nullptr, 0, &r));
+        const int n = (int)polarcontexts_.size();
+        if (use_tree_candidates && (int)curr_key.size() == PC_NUM_RING) {
+            int32_t cand[16];
+            check(nrs_sc_knn(db_, curr_key.data(), 0, n, NUM_CANDIDATES_FROM_TREE, cand, nullptr));
+            int m = 0;
+            while (m < NUM_CANDIDATES_FROM_TREE && cand[m] >= 0) ++m;
+            check(nrs_sc_query(db_, curr_desc.data(), 0, 0, cand, m, &r));
+        } else
+            check(nrs_sc_query(db_, curr_desc.data(), 0, n, nullptr, 0, &r));
         return {r.dist < SC_DIST_THRES ? r.idx : -1, yaw(r.shift)};
     }
     const MatrixXd &getConstRefRecentSCD(void) { return polarcontexts_.back(); }
@@ -152,6 +164,8 @@ public:
     std::vector<MatrixXd> polarcontext_vkeys_;
     KeyMat polarcontext_invkeys_mat_;
     bool is_tree_batch_made = false;
+    // false (default): exhaustive search; true: ring-key nearest neighbours + 3 candidates like the reference
+    bool use_tree_candidates = false;
 
 private:
     static std::vector<float> flatten(Cloud &c)

@@ -866,12 +866,150 @@ sc_dist_direct_kernel(const double *__restrict__ sc1, const double *__restrict__
     }
 }
 
+// ---- ring-key nearest neighbours: the candidate step of detectLoopClosureID (Scancontext.cpp:361-377) ----
+// The reference asks a nanoflann kd-tree (metric_L2 -> L2_Adaptor, nanoflann.hpp:375-412) for the
+// NUM_CANDIDATES_FROM_TREE nearest ring keys.  An exact kd-tree search returns the exact k nearest, so a
+// brute-force scan with the SAME distance arithmetic -- float, groups of four:
+// result += d0*d0 + d1*d1 + d2*d2 + d3*d3 -- returns the same set with bit-identical distances, without
+// a tree to rebuild.  Order: ascending distance, equal distances by ascending index (the kd-tree's order
+// among exact ties depends on its traversal; documented in DESIGN.md).  NaN distances never enter.
+constexpr int KNN_MAX = 16;
+constexpr int KNN_THREADS = 256;
+constexpr int KNN_PER_BLOCK = KNN_THREADS * 16;
+
+__device__ __forceinline__ float ringkey_l2(const float (&q)[R], const float *__restrict__ key)
+{
+    float result = 0.f;
+#pragma unroll
+    for (int i = 0; i < R; i += 4) {
+        const float4 b = *reinterpret_cast<const float4 *>(key + i);
+        const float d0 = q[i] - b.x, d1 = q[i + 1] - b.y, d2 = q[i + 2] - b.z, d3 = q[i + 3] - b.w;
+        result += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+    return result;
+}
+__device__ __forceinline__ bool knn_before(float d1, int i1, float d2, int i2)
+{
+    return (d1 < d2) || (d1 == d2 && i1 < i2);
+}
+
+// block-wide selection of the k smallest (d, idx) among the per-thread sorted lists; out[0..k) ascending
+__device__ void knn_block_select(float (&ld)[KNN_MAX], int (&li)[KNN_MAX], int k, float *out_d, int32_t *out_i)
+{
+    __shared__ float sd[KNN_THREADS / 32];
+    __shared__ int si[KNN_THREADS / 32], so[KNN_THREADS / 32];
+    __shared__ int winner;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int round = 0; round < k; ++round) {
+        float d = ld[0];
+        int i = li[0], o = threadIdx.x;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, d, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, i, off), oo = __shfl_xor_sync(0xffffffffu, o, off);
+            // entries with idx < 0 are empty; among real entries (d, idx) ascending
+            const bool take = (oi >= 0) && (i < 0 || knn_before(od, oi, d, i));
+            if (take) { d = od; i = oi; o = oo; }
+        }
+        if (lane == 0) { sd[warp] = d; si[warp] = i; so[warp] = o; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float bd = sd[0];
+            int bi = si[0], bo = so[0];
+            for (int w = 1; w < KNN_THREADS / 32; ++w)
+                if (si[w] >= 0 && (bi < 0 || knn_before(sd[w], si[w], bd, bi))) { bd = sd[w]; bi = si[w]; bo = so[w]; }
+            out_d[round] = bi >= 0 ? bd : INFINITY;
+            out_i[round] = bi;
+            winner = bi >= 0 ? bo : -1;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x == winner) {
+#pragma unroll
+            for (int j = 0; j + 1 < KNN_MAX; ++j) { ld[j] = ld[j + 1]; li[j] = li[j + 1]; }
+            ld[KNN_MAX - 1] = INFINITY;
+            li[KNN_MAX - 1] = -1;
+        }
+        __syncthreads();
+    }
+}
+// insert (d, i) into the thread's ascending list of length k (empty slots: idx -1, at the end)
+__device__ __forceinline__ void knn_insert(float (&ld)[KNN_MAX], int (&li)[KNN_MAX], int k, float d, int i)
+{
+    if (!(d == d)) return;
+    if (li[k - 1] >= 0 && !knn_before(d, i, ld[k - 1], li[k - 1])) return;     // not better than the worst kept
+    // slot j takes old[j-1] if that sorts after the new entry, else the new entry if old[j] sorts after it
+#pragma unroll
+    for (int j = KNN_MAX - 1; j >= 0; --j) {
+        if (j >= k) continue;
+        const bool prev_after = (j > 0) && (li[j > 0 ? j - 1 : 0] < 0 || knn_before(d, i, ld[j > 0 ? j - 1 : 0], li[j > 0 ? j - 1 : 0]));
+        const bool self_after = li[j] < 0 || knn_before(d, i, ld[j], li[j]);
+        if (prev_after) { ld[j] = ld[j - 1 < 0 ? 0 : j - 1]; li[j] = li[j - 1 < 0 ? 0 : j - 1]; }
+        else if (self_after) { ld[j] = d; li[j] = i; }
+    }
+}
+
+// stage 1: every block scans KNN_PER_BLOCK ring keys of [first, last) and emits its k best
+__global__ void __launch_bounds__(KNN_THREADS)
+sc_knn_scan_kernel(const float *__restrict__ rkeys, const float *__restrict__ query, int first, int last, int k,
+                   float *__restrict__ part_d, int32_t *__restrict__ part_i)
+{
+    float q[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) q[i] = query[i];
+    float ld[KNN_MAX];
+    int li[KNN_MAX];
+#pragma unroll
+    for (int j = 0; j < KNN_MAX; ++j) { ld[j] = INFINITY; li[j] = -1; }
+    const int lo = first + blockIdx.x * KNN_PER_BLOCK;
+    const int hi = min(last, lo + KNN_PER_BLOCK);
+    for (int g = lo + threadIdx.x; g < hi; g += KNN_THREADS)
+        knn_insert(ld, li, k, ringkey_l2(q, rkeys + (size_t)g * R), g);
+    knn_block_select(ld, li, k, part_d + (size_t)blockIdx.x * k, part_i + (size_t)blockIdx.x * k);
+}
+
+// stage 2: one block merges the per-block lists; entries the scan could not fill (fewer than k valid
+// neighbours) repeat the best one, so that the candidate search below can run on exactly k ids
+__global__ void __launch_bounds__(KNN_THREADS)
+sc_knn_merge_kernel(const float *__restrict__ part_d, const int32_t *__restrict__ part_i, int n_part, int k,
+                    int fallback, float *__restrict__ out_d, int32_t *__restrict__ out_i, int32_t *__restrict__ cand)
+{
+    __shared__ float fd[KNN_MAX];
+    __shared__ int32_t fi[KNN_MAX];
+    float ld[KNN_MAX];
+    int li[KNN_MAX];
+#pragma unroll
+    for (int j = 0; j < KNN_MAX; ++j) { ld[j] = INFINITY; li[j] = -1; }
+    for (int e = threadIdx.x; e < n_part; e += KNN_THREADS)
+        if (part_i[e] >= 0) knn_insert(ld, li, k, part_d[e], part_i[e]);
+    knn_block_select(ld, li, k, fd, fi);
+    if ((int)threadIdx.x < k) {
+        out_d[threadIdx.x] = fd[threadIdx.x];
+        out_i[threadIdx.x] = fi[threadIdx.x];
+        if (cand) cand[threadIdx.x] = fi[threadIdx.x] >= 0 ? fi[threadIdx.x] : (fi[0] >= 0 ? fi[0] : fallback);
+    }
+}
+
+// query ring key (f32) from a descriptor on the device: polarcontext_invkeys_mat_.back() (Scancontext.cpp:333)
+__global__ void __launch_bounds__(32)
+sc_query_ringkey_kernel(const double *__restrict__ desc, float *__restrict__ key)
+{
+    const int r = threadIdx.x;
+    if (r >= R) return;
+    double acc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = desc[i * R + r];
+    for (int i = 4; i < S; i += 4)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += desc[(i + j) * R + r];
+    key[r] = (float)(((acc[0] + acc[2]) + (acc[1] + acc[3])) / (double)S);
+}
+
 // canonical 20x60 column-major descriptor(s) -> the three device records of a keyframe:
 // desc (the reference's 9600 bytes, verbatim), keys (f64 sector key + column norms, the reference's
 // arithmetic) and the f32 filter record (layout: K10 header).  One 64-thread CTA per keyframe.
 __global__ void __launch_bounds__(64)
 sc_pack_kernel(const double *__restrict__ canon, double *__restrict__ desc, double *__restrict__ keys,
-               float *__restrict__ frec, int count)
+               float *__restrict__ frec, float *__restrict__ rkeys, int count)
 {
     __shared__ float sq2[S];
     __shared__ double am[S];
@@ -883,6 +1021,18 @@ sc_pack_kernel(const double *__restrict__ canon, double *__restrict__ desc, doub
     float *fr = frec + (size_t)k * FREC_F;
     if (t == 0) flags = 0ull;
     for (int i = t; i < F_VK; i += 64) fr[i] = 0.f;          // pair padding included
+    if (t >= 64 - R) {
+        // ring key (Scancontext.cpp:198-211: row mean in Eigen's order), narrowed to float like
+        // eig2stdvec (:62-66) -- polarcontext_invkeys_mat_ (Scancontext.h:114)
+        const int r = t - (64 - R);
+        double acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = src[i * R + r];
+        for (int i = 4; i < S; i += 4)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] += src[(i + j) * R + r];
+        rkeys[(size_t)k * R + r] = (float)(((acc[0] + acc[2]) + (acc[1] + acc[3])) / (double)S);
+    }
     __syncthreads();
     if (t < S) {
         double v[R], sq[R];
@@ -933,6 +1083,10 @@ struct nrs_sc_db {
     double      *d_desc = nullptr;       // capacity x 1200 doubles: polarcontexts_ verbatim (Scancontext.h:111)
     double      *d_keys = nullptr;       // capacity x 120 doubles: sector key, column norms (f64)
     float       *d_frec = nullptr;       // capacity x FREC_F floats: filter records
+    float       *d_rkeys = nullptr;      // capacity x 20 floats: ring keys (polarcontext_invkeys_mat_)
+    float       *d_knn_pd = nullptr;     // per-block partial k-NN lists (distance, index)
+    int32_t     *d_knn_pi = nullptr;
+    float       *d_knn_out = nullptr;    // [0,16) d2, [16,32) idx, [32,48) candidate ids, [48,68) query ring key
     Survivor    *d_surv = nullptr;       // capacity entries
     int          size = 0;
     int          capacity = 0;
@@ -1014,14 +1168,19 @@ int db_reserve(nrs_sc_db *db, int want)
     int cap = db->capacity ? db->capacity : 1024;
     while (cap < want) cap *= 2;
     double *nd = nullptr, *nk = nullptr;
-    float *nf = nullptr;
+    float *nf = nullptr, *nr = nullptr, *npd = nullptr;
+    int32_t *npi = nullptr;
     Survivor *ns = nullptr;
+    const size_t n_part = ((size_t)cap / KNN_PER_BLOCK + 1) * KNN_MAX;
     cudaError_t e = cudaSuccess;
-    if ((e = cudaMalloc(&nd, (size_t)cap * DESC * sizeof(double))) != cudaSuccess ||
+    if ((e = cudaMalloc(&nr, (size_t)cap * R * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&npd, n_part * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&npi, n_part * sizeof(int32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&nd, (size_t)cap * DESC * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&nk, (size_t)cap * KEYS_D * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&nf, (size_t)cap * FREC_BYTES)) != cudaSuccess ||
         (e = cudaMalloc(&ns, ((size_t)cap + SURV_EXTRA) * sizeof(Survivor))) != cudaSuccess) {
-        cudaFree(nd); cudaFree(nk); cudaFree(nf); cudaFree(ns);
+        cudaFree(nd); cudaFree(nk); cudaFree(nf); cudaFree(ns); cudaFree(nr); cudaFree(npd); cudaFree(npi);
         nrs::set_error("nrs_sc_db: growing to %d keyframes: %s", cap, cudaGetErrorString(e));
         return NRS_ECUDA;
     }
@@ -1031,19 +1190,23 @@ int db_reserve(nrs_sc_db *db, int want)
         NRS_CUDA(cudaMemcpyAsync(nd, db->d_desc, (size_t)db->size * DESC * sizeof(double), cudaMemcpyDeviceToDevice, db->ctx->stream));
         NRS_CUDA(cudaMemcpyAsync(nk, db->d_keys, (size_t)db->size * KEYS_D * sizeof(double), cudaMemcpyDeviceToDevice, db->ctx->stream));
         NRS_CUDA(cudaMemcpyAsync(nf, db->d_frec, (size_t)db->size * FREC_BYTES, cudaMemcpyDeviceToDevice, db->ctx->stream));
+        NRS_CUDA(cudaMemcpyAsync(nr, db->d_rkeys, (size_t)db->size * R * sizeof(float), cudaMemcpyDeviceToDevice, db->ctx->stream));
         NRS_CUDA(cudaStreamSynchronize(db->ctx->stream));
     }
     cudaFree(db->d_desc); cudaFree(db->d_keys); cudaFree(db->d_frec); cudaFree(db->d_surv);
+    cudaFree(db->d_rkeys); cudaFree(db->d_knn_pd); cudaFree(db->d_knn_pi);
     db->d_desc = nd; db->d_keys = nk; db->d_frec = nf; db->d_surv = ns;
+    db->d_rkeys = nr; db->d_knn_pd = npd; db->d_knn_pi = npi;
     db->capacity = cap;
     return NRS_OK;
 }
 
 // canonical descriptors (device) -> records of keyframes [at, at + count)
-int pack_records(nrs_ctx *ctx, const double *d_canon, double *d_desc, double *d_keys, float *d_frec, int at, int count)
+int pack_records(nrs_ctx *ctx, const double *d_canon, double *d_desc, double *d_keys, float *d_frec, float *d_rkeys,
+                 int at, int count)
 {
     sc_pack_kernel<<<count, 64, 0, ctx->stream>>>(d_canon, d_desc + (size_t)at * DESC, d_keys + (size_t)at * KEYS_D,
-                                                  d_frec + (size_t)at * FREC_F, count);
+                                                  d_frec + (size_t)at * FREC_F, d_rkeys + (size_t)at * R, count);
     NRS_LAUNCHED();
     return NRS_OK;
 }
@@ -1100,6 +1263,7 @@ int nrs_sc_db_create(nrs_ctx *ctx, int capacity_hint, nrs_sc_db **out)
         (e = cudaMalloc(&db->d_state, sizeof(SearchState))) != cudaSuccess ||
         (e = cudaMalloc(&db->d_result, sizeof(nrs_sc_result))) != cudaSuccess ||
         (e = cudaMalloc(&db->d_query, DESC * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&db->d_knn_out, 68 * sizeof(float))) != cudaSuccess ||
         (e = cudaMallocHost(&db->h_result, sizeof(nrs_sc_result))) != cudaSuccess ||
         (e = cudaMallocHost(&db->h_query, DESC * sizeof(double))) != cudaSuccess ||
         init_state(db->d_state, ctx->stream) != NRS_OK) {
@@ -1120,6 +1284,7 @@ int nrs_sc_db_destroy(nrs_sc_db *db)
     cudaStreamSynchronize(db->ctx->stream);
     cudaFree(db->d_desc); cudaFree(db->d_keys); cudaFree(db->d_frec); cudaFree(db->d_surv);
     cudaFree(db->d_block); cudaFree(db->d_state);
+    cudaFree(db->d_rkeys); cudaFree(db->d_knn_pd); cudaFree(db->d_knn_pi); cudaFree(db->d_knn_out);
     for (void *m : db->x_opened) if (m) cudaIpcCloseMemHandle(m);
     cudaFree(db->x_local); cudaFree(db->x_peers_dev);
     cudaFree(db->d_result); cudaFree(db->d_query);
@@ -1163,7 +1328,7 @@ int nrs_sc_db_append(nrs_sc_db *db, const double *desc_host, int count)
         const int n = std::min(chunk, count - done);
         NRS_CUDA(cudaMemcpyAsync(d_stage, desc_host + (size_t)done * DESC, (size_t)n * DESC * sizeof(double),
                                  cudaMemcpyHostToDevice, ctx->stream));
-        rc = pack_records(ctx, d_stage, db->d_desc, db->d_keys, db->d_frec, db->size + done, n);
+        rc = pack_records(ctx, d_stage, db->d_desc, db->d_keys, db->d_frec, db->d_rkeys, db->size + done, n);
         if (rc) return rc;
         NRS_CUDA(cudaStreamSynchronize(ctx->stream));
     }
@@ -1188,7 +1353,7 @@ int nrs_sc_db_append_cloud(nrs_sc_db *db, const float *xyz, int P, double lidar_
     if (P) NRS_CUDA(cudaMemcpyAsync(d_xyz, xyz, (size_t)P * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     sc_make_kernel<<<1, 256, 0, ctx->stream>>>(d_xyz, P, lidar_height, max_radius, d_canon);
     NRS_LAUNCHED();
-    rc = pack_records(ctx, d_canon, db->d_desc, db->d_keys, db->d_frec, db->size, 1);
+    rc = pack_records(ctx, d_canon, db->d_desc, db->d_keys, db->d_frec, db->d_rkeys, db->size, 1);
     if (rc) return rc;
     if (desc_out) NRS_CUDA(cudaMemcpyAsync(desc_out, d_canon, DESC * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     NRS_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1292,6 +1457,83 @@ int nrs_sc_query_dev(nrs_sc_db *db, const double *query_dev, int first, int last
     return launch_search(db->ctx, view_of(db), query_dev, nullptr, first, std::max(0, last - first),
                          idx_offset, nullptr, nullptr, db->d_block, db->d_state, result_dev,
                          db->max_blocks);
+}
+
+// enqueue the two k-NN kernels: d_key (20 floats, device) against ring keys [first, last)
+static int launch_knn(nrs_sc_db *db, const float *d_key, int first, int last, int k)
+{
+    nrs_ctx *ctx = db->ctx;
+    const int n = std::max(0, last - first);
+    const int blocks = std::max(1, (n + KNN_PER_BLOCK - 1) / KNN_PER_BLOCK);
+    float *out_d = db->d_knn_out;
+    int32_t *out_i = reinterpret_cast<int32_t *>(db->d_knn_out + 16), *cand = reinterpret_cast<int32_t *>(db->d_knn_out + 32);
+    sc_knn_scan_kernel<<<blocks, KNN_THREADS, 0, ctx->stream>>>(db->d_rkeys, d_key, first, last, k, db->d_knn_pd, db->d_knn_pi);
+    NRS_LAUNCHED();
+    sc_knn_merge_kernel<<<1, KNN_THREADS, 0, ctx->stream>>>(db->d_knn_pd, db->d_knn_pi, blocks * k, k, first, out_d, out_i, cand);
+    NRS_LAUNCHED();
+    return NRS_OK;
+}
+
+int nrs_sc_knn(nrs_sc_db *db, const float *ringkey20_host, int first, int last, int k, int32_t *idx_out, float *d2_out)
+{
+    NRS_CHECK_ARG(db && ringkey20_host && idx_out, "bad argument");
+    NRS_CHECK_ARG(k >= 1 && k <= KNN_MAX, "k must be 1..16");
+    std::lock_guard<std::mutex> lk(db->mu);
+    NRS_CHECK_ARG(first >= 0 && last <= db->size && first <= last, "search range outside the database");
+    nrs_ctx *ctx = db->ctx;
+    std::lock_guard<std::mutex> lk2(ctx->mu);
+    NRS_CUDA(cudaSetDevice(ctx->device));
+    float *d_key = db->d_knn_out + 48;
+    NRS_CUDA(cudaMemcpyAsync(d_key, ringkey20_host, R * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_knn(db, d_key, first, last, k);
+    if (rc) return rc;
+    float h[32];
+    NRS_CUDA(cudaMemcpyAsync(h, db->d_knn_out, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    NRS_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int j = 0; j < k; ++j) {
+        int32_t id;
+        memcpy(&id, &h[16 + j], sizeof(id));
+        idx_out[j] = id;
+        if (d2_out) d2_out[j] = h[j];
+    }
+    return NRS_OK;
+}
+
+int nrs_sc_detect_knn(nrs_sc_db *db, const double *query_host, int first, int last, int k, int32_t *cand_out,
+                      nrs_sc_result *result_host)
+{
+    NRS_CHECK_ARG(db && query_host && result_host, "bad argument");
+    NRS_CHECK_ARG(k >= 1 && k <= KNN_MAX, "k must be 1..16");
+    std::lock_guard<std::mutex> lk(db->mu);
+    NRS_CHECK_ARG(first >= 0 && last <= db->size && first <= last, "search range outside the database");
+    nrs_ctx *ctx = db->ctx;
+    std::lock_guard<std::mutex> lk2(ctx->mu);
+    NRS_CUDA(cudaSetDevice(ctx->device));
+    if (last == first) {                       // empty tree: nothing found
+        result_host->dist = SENTINEL; result_host->idx = 0; result_host->shift = 0;
+        if (cand_out) for (int j = 0; j < k; ++j) cand_out[j] = -1;
+        return NRS_OK;
+    }
+    memcpy(db->h_query, query_host, DESC * sizeof(double));
+    NRS_CUDA(cudaMemcpyAsync(db->d_query, db->h_query, DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    float *d_key = db->d_knn_out + 48;
+    sc_query_ringkey_kernel<<<1, 32, 0, ctx->stream>>>(db->d_query, d_key);
+    NRS_LAUNCHED();
+    int rc = launch_knn(db, d_key, first, last, k);
+    if (rc) return rc;
+    // the k ids stay on the device and feed the candidate search directly (Scancontext.cpp:380-396)
+    const int32_t *d_cand = reinterpret_cast<const int32_t *>(db->d_knn_out + 32);
+    rc = launch_search(ctx, view_of(db), db->d_query, d_cand, 0, k, 0, nullptr, nullptr, db->d_block, db->d_state,
+                       db->d_result, db->max_blocks);
+    if (rc) return rc;
+    NRS_CUDA(cudaMemcpyAsync(db->h_result, db->d_result, sizeof(nrs_sc_result), cudaMemcpyDeviceToHost, ctx->stream));
+    float h[32];
+    if (cand_out) NRS_CUDA(cudaMemcpyAsync(h, db->d_knn_out, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    NRS_CUDA(cudaStreamSynchronize(ctx->stream));
+    *result_host = *db->h_result;
+    if (cand_out)
+        for (int j = 0; j < k; ++j) memcpy(&cand_out[j], &h[16 + j], sizeof(int32_t));
+    return NRS_OK;
 }
 
 int nrs_sc_xchg_create(nrs_sc_db *db, int world, int rank, unsigned char *handle_out)
@@ -1411,6 +1653,7 @@ int nrs_sc_pair(nrs_ctx *ctx, const double *sc1, const double *sc2, double *dist
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
     const size_t o_q = take(DESC * 8), o_k = take(DESC * 8), o_desc = take(DESC * 8);
     const size_t o_keys = take(KEYS_D * 8), o_frec = take(FREC_BYTES), o_surv = take(sizeof(Survivor) * (WARPS + 1));
+    const size_t o_rk = take(R * sizeof(float));
     const size_t o_blk = take(sizeof(BlockResult)), o_st = take(sizeof(SearchState)), o_res = take(sizeof(nrs_sc_result));
     const size_t o_d = take(8), o_s = take(4);
     int rc = ctx->scratch[2].reserve(off);
@@ -1428,7 +1671,7 @@ int nrs_sc_pair(nrs_ctx *ctx, const double *sc1, const double *sc2, double *dist
     if (rc) return rc;
     NRS_CUDA(cudaMemcpyAsync(d_q, sc1, DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     NRS_CUDA(cudaMemcpyAsync(d_k, sc2, DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    rc = pack_records(ctx, d_k, d_desc, d_keys, d_frec, 0, 1);
+    rc = pack_records(ctx, d_k, d_desc, d_keys, d_frec, reinterpret_cast<float *>(base + o_rk), 0, 1);
     if (rc) return rc;
     const DbView v{d_frec, d_desc, d_keys, reinterpret_cast<Survivor *>(base + o_surv)};
     rc = launch_search(ctx, v, d_q, nullptr, 0, 1, 0, d_dist, d_shift, d_block, d_state, d_res, 1);

@@ -135,6 +135,26 @@ class SCDatabase:
                                      C.byref(res)))
         return dist, shift, (res.dist, res.idx, res.shift)
 
+    def knn(self, ringkey, first=0, last=None, k=3):
+        """nrs_sc_knn: the k nearest ring keys among keyframes [first,last) -> (ids int32, squared distances f32)"""
+        key = np.ascontiguousarray(np.asarray(ringkey).reshape(-1), dtype=np.float32)
+        assert key.size == RINGS
+        last = len(self) if last is None else last
+        idx = np.empty(k, dtype=np.int32)
+        d2 = np.empty(k, dtype=np.float32)
+        check(lib().nrs_sc_knn(self._h, ptr(key), first, last, k, ptr(idx), ptr(d2)))
+        return idx, d2
+
+    def detect_knn(self, query, first=0, last=None, k=3):
+        """nrs_sc_detect_knn: ring key -> k nearest -> distanceBtnScanContext over them, all on the device.
+        -> ((dist, idx, shift), candidate ids)"""
+        q = f64(query, DESC)
+        last = len(self) if last is None else last
+        cand = np.empty(k, dtype=np.int32)
+        res = ScResult()
+        check(lib().nrs_sc_detect_knn(self._h, ptr(q), first, last, k, ptr(cand), C.byref(res)))
+        return (res.dist, res.idx, res.shift), cand
+
     def query_dev(self, query_dev_ptr, first, last, idx_offset, result_dev_ptr):
         check(lib().nrs_sc_query_dev(self._h, C.c_void_p(query_dev_ptr), first, last, idx_offset,
                                      C.c_void_p(result_dev_ptr)))
@@ -169,8 +189,9 @@ class SCManager:
     def __init__(self, ctx=None, device=0, candidate_fn=None):
         """candidate_fn(keys_to_search (n,20) float32, query_key (20,) float32, k) -> ids.
         None (default) = exhaustive search over every searchable keyframe, which is what
-        BASELINE.json's north_star specifies; pass a kNN callable to reproduce the
-        reference's 3-candidate behaviour on the same candidate set."""
+        BASELINE.json's north_star specifies; "kdtree" = the reference's own flow on the device
+        (ring-key k-NN with nanoflann's arithmetic, then the NUM_CANDIDATES_FROM_TREE candidates,
+        nrs_sc_detect_knn); a callable supplies the candidate ids from the host (tests)."""
         self.ctx = ctx if ctx is not None else _lib.Context(device)
         self.db = SCDatabase(self.ctx)
         self.SC_DIST_THRES = 0.2                       # Scancontext.h:99
@@ -269,6 +290,9 @@ class SCManager:
         curr_desc = flat(self.polarcontexts_[-1])
         if self._candidate_fn is None:
             min_dist, nn_idx, nn_align = self.db.query(curr_desc, 0, self._searchable_end)
+        elif self._candidate_fn == "kdtree":
+            (min_dist, nn_idx, nn_align), self.last_candidates = self.db.detect_knn(
+                curr_desc, 0, self._searchable_end, self.NUM_CANDIDATES_FROM_TREE)
         else:
             keys = np.stack(self.polarcontext_invkeys_to_search_).astype(np.float32)
             cand = self._candidate_fn(keys, self.polarcontext_invkeys_mat_[-1], self.NUM_CANDIDATES_FROM_TREE)
@@ -286,6 +310,11 @@ class SCManager:
         self.is_tree_batch_made = True
         if self._candidate_fn is None:
             min_dist, nn_idx, nn_align = self.db.query(q, 0, n)
+        elif self._candidate_fn == "kdtree":
+            # the reference searches the tree with the caller's curr_key (:297-300), whatever it is
+            cand, _ = self.db.knn(curr_key, 0, n, self.NUM_CANDIDATES_FROM_TREE)
+            self.last_candidates = cand
+            min_dist, nn_idx, nn_align = self.db.query(q, candidates=cand[cand >= 0])
         else:
             keys = np.stack(self.polarcontext_invkeys_mat_).astype(np.float32)
             cand = self._candidate_fn(keys, np.asarray(curr_key, dtype=np.float32), self.NUM_CANDIDATES_FROM_TREE)

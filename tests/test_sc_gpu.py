@@ -305,3 +305,58 @@ def test_cpp_adapters_end_to_end():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "adapters ok" in r.stdout
+
+
+def test_ringkey_knn_matches_reference_nanoflann(sc, ctx, oracle, synth):
+    """The candidate step of detectLoopClosureID on the device (nrs_sc_knn) against (a) the oracle's
+    brute force and (b) the reference's own vendored nanoflann compiled into oracle/_ref: same ids in the
+    same order, bit-identical squared distances (no exact ties in general-valued keys)."""
+    db, _ = synth.sc_database(9000, 300, seed=5, binary=False)
+    d = sc.SCDatabase(ctx, capacity_hint=16)                  # grows several times
+    d.append(db)
+    keys = np.stack([oracle.sc_ringkey_f32(x) for x in db[:9000]])
+    ref = oracle.ref_kdtree()
+    for qi, (first, last, k) in enumerate([(0, 9000, 3), (0, 8970, 10), (100, 4197, 16), (5, 6, 3), (0, 2, 3), (7, 7, 3)]):
+        q = oracle.sc_ringkey_f32(db[(qi * 997 + 13) % 9000])
+        idx, d2 = d.knn(q, first, last, k)
+        oi, od = oracle.sc_knn_bruteforce(keys[first:last], q, k)
+        oi = np.where(oi >= 0, oi + first, -1)
+        assert np.array_equal(idx, oi), (first, last, k)
+        n = int(np.sum(oi >= 0))
+        assert np.array_equal(d2[:n].view(np.uint32), od[:n].view(np.uint32))
+        if ref is not None and last - first >= k:
+            ri, rd = oracle.ref_knn(keys[first:last], q, k)
+            assert np.array_equal(idx, ri + first) and np.array_equal(d2.view(np.uint32), rd.view(np.uint32))
+    # exact ties (duplicated keyframes): ascending index among equal distances
+    dup = np.concatenate([db[:50], db[:50]])
+    d.clear()
+    d.append(dup)
+    idx, d2 = d.knn(oracle.sc_ringkey_f32(db[7]), 0, 100, 4)
+    assert list(idx[:2]) == [7, 57] and d2[0] == d2[1] == 0.0
+    d.close()
+
+
+def test_detect_flow_kdtree_mode(sc, ctx, oracle, synth):
+    """SCManager in the reference's own mode (ring-key k-NN + 3 candidates, every step on the device)
+    against the oracle fed with the reference nanoflann's candidates over the same searchable set."""
+    db, rev = synth.sc_database(400, 120, seed=21, binary=False)
+    m = sc.SCManager(ctx, candidate_fn="kdtree")
+    ref = oracle.ref_kdtree()
+    checked = 0
+    for i in range(400):
+        m.saveScancontextAndKeys(sc.as_desc(db[i]))
+        loop, yaw = m.detectLoopClosureID()
+        n = i + 1
+        if n < m.NUM_EXCLUDE_RECENT + 1:
+            assert loop == -1
+            continue
+        end = m._searchable_end
+        keys = np.stack([oracle.sc_ringkey_f32(x) for x in db[:end]])
+        qk = oracle.sc_ringkey_f32(db[i])
+        if end >= 3:
+            cand = oracle.ref_knn(keys, qk, 3)[0] if ref is not None else oracle.sc_knn_bruteforce(keys, qk, 3)[0]
+            assert np.array_equal(m.last_candidates, cand)
+            eloop, eyaw, emd, enn = oracle.sc_detect_from_candidates(db[i], db, cand, m.SC_DIST_THRES)
+            assert (loop, yaw) == (eloop, eyaw) and m.last_min_dist == emd and m.last_nn_idx == enn
+            checked += 1
+    assert checked > 300
