@@ -206,6 +206,10 @@ typedef struct nrs_solver_info {
     double  cost;
 } nrs_solver_info;
 
+/* diagnostics: %globaltimer (ns) stamps of the most recent nrs_orora_solve in this process --
+ * clique kernel [0] start [1] adjacency in shared memory [2] greedy bound [3] core pruning
+ * [4] exact search done; tail kernel [5] start [6] chain TIMs [7] GNC-TLS [8] COTE x [9] COTE y */
+int nrs_orora_last_timings(uint64_t *t_ns12);
 void nrs_solver_default_params(nrs_solver_params *p);
 
 /* ORORA::calcTransform (ORORA.hpp:37-93) minus the velocity bookkeeping the caller keeps:

@@ -110,6 +110,7 @@ def _declare(L):
     L.nrs_sc_db_device_ptr.restype = vp
     L.nrs_sc_db_device_ptr.argtypes = [vp]
     L.nrs_sc_filter_record_bytes.argtypes = []
+    L.nrs_orora_last_timings.argtypes = [vp]
     L.nrs_sc_knn.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.nrs_sc_detect_knn.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.nrs_sc_xchg_create.argtypes = [vp, i32, i32, vp]

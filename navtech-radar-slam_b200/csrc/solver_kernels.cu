@@ -30,12 +30,23 @@ namespace {
 
 constexpr int MAXN = 1024;      // one 32-bit adjacency word per lane
 constexpr int WORDS = 32;
+constexpr int SROW = 33;        // shared-memory row stride of the adjacency matrix (words): thread u reads row u,
+                                // an odd stride spreads a warp's 32 rows over 32 banks
 
 struct SolverInfoDev {
     int    valid, n_edges, M, gnc_iters, gnc_early_return, n_rot_inliers, n_final_inliers, clique_exact;
     double R[4], t[2], cost;
     long long nodes;
+    unsigned long long t_ns[12];   // %globaltimer stamps: clique [0] start [1] loaded [2] greedy [3] core [4] search done;
+                                   // tail [5] start [6] TIMs [7] GNC [8] COTE x [9] COTE y / end
 };
+__device__ __forceinline__ unsigned long long gtimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define STAMP(i) do { if (threadIdx.x == 0) info->t_ns[i] = gtimer(); } while (0)
 
 // ---- K7 ---------------------------------------------------------------------------------------
 // ORORA.hpp:139-151 Doppler compensation fused in front: p.x += beta*v*x*x/rsq; p.y += beta*v*x'*y/rsq
@@ -144,7 +155,7 @@ __device__ int warp_color_sort(uint32_t Pw, uint16_t *__restrict__ ord, uint16_t
             const int bit = __ffs(wd) - 1;
             const int v = f * 32 + bit;
             if (lane == f) { Qc &= ~(1u << bit); Q &= ~(1u << bit); }
-            Qc &= ~sadj[v * WORDS + lane];
+            Qc &= ~sadj[v * SROW + lane];
             if (lane == 0) { ord[n] = (uint16_t)v; col[n] = (uint16_t)k; }
             ++n;
         }
@@ -176,10 +187,11 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restri
 {
     extern __shared__ uint32_t sadj[];
     __shared__ uint32_t sP[WORDS];          // current vertex set, one word per entry
-    __shared__ int s_cnt[32], s_idx[32];
-    __shared__ int s_pick, s_changed;
+    __shared__ int s_changed;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < N * WORDS; i += CLQ_THREADS) sadj[i] = adjp[i];
+    STAMP(0);
+    const int nthr = blockDim.x;
+    for (int i = tid; i < N * WORDS; i += nthr) sadj[(i >> 5) * SROW + (i & 31)] = adjp[i];
     // all-vertices mask, word `lane`
     uint32_t full = 0;
     {
@@ -189,41 +201,58 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restri
     }
     if (warp == 0) sP[lane] = full;
     __syncthreads();
+    STAMP(1);
     // ---- greedy lower bound, whole block: take the vertex with the most neighbours inside the current
-    //      set (ties: lowest index), shrink the set to its neighbourhood (oracle/solver_ref.c) --------
+    //      set (ties: lowest index), shrink the set to its neighbourhood (oracle/solver_ref.c).  Every warp
+    //      keeps its own copy of the set, so one CTA barrier per step suffices: warp maxima by REDUX on a
+    //      packed (count, 1023 - index) key, exchanged through a double-buffered shared array ---------------
+    __shared__ uint32_t sPw[32][WORDS];
+    __shared__ int s_key[2][32], s_min[2][32];
+    const int nw = (N + 31) >> 5;
+    sPw[warp][lane] = full;
+    if (warp == 0) { s_key[0][lane] = -1; s_key[1][lane] = -1; s_min[0][lane] = 0x7fffffff; s_min[1][lane] = 0x7fffffff; }
+    __syncthreads();
     int best_n = 0;
-    for (;;) {
-        // thread u scores vertex u
-        int c = -1;
-        if (tid < N && ((sP[tid >> 5] >> (tid & 31)) & 1u)) {
-            c = 0;
-            for (int w = 0; w < WORDS; ++w) c += __popc(sadj[tid * WORDS + w] & sP[w]);
+    for (int buf = 0;; buf ^= 1) {
+        int key = -1, cmin = 0x7fffffff;
+        if (tid < N && ((sPw[warp][warp] >> lane) & 1u)) {
+            int c = 0;
+            for (int w = 0; w < nw; ++w) c += __popc(sadj[tid * SROW + w] & sPw[warp][w]);
+            key = (c << 10) | (1023 - tid);
+            cmin = c;
         }
-        int bi = tid;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const int oc = __shfl_xor_sync(0xffffffffu, c, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (oc > c || (oc == c && oi < bi)) { c = oc; bi = oi; }
-        }
-        if (lane == 0) { s_cnt[warp] = c; s_idx[warp] = bi; }
+        key = __reduce_max_sync(0xffffffffu, key);
+        cmin = __reduce_min_sync(0xffffffffu, cmin);
+        if (lane == 0) { s_key[buf][warp] = key; s_min[buf][warp] = cmin; }
         __syncthreads();
-        if (warp == 0) {
-            c = s_cnt[lane]; bi = s_idx[lane];
+        const int k2 = __reduce_max_sync(0xffffffffu, s_key[buf][lane]);
+        if (k2 < 0) break;
+        const int np = __reduce_add_sync(0xffffffffu, __popc(sPw[warp][lane]));
+        const int m2 = __reduce_min_sync(0xffffffffu, s_min[buf][lane]);
+        if (m2 == np - 1) {
+            // the set is a clique: the remaining steps would take its vertices one by one in ascending index
+            // (equal counts, lowest index first) -- emit them all at once
+            if (warp == 0) {
+                const uint32_t pw = sPw[0][lane];
+                int pre = __popc(pw);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const int oc = __shfl_xor_sync(0xffffffffu, c, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (oc > c || (oc == c && oi < bi)) { c = oc; bi = oi; }
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, pre, o);
+                    if (lane >= o) pre += up;
+                }
+                int pos = best_n + pre - __popc(pw);
+                for (uint32_t x = pw; x; x &= x - 1) best[pos++] = lane * 32 + __ffs(x) - 1;
             }
-            if (lane == 0) s_pick = (c >= 0) ? bi : -1;
+            best_n += np;
+            break;
         }
-        __syncthreads();
-        const int v = s_pick;
-        if (v < 0) break;
+        const int v = 1023 - (k2 & 1023);
         if (tid == 0) best[best_n] = v;
         ++best_n;
-        if (warp == 0) sP[lane] &= sadj[v * WORDS + lane];
-        __syncthreads();
+        sPw[warp][lane] &= sadj[v * SROW + lane];
+        __syncwarp();
     }
+    STAMP(2);
     // ---- peel to the best_n-core (Jacobi sweeps; the fixpoint does not depend on the order) ---------
     if (warp == 0) sP[lane] = full;
     __syncthreads();
@@ -233,7 +262,7 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restri
         bool drop = false;
         if (tid < N && ((sP[tid >> 5] >> (tid & 31)) & 1u)) {
             int c = 0;
-            for (int w = 0; w < WORDS; ++w) c += __popc(sadj[tid * WORDS + w] & sP[w]);
+            for (int w = 0; w < WORDS; ++w) c += __popc(sadj[tid * SROW + w] & sP[w]);
             drop = c < best_n;
         }
         __syncthreads();
@@ -242,6 +271,7 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restri
         __syncthreads();
         if (!s_changed) break;
     }
+    STAMP(3);
     // ---- method selection: complement edges inside the core (oracle/solver_ref.c orora_max_clique) ------
     __shared__ int s_ncore, s_mh2;
     if (tid == 0) { s_ncore = 0; s_mh2 = 0; }
@@ -250,7 +280,7 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restri
         int hc = 0;
         const bool in = tid < N && ((sP[tid >> 5] >> (tid & 31)) & 1u);
         if (in) {
-            for (int w = 0; w < WORDS; ++w) hc += __popc(~sadj[tid * WORDS + w] & sP[w]);
+            for (int w = 0; w < WORDS; ++w) hc += __popc(~sadj[tid * SROW + w] & sP[w]);
             hc -= 1;
         }
         const unsigned int bm = __ballot_sync(0xffffffffu, in);
@@ -268,7 +298,7 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restri
         __shared__ int sd[MAXN];
         __shared__ int s_size, s_depth, s_np, s_m2, s_md, s_vstar, s_improved, s_exact;
         __shared__ long long s_nodes;
-        if (warp == 0) { sCore[lane] = sP[lane]; bestC[lane] = 0u; }
+        if (warp == 0) { sCore[lane] = sP[lane]; bestC[lane] = 0u; sTake[lane] = 0u; }
         if (tid == 0) { s_depth = 0; s_improved = 0; s_exact = 1; s_nodes = 0; }
         if (tid < WORDS) { misStack[tid] = sP[tid]; misStack[WORDS + tid] = 0u; }
         if (tid == 0) { misStack[2 * WORDS] = 0u; misStack[2 * WORDS + 1] = 0u; misStack[2 * WORDS + 2] = 0u; }
@@ -287,7 +317,7 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restri
                     d = -1;
                     if (inP) {
                         d = 0;
-                        for (int w = 0; w < WORDS; ++w) d += __popc(~sadj[tid * WORDS + w] & sCore[w] & curP[w]);
+                        for (int w = 0; w < WORDS; ++w) d += __popc(~sadj[tid * SROW + w] & sCore[w] & curP[w]);
                         d -= 1;                                  // the complement row includes the vertex itself
                     }
                     if (tid < MAXN) sd[tid] = d;
@@ -298,7 +328,7 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restri
                     else if (d == 1) {
                         int u = -1;
                         for (int w = 0; w < WORDS && u < 0; ++w) {
-                            uint32_t x = ~sadj[tid * WORDS + w] & sCore[w] & curP[w];
+                            uint32_t x = ~sadj[tid * SROW + w] & sCore[w] & curP[w];
                             if ((tid >> 5) == w) x &= ~(1u << (tid & 31));
                             if (x) u = w * 32 + __ffs(x) - 1;
                         }
@@ -364,7 +394,7 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restri
                         ent[lane] = curP[lane]; ent[WORDS + lane] = curC[lane];          // reduced state for the exclude branch
                         uint32_t cw = curC[lane];
                         if (lane == (v >> 5)) cw |= 1u << (v & 31);
-                        child[lane] = curP[lane] & sadj[v * WORDS + lane];                // P \ H[v] \ {v}
+                        child[lane] = curP[lane] & sadj[v * SROW + lane];                // P \ H[v] \ {v}
                         child[WORDS + lane] = cw;
                     }
                     if (tid == 0) {
@@ -415,6 +445,7 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restri
             info->nodes = s_nodes;
             info->clique_exact = s_exact;
         }
+        STAMP(4);
         return;
     }
     if (warp != 0) return;
@@ -445,7 +476,7 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restri
             else {
                 if (lane == 0) cur[cur_n] = v;
                 ++cur_n;
-                const uint32_t Pn = P & sadj[v * WORDS + lane];
+                const uint32_t Pn = P & sadj[v * SROW + lane];
                 if (__ballot_sync(0xffffffffu, Pn != 0) == 0) {
                     if (cur_n > best_n) {
                         __syncwarp();
@@ -494,7 +525,7 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restri
 }
 
 // ---- K9 ---------------------------------------------------------------------------------------
-constexpr int TT = 1024;   // tail kernel threads
+constexpr int TT_MAX = 1024;   // tail kernel launch size; the kernel keeps nextpow2(M) threads alive
 
 struct TailSmem {
     double a[MAXN];          // general per-element scratch (ps.x / X)
@@ -506,7 +537,7 @@ struct TailSmem {
     int    tag[2 * MAXN];
     double s1[2 * MAXN], s2[2 * MAXN], s3[2 * MAXN], s4[2 * MAXN], s5[2 * MAXN];
     int    si[2 * MAXN];
-    double red[32 * 6];
+    double red[32 * 12];     // block_sum4/max: [0,192); block_sum5: two halves of 5 x 32 partials at [0,160) and [192,352)
     int    redi[32];
     int    clique[MAXN];
     unsigned char inl[MAXN];
@@ -526,8 +557,11 @@ __device__ __forceinline__ double warp_max(double v)
     return v;
 }
 
-// block-wide sum of up to 4 values per thread; result broadcast to all threads
-__device__ void block_sum4(double &x0, double &x1, double &x2, double &x3, double *red)
+// Live threads of the tail kernel: warps beyond what the clique size needs exit right after reading M
+// (CTA barriers count non-exited threads only), so every barrier and reduction below spans few warps.
+// block-wide sum of up to 4 values per thread; result broadcast to all threads.  `nwl` = live warps;
+// slots of exited warps read as zero, i.e. exactly what those warps used to contribute.
+__device__ void block_sum4(double &x0, double &x1, double &x2, double &x3, double *red, int nwl)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     x0 = warp_sum(x0); x1 = warp_sum(x1); x2 = warp_sum(x2); x3 = warp_sum(x3);
@@ -535,14 +569,31 @@ __device__ void block_sum4(double &x0, double &x1, double &x2, double &x3, doubl
     if (lane == 0) { red[warp * 4] = x0; red[warp * 4 + 1] = x1; red[warp * 4 + 2] = x2; red[warp * 4 + 3] = x3; }
     __syncthreads();
     if (warp == 0) {
-        double y0 = red[lane * 4], y1 = red[lane * 4 + 1], y2 = red[lane * 4 + 2], y3 = red[lane * 4 + 3];
+        const bool on = lane < nwl;
+        double y0 = on ? red[lane * 4] : 0.0, y1 = on ? red[lane * 4 + 1] : 0.0;
+        double y2 = on ? red[lane * 4 + 2] : 0.0, y3 = on ? red[lane * 4 + 3] : 0.0;
         y0 = warp_sum(y0); y1 = warp_sum(y1); y2 = warp_sum(y2); y3 = warp_sum(y3);
         if (lane == 0) { red[128] = y0; red[129] = y1; red[130] = y2; red[131] = y3; }
     }
     __syncthreads();
     x0 = red[128]; x1 = red[129]; x2 = red[130]; x3 = red[131];
 }
-__device__ double block_max(double x, double *red)
+// five values, two barriers: the partials alternate between two halves of `red` (parity), so the barrier that
+// protected the buffer against the previous call's readers is not needed
+__device__ void block_sum5(double &x0, double &x1, double &x2, double &x3, double &x4, double *red, int nwl, int parity)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *buf = red + parity * 192;
+    x0 = warp_sum(x0); x1 = warp_sum(x1); x2 = warp_sum(x2); x3 = warp_sum(x3); x4 = warp_sum(x4);
+    if (lane == 0) { buf[warp] = x0; buf[32 + warp] = x1; buf[64 + warp] = x2; buf[96 + warp] = x3; buf[128 + warp] = x4; }
+    __syncthreads();
+    // every warp finishes the sum itself (same tree in every warp: identical results), no broadcast barrier
+    const bool on = lane < nwl;
+    double y0 = on ? buf[lane] : 0.0, y1 = on ? buf[32 + lane] : 0.0, y2 = on ? buf[64 + lane] : 0.0;
+    double y3 = on ? buf[96 + lane] : 0.0, y4 = on ? buf[128 + lane] : 0.0;
+    x0 = warp_sum(y0); x1 = warp_sum(y1); x2 = warp_sum(y2); x3 = warp_sum(y3); x4 = warp_sum(y4);
+}
+__device__ double block_max(double x, double *red, int nwl)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     x = warp_max(x);
@@ -550,7 +601,7 @@ __device__ double block_max(double x, double *red)
     if (lane == 0) red[warp] = x;
     __syncthreads();
     if (warp == 0) {
-        double y = warp_max(red[lane]);
+        double y = warp_max(lane < nwl ? red[lane] : -INFINITY);
         if (lane == 0) red[128] = y;
     }
     __syncthreads();
@@ -569,9 +620,10 @@ __device__ void rot_from_H(double h00, double h10, double h01, double h11, doubl
 }
 
 // COTE on one axis (nonminimal_solver.hpp:532-661): X, alpha in sm.a / sm.b, M elements.
-__device__ double cote_axis(TailSmem &sm, int M, unsigned char *inl_and)
+__device__ double cote_axis(TailSmem &sm, int M, unsigned char *inl_and, int TT)
 {
     const int t = threadIdx.x;
+    const int nwl = TT >> 5;
     const int n2 = 2 * M;
     int P2 = 1;
     while (P2 < n2) P2 <<= 1;
@@ -588,70 +640,59 @@ __device__ double cote_axis(TailSmem &sm, int M, unsigned char *inl_and)
         }
     }
     __syncthreads();
-    // bitonic sort ascending on (key, original order) (:555 std::sort, restated stable)
-    for (int k = 2; k <= P2; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int e = t; e < P2; e += TT) {
-                const int p = e ^ j;
-                if (p > e) {
-                    const bool up = (e & k) == 0;
-                    const double ke = sm.key[e], kp = sm.key[p];
-                    const int oe = sm.si[e], op = sm.si[p];
-                    const bool gt = (ke > kp) || (ke == kp && oe > op);
-                    if (gt == up) {
-                        sm.key[e] = kp; sm.key[p] = ke;
-                        sm.si[e] = op; sm.si[p] = oe;
-                        const int te = sm.tag[e]; sm.tag[e] = sm.tag[p]; sm.tag[p] = te;
-                    }
-                }
+    // sort ascending on (key, original order) (:555 std::sort, restated stable) by counting ranks: with at
+    // most 2048 endpoints an all-pairs count needs no barrier at all (the bitonic network it replaces spent
+    // ~45 CTA barriers on a few hundred elements)
+    int rk[2];
+    {
+        int cnt = 0;
+        for (int e = t; e < n2; e += TT, ++cnt) {
+            const double ke = sm.key[e];
+            int r = 0;
+            for (int j = 0; j < n2; ++j) {
+                const double kj = sm.key[j];
+                r += (kj < ke) || (kj == ke && j < e);
             }
-            __syncthreads();
+            rk[cnt] = r;
         }
-    // per-endpoint increments (:604-612), then an inclusive block scan
+    }
     double tot = 0.0;
     {
         double x0 = (t < M) ? sm.b[t] : 0.0, x1 = 0, x2 = 0, x3 = 0;
-        block_sum4(x0, x1, x2, x3, sm.red);
+        block_sum4(x0, x1, x2, x3, sm.red, nwl);
         tot = x0;                         // ranges.sum() (:566)
     }
-    for (int e = t; e < P2; e += TT) {
-        double i1 = 0, i2 = 0, i3 = 0, i4 = 0, i5 = 0;
-        int ic = 0;
-        if (e < n2) {
-            const int tg = sm.tag[e];
-            const int idx = abs(tg) - 1;
-            const double eps = tg > 0 ? 1.0 : -1.0;
-            const double r = sm.b[idx], x = sm.a[idx];
+    // per-endpoint increments (:604-612) scattered to their sorted position
+    {
+        int cnt = 0;
+        for (int e = t; e < n2; e += TT, ++cnt) {
+            const int i = e >> 1;
+            const bool lo = (e & 1) == 0;
+            const double eps = lo ? 1.0 : -1.0;
+            const double r = sm.b[i], x = sm.a[i];
             const double wgt = 1.0 / (r * r);
-            ic = tg > 0 ? 1 : -1;
-            i1 = eps * wgt;               // dot_weights_consensus
-            i2 = eps * wgt * x;           // dot_X_weights
-            i3 = eps * r;                 // subtracted from ranges_inverse_sum
-            i4 = eps * x;                 // sum_xi
-            i5 = eps * x * x;             // sum_xi_square
+            const int d = rk[cnt];
+            sm.s1[d] = eps * wgt;         // dot_weights_consensus
+            sm.s2[d] = eps * wgt * x;     // dot_X_weights
+            sm.s3[d] = eps * r;           // subtracted from ranges_inverse_sum
+            sm.s4[d] = eps * x;           // sum_xi
+            sm.s5[d] = eps * x * x;       // sum_xi_square
+            sm.si[d] = lo ? 1 : -1;
         }
-        sm.s1[e] = i1; sm.s2[e] = i2; sm.s3[e] = i3; sm.s4[e] = i4; sm.s5[e] = i5; sm.si[e] = ic;
     }
     __syncthreads();
-    // Hillis-Steele inclusive scan over P2 <= 2048 elements (2 per thread)
-    for (int off = 1; off < P2; off <<= 1) {
-        double v1[2], v2[2], v3[2], v4[2], v5[2];
-        int vi[2];
-        int cnt = 0;
-        for (int e = t; e < P2; e += TT, ++cnt) {
-            const bool has = e >= off;
-            v1[cnt] = has ? sm.s1[e - off] : 0.0; v2[cnt] = has ? sm.s2[e - off] : 0.0;
-            v3[cnt] = has ? sm.s3[e - off] : 0.0; v4[cnt] = has ? sm.s4[e - off] : 0.0;
-            v5[cnt] = has ? sm.s5[e - off] : 0.0; vi[cnt] = has ? sm.si[e - off] : 0;
+    // running sums in sorted order, sequentially like the reference's loop (six independent chains, one lane each)
+    if (t < 6) {
+        if (t == 5) {
+            int acc = 0;
+            for (int e = 0; e < n2; ++e) { acc += sm.si[e]; sm.si[e] = acc; }
+        } else {
+            double *arr = t == 0 ? sm.s1 : t == 1 ? sm.s2 : t == 2 ? sm.s3 : t == 3 ? sm.s4 : sm.s5;
+            double acc = 0.0;
+            for (int e = 0; e < n2; ++e) { acc = acc + arr[e]; arr[e] = acc; }
         }
-        __syncthreads();
-        cnt = 0;
-        for (int e = t; e < P2; e += TT, ++cnt) {
-            sm.s1[e] += v1[cnt]; sm.s2[e] += v2[cnt]; sm.s3[e] += v3[cnt];
-            sm.s4[e] += v4[cnt]; sm.s5[e] += v5[cnt]; sm.si[e] += vi[cnt];
-        }
-        __syncthreads();
     }
+    __syncthreads();
     // x_hat, cost (:618-622) and the first minimum (:626)
     double bc = INFINITY, bh = 0.0;
     int bi = 0x7fffffff;
@@ -675,7 +716,8 @@ __device__ double cote_axis(TailSmem &sm, int M, unsigned char *inl_and)
         if (lane == 0) { sm.red[warp] = bc; sm.red[32 + warp] = bh; sm.redi[warp] = bi; }
         __syncthreads();
         if (warp == 0) {
-            bc = sm.red[lane]; bh = sm.red[32 + lane]; bi = sm.redi[lane];
+            bc = lane < nwl ? sm.red[lane] : INFINITY; bh = lane < nwl ? sm.red[32 + lane] : 0.0;
+            bi = lane < nwl ? sm.redi[lane] : 0x7fffffff;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const double oc = __shfl_xor_sync(0xffffffffu, bc, o);
@@ -693,7 +735,7 @@ __device__ double cote_axis(TailSmem &sm, int M, unsigned char *inl_and)
     return est;
 }
 
-__global__ void __launch_bounds__(TT)
+__global__ void __launch_bounds__(TT_MAX)
 orora_tail_kernel(const double *__restrict__ src, const double *__restrict__ tgt, int N,
                   const int *__restrict__ perm, const int *__restrict__ best,
                   double noise_bound, int max_iter, double gnc_factor, double cost_thr,
@@ -705,7 +747,13 @@ orora_tail_kernel(const double *__restrict__ src, const double *__restrict__ tgt
     TailSmem &sm = *reinterpret_cast<TailSmem *>(tail_raw);
     const int t = threadIdx.x;
     const int M = info->M;
+    STAMP(5);
     if (t < 16) T_out[t] = (t % 5 == 0) ? 1.0 : 0.0;           // :681 identity on failure
+    // threads kept alive: the next power of two >= M (the COTE sort handles 2 endpoints per thread), >= 32
+    int TT = 32;
+    while (TT < M) TT <<= 1;
+    if (t >= TT) return;
+    const int nwl = TT >> 5;
     if (M <= 1) {                                             // :715-720
         if (t == 0) { info->valid = 0; info->R[0] = 1; info->R[1] = 0; info->R[2] = 0; info->R[3] = 1; info->t[0] = info->t[1] = 0; }
         return;
@@ -729,8 +777,9 @@ orora_tail_kernel(const double *__restrict__ src, const double *__restrict__ tgt
         const double rr = tgt[2 * root] * tgt[2 * root] + tgt[2 * root + 1] * tgt[2 * root + 1] + 1.0;
         w0 = 1.0 / sqrt(rl + rr);
     }
-    const double max_w = block_max(t < M ? w0 : 0.0, sm.red);
+    const double max_w = block_max(t < M ? w0 : 0.0, sm.red, nwl);
     w0 = w0 / max_w;
+    STAMP(6);
     // ---- GNC-TLS (:292-440) ------------------------------------------------------------------------
     const double sx = t < M ? sm.a[t] : 0.0, sy = t < M ? sm.b[t] : 0.0;
     const double dx = t < M ? sm.c[t] : 0.0, dy = t < M ? sm.d[t] : 0.0;
@@ -742,14 +791,14 @@ orora_tail_kernel(const double *__restrict__ src, const double *__restrict__ tgt
     double cost = INFINITY, prev_cost = INFINITY;
     {
         double h00 = sx * w0 * dx, h10 = sy * w0 * dx, h01 = sx * w0 * dy, h11 = sy * w0 * dy;
-        block_sum4(h00, h10, h01, h11, sm.red);
+        block_sum4(h00, h10, h01, h11, sm.red, nwl);
         rot_from_H(h00, h10, h01, h11, R);                    // :333
     }
     {
         const double ex = dx - (R[0] * sx + R[2] * sy), ey = dy - (R[1] * sx + R[3] * sy);
         res = ex * ex + ey * ey;
     }
-    const double max_res = block_max(t < M ? res : -INFINITY, sm.red);
+    const double max_res = block_max(t < M ? res : -INFINITY, sm.red, nwl);
     if (max_res < nb2) nb2 = 0.01;                            // :342-344
     double mu = 1 / (2 * max_res / nb2 - 1);
     if (mu <= 0) {
@@ -762,34 +811,42 @@ orora_tail_kernel(const double *__restrict__ src, const double *__restrict__ tgt
             else wgt = sqrt(nb2 * mu * (mu + 1) / res + 0.00000000000001) - mu;   // :368
             mu = mu * gnc_factor;
         }
-        for (int it = 0; it < max_iter; ++it) {               // :376-433
+        // One CTA reduction per iteration: the cost of iteration it-1 rides along with the correlation sums
+        // of iteration it, so its stopping test is evaluated one pass later -- before anything of iteration
+        // it is applied.  Values and order of every sum are unchanged.
+        double cterm = 0.0;
+        for (int it = 0; it <= max_iter; ++it) {              // :376-433
             double h00 = (t < M) ? sx * wgt * dx : 0.0, h10 = (t < M) ? sy * wgt * dx : 0.0;
             double h01 = (t < M) ? sx * wgt * dy : 0.0, h11 = (t < M) ? sy * wgt * dy : 0.0;
-            block_sum4(h00, h10, h01, h11, sm.red);
+            double c0 = (t < M) ? cterm : 0.0;
+            block_sum5(h00, h10, h01, h11, c0, sm.red, nwl, (it + 1) & 1);   // first call: upper half (red[128] may still be read)
+            if (it > 0) {
+                cost = c0;
+                const double cost_diff = fabs(cost - prev_cost);
+                prev_cost = cost;
+                iters = it;
+                if (cost_diff < cost_thr) break;
+            }
+            if (it == max_iter) break;
             rot_from_H(h00, h10, h01, h11, R);
             const double ex = dx - (R[0] * sx + R[2] * sy), ey = dy - (R[1] * sx + R[3] * sy);
             res = ex * ex + ey * ey;
-            double c0 = (t < M) ? wgt * res : 0.0, c1 = 0, c2 = 0, c3 = 0;
-            block_sum4(c0, c1, c2, c3, sm.red);
-            cost = c0;
+            cterm = wgt * res;
             const double th1 = (mu + 1) / mu * nb2, th2 = mu / (mu + 1) * nb2;
             if (res >= th1) wgt = 0;
             else if (res <= th2) wgt = 1;
             else wgt = sqrt(nb2 * mu * (mu + 1) / res) - mu;  // :406
-            const double cost_diff = fabs(cost - prev_cost);
             mu = mu * gnc_factor;
-            prev_cost = cost;
-            iters = it + 1;
-            if (cost_diff < cost_thr) break;
         }
     }
+    STAMP(7);
     if (t < M) sm.rot_inl[t] = early ? 0 : (wgt >= 0.4);      // :435-439
     __syncthreads();
     double nrot = 0.0;
     if (t < M) nrot = (sm.rot_inl[t == 0 ? M - 1 : t - 1] && sm.rot_inl[t]) ? 1.0 : 0.0;   // :776-789
     {
         double z1 = 0, z2 = 0, z3 = 0;
-        block_sum4(nrot, z1, z2, z3, sm.red);
+        block_sum4(nrot, z1, z2, z3, sm.red, nwl);
     }
     // ---- translation (:480-529): rotate the clique's source points, anisotropic bounds, COTE ------
     double ax = 0, ay = 0, X0 = 0, X1 = 0;
@@ -811,10 +868,12 @@ orora_tail_kernel(const double *__restrict__ src, const double *__restrict__ tgt
     __syncthreads();
     if (t < M) { sm.a[t] = X0; sm.b[t] = ax; }
     __syncthreads();
-    const double tx = cote_axis(sm, M, sm.inl);
+    const double tx = cote_axis(sm, M, sm.inl, TT);
+    STAMP(8);
     if (t < M) { sm.a[t] = X1; sm.b[t] = ay; }
     __syncthreads();
-    const double ty = cote_axis(sm, M, sm.inl);
+    const double ty = cote_axis(sm, M, sm.inl, TT);
+    STAMP(9);
     // ---- final inliers (:807-818), compose (:820-824) -------------------------------------------
     if (t == 0) {
         int nf = 0;
@@ -848,6 +907,7 @@ struct SolverBufs {
 };
 
 size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+unsigned long long g_last_t_ns[12];
 
 int carve(nrs_ctx *ctx, int N, SolverBufs &b)
 {
@@ -878,7 +938,7 @@ int configure_solver_kernels()
     static int done = 0;
     if (!done) {
         NRS_CUDA(cudaFuncSetAttribute(orora_clique_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      MAXN * WORDS * 4));
+                                      MAXN * SROW * 4));
         NRS_CUDA(cudaFuncSetAttribute(orora_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(TailSmem)));
         done = 1;
@@ -933,10 +993,10 @@ int nrs_orora_solve(nrs_ctx *ctx, const double *prev_2xN, const double *curr_2xN
     orora_permute_kernel<<<(nthreads + 255) / 256, 256, 0, st>>>(b.d_adj, b.d_perm, N, b.d_adjp);
     NRS_LAUNCHED();
     const long long node_limit = p->clique_node_limit > 0 ? p->clique_node_limit : 2000000;
-    orora_clique_kernel<<<1, CLQ_THREADS, (size_t)N * WORDS * 4, st>>>(b.d_adjp, N, b.d_stackP, b.d_ord, b.d_col, b.d_cur,
+    orora_clique_kernel<<<1, std::max(64, (N + 31) & ~31), (size_t)N * SROW * 4, st>>>(b.d_adjp, N, b.d_stackP, b.d_ord, b.d_col, b.d_cur,
                                                              b.d_best, b.d_idx, b.d_info, node_limit, b.d_mis);
     NRS_LAUNCHED();
-    orora_tail_kernel<<<1, TT, sizeof(TailSmem), st>>>(b.d_src, b.d_tgt, N, b.d_perm, b.d_best, p->noise_bound,
+    orora_tail_kernel<<<1, TT_MAX, sizeof(TailSmem), st>>>(b.d_src, b.d_tgt, N, b.d_perm, b.d_best, p->noise_bound,
                                                        p->rotation_max_iterations, p->rotation_gnc_factor,
                                                        p->rotation_cost_threshold, p->noise_bound_radial,
                                                        p->noise_bound_tangential, b.d_info, b.d_T, b.d_clique,
@@ -966,11 +1026,19 @@ int nrs_orora_solve(nrs_ctx *ctx, const double *prev_2xN, const double *curr_2xN
     info_out->n_final_inliers = h_info->n_final_inliers;
     info_out->clique_exact = h_info->clique_exact;
     info_out->clique_nodes = h_info->nodes;
+    for (int i = 0; i < 12; ++i) g_last_t_ns[i] = h_info->t_ns[i];
     for (int i = 0; i < 4; ++i) info_out->R[i] = h_info->R[i];
     info_out->t[0] = h_info->t[0]; info_out->t[1] = h_info->t[1];
     info_out->cost = h_info->cost;
     if (clique_out) memcpy(clique_out, h_clique, (size_t)h_info->M * 4);
     if (final_inliers_out) memcpy(final_inliers_out, h_final, (size_t)h_info->n_final_inliers * 4);
+    return NRS_OK;
+}
+
+int nrs_orora_last_timings(uint64_t *t_ns12)
+{
+    if (!t_ns12) return NRS_EINVAL;
+    for (int i = 0; i < 12; ++i) t_ns12[i] = g_last_t_ns[i];
     return NRS_OK;
 }
 
