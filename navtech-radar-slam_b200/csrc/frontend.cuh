@@ -62,6 +62,10 @@ struct FrontendState {
     float *d_pts32 = nullptr;            // 2 * KP_CAP float x,y
     int   *d_rowcount = nullptr;         // per-row keypoint counts / offsets
     int    R = 0, C = 0, pitch = 0;
+    // the Cartesian-image branch of extractFeature (remap, 8-bit conversion, ORB's blur) does not depend on
+    // the keypoints: it runs on a second stream beside cen2019 and joins in front of the descriptor kernel
+    cudaStream_t st_img = nullptr;
+    cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
 };
 
 }  // namespace nrs

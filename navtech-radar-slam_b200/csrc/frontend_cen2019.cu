@@ -478,13 +478,13 @@ fe_bev_kernel(const double *__restrict__ pts_xy, const long long *__restrict__ t
 static int stats_blocks(const nrs_ctx *ctx) { return ctx->sm_count * 8; }
 
 int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_points, int min_range,
-                      int *d_polar)
+                      int *d_polar, bool reset_counts)
 {
     cudaStream_t st = ctx->stream;
     const size_t N = (size_t)R * C;
     const int nb = stats_blocks(ctx);
     FrameCounts *cnt = S.d_counts;
-    NRS_CUDA(cudaMemsetAsync(cnt, 0, sizeof(FrameCounts), st));
+    if (reset_counts) NRS_CUDA(cudaMemsetAsync(cnt, 0, sizeof(FrameCounts), st));
     fe_stats_kernel<<<nb, RED_THREADS, 0, st>>>(S.d_fft, R, C, S.d_partial, (int *)&cnt->maxg);
     NRS_LAUNCHED();
     fe_mean_kernel<<<1, 32, 0, st>>>(S.d_partial, nb, 1.0 / (double)N, &cnt->mean);
@@ -537,8 +537,13 @@ int fe_points_voxel_bev_device(nrs_ctx *ctx, FrontendState &S, nrs_frame *f)
                                                S.d_vval[0], S.d_pts32);
         NRS_LAUNCHED();
         size_t need = S.cub_bytes;
+        // voxel keys are i0 + i1 * div_x with both indices below extent / leaf + 2 (the points lie within the
+        // sensor range): when that product stays under 2^24 three radix passes suffice.  The padding key
+        // 0xffffffff has its low 24 bits set, so it still sorts behind every real key.
+        const double cells = 2.0 * S.C * p.radar_resolution / p.voxel_size + 4.0;
+        const int end_bit = (cells * cells < 16777214.0) ? 24 : 32;
         NRS_CUDA(cub::DeviceRadixSort::SortPairs(S.d_cub, need, S.d_vkey[0], S.d_vkey[1], S.d_vval[0], S.d_vval[1],
-                                                 FE_KP_CAP, 0, 32, st));
+                                                 FE_KP_CAP, 0, end_bit, st));
         g_launches.fetch_add(1, std::memory_order_relaxed);
         // voxel centroids are staged in d_partial's neighbour: reuse d_keys[0] (free after the sort)
         double *vox = reinterpret_cast<double *>(S.d_keys[0]);

@@ -30,7 +30,8 @@
 
 namespace nrs {
 
-int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_points, int min_range, int *d_polar);
+int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_points, int min_range, int *d_polar,
+                      bool reset_counts = true);
 int fe_points_voxel_bev_device(nrs_ctx *ctx, FrontendState &S, nrs_frame *f);
 int fe_decode_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int pitch);
 size_t fe_cub_bytes(size_t N);
@@ -287,6 +288,9 @@ static void frontend_free(void *p)
                    S->d_vkey[0], S->d_vkey[1], S->d_vval[0], S->d_vval[1], S->d_pts32, S->d_rowcount};
     for (void *d : dev) if (d) cudaFree(d);
     if (S->h_counts) cudaFreeHost(S->h_counts);
+    if (S->st_img) { cudaStreamSynchronize(S->st_img); cudaStreamDestroy(S->st_img); }
+    if (S->ev_fork) cudaEventDestroy(S->ev_fork);
+    if (S->ev_join) cudaEventDestroy(S->ev_join);
     delete S;
 }
 
@@ -317,6 +321,9 @@ static int frontend_state(nrs_ctx *ctx, const nrs_extract_params *p, int R, int 
     ctx->frontend = S;
     ctx->frontend_free = frontend_free;
     S->p = *p; S->R = R; S->C = C; S->pitch = pitch;
+    NRS_CUDA(cudaStreamCreateWithFlags(&S->st_img, cudaStreamNonBlocking));
+    NRS_CUDA(cudaEventCreateWithFlags(&S->ev_fork, cudaEventDisableTiming));
+    NRS_CUDA(cudaEventCreateWithFlags(&S->ev_join, cudaEventDisableTiming));
     const int W = p->cart_pixel_width;
     const size_t N = (size_t)R * C, WW = (size_t)W * W;
     int rc = 0;
@@ -538,21 +545,31 @@ int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw, int R, int row_pitch, co
     NRS_CUDA(cudaMemcpyAsync(S->d_times, times, R * sizeof(long long), cudaMemcpyHostToDevice, st));
 
     // ---- device pipeline ------------------------------------------------------------------------
+    NRS_CUDA(cudaMemsetAsync(S->d_counts, 0, sizeof(FrameCounts), st));
     if ((rc = fe_decode_device(ctx, *S, R, C, row_pitch))) { frame_release_locked(f); return rc; }
-    if ((rc = fe_cen2019_device(ctx, *S, R, C, p->max_points, p->min_range, f->d_polar))) { frame_release_locked(f); return rc; }
-    fe_remap_kernel<<<(W * W + 255) / 256, 256, 0, st>>>(S->d_fft, R, C, S->d_theta, S->d_sx, S->d_az, S->d_azsort,
+    // fork: Cartesian image branch (radar_utils.cpp:227-316 + ORB's blur) on the second stream
+    cudaStream_t si = S->st_img;
+    NRS_CUDA(cudaEventRecord(S->ev_fork, st));
+    NRS_CUDA(cudaStreamWaitEvent(si, S->ev_fork, 0));
+    fe_remap_kernel<<<(W * W + 255) / 256, 256, 0, si>>>(S->d_fft, R, C, S->d_theta, S->d_sx, S->d_az, S->d_azsort,
                                                         S->d_azidx, n_sorted, p->navtech_version == 0,
                                                         p->interpolate_crossover, W, S->d_cart,
                                                         (int *)&S->d_counts->cart_max);
     NRS_LAUNCHED();
-    fe_to_u8_kernel<<<(W * W + 255) / 256, 256, 0, st>>>(S->d_cart, W * W, S->d_counts, f->d_img);
+    fe_to_u8_kernel<<<(W * W + 255) / 256, 256, 0, si>>>(S->d_cart, W * W, S->d_counts, f->d_img);
     NRS_LAUNCHED();
-    if ((rc = fe_points_voxel_bev_device(ctx, *S, f))) { frame_release_locked(f); return rc; }
     dim3 bg((W + 255) / 256, W);
-    fe_blur_row_kernel<<<bg, 256, 0, st>>>(f->d_img, W, S->d_rowbuf);
+    fe_blur_row_kernel<<<bg, 256, 0, si>>>(f->d_img, W, S->d_rowbuf);
     NRS_LAUNCHED();
-    fe_blur_col_kernel<<<bg, 256, 0, st>>>(S->d_rowbuf, W, S->d_blur);
+    fe_blur_col_kernel<<<bg, 256, 0, si>>>(S->d_rowbuf, W, S->d_blur);
     NRS_LAUNCHED();
+    NRS_CUDA(cudaEventRecord(S->ev_join, si));
+    // keypoint branch on the context stream
+    if ((rc = fe_cen2019_device(ctx, *S, R, C, p->max_points, p->min_range, f->d_polar, false))) {
+        cudaStreamSynchronize(si); frame_release_locked(f); return rc;
+    }
+    if ((rc = fe_points_voxel_bev_device(ctx, *S, f))) { cudaStreamSynchronize(si); frame_release_locked(f); return rc; }
+    NRS_CUDA(cudaStreamWaitEvent(st, S->ev_join, 0));           // join
     fe_brief_kernel<<<(FE_KP_CAP * 32 + 255) / 256, 256, 0, st>>>(S->d_blur, W, f->d_kp_orb, S->d_counts, S->d_pattern, f->d_desc);
     NRS_LAUNCHED();
     NRS_CUDA(cudaMemcpyAsync(S->h_counts, S->d_counts, sizeof(FrameCounts), cudaMemcpyDeviceToHost, st));
