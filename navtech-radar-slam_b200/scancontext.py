@@ -442,6 +442,9 @@ class ShardedSCDatabase:
         torch, dist = self._torch, self._dist
         last = self.n_total if last is None else last
         q = f64(query, DESC)
+        if self.world == 1 and self.db is not None:
+            # one GPU: the plain C-ABI call (host query in, host result out), nothing to exchange
+            return self.db.query(q, max(first, 0), max(first, min(last, self._local_n)))
         if self.exchange == "peer":
             # local search + in-kernel exchange over peer memory: the record that comes back is global
             lo, hi = local_range(first, last, self.rank, self.world)
