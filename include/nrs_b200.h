@@ -244,7 +244,9 @@ typedef struct nrs_extract_params {
     int32_t interpolate_crossover;  /* 1 */
     double  voxel_size;             /* 0.6 m */
     float   nndr;                   /* 0.8 */
-    int32_t pad_;
+    int32_t keypoint_extraction;    /* 0 = "cen2019" (default), 1 = "cen2018" (radar_loader.hpp:95-99) */
+    float   zq;                     /* cen2018: 3.0 (radar_loader.hpp:284) */
+    int32_t sigma_gauss;            /* cen2018: 17, odd (radar_loader.hpp:285) */
 } nrs_extract_params;
 
 /* counts and scalars of one extraction, for callers and stage-parity tests */
@@ -271,10 +273,16 @@ int nrs_extract_default_params(const char *dataset, nrs_extract_params *p);
 int nrs_cen2019(nrs_ctx *ctx, const float *fft_RxC, int R, int C, int max_points, int min_range,
                 double *targets_3xKcap, int Kcap, int *K);
 
+/* cen2018features (features.hpp:27, features.cpp:44-131) as a stand-alone operator -- the extractor the
+ * shipped launch file selects (run_orora.launch:11).  Same conventions as nrs_cen2019.  y_RxC (nullable,
+ * host, R x C floats) receives the per-pixel response for stage-wise comparison (0 left of min_range). */
+int nrs_cen2018(nrs_ctx *ctx, const float *fft_RxC, int R, int C, float zq, int sigma_gauss, int min_range,
+                double *targets_3xKcap, int Kcap, int *K, float *y_RxC);
+
 /* RadarLoader::extractFeature (radar_loader.hpp:74-141) on the decoded 8-bit rows of one
  * "oxford-form" polar PNG (what cv::imread hands load_radar, radar_utils.cpp:104-129):
  * row i = [int64 stamp | uint16 encoder | valid | R bins of power ...], row_pitch bytes apart.
- * load_radar -> cen2019features -> polar_to_cartesian_radar_img -> polar_to_cartesian_points ->
+ * load_radar -> cen2019features | cen2018features -> polar_to_cartesian_radar_img -> polar_to_cartesian_points ->
  * voxelize -> convert_to_bev -> ORB compute.  t_criteria = the stamp in the file name. */
 int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw_rows, int R, int row_pitch,
                       const nrs_extract_params *p, int64_t t_criteria, nrs_frame **out);

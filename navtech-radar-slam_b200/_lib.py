@@ -47,7 +47,7 @@ class ExtractParams(C.Structure):
                 ("cart_resolution", C.c_float), ("cart_pixel_width", C.c_int32), ("min_range", C.c_int32),
                 ("max_points", C.c_int32), ("patch_size", C.c_int32), ("use_voxelization", C.c_int32),
                 ("interpolate_crossover", C.c_int32), ("voxel_size", C.c_double), ("nndr", C.c_float),
-                ("pad_", C.c_int32)]
+                ("keypoint_extraction", C.c_int32), ("zq", C.c_float), ("sigma_gauss", C.c_int32)]
 
 
 class FrameInfo(C.Structure):
@@ -125,6 +125,7 @@ def _declare(L):
     L.nrs_orora_solve.argtypes = [vp, vp, vp, i32, vp, f64, vp, vp, vp, vp]
     L.nrs_extract_default_params.argtypes = [C.c_char_p, vp]
     L.nrs_cen2019.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, vp]
+    L.nrs_cen2018.argtypes = [vp, vp, i32, i32, C.c_float, i32, i32, vp, i32, vp, vp]
     L.nrs_frame_extract.argtypes = [vp, vp, i32, i32, vp, C.c_int64, C.POINTER(vp)]
     L.nrs_frame_destroy.argtypes = [vp]
     L.nrs_frame_info_get.argtypes = [vp, vp]

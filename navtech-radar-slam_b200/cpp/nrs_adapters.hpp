@@ -6,6 +6,7 @@
 //
 //   nrs::SCManagerT<MatrixXd, Cloud>   <-> pgo/SC-A-LOAM/include/scancontext/Scancontext.h:57-122
 //   nrs::cen2019features               <-> outlier-robust-radar-odometry/include/features.hpp:36
+//   nrs::cen2018features               <-> outlier-robust-radar-odometry/include/features.hpp:27
 //   nrs::RadarLoaderT<MatrixXd>        <-> include/radar_loader.hpp:35-308 (extractFeature, matchFeatures)
 //   nrs::ORORAT<MatrixXd>              <-> include/ORORA.hpp:13-181 (calcTransform)
 //   nrs::setParams                     <-> include/solver/nonminimal_solver.hpp:959-973
@@ -211,6 +212,20 @@ double cen2019features(const float *fft_data, int rows, int cols, int max_points
     return 0.0;
 }
 
+// cen2018features (features.hpp:27): same conventions
+template <class MatrixXd>
+double cen2018features(const float *fft_data, int rows, int cols, float zq, int sigma_gauss, int min_range,
+                       MatrixXd &targets, nrs_ctx *ctx = nullptr)
+{
+    std::vector<double> buf(3 * 16384);
+    int K = 0;
+    check(nrs_cen2018(ctx ? ctx : default_ctx(), fft_data, rows, cols, zq, sigma_gauss, min_range, buf.data(), 16384, &K,
+                      nullptr));
+    targets.resize(3, K);
+    std::memcpy(targets.data(), buf.data(), sizeof(double) * 3 * (size_t)K);
+    return 0.0;
+}
+
 // ================================================================================================
 // RadarFeature / RadarLoader (radar_loader.hpp:16-33, 35-308)
 // ================================================================================================
@@ -242,7 +257,7 @@ public:
         check(nrs_extract_default_params(dataset.c_str(), &p_));                   // throws invalid_argument like :62
         if (keypoint_extraction != "cen2018" && keypoint_extraction != "cen2019")
             throw std::invalid_argument("Keypoint extraction method seems to be wrong!");   // :64-66
-        if (keypoint_extraction != "cen2019") throw std::invalid_argument("only cen2019 is implemented on the GPU path");
+        p_.keypoint_extraction = keypoint_extraction == "cen2018" ? 1 : 0;         // :95-99
         p_.voxel_size = voxel_size;
         p_.use_voxelization = use_voxelization ? 1 : 0;
         time_unit_denominator_ = dataset == "oxford" ? 1000000.0 : 1000000000.0;

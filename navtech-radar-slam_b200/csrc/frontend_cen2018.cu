@@ -1,0 +1,239 @@
+// frontend_cen2018.cu -- cen2018features (outlier-robust-radar-odometry/src/features.cpp:44-131), the
+// keypoint extractor the shipped launch file selects (run_orora.launch:11).
+//
+// Arithmetic contract (what makes the output identical to the reference's):
+//   * per-azimuth bias (:49-59) and noise level (:77-91) are SEQUENTIAL float sums in column order; they
+//     are kept sequential here (one thread per azimuth walks its row through shared-memory tiles that the
+//     whole CTA loads coalesced), because any other order rounds differently;
+//   * the Gaussian taps (:62-73) are computed on the host with the same libm exp() the reference links;
+//   * cv::filter2D with that 1 x 3*sigma kernel (:74) is OpenCV's direct filter engine: per output pixel one
+//     forward chain acc = fma(src[j + k - anchor], tap[k], acc) over k, starting from 0, BORDER_REFLECT101;
+//     the last C % 8 columns of a row are its scalar tail, acc = acc + src * tap without fusion (both radar
+//     widths, 3360 and 3768, are multiples of 8).  Established against cv2 4.13 (AVX2 build) in
+//     tests/test_oracle_frontend.py::test_cen2018_filter_rule_and_run_centres; the oracle runs the real cv2;
+//   * the per-pixel response (:97-101) is float arithmetic without contraction (this library is built with
+//     --fmad=false); pow(float, 2) promotes to double and squares exactly; exp() is evaluated in double and
+//     rounded to float.  exp is the one libm call on the per-pixel path: CUDA's and glibc's double exp are
+//     both within 1 ulp but not bit-identical, so a last-bit difference survives the rounding to float with
+//     probability ~2^-28 per pixel and then matters only if y lies within one float ulp of the threshold.
+//   * peak centres (:102-112): runs of consecutive columns with y > thres, closed by a column that fails the
+//     test or by the end of the row, emit their middle element run[len / 2], azimuth-major (:118-128).
+#include <math.h>
+
+#include "frontend.cuh"
+
+namespace nrs {
+
+namespace {
+
+constexpr int ROWS_PB = 8;       // azimuths per CTA in the bias / noise kernel
+constexpr int TILE = 512;        // columns staged per step
+
+// :49-59 + :77-91.  q = f - mean(row), sigma_q(row); both sums sequential in column order.
+__global__ void __launch_bounds__(256)
+fe18_bias_sigma_kernel(const float *__restrict__ fft, int R, int C, float *__restrict__ q,
+                       float *__restrict__ sigma_q)
+{
+    __shared__ float tile[ROWS_PB][TILE + 1];
+    __shared__ float s_mean[ROWS_PB];
+    const int t = threadIdx.x, row0 = blockIdx.x * ROWS_PB;
+    const bool walker = t < ROWS_PB && row0 + t < R;
+    float acc = 0.f;
+    for (int c0 = 0; c0 < C; c0 += TILE) {
+        for (int idx = t; idx < ROWS_PB * TILE; idx += 256) {
+            const int r = idx / TILE, c = idx - r * TILE;
+            tile[r][c] = (row0 + r < R && c0 + c < C) ? fft[(size_t)(row0 + r) * C + c0 + c] : 0.f;
+        }
+        __syncthreads();
+        if (walker) {
+            const int n = min(TILE, C - c0);
+            for (int c = 0; c < n; ++c) acc += tile[t][c];          // mean += fft_data.at<float>(i, j)
+        }
+        __syncthreads();
+    }
+    if (walker) s_mean[t] = acc / (float)C;                          // mean /= fft_data.cols
+    __syncthreads();
+    float sig = 0.f;
+    int nonzero = 0;
+    for (int c0 = 0; c0 < C; c0 += TILE) {
+        for (int idx = t; idx < ROWS_PB * TILE; idx += 256) {
+            const int r = idx / TILE, c = idx - r * TILE;
+            float v = 0.f;
+            if (row0 + r < R && c0 + c < C) {
+                v = fft[(size_t)(row0 + r) * C + c0 + c] - s_mean[r];
+                q[(size_t)(row0 + r) * C + c0 + c] = v;
+            }
+            tile[r][c] = v;
+        }
+        __syncthreads();
+        if (walker) {
+            const int n = min(TILE, C - c0);
+            for (int c = 0; c < n; ++c) {
+                const float v = tile[t][c];
+                if (v < 0.f) { sig += 2 * (v * v); ++nonzero; }      // :83-84
+            }
+        }
+        __syncthreads();
+    }
+    if (walker) sigma_q[row0 + t] = nonzero ? sqrtf(sig / (float)nonzero) : 0.034f;   // :87-90
+}
+
+__device__ __forceinline__ int reflect101(int j, int C)
+{
+    if (C == 1) return 0;
+    while (j < 0 || j >= C) j = (j < 0) ? -j : 2 * C - 2 - j;
+    return j;
+}
+
+// :74 cv::filter2D(q, p, -1, filter, Point(-1,-1), 0, BORDER_REFLECT101): forward FMA chain per pixel
+constexpr int FILT_THREADS = 256;
+constexpr int FILT_MAX = 255;    // taps (3 * sigma_gauss, odd)
+__global__ void __launch_bounds__(FILT_THREADS)
+fe18_filter_kernel(const float *__restrict__ q, int R, int C, const float *__restrict__ taps, int fsize,
+                   float *__restrict__ p)
+{
+    __shared__ float row[FILT_THREADS + FILT_MAX];
+    __shared__ float kf[FILT_MAX];
+    const int i = blockIdx.y, j0 = blockIdx.x * FILT_THREADS, t = threadIdx.x;
+    const int anchor = fsize / 2;
+    for (int k = t; k < fsize; k += FILT_THREADS) kf[k] = taps[k];
+    const float *qr = q + (size_t)i * C;
+    for (int e = t; e < FILT_THREADS + fsize - 1; e += FILT_THREADS) row[e] = qr[reflect101(j0 + e - anchor, C)];
+    __syncthreads();
+    const int j = j0 + t;
+    if (j >= C) return;
+    float acc = 0.f;
+    if (j < (C & ~7)) {
+        for (int k = 0; k < fsize; ++k) acc = fmaf(row[t + k], kf[k], acc);      // OpenCV's 8-wide vector body
+    } else {
+        for (int k = 0; k < fsize; ++k) acc = acc + row[t + k] * kf[k];          // its scalar tail: multiply, then add
+    }
+    p[(size_t)i * C + j] = acc;
+}
+
+// :95-103 the per-pixel response and its threshold test (flag = y > zq * sigma_q[i]); y optional (tests)
+__global__ void __launch_bounds__(256)
+fe18_flags_kernel(const float *__restrict__ q, const float *__restrict__ p, const float *__restrict__ sigma_q,
+                  int R, int C, float zq, int min_range, unsigned char *__restrict__ flags, float *__restrict__ y_out)
+{
+    const int i = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= C) return;
+    const size_t e = (size_t)i * C + j;
+    unsigned char f = 0;
+    if (j >= min_range) {
+        const float sg = sigma_q[i];
+        const float thres = zq * sg;
+        const float qv = q[e], pv = p[e];
+        const double a = (double)((qv - pv) / sg), b2 = (double)(pv / sg);
+        const float nqp = (float)exp(-0.5 * (a * a));
+        const float npp = (float)exp(-0.5 * (b2 * b2));
+        const float b = nqp - npp;
+        const float y = qv * (1 - nqp) + pv * b;
+        if (y_out) y_out[e] = y;
+        f = y > thres;
+    } else if (y_out) {
+        y_out[e] = 0.f;
+    }
+    flags[e] = f;
+}
+
+// :102-112 one CTA per azimuth: a run starts at a flagged column whose left neighbour (from min_range on) is
+// not flagged; it emits column start + len / 2.  Emission stays ordered through per-warp ballots.
+template <bool EMIT>
+__global__ void __launch_bounds__(256)
+fe18_runs_kernel(const unsigned char *__restrict__ flags, int R, int C, int min_range, int *__restrict__ rowcount,
+                 int *__restrict__ polar, int cap)
+{
+    __shared__ int wsum[8];
+    __shared__ int running;
+    const int i = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned char *fr = flags + (size_t)i * C;
+    if (threadIdx.x == 0) running = EMIT ? rowcount[i] : 0;
+    __syncthreads();
+    for (int j0 = min_range; j0 < C; j0 += 256) {
+        const int j = j0 + threadIdx.x;
+        bool emit = false;
+        int centre = 0;
+        if (j < C && fr[j] && (j == min_range || !fr[j - 1])) {
+            int end = j;
+            while (end + 1 < C && fr[end + 1]) ++end;
+            centre = j + (end - j + 1) / 2;                 // peak_points[peak_points.size() / 2]
+            emit = true;
+        }
+        const unsigned int mask = __ballot_sync(0xffffffffu, emit);
+        if (lane == 0) wsum[warp] = __popc(mask);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const int c = wsum[w]; if (w < warp) before += c; total += c; }
+        const int base = running;
+        if (EMIT && emit) {
+            const int pos = base + before + __popc(mask & ((1u << lane) - 1u));
+            if (pos < cap) { polar[2 * pos] = i; polar[2 * pos + 1] = centre; }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) running = base + total;
+        __syncthreads();
+    }
+    if (!EMIT && threadIdx.x == 0) rowcount[i] = running;
+}
+
+}  // namespace
+
+// exclusive scan of the per-azimuth counts, total -> cnt->K0 (defined in frontend_cen2019.cu)
+int fe_launch_rowscan(cudaStream_t st, int *rowcount, int R, FrameCounts *cnt, int cap);
+
+// host libm taps, the reference's expression (:62-73); returns the number of taps
+int fe_cen2018_taps_host(int sigma_gauss, float *taps)
+{
+    const int fsize = sigma_gauss * 3, mu = fsize / 2;
+    const float sig_sqr = (float)(sigma_gauss * sigma_gauss);
+    float s = 0;
+    for (int i = 0; i < fsize; ++i) {
+        taps[i] = (float)exp(-0.5 * (i - mu) * (i - mu) / sig_sqr);
+        s += taps[i];
+    }
+    // filter /= s: cv::Mat::operator/=(double) is convertTo(-1, 1. / s), i.e. a multiplication by (float)(1 / s)
+    const float inv = (float)(1.0 / (double)s);
+    for (int i = 0; i < fsize; ++i) taps[i] = taps[i] * inv;
+    return fsize;
+}
+
+// d_fft (S.d_fft) -> d_polar + cnt->K0.  Scratch reuse: q in S.d_h, p in d_keys[0], flags in d_claim (bytes),
+// y (optional, tests) in d_keys[1], sigma_q + taps in d_partial's neighbour d_incr.
+int fe_cen2018_device(nrs_ctx *ctx, FrontendState &S, int R, int C, float zq, int sigma_gauss, int min_range,
+                      int *d_polar, bool reset_counts, bool keep_y)
+{
+    cudaStream_t st = ctx->stream;
+    FrameCounts *cnt = S.d_counts;
+    if (reset_counts) NRS_CUDA(cudaMemsetAsync(cnt, 0, sizeof(FrameCounts), st));
+    float taps[FILT_MAX];
+    if (sigma_gauss < 1 || sigma_gauss * 3 > FILT_MAX || sigma_gauss % 2 != 1) {
+        set_error("cen2018: sigma_gauss must be odd and 3 * sigma_gauss <= %d (features.cpp:63 asserts odd)", FILT_MAX);
+        return NRS_EINVAL;
+    }
+    const int fsize = fe_cen2018_taps_host(sigma_gauss, taps);
+    float *d_q = S.d_h, *d_p = S.d_keys[0], *d_y = keep_y ? S.d_keys[1] : nullptr;
+    unsigned char *d_flags = reinterpret_cast<unsigned char *>(S.d_claim);
+    float *d_sigma = reinterpret_cast<float *>(S.d_incr);
+    float *d_taps = d_sigma + FE_MAX_AZ;
+    NRS_CUDA(cudaMemcpyAsync(d_taps, taps, fsize * sizeof(float), cudaMemcpyHostToDevice, st));
+    fe18_bias_sigma_kernel<<<(R + ROWS_PB - 1) / ROWS_PB, 256, 0, st>>>(S.d_fft, R, C, d_q, d_sigma);
+    NRS_LAUNCHED();
+    dim3 gf((C + FILT_THREADS - 1) / FILT_THREADS, R);
+    fe18_filter_kernel<<<gf, FILT_THREADS, 0, st>>>(d_q, R, C, d_taps, fsize, d_p);
+    NRS_LAUNCHED();
+    dim3 gp((C + 255) / 256, R);
+    fe18_flags_kernel<<<gp, 256, 0, st>>>(d_q, d_p, d_sigma, R, C, zq, min_range, d_flags, d_y);
+    NRS_LAUNCHED();
+    fe18_runs_kernel<false><<<R, 256, 0, st>>>(d_flags, R, C, min_range, S.d_rowcount, nullptr, 0);
+    NRS_LAUNCHED();
+    int rc = fe_launch_rowscan(st, S.d_rowcount, R, cnt, FE_KP_CAP);
+    if (rc) return rc;
+    fe18_runs_kernel<true><<<R, 256, 0, st>>>(d_flags, R, C, min_range, S.d_rowcount, d_polar, FE_KP_CAP);
+    NRS_LAUNCHED();
+    return NRS_OK;
+}
+
+}  // namespace nrs

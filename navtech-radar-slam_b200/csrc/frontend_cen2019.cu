@@ -477,6 +477,13 @@ fe_bev_kernel(const double *__restrict__ pts_xy, const long long *__restrict__ t
 // ------------------------------------------------------------------------------------------------
 static int stats_blocks(const nrs_ctx *ctx) { return ctx->sm_count * 8; }
 
+int fe_launch_rowscan(cudaStream_t st, int *rowcount, int R, FrameCounts *cnt, int cap)
+{
+    fe_rowscan_kernel<<<1, 1024, 0, st>>>(rowcount, R, cnt, cap);
+    NRS_LAUNCHED();
+    return NRS_OK;
+}
+
 int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_points, int min_range,
                       int *d_polar, bool reset_counts)
 {

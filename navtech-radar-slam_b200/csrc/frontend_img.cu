@@ -32,6 +32,8 @@ namespace nrs {
 
 int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_points, int min_range, int *d_polar,
                       bool reset_counts = true);
+int fe_cen2018_device(nrs_ctx *ctx, FrontendState &S, int R, int C, float zq, int sigma_gauss, int min_range,
+                      int *d_polar, bool reset_counts, bool keep_y);
 int fe_points_voxel_bev_device(nrs_ctx *ctx, FrontendState &S, nrs_frame *f);
 int fe_decode_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int pitch);
 size_t fe_cub_bytes(size_t N);
@@ -451,6 +453,41 @@ int nrs_extract_default_params(const char *dataset, nrs_extract_params *p)
     p->cart_resolution = 0.2592f; p->cart_pixel_width = 964; p->min_range = 58;
     p->max_points = 10000; p->patch_size = 21; p->use_voxelization = 1; p->interpolate_crossover = 1;
     p->voxel_size = 0.6; p->nndr = 0.8f;
+    p->keypoint_extraction = 0; p->zq = 3.0f; p->sigma_gauss = 17;     // radar_loader.hpp:284-285
+    return NRS_OK;
+}
+
+int nrs_cen2018(nrs_ctx *ctx, const float *fft, int R, int C, float zq, int sigma_gauss, int min_range,
+                double *targets, int Kcap, int *K, float *y_out)
+{
+    NRS_CHECK_ARG(ctx && fft && K && R >= 2 && R <= FE_MAX_AZ && C >= 3 && min_range >= 0 &&
+                  (targets || Kcap == 0), "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    NRS_CUDA(cudaSetDevice(ctx->device));
+    nrs_extract_params p;
+    nrs_extract_default_params("mulran", &p);
+    p.range_bins = C; p.min_range = min_range;
+    FrontendState *S = nullptr;
+    int rc = frontend_state(ctx, &p, R, C, C + 11, &S);
+    if (rc) return rc;
+    rc = ctx->scratch[4].reserve(2 * FE_KP_CAP * sizeof(int));
+    if (rc) return rc;
+    int *d_polar = ctx->scratch[4].as<int>();
+    NRS_CUDA(cudaMemcpyAsync(S->d_fft, fft, (size_t)R * C * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    rc = fe_cen2018_device(ctx, *S, R, C, zq, sigma_gauss, min_range, d_polar, true, y_out != nullptr);
+    if (rc) return rc;
+    NRS_CUDA(cudaMemcpyAsync(S->h_counts, S->d_counts, sizeof(FrameCounts), cudaMemcpyDeviceToHost, ctx->stream));
+    if (y_out) NRS_CUDA(cudaMemcpyAsync(y_out, S->d_keys[1], (size_t)R * C * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    NRS_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int k = S->h_counts->K0;
+    *K = k;
+    if (S->h_counts->overflow) { set_error("nrs_cen2018: more than %d keypoints", FE_KP_CAP); return NRS_ECAPACITY; }
+    if (k > Kcap) { set_error("nrs_cen2018: K = %d exceeds Kcap = %d", k, Kcap); return NRS_ECAPACITY; }
+    std::vector<int> hp(2 * (size_t)std::max(k, 1));
+    if (k) NRS_CUDA(cudaMemcpy(hp.data(), d_polar, 2 * (size_t)k * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < k; ++c) {
+        targets[3 * c] = hp[2 * c]; targets[3 * c + 1] = hp[2 * c + 1]; targets[3 * c + 2] = 1.0;
+    }
     return NRS_OK;
 }
 
@@ -496,6 +533,7 @@ int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw, int R, int row_pitch, co
     NRS_CHECK_ARG(R >= 2 && R <= FE_MAX_AZ, "number of azimuths out of range");
     NRS_CHECK_ARG(row_pitch >= C + 11, "row pitch smaller than 11 + range_bins");
     NRS_CHECK_ARG(p->cart_pixel_width >= 64 && p->patch_size >= 3 && p->patch_size <= 63 && p->max_points <= FE_KP_CAP, "bad parameters");
+    NRS_CHECK_ARG(p->keypoint_extraction == 0 || p->keypoint_extraction == 1, "keypoint_extraction must be 0 (cen2019) or 1 (cen2018)");
     std::lock_guard<std::mutex> lk(ctx->mu);
     NRS_CUDA(cudaSetDevice(ctx->device));
     FrontendState *S = nullptr;
@@ -565,9 +603,10 @@ int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw, int R, int row_pitch, co
     NRS_LAUNCHED();
     NRS_CUDA(cudaEventRecord(S->ev_join, si));
     // keypoint branch on the context stream
-    if ((rc = fe_cen2019_device(ctx, *S, R, C, p->max_points, p->min_range, f->d_polar, false))) {
-        cudaStreamSynchronize(si); frame_release_locked(f); return rc;
-    }
+    rc = (p->keypoint_extraction == 1)
+             ? fe_cen2018_device(ctx, *S, R, C, p->zq, p->sigma_gauss, p->min_range, f->d_polar, false, false)
+             : fe_cen2019_device(ctx, *S, R, C, p->max_points, p->min_range, f->d_polar, false);
+    if (rc) { cudaStreamSynchronize(si); frame_release_locked(f); return rc; }
     if ((rc = fe_points_voxel_bev_device(ctx, *S, f))) { cudaStreamSynchronize(si); frame_release_locked(f); return rc; }
     NRS_CUDA(cudaStreamWaitEvent(st, S->ev_join, 0));           // join
     fe_brief_kernel<<<(FE_KP_CAP * 32 + 255) / 256, 256, 0, st>>>(S->d_blur, W, f->d_kp_orb, S->d_counts, S->d_pattern, f->d_desc);

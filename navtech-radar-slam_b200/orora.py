@@ -159,6 +159,21 @@ def cen2019features(ctx, fft_data, max_points, min_range):
     return out[: 3 * K.value].reshape(-1, 3).T.copy()
 
 
+def cen2018features(ctx, fft_data, zq, sigma_gauss, min_range, return_response=False):
+    """features.hpp:27 cen2018features(fft, zq, sigma_gauss, min_range, targets) -> targets (3, K)
+    (and the per-pixel response y, R x C, when asked -- a stage output for the parity tests)."""
+    fft = np.ascontiguousarray(fft_data, dtype=np.float32)
+    R, Cc = fft.shape
+    cap = 16384
+    out = np.zeros(3 * cap, dtype=np.float64)
+    y = np.zeros((R, Cc), dtype=np.float32) if return_response else None
+    K = C.c_int()
+    check(lib().nrs_cen2018(ctx.handle, ptr(fft), R, Cc, float(zq), int(sigma_gauss), int(min_range), ptr(out), cap,
+                            C.byref(K), ptr(y) if y is not None else None))
+    t = out[: 3 * K.value].reshape(-1, 3).T.copy()
+    return (t, y) if return_response else t
+
+
 class Frame:
     """nrs_frame: the device-resident products of one extractFeature call."""
 
@@ -218,11 +233,11 @@ class RadarLoader:
             raise ValueError("Note implemented!")                                  # radar_loader.hpp:62
         if keypoint_extraction not in ("cen2018", "cen2019"):
             raise ValueError("Keypoint extraction method seems to be wrong!")      # :64-66
-        if keypoint_extraction != "cen2019":
-            raise ValueError("cen2018 is listed as 'next' in SURVEY.md 8(f); this build implements cen2019")
         self.ctx = ctx if ctx is not None else _lib.Context(0)
         self.dataset_ = dataset
+        self.keypoint_extraction_ = keypoint_extraction
         self.params = extract_params(dataset)
+        self.params.keypoint_extraction = 1 if keypoint_extraction == "cen2018" else 0      # radar_loader.hpp:95-99
         self.params.voxel_size = voxel_size
         self.params.use_voxelization = int(bool(use_voxelization))
         self.time_unit_denominator_ = 1000000.0 if dataset == "oxford" else 1000000000.0

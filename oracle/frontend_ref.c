@@ -157,3 +157,85 @@ int fe_hamming256(const unsigned char *a, const unsigned char *b)
     for (int i = 0; i < 32; ++i) d += __builtin_popcount(a[i] ^ b[i]);
     return d;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * cen2018features (outlier-robust-radar-odometry/src/features.cpp:44-131), the reference's own
+ * loops; the 1 x 3*sigma Gaussian cv::filter2D in the middle (:74) is run by the real cv2 from
+ * oracle/frontend_ref.py.  All arithmetic is float unless the C++ promotes it (noted).
+ * --------------------------------------------------------------------------------------------- */
+
+/* :49-59 per-azimuth bias: sequential float sum, mean /= cols, q = f - mean */
+void fe_cen2018_bias(const float *fft, int rows, int cols, float *q)
+{
+    for (int i = 0; i < rows; ++i) {
+        float mean = 0;
+        for (int j = 0; j < cols; ++j) mean += fft[(size_t)i * cols + j];
+        mean /= cols;
+        for (int j = 0; j < cols; ++j) q[(size_t)i * cols + j] = fft[(size_t)i * cols + j] - mean;
+    }
+}
+
+/* :62-72 the filter taps: exp() of a double argument stored to float, float running sum.
+ * (filter /= s is a cv::Mat operation: done by cv2 in the Python driver.) */
+float fe_cen2018_taps(int sigma_gauss, float *taps)
+{
+    const int fsize = sigma_gauss * 3, mu = fsize / 2;
+    const float sig_sqr = sigma_gauss * sigma_gauss;
+    float s = 0;
+    for (int i = 0; i < fsize; ++i) {
+        taps[i] = exp(-0.5 * (i - mu) * (i - mu) / sig_sqr);
+        s += taps[i];
+    }
+    return s;
+}
+
+/* :77-91 noise level per azimuth from the negative half of q */
+void fe_cen2018_sigma(const float *q, int rows, int cols, float *sigma_q)
+{
+    for (int i = 0; i < rows; ++i) {
+        int nonzero = 0;
+        float acc = 0;
+        for (int j = 0; j < cols; ++j) {
+            const float n = q[(size_t)i * cols + j];
+            if (n < 0) { acc += 2 * (n * n); nonzero++; }
+        }
+        if (nonzero) acc = sqrt(acc / nonzero);
+        else acc = 0.034;
+        sigma_q[i] = acc;
+    }
+}
+
+/* :94-113 peak centres per azimuth; y is also written out (nullable) for stage-wise comparison.
+ * Returns the number of targets; out_a/out_r hold (azimuth, range bin) azimuth-major like :118-128. */
+int fe_cen2018_scan(const float *q, const float *p, const float *sigma_q, int rows, int cols, float zq,
+                    int min_range, float *y_out, int *out_a, int *out_r, int cap)
+{
+    int k = 0;
+    int *peak = (int *)malloc(sizeof(int) * (size_t)(cols > 0 ? cols : 1));
+    for (int i = 0; i < rows; ++i) {
+        int np = 0;
+        const float thres = zq * sigma_q[i];
+        for (int j = min_range; j < cols; ++j) {
+            const float qv = q[(size_t)i * cols + j], pv = p[(size_t)i * cols + j];
+            /* pow(float, int) promotes to double in C++11: the float quotient is squared exactly */
+            const float nqp = exp(-0.5 * pow((double)((qv - pv) / sigma_q[i]), 2));
+            const float npp = exp(-0.5 * pow((double)(pv / sigma_q[i]), 2));
+            const float b = nqp - npp;
+            const float y = qv * (1 - nqp) + pv * b;
+            if (y_out) y_out[(size_t)i * cols + j] = y;
+            if (y > thres) {
+                peak[np++] = j;
+            } else if (np > 0) {
+                if (k < cap) { out_a[k] = i; out_r[k] = peak[np / 2]; }
+                ++k;
+                np = 0;
+            }
+        }
+        if (np > 0) {
+            if (k < cap) { out_a[k] = i; out_r[k] = peak[np / 2]; }
+            ++k;
+        }
+    }
+    free(peak);
+    return k;
+}

@@ -3,6 +3,7 @@
 Follows /root/reference/outlier-robust-radar-odometry/
     src/radar_utils.cpp:104-129   load_radar
     src/features.cpp:197-299      cen2019features
+    src/features.cpp:44-131       cen2018features
     src/radar_utils.cpp:252-316   polar_to_cartesian_radar_img
     src/radar_utils.cpp:329-341   polar_to_cartesian_points
     include/radar_loader.hpp:207-222  voxelize  (pcl::VoxelGrid<PointXYZ>, recalled semantics)
@@ -66,6 +67,14 @@ def _lib():
         L.fe_cen2019_mark.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp, vp]
         L.fe_cen2019_scan.restype = i32
         L.fe_cen2019_scan.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32]
+        L.fe_cen2018_bias.restype = None
+        L.fe_cen2018_bias.argtypes = [vp, i32, i32, vp]
+        L.fe_cen2018_taps.restype = f32
+        L.fe_cen2018_taps.argtypes = [i32, vp]
+        L.fe_cen2018_sigma.restype = None
+        L.fe_cen2018_sigma.argtypes = [vp, i32, i32, vp]
+        L.fe_cen2018_scan.restype = i32
+        L.fe_cen2018_scan.argtypes = [vp, vp, vp, i32, i32, f32, i32, vp, vp, vp, i32]
         L._fe_declared = True
     return L
 
@@ -131,6 +140,38 @@ def cen2019_stages(fft, max_points=10000, min_range=58):
 
 def cen2019features(fft, max_points=10000, min_range=58):
     return cen2019_stages(fft, max_points, min_range)["targets"]
+
+
+def cen2018_stages(fft, zq=3.0, sigma_gauss=17, min_range=58):
+    """features.cpp:44-131 (what run_orora.launch selects): the reference's loops in C, its one OpenCV call --
+    filter2D with the 1 x 3*sigma Gaussian, BORDER_REFLECT101 -- by the real cv2."""
+    fft = np.ascontiguousarray(fft, dtype=np.float32)
+    rows, cols = fft.shape
+    L = _lib()
+    q = np.empty_like(fft)
+    L.fe_cen2018_bias(_p(fft), rows, cols, _p(q))
+    taps = np.zeros((1, 3 * sigma_gauss), dtype=np.float32)
+    s = L.fe_cen2018_taps(sigma_gauss, _p(taps))
+    filt = taps * np.float32(1.0 / float(s))                # filter /= s (:73): Mat /= double == convertTo(-1, 1./s)
+    p = cv2.filter2D(q, -1, filt, anchor=(-1, -1), delta=0, borderType=cv2.BORDER_REFLECT101)
+    sigma_q = np.zeros(rows, dtype=np.float32)
+    L.fe_cen2018_sigma(_p(q), rows, cols, _p(sigma_q))
+    cap = rows * (cols // 2 + 1)
+    oa = np.zeros(cap, dtype=np.int32)
+    orr = np.zeros(cap, dtype=np.int32)
+    y = np.zeros_like(fft)
+    p = np.ascontiguousarray(p)
+    with np.errstate(all="ignore"):
+        k = L.fe_cen2018_scan(_p(q), _p(p), _p(sigma_q), rows, cols, np.float32(zq), min_range, _p(y), _p(oa), _p(orr), cap)
+    assert k <= cap
+    targets = np.ones((3, k), dtype=np.float64)
+    targets[0] = oa[:k]
+    targets[1] = orr[:k]
+    return {"q": q, "taps": filt.reshape(-1), "p": p, "sigma_q": sigma_q, "y": y, "targets": targets}
+
+
+def cen2018features(fft, zq=3.0, sigma_gauss=17, min_range=58):
+    return cen2018_stages(fft, zq, sigma_gauss, min_range)["targets"]
 
 
 # ---- radar_utils.cpp:252-316 -------------------------------------------------------------------------
@@ -268,10 +309,13 @@ def match_features(desc_prev, desc_curr, nndr=np.float32(0.8)):
 
 
 # ---- radar_loader.hpp:74-141 ---------------------------------------------------------------------------------
-def extract_feature(raw, dataset="mulran", voxel_size=0.6, use_voxelization=True):
+def extract_feature(raw, dataset="mulran", voxel_size=0.6, use_voxelization=True, keypoint_extraction="cen2019"):
     P = DatasetParams(dataset)
     times, azimuths, valid, fft = load_radar(raw, P.navtech_version)
-    st = cen2019_stages(fft, P.max_points, P.min_range)
+    if keypoint_extraction == "cen2018":                  # radar_loader.hpp:95-99, zq_ / sigma_gauss_ :284-285
+        st = cen2018_stages(fft, 3.0, 17, P.min_range)
+    else:
+        st = cen2019_stages(fft, P.max_points, P.min_range)
     polar = st["targets"]
     img = polar_to_cartesian_radar_img(azimuths, fft, P.radar_resolution, P.cart_resolution,
                                        P.cart_pixel_width, True, P.navtech_version)

@@ -113,3 +113,67 @@ def test_matcher_ties_and_edges(nrs, ctx, F, synth, world):
         nrs.orora.RadarLoader("kitti", "cen2019")
     with pytest.raises(ValueError):
         nrs.orora.RadarLoader("mulran", "orb")
+
+
+def test_cen2018_operator_stagewise(nrs, ctx, F, synth, world):
+    """cen2018features (features.cpp:44-131, the extractor run_orora.launch selects) as a stand-alone operator:
+    the per-pixel response y and the keypoint list against the oracle (reference loops in C with glibc, the
+    Gaussian filter2D by the real cv2).  y is compared bit for bit; exp() is the one libm call whose CUDA and
+    glibc implementations may differ in the last bit of a double, so up to 4 pixels per frame may differ by one
+    float ulp -- and the keypoints must then still be identical unless such a pixel sits on the threshold."""
+    rng = np.random.default_rng(5)
+    frames = []
+    raw = synth.radar_frame(world, (0, 0, 0), seed=1234, dataset="mulran")
+    frames.append((F.load_radar(raw, 0)[3], 3.0, 17, 58))
+    raw = synth.radar_frame(world, (1.0, 0.5, 0.1), seed=99, dataset="oxford")
+    frames.append((F.load_radar(raw, 1)[3], 3.0, 17, 58))
+    f = (rng.integers(0, 24, (37, 701)) / 255.0).astype(np.float32)
+    hot = rng.random(f.shape) < 0.03
+    f[hot] = (rng.integers(120, 256, int(hot.sum())) / 255.0).astype(np.float32)
+    f[:, :42] = 0
+    frames.append((f, 2.0, 5, 10))                                   # odd sizes, short filter, ragged tiles, scalar filter tail
+    f = np.zeros((9, 300), dtype=np.float32)
+    f[3, 100:160] = 1.0
+    f[4, 290:] = 0.7                                                 # run open at the last column
+    f[5] = 0.25                                                      # constant row: q == 0, sigma_q = 0.034
+    frames.append((f, 1.0, 17, 58))
+    n_total = 0
+    for fft, zq, sg, mr in frames:
+        st = F.cen2018_stages(fft, zq, sg, mr)
+        got, y = nrs.orora.cen2018features(ctx, fft, zq, sg, mr, return_response=True)
+        ydiff = y.view(np.uint32)[:, mr:] != st["y"].view(np.uint32)[:, mr:]
+        assert ydiff.sum() <= 4, int(ydiff.sum())
+        if ydiff.any():
+            assert np.max(np.abs(y[:, mr:].astype(np.float64) - st["y"][:, mr:])) < 1e-6
+        want = st["targets"]
+        assert got.shape == want.shape and np.array_equal(got, want)
+        n_total += want.shape[1]
+    assert n_total > 3000
+
+
+@pytest.mark.parametrize("dataset", ["mulran"])
+def test_extract_with_cen2018_parity(nrs, ctx, oracle, synth, F, world, dataset):
+    """RadarLoader("...", "cen2018"): the whole extractFeature chain with the cen2018 keypoints, then match and
+    solve, against the oracle chain."""
+    loader = nrs.orora.RadarLoader(dataset, "cen2018", 0.6, True, False, ctx=ctx)
+    res = []
+    for pose, seed in (((0, 0, 0), 1234), ((2.5, 0.1, np.deg2rad(1.0)), 1235)):
+        raw = synth.radar_frame(world, pose, seed=seed, dataset=dataset)
+        o = F.extract_feature(raw, dataset, keypoint_extraction="cen2018")
+        g = loader.extractFeatureFromRows(raw, 77)
+        assert np.array_equal(g.feat_in_polar_, o["polar"])
+        assert np.array_equal(g.img_, o["img"])
+        assert np.array_equal(g.feat_in_cart_, o["feat_in_cart"])
+        assert np.array_equal(g.kp_, o["kp"]) and np.array_equal(g.t_, o["t"])
+        assert np.array_equal(g.desc_, o["desc"])
+        res.append((o, g))
+    (o0, g0), (o1, g1) = res
+    pm_o, cm_o, q_o, t_o = F.match_frames(o0, o1)
+    pm, cm = loader.matchFeatures(g0, g1)
+    assert np.array_equal(pm.query_idx, q_o) and np.array_equal(pm.train_idx, t_o)
+    est = nrs.orora.ORORA(dataset, "rot", True, False, True, 700, 0.049, 0.1, np.deg2rad(9.0), ctx=ctx)
+    params = nrs.orora.setParams(0.75, 1.0, False, 100, 1.4, 1e-6)
+    T = est.calcTransform(params, 0.25, pm, cm)
+    ro, _ = oracle.orora_calc_transform(pm_o, cm_o, 0.0)
+    dth = np.arctan2(T[1, 0], T[0, 0]) - np.arctan2(ro["T"][1, 0], ro["T"][0, 0])
+    assert np.hypot(T[0, 3] - ro["T"][0, 3], T[1, 3] - ro["T"][1, 3]) <= 1e-4 and abs(dth) <= 1e-5

@@ -193,3 +193,48 @@ def test_chain_recovers_planted_motion(F, oracle, synth):
     assert r["valid"] and r["info"].M > 50
     assert abs(np.arctan2(r["T"][1, 0], r["T"][0, 0]) - np.deg2rad(1.0)) < 5e-3
     assert abs(r["T"][0, 3] - 2.5) < 0.3 and abs(r["T"][1, 3] - 0.1) < 0.3
+
+
+def test_cen2018_filter_rule_and_run_centres(F):
+    """cen2018features (features.cpp:44-131): (1) the CUDA path's restatement of cv::filter2D with the
+    1 x 51 Gaussian -- forward FMA chain from 0, BORDER_REFLECT101 -- equals the real cv2 bit for bit on
+    whole rows including both borders; (2) the run-centre rule (middle element, closing column or end of row)
+    against a direct Python transcription of :102-112."""
+    rng = np.random.default_rng(11)
+    n_total = 0
+    for trial, (rows, cols) in enumerate([(6, 3360), (5, 700), (3, 130), (4, 64)]):
+        fft = (rng.integers(0, 24, (rows, cols)) / 255.0).astype(np.float32)           # receiver noise ...
+        hot = rng.random((rows, cols)) < 0.02
+        fft[hot] = (rng.integers(120, 256, int(hot.sum())) / 255.0).astype(np.float32)   # ... and sparse strong returns
+        fft[:, : min(42, cols // 3)] = 0
+        if trial == 1:
+            fft[2, 200:260] = 1.0                       # a long plateau: even / odd run lengths
+            fft[3, cols - 7:] = 1.0                     # a run still open at the last column is emitted (:111-112)
+        st = F.cen2018_stages(fft, 3.0, 17, 58 if cols > 200 else 5)
+        q, taps = st["q"], st["taps"]
+        pad = np.pad(q, ((0, 0), (25, 25)), mode="reflect")
+        acc = np.zeros_like(q)
+        tail = np.zeros_like(q)
+        for k in range(51):
+            x = pad[:, k:k + cols]
+            acc = (acc.astype(np.float64) + x.astype(np.float64) * np.float64(taps[k])).astype(np.float32)   # fma: one rounding
+            tail = (tail + (x * taps[k]).astype(np.float32)).astype(np.float32)                              # multiply, then add
+        body = cols & ~7                                # OpenCV's 8-wide vector body; the rest is its scalar tail
+        acc[:, body:] = tail[:, body:]
+        assert np.array_equal(acc.view(np.uint32), st["p"].view(np.uint32))
+        mr = 58 if cols > 200 else 5
+        exp = []
+        for i in range(rows):
+            thres = np.float32(3.0) * st["sigma_q"][i]
+            run = []
+            for j in range(mr, cols):
+                if st["y"][i, j] > thres:
+                    run.append(j)
+                elif run:
+                    exp.append((i, run[len(run) // 2])); run = []
+            if run:
+                exp.append((i, run[len(run) // 2]))
+        got = [(int(a), int(r)) for a, r in zip(st["targets"][0], st["targets"][1])]
+        assert got == exp and np.all(st["targets"][2] == 1)
+        n_total += len(exp)
+    assert n_total > 20
