@@ -408,6 +408,34 @@ def orora_block(pkg, ctx, n_pairs=40, cpu_pairs=3):
         L.nrs_frame_destroy(prev)
         prev = cur
     L.nrs_frame_destroy(prev)
+    # the same chain with the extractor the shipped launch file selects (run_orora.launch:11): cen2018
+    ep18 = orr.extract_params("mulran")
+    ep18.keypoint_extraction = 1
+    ep_saved = ep
+
+    def extract18(k):
+        h = C.c_void_p()
+        pkg._lib.check(L.nrs_frame_extract(ctx.handle, raws[k % 8].ctypes.data_as(C.c_void_p), 400, raws[k % 8].shape[1],
+                                           C.byref(ep18), k, C.byref(h)))
+        return h
+
+    prev, vel = extract18(0), 0.0
+    t18 = None
+    for k in range(1, 4 + n_pairs // 2):
+        if k == 4:
+            ctx.sync(); t18 = time.perf_counter()
+        cur = extract18(k)
+        pkg._lib.check(L.nrs_match(ctx.handle, prev, cur, float(ep.nndr), cap, q.ctypes.data_as(C.c_void_p),
+                                   t.ctypes.data_as(C.c_void_p), pxy.ctypes.data_as(C.c_void_p),
+                                   cxy.ctypes.data_as(C.c_void_p), None, None, C.byref(n)))
+        pkg._lib.check(L.nrs_orora_solve(ctx.handle, pxy.ctypes.data_as(C.c_void_p), cxy.ctypes.data_as(C.c_void_p), n.value,
+                                         C.byref(sp), vel, T.ctypes.data_as(C.c_void_p), None, None, C.byref(info)))
+        L.nrs_frame_destroy(prev)
+        prev, vel = cur, T[12] / 0.25
+    ctx.sync()
+    dt18 = (time.perf_counter() - t18) / (n_pairs // 2)
+    n18, M18 = n.value, info.M
+    L.nrs_frame_destroy(prev)
     # pipelined throughput: frame k+1 is extracted on one context (stream) by one host thread while the pair
     # (k-1, k) is matched and solved on a second context by another -- same public C ABI, same per-pair chain
     # (the Doppler velocity still flows from solve to solve); latency per pair is unchanged
@@ -460,6 +488,8 @@ def orora_block(pkg, ctx, n_pairs=40, cpu_pairs=3):
             "e2e": "pinned host PNG rows in (1.35 MB H2D per frame), 4x4 pose out; value == e2e (the path starts on the host)",
             "h2d_bytes_per_pair": int(raws[0].nbytes), "d2h_bytes_per_pair": 128 + 40 * max(n_matches, 1),
             "stage_ms": {k: round(v, 3) for k, v in st.items()}, "matches": n_matches, "clique": M,
+            "cen2018": {"value": 1.0 / dt18, "unit": "pairs/s", "ms_per_pair": 1e3 * dt18, "matches": n18, "clique": M18,
+                        "what": "same chain with keypoint_extraction = cen2018 (the shipped launch's choice)"},
             "pipelined": {"value": 1.0 / dt_pipe, "unit": "pairs/s", "ms_per_pair": 1e3 * dt_pipe,
                           "how": "2 host threads, 2 contexts: extraction of frame k+1 overlaps match+solve of pair (k-1,k)"},
             "gpu_launches_per_pair": launches / n_pairs,
