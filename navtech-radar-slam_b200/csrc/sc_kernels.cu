@@ -13,14 +13,16 @@
 // With that, distances are bit-identical to the CPU restatement in oracle/sc_ref.c for
 // binary {0,c} descriptors (every partial sum is exact) and for general-valued ones.
 //
-// Kernel sc_search_kernel (K10): one warp per keyframe, persistent grid (one 16-warp CTA per SM,
-// ~205 KB of shared memory).  Each keyframe's 5536-byte f32 filter record (written at append time)
-// is staged by ONE 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) onto a per-warp mbarrier, two
-// records in flight per warp; the prepared query arrives the same way.  All three arg-mins of the
-// reference are filtered in f32 and certified in f64 from the canonical 9600-byte descriptor (see
-// the K10 block below); only keyframes the filter cannot rule out are ever read in f64.
-// Bound: HBM.  Algorithmic bytes per keyframe = 9600 (f64 20x60, the reference's MatrixXd);
-// per query = 9600*D + 9600 + 16; bytes actually streamed = 5536*D + survivors.
+// Kernel sc_search_kernel (K10), ONE launch per query: one warp per keyframe, persistent grid (one
+// 24-warp CTA per SM, ~160 KB of shared memory).  Each keyframe's 5536-byte f32 filter record
+// (written at append time) is staged by ONE 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) onto a
+// per-warp mbarrier and re-armed as soon as it has been consumed into registers; every CTA prepares
+// the query itself while its first records are in flight.  All three arg-mins of the reference are
+// filtered in f32 and certified in f64 from the canonical 9600-byte descriptor (see the K10 block
+// below); only keyframes the filter cannot rule out are ever read in f64.  For a sharded database
+// the last CTA also exchanges the per-rank records over peer memory (XchgView).
+// Bound: HBM by design; algorithmic bytes per keyframe = 9600 (f64 20x60, the reference's
+// MatrixXd), per query = 9600*D + 9600 + 16; bytes actually streamed = 5536*D + survivors.
 #include <stddef.h>
 #include <stdlib.h>
 #include <string.h>

@@ -9,14 +9,17 @@
 //                                N x 32-word bit adjacency matrix (replaces computeTIMs' 3 x N^2/2
 //                                f64 temporaries and Graph::addEdge's O(N^3) linear finds).
 //   K8  orora_order_kernel /     degree ordering, permuted adjacency, then an exact maximum-clique
-//       orora_permute_kernel /   search (greedy bound + bitset branch and bound with greedy
-//       orora_clique_kernel      colouring) by ONE warp: lane l owns word l of every vertex set, the
-//                                adjacency matrix sits in shared memory.  PMC (un-vendored in the
-//                                reference) is replaced by this exact solver.
-//   K9  orora_tail_kernel        one 1024-thread CTA: clique sort, chain TIMs + initial weights,
-//                                GNC-TLS rotation (warp-shuffle reduced weighted 2x2 correlation,
-//                                closed-form 2-D Kabsch), anisotropic COTE translation (bitonic
-//                                sort of the 2M interval endpoints + block scan + argmin).
+//       orora_permute_kernel /   search in one CTA of ceil(N/32) warps with the adjacency matrix in shared
+//       orora_clique_kernel      memory: greedy bound (one CTA barrier per step, REDUX-packed warp maxima,
+//                                finishes at once when the candidate set is a clique), Jacobi core pruning,
+//                                then maximum independent set on the sparse complement or, for sparse cores,
+//                                bitset branch and bound with greedy colouring on warp 0.  PMC (un-vendored
+//                                in the reference) is replaced by this exact solver.
+//   K9  orora_tail_kernel        launched with 1024 threads, keeps nextpow2(M) alive: clique sort, chain TIMs +
+//                                initial weights, GNC-TLS rotation (one warp-shuffle CTA reduction per
+//                                iteration, closed-form 2-D Kabsch), anisotropic COTE translation (rank
+//                                counting instead of a sorting network, running sums in sorted order like
+//                                the reference's loop, first-minimum argmin).
 //
 // All of it is latency-bound on <= 1024 correspondences (22 KB of input): it sits far below the
 // HBM roofline by construction and DESIGN.md reports it that way.  Built with --fmad=false so the

@@ -177,3 +177,16 @@ def test_extract_with_cen2018_parity(nrs, ctx, oracle, synth, F, world, dataset)
     ro, _ = oracle.orora_calc_transform(pm_o, cm_o, 0.0)
     dth = np.arctan2(T[1, 0], T[0, 0]) - np.arctan2(ro["T"][1, 0], ro["T"][0, 0])
     assert np.hypot(T[0, 3] - ro["T"][0, 3], T[1, 3] - ro["T"][1, 3]) <= 1e-4 and abs(dth) <= 1e-5
+
+
+def test_cen2018_against_committed_golden(nrs, ctx):
+    """The CUDA path against the fixtures generated in the build container (tests/golden/make_cen2018_golden.py):
+    keypoints exactly, the response within the same <= 4-pixels-one-ulp allowance as above."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cen2018_golden.npz"))
+    for tag in ("a", "b"):
+        zq, sg, mr = g[f"{tag}_par"]
+        got, y = nrs.orora.cen2018features(ctx, g[f"{tag}_fft"], float(zq), int(sg), int(mr), return_response=True)
+        diff = y.view(np.uint32)[:, int(mr):] != g[f"{tag}_y"].view(np.uint32)[:, int(mr):]
+        assert diff.sum() <= 4
+        assert np.array_equal(got, g[f"{tag}_targets"]) and got.shape[1] > 50

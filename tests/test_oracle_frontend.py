@@ -238,3 +238,15 @@ def test_cen2018_filter_rule_and_run_centres(F):
         assert got == exp and np.all(st["targets"][2] == 1)
         n_total += len(exp)
     assert n_total > 20
+
+
+def test_cen2018_oracle_reproduces_committed_golden(F):
+    """the oracle on this machine (its glibc, its cv2) against the committed fixture"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cen2018_golden.npz"))
+    for tag in ("a", "b"):
+        zq, sg, mr = g[f"{tag}_par"]
+        st = F.cen2018_stages(g[f"{tag}_fft"], float(zq), int(sg), int(mr))
+        assert np.array_equal(st["targets"], g[f"{tag}_targets"])
+        assert np.array_equal(st["sigma_q"], g[f"{tag}_sigma"])
+        assert (st["y"].view(np.uint32) != g[f"{tag}_y"].view(np.uint32)).sum() <= 4
