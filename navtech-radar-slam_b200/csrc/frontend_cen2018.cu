@@ -3,8 +3,8 @@
 //
 // Arithmetic contract (what makes the output identical to the reference's):
 //   * per-azimuth bias (:49-59) and noise level (:77-91) are SEQUENTIAL float sums in column order; they
-//     are kept sequential here (one thread per azimuth walks its row through shared-memory tiles that the
-//     whole CTA loads coalesced), because any other order rounds differently;
+//     are kept sequential here (one thread per azimuth walks its row, staged whole in shared memory by its
+//     CTA), because any other order rounds differently;
 //   * the Gaussian taps (:62-73) are computed on the host with the same libm exp() the reference links;
 //   * cv::filter2D with that 1 x 3*sigma kernel (:74) is OpenCV's direct filter engine: per output pixel one
 //     forward chain acc = fma(src[j + k - anchor], tap[k], acc) over k, starting from 0, BORDER_REFLECT101;
@@ -26,56 +26,63 @@ namespace nrs {
 
 namespace {
 
-constexpr int ROWS_PB = 8;       // azimuths per CTA in the bias / noise kernel
-constexpr int TILE = 512;        // columns staged per step
+constexpr int ROWS_PB = 3;       // azimuths per CTA in the bias / noise kernel (134 CTAs for 400 azimuths)
 
-// :49-59 + :77-91.  q = f - mean(row), sigma_q(row); both sums sequential in column order.
+// :49-59 + :77-91.  q = f - mean(row), sigma_q(row); both sums are sequential in column order, so the
+// floor is two dependent chains of C float adds per azimuth.  Each CTA stages its rows whole in shared
+// memory (one coalesced read of the frame), one thread per row walks it with 16-byte loads kept ahead of the
+// add chain, all threads form q in place and write it out, the walkers go over q once more.
 __global__ void __launch_bounds__(256)
-fe18_bias_sigma_kernel(const float *__restrict__ fft, int R, int C, float *__restrict__ q,
+fe18_bias_sigma_kernel(const float *__restrict__ fft, int R, int C, int stride, float *__restrict__ q,
                        float *__restrict__ sigma_q)
 {
-    __shared__ float tile[ROWS_PB][TILE + 1];
+    extern __shared__ __align__(16) float rows[];            // ROWS_PB x stride (stride = C rounded up to 4, + 4)
     __shared__ float s_mean[ROWS_PB];
     const int t = threadIdx.x, row0 = blockIdx.x * ROWS_PB;
-    const bool walker = t < ROWS_PB && row0 + t < R;
-    float acc = 0.f;
-    for (int c0 = 0; c0 < C; c0 += TILE) {
-        for (int idx = t; idx < ROWS_PB * TILE; idx += 256) {
-            const int r = idx / TILE, c = idx - r * TILE;
-            tile[r][c] = (row0 + r < R && c0 + c < C) ? fft[(size_t)(row0 + r) * C + c0 + c] : 0.f;
-        }
-        __syncthreads();
-        if (walker) {
-            const int n = min(TILE, C - c0);
-            for (int c = 0; c < n; ++c) acc += tile[t][c];          // mean += fft_data.at<float>(i, j)
-        }
-        __syncthreads();
+    const int nr = min(ROWS_PB, R - row0);
+    for (int r = 0; r < nr; ++r) {
+        const float *src = fft + (size_t)(row0 + r) * C;
+        float *dst = rows + r * stride;
+        for (int c = t; c < stride; c += 256) dst[c] = (c < C) ? src[c] : 0.f;
     }
-    if (walker) s_mean[t] = acc / (float)C;                          // mean /= fft_data.cols
     __syncthreads();
-    float sig = 0.f;
-    int nonzero = 0;
-    for (int c0 = 0; c0 < C; c0 += TILE) {
-        for (int idx = t; idx < ROWS_PB * TILE; idx += 256) {
-            const int r = idx / TILE, c = idx - r * TILE;
-            float v = 0.f;
-            if (row0 + r < R && c0 + c < C) {
-                v = fft[(size_t)(row0 + r) * C + c0 + c] - s_mean[r];
-                q[(size_t)(row0 + r) * C + c0 + c] = v;
-            }
-            tile[r][c] = v;
+    const bool walker = t < nr;
+    const float4 *mine = reinterpret_cast<const float4 *>(rows + (walker ? t : 0) * stride);
+    const int c4 = C >> 2;
+    if (walker) {
+        float acc = 0.f;
+        for (int k = 0; k < c4; ++k) {                          // mean += fft_data.at<float>(i, j)
+            const float4 a = mine[k];
+            acc += a.x; acc += a.y; acc += a.z; acc += a.w;
         }
-        __syncthreads();
-        if (walker) {
-            const int n = min(TILE, C - c0);
-            for (int c = 0; c < n; ++c) {
-                const float v = tile[t][c];
-                if (v < 0.f) { sig += 2 * (v * v); ++nonzero; }      // :83-84
-            }
-        }
-        __syncthreads();
+        for (int c = c4 * 4; c < C; ++c) acc += rows[t * stride + c];
+        s_mean[t] = acc / (float)C;                             // mean /= fft_data.cols
     }
-    if (walker) sigma_q[row0 + t] = nonzero ? sqrtf(sig / (float)nonzero) : 0.034f;   // :87-90
+    __syncthreads();
+    for (int r = 0; r < nr; ++r) {
+        const float m = s_mean[r];
+        float *dst = rows + r * stride;
+        float *qo = q + (size_t)(row0 + r) * C;
+        for (int c = t; c < C; c += 256) {
+            const float v = dst[c] - m;
+            dst[c] = v;
+            qo[c] = v;
+        }
+    }
+    __syncthreads();
+    if (walker) {
+        float sig = 0.f;
+        int nonzero = 0;
+        // adding +0.0f to the non-negative running sum changes nothing, so the test of :82 becomes a select
+#define NRS_SIG_STEP(v) { const float a_ = 2 * ((v) * (v)); const bool neg_ = (v) < 0.f; sig = sig + (neg_ ? a_ : 0.f); nonzero += neg_; }
+        for (int k = 0; k < c4; ++k) {
+            const float4 a = mine[k];
+            NRS_SIG_STEP(a.x) NRS_SIG_STEP(a.y) NRS_SIG_STEP(a.z) NRS_SIG_STEP(a.w)
+        }
+        for (int c = c4 * 4; c < C; ++c) { const float v = rows[t * stride + c]; NRS_SIG_STEP(v) }
+#undef NRS_SIG_STEP
+        sigma_q[row0 + t] = nonzero ? sqrtf(sig / (float)nonzero) : 0.034f;   // :87-90
+    }
 }
 
 __device__ __forceinline__ int reflect101(int j, int C)
@@ -85,30 +92,53 @@ __device__ __forceinline__ int reflect101(int j, int C)
     return j;
 }
 
-// :74 cv::filter2D(q, p, -1, filter, Point(-1,-1), 0, BORDER_REFLECT101): forward FMA chain per pixel
+// :74 cv::filter2D(q, p, -1, filter, Point(-1,-1), 0, BORDER_REFLECT101): forward FMA chain per pixel.
+// Each thread produces four adjacent columns: the 16 taps of a chunk and the 19 inputs they touch come in by
+// 16-byte shared-memory loads and serve 64 multiply-adds (the one-column version spent two loads per FMA).
 constexpr int FILT_THREADS = 256;
-constexpr int FILT_MAX = 255;    // taps (3 * sigma_gauss, odd)
+constexpr int FILT_COLS = FILT_THREADS * 4;      // columns per CTA
+constexpr int FILT_MAX = 255;                    // taps (3 * sigma_gauss, odd)
+constexpr int FILT_KPAD = 256;                   // taps padded to whole chunks of 16
 __global__ void __launch_bounds__(FILT_THREADS)
 fe18_filter_kernel(const float *__restrict__ q, int R, int C, const float *__restrict__ taps, int fsize,
                    float *__restrict__ p)
 {
-    __shared__ float row[FILT_THREADS + FILT_MAX];
-    __shared__ float kf[FILT_MAX];
-    const int i = blockIdx.y, j0 = blockIdx.x * FILT_THREADS, t = threadIdx.x;
+    __shared__ __align__(16) float row[FILT_COLS + FILT_KPAD + 4];
+    __shared__ __align__(16) float kf[FILT_KPAD];
+    const int i = blockIdx.y, j0 = blockIdx.x * FILT_COLS, t = threadIdx.x;
     const int anchor = fsize / 2;
-    for (int k = t; k < fsize; k += FILT_THREADS) kf[k] = taps[k];
+    const int nchunk = (fsize + 15) >> 4;
+    for (int k = t; k < nchunk * 16; k += FILT_THREADS) kf[k] = (k < fsize) ? taps[k] : 0.f;
     const float *qr = q + (size_t)i * C;
-    for (int e = t; e < FILT_THREADS + fsize - 1; e += FILT_THREADS) row[e] = qr[reflect101(j0 + e - anchor, C)];
+    for (int e = t; e < FILT_COLS + nchunk * 16 + 4; e += FILT_THREADS)
+        row[e] = (e < FILT_COLS + fsize - 1) ? qr[reflect101(j0 + e - anchor, C)] : 0.f;
     __syncthreads();
-    const int j = j0 + t;
-    if (j >= C) return;
-    float acc = 0.f;
-    if (j < (C & ~7)) {
-        for (int k = 0; k < fsize; ++k) acc = fmaf(row[t + k], kf[k], acc);      // OpenCV's 8-wide vector body
-    } else {
-        for (int k = 0; k < fsize; ++k) acc = acc + row[t + k] * kf[k];          // its scalar tail: multiply, then add
+    const int body = C & ~7;                         // OpenCV's 8-wide vector body; beyond it its scalar tail
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float4 *rw = reinterpret_cast<const float4 *>(row + 4 * t);
+    const float4 *kw = reinterpret_cast<const float4 *>(kf);
+    for (int ch = 0; ch < nchunk; ++ch) {
+        float x[20], w[16];
+#pragma unroll
+        for (int v = 0; v < 5; ++v) { const float4 a = rw[ch * 4 + v]; x[4 * v] = a.x; x[4 * v + 1] = a.y; x[4 * v + 2] = a.z; x[4 * v + 3] = a.w; }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { const float4 a = kw[ch * 4 + v]; w[4 * v] = a.x; w[4 * v + 1] = a.y; w[4 * v + 2] = a.z; w[4 * v + 3] = a.w; }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (ch * 16 + k < fsize) {
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const int j = j0 + 4 * t + o;
+                    acc[o] = (j < body) ? fmaf(x[k + o], w[k], acc[o]) : acc[o] + x[k + o] * w[k];
+                }
+            }
+        }
     }
-    p[(size_t)i * C + j] = acc;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        const int j = j0 + 4 * t + o;
+        if (j < C) p[(size_t)i * C + j] = acc[o];
+    }
 }
 
 // :95-103 the per-pixel response and its threshold test (flag = y > zq * sigma_q[i]); y optional (tests)
@@ -219,9 +249,18 @@ int fe_cen2018_device(nrs_ctx *ctx, FrontendState &S, int R, int C, float zq, in
     float *d_sigma = reinterpret_cast<float *>(S.d_incr);
     float *d_taps = d_sigma + FE_MAX_AZ;
     NRS_CUDA(cudaMemcpyAsync(d_taps, taps, fsize * sizeof(float), cudaMemcpyHostToDevice, st));
-    fe18_bias_sigma_kernel<<<(R + ROWS_PB - 1) / ROWS_PB, 256, 0, st>>>(S.d_fft, R, C, d_q, d_sigma);
-    NRS_LAUNCHED();
-    dim3 gf((C + FILT_THREADS - 1) / FILT_THREADS, R);
+    {
+        const int stride = ((C + 3) & ~3) + 4;               // rows 16-byte aligned, walkers on different banks
+        const size_t smem = (size_t)ROWS_PB * stride * sizeof(float);
+        static size_t configured = 0;
+        if (smem > configured) {
+            NRS_CUDA(cudaFuncSetAttribute(fe18_bias_sigma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        fe18_bias_sigma_kernel<<<(R + ROWS_PB - 1) / ROWS_PB, 256, smem, st>>>(S.d_fft, R, C, stride, d_q, d_sigma);
+        NRS_LAUNCHED();
+    }
+    dim3 gf((C + FILT_COLS - 1) / FILT_COLS, R);
     fe18_filter_kernel<<<gf, FILT_THREADS, 0, st>>>(d_q, R, C, d_taps, fsize, d_p);
     NRS_LAUNCHED();
     dim3 gp((C + 255) / 256, R);

@@ -69,3 +69,20 @@ def test_odometry_and_loop_stream(nrs, ctx, oracle, synth):
         loops.append((k, loop, bd))
     # the drive back passes the places of the first frames: the detector must say so
     assert any(l >= 0 for _, l, _ in loops), loops
+
+
+def test_png_directory_driver(nrs, ctx, synth, tmp_path):
+    """navtech-radar-slam_b200/stream.py::run_odometry on a directory of PNGs written by cv2 (what the node reads
+    with cv::imread): the chained trajectory follows the planted motion and the outputs are written."""
+    import cv2
+    stream = importlib.import_module("navtech-radar-slam_b200.stream")
+    world = synth.radar_world(seed=1234)
+    for k in range(6):
+        raw = synth.radar_frame(world, (2.5 * k, 0.1 * k, np.deg2rad(1.0) * k), seed=900 + k, dataset="mulran")
+        assert cv2.imwrite(str(tmp_path / f"{1560000000000000000 + k * 250000000}.png"), raw)
+    r = stream.run_odometry(str(tmp_path), "mulran", "cen2019", loop_detection=True, ctx=ctx, out_dir=str(tmp_path / "out"))
+    assert r["relative"].shape == (5, 4, 4) and r["trajectory"].shape == (6, 4, 4)
+    for T in r["relative"]:                                   # each step: ~2.5 m forward, ~1 degree
+        assert abs(T[0, 3] - 2.5) < 0.6 and abs(np.arctan2(T[1, 0], T[0, 0]) - np.deg2rad(1.0)) < 2e-2
+    assert abs(r["trajectory"][-1][0, 3] - 12.5) < 2.5
+    assert (tmp_path / "out" / "est_traj.txt").read_text().count("\n") == 6
