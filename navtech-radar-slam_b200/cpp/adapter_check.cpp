@@ -79,6 +79,36 @@ int main()
     try { RadarLoader bad("kitti", "cen2019", 0.6, true, false, ctx); return 1; } catch (const std::invalid_argument &) {}
     RadarLoader loader("mulran", "cen2019", 0.6, true, false, ctx);
     (void)loader;
+    RadarLoader loader18("mulran", "cen2018", 0.6, true, false, ctx);     // what run_orora.launch passes
+    (void)loader18;
+    // the reference's own candidate flow (ring-key 3-NN + 3 candidates) must agree with the exhaustive
+    // search whenever the exhaustive winner is among the candidates -- here: exact revisits
+    {
+        SCManager tree(ctx);
+        tree.use_tree_candidates = true;
+        tree.setSCdistThres(0.45);
+        int ok = 0;
+        for (int k = 0; k < 70; ++k) {
+            tree.makeAndSaveScancontextAndKeys(clouds[k % 8]);
+            auto r = tree.detectLoopClosureID();
+            if (r.first >= 0) { ++ok; if (r.first % 8 != k % 8) { std::printf("tree mode: wrong loop %d for %d\n", r.first, k); return 1; } }
+        }
+        std::printf("SCManager (kd-tree mode): %d loops found\n", ok);
+        if (ok < 5) return 1;
+    }
+    // cen2018features / cen2019features as free functions on a small synthetic polar image
+    {
+        const int R = 16, C = 640;
+        std::vector<float> fft((size_t)R * C);
+        std::uniform_int_distribution<int> noise(0, 23), hot(0, 39), lvl(120, 255);
+        for (int i = 0; i < R; ++i)
+            for (int j = 0; j < C; ++j) fft[(size_t)i * C + j] = j < 42 ? 0.f : (hot(rng) == 0 ? lvl(rng) : noise(rng)) / 255.0f;
+        MiniMatrix t18, t19;
+        nrs::cen2018features(fft.data(), R, C, 3.0f, 17, 58, t18, ctx);
+        nrs::cen2019features(fft.data(), R, C, 200, 58, t19, ctx);
+        std::printf("cen2018: %d keypoints, cen2019: %d keypoints\n", (int)t18.cols(), (int)t19.cols());
+        if (t18.cols() < 10 || t19.cols() < 10) return 1;
+    }
     std::printf("adapters ok\n");
     }
     nrs_ctx_destroy(ctx);
