@@ -5,7 +5,9 @@ Headline metric (BASELINE.json): ScanContext loop-queries/s against a 10k-keyfra
 (config 2 scaled to the 10k size the metric is quoted on; it fits one GPU), exhaustive
 distanceBtnScanContext over every keyframe as north_star specifies.  A "step" is ONE loop
 query over the whole database.  At N>1 the 10k keyframes are sharded over the ranks
-(round-robin) and each step adds one 16-byte all_gather (strong scaling: the job is fixed).
+(round-robin) and the search kernel's last CTA exchanges the 16-byte per-shard records over
+peer memory (one NCCL all_gather per step if CUDA IPC is unavailable); strong scaling: the
+job is fixed.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 

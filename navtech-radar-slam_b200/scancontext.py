@@ -11,9 +11,10 @@ libnrs_b200.so on the GPU; matrices are numpy float64 arrays of shape (20, 60) i
 
 ``ShardedSCDatabase`` is the multi-GPU form north_star asks for: one process per GPU, each
 rank holds a slice of the keyframes, every rank scores the same query against its slice
-and the 16-byte per-shard minima are exchanged with ONE collective
-(torch.distributed all_gather: NCCL over NVLink on GPUs, gloo in the CPU tests of the host
-logic), followed by the exact lowest-index tie-break the sequential scan would apply.
+and the 16-byte per-shard minima are exchanged and merged with the exact lowest-index
+tie-break the sequential scan would apply -- on GPUs inside the search kernel itself, over
+peer memory (NVLink; nrs_sc_query_dev_sharded), otherwise with ONE collective
+(torch.distributed all_gather: NCCL, or gloo in the CPU tests of the host logic).
 """
 import ctypes as C
 import math
@@ -324,7 +325,7 @@ class SCManager:
 
 
 # -------------------------------------------------------------------------------------------------
-# multi-GPU: keyframes sharded over ranks, one collective per query
+# multi-GPU: keyframes sharded over ranks; per-shard records merged in-kernel over peer memory or by one collective
 # -------------------------------------------------------------------------------------------------
 def shard_owner(global_idx, world):
     """Round-robin ownership: keyframe g lives on rank g % world at local slot g // world, so a
