@@ -938,7 +938,13 @@ __device__ void knn_block_select(float (&ld)[KNN_MAX], int (&li)[KNN_MAX], int k
 __device__ __forceinline__ void knn_insert(float (&ld)[KNN_MAX], int (&li)[KNN_MAX], int k, float d, int i)
 {
     if (!(d == d)) return;
-    if (li[k - 1] >= 0 && !knn_before(d, i, ld[k - 1], li[k - 1])) return;     // not better than the worst kept
+    // the worst kept entry, slot k - 1, read without a run-time index (which would push the lists into local memory)
+    float wd = ld[0];
+    int wi = li[0];
+#pragma unroll
+    for (int j = 1; j < KNN_MAX; ++j)
+        if (j < k) { wd = ld[j]; wi = li[j]; }
+    if (wi >= 0 && !knn_before(d, i, wd, wi)) return;                          // not better than the worst kept
     // slot j takes old[j-1] if that sorts after the new entry, else the new entry if old[j] sorts after it
 #pragma unroll
     for (int j = KNN_MAX - 1; j >= 0; --j) {
