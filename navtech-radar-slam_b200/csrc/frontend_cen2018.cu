@@ -123,21 +123,32 @@ fe18_filter_kernel(const float *__restrict__ q, int R, int C, const float *__res
         for (int v = 0; v < 5; ++v) { const float4 a = rw[ch * 4 + v]; x[4 * v] = a.x; x[4 * v + 1] = a.y; x[4 * v + 2] = a.z; x[4 * v + 3] = a.w; }
 #pragma unroll
         for (int v = 0; v < 4; ++v) { const float4 a = kw[ch * 4 + v]; w[4 * v] = a.x; w[4 * v + 1] = a.y; w[4 * v + 2] = a.z; w[4 * v + 3] = a.w; }
+        // a thread's four columns lie on one side of the body / tail border (both are multiples of 4)
+        if (j0 + 4 * t < body) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            if (ch * 16 + k < fsize) {
+            for (int k = 0; k < 16; ++k) {
+                if (ch * 16 + k < fsize) {
 #pragma unroll
-                for (int o = 0; o < 4; ++o) {
-                    const int j = j0 + 4 * t + o;
-                    acc[o] = (j < body) ? fmaf(x[k + o], w[k], acc[o]) : acc[o] + x[k + o] * w[k];
+                    for (int o = 0; o < 4; ++o) acc[o] = fmaf(x[k + o], w[k], acc[o]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if (ch * 16 + k < fsize) {
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) acc[o] = acc[o] + x[k + o] * w[k];
                 }
             }
         }
     }
+    const int jb = j0 + 4 * t;
+    if ((C & 3) == 0 && jb + 3 < C) {
+        *reinterpret_cast<float4 *>(p + (size_t)i * C + jb) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else {
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
-        const int j = j0 + 4 * t + o;
-        if (j < C) p[(size_t)i * C + j] = acc[o];
+        for (int o = 0; o < 4; ++o)
+            if (jb + o < C) p[(size_t)i * C + jb + o] = acc[o];
     }
 }
 
