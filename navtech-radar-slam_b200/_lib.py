@@ -100,6 +100,11 @@ def _declare(L):
     L.nrs_sc_make.argtypes = [vp, vp, i32, f64, f64, vp]
     L.nrs_sc_keys.argtypes = [vp, vp, vp, vp]
     L.nrs_sc_pair.argtypes = [vp, vp, vp, vp, vp]
+    L.nrs_sc_fast_align.argtypes = [vp, vp, vp, vp]
+    L.nrs_sc_dist_direct.argtypes = [vp, vp, vp, vp]
+    L.nrs_version.argtypes = []
+    L.nrs_last_error.argtypes = []
+    L.nrs_kernel_launches.argtypes = []
     L.nrs_sc_db_create.argtypes = [vp, i32, C.POINTER(vp)]
     L.nrs_sc_db_destroy.argtypes = [vp]
     L.nrs_sc_db_size.argtypes = [vp]

@@ -60,3 +60,53 @@ def test_cpp_adapters_compile_and_link(nrs):
         assert r.returncode == 0, r.stdout + r.stderr
     else:
         assert r.returncode == 77 and "no CPU fallback" in r.stdout
+
+
+def test_ctypes_structs_match_the_header(nrs, tmp_path):
+    """The Python host side mirrors the header's POD structs by hand: their sizes and field offsets must be
+    what a C compiler makes of include/nrs_b200.h."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = importlib_lib(nrs)
+    structs = {
+        "nrs_sc_result": (lib.ScResult, ["dist", "idx", "shift"]),
+        "nrs_extract_params": (lib.ExtractParams, ["navtech_version", "range_bins", "radar_resolution", "cart_resolution",
+                                                   "cart_pixel_width", "min_range", "max_points", "patch_size",
+                                                   "use_voxelization", "interpolate_crossover", "voxel_size", "nndr",
+                                                   "keypoint_extraction", "zq", "sigma_gauss"]),
+        "nrs_frame_info": (lib.FrameInfo, ["n_candidates", "j_consumed", "l_regions", "K_polar", "K_voxel", "K", "K_desc",
+                                           "maxg", "mean", "mean_h", "cart_max", "t_criteria"]),
+        "nrs_solver_params": (lib.SolverParams, None),
+        "nrs_solver_info": (lib.SolverInfo, None),
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "nrs_b200.h"', 'int main(void){']
+    for cname, (ct, fields) in structs.items():
+        lines.append(f'printf("{cname} size %zu\\n", sizeof({cname}));')
+        for f in (fields if fields is not None else [n for n, _ in ct._fields_]):
+            lines.append(f'printf("{cname} {f} %zu\\n", offsetof({cname}, {f}));')
+    lines.append("return 0;}")
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    assert os.system(f"/usr/bin/gcc -std=c99 -I{root}/include {src} -o {exe}") == 0
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    for ln in out:
+        if not ln:
+            continue
+        cname, field, val = ln.split()
+        ct = structs[cname][0]
+        if field == "size":
+            assert C.sizeof(ct) == int(val), (cname, C.sizeof(ct), val)
+        else:
+            assert getattr(ct, field).offset == int(val), (cname, field)
+
+
+def test_every_symbol_has_a_ctypes_signature(nrs):
+    """an undeclared signature would make ctypes pass Python ints as 32-bit C ints -- fatal for pointers"""
+    L = nrs.lib()
+    assert [n for n in nrs.declared_symbols() if getattr(L, n).argtypes is None] == []
+
+
+def importlib_lib(nrs):
+    import importlib
+    return importlib.import_module("navtech-radar-slam_b200._lib")
