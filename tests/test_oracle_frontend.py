@@ -250,3 +250,35 @@ def test_cen2018_oracle_reproduces_committed_golden(F):
         assert np.array_equal(st["targets"], g[f"{tag}_targets"])
         assert np.array_equal(st["sigma_q"], g[f"{tag}_sigma"])
         assert (st["y"].view(np.uint32) != g[f"{tag}_y"].view(np.uint32)).sum() <= 4
+
+
+def test_cen2018_c_loops_against_numpy_rederivation(F):
+    """The oracle's C loops for cen2018 (bias, noise level, response) re-derived independently in numpy:
+    np.cumsum on float32 is a sequential float32 accumulation, i.e. the reference's summation order, so bias and
+    noise level must agree bit for bit; the response goes through numpy's own exp (not glibc's), so it is
+    compared to one float ulp."""
+    rng = np.random.default_rng(21)
+    fft = (rng.integers(0, 24, (12, 900)) / 255.0).astype(np.float32)
+    hot = rng.random(fft.shape) < 0.03
+    fft[hot] = (rng.integers(120, 256, int(hot.sum())) / 255.0).astype(np.float32)
+    fft[:, :42] = 0
+    fft[7] = 0.5                                              # constant row: no negative q, sigma = 0.034
+    st = F.cen2018_stages(fft, 3.0, 17, 58)
+    rows, cols = fft.shape
+    mean = np.cumsum(fft, axis=1, dtype=np.float32)[:, -1] / np.float32(cols)
+    q = fft - mean[:, None]
+    assert np.array_equal(q.view(np.uint32), st["q"].view(np.uint32))
+    terms = np.where(q < 0, np.float32(2) * (q * q), np.float32(0)).astype(np.float32)
+    acc = np.cumsum(terms, axis=1, dtype=np.float32)[:, -1]
+    nz = (q < 0).sum(axis=1)
+    with np.errstate(all="ignore"):
+        sigma = np.where(nz > 0, np.sqrt(acc / np.maximum(nz, 1).astype(np.float32)), np.float32(0.034)).astype(np.float32)
+    assert np.array_equal(sigma.view(np.uint32), st["sigma_q"].view(np.uint32))
+    p = st["p"]
+    a = ((q - p) / sigma[:, None]).astype(np.float32).astype(np.float64)
+    b = (p / sigma[:, None]).astype(np.float32).astype(np.float64)
+    nqp = np.exp(-0.5 * a * a).astype(np.float32)
+    npp = np.exp(-0.5 * b * b).astype(np.float32)
+    y = (q * (np.float32(1) - nqp)).astype(np.float32) + (p * (nqp - npp).astype(np.float32)).astype(np.float32)
+    d = np.abs(y[:, 58:].astype(np.float64) - st["y"][:, 58:])
+    assert d.max() <= 2e-7 and (y[:, 58:].view(np.uint32) != st["y"][:, 58:].view(np.uint32)).mean() < 0.01
