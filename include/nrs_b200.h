@@ -44,6 +44,7 @@ extern "C" {
 #define NRS_SC_RINGS    20  /* SC/Scancontext.h:85 */
 #define NRS_SC_SECTORS  60  /* SC/Scancontext.h:86 */
 #define NRS_SC_DESC     (NRS_SC_RINGS * NRS_SC_SECTORS)
+#define NRS_SC_MAX_BATCH 1024 /* queries per launch of the batched search (larger batches are split) */
 
 typedef struct nrs_ctx   nrs_ctx;    /* one CUDA device + stream + scratch            */
 typedef struct nrs_sc_db nrs_sc_db;  /* device-resident keyframe descriptor database  */
@@ -130,8 +131,21 @@ int nrs_sc_knn(nrs_sc_db *db, const float *ringkey20_host, int first, int last, 
  * device; cand_out (nullable, k ids) reports the candidates. */
 int nrs_sc_detect_knn(nrs_sc_db *db, const double *query_host, int first, int last, int k,
                       int32_t *cand_out, nrs_sc_result *result_host);
-/* bytes per keyframe that an exhaustive query streams from HBM (the f32 filter record) */
+/* bytes per keyframe that an exhaustive query streams from HBM: the f32 filter record of the
+ * general-valued search, and the 256-byte bit-mask record of the {0,c} search (below) */
 int nrs_sc_filter_record_bytes(void);
+int nrs_sc_bin_record_bytes(void);
+
+/* {0,c} descriptors.  In this pipeline every occupied bin holds the same value (ORORA publishes
+ * z = 1.0, ORORA/src/odometry.cpp:305-316; makeScancontext adds LIDAR_HEIGHT, Scancontext.cpp:168),
+ * so distanceBtnScanContext is a function of 60 20-bit column masks.  The database classifies every
+ * keyframe at append time; while ALL stored keyframes are {0,c} (c > 0 with <= 24 significant bits)
+ * exhaustive and candidate searches run on the bit-mask kernel (sc_search_bin.cu) -- same results,
+ * bit for bit (the f64 certification reproduces the reference's sums exactly from the masks) -- else
+ * on the general-valued f32-filter kernel.  nrs_sc_db_is_binary: 1 when the bit-mask search applies.
+ * nrs_sc_db_set_search_mode(db, 1) forces the general-valued kernel (tests, benchmarks); 0 = auto. */
+int nrs_sc_db_is_binary(nrs_sc_db *db);
+int nrs_sc_db_set_search_mode(nrs_sc_db *db, int mode);
 
 /* Multi-GPU (one process per GPU, keyframe g stored on rank g % world as local slot g / world):
  * result exchange through peer memory instead of a collective.  Each rank creates its slot array
@@ -148,6 +162,12 @@ int nrs_sc_xchg_create(nrs_sc_db *db, int world, int rank, unsigned char *handle
 int nrs_sc_xchg_open(nrs_sc_db *db, const unsigned char *handles_world_x_64);
 int nrs_sc_query_dev_sharded(nrs_sc_db *db, const double *query_dev, int first, int last,
                              nrs_sc_result *result_dev);
+/* Q queries, ONE exchange: every rank's per-query records travel while later queries are still being
+ * scored and the world's records are merged once per launch ({0,c} databases; otherwise Q exchanges). */
+int nrs_sc_query_batch_dev_sharded(nrs_sc_db *db, const double *queries_dev, int Q, int first, int last,
+                                   nrs_sc_result *results_dev);
+/* how long the merge waits for a peer's records before reporting idx == -2 (default ~3000 ms) */
+int nrs_sc_xchg_set_timeout_ms(nrs_sc_db *db, int ms);
 /* diagnostics: %globaltimer (ns) stamps of the database's most recent search, taken by its last
  * CTA: [0] tail entered, [1] local result ready, [2] record + flag written to the peers
  * (sharded queries only), [3] result written.  Synchronises the stream. */
@@ -169,6 +189,16 @@ int nrs_sc_query_all(nrs_sc_db *db, const double *query_host, int first, int las
  * added to the reported index (a shard's global offset). */
 int nrs_sc_query_dev(nrs_sc_db *db, const double *query_dev, int first, int last,
                      int32_t idx_offset, nrs_sc_result *result_dev);
+/* Batched search: Q queries (Q x 1200 doubles, query-major) against keyframes [first,last) -- the
+ * detectLoopClosureID search loop (Scancontext.cpp:380-396) for Q query descriptors at once (multi-
+ * session relocalisation, offline loop mining, Scancontext.cpp:267-328).  results[q] is exactly what
+ * nrs_sc_query returns for query q.  On a {0,c} database this is ONE kernel launch whose CTAs share
+ * the keyframe records between queries; otherwise Q launches.  _dev: device pointers, enqueued on
+ * the context stream, no synchronisation. */
+int nrs_sc_query_batch(nrs_sc_db *db, const double *queries_host, int Q, int first, int last,
+                       nrs_sc_result *results_host);
+int nrs_sc_query_batch_dev(nrs_sc_db *db, const double *queries_dev, int Q, int first, int last,
+                           int32_t idx_offset, nrs_sc_result *results_dev);
 
 /* ---- ORORA solver (ORORA/include/ORORA.hpp, ORORA/include/solver/nonminimal_solver.hpp) ---- */
 

@@ -125,6 +125,13 @@ def _declare(L):
     L.nrs_sc_query.argtypes = [vp, vp, i32, i32, vp, i32, vp]
     L.nrs_sc_query_all.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     L.nrs_sc_query_dev.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.nrs_sc_query_batch.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.nrs_sc_query_batch_dev.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    L.nrs_sc_query_batch_dev_sharded.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.nrs_sc_xchg_set_timeout_ms.argtypes = [vp, i32]
+    L.nrs_sc_db_is_binary.argtypes = [vp]
+    L.nrs_sc_db_set_search_mode.argtypes = [vp, i32]
+    L.nrs_sc_bin_record_bytes.argtypes = []
     L.nrs_solver_default_params.restype = None
     L.nrs_solver_default_params.argtypes = [vp]
     L.nrs_orora_solve.argtypes = [vp, vp, vp, i32, vp, f64, vp, vp, vp, vp]

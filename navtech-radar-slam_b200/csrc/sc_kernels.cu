@@ -29,61 +29,11 @@
 #include <algorithm>
 #include <vector>
 
-#include "common.cuh"
+#include "sc_common.cuh"
+
+using namespace nrs_sc;
 
 namespace {
-
-constexpr int R = NRS_SC_RINGS;      // 20
-constexpr int S = NRS_SC_SECTORS;    // 60
-constexpr int DESC = R * S;          // 1200 doubles = 9600 B (the reference's MatrixXd)
-constexpr int NSHIFT = 7;            // 2 * round(0.5 * SEARCH_RATIO * 60) + 1   (Scancontext.cpp:123)
-constexpr int RADIUS = 3;
-constexpr double SENTINEL = 10000000.0;   // Scancontext.cpp:134,362
-
-struct BlockResult {
-    double dist;
-    int    pos;
-    int    idx;
-    int    shift;
-    int    pad;
-};
-
-// Eigen redux order over 20 values held in registers.
-__device__ __forceinline__ double redux20(const double (&v)[R])
-{
-    double a0 = v[0], a1 = v[1], b0 = v[2], b1 = v[3];
-#pragma unroll
-    for (int i = 4; i < R; i += 4) {
-        a0 += v[i];
-        a1 += v[i + 1];
-        b0 += v[i + 2];
-        b1 += v[i + 3];
-    }
-    a0 += b0;
-    a1 += b1;
-    return a0 + a1;
-}
-
-__device__ __forceinline__ double redux20_dot(const double (&a)[R], const double (&b)[R])
-{
-    double a0 = a[0] * b[0], a1 = a[1] * b[1], b0 = a[2] * b[2], b1 = a[3] * b[3];
-#pragma unroll
-    for (int i = 4; i < R; i += 4) {
-        a0 += a[i] * b[i];
-        a1 += a[i + 1] * b[i + 1];
-        b0 += a[i + 2] * b[i + 2];
-        b1 += a[i + 3] * b[i + 3];
-    }
-    a0 += b0;
-    a1 += b1;
-    return a0 + a1;
-}
-
-// strict-'<' sequential scan == lexicographic min over (value, order key); NaN never wins.
-__device__ __forceinline__ bool better(double d1, int k1, double d2, int k2)
-{
-    return (d1 < d2) || (d1 == d2 && k1 < k2);
-}
 
 // =================================================================================================
 // K10: f32 filter over a compact filter record + f64 certification of the survivors
@@ -128,23 +78,11 @@ constexpr int F_B2 = F_VK + S;              // |vk|^2 (f32), one pad float, then
 constexpr int FREC_F = F_B2 + 4;            // 1384 floats
 constexpr int FREC_BYTES = FREC_F * 4;      // 5536 B per keyframe
 static_assert(FREC_BYTES % 16 == 0 && (F_VK * 4) % 16 == 0 && ((F_B2 + 2) * 4) % 8 == 0, "filter record alignment");
-constexpr int KEYS_D = 2 * S;               // f64 side record: vk[60], kn[60]
-constexpr unsigned long long MASK60 = (1ull << S) - 1ull;
-constexpr unsigned long long HAZ_B = 1ull << 62, HAZ_C = 1ull << 63;
 // Filter B: lane l scores the shifts 2l and 2l+1 from ONE sliding window of the doubled query key that
 // starts at index 2l.  Two copies (copy m holds vq[(j + 2m) mod 60] at j) make every window start 16-byte
 // aligned: lane l reads copy l & 1 from float index 4 (l >> 1).  Copy stride 144 floats = 36 x 16 B,
 // 36 mod 8 = 4: the eight lanes of a quarter-warp (four bases x two copies) hit eight different banks.
 constexpr int QW_STRIDE = 144;
-constexpr float EPS_B = 3.0517578125e-5f;   // 2^-15
-constexpr float EPS_C = 7.62939453125e-6f;  // 2^-17
-
-struct __align__(16) Survivor {          // 16 bytes, one per keyframe the filter could not rule out
-    int   item;                          // position in the searched range / candidate list
-    int   code;                          // s0 | candC << 8 | certain << 16
-    float lo;                            // f32 minimum of the 7 distances
-    int   pad;
-};
 
 struct WarpSmem {
     float    tile[FREC_F];               // TMA destination: the warp's filter record; consumed into registers
@@ -166,50 +104,7 @@ struct QHot {
     float  qv_norm2;                     // |vq|^2 (f32), inflated
     float  pad_[1];
 };
-// ... and the f64 side for the (rare) certification: keys and norms here, the columns straight from the query
-struct QCold {
-    const double *q64;                   // the query itself (global memory, the reference's layout)
-    double qn[S], qv[S];
-};
 static_assert(offsetof(QHot, qh) % 16 == 0 && offsetof(QHot, qw) % 16 == 0, "LDS.128 alignment");
-
-// search state shared by the launches of one database (device memory, 32 bytes)
-struct SearchState {
-    unsigned int ticket;                 // last-block-done counter (zero between launches)
-    unsigned int gub;                    // smallest f32 upper bound of any keyframe's distance (order-preserving bits)
-    unsigned int n_surv;                 // survivor list length
-    unsigned int pad;
-    unsigned long long t_ns[4];          // %globaltimer of the last launch: tail entered, local result ready,
-                                         // record + flag written to the peers, world's records merged
-};
-__device__ __forceinline__ unsigned long long globaltimer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
-// Result exchange between the ranks of a keyframe-sharded database (one process per GPU): every
-// rank owns a slot array in its own HBM, slot[parity][source rank], mapped into all peers (CUDA IPC over
-// NVLink).  The last CTA of the search writes the rank's 16-byte record straight into every peer's
-// array (payload, fence.sys, epoch flag), waits until the world's records of this epoch have arrived
-// in its own array and merges them -- no collective call, no host round trip.  Slots are reused every
-// second query: a rank can only start writing epoch e+2 after it has seen every peer's e+1 flag, and a
-// peer raises that flag only after it has finished reading epoch e.
-struct XchgSlot {
-    double dist;
-    int    idx;
-    int    shift;
-    unsigned int epoch;
-    unsigned int pad[3];
-};
-struct XchgView {
-    XchgSlot *const *peers;              // device array of `world` base pointers (entry `rank` = local array)
-    int world, rank;
-    unsigned int epoch;
-};
-constexpr int XCHG_MAX_WORLD = 32;       // one lane per peer
-constexpr long long XCHG_TIMEOUT_CYCLES = 6000000000ll;   // ~3 s: a peer that never answers must not hang the GPU
 
 struct BlockSmem {
     QHot   q;
@@ -225,33 +120,6 @@ struct BlockSmem {
     double prep_am[S];
     double prep_inv[S];
 };
-
-// warp-wide f32 minimum in one instruction (sm_100a: CREDUX.MIN.F32)
-__device__ __forceinline__ float warp_min_f(float v)
-{
-    float r;
-    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
-    return r;
-}
-// order-preserving f32 -> u32 (atomicMin on the result == min on the floats)
-__device__ __forceinline__ unsigned int ord_f32(float f)
-{
-    const unsigned int b = __float_as_uint(f);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float unord_f32(unsigned int u)
-{
-    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
-}
-__device__ __forceinline__ int wrap60(int s)          // s in [-60, 120) -> [0, 60)
-{
-    s = s < 0 ? s + S : s;
-    return s >= S ? s - S : s;
-}
-
-// magnitude window in which the f32 filter's error bounds hold (see the K10 header)
-__device__ __forceinline__ bool hazard_col(double mx) { return !(mx <= 1e150) || (mx != 0.0 && mx < 1e-140); }
-__device__ __forceinline__ bool hazard_key(double mx) { return !(mx <= 1e15) || (mx != 0.0 && mx < 1e-15); }
 
 // Query preparation, once per CTA (threads 0..59 take one column each; the rest of the CTA is waiting for its
 // first records anyway): the reference's sector key / column norm arithmetic (Scancontext.cpp:223, :78) in
@@ -311,87 +179,6 @@ __device__ __forceinline__ void prepare_query(BlockSmem &sm, const double *__res
         sm.q.qflags = sm.prep_flags | (hazard_key(mk) ? HAZ_B : 0ull);
     }
     __syncthreads();
-}
-
-// ---- exact f64 evaluation, the reference's order -----------------------------------------------------
-// fastAlignUsingVkey over the candidate shifts (bit l of even <=> shift 2l, of odd <=> shift 2l + 1),
-// ascending; one warp.
-__device__ __noinline__ int certify_shift(const QCold *__restrict__ qc, double *scr, const double *__restrict__ vk,
-                                          unsigned int even, unsigned int odd, int lane)
-{
-    double fa_n = SENTINEL;
-    int s0 = 0;
-    while (even | odd) {
-        const int se = even ? 2 * (__ffs(even) - 1) : 2 * S, so = odd ? 2 * (__ffs(odd) - 1) + 1 : 2 * S;
-        const int s = min(se, so);
-        if (se < so) even &= even - 1; else odd &= odd - 1;
-        __syncwarp();
-        for (int i = lane; i < S; i += 32) {
-            const double d = qc->qv[i] - vk[wrap60(i - s)];
-            scr[i] = d * d;
-        }
-        __syncwarp();
-        double acc = 0.0;
-        if (lane < 4) {
-            acc = scr[lane];
-#pragma unroll
-            for (int i = 4; i < S; i += 4) acc += scr[lane + i];
-        }
-        const double a2 = __shfl_sync(0xffffffffu, acc, 2), a3 = __shfl_sync(0xffffffffu, acc, 3);
-        const double a1 = __shfl_sync(0xffffffffu, acc, 1), a0 = __shfl_sync(0xffffffffu, acc, 0);
-        const double nrm = sqrt((a0 + a2) + (a1 + a3));
-        if (nrm < fa_n) { fa_n = nrm; s0 = s; }          // ascending s + strict '<' == reference scan
-    }
-    __syncwarp();
-    return s0;
-}
-
-// distDirectSC for the shift slots in candC (bit d <=> shift s0 + d - 3); one warp; returns on all lanes
-// the lexicographic (dist, shift) minimum, (SENTINEL, 0) when no slot has an effective column.
-__device__ __noinline__ void certify_dist(const QCold *__restrict__ qc, unsigned long long qzero, double *scr,
-                                          const double *__restrict__ desc, const double *__restrict__ kn,
-                                          unsigned long long kzero, int s0, unsigned int candC, int lane,
-                                          double &dd, int &ds)
-{
-    dd = SENTINEL;
-    ds = 0;
-    while (candC) {
-        const int d = __ffs(candC) - 1;
-        candC &= candC - 1;
-        const int s = wrap60(s0 + d - RADIUS);
-        __syncwarp();
-        // key column paired with query column c is (c - s) mod 60: rotate the key mask up by s;
-        // effective columns (both norms non-zero), in column order, packed densely into scr[]
-        const unsigned long long krot = s ? (((kzero << s) | (kzero >> (S - s))) & MASK60) : kzero;
-        const unsigned long long eff = ~(qzero | krot) & MASK60;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {                 // both columns' loads in flight together
-            const int c = lane + 32 * h;
-            if (c >= S || !((eff >> c) & 1ull)) continue;
-            const int kc = wrap60(c - s);
-            double a[R], b[R];
-            const double2 *qa = reinterpret_cast<const double2 *>(qc->q64 + c * R);
-            const double2 *kb = reinterpret_cast<const double2 *>(desc + kc * R);
-#pragma unroll
-            for (int r = 0; r < R / 2; ++r) {
-                const double2 x = qa[r], y = kb[r];
-                a[2 * r] = x.x; a[2 * r + 1] = x.y; b[2 * r] = y.x; b[2 * r + 1] = y.y;
-            }
-            const int pos = __popcll(eff & ((1ull << c) - 1ull));
-            scr[pos] = redux20_dot(a, b) / (qc->qn[c] * kn[kc]);
-        }
-        __syncwarp();
-        double dist = SENTINEL;
-        if (lane == 0) {
-            const int cnt = __popcll(eff);
-            double sum = 0.0;                       // distDirectSC's left-to-right sum (:83)
-            for (int i = 0; i < cnt; ++i) sum = sum + scr[i];
-            dist = 1.0 - sum / (double)cnt;
-        }
-        dist = __shfl_sync(0xffffffffu, dist, 0);
-        if (better(dist, s, dd, ds)) { dd = dist; ds = s; }   // lexicographic (dist, shift) == ascending-shift scan
-    }
-    __syncwarp();
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -694,21 +481,20 @@ sc_search_kernel(const float *__restrict__ frec, const double *__restrict__ desc
             const int par = (int)(xv.epoch & 1u);
             bool ok = true;
             if (lane < xv.world) {
-                XchgSlot *dst = xv.peers[lane] + par * xv.world + xv.rank;
-                *reinterpret_cast<volatile double *>(&dst->dist) = d;
-                *reinterpret_cast<volatile int *>(&dst->idx) = ix;
-                *reinterpret_cast<volatile int *>(&dst->shift) = sh;
-                __threadfence_system();
-                *reinterpret_cast<volatile unsigned int *>(&dst->epoch) = xv.epoch;
+                // slot layout shared with the bit-mask kernel: [parity][query 0 of XCHG_QCAP][source rank]
+                XchgSlot *dst = xv.peers[lane] + (size_t)par * XCHG_QCAP * xv.world + xv.rank;
+                dst->dist = d;
+                dst->idx = ix;
+                dst->shift = sh;
+                st_release_sys(&dst->epoch, xv.epoch);
                 if (lane == 0) st->t_ns[2] = globaltimer_ns();
-                const XchgSlot *src = xv.peers[xv.rank] + par * xv.world + lane;
+                const XchgSlot *src = xv.peers[xv.rank] + (size_t)par * XCHG_QCAP * xv.world + lane;
                 const long long t0 = clock64();
-                while (*reinterpret_cast<const volatile unsigned int *>(&src->epoch) != xv.epoch)
-                    if (clock64() - t0 > XCHG_TIMEOUT_CYCLES) { ok = false; break; }
-                __threadfence_system();
-                d = *reinterpret_cast<const volatile double *>(&src->dist);
-                ix = *reinterpret_cast<const volatile int *>(&src->idx);
-                sh = *reinterpret_cast<const volatile int *>(&src->shift);
+                while (ld_acquire_sys(&src->epoch) != xv.epoch)
+                    if (clock64() - t0 > xv.timeout_cycles) { ok = false; break; }
+                d = src->dist;
+                ix = src->idx;
+                sh = src->shift;
             } else {
                 d = SENTINEL;
             }
@@ -1017,17 +803,20 @@ sc_query_ringkey_kernel(const double *__restrict__ desc, float *__restrict__ key
 // arithmetic) and the f32 filter record (layout: K10 header).  One 64-thread CTA per keyframe.
 __global__ void __launch_bounds__(64)
 sc_pack_kernel(const double *__restrict__ canon, double *__restrict__ desc, double *__restrict__ keys,
-               float *__restrict__ frec, float *__restrict__ rkeys, int count)
+               float *__restrict__ frec, float *__restrict__ rkeys, unsigned int *__restrict__ brec,
+               unsigned int *__restrict__ n_general, int count)
 {
     __shared__ float sq2[S];
     __shared__ double am[S];
     __shared__ unsigned long long flags;
+    __shared__ unsigned long long pat_and, pat_or;      // AND / OR of the bit patterns of the non-zero entries
     const int k = blockIdx.x, t = threadIdx.x;
     if (k >= count) return;
     const double *src = canon + (size_t)k * DESC;
     double *dk = keys + (size_t)k * KEYS_D;
     float *fr = frec + (size_t)k * FREC_F;
-    if (t == 0) flags = 0ull;
+    unsigned int *br = brec + (size_t)k * BIN_WORDS;
+    if (t == 0) { flags = 0ull; pat_and = ~0ull; pat_or = 0ull; }
     for (int i = t; i < F_VK; i += 64) fr[i] = 0.f;          // pair padding included
     if (t >= 64 - R) {
         // ring key (Scancontext.cpp:198-211: row mean in Eigen's order), narrowed to float like
@@ -1046,6 +835,8 @@ sc_pack_kernel(const double *__restrict__ canon, double *__restrict__ desc, doub
         double v[R], sq[R];
         double mx = 0.0;
         bool bad = false;
+        unsigned int bits = 0u;
+        unsigned long long pa = ~0ull, po = 0ull;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             v[r] = src[t * R + r];
@@ -1053,7 +844,14 @@ sc_pack_kernel(const double *__restrict__ canon, double *__restrict__ desc, doub
             sq[r] = v[r] * v[r];
             bad |= !(fabs(v[r]) <= 1e300);
             mx = fmax(mx, fabs(v[r]));
+            if (!(v[r] == 0.0)) {
+                bits |= 1u << r;
+                const unsigned long long b = (unsigned long long)__double_as_longlong(v[r]);
+                pa &= b; po |= b;
+            }
         }
+        br[t] = bits;                                                          // bit-mask record: column masks
+        if (bits) { atomicAnd(&pat_and, pa); atomicOr(&pat_or, po); }
         const double mean = redux20(v) / (double)R, nrm = sqrt(redux20(sq));   // Scancontext.cpp:223, :78
         dk[t] = mean;
         dk[S + t] = nrm;
@@ -1077,6 +875,18 @@ sc_pack_kernel(const double *__restrict__ canon, double *__restrict__ desc, doub
         fr[F_B2] = b2;
         fr[F_B2 + 1] = 0.f;
         *reinterpret_cast<unsigned long long *>(fr + F_B2 + 2) = flags | (hazard_key(mk) ? HAZ_B : 0ull);
+        // {0,c} keyframe?  every non-zero entry has the same bit pattern c, c > 0 with at most 24 significant
+        // bits and a sane exponent (then every partial sum of the reference's reductions is exact, sc_search_bin.cu)
+        const bool none = (pat_or == 0ull);
+        const double c = none ? 1.0 : __longlong_as_double((long long)pat_or);
+        const bool isbin = (none || pat_and == pat_or) && (c > 0.0) && ((double)(float)c == c) &&
+                           (c >= 7.888609052210118e-31) && (c <= 1.2676506002282294e30);
+        const unsigned long long kz = flags & MASK60;
+        br[60] = (unsigned int)kz;
+        br[61] = (unsigned int)(kz >> 32);
+        br[62] = __float_as_uint(isbin ? (float)c : 0.f);
+        br[63] = isbin ? 1u : 0u;
+        if (!isbin && n_general) atomicAdd(n_general, 1u);
     }
 }
 
@@ -1085,36 +895,6 @@ sc_pack_kernel(const double *__restrict__ canon, double *__restrict__ desc, doub
 // =================================================================================================
 // host side
 // =================================================================================================
-struct nrs_sc_db {
-    nrs_ctx     *ctx = nullptr;
-    std::mutex   mu;
-    double      *d_desc = nullptr;       // capacity x 1200 doubles: polarcontexts_ verbatim (Scancontext.h:111)
-    double      *d_keys = nullptr;       // capacity x 120 doubles: sector key, column norms (f64)
-    float       *d_frec = nullptr;       // capacity x FREC_F floats: filter records
-    float       *d_rkeys = nullptr;      // capacity x 20 floats: ring keys (polarcontext_invkeys_mat_)
-    float       *d_knn_pd = nullptr;     // per-block partial k-NN lists (distance, index)
-    int32_t     *d_knn_pi = nullptr;
-    float       *d_knn_out = nullptr;    // [0,16) d2, [16,32) idx, [32,48) candidate ids, [48,68) query ring key
-    Survivor    *d_surv = nullptr;       // capacity entries
-    int          size = 0;
-    int          capacity = 0;
-    // per-db search scratch
-    BlockResult   *d_block = nullptr;
-    SearchState   *d_state = nullptr;
-    nrs_sc_result *d_result = nullptr;
-    double        *d_query = nullptr;
-    nrs_sc_result *h_result = nullptr;   // pinned
-    double        *h_query = nullptr;    // pinned
-    int            max_blocks = 0;
-    // peer-memory result exchange (keyframe-sharded databases)
-    XchgSlot      *x_local = nullptr;    // 2 x world slots in this GPU's HBM, exported by CUDA IPC
-    XchgSlot     **x_peers_dev = nullptr;   // device array of world base pointers
-    void          *x_opened[XCHG_MAX_WORLD] = {};   // peer mappings to close
-    int            x_world = 0, x_rank = 0;
-    unsigned int   x_epoch = 0;
-    bool           x_ready = false;
-};
-
 namespace {
 
 constexpr int SURV_EXTRA = 64;
@@ -1129,18 +909,33 @@ struct DbView {
 
 int search_smem_bytes() { return (int)sizeof(BlockSmem); }
 
-int configure_search_kernel()
+// the opt-in is per device: remember which devices of this process have it (under a mutex; contexts on
+// several GPUs and threads may race here)
+int configure_search_kernel(int device)
 {
-    static int done = 0;
-    if (!done) {
+    static std::mutex mu;
+    static unsigned long long done_mask = 0ull;
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 0 || device >= 64 || !((done_mask >> device) & 1ull)) {
         NRS_CUDA(cudaFuncSetAttribute(sc_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       search_smem_bytes()));
-        done = 1;
+        if (device >= 0 && device < 64) done_mask |= 1ull << device;
     }
     return NRS_OK;
 }
 
 constexpr unsigned int GUB_INIT = 0xff800000u;     // ord_f32(+inf)
+
+int init_bin_state(nrs_sc_db *db, cudaStream_t stream)
+{
+    std::vector<SearchState> h(XCHG_QCAP);
+    for (auto &x : h) { x = SearchState{}; x.gub = GUB_INIT; }
+    NRS_CUDA(cudaMemcpyAsync(db->d_bstate, h.data(), h.size() * sizeof(SearchState), cudaMemcpyHostToDevice, stream));
+    NRS_CUDA(cudaMemsetAsync(db->d_gticket, 0, sizeof(unsigned int), stream));
+    NRS_CUDA(cudaMemsetAsync(db->d_ngen, 0, sizeof(unsigned int), stream));
+    NRS_CUDA(cudaStreamSynchronize(stream));
+    return NRS_OK;
+}
 
 int init_state(SearchState *d_state, cudaStream_t stream)
 {
@@ -1155,9 +950,9 @@ int init_state(SearchState *d_state, cudaStream_t stream)
 int launch_search(nrs_ctx *ctx, const DbView &v, const double *d_query, const int32_t *d_cand,
                   int first, int n_items, int idx_offset, double *d_dist_all, int32_t *d_shift_all,
                   BlockResult *d_block, SearchState *d_state, nrs_sc_result *d_result, int max_blocks,
-                  int idx_scale = 1, XchgView xv = XchgView{nullptr, 0, 0, 0u})
+                  int idx_scale = 1, XchgView xv = XchgView{nullptr, 0, 0, 0u, 0ll})
 {
-    int rc = configure_search_kernel();
+    int rc = configure_search_kernel(ctx->device);
     if (rc) return rc;
     int blocks = (n_items + WARPS - 1) / WARPS;
     blocks = std::max(1, std::min(blocks, max_blocks));
@@ -1173,12 +968,15 @@ DbView view_of(const nrs_sc_db *db) { return DbView{db->d_frec, db->d_desc, db->
 int db_reserve(nrs_sc_db *db, int want)
 {
     if (want <= db->capacity) return NRS_OK;
-    int cap = db->capacity ? db->capacity : 1024;
-    while (cap < want) cap *= 2;
+    long long cap64 = db->capacity ? db->capacity : 1024;
+    while (cap64 < want) cap64 *= 2;
+    if (cap64 > (1ll << 30)) { nrs::set_error("nrs_sc_db: %d keyframes exceed the supported capacity", want); return NRS_ENOMEM; }
+    const int cap = (int)cap64;
     double *nd = nullptr, *nk = nullptr;
     float *nf = nullptr, *nr = nullptr, *npd = nullptr;
     int32_t *npi = nullptr;
     Survivor *ns = nullptr;
+    unsigned int *nb = nullptr;
     const size_t n_part = ((size_t)cap / KNN_PER_BLOCK + 1) * KNN_MAX;
     cudaError_t e = cudaSuccess;
     if ((e = cudaMalloc(&nr, (size_t)cap * R * sizeof(float))) != cudaSuccess ||
@@ -1187,8 +985,9 @@ int db_reserve(nrs_sc_db *db, int want)
         (e = cudaMalloc(&nd, (size_t)cap * DESC * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&nk, (size_t)cap * KEYS_D * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&nf, (size_t)cap * FREC_BYTES)) != cudaSuccess ||
+        (e = cudaMalloc(&nb, (size_t)cap * BIN_WORDS * sizeof(unsigned int))) != cudaSuccess ||
         (e = cudaMalloc(&ns, ((size_t)cap + SURV_EXTRA) * sizeof(Survivor))) != cudaSuccess) {
-        cudaFree(nd); cudaFree(nk); cudaFree(nf); cudaFree(ns); cudaFree(nr); cudaFree(npd); cudaFree(npi);
+        cudaFree(nd); cudaFree(nk); cudaFree(nf); cudaFree(ns); cudaFree(nr); cudaFree(npd); cudaFree(npi); cudaFree(nb);
         nrs::set_error("nrs_sc_db: growing to %d keyframes: %s", cap, cudaGetErrorString(e));
         return NRS_ECUDA;
     }
@@ -1199,10 +998,12 @@ int db_reserve(nrs_sc_db *db, int want)
         NRS_CUDA(cudaMemcpyAsync(nk, db->d_keys, (size_t)db->size * KEYS_D * sizeof(double), cudaMemcpyDeviceToDevice, db->ctx->stream));
         NRS_CUDA(cudaMemcpyAsync(nf, db->d_frec, (size_t)db->size * FREC_BYTES, cudaMemcpyDeviceToDevice, db->ctx->stream));
         NRS_CUDA(cudaMemcpyAsync(nr, db->d_rkeys, (size_t)db->size * R * sizeof(float), cudaMemcpyDeviceToDevice, db->ctx->stream));
+        NRS_CUDA(cudaMemcpyAsync(nb, db->d_brec, (size_t)db->size * BIN_WORDS * sizeof(unsigned int), cudaMemcpyDeviceToDevice, db->ctx->stream));
         NRS_CUDA(cudaStreamSynchronize(db->ctx->stream));
     }
     cudaFree(db->d_desc); cudaFree(db->d_keys); cudaFree(db->d_frec); cudaFree(db->d_surv);
-    cudaFree(db->d_rkeys); cudaFree(db->d_knn_pd); cudaFree(db->d_knn_pi);
+    cudaFree(db->d_rkeys); cudaFree(db->d_knn_pd); cudaFree(db->d_knn_pi); cudaFree(db->d_brec);
+    db->d_brec = nb;
     db->d_desc = nd; db->d_keys = nk; db->d_frec = nf; db->d_surv = ns;
     db->d_rkeys = nr; db->d_knn_pd = npd; db->d_knn_pi = npi;
     db->capacity = cap;
@@ -1211,10 +1012,11 @@ int db_reserve(nrs_sc_db *db, int want)
 
 // canonical descriptors (device) -> records of keyframes [at, at + count)
 int pack_records(nrs_ctx *ctx, const double *d_canon, double *d_desc, double *d_keys, float *d_frec, float *d_rkeys,
-                 int at, int count)
+                 unsigned int *d_brec, unsigned int *d_ngen, int at, int count)
 {
     sc_pack_kernel<<<count, 64, 0, ctx->stream>>>(d_canon, d_desc + (size_t)at * DESC, d_keys + (size_t)at * KEYS_D,
-                                                  d_frec + (size_t)at * FREC_F, d_rkeys + (size_t)at * R, count);
+                                                  d_frec + (size_t)at * FREC_F, d_rkeys + (size_t)at * R,
+                                                  d_brec + (size_t)at * BIN_WORDS, d_ngen, count);
     NRS_LAUNCHED();
     return NRS_OK;
 }
@@ -1274,6 +1076,15 @@ int nrs_sc_db_create(nrs_ctx *ctx, int capacity_hint, nrs_sc_db **out)
         (e = cudaMalloc(&db->d_knn_out, 68 * sizeof(float))) != cudaSuccess ||
         (e = cudaMallocHost(&db->h_result, sizeof(nrs_sc_result))) != cudaSuccess ||
         (e = cudaMallocHost(&db->h_query, DESC * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&db->d_ngen, sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMallocHost(&db->h_ngen, sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMalloc(&db->d_bstate, XCHG_QCAP * sizeof(SearchState))) != cudaSuccess ||
+        (e = cudaMalloc(&db->d_gticket, sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMalloc(&db->d_queries, (size_t)XCHG_QCAP * DESC * sizeof(double))) != cudaSuccess ||
+        (e = cudaMallocHost(&db->h_queries, (size_t)XCHG_QCAP * DESC * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&db->d_results, XCHG_QCAP * sizeof(nrs_sc_result))) != cudaSuccess ||
+        (e = cudaMallocHost(&db->h_results, XCHG_QCAP * sizeof(nrs_sc_result))) != cudaSuccess ||
+        init_bin_state(db, ctx->stream) != NRS_OK ||
         init_state(db->d_state, ctx->stream) != NRS_OK) {
         nrs::set_error("nrs_sc_db_create: %s", cudaGetErrorString(e));
         nrs_sc_db_destroy(db);
@@ -1296,8 +1107,14 @@ int nrs_sc_db_destroy(nrs_sc_db *db)
     for (void *m : db->x_opened) if (m) cudaIpcCloseMemHandle(m);
     cudaFree(db->x_local); cudaFree(db->x_peers_dev);
     cudaFree(db->d_result); cudaFree(db->d_query);
+    cudaFree(db->d_brec); cudaFree(db->d_ngen); cudaFree(db->d_bstate); cudaFree(db->d_gticket);
+    cudaFree(db->d_queries); cudaFree(db->d_results);
+    db->bin_surv.release(); db->bin_block.release();
     if (db->h_result) cudaFreeHost(db->h_result);
     if (db->h_query) cudaFreeHost(db->h_query);
+    if (db->h_ngen) cudaFreeHost(db->h_ngen);
+    if (db->h_queries) cudaFreeHost(db->h_queries);
+    if (db->h_results) cudaFreeHost(db->h_results);
     delete db;
     return NRS_OK;
 }
@@ -1313,7 +1130,13 @@ int nrs_sc_db_clear(nrs_sc_db *db)
 {
     NRS_CHECK_ARG(db, "db is NULL");
     std::lock_guard<std::mutex> lk(db->mu);
+    std::lock_guard<std::mutex> lk2(db->ctx->mu);
+    NRS_CUDA(cudaSetDevice(db->ctx->device));
+    NRS_CUDA(cudaStreamSynchronize(db->ctx->stream));
+    NRS_CUDA(cudaMemsetAsync(db->d_ngen, 0, sizeof(unsigned int), db->ctx->stream));
+    NRS_CUDA(cudaStreamSynchronize(db->ctx->stream));
     db->size = 0;
+    db->n_general = 0;
     return NRS_OK;
 }
 
@@ -1325,6 +1148,7 @@ int nrs_sc_db_append(nrs_sc_db *db, const double *desc_host, int count)
     nrs_ctx *ctx = db->ctx;
     std::lock_guard<std::mutex> lk2(ctx->mu);
     NRS_CUDA(cudaSetDevice(ctx->device));
+    NRS_CHECK_ARG(count <= (1 << 30) - db->size, "database would exceed the supported capacity");
     int rc = db_reserve(db, db->size + count);
     if (rc) return rc;
     // stage the canonical 9600-byte descriptors, then derive the device records from them
@@ -1336,10 +1160,12 @@ int nrs_sc_db_append(nrs_sc_db *db, const double *desc_host, int count)
         const int n = std::min(chunk, count - done);
         NRS_CUDA(cudaMemcpyAsync(d_stage, desc_host + (size_t)done * DESC, (size_t)n * DESC * sizeof(double),
                                  cudaMemcpyHostToDevice, ctx->stream));
-        rc = pack_records(ctx, d_stage, db->d_desc, db->d_keys, db->d_frec, db->d_rkeys, db->size + done, n);
+        rc = pack_records(ctx, d_stage, db->d_desc, db->d_keys, db->d_frec, db->d_rkeys, db->d_brec, db->d_ngen, db->size + done, n);
         if (rc) return rc;
+        NRS_CUDA(cudaMemcpyAsync(db->h_ngen, db->d_ngen, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
         NRS_CUDA(cudaStreamSynchronize(ctx->stream));
     }
+    db->n_general = (int)*db->h_ngen;
     db->size += count;
     return NRS_OK;
 }
@@ -1361,10 +1187,12 @@ int nrs_sc_db_append_cloud(nrs_sc_db *db, const float *xyz, int P, double lidar_
     if (P) NRS_CUDA(cudaMemcpyAsync(d_xyz, xyz, (size_t)P * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     sc_make_kernel<<<1, 256, 0, ctx->stream>>>(d_xyz, P, lidar_height, max_radius, d_canon);
     NRS_LAUNCHED();
-    rc = pack_records(ctx, d_canon, db->d_desc, db->d_keys, db->d_frec, db->d_rkeys, db->size, 1);
+    rc = pack_records(ctx, d_canon, db->d_desc, db->d_keys, db->d_frec, db->d_rkeys, db->d_brec, db->d_ngen, db->size, 1);
     if (rc) return rc;
     if (desc_out) NRS_CUDA(cudaMemcpyAsync(desc_out, d_canon, DESC * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NRS_CUDA(cudaMemcpyAsync(db->h_ngen, db->d_ngen, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
     NRS_CUDA(cudaStreamSynchronize(ctx->stream));
+    db->n_general = (int)*db->h_ngen;
     db->size += 1;
     return NRS_OK;
 }
@@ -1373,7 +1201,7 @@ int nrs_sc_db_read(nrs_sc_db *db, int first, int count, double *desc_host)
 {
     NRS_CHECK_ARG(db && desc_host && first >= 0 && count >= 0, "bad argument");
     std::lock_guard<std::mutex> lk(db->mu);
-    NRS_CHECK_ARG(first + count <= db->size, "range exceeds database size");
+    NRS_CHECK_ARG(count <= db->size - first && first <= db->size, "range exceeds database size");
     if (count == 0) return NRS_OK;
     nrs_ctx *ctx = db->ctx;
     std::lock_guard<std::mutex> lk2(ctx->mu);
@@ -1387,6 +1215,25 @@ int nrs_sc_db_read(nrs_sc_db *db, int first, int count, double *desc_host)
 const double *nrs_sc_db_device_ptr(nrs_sc_db *db) { return db ? db->d_desc : nullptr; }
 
 int nrs_sc_filter_record_bytes(void) { return FREC_BYTES; }
+
+// {0,c} query?  (the host-side twin of prep_query's classification in sc_search_bin.cu)
+static bool host_query_is_binary(const double *q)
+{
+    unsigned long long pa = ~0ull, po = 0ull;
+    for (int i = 0; i < DESC; ++i)
+        if (!(q[i] == 0.0)) {
+            unsigned long long b;
+            memcpy(&b, &q[i], sizeof(b));
+            pa &= b; po |= b;
+        }
+    if (po == 0ull) return true;
+    if (pa != po) return false;
+    double c;
+    memcpy(&c, &po, sizeof(c));
+    return (c > 0.0) && ((double)(float)c == c) && (c >= 7.888609052210118e-31) && (c <= 1.2676506002282294e30);
+}
+static inline bool db_bin_ok(const nrs_sc_db *db) { return db->search_mode == 0 && db->n_general == 0; }
+static const XchgView XV_NONE{nullptr, 0, 0, 0u, 0ll};
 
 static int sc_query_impl(nrs_sc_db *db, const double *query_host, int first, int last,
                          const int32_t *cand, int n_cand, double *dist_out, int32_t *shift_out,
@@ -1426,9 +1273,14 @@ static int sc_query_impl(nrs_sc_db *db, const double *query_host, int first, int
         if (rc) return rc;
         view.surv = ctx->scratch[7].as<Survivor>();
     }
-    rc = launch_search(ctx, view, db->d_query, cand ? d_cand : nullptr, first, n_items, 0,
-                       want_all ? d_dist : nullptr, want_all ? d_shift : nullptr, db->d_block,
-                       db->d_state, db->d_result, db->max_blocks);
+    // {0,c} query against an all-{0,c} database: the bit-mask kernel; per-keyframe outputs and everything
+    // general-valued: the f32-filter kernel
+    if (!want_all && db_bin_ok(db) && host_query_is_binary(query_host))
+        rc = nrs_sc::bin_launch(db, db->d_query, 1, cand ? d_cand : nullptr, first, n_items, 1, 0, db->d_result, XV_NONE);
+    else
+        rc = launch_search(ctx, view, db->d_query, cand ? d_cand : nullptr, first, n_items, 0,
+                           want_all ? d_dist : nullptr, want_all ? d_shift : nullptr, db->d_block,
+                           db->d_state, db->d_result, db->max_blocks);
     if (rc) return rc;
     NRS_CUDA(cudaMemcpyAsync(db->h_result, db->d_result, sizeof(nrs_sc_result), cudaMemcpyDeviceToHost, ctx->stream));
     if (dist_out && n_items)
@@ -1458,13 +1310,117 @@ int nrs_sc_query_all(nrs_sc_db *db, const double *query_host, int first, int las
 int nrs_sc_query_dev(nrs_sc_db *db, const double *query_dev, int first, int last,
                      int32_t idx_offset, nrs_sc_result *result_dev)
 {
-    NRS_CHECK_ARG(db && query_dev && result_dev, "bad argument");
+    return nrs_sc_query_batch_dev(db, query_dev, 1, first, last, idx_offset, result_dev);
+}
+
+// Q searches enqueued on the context stream: one launch of the bit-mask kernel when every stored keyframe is
+// {0,c} (a general-valued query is still answered exactly there, on its slow path), else Q launches of the
+// f32-filter kernel
+static int batch_dev_locked(nrs_sc_db *db, const double *queries_dev, int Q, int first, int last, int idx_scale,
+                            int32_t idx_offset, nrs_sc_result *results_dev, bool sharded)
+{
+    nrs_ctx *ctx = db->ctx;
+    const int n_items = std::max(0, last - first);
+    for (int done = 0; done < Q; done += XCHG_QCAP) {
+        const int q = std::min(XCHG_QCAP, Q - done);
+        if (db_bin_ok(db)) {
+            XchgView xv = XV_NONE;
+            if (sharded) xv = XchgView{db->x_peers_dev, db->x_world, db->x_rank, ++db->x_epoch, db->x_timeout_cycles};
+            int rc = nrs_sc::bin_launch(db, queries_dev + (size_t)done * DESC, q, nullptr, first, n_items, idx_scale, idx_offset,
+                                        results_dev + done, xv);
+            if (rc) return rc;
+        } else {
+            for (int i = 0; i < q; ++i) {
+                XchgView xv = XV_NONE;
+                if (sharded) xv = XchgView{db->x_peers_dev, db->x_world, db->x_rank, ++db->x_epoch, db->x_timeout_cycles};
+                int rc = launch_search(ctx, view_of(db), queries_dev + (size_t)(done + i) * DESC, nullptr, first, n_items, idx_offset,
+                                       nullptr, nullptr, db->d_block, db->d_state, results_dev + done + i, db->max_blocks,
+                                       idx_scale, xv);
+                if (rc) return rc;
+            }
+        }
+    }
+    return NRS_OK;
+}
+
+int nrs_sc_query_batch_dev(nrs_sc_db *db, const double *queries_dev, int Q, int first, int last,
+                           int32_t idx_offset, nrs_sc_result *results_dev)
+{
+    NRS_CHECK_ARG(db && queries_dev && results_dev && Q >= 1, "bad argument");
     std::lock_guard<std::mutex> lk(db->mu);
     NRS_CHECK_ARG(first >= 0 && last <= db->size, "search range outside the database");
+    std::lock_guard<std::mutex> lk2(db->ctx->mu);
     NRS_CUDA(cudaSetDevice(db->ctx->device));
-    return launch_search(db->ctx, view_of(db), query_dev, nullptr, first, std::max(0, last - first),
-                         idx_offset, nullptr, nullptr, db->d_block, db->d_state, result_dev,
-                         db->max_blocks);
+    return batch_dev_locked(db, queries_dev, Q, first, last, 1, idx_offset, results_dev, false);
+}
+
+int nrs_sc_query_batch_dev_sharded(nrs_sc_db *db, const double *queries_dev, int Q, int first, int last,
+                                   nrs_sc_result *results_dev)
+{
+    NRS_CHECK_ARG(db && queries_dev && results_dev && Q >= 1, "bad argument");
+    std::lock_guard<std::mutex> lk(db->mu);
+    NRS_CHECK_ARG(db->x_ready, "exchange not opened (nrs_sc_xchg_create / nrs_sc_xchg_open)");
+    NRS_CHECK_ARG(first >= 0 && last <= db->size, "search range outside the database");
+    std::lock_guard<std::mutex> lk2(db->ctx->mu);
+    NRS_CUDA(cudaSetDevice(db->ctx->device));
+    return batch_dev_locked(db, queries_dev, Q, first, last, db->x_world, db->x_rank, results_dev, true);
+}
+
+int nrs_sc_query_batch(nrs_sc_db *db, const double *queries_host, int Q, int first, int last,
+                       nrs_sc_result *results_host)
+{
+    NRS_CHECK_ARG(db && queries_host && results_host && Q >= 1, "bad argument");
+    std::lock_guard<std::mutex> lk(db->mu);
+    NRS_CHECK_ARG(first >= 0 && last <= db->size, "search range outside the database");
+    nrs_ctx *ctx = db->ctx;
+    std::lock_guard<std::mutex> lk2(ctx->mu);
+    NRS_CUDA(cudaSetDevice(ctx->device));
+    const int n_items = std::max(0, last - first);
+    for (int done = 0; done < Q; done += XCHG_QCAP) {
+        const int q = std::min(XCHG_QCAP, Q - done);
+        const double *src = queries_host + (size_t)done * DESC;
+        // straight from the caller's buffer (true DMA when it is pinned, driver-staged when pageable)
+        NRS_CUDA(cudaMemcpyAsync(db->d_queries, src, (size_t)q * DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        bool all_bin = db_bin_ok(db);
+        for (int i = 0; all_bin && i < q; ++i) all_bin = host_query_is_binary(src + (size_t)i * DESC);
+        int rc = NRS_OK;
+        if (all_bin) {
+            rc = nrs_sc::bin_launch(db, db->d_queries, q, nullptr, first, n_items, 1, 0, db->d_results, XV_NONE);
+        } else {
+            for (int i = 0; i < q && !rc; ++i)
+                rc = launch_search(ctx, view_of(db), db->d_queries + (size_t)i * DESC, nullptr, first, n_items, 0, nullptr, nullptr,
+                                   db->d_block, db->d_state, db->d_results + i, db->max_blocks);
+        }
+        if (rc) return rc;
+        NRS_CUDA(cudaMemcpyAsync(results_host + done, db->d_results, (size_t)q * sizeof(nrs_sc_result), cudaMemcpyDeviceToHost, ctx->stream));
+        NRS_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return NRS_OK;
+}
+
+int nrs_sc_db_set_search_mode(nrs_sc_db *db, int mode)
+{
+    NRS_CHECK_ARG(db && (mode == 0 || mode == 1), "mode must be 0 (auto) or 1 (general-valued kernel only)");
+    std::lock_guard<std::mutex> lk(db->mu);
+    db->search_mode = mode;
+    return NRS_OK;
+}
+
+int nrs_sc_db_is_binary(nrs_sc_db *db)
+{
+    if (!db) return NRS_EINVAL;
+    std::lock_guard<std::mutex> lk(db->mu);
+    return db->n_general == 0 ? 1 : 0;
+}
+
+int nrs_sc_bin_record_bytes(void) { return BIN_WORDS * (int)sizeof(unsigned int); }
+
+int nrs_sc_xchg_set_timeout_ms(nrs_sc_db *db, int ms)
+{
+    NRS_CHECK_ARG(db && ms >= 1, "bad argument");
+    std::lock_guard<std::mutex> lk(db->mu);
+    db->x_timeout_cycles = (long long)ms * 2000000ll;      // ~2 GHz SM clock
+    return NRS_OK;
 }
 
 // enqueue the two k-NN kernels: d_key (20 floats, device) against ring keys [first, last)
@@ -1531,8 +1487,11 @@ int nrs_sc_detect_knn(nrs_sc_db *db, const double *query_host, int first, int la
     if (rc) return rc;
     // the k ids stay on the device and feed the candidate search directly (Scancontext.cpp:380-396)
     const int32_t *d_cand = reinterpret_cast<const int32_t *>(db->d_knn_out + 32);
-    rc = launch_search(ctx, view_of(db), db->d_query, d_cand, 0, k, 0, nullptr, nullptr, db->d_block, db->d_state,
-                       db->d_result, db->max_blocks);
+    if (db_bin_ok(db) && host_query_is_binary(query_host))
+        rc = nrs_sc::bin_launch(db, db->d_query, 1, d_cand, 0, k, 1, 0, db->d_result, XV_NONE);
+    else
+        rc = launch_search(ctx, view_of(db), db->d_query, d_cand, 0, k, 0, nullptr, nullptr, db->d_block, db->d_state,
+                           db->d_result, db->max_blocks);
     if (rc) return rc;
     NRS_CUDA(cudaMemcpyAsync(db->h_result, db->d_result, sizeof(nrs_sc_result), cudaMemcpyDeviceToHost, ctx->stream));
     float h[32];
@@ -1552,7 +1511,7 @@ int nrs_sc_xchg_create(nrs_sc_db *db, int world, int rank, unsigned char *handle
     std::lock_guard<std::mutex> lk(db->mu);
     NRS_CHECK_ARG(db->x_local == nullptr, "exchange already created for this database");
     NRS_CUDA(cudaSetDevice(db->ctx->device));
-    const size_t bytes = (size_t)2 * world * sizeof(XchgSlot);
+    const size_t bytes = (size_t)2 * XCHG_QCAP * world * sizeof(XchgSlot);
     NRS_CUDA(cudaMalloc(&db->x_local, bytes));
     NRS_CUDA(cudaMemset(db->x_local, 0, bytes));
     NRS_CUDA(cudaMalloc(&db->x_peers_dev, world * sizeof(XchgSlot *)));
@@ -1591,15 +1550,7 @@ int nrs_sc_xchg_open(nrs_sc_db *db, const unsigned char *handles)
 
 int nrs_sc_query_dev_sharded(nrs_sc_db *db, const double *query_dev, int first, int last, nrs_sc_result *result_dev)
 {
-    NRS_CHECK_ARG(db && query_dev && result_dev, "bad argument");
-    std::lock_guard<std::mutex> lk(db->mu);
-    NRS_CHECK_ARG(db->x_ready, "exchange not opened (nrs_sc_xchg_create / nrs_sc_xchg_open)");
-    NRS_CHECK_ARG(first >= 0 && last <= db->size, "search range outside the database");
-    NRS_CUDA(cudaSetDevice(db->ctx->device));
-    const XchgView xv{db->x_peers_dev, db->x_world, db->x_rank, ++db->x_epoch};
-    return launch_search(db->ctx, view_of(db), query_dev, nullptr, first, std::max(0, last - first),
-                         db->x_rank, nullptr, nullptr, db->d_block, db->d_state, result_dev, db->max_blocks,
-                         db->x_world, xv);
+    return nrs_sc_query_batch_dev_sharded(db, query_dev, 1, first, last, result_dev);
 }
 
 int nrs_sc_db_tail_times(nrs_sc_db *db, uint64_t *t_ns4)
@@ -1661,7 +1612,7 @@ int nrs_sc_pair(nrs_ctx *ctx, const double *sc1, const double *sc2, double *dist
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
     const size_t o_q = take(DESC * 8), o_k = take(DESC * 8), o_desc = take(DESC * 8);
     const size_t o_keys = take(KEYS_D * 8), o_frec = take(FREC_BYTES), o_surv = take(sizeof(Survivor) * (WARPS + 1));
-    const size_t o_rk = take(R * sizeof(float));
+    const size_t o_rk = take(R * sizeof(float)), o_br = take(BIN_WORDS * sizeof(unsigned int));
     const size_t o_blk = take(sizeof(BlockResult)), o_st = take(sizeof(SearchState)), o_res = take(sizeof(nrs_sc_result));
     const size_t o_d = take(8), o_s = take(4);
     int rc = ctx->scratch[2].reserve(off);
@@ -1679,7 +1630,8 @@ int nrs_sc_pair(nrs_ctx *ctx, const double *sc1, const double *sc2, double *dist
     if (rc) return rc;
     NRS_CUDA(cudaMemcpyAsync(d_q, sc1, DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     NRS_CUDA(cudaMemcpyAsync(d_k, sc2, DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    rc = pack_records(ctx, d_k, d_desc, d_keys, d_frec, reinterpret_cast<float *>(base + o_rk), 0, 1);
+    rc = pack_records(ctx, d_k, d_desc, d_keys, d_frec, reinterpret_cast<float *>(base + o_rk),
+                      reinterpret_cast<unsigned int *>(base + o_br), nullptr, 0, 1);
     if (rc) return rc;
     const DbView v{d_frec, d_desc, d_keys, reinterpret_cast<Survivor *>(base + o_surv)};
     rc = launch_search(ctx, v, d_q, nullptr, 0, 1, 0, d_dist, d_shift, d_block, d_state, d_res, 1);

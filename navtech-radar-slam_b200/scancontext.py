@@ -156,6 +156,35 @@ class SCDatabase:
         check(lib().nrs_sc_detect_knn(self._h, ptr(q), first, last, k, ptr(cand), C.byref(res)))
         return (res.dist, res.idx, res.shift), cand
 
+    def query_batch(self, queries, first=0, last=None):
+        """nrs_sc_query_batch: Q queries (Q,1200) against keyframes [first,last) -> [(dist, idx, shift)] * Q,
+        each exactly what query() returns; one kernel launch on a {0,c} database."""
+        q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, DESC)
+        last = len(self) if last is None else last
+        res = (ScResult * q.shape[0])()
+        check(lib().nrs_sc_query_batch(self._h, ptr(q), q.shape[0], first, last, res))
+        return [(r.dist, r.idx, r.shift) for r in res]
+
+    def query_batch_dev(self, queries_dev_ptr, Q, first, last, idx_offset, results_dev_ptr):
+        check(lib().nrs_sc_query_batch_dev(self._h, C.c_void_p(queries_dev_ptr), Q, first, last, idx_offset,
+                                           C.c_void_p(results_dev_ptr)))
+
+    def query_batch_dev_sharded(self, queries_dev_ptr, Q, first, last, results_dev_ptr):
+        """local slots [first,last); results_dev[q] = GLOBAL (dist, idx, shift) after ONE in-kernel exchange"""
+        check(lib().nrs_sc_query_batch_dev_sharded(self._h, C.c_void_p(queries_dev_ptr), Q, first, last,
+                                                   C.c_void_p(results_dev_ptr)))
+
+    def is_binary(self):
+        """True while every stored keyframe is {0,c}: searches run on the bit-mask kernel"""
+        return bool(check(lib().nrs_sc_db_is_binary(self._h)))
+
+    def set_search_mode(self, mode):
+        """0 = auto (bit-mask kernel when applicable), 1 = always the general-valued f32-filter kernel"""
+        check(lib().nrs_sc_db_set_search_mode(self._h, mode))
+
+    def set_exchange_timeout_ms(self, ms):
+        check(lib().nrs_sc_xchg_set_timeout_ms(self._h, ms))
+
     def query_dev(self, query_dev_ptr, first, last, idx_offset, result_dev_ptr):
         check(lib().nrs_sc_query_dev(self._h, C.c_void_p(query_dev_ptr), first, last, idx_offset,
                                      C.c_void_p(result_dev_ptr)))
@@ -393,6 +422,7 @@ class ShardedSCDatabase:
             self._rec_dev = torch.zeros(self.RECORD, dtype=torch.uint8, device=self.dev)
             self._all_dev = torch.zeros(self.RECORD * world, dtype=torch.uint8, device=self.dev)
             self._all_pin = torch.zeros(self.RECORD * world, dtype=torch.uint8).pin_memory()
+            self._qb_dev = self._qb_pin = self._rb_dev = self._rb_pin = self._rb_all = None   # batch staging, lazily
             self.exchange = "none" if world == 1 else "nccl"
             if world > 1 and exchange in ("auto", "peer"):
                 if enable_peer_exchange([self.db], rank, world, self.dev, group):
@@ -488,3 +518,64 @@ class ShardedSCDatabase:
         triples = [(float(recs["dist"][r]), int(recs["idx"][r]) * self.world + (r + base),
                     int(recs["shift"][r])) for r in range(n_r)]
         return best_of(triples)
+
+    # -- batched search: Q queries, ONE exchange ------------------------------------------------------
+    def _batch_buffers(self, Q):
+        torch = self._torch
+        if self._qb_dev is None or self._qb_dev.shape[0] < Q:
+            cap = max(Q, 64)
+            self._qb_dev = torch.empty((cap, DESC), dtype=torch.float64, device=self.dev)
+            self._qb_pin = torch.empty((cap, DESC), dtype=torch.float64).pin_memory()
+            self._rb_dev = torch.zeros(cap * self.RECORD, dtype=torch.uint8, device=self.dev)
+            self._rb_pin = torch.zeros(cap * self.RECORD * max(1, self.world), dtype=torch.uint8).pin_memory()
+            self._rb_all = torch.zeros(cap * self.RECORD * max(1, self.world), dtype=torch.uint8, device=self.dev)
+
+    def query_batch(self, queries, first=0, last=None):
+        """[(dist, idx, shift)] * Q over keyframes [first,last), each identical to query(); identical on every
+        rank.  One GPU: nrs_sc_query_batch.  Sharded on GPUs: nrs_sc_query_batch_dev_sharded (one launch, the
+        per-query records exchanged in-kernel over peer memory, merged once).  Otherwise one all_gather of
+        the Q records per rank and best_of() per query."""
+        torch, dist = self._torch, self._dist
+        last = self.n_total if last is None else last
+        qs = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, DESC)
+        Q = qs.shape[0]
+        rec_t = [("dist", "<f8"), ("idx", "<i4"), ("shift", "<i4")]
+        if self.world == 1 and self.db is not None:
+            return self.db.query_batch(qs, max(first, 0), max(first, min(last, self._local_n)))
+        lo, hi = local_range(first, last, self.rank, self.world)
+        hi = min(hi, self._local_n)
+        if self.db is None:
+            # CPU test double: per-query local search, one collective for the whole batch
+            recs = np.zeros(Q, dtype=rec_t)
+            for k in range(Q):
+                recs["dist"][k], recs["idx"][k], recs["shift"][k] = self._ext_search(qs[k], lo, hi)
+            mine = torch.from_numpy(recs.view(np.uint8).copy())
+            outs = [torch.zeros(Q * self.RECORD, dtype=torch.uint8) for _ in range(self.world)]
+            dist.all_gather(outs, mine, group=self.group)
+            allr = [o.numpy().view(rec_t) for o in outs]
+            return [best_of([(float(allr[r]["dist"][k]), int(allr[r]["idx"][k]) * self.world + r, int(allr[r]["shift"][k]))
+                             for r in range(self.world)]) for k in range(Q)]
+        self._batch_buffers(Q)
+        self._qb_pin[:Q].copy_(torch.from_numpy(qs))
+        nb = Q * self.RECORD
+        with torch.cuda.stream(self._nrs_stream):
+            self._qb_dev[:Q].copy_(self._qb_pin[:Q], non_blocking=True)
+            if self.exchange == "peer":
+                self.db.query_batch_dev_sharded(self._qb_dev.data_ptr(), Q, lo, hi, self._rb_dev.data_ptr())
+                self._rb_pin[:nb].copy_(self._rb_dev[:nb], non_blocking=True)
+        if self.exchange == "peer":
+            self._nrs_stream.synchronize()
+            r = self._rb_pin[:nb].numpy().view(rec_t)
+            if np.any(r["idx"] == -2):
+                raise RuntimeError("sharded ScanContext batch: a peer rank did not answer within the exchange timeout")
+            return [(float(r["dist"][k]), int(r["idx"][k]), int(r["shift"][k])) for k in range(Q)]
+        with torch.cuda.stream(self._nrs_stream):
+            self.db.query_batch_dev(self._qb_dev.data_ptr(), Q, lo, hi, 0, self._rb_dev.data_ptr())
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_stream(self._nrs_stream)
+        dist.all_gather_into_tensor(self._rb_all[: nb * self.world], self._rb_dev[:nb], group=self.group)
+        self._rb_pin[: nb * self.world].copy_(self._rb_all[: nb * self.world], non_blocking=True)
+        cur.synchronize()
+        allr = self._rb_pin[: nb * self.world].numpy().view(rec_t).reshape(self.world, Q)
+        return [best_of([(float(allr[r]["dist"][k]), int(allr[r]["idx"][k]) * self.world + r, int(allr[r]["shift"][k]))
+                         for r in range(self.world)]) for k in range(Q)]

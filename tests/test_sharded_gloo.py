@@ -58,6 +58,13 @@ def _worker(rank, world, port, out_q):
         got = sdb.query(q, a, b)
         _, _, exp = O.sc_search(q, db, a, b, want_all=False)
         results.append((got, exp))
+    # batched: one collective for the whole batch, per-query merge
+    qs = np.stack([db[rev[k][0]] for k in range(9)] + [db[7], np.zeros(1200)])
+    for a, b in ((0, 290), (8, 301), (0, 0)):
+        got = sdb.query_batch(qs, a, b)
+        for k in range(qs.shape[0]):
+            _, _, exp = O.sc_search(qs[k], db, a, b, want_all=False)
+            results.append((got[k], exp))
     out_q.put((rank, results))
     dist.barrier()
     dist.destroy_process_group()

@@ -27,7 +27,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_q):
+def _worker(rank, world, port, out_q, binary=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -39,7 +39,7 @@ def _worker(rank, world, port, out_q):
     from oracle import pyoracle as O
     sc = nrs.scancontext
     ctx = nrs.Context(rank)
-    db, rev = synth.sc_database(3001, 200, seed=17, binary=False)
+    db, rev = synth.sc_database(3001, 200, seed=17, binary=binary)
     db[2500] = db[7]
     db[2601] = db[7]          # exact ties across shards: lowest global index must win on every rank
     sdb = sc.ShardedSCDatabase(rank, world, ctx=ctx, exchange="peer")
@@ -68,6 +68,25 @@ def _worker(rank, world, port, out_q):
     for k in range(64):
         _, _, exp = O.sc_search(db[rev[k][0]], db, 0, 2900, want_all=False)
         results.append(((float(recs["dist"][k]), int(recs["idx"][k]), int(recs["shift"][k])), exp))
+    # batched: Q queries, one launch, ONE exchange (per-query records travel, merged once per launch)
+    qs = np.stack([db[j] for j, _, _ in rev[:70]] + [db[7], np.zeros(1200)])
+    for a, b in ((0, 2900), (8, 3001), (0, 0), (2, 3)):
+        got = sdb.query_batch(qs, a, b)
+        for k in range(qs.shape[0]):
+            _, _, exp = O.sc_search(qs[k], db, a, b, want_all=False)
+            results.append((got[k], exp))
+    # back-to-back batched launches of different sizes without host synchronisation (slot reuse by parity)
+    outb = torch.zeros(6 * 64 * 16, dtype=torch.uint8, device=dev)
+    sizes = [64, 1, 17, 64, 3, 64]
+    with torch.cuda.stream(stream):
+        for i, n in enumerate(sizes):
+            sdb.db.query_batch_dev_sharded(qd.data_ptr(), n, lo, hi, outb.data_ptr() + i * 64 * 16)
+    stream.synchronize()
+    recb = outb.cpu().numpy().view([("dist", "<f8"), ("idx", "<i4"), ("shift", "<i4")]).reshape(6, 64)
+    for i, n in enumerate(sizes):
+        for k in range(n):
+            _, _, exp = O.sc_search(db[rev[k][0]], db, 0, 2900, want_all=False)
+            results.append(((float(recb["dist"][i, k]), int(recb["idx"][i, k]), int(recb["shift"][i, k])), exp))
     out_q.put((rank, results))
     dist.barrier()
     torch.cuda.synchronize()
@@ -80,12 +99,15 @@ def _worker(rank, world, port, out_q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
-def test_peer_exchange_matches_single_scan():
+@pytest.mark.parametrize("binary", [False, True])
+def test_peer_exchange_matches_single_scan(binary):
+    """binary=False: general-valued descriptors (f32-filter kernel); binary=True: {0,3.0} descriptors (bit-mask
+    kernel, batched launches with one exchange)."""
     world = min(torch.cuda.device_count(), 4)
     mpc = mp.get_context("spawn")
     q = mpc.Queue()
     port = _free_port()
-    procs = [mpc.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [mpc.Process(target=_worker, args=(r, world, port, q, binary)) for r in range(world)]
     for p in procs:
         p.start()
     got = [q.get(timeout=300) for _ in range(world)]
