@@ -16,13 +16,32 @@ _REF = os.path.join(_HERE, "_ref", "libref_kdtree.so")
 RINGS, SECTORS, DESC = 20, 60, 1200
 
 
+def _cpu_id():
+    """model name + flags of this host's CPU: the library is built -march=native, so a copy that travelled from
+    another machine is rebuilt (seconds)."""
+    try:
+        txt = open("/proc/cpuinfo").read()
+        model = next((l.split(":", 1)[1].strip() for l in txt.splitlines() if l.startswith("model name")), "?")
+        flags = next((l.split(":", 1)[1].strip() for l in txt.splitlines() if l.startswith("flags")), "?")
+        import hashlib
+        return model + " " + hashlib.sha1(flags.encode()).hexdigest()[:12]
+    except Exception:
+        return "unknown"
+
+
 def build(force=False):
     """Compile the C restatement (gcc, seconds).  Also builds oracle/_ref when /root/reference
-    exists (this container); on the GPU box the prebuilt files are used as they travelled."""
-    if force or not os.path.exists(_LIB) or any(
+    exists (this container); on the GPU box the prebuilt _ref files are used as they travelled."""
+    stamp = os.path.join(_HERE, "_build", ".cpu")
+    same_cpu = os.path.exists(stamp) and open(stamp).read() == _cpu_id()
+    if force or not same_cpu or not os.path.exists(_LIB) or any(
             os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB)
-            for f in os.listdir(_HERE) if f.endswith(".c")):
+            for f in os.listdir(_HERE) if f.endswith(".c") or f == "Makefile"):
+        if not same_cpu:
+            subprocess.call(["make", "-s", "-C", _HERE, "clean"])
         subprocess.check_call(["make", "-s", "-C", _HERE, "all"])
+        with open(stamp, "w") as f:
+            f.write(_cpu_id())
     if os.path.isdir("/root/reference/pgo/SC-A-LOAM/include/scancontext"):
         subprocess.check_call(["make", "-s", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
