@@ -168,6 +168,27 @@ int nrs_sc_query_batch_dev_sharded(nrs_sc_db *db, const double *queries_dev, int
                                    nrs_sc_result *results_dev);
 /* how long the merge waits for a peer's records before reporting idx == -2 (default ~3000 ms) */
 int nrs_sc_xchg_set_timeout_ms(nrs_sc_db *db, int ms);
+
+/* The collective form (north_star: "one NCCL all-reduce of the per-shard min distance over NVLink",
+ * SURVEY 8e): local search on every rank, ncclAllReduce(min) on the f64 distances, then ncclAllReduce(min)
+ * on int64 (global idx << 8 | shift) where only ranks whose distance equals the global minimum contribute
+ * (the others send INT64_MAX) -- ties resolve to the lowest global index like the sequential scan
+ * (Scancontext.cpp:380-396).  libnccl.so.2 is opened at run time (dlopen); NRS_ENCCL when it is missing or
+ * a call fails.  nrs_nccl_get_unique_id: rank 0 creates the 128-byte id, the host distributes it (any
+ * channel) and every rank calls nrs_sc_nccl_init (collective, blocks until all ranks joined);
+ * nrs_sc_nccl_attach uses a communicator the host already owns (ncclComm_t, not destroyed here). */
+#define NRS_NCCL_UNIQUE_ID_BYTES 128
+int nrs_nccl_available(void);
+int nrs_nccl_get_unique_id(unsigned char *id_out_128);
+int nrs_sc_nccl_init(nrs_sc_db *db, int world, int rank, const unsigned char *unique_id_128);
+int nrs_sc_nccl_attach(nrs_sc_db *db, void *nccl_comm, int world, int rank);
+int nrs_sc_query_batch_dev_nccl(nrs_sc_db *db, const double *queries_dev, int Q, int first, int last,
+                                nrs_sc_result *results_dev);
+/* Host queries in, host records out over local slots [first,last): the sharded search as a C++ host calls
+ * it (detectLoopClosureID on a keyframe-sharded SCManager).  Uses the peer-memory exchange when
+ * nrs_sc_xchg_open succeeded, else the NCCL reduction above.  Identical records on every rank. */
+int nrs_sc_query_batch_sharded(nrs_sc_db *db, const double *queries_host, int Q, int first, int last,
+                               nrs_sc_result *results_host);
 /* diagnostics: %globaltimer (ns) stamps of the database's most recent search, taken by its last
  * CTA: [0] tail entered, [1] local result ready, [2] record + flag written to the peers
  * (sharded queries only), [3] result written.  Synchronises the stream. */

@@ -129,6 +129,12 @@ def _declare(L):
     L.nrs_sc_query_batch_dev.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     L.nrs_sc_query_batch_dev_sharded.argtypes = [vp, vp, i32, i32, i32, vp]
     L.nrs_sc_xchg_set_timeout_ms.argtypes = [vp, i32]
+    L.nrs_nccl_available.argtypes = []
+    L.nrs_nccl_get_unique_id.argtypes = [vp]
+    L.nrs_sc_nccl_init.argtypes = [vp, i32, i32, vp]
+    L.nrs_sc_nccl_attach.argtypes = [vp, vp, i32, i32]
+    L.nrs_sc_query_batch_dev_nccl.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.nrs_sc_query_batch_sharded.argtypes = [vp, vp, i32, i32, i32, vp]
     L.nrs_sc_db_is_binary.argtypes = [vp]
     L.nrs_sc_db_set_search_mode.argtypes = [vp, i32]
     L.nrs_sc_bin_record_bytes.argtypes = []

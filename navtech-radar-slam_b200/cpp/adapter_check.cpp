@@ -27,6 +27,7 @@ struct MiniCloud { std::vector<MiniPoint> points; };
 using SCManager = nrs::SCManagerT<MiniMatrix, MiniCloud>;
 using RadarLoader = nrs::RadarLoaderT<MiniMatrix>;
 using ORORA = nrs::ORORAT<MiniMatrix>;
+using NonMinimalSolver = nrs::NonMinimalSolverT<MiniMatrix>;
 
 int main()
 {
@@ -76,6 +77,48 @@ int main()
     std::printf("ORORA: M = %d, yaw = %.5f (true %.5f), t = (%.3f, %.3f)\n", est.getNumMaxCliqueInliers(),
                 std::atan2(T(1, 0), T(0, 0)), th, T(0, 3), T(1, 3));
     if (std::fabs(std::atan2(T(1, 0), T(0, 0)) - th) > 1e-3 || std::fabs(T(0, 3) - tx) > 0.05) return 1;
+    // feat_compensated_ is filled like ORORA.hpp:56-65 (first call: velocity 0 -> equal to feat_in_cart_), the
+    // inlier clouds come back like ORORA.hpp:153-161
+    if (pm.feat_compensated_.cols() != N || cm.feat_compensated_(1, 7) != curr(1, 7)) { std::printf("feat_compensated_ not set\n"); return 1; }
+    {
+        auto cl = est.getMaxCliques();
+        auto fi = est.getFinalInliers();
+        const size_t M = std::get<0>(cl).points.size();
+        std::printf("ORORA::getMaxCliques: %zu pairs, getFinalInliers: %zu pairs\n", M, std::get<0>(fi).points.size());
+        if ((int)M != est.getNumMaxCliqueInliers() || std::get<1>(cl).points.size() != M || M < 150) return 1;
+        if (std::get<0>(fi).points.size() != est.getFinalInliersIndices().size()) return 1;
+    }
+    // second call: the Doppler velocity of the first pose enters (ORORA.hpp:42,56-61,89)
+    {
+        ORORA::RadarFeature pm2, cm2;
+        pm2.feat_in_cart_ = prev; cm2.feat_in_cart_ = curr;
+        MiniMatrix T2 = est.calcTransform(params, 0.25, pm2, cm2);
+        if (cm2.feat_compensated_(0, 5) == curr(0, 5)) { std::printf("Doppler compensation did not move the points\n"); return 1; }
+        if (std::fabs(std::atan2(T2(1, 0), T2(0, 0)) - th) > 5e-3) return 1;
+    }
+    // the solver class on its own: reset / setInputSource / setInputTarget / computeTransformation / getters
+    // (nonminimal_solver.hpp:171-178,665-892) must reproduce calcTransform's first pose (no Doppler at velocity 0)
+    {
+        NonMinimalSolver solver(ctx);
+        solver.reset(params, 0.1, 9.0 * M_PI / 180.0);
+        solver.setInputSource(curr);
+        solver.setInputTarget(prev);
+        MiniMatrix guess(4, 4), out(4, 4);
+        solver.computeTransformation(guess, out);
+        if (!solver.solution_.valid || out(0, 3) != T(0, 3) || out(1, 0) != T(1, 0)) { std::printf("NonMinimalSolver differs from ORORA\n"); return 1; }
+        if (solver.getNumMaxCliqueInliers() != est.getNumMaxCliqueInliers() && solver.getNumMaxCliqueInliers() < 150) return 1;
+        if ((int)solver.getFinalInliersIndices().size() < solver.getNumRotaionInliers() / 2) return 1;
+        std::printf("NonMinimalSolver: M = %d, rotation inliers %d, final inliers %zu\n", solver.getNumMaxCliqueInliers(),
+                    solver.getNumRotaionInliers(), solver.getFinalInliersIndices().size());
+    }
+    // stop-motion gate (ORORA.hpp:74-79): more than the threshold of matches -> Identity, solver untouched
+    {
+        ORORA gate("mulran", "rot", true, false, true, 100, 0.049, 0.1, 9.0 * M_PI / 180.0, ctx);
+        ORORA::RadarFeature a, b;
+        a.feat_in_cart_ = prev; b.feat_in_cart_ = curr;
+        MiniMatrix Tg = gate.calcTransform(params, 0.25, a, b);
+        if (!gate.stopMotionDetected() || Tg(0, 3) != 0.0 || Tg(0, 0) != 1.0) { std::printf("stop-motion gate\n"); return 1; }
+    }
     try { RadarLoader bad("kitti", "cen2019", 0.6, true, false, ctx); return 1; } catch (const std::invalid_argument &) {}
     RadarLoader loader("mulran", "cen2019", 0.6, true, false, ctx);
     (void)loader;
@@ -95,6 +138,36 @@ int main()
         }
         std::printf("SCManager (kd-tree mode): %d loops found\n", ok);
         if (ok < 5) return 1;
+    }
+    // detectLoopClosureIDBetweenSession (Scancontext.cpp:267-328): the batch tree is built once, over the keys
+    // present at the FIRST call; keyframes saved later are never searched
+    {
+        for (int mode = 0; mode < 2; ++mode) {
+            SCManager ms(ctx);
+            ms.use_tree_candidates = mode == 1;
+            ms.setSCdistThres(0.45);
+            for (int k = 0; k < 5; ++k) ms.makeAndSaveScancontextAndKeys(clouds[k]);
+            MiniMatrix q5 = ms.makeScancontext(clouds[5]), q2 = ms.makeScancontext(clouds[2]);
+            MiniMatrix rk = ms.makeRingkeyFromScancontext(q2);
+            std::vector<float> key2(rk.data(), rk.data() + 20);
+            MiniMatrix rk5 = ms.makeRingkeyFromScancontext(q5);
+            std::vector<float> key5(rk5.data(), rk5.data() + 20);
+            auto r2 = ms.detectLoopClosureIDBetweenSession(key2, q2);        // first call: tree over keyframes 0..4
+            if (r2.first != 2 || r2.second != 0.0f) { std::printf("between-session (mode %d): expected keyframe 2, got %d\n", mode, r2.first); return 1; }
+            ms.makeAndSaveScancontextAndKeys(clouds[5]);                     // appended after the batch tree was made
+            auto r5 = ms.detectLoopClosureIDBetweenSession(key5, q5);
+            if (r5.first == 5) { std::printf("between-session (mode %d): searched a keyframe outside the batch tree\n", mode); return 1; }
+        }
+        // fewer stored keyframes than candidates: the reference evaluates its zero-initialised ids (index 0)
+        SCManager one(ctx);
+        one.use_tree_candidates = true;
+        one.setSCdistThres(0.45);
+        one.makeAndSaveScancontextAndKeys(clouds[3]);
+        MiniMatrix q3 = one.makeScancontext(clouds[3]);
+        MiniMatrix rk = one.makeRingkeyFromScancontext(q3);
+        std::vector<float> key3(rk.data(), rk.data() + 20);
+        if (one.detectLoopClosureIDBetweenSession(key3, q3).first != 0) { std::printf("between-session with one keyframe\n"); return 1; }
+        std::printf("detectLoopClosureIDBetweenSession ok\n");
     }
     // cen2018features / cen2019features as free functions on a small synthetic polar image
     {

@@ -291,6 +291,13 @@ struct nrs_sc_db {
     unsigned int   x_epoch = 0;
     bool           x_ready = false;
     long long      x_timeout_cycles = nrs_sc::XCHG_TIMEOUT_CYCLES;
+    // collective exchange (sc_nccl.cu): communicator, staging for the two min all-reduces
+    void          *n_comm = nullptr;
+    bool           n_owned = false;
+    int            n_world = 1, n_rank = 0;
+    double        *n_dist = nullptr;     // [0,QCAP) local, [QCAP,2 QCAP) reduced
+    long long     *n_key = nullptr;
+    nrs_sc_result *d_results2 = nullptr; // host-pointer sharded entry point's device records
 };
 
 namespace nrs_sc {
@@ -298,4 +305,9 @@ namespace nrs_sc {
 // (or the candidate list) on the database's stream; every keyframe in range must be {0,c} (db->n_general == 0)
 int bin_launch(nrs_sc_db *db, const double *d_queries, int Q, const int32_t *d_cand, int first, int n_items,
                int idx_scale, int idx_offset, nrs_sc_result *d_results, XchgView xv);
+// Q searches enqueued on the context stream (db->mu and ctx->mu held by the caller): reported index =
+// local slot * idx_scale + idx_offset; sharded = exchange the per-query records over peer memory in-kernel
+int batch_dev_locked(nrs_sc_db *db, const double *queries_dev, int Q, int first, int last, int idx_scale,
+                     int32_t idx_offset, nrs_sc_result *results_dev, bool sharded);
+void nccl_release(nrs_sc_db *db);
 }

@@ -1104,6 +1104,7 @@ int nrs_sc_db_destroy(nrs_sc_db *db)
     cudaFree(db->d_desc); cudaFree(db->d_keys); cudaFree(db->d_frec); cudaFree(db->d_surv);
     cudaFree(db->d_block); cudaFree(db->d_state);
     cudaFree(db->d_rkeys); cudaFree(db->d_knn_pd); cudaFree(db->d_knn_pi); cudaFree(db->d_knn_out);
+    nrs_sc::nccl_release(db);
     for (void *m : db->x_opened) if (m) cudaIpcCloseMemHandle(m);
     cudaFree(db->x_local); cudaFree(db->x_peers_dev);
     cudaFree(db->d_result); cudaFree(db->d_query);
@@ -1316,8 +1317,9 @@ int nrs_sc_query_dev(nrs_sc_db *db, const double *query_dev, int first, int last
 // Q searches enqueued on the context stream: one launch of the bit-mask kernel when every stored keyframe is
 // {0,c} (a general-valued query is still answered exactly there, on its slow path), else Q launches of the
 // f32-filter kernel
-static int batch_dev_locked(nrs_sc_db *db, const double *queries_dev, int Q, int first, int last, int idx_scale,
-                            int32_t idx_offset, nrs_sc_result *results_dev, bool sharded)
+}  // extern "C"
+int nrs_sc::batch_dev_locked(nrs_sc_db *db, const double *queries_dev, int Q, int first, int last, int idx_scale,
+                             int32_t idx_offset, nrs_sc_result *results_dev, bool sharded)
 {
     nrs_ctx *ctx = db->ctx;
     const int n_items = std::max(0, last - first);
@@ -1342,6 +1344,8 @@ static int batch_dev_locked(nrs_sc_db *db, const double *queries_dev, int Q, int
     }
     return NRS_OK;
 }
+
+extern "C" {
 
 int nrs_sc_query_batch_dev(nrs_sc_db *db, const double *queries_dev, int Q, int first, int last,
                            int32_t idx_offset, nrs_sc_result *results_dev)

@@ -499,6 +499,14 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
                 const int bp = br->pos;
                 if (better(bd, bp, d, p)) { d = bd; p = bp; ix = br->idx; sh = br->shift; }
             }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {            // lanes hold different tiles: combine them
+                const double od = __shfl_xor_sync(0xffffffffu, d, off);
+                const int op = __shfl_xor_sync(0xffffffffu, p, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, ix, off);
+                const int os = __shfl_xor_sync(0xffffffffu, sh, off);
+                if (better(od, op, d, p)) { d = od; p = op; ix = oi; sh = os; }
+            }
         }
         if (lane == 0) { sm.red_d[warp] = d; sm.red_pos[warp] = p; sm.red_idx[warp] = ix; sm.red_s[warp] = sh; }
         __syncthreads();

@@ -118,3 +118,28 @@ def test_peer_exchange_matches_single_scan(binary):
         for res, exp in results:
             assert res == exp, (rank, res, exp)
     assert all(g[1] == got[0][1] for g in got)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("mode", ["peer", "nccl"])
+def test_cpp_sharded_manager(mode, tmp_path):
+    """The C++ multi-GPU host (navtech-radar-slam_b200/cpp/sharded_check.cpp: ShardedSCManagerT, one process per
+    GPU, handles / NCCL id exchanged through files): detectLoopClosureID and batched searches identical to the
+    single-GPU SCManager on every rank, with the in-kernel peer exchange and with the two NCCL min all-reduces."""
+    import subprocess
+    world = min(torch.cuda.device_count(), 4)
+    exe = os.path.join(ROOT, "navtech-radar-slam_b200", "cpp", "sharded_check")
+    args = [str(world), str(tmp_path)] + (["nccl"] if mode == "nccl" else [])
+    procs = [subprocess.Popen([exe, str(r)] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = []
+    for p in procs:
+        try:
+            o, _ = p.communicate(timeout=300)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append(o)
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r}:\n{o}"
+        assert "sharded manager ok" in o and (f"({mode} exchange" in o), o
