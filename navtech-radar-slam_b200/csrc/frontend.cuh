@@ -11,6 +11,7 @@ namespace nrs {
 constexpr int FE_MAX_AZ = 1024;          // azimuth rows supported (Navtech: 400)
 constexpr int FE_KP_CAP = 16384;         // >= max_points (10000): one keypoint per marked region at most
 constexpr int FE_PATTERN = 512;          // rBRIEF sample points (256 pairs)
+constexpr int FE_SUB_CAP = 65536;        // cen2019: capacity of the top-candidate subset (>= 4 x max_points regions)
 
 struct FrameCounts {
     int   n_cand;        // pixels with h > mean_h
@@ -25,6 +26,10 @@ struct FrameCounts {
     float mean_h;
     float cart_max;
     int   overflow;      // a capacity was exceeded (reported as NRS_ECAPACITY)
+    int   n_sub;         // top-candidate subset: pixels with h >= the carried threshold (0 in full-sort mode)
+    int   n_sorted;      // candidates in the sorted list the marking loop walked (== n_cand in full-sort mode)
+    int   need_full;     // the subset could not prove the marking loop's outcome: redo with the full sort
+    int   pad_;
 };
 
 struct FrontendState {
@@ -56,6 +61,9 @@ struct FrontendState {
     long long *d_times = nullptr;        // R
     FrameCounts *d_counts = nullptr;
     FrameCounts *h_counts = nullptr;     // pinned
+    // cen2019 top-candidate subset: threshold on h carried from frame to frame (device), valid once a frame ran
+    float *d_thresh = nullptr;
+    bool   have_thresh = false;
     // voxel scratch
     unsigned int *d_vkey[2] = {nullptr, nullptr};
     unsigned int *d_vval[2] = {nullptr, nullptr};

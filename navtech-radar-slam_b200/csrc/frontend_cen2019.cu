@@ -25,6 +25,7 @@
 //                                       getMaxInRegion's int-truncated running max, ordered emission.
 // Bound: HBM (R*C*4 = 5.4 MB per frame plus the sort's passes); DESIGN.md gives the byte counts.
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <float.h>
 #include <math.h>
 #include <string.h>
@@ -167,7 +168,7 @@ __global__ void fe_claim_kernel(const unsigned int *__restrict__ sorted_vals,
                                 const FrameCounts *__restrict__ cnt, unsigned int *__restrict__ claim)
 {
     const unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= (unsigned int)cnt->n_cand) return;
+    if (k >= (unsigned int)cnt->n_sorted) return;
     const unsigned int e = sorted_vals[k];
     const int a = e / C, r = e - a * C;
     const float *row = fft + (size_t)a * C;
@@ -186,7 +187,7 @@ __global__ void fe_incr_kernel(const unsigned int *__restrict__ sorted_vals,
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= N) return;
     unsigned int fresh = 0;
-    if (k < (size_t)cnt->n_cand) {
+    if (k < (size_t)cnt->n_sorted) {
         const unsigned int e = sorted_vals[k];
         const int a = e / C, r = e - a * C;
         const float *row = fft + (size_t)a * C;
@@ -206,12 +207,83 @@ __global__ void fe_jstar_kernel(const unsigned int *__restrict__ incr, const uns
 {
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= N) return;
-    if (k < (size_t)cnt->n_cand && incr[k] && cums[k] == (unsigned int)max_points) cnt->j_star = (int)k;
+    if (k < (size_t)cnt->n_sorted && incr[k] && cums[k] == (unsigned int)max_points) cnt->j_star = (int)k;
     if (k == N - 1) cnt->l_regions = min((int)cums[k], max_points);
 }
-__global__ void fe_jstar_fix_kernel(FrameCounts *__restrict__ cnt)
+// the loop ran out of candidates before max_points regions: every candidate was consumed -- which the
+// top-candidate subset can only vouch for when it held them all.  Also carries the threshold to the next frame:
+// the h value at rank ~4x the candidates this frame consumed (at least 16k, at most 48k of the 64k capacity).
+__global__ void fe_jstar_fix_kernel(FrameCounts *__restrict__ cnt, const float *__restrict__ sorted_keys,
+                                    float *__restrict__ thresh)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0 && cnt->j_star < 0) cnt->j_star = cnt->n_cand - 1;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (cnt->j_star < 0) {
+        if (cnt->n_sorted == cnt->n_cand) cnt->j_star = cnt->n_cand - 1;
+        else cnt->need_full = 1;
+    }
+    if (cnt->need_full || cnt->n_sorted <= 0) return;
+    const int want = min(max(4 * (cnt->j_star + 1), 16384), 49152);
+    if (cnt->n_sorted > want) *thresh = sorted_keys[want];
+    else if (cnt->n_sorted == cnt->n_cand) *thresh = sorted_keys[cnt->n_sorted - 1];           // everything fits: keep it all
+    else if (cnt->n_sorted >= 2 * (cnt->j_star + 1)) *thresh = sorted_keys[cnt->n_sorted - 1]; // comfortable margin: keep
+    else *thresh = cnt->mean_h + 0.5f * (sorted_keys[cnt->n_sorted - 1] - cnt->mean_h);        // thin margin: loosen
+}
+
+// ---- top-candidate subset (replaces the full-frame sort when a threshold is known) -----------------------------
+// The marking loop (features.cpp:227-249) walks the candidates in descending h and stops after max_points fresh
+// regions: only the first j_star + 1 of the ~6e5 candidates matter.  With a threshold T carried from the previous
+// frame, the pixels with h >= T are compacted IN PIXEL ORDER (cub::DeviceSelect), sorted (64k pairs instead of
+// 1.3M; stable, so ties keep pixel order exactly like the full sort) and walked.  Their ranks equal their ranks in
+// the full order, so claims, regions and j_star are identical -- provided the loop terminates inside the subset
+// (or the subset holds every candidate).  Otherwise need_full is raised and the host redoes the frame with the
+// full sort; the result never depends on T.
+struct SubSelect {
+    const float *h;
+    const float *thresh;
+    const FrameCounts *cnt;
+    __device__ __forceinline__ bool operator()(const unsigned int &e) const
+    {
+        const float hv = h[e];
+        return hv > cnt->mean_h && hv >= *thresh;
+    }
+};
+
+__global__ void __launch_bounds__(RED_THREADS)
+fe_prep_sub_kernel(const float *__restrict__ h, size_t N, FrameCounts *__restrict__ cnt, unsigned int *__restrict__ claim)
+{
+    const float mean_h = cnt->mean_h;
+    int c = 0;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < N; e += (size_t)gridDim.x * blockDim.x) {
+        c += h[e] > mean_h;                                  // features.cpp:220
+        claim[e] = 0xffffffffu;
+    }
+    typedef cub::BlockReduce<int, RED_THREADS> BR;
+    __shared__ typename BR::TempStorage tmp;
+    const int bc = BR(tmp).Sum(c);
+    if (threadIdx.x == 0 && bc) atomicAdd(&cnt->n_cand, bc);
+}
+
+__global__ void fe_sub_keys_kernel(const float *__restrict__ h, FrameCounts *__restrict__ cnt, float *__restrict__ keys,
+                                   unsigned int *__restrict__ vals)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= FE_SUB_CAP) return;
+    const int n_sub = cnt->n_sub;
+    if (k == 0) {
+        cnt->n_sorted = min(n_sub, FE_SUB_CAP);
+        if (n_sub > FE_SUB_CAP) cnt->need_full = 1;         // the first 64k in pixel order are not the top 64k
+    }
+    if (k < n_sub) {
+        const float hv = h[vals[k]];
+        keys[k] = (hv == 0.0f) ? 0.0f : hv;
+    } else {
+        keys[k] = -FLT_MAX;
+        vals[k] = 0xffffffffu;
+    }
+}
+__global__ void fe_set_sorted_full_kernel(FrameCounts *__restrict__ cnt)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) cnt->n_sorted = cnt->n_cand;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -485,7 +557,7 @@ int fe_launch_rowscan(cudaStream_t st, int *rowcount, int R, FrameCounts *cnt, i
 }
 
 int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_points, int min_range,
-                      int *d_polar, bool reset_counts)
+                      int *d_polar, bool reset_counts, bool force_full)
 {
     cudaStream_t st = ctx->stream;
     const size_t N = (size_t)R * C;
@@ -500,26 +572,42 @@ int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_poin
     NRS_LAUNCHED();
     fe_mean_kernel<<<1, 32, 0, st>>>(S.d_partial, nb, 1.0 / (double)N, &cnt->mean_h);
     NRS_LAUNCHED();
-    fe_keys_kernel<<<nb, RED_THREADS, 0, st>>>(S.d_h, N, cnt, S.d_keys[0], S.d_vals[0], S.d_claim);
-    NRS_LAUNCHED();
+    const bool sub = S.have_thresh && !force_full;
+    const size_t n_walk = sub ? (size_t)FE_SUB_CAP : N;       // length of the sorted list the marking kernels cover
     size_t need = S.cub_bytes;
+    if (sub) {
+        fe_prep_sub_kernel<<<nb, RED_THREADS, 0, st>>>(S.d_h, N, cnt, S.d_claim);
+        NRS_LAUNCHED();
+        thrust::counting_iterator<unsigned int> ids(0u);
+        NRS_CUDA(cub::DeviceSelect::If(S.d_cub, need, ids, S.d_vals[0], &cnt->n_sub, (int)N, SubSelect{S.d_h, S.d_thresh, cnt}, st));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        fe_sub_keys_kernel<<<FE_SUB_CAP / 256, 256, 0, st>>>(S.d_h, cnt, S.d_keys[0], S.d_vals[0]);
+        NRS_LAUNCHED();
+    } else {
+        fe_keys_kernel<<<nb, RED_THREADS, 0, st>>>(S.d_h, N, cnt, S.d_keys[0], S.d_vals[0], S.d_claim);
+        NRS_LAUNCHED();
+        fe_set_sorted_full_kernel<<<1, 32, 0, st>>>(cnt);
+        NRS_LAUNCHED();
+    }
+    need = S.cub_bytes;
     NRS_CUDA(cub::DeviceRadixSort::SortPairsDescending(S.d_cub, need, S.d_keys[0], S.d_keys[1], S.d_vals[0],
-                                                       S.d_vals[1], (int)N, 0, 32, st));
+                                                       S.d_vals[1], (int)n_walk, 0, 32, st));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     const int tb = 256;
-    const unsigned int gb = (unsigned int)((N + tb - 1) / tb);
+    const unsigned int gb = (unsigned int)((n_walk + tb - 1) / tb);
     fe_claim_kernel<<<gb, tb, 0, st>>>(S.d_vals[1], S.d_fft, R, C, cnt, S.d_claim);
     NRS_LAUNCHED();
-    fe_incr_kernel<<<gb, tb, 0, st>>>(S.d_vals[1], S.d_fft, R, C, cnt, S.d_claim, S.d_incr, N);
+    fe_incr_kernel<<<gb, tb, 0, st>>>(S.d_vals[1], S.d_fft, R, C, cnt, S.d_claim, S.d_incr, n_walk);
     NRS_LAUNCHED();
     need = S.cub_bytes;
-    NRS_CUDA(cub::DeviceScan::InclusiveSum(S.d_cub, need, S.d_incr, S.d_vals[0], (int)N, st));
+    NRS_CUDA(cub::DeviceScan::InclusiveSum(S.d_cub, need, S.d_incr, S.d_vals[0], (int)n_walk, st));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     NRS_CUDA(cudaMemsetAsync(&cnt->j_star, 0xff, sizeof(int), st));      // -1
-    fe_jstar_kernel<<<gb, tb, 0, st>>>(S.d_incr, S.d_vals[0], N, max_points, cnt);
+    fe_jstar_kernel<<<gb, tb, 0, st>>>(S.d_incr, S.d_vals[0], n_walk, max_points, cnt);
     NRS_LAUNCHED();
-    fe_jstar_fix_kernel<<<1, 32, 0, st>>>(cnt);
+    fe_jstar_fix_kernel<<<1, 32, 0, st>>>(cnt, S.d_keys[1], S.d_thresh);
     NRS_LAUNCHED();
+    S.have_thresh = true;
     const int sb = R;
     fe_scan_rows_kernel<false><<<sb, 256, 0, st>>>(S.d_claim, S.d_h, R, C, min_range, cnt, S.d_rowcount, nullptr, 0);
     NRS_LAUNCHED();
@@ -580,7 +668,10 @@ size_t fe_cub_bytes(size_t N)
     cub::DeviceScan::InclusiveSum(nullptr, b, (unsigned int *)nullptr, (unsigned int *)nullptr, (int)N);
     cub::DeviceRadixSort::SortPairs(nullptr, c, (unsigned int *)nullptr, (unsigned int *)nullptr, (unsigned int *)nullptr,
                                     (unsigned int *)nullptr, FE_KP_CAP);
-    return std::max(a, std::max(b, c)) + 256;
+    size_t d = 0;
+    thrust::counting_iterator<unsigned int> ids(0u);
+    cub::DeviceSelect::If(nullptr, d, ids, (unsigned int *)nullptr, (int *)nullptr, (int)N, SubSelect{nullptr, nullptr, nullptr});
+    return std::max(std::max(a, d), std::max(b, c)) + 256;
 }
 
 }  // namespace nrs

@@ -31,7 +31,7 @@
 namespace nrs {
 
 int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_points, int min_range, int *d_polar,
-                      bool reset_counts = true);
+                      bool reset_counts = true, bool force_full = false);
 int fe_cen2018_device(nrs_ctx *ctx, FrontendState &S, int R, int C, float zq, int sigma_gauss, int min_range,
                       int *d_polar, bool reset_counts, bool keep_y);
 int fe_points_voxel_bev_device(nrs_ctx *ctx, FrontendState &S, nrs_frame *f);
@@ -287,7 +287,7 @@ static void frontend_free(void *p)
     void *dev[] = {S->d_theta, S->d_sx, S->d_pattern, S->d_raw, S->d_fft, S->d_h, S->d_keys[0], S->d_keys[1],
                    S->d_vals[0], S->d_vals[1], S->d_claim, S->d_incr, S->d_partial, S->d_cart, S->d_rowbuf,
                    S->d_blur, S->d_cub, S->d_az, S->d_azsort, S->d_azidx, S->d_cossin, S->d_times, S->d_counts,
-                   S->d_vkey[0], S->d_vkey[1], S->d_vval[0], S->d_vval[1], S->d_pts32, S->d_rowcount};
+                   S->d_vkey[0], S->d_vkey[1], S->d_vval[0], S->d_vval[1], S->d_pts32, S->d_rowcount, S->d_thresh};
     for (void *d : dev) if (d) cudaFree(d);
     if (S->h_counts) cudaFreeHost(S->h_counts);
     if (S->st_img) { cudaStreamSynchronize(S->st_img); cudaStreamDestroy(S->st_img); }
@@ -342,6 +342,7 @@ static int frontend_state(nrs_ctx *ctx, const nrs_extract_params *p, int R, int 
     rc |= dmalloc(&S->d_vkey[0], FE_KP_CAP); rc |= dmalloc(&S->d_vkey[1], FE_KP_CAP);
     rc |= dmalloc(&S->d_vval[0], FE_KP_CAP); rc |= dmalloc(&S->d_vval[1], FE_KP_CAP);
     rc |= dmalloc(&S->d_pts32, 2 * FE_KP_CAP); rc |= dmalloc(&S->d_rowcount, FE_MAX_AZ);
+    rc |= dmalloc(&S->d_thresh, 1);
     if (rc) return rc;
     NRS_CUDA(cudaMallocHost((void **)&S->h_counts, sizeof(FrameCounts)));
 
@@ -508,10 +509,13 @@ int nrs_cen2019(nrs_ctx *ctx, const float *fft, int R, int C, int max_points, in
     if (rc) return rc;
     int *d_polar = ctx->scratch[4].as<int>();
     NRS_CUDA(cudaMemcpyAsync(S->d_fft, fft, (size_t)R * C * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    rc = fe_cen2019_device(ctx, *S, R, C, max_points, min_range, d_polar);
-    if (rc) return rc;
-    NRS_CUDA(cudaMemcpyAsync(S->h_counts, S->d_counts, sizeof(FrameCounts), cudaMemcpyDeviceToHost, ctx->stream));
-    NRS_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        rc = fe_cen2019_device(ctx, *S, R, C, max_points, min_range, d_polar, true, attempt == 1);
+        if (rc) return rc;
+        NRS_CUDA(cudaMemcpyAsync(S->h_counts, S->d_counts, sizeof(FrameCounts), cudaMemcpyDeviceToHost, ctx->stream));
+        NRS_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (!S->h_counts->need_full) break;          // the top-candidate subset vouched for the result (or the full sort ran)
+    }
     const int k = S->h_counts->K0;
     *K = k;
     if (S->h_counts->overflow) { set_error("nrs_cen2019: more than %d keypoints", FE_KP_CAP); return NRS_ECAPACITY; }
@@ -582,7 +586,9 @@ int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw, int R, int row_pitch, co
     NRS_CUDA(cudaMemcpyAsync(S->d_cossin, cossin, 2 * R * sizeof(double), cudaMemcpyHostToDevice, st));
     NRS_CUDA(cudaMemcpyAsync(S->d_times, times, R * sizeof(long long), cudaMemcpyHostToDevice, st));
 
-    // ---- device pipeline ------------------------------------------------------------------------
+    // ---- device pipeline (a second pass with the full-frame sort only when cen2019's top-candidate subset could
+    //      not vouch for the marking loop's outcome: FrameCounts::need_full) ----------------------------------------
+    for (int attempt = 0; attempt < 2; ++attempt) {
     NRS_CUDA(cudaMemsetAsync(S->d_counts, 0, sizeof(FrameCounts), st));
     if ((rc = fe_decode_device(ctx, *S, R, C, row_pitch))) { frame_release_locked(f); return rc; }
     // fork: Cartesian image branch (radar_utils.cpp:227-316 + ORB's blur) on the second stream
@@ -605,7 +611,7 @@ int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw, int R, int row_pitch, co
     // keypoint branch on the context stream
     rc = (p->keypoint_extraction == 1)
              ? fe_cen2018_device(ctx, *S, R, C, p->zq, p->sigma_gauss, p->min_range, f->d_polar, false, false)
-             : fe_cen2019_device(ctx, *S, R, C, p->max_points, p->min_range, f->d_polar, false);
+             : fe_cen2019_device(ctx, *S, R, C, p->max_points, p->min_range, f->d_polar, false, attempt == 1);
     if (rc) { cudaStreamSynchronize(si); frame_release_locked(f); return rc; }
     if ((rc = fe_points_voxel_bev_device(ctx, *S, f))) { cudaStreamSynchronize(si); frame_release_locked(f); return rc; }
     NRS_CUDA(cudaStreamWaitEvent(st, S->ev_join, 0));           // join
@@ -613,6 +619,8 @@ int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw, int R, int row_pitch, co
     NRS_LAUNCHED();
     NRS_CUDA(cudaMemcpyAsync(S->h_counts, S->d_counts, sizeof(FrameCounts), cudaMemcpyDeviceToHost, st));
     NRS_CUDA(cudaStreamSynchronize(st));
+    if (!S->h_counts->need_full) break;
+    }
     f->counts = *S->h_counts;
     if (f->counts.overflow) {
         frame_release_locked(f);

@@ -234,6 +234,7 @@ class SCManager:
         self.polarcontext_invkeys_mat_ = []
         self.polarcontext_invkeys_to_search_ = []
         self.is_tree_batch_made = False
+        self._batch_end = 0
         self._searchable_end = 0
         self._candidate_fn = candidate_fn
 
@@ -333,21 +334,31 @@ class SCManager:
         return loop_id, self._yaw(nn_align)                               # :417-420
 
     def detectLoopClosureIDBetweenSession(self, curr_key, curr_desc):
-        """Scancontext.cpp:267-328: one-shot search over *all* stored keyframes (no
-        recent-exclusion).  curr_key is only used in candidate mode."""
-        n = len(self.polarcontexts_)
+        """Scancontext.cpp:267-328.  The reference builds its batch tree ONCE, on the first call, over the
+        keys present then (is_tree_batch_made): later calls search exactly those keyframes whatever has been
+        saved since; no recent-exclusion.  Candidate ids the 3-NN search cannot fill stay 0 in the reference
+        (zero-initialised vector, :292).  curr_key is only used in candidate mode."""
+        if not self.is_tree_batch_made:
+            self._batch_end = len(self.polarcontext_invkeys_mat_)
+            self.polarcontext_invkeys_to_search_ = self.polarcontext_invkeys_mat_[: self._batch_end]
+            self.is_tree_batch_made = True
+        n = self._batch_end
         q = flat(curr_desc)
-        self.is_tree_batch_made = True
+        k = self.NUM_CANDIDATES_FROM_TREE
+        if n == 0:                                   # the reference would index an empty vector here (UB)
+            return -1, self._yaw(0)
         if self._candidate_fn is None:
             min_dist, nn_idx, nn_align = self.db.query(q, 0, n)
         elif self._candidate_fn == "kdtree":
             # the reference searches the tree with the caller's curr_key (:297-300), whatever it is
-            cand, _ = self.db.knn(curr_key, 0, n, self.NUM_CANDIDATES_FROM_TREE)
+            cand, _ = self.db.knn(curr_key, 0, n, k) if n > 0 else (np.full(k, -1, np.int32), None)
+            cand = np.where(cand >= 0, cand, 0).astype(np.int32)
             self.last_candidates = cand
-            min_dist, nn_idx, nn_align = self.db.query(q, candidates=cand[cand >= 0])
+            min_dist, nn_idx, nn_align = self.db.query(q, candidates=cand) if n > 0 else (SENTINEL, 0, 0)
         else:
-            keys = np.stack(self.polarcontext_invkeys_mat_).astype(np.float32)
-            cand = self._candidate_fn(keys, np.asarray(curr_key, dtype=np.float32), self.NUM_CANDIDATES_FROM_TREE)
+            keys = np.stack(self.polarcontext_invkeys_to_search_).astype(np.float32)
+            cand = np.asarray(self._candidate_fn(keys, np.asarray(curr_key, dtype=np.float32), k), dtype=np.int32)
+            cand = np.concatenate([np.where(cand >= 0, cand, 0), np.zeros(max(0, k - cand.size), np.int32)]).astype(np.int32)
             min_dist, nn_idx, nn_align = self.db.query(q, candidates=cand)
         loop_id = nn_idx if min_dist < self.SC_DIST_THRES else -1
         return loop_id, self._yaw(nn_align)

@@ -190,3 +190,22 @@ def test_cen2018_against_committed_golden(nrs, ctx):
         diff = y.view(np.uint32)[:, int(mr):] != g[f"{tag}_y"].view(np.uint32)[:, int(mr):]
         assert diff.sum() <= 4
         assert np.array_equal(got, g[f"{tag}_targets"]) and got.shape[1] > 50
+
+
+def test_cen2019_subset_threshold_sequence(nrs, ctx, F, synth, world):
+    """cen2019's top-candidate subset (threshold on h carried from frame to frame): a sequence whose contrast
+    changes abruptly -- the carried threshold is far too high (dark frame: the subset cannot vouch, the full sort
+    runs), then far too low (bright frame: more than the subset's capacity) -- must give the oracle's keypoints on
+    every frame, whatever the history."""
+    rng = np.random.default_rng(3)
+    raw = synth.radar_frame(world, (0, 0, 0), seed=77)
+    base = (raw[:, 11:].astype(np.float32) / 255.0).astype(np.float32)
+    base[:, :42] = 0
+    frames = [base, (base * 0.25).astype(np.float32), base, np.clip(base * 3.0, 0, 1).astype(np.float32),
+              (rng.integers(0, 256, base.shape) / 255.0).astype(np.float32), base]
+    frames[4][:, :42] = 0
+    for k, fft in enumerate(frames):
+        for mp in ((10000, 300) if k in (0, 5) else (10000,)):
+            want = F.cen2019features(fft, mp, 58)
+            got = nrs.orora.cen2019features(ctx, fft, mp, 58)
+            assert got.shape == want.shape and np.array_equal(got, want), (k, mp)

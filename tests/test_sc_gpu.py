@@ -360,3 +360,39 @@ def test_detect_flow_kdtree_mode(sc, ctx, oracle, synth):
             assert (loop, yaw) == (eloop, eyaw) and m.last_min_dist == emd and m.last_nn_idx == enn
             checked += 1
     assert checked > 300
+
+
+def test_between_session_flow(sc, ctx, oracle, synth):
+    """detectLoopClosureIDBetweenSession (Scancontext.cpp:267-328): the batch tree is made once, over the keys
+    stored at the FIRST call; later calls search exactly those keyframes.  Both modes against the oracle: the
+    reference's 3 tree candidates (its own nanoflann when oracle/_ref is present) and the exhaustive search."""
+    db, rev = synth.sc_database(260, 80, seed=33, binary=True)
+    ref = oracle.ref_kdtree()
+    for mode in ("kdtree", None):
+        m = sc.SCManager(ctx, candidate_fn=mode)
+        m.setSCdistThres(0.45)
+        for i in range(200):
+            m.saveScancontextAndKeys(sc.as_desc(db[i]))
+        keys = np.stack([oracle.sc_ringkey_f32(x) for x in db[:200]])
+        for step, qi in enumerate([210, 220, 5, 250, 231]):
+            if step == 2:                                   # saved AFTER the batch tree was made: never searched
+                for i in range(200, 240):
+                    m.saveScancontextAndKeys(sc.as_desc(db[i]))
+            q = db[qi]
+            qk = oracle.sc_ringkey_f32(q)
+            got = m.detectLoopClosureIDBetweenSession(qk, sc.as_desc(q))
+            if mode == "kdtree":
+                cand = oracle.ref_knn(keys, qk, 3)[0] if ref is not None else oracle.sc_knn_bruteforce(keys, qk, 3)[0]
+                assert np.array_equal(m.last_candidates, cand)
+                loop, yaw, md, nn = oracle.sc_detect_from_candidates(q, db, cand, 0.45)
+                assert got == (loop, yaw)
+            else:
+                _, _, (bd, bi, bs) = oracle.sc_search(q, db, 0, 200, want_all=False)
+                assert got == ((bi if bd < 0.45 else -1), m._yaw(bs))
+            assert got[0] < 200
+    # fewer stored keyframes than candidates: unfilled ids stay 0 like the reference's zero-initialised vector
+    m = sc.SCManager(ctx, candidate_fn="kdtree")
+    m.setSCdistThres(0.45)
+    m.saveScancontextAndKeys(sc.as_desc(db[3]))
+    assert m.detectLoopClosureIDBetweenSession(oracle.sc_ringkey_f32(db[3]), sc.as_desc(db[3]))[0] == 0
+    assert list(m.last_candidates) == [0, 0, 0]
