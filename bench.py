@@ -583,6 +583,15 @@ def orora_block(pkg, ctx, n_pairs=40, cpu_pairs=3):
         return h
 
     def pair(prev_h, k, vel):
+        """one scan pair through the fused entry point: host rows in, 4x4 pose out"""
+        cur = C.c_void_p()
+        r = raws[k % 8]
+        pkg._lib.check(L.nrs_orora_pair(ctx.handle, prev_h, r.ctypes.data_as(C.c_void_p), 400, r.shape[1], C.byref(ep), k,
+                                        C.byref(sp), vel, C.byref(cur), T.ctypes.data_as(C.c_void_p), C.byref(n), C.byref(info)))
+        L.nrs_frame_destroy(prev_h)
+        return cur, T[12] / 0.25
+
+    def pair_separate(prev_h, k, vel):
         cur = extract(k)
         pkg._lib.check(L.nrs_match(ctx.handle, prev_h, cur, float(ep.nndr), cap, q.ctypes.data_as(C.c_void_p),
                                    t.ctypes.data_as(C.c_void_p), pxy.ctypes.data_as(C.c_void_p),
@@ -605,6 +614,11 @@ def orora_block(pkg, ctx, n_pairs=40, cpu_pairs=3):
     dt = time.perf_counter() - t0
     launches = L.nrs_kernel_launches() - l0
     n_matches, M = n.value, info.M
+    t0 = time.perf_counter()
+    for k in range(4, 4 + n_pairs):
+        prev, vel = pair_separate(prev, k, vel)
+    ctx.sync()
+    dt_sep = time.perf_counter() - t0
     # stage breakdown (separate pass; wall clock around each synchronous C-ABI call)
     for k in range(100, 110):
         a = time.perf_counter(); cur = extract(k); b = time.perf_counter()
@@ -635,12 +649,10 @@ def orora_block(pkg, ctx, n_pairs=40, cpu_pairs=3):
     for k in range(1, 4 + n_pairs // 2):
         if k == 4:
             ctx.sync(); t18 = time.perf_counter()
-        cur = extract18(k)
-        pkg._lib.check(L.nrs_match(ctx.handle, prev, cur, float(ep.nndr), cap, q.ctypes.data_as(C.c_void_p),
-                                   t.ctypes.data_as(C.c_void_p), pxy.ctypes.data_as(C.c_void_p),
-                                   cxy.ctypes.data_as(C.c_void_p), None, None, C.byref(n)))
-        pkg._lib.check(L.nrs_orora_solve(ctx.handle, pxy.ctypes.data_as(C.c_void_p), cxy.ctypes.data_as(C.c_void_p), n.value,
-                                         C.byref(sp), vel, T.ctypes.data_as(C.c_void_p), None, None, C.byref(info)))
+        cur = C.c_void_p()
+        r = raws[k % 8]
+        pkg._lib.check(L.nrs_orora_pair(ctx.handle, prev, r.ctypes.data_as(C.c_void_p), 400, r.shape[1], C.byref(ep18), k,
+                                        C.byref(sp), vel, C.byref(cur), T.ctypes.data_as(C.c_void_p), C.byref(n), C.byref(info)))
         L.nrs_frame_destroy(prev)
         prev, vel = cur, T[12] / 0.25
     ctx.sync()
@@ -693,6 +705,9 @@ def orora_block(pkg, ctx, n_pairs=40, cpu_pairs=3):
             "parity_gate": parity,
             "workload": "synthetic MulRan-format 400x3360 frames, cen2019 + remap + ORB + match + max-clique/GNC/COTE",
             "e2e": "pinned host PNG rows in (1.35 MB H2D per frame), 4x4 pose out; value == e2e (the path starts on the host)",
+            "api": "nrs_orora_pair (extract + match + solve in one call, two host synchronisations per pair)",
+            "separate_calls": {"value": n_pairs / dt_sep, "ms_per_pair": 1e3 * dt_sep / n_pairs,
+                               "api": "nrs_frame_extract + nrs_match + nrs_orora_solve (four synchronisations, matches through host memory)"},
             "h2d_bytes_per_pair": int(raws[0].nbytes), "d2h_bytes_per_pair": 128 + 40 * max(n_matches, 1),
             "stage_ms": {k: round(v, 3) for k, v in st.items()}, "matches": n_matches, "clique": M,
             "cen2018": {"value": 1.0 / dt18, "unit": "pairs/s", "ms_per_pair": 1e3 * dt18, "matches": n18, "clique": M18,

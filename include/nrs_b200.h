@@ -361,6 +361,18 @@ int nrs_match(nrs_ctx *ctx, const nrs_frame *prev, const nrs_frame *curr, float 
               int32_t *query_idx, int32_t *train_idx, double *prev_2xN, double *curr_2xN,
               int64_t *prev_t, int64_t *curr_t, int *N);
 
+/* One iteration of the node's per-frame loop (odometry.cpp:153-284) in ONE call:
+ *   curr = Loader.extractFeature(new frame); (prev_m, curr_m) = Loader.matchFeatures(prev, curr);
+ *   T = orora_estimator.calcTransform(params, dt, prev_m, curr_m)
+ * with the same results as nrs_frame_extract + nrs_match + nrs_orora_solve, but the matcher is enqueued behind the
+ * extraction without waiting for it and the matched points reach the solver without a round trip through host
+ * memory (two host synchronisations per scan pair instead of four).  prev: the previous frame's handle (same
+ * context); *curr_out: the new frame's handle (caller destroys); vel_x as in nrs_orora_solve;
+ * *n_matches (nullable): matches fed to the solver. */
+int nrs_orora_pair(nrs_ctx *ctx, const nrs_frame *prev, const uint8_t *raw_rows, int R, int row_pitch,
+                   const nrs_extract_params *p, int64_t t_criteria, const nrs_solver_params *sp, double vel_x,
+                   nrs_frame **curr_out, double T_out[16], int *n_matches, nrs_solver_info *info_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -150,6 +150,7 @@ def _declare(L):
     L.nrs_frame_get.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.nrs_frame_get_stages.argtypes = [vp, vp, vp, vp, vp]
     L.nrs_match.argtypes = [vp, vp, vp, C.c_float, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.nrs_orora_pair.argtypes = [vp, vp, vp, i32, i32, vp, C.c_int64, vp, f64, C.POINTER(vp), vp, vp, vp]
     for name in declared_symbols():
         fn = getattr(L, name, None)
         if fn is not None and fn.restype is C.c_int and name not in ("nrs_version",):

@@ -63,6 +63,11 @@ struct PinBuf {
     template <class T> T *as() { return reinterpret_cast<T *>(ptr); }
 };
 
+// solver entry for callers that already hold ctx->mu (the fused pair call): points may live on the device
+int orora_solve_locked(nrs_ctx *ctx, const double *prev_2xN, const double *curr_2xN, bool points_on_device, int N,
+                       const nrs_solver_params *p, double vel_x, double T_out[16], int32_t *clique_out,
+                       int32_t *final_inliers_out, nrs_solver_info *info_out);
+
 }  // namespace nrs
 
 struct nrs_ctx {

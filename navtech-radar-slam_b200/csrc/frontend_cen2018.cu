@@ -263,10 +263,16 @@ int fe_cen2018_device(nrs_ctx *ctx, FrontendState &S, int R, int C, float zq, in
     {
         const int stride = ((C + 3) & ~3) + 4;               // rows 16-byte aligned, walkers on different banks
         const size_t smem = (size_t)ROWS_PB * stride * sizeof(float);
-        static size_t configured = 0;
-        if (smem > configured) {
-            NRS_CUDA(cudaFuncSetAttribute(fe18_bias_sigma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
+        // per device and thread-safe (contexts on several GPUs may share this process)
+        static std::mutex cfg_mu;
+        static size_t configured[64] = {};
+        {
+            std::lock_guard<std::mutex> lk(cfg_mu);
+            const int dv = (ctx->device >= 0 && ctx->device < 64) ? ctx->device : 0;
+            if (smem > configured[dv] || ctx->device >= 64) {
+                NRS_CUDA(cudaFuncSetAttribute(fe18_bias_sigma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured[dv] = smem;
+            }
         }
         fe18_bias_sigma_kernel<<<(R + ROWS_PB - 1) / ROWS_PB, 256, smem, st>>>(S.d_fft, R, C, stride, d_q, d_sigma);
         NRS_LAUNCHED();

@@ -199,12 +199,14 @@ __global__ void fe_brief_kernel(const unsigned char *__restrict__ blur, int W, c
 __device__ __forceinline__ bool lex_less(int d1, int i1, int d2, int i2) { return d1 < d2 || (d1 == d2 && i1 < i2); }
 
 __global__ void __launch_bounds__(256)
-fe_match_kernel(const unsigned char *__restrict__ qdesc, int nq, const unsigned char *__restrict__ tdesc, int nt,
-                float nndr, int *__restrict__ best_train, unsigned char *__restrict__ good)
+fe_match_kernel(const unsigned char *__restrict__ qdesc, int nq, const unsigned char *__restrict__ tdesc, int nt_host,
+                const FrameCounts *__restrict__ tcnt, float nndr, int *__restrict__ best_train,
+                unsigned char *__restrict__ good)
 {
     const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (q >= nq) return;
+    const int nt = tcnt ? tcnt->Kd : nt_host;            // fused pair call: the train frame's counts are still on the device
     const uint4 *qp = reinterpret_cast<const uint4 *>(qdesc + (size_t)q * 32);
     const uint4 qa = qp[0], qb = qp[1];
     int d0 = 0x7fffffff, i0 = 0x7fffffff, d1 = 0x7fffffff, i1 = 0x7fffffff;
@@ -528,69 +530,62 @@ int nrs_cen2019(nrs_ctx *ctx, const float *fft, int R, int C, int max_points, in
     return NRS_OK;
 }
 
-int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw, int R, int row_pitch, const nrs_extract_params *p,
-                      int64_t t_criteria, nrs_frame **out)
-{
-    NRS_CHECK_ARG(ctx && raw && p && out, "bad argument");
-    *out = nullptr;
-    const int C = p->range_bins;
-    NRS_CHECK_ARG(R >= 2 && R <= FE_MAX_AZ, "number of azimuths out of range");
-    NRS_CHECK_ARG(row_pitch >= C + 11, "row pitch smaller than 11 + range_bins");
-    NRS_CHECK_ARG(p->cart_pixel_width >= 64 && p->patch_size >= 3 && p->patch_size <= 63 && p->max_points <= FE_KP_CAP, "bad parameters");
-    NRS_CHECK_ARG(p->keypoint_extraction == 0 || p->keypoint_extraction == 1, "keypoint_extraction must be 0 (cen2019) or 1 (cen2018)");
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    NRS_CUDA(cudaSetDevice(ctx->device));
-    FrontendState *S = nullptr;
-    int rc = frontend_state(ctx, p, R, C, row_pitch, &S);
-    if (rc) return rc;
-    nrs_frame *f = nullptr;
-    rc = alloc_frame(ctx, p->cart_pixel_width, &f);
-    if (rc) return rc;
-    f->t_criteria = t_criteria;
-    cudaStream_t st = ctx->stream;
-    const int W = p->cart_pixel_width;
+namespace {
 
-    // ---- host: row headers (radar_utils.cpp:121-123), libm tables ---------------------------------
+// row headers (radar_utils.cpp:121-123) and the libm tables derived from them, uploaded with the raw rows
+struct HostTables {
     double az[FE_MAX_AZ], cossin[2 * FE_MAX_AZ], azs[FE_MAX_AZ];
     long long times[FE_MAX_AZ];
     int azi[FE_MAX_AZ];
+    int n_sorted = 0;
     long long tmin = 0, tmax = 0;
+};
+
+int extract_upload(nrs_ctx *ctx, FrontendState *S, const uint8_t *raw, int R, int row_pitch, HostTables &H)
+{
+    cudaStream_t st = ctx->stream;
     for (int i = 0; i < R; ++i) {
         const uint8_t *row = raw + (size_t)i * row_pitch;
         int64_t stamp; uint16_t enc;
         memcpy(&stamp, row, 8);
         memcpy(&enc, row + 8, 2);
-        times[i] = stamp;
-        az[i] = enc * 2 * M_PI / double(5600);
-        cossin[2 * i] = cos(az[i]);
-        cossin[2 * i + 1] = sin(az[i]);
-        if (i == 0 || stamp < tmin) tmin = stamp;
-        if (i == 0 || stamp > tmax) tmax = stamp;
+        H.times[i] = stamp;
+        H.az[i] = enc * 2 * M_PI / double(5600);
+        H.cossin[2 * i] = cos(H.az[i]);
+        H.cossin[2 * i + 1] = sin(H.az[i]);
+        if (i == 0 || stamp < H.tmin) H.tmin = stamp;
+        if (i == 0 || stamp > H.tmax) H.tmax = stamp;
     }
-    f->t_min = tmin; f->t_max = tmax;
-    int n_sorted = 0;
+    H.n_sorted = 0;
     {
         std::vector<int> order(R);
         for (int i = 0; i < R; ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return az[a] < az[b]; });
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return H.az[a] < H.az[b]; });
         for (int k = 0; k < R; ++k) {
             const int i = order[k];
-            if (n_sorted && azs[n_sorted - 1] == az[i]) continue;     // duplicates: keep the lowest index
-            azs[n_sorted] = az[i]; azi[n_sorted] = i; ++n_sorted;
+            if (H.n_sorted && H.azs[H.n_sorted - 1] == H.az[i]) continue;     // duplicates: keep the lowest index
+            H.azs[H.n_sorted] = H.az[i]; H.azi[H.n_sorted] = i; ++H.n_sorted;
         }
     }
     NRS_CUDA(cudaMemcpyAsync(S->d_raw, raw, (size_t)R * row_pitch, cudaMemcpyHostToDevice, st));
-    NRS_CUDA(cudaMemcpyAsync(S->d_az, az, R * sizeof(double), cudaMemcpyHostToDevice, st));
-    NRS_CUDA(cudaMemcpyAsync(S->d_azsort, azs, n_sorted * sizeof(double), cudaMemcpyHostToDevice, st));
-    NRS_CUDA(cudaMemcpyAsync(S->d_azidx, azi, n_sorted * sizeof(int), cudaMemcpyHostToDevice, st));
-    NRS_CUDA(cudaMemcpyAsync(S->d_cossin, cossin, 2 * R * sizeof(double), cudaMemcpyHostToDevice, st));
-    NRS_CUDA(cudaMemcpyAsync(S->d_times, times, R * sizeof(long long), cudaMemcpyHostToDevice, st));
+    NRS_CUDA(cudaMemcpyAsync(S->d_az, H.az, R * sizeof(double), cudaMemcpyHostToDevice, st));
+    NRS_CUDA(cudaMemcpyAsync(S->d_azsort, H.azs, H.n_sorted * sizeof(double), cudaMemcpyHostToDevice, st));
+    NRS_CUDA(cudaMemcpyAsync(S->d_azidx, H.azi, H.n_sorted * sizeof(int), cudaMemcpyHostToDevice, st));
+    NRS_CUDA(cudaMemcpyAsync(S->d_cossin, H.cossin, 2 * R * sizeof(double), cudaMemcpyHostToDevice, st));
+    NRS_CUDA(cudaMemcpyAsync(S->d_times, H.times, R * sizeof(long long), cudaMemcpyHostToDevice, st));
+    return NRS_OK;
+}
 
-    // ---- device pipeline (a second pass with the full-frame sort only when cen2019's top-candidate subset could
-    //      not vouch for the marking loop's outcome: FrameCounts::need_full) ----------------------------------------
-    for (int attempt = 0; attempt < 2; ++attempt) {
+// the whole device pipeline of extractFeature for the uploaded frame, enqueued on the context stream (image
+// branch on the second stream, joined before the descriptors); no host synchronisation
+int extract_enqueue(nrs_ctx *ctx, FrontendState *S, nrs_frame *f, int R, int C, int row_pitch, const nrs_extract_params *p,
+                    int n_sorted, bool force_full)
+{
+    cudaStream_t st = ctx->stream;
+    const int W = p->cart_pixel_width;
+    int rc;
     NRS_CUDA(cudaMemsetAsync(S->d_counts, 0, sizeof(FrameCounts), st));
-    if ((rc = fe_decode_device(ctx, *S, R, C, row_pitch))) { frame_release_locked(f); return rc; }
+    if ((rc = fe_decode_device(ctx, *S, R, C, row_pitch))) return rc;
     // fork: Cartesian image branch (radar_utils.cpp:227-316 + ORB's blur) on the second stream
     cudaStream_t si = S->st_img;
     NRS_CUDA(cudaEventRecord(S->ev_fork, st));
@@ -611,15 +606,78 @@ int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw, int R, int row_pitch, co
     // keypoint branch on the context stream
     rc = (p->keypoint_extraction == 1)
              ? fe_cen2018_device(ctx, *S, R, C, p->zq, p->sigma_gauss, p->min_range, f->d_polar, false, false)
-             : fe_cen2019_device(ctx, *S, R, C, p->max_points, p->min_range, f->d_polar, false, attempt == 1);
-    if (rc) { cudaStreamSynchronize(si); frame_release_locked(f); return rc; }
-    if ((rc = fe_points_voxel_bev_device(ctx, *S, f))) { cudaStreamSynchronize(si); frame_release_locked(f); return rc; }
+             : fe_cen2019_device(ctx, *S, R, C, p->max_points, p->min_range, f->d_polar, false, force_full);
+    if (rc) { cudaStreamSynchronize(si); return rc; }
+    if ((rc = fe_points_voxel_bev_device(ctx, *S, f))) { cudaStreamSynchronize(si); return rc; }
     NRS_CUDA(cudaStreamWaitEvent(st, S->ev_join, 0));           // join
     fe_brief_kernel<<<(FE_KP_CAP * 32 + 255) / 256, 256, 0, st>>>(S->d_blur, W, f->d_kp_orb, S->d_counts, S->d_pattern, f->d_desc);
     NRS_LAUNCHED();
-    NRS_CUDA(cudaMemcpyAsync(S->h_counts, S->d_counts, sizeof(FrameCounts), cudaMemcpyDeviceToHost, st));
-    NRS_CUDA(cudaStreamSynchronize(st));
-    if (!S->h_counts->need_full) break;
+    return NRS_OK;
+}
+
+int check_extract_args(nrs_ctx *ctx, const uint8_t *raw, int R, int row_pitch, const nrs_extract_params *p)
+{
+    NRS_CHECK_ARG(ctx && raw && p, "bad argument");
+    NRS_CHECK_ARG(R >= 2 && R <= FE_MAX_AZ, "number of azimuths out of range");
+    NRS_CHECK_ARG(row_pitch >= p->range_bins + 11, "row pitch smaller than 11 + range_bins");
+    NRS_CHECK_ARG(p->cart_pixel_width >= 64 && p->patch_size >= 3 && p->patch_size <= 63 && p->max_points <= FE_KP_CAP, "bad parameters");
+    NRS_CHECK_ARG(p->keypoint_extraction == 0 || p->keypoint_extraction == 1, "keypoint_extraction must be 0 (cen2019) or 1 (cen2018)");
+    return NRS_OK;
+}
+
+// scratch of the matcher (ctx->scratch[5])
+struct MatchBufs {
+    int *best, *q, *t, *n;
+    unsigned char *good;
+    double *p, *c;
+    long long *pt, *ct;
+};
+int match_carve(nrs_ctx *ctx, int nq, int cap, MatchBufs &m)
+{
+    const size_t c = (size_t)std::max(cap, 1);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+    const size_t o_best = take((size_t)std::max(nq, 1) * 4), o_good = take(std::max(nq, 1)), o_q = take(c * 4), o_t = take(c * 4);
+    const size_t o_p = take(2 * c * 8), o_c = take(2 * c * 8), o_pt = take(c * 8), o_ct = take(c * 8), o_n = take(4);
+    int rc = ctx->scratch[5].reserve(off);
+    if (rc) return rc;
+    unsigned char *b = ctx->scratch[5].as<unsigned char>();
+    m.best = (int *)(b + o_best); m.good = b + o_good; m.q = (int *)(b + o_q); m.t = (int *)(b + o_t);
+    m.p = (double *)(b + o_p); m.c = (double *)(b + o_c); m.pt = (long long *)(b + o_pt); m.ct = (long long *)(b + o_ct);
+    m.n = (int *)(b + o_n);
+    return NRS_OK;
+}
+
+}  // namespace
+
+int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw, int R, int row_pitch, const nrs_extract_params *p,
+                      int64_t t_criteria, nrs_frame **out)
+{
+    NRS_CHECK_ARG(out, "bad argument");
+    *out = nullptr;
+    int rc = check_extract_args(ctx, raw, R, row_pitch, p);
+    if (rc) return rc;
+    const int C = p->range_bins;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    NRS_CUDA(cudaSetDevice(ctx->device));
+    FrontendState *S = nullptr;
+    rc = frontend_state(ctx, p, R, C, row_pitch, &S);
+    if (rc) return rc;
+    nrs_frame *f = nullptr;
+    rc = alloc_frame(ctx, p->cart_pixel_width, &f);
+    if (rc) return rc;
+    f->t_criteria = t_criteria;
+    cudaStream_t st = ctx->stream;
+    HostTables H;
+    if ((rc = extract_upload(ctx, S, raw, R, row_pitch, H))) { frame_release_locked(f); return rc; }
+    f->t_min = H.tmin; f->t_max = H.tmax;
+    // a second pass with the full-frame sort only when cen2019's top-candidate subset could not vouch for the
+    // marking loop's outcome (FrameCounts::need_full)
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if ((rc = extract_enqueue(ctx, S, f, R, C, row_pitch, p, H.n_sorted, attempt == 1))) { frame_release_locked(f); return rc; }
+        NRS_CUDA(cudaMemcpyAsync(S->h_counts, S->d_counts, sizeof(FrameCounts), cudaMemcpyDeviceToHost, st));
+        NRS_CUDA(cudaStreamSynchronize(st));
+        if (!S->h_counts->need_full) break;
     }
     f->counts = *S->h_counts;
     if (f->counts.overflow) {
@@ -628,6 +686,66 @@ int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw, int R, int row_pitch, co
         return NRS_ECAPACITY;
     }
     *out = f;
+    return NRS_OK;
+}
+
+// One iteration of the node's loop (odometry.cpp:153-284) in ONE call: extractFeature(new frame),
+// matchFeatures(prev, curr), ORORA::calcTransform -- the matcher is enqueued behind the extraction without
+// waiting for it (the new frame's keypoint count stays on the device), the matched points go to the solver
+// without a round trip through host memory: two host synchronisations per scan pair instead of four.
+int nrs_orora_pair(nrs_ctx *ctx, const nrs_frame *prev, const uint8_t *raw, int R, int row_pitch,
+                   const nrs_extract_params *p, int64_t t_criteria, const nrs_solver_params *sp, double vel_x,
+                   nrs_frame **curr_out, double T_out[16], int *n_matches, nrs_solver_info *info_out)
+{
+    NRS_CHECK_ARG(prev && sp && curr_out && T_out && info_out, "bad argument");
+    *curr_out = nullptr;
+    int rc = check_extract_args(ctx, raw, R, row_pitch, p);
+    if (rc) return rc;
+    NRS_CHECK_ARG(prev->ctx == ctx, "prev belongs to another context");
+    const int C = p->range_bins;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    NRS_CUDA(cudaSetDevice(ctx->device));
+    FrontendState *S = nullptr;
+    rc = frontend_state(ctx, p, R, C, row_pitch, &S);
+    if (rc) return rc;
+    nrs_frame *f = nullptr;
+    rc = alloc_frame(ctx, p->cart_pixel_width, &f);
+    if (rc) return rc;
+    f->t_criteria = t_criteria;
+    cudaStream_t st = ctx->stream;
+    HostTables H;
+    if ((rc = extract_upload(ctx, S, raw, R, row_pitch, H))) { frame_release_locked(f); return rc; }
+    f->t_min = H.tmin; f->t_max = H.tmax;
+    const int nq = prev->counts.Kd, cap = std::max(nq, 1);
+    MatchBufs m;
+    if ((rc = match_carve(ctx, nq, cap, m))) { frame_release_locked(f); return rc; }
+    int h_n = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if ((rc = extract_enqueue(ctx, S, f, R, C, row_pitch, p, H.n_sorted, attempt == 1))) { frame_release_locked(f); return rc; }
+        NRS_CUDA(cudaMemsetAsync(m.n, 0, 4, st));
+        if (nq > 0) {
+            fe_match_kernel<<<(nq * 32 + 255) / 256, 256, 0, st>>>(prev->d_desc, nq, f->d_desc, 0, S->d_counts, p->nndr, m.best, m.good);
+            NRS_LAUNCHED();
+            fe_match_gather_kernel<<<1, 1024, 0, st>>>(m.best, m.good, nq, prev->d_feat, f->d_feat, prev->d_t, f->d_t, cap, m.q, m.t,
+                                                       m.p, m.c, m.pt, m.ct, m.n);
+            NRS_LAUNCHED();
+        }
+        NRS_CUDA(cudaMemcpyAsync(S->h_counts, S->d_counts, sizeof(FrameCounts), cudaMemcpyDeviceToHost, st));
+        NRS_CUDA(cudaMemcpyAsync(&h_n, m.n, 4, cudaMemcpyDeviceToHost, st));
+        NRS_CUDA(cudaStreamSynchronize(st));
+        if (!S->h_counts->need_full) break;
+    }
+    f->counts = *S->h_counts;
+    if (f->counts.overflow) {
+        frame_release_locked(f);
+        set_error("nrs_orora_pair: more than %d keypoints", FE_KP_CAP);
+        return NRS_ECAPACITY;
+    }
+    if (f->counts.Kd == 0) h_n = 0;                  // the matcher saw an empty train set
+    if (n_matches) *n_matches = h_n;
+    rc = nrs::orora_solve_locked(ctx, m.p, m.c, true, h_n, sp, vel_x, T_out, nullptr, nullptr, info_out);
+    if (rc) { frame_release_locked(f); return rc; }
+    *curr_out = f;
     return NRS_OK;
 }
 
@@ -742,7 +860,7 @@ int nrs_match(nrs_ctx *ctx, const nrs_frame *prev, const nrs_frame *curr, float 
     if (rc) return rc;
     unsigned char *b = ctx->scratch[5].as<unsigned char>();
     cudaStream_t st = ctx->stream;
-    fe_match_kernel<<<(nq * 32 + 255) / 256, 256, 0, st>>>(prev->d_desc, nq, curr->d_desc, nt, nndr,
+    fe_match_kernel<<<(nq * 32 + 255) / 256, 256, 0, st>>>(prev->d_desc, nq, curr->d_desc, nt, nullptr, nndr,
                                                           (int *)(b + o_best), b + o_good);
     NRS_LAUNCHED();
     fe_match_gather_kernel<<<1, 1024, 0, st>>>((int *)(b + o_best), b + o_good, nq, prev->d_feat, curr->d_feat,

@@ -936,15 +936,18 @@ int carve(nrs_ctx *ctx, int N, SolverBufs &b)
     return NRS_OK;
 }
 
-int configure_solver_kernels()
+// the dynamic shared memory opt-in is per device (and this may be called from several threads)
+int configure_solver_kernels(int device)
 {
-    static int done = 0;
-    if (!done) {
+    static std::mutex mu;
+    static unsigned long long done_mask = 0ull;
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 0 || device >= 64 || !((done_mask >> device) & 1ull)) {
         NRS_CUDA(cudaFuncSetAttribute(orora_clique_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       MAXN * SROW * 4));
         NRS_CUDA(cudaFuncSetAttribute(orora_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(TailSmem)));
-        done = 1;
+        if (device >= 0 && device < 64) done_mask |= 1ull << device;
     }
     return NRS_OK;
 }
@@ -958,13 +961,23 @@ int nrs_orora_solve(nrs_ctx *ctx, const double *prev_2xN, const double *curr_2xN
                     int32_t *final_inliers_out, nrs_solver_info *info_out)
 {
     NRS_CHECK_ARG(ctx && p && T_out && info_out && N >= 0 && (N == 0 || (prev_2xN && curr_2xN)), "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    NRS_CUDA(cudaSetDevice(ctx->device));
+    return nrs::orora_solve_locked(ctx, prev_2xN, curr_2xN, false, N, p, vel_x, T_out, clique_out, final_inliers_out, info_out);
+}
+
+}  // extern "C"
+
+// ctx->mu held, device current.  points_on_device: prev/curr are device pointers (the matcher's output buffers)
+int nrs::orora_solve_locked(nrs_ctx *ctx, const double *prev_2xN, const double *curr_2xN, bool points_on_device, int N,
+                            const nrs_solver_params *p, double vel_x, double T_out[16], int32_t *clique_out,
+                            int32_t *final_inliers_out, nrs_solver_info *info_out)
+{
     if (N > MAXN) {
         nrs::set_error("nrs_orora_solve: N = %d exceeds the %d correspondences one warp-wide bitset holds "
                        "(the reference skips estimation above num_feat_thr_for_stop_motion = 700)", N, MAXN);
         return NRS_ECAPACITY;
     }
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    NRS_CUDA(cudaSetDevice(ctx->device));
     memset(info_out, 0, sizeof(*info_out));
     for (int i = 0; i < 16; ++i) T_out[i] = (i % 5 == 0) ? 1.0 : 0.0;
     info_out->R[0] = info_out->R[3] = 1.0;
@@ -974,17 +987,21 @@ int nrs_orora_solve(nrs_ctx *ctx, const double *prev_2xN, const double *curr_2xN
         info_out->stop_motion = (p->check_stop_motion && N > p->num_feat_thr_for_stop_motion) ? 1 : 0;
         return NRS_OK;
     }
-    int rc = configure_solver_kernels();
+    int rc = configure_solver_kernels(ctx->device);
     if (rc) return rc;
     SolverBufs b;
     rc = carve(ctx, N, b);
     if (rc) return rc;
     cudaStream_t st = ctx->stream;
-    NRS_CUDA(cudaMemcpyAsync(b.d_prev, prev_2xN, 2 * (size_t)N * 8, cudaMemcpyHostToDevice, st));
-    NRS_CUDA(cudaMemcpyAsync(b.d_curr, curr_2xN, 2 * (size_t)N * 8, cudaMemcpyHostToDevice, st));
+    const double *d_prev_in = prev_2xN, *d_curr_in = curr_2xN;
+    if (!points_on_device) {
+        NRS_CUDA(cudaMemcpyAsync(b.d_prev, prev_2xN, 2 * (size_t)N * 8, cudaMemcpyHostToDevice, st));
+        NRS_CUDA(cudaMemcpyAsync(b.d_curr, curr_2xN, 2 * (size_t)N * 8, cudaMemcpyHostToDevice, st));
+        d_prev_in = b.d_prev; d_curr_in = b.d_curr;
+    }
     NRS_CUDA(cudaMemsetAsync(b.d_info, 0, sizeof(SolverInfoDev), st));
     const double beta_v = p->doppler_beta * fabs(vel_x);
-    orora_prep_kernel<<<(N + 255) / 256, 256, 0, st>>>(b.d_prev, b.d_curr, N, beta_v, p->use_doppler_compensation,
+    orora_prep_kernel<<<(N + 255) / 256, 256, 0, st>>>(d_prev_in, d_curr_in, N, beta_v, p->use_doppler_compensation,
                                                       b.d_src, b.d_tgt);
     NRS_LAUNCHED();
     const double beta = 2 * p->noise_bound * sqrt(p->cbar2);
@@ -1037,6 +1054,8 @@ int nrs_orora_solve(nrs_ctx *ctx, const double *prev_2xN, const double *curr_2xN
     if (final_inliers_out) memcpy(final_inliers_out, h_final, (size_t)h_info->n_final_inliers * 4);
     return NRS_OK;
 }
+
+extern "C" {
 
 int nrs_orora_last_timings(uint64_t *t_ns12)
 {

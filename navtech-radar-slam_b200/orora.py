@@ -289,3 +289,18 @@ class RadarLoader:
                           t_norm_=curr_feat.t_norm_[t], handle=curr_feat.handle)
         pm.query_idx, pm.train_idx = q, t
         return pm, cm
+
+
+def pair(ctx, prev_frame, raw_rows, extract_p, solver_p, vel_x=0.0, t_criteria=0):
+    """nrs_orora_pair: extractFeature(new frame) + matchFeatures(prev, curr) + calcTransform in one call
+    (odometry.cpp:153-284).  prev_frame: Frame of the previous scan.  -> (Frame of the new scan, T (4,4),
+    number of matches, SolverInfo)."""
+    raw = np.ascontiguousarray(raw_rows, dtype=np.uint8)
+    h = C.c_void_p()
+    T = np.zeros(16)
+    n = C.c_int()
+    info = SolverInfo()
+    check(lib().nrs_orora_pair(ctx.handle, prev_frame.handle, ptr(raw), raw.shape[0], raw.shape[1], C.byref(extract_p),
+                               int(t_criteria), C.byref(solver_p), float(vel_x), C.byref(h), ptr(T), C.byref(n),
+                               C.byref(info)))
+    return Frame(ctx, h), T.reshape(4, 4).T.copy(), n.value, info

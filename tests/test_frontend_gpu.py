@@ -209,3 +209,37 @@ def test_cen2019_subset_threshold_sequence(nrs, ctx, F, synth, world):
             want = F.cen2019features(fft, mp, 58)
             got = nrs.orora.cen2019features(ctx, fft, mp, 58)
             assert got.shape == want.shape and np.array_equal(got, want), (k, mp)
+
+
+@pytest.mark.parametrize("extraction", ["cen2019", "cen2018"])
+def test_fused_pair_equals_separate_calls(nrs, ctx, synth, world, extraction):
+    """nrs_orora_pair (extract + match + solve in one call, device-side chaining) against the three separate
+    entry points on a 5-frame sequence with the Doppler velocity carried from pair to pair: frames, match
+    counts, cliques and poses identical."""
+    orr = nrs.orora
+    raws = [synth.radar_frame(world, (2.5 * k, 0.1 * k, np.deg2rad(1.0) * k), seed=500 + k) for k in range(5)]
+    loader = orr.RadarLoader("mulran", extraction, 0.6, True, False, ctx=ctx)
+    sp = orr.default_params()
+    # separate calls
+    feats = [loader.extractFeatureFromRows(r, k) for k, r in enumerate(raws)]
+    sep, vel = [], 0.0
+    for k in range(1, 5):
+        pm, cm = loader.matchFeatures(feats[k - 1], feats[k])
+        r = orr.solve(ctx, pm.feat_in_cart_, cm.feat_in_cart_, sp, vel)
+        sep.append((pm.feat_in_cart_.shape[1], r))
+        vel = r["T"][0, 3] / 0.25
+    # fused
+    prev = feats[0].handle
+    vel = 0.0
+    alive = []
+    for k in range(1, 5):
+        fr, T, n, info = orr.pair(ctx, prev, raws[k], loader.params, sp, vel, t_criteria=k)
+        alive.append(fr)
+        n_sep, r = sep[k - 1]
+        assert n == n_sep and info.M == r["info"].M and info.n_edges == r["info"].n_edges
+        assert np.array_equal(T, r["T"]), k
+        d = fr.get(want_img=True)
+        assert np.array_equal(d["desc"], feats[k].desc_) and np.array_equal(d["feat_in_cart"], feats[k].feat_in_cart_)
+        assert np.array_equal(d["img"], feats[k].img_) and np.array_equal(d["polar"], feats[k].feat_in_polar_)
+        vel = T[0, 3] / 0.25
+        prev = fr
