@@ -187,20 +187,20 @@ static __device__ __forceinline__ void prep_query(BinSmem &sm, const double *__r
 }
 
 // ---- exact f64 re-evaluation from the masks ---------------------------------------------------------
-// fastAlignUsingVkey over the candidate shifts, ascending, strict '<'; vk[j] = (n_k[j] * c_k) / 20 is the
+// fastAlignUsingVkey over the candidate shifts (lo: shifts 0..31, hi: 32..59), ascending, strict '<'; vk[j] = (n_k[j] * c_k) / 20 is the
 // keyframe's sector key exactly as sc_pack_kernel / the reference compute it (the column sum is exact).
 static __device__ __noinline__ int certify_shift_bin(const double *__restrict__ qv, const unsigned int *nkb_w, double ck,
-                                                     double *vkd, double *scr, unsigned int even, unsigned int odd, int lane)
+                                                     double *vkd, double *scr, unsigned int lo, unsigned int hi, int lane)
 {
     const unsigned char *nkb = reinterpret_cast<const unsigned char *>(nkb_w);
     __syncwarp();
     for (int i = lane; i < S; i += 32) vkd[i] = ((double)nkb[i] * ck) / (double)R;
     double fa_n = SENTINEL;
     int s0 = 0;
-    while (even | odd) {
-        const int se = even ? 2 * (__ffs(even) - 1) : 2 * S, so = odd ? 2 * (__ffs(odd) - 1) + 1 : 2 * S;
-        const int s = min(se, so);
-        if (se < so) even &= even - 1; else odd &= odd - 1;
+    while (lo | hi) {                              // bit l of lo <=> shift l, of hi <=> shift 32 + l: ascending
+        int s;
+        if (lo) { s = __ffs(lo) - 1; lo &= lo - 1; }
+        else { s = 31 + __ffs(hi); hi &= hi - 1; }
         __syncwarp();
         for (int i = lane; i < S; i += 32) {
             const double d = qv[i] - vkd[wrap60(i - s)];
@@ -299,25 +299,24 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
         const unsigned long long qzero = sm.qzero;
 
         if (qbin) {
-            // sliding windows of the query's count vector for this lane's two shifts (2 lane, 2 lane + 1)
-            // (the window of shift 2l + 1 is the window of shift 2l moved on by one byte: a funnel shift per word)
-            unsigned int W0[16];
-            {
-                const int sa = 2 * lb;
+            // sliding window of the query's count vector for this lane's shift l: word i = counts of columns
+            // (4i + l + k) % 60, k = 0..3.  The window of shift l + 32 is the same 15 words rotated by 8 (32 bytes),
+            // so lane l scores the shifts l and l + 32 (< 60: lanes 0..27) from ONE register window.
+            unsigned int W[15];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) W0[i] = sm.win[sa & 3][i + (sa >> 2)];
-            }
+            for (int i = 0; i < 15; ++i) W[i] = sm.win[lane & 3][i + (lane >> 2)];
+            const bool hasB = lane < S - 32;
+            const float cqf = (float)sm.cq;
             const double cq = sm.cq;
-            float my_ub = INFINITY;
-            bool parked = false;
+            float my_ub = INFINITY;                    // warp-uniform
+            bool parked = false;                       // warp-uniform
             for (int item = lo + warp; item < hi; item += BWARPS) {
                 const uint2 km = cur;
                 if (item + BWARPS < hi) {
                     const int kf2 = cand ? cand[item + BWARPS] : first + item + BWARPS;
                     cur = ldg_u2(brec + (size_t)kf2 * BIN_WORDS + 2 * lane);
                 }
-                const unsigned long long kzero =
-                    (((unsigned long long)__shfl_sync(0xffffffffu, km.y, 30) << 32) | __shfl_sync(0xffffffffu, km.x, 30)) & MASK60;
+                const unsigned int kz_lo = __shfl_sync(0xffffffffu, km.x, 30), kz_hi = __shfl_sync(0xffffffffu, km.y, 30);
                 const float ckf = __uint_as_float(__shfl_sync(0xffffffffu, km.x, 31));
                 const unsigned int m0 = own ? km.x : 0u, m1 = own ? km.y : 0u;
                 const int n0 = __popc(m0), n1 = __popc(m1);
@@ -326,7 +325,7 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
                 __syncwarp();
                 reinterpret_cast<unsigned short *>(ws.nkb)[lane] = (unsigned short)(n0 | (n1 << 8));
                 __syncwarp();
-                unsigned int c0 = 0u, c1 = 0u;
+                unsigned int cA = 0u, cB = 0u;
                 {
                     const uint4 *kb = reinterpret_cast<const uint4 *>(ws.nkb);
 #pragma unroll
@@ -335,21 +334,22 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
                         const unsigned int kk[4] = {k4.x, k4.y, k4.z, k4.w};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            if (4 * i + j >= 15) continue;              // bytes 60..63 of the counts are zero
-                            c0 = __dp4a(kk[j], W0[4 * i + j], c0);
-                            c1 = __dp4a(kk[j], __funnelshift_r(W0[4 * i + j], W0[4 * i + j + 1], 8), c1);
+                            const int w = 4 * i + j;
+                            if (w >= 15) continue;                      // bytes 60..63 of the counts are zero
+                            cA = __dp4a(kk[j], W[w], cA);
+                            cB = __dp4a(kk[j], W[(w + 8) % 15], cB);
                         }
                     }
                 }
-                const unsigned int cmx = __reduce_max_sync(0xffffffffu, own ? max(c0, c1) : 0u);
+                if (!hasB) cB = 0u;
+                const unsigned int cmx = __reduce_max_sync(0xffffffffu, max(cA, cB));
                 // the integer score orders the f64 norms only while the two scales are comparable
-                const double ck = (double)ckf;
-                const bool scale_ok = (ck <= cq * 1024.0) && (cq <= ck * 1024.0);
-                const unsigned int candB0 = __ballot_sync(0xffffffffu, own && (!scale_ok || c0 == cmx));
-                const unsigned int candB1 = __ballot_sync(0xffffffffu, own && (!scale_ok || c1 == cmx));
+                const bool scale_ok = (ckf <= cqf * 1024.0f) && (cqf <= ckf * 1024.0f);
+                const unsigned int candLo = __ballot_sync(0xffffffffu, !scale_ok || cA == cmx);
+                const unsigned int candHi = __ballot_sync(0xffffffffu, hasB && (!scale_ok || cB == cmx));
                 int s0;
-                if (__popc(candB0) + __popc(candB1) == 1) s0 = candB0 ? 2 * (__ffs(candB0) - 1) : 2 * (__ffs(candB1) - 1) + 1;
-                else s0 = certify_shift_bin(sm.qc.qv, ws.nkb, ck, ws.vkd, ws.scr, candB0, candB1, lane);
+                if (__popc(candLo) + __popc(candHi) == 1) s0 = candLo ? __ffs(candLo) - 1 : 31 + __ffs(candHi);
+                else s0 = certify_shift_bin(sm.qc.qv, ws.nkb, (double)ckf, ws.vkd, ws.scr, candLo, candHi, lane);
 
                 // ---- 7 shifts x 60 columns of cosine similarity from the masks --------------------------------
                 float part[NSHIFT];
@@ -363,7 +363,7 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
                     for (int d = 0; d < NSHIFT; ++d) {
                         const float a = u2f(__popc(m0 & qe[d].x)) * __uint_as_float(qe[d].y);
                         const float b = u2f(__popc(m1 & qe[d + 1].x)) * __uint_as_float(qe[d + 1].y);
-                        part[d] = a * rk0 + b * rk1;
+                        part[d] = fmaf(a, rk0, b * rk1);
                     }
                 }
                 float dC = INFINITY;
@@ -392,6 +392,7 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
                     const float v = __shfl_sync(0xffffffffu, v1, srcl);
                     if (lane < NSHIFT) {
                         const int s = wrap60(s0 + lane - RADIUS);
+                        const unsigned long long kzero = (((unsigned long long)kz_hi << 32) | kz_lo) & MASK60;
                         const unsigned long long krot = s ? (((kzero << s) | (kzero >> (S - s))) & MASK60) : kzero;
                         cntC = S - __popcll((qzero | krot) & MASK60);
                         dC = cntC ? 1.0f - v / (float)cntC : INFINITY;
@@ -400,24 +401,28 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
                 const float mC = warp_min_f(dC);
                 const unsigned int candC = __ballot_sync(0xffffffffu, lane < NSHIFT && cntC > 0 && dC <= mC + 2.0f * EPS_C);
 
-                if (lane == 0) {
-                    Survivor sv;
-                    sv.item = item; sv.code = 1 << 16; sv.lo = INFINITY;      // "ruled out"
-                    __builtin_memcpy(&sv.pad, &ckf, 4);
-                    bool push = false;
-                    if (candC) {
-                        const float bound = fminf(my_ub, unord_f32(*reinterpret_cast<volatile unsigned int *>(&sm.ub)));
-                        push = mC - EPS_C <= bound;
-                        if (push) { sv.code = s0 | (int)(candC << 8) | (1 << 16); sv.lo = mC; }
-                        if (mC + EPS_C < bound) {
-                            my_ub = mC + EPS_C;
+                // every exact distance of this keyframe is >= mC - e_C and its best one is <= mC + e_C: it survives unless
+                // that lower bound already exceeds an upper bound seen by this CTA; all of it warp-uniform, lane 0 acts
+                const float bound = fminf(my_ub, unord_f32(*reinterpret_cast<volatile unsigned int *>(&sm.ub)));
+                const bool push = candC && (mC - EPS_C <= bound);
+                const bool improve = candC && (mC + EPS_C < bound);
+                if (improve) my_ub = mC + EPS_C;
+                if (push || improve || !parked) {
+                    if (lane == 0) {
+                        Survivor sv;
+                        sv.item = item;
+                        sv.code = push ? (s0 | (int)(candC << 8) | (1 << 16)) : (1 << 16);
+                        sv.lo = push ? mC : INFINITY;                          // INFINITY: "ruled out"
+                        sv.pad = __float_as_int(ckf);
+                        if (improve) {
                             atomicMin(&sm.ub, ord_f32(my_ub));
                             atomicMin(&stq->gub, ord_f32(my_ub));
                         }
+                        // the first keyframe of a warp may meet no bound yet: park it and judge it after the loop
+                        if (!parked) ws.first = sv;
+                        else if (push) survq[atomicAdd(&stq->n_surv, 1u)] = sv;
                     }
-                    // the first keyframe of a warp may meet no bound yet: park it and judge it after the loop
-                    if (!parked) { ws.first = sv; parked = true; }
-                    else if (push) survq[atomicAdd(&stq->n_surv, 1u)] = sv;
+                    parked = true;
                 }
             }
             if (lane == 0 && parked) {
