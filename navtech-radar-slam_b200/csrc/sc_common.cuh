@@ -263,7 +263,7 @@ struct nrs_sc_db {
     int          search_mode = 0;        // 0 auto, 1 always the general-valued kernel (nrs_sc_db_set_search_mode)
     float       *d_knn_pd = nullptr;     // per-block partial k-NN lists (distance, index)
     int32_t     *d_knn_pi = nullptr;
-    float       *d_knn_out = nullptr;    // [0,16) d2, [16,32) idx, [32,48) candidate ids, [48,68) query ring key
+    float       *d_knn_out = nullptr;    // [0,16) d2, [16,32) idx, [32,48) candidate ids, [48,68) query ring key, [68] ticket
     nrs_sc::Survivor    *d_surv = nullptr;       // capacity entries
     int          size = 0;
     int          capacity = 0;

@@ -662,8 +662,8 @@ sc_dist_direct_kernel(const double *__restrict__ sc1, const double *__restrict__
 // a tree to rebuild.  Order: ascending distance, equal distances by ascending index (the kd-tree's order
 // among exact ties depends on its traversal; documented in DESIGN.md).  NaN distances never enter.
 constexpr int KNN_MAX = 16;
-constexpr int KNN_THREADS = 256;
-constexpr int KNN_PER_BLOCK = KNN_THREADS * 16;
+constexpr int KNN_THREADS = 128;
+constexpr int KNN_PER_BLOCK = KNN_THREADS;       // one ring key per thread: 79 CTAs for 10k keyframes (was 3 CTAs of 4096)
 
 __device__ __forceinline__ float ringkey_l2(const float (&q)[R], const float *__restrict__ key)
 {
@@ -742,14 +742,59 @@ __device__ __forceinline__ void knn_insert(float (&ld)[KNN_MAX], int (&li)[KNN_M
     }
 }
 
-// stage 1: every block scans KNN_PER_BLOCK ring keys of [first, last) and emits its k best
-__global__ void __launch_bounds__(KNN_THREADS)
-sc_knn_scan_kernel(const float *__restrict__ rkeys, const float *__restrict__ query, int first, int last, int k,
-                   float *__restrict__ part_d, int32_t *__restrict__ part_i)
+// The candidate step in ONE launch: every block (optionally) derives the query's ring key from its descriptor
+// (polarcontext_invkeys_mat_.back(), Scancontext.cpp:333: row means in Eigen's order, narrowed to float), scans
+// KNN_PER_BLOCK ring keys of [first, last) and emits its k best; the last block to finish (ticket) merges the
+// per-block lists.  Entries the scan could not fill (fewer than k valid neighbours) repeat the best one in
+// `cand`, so that the candidate search that follows can run on exactly k ids.
+__device__ void knn_merge(const float *__restrict__ part_d, const int32_t *__restrict__ part_i, int n_part, int k,
+                          int fallback, float *__restrict__ out_d, int32_t *__restrict__ out_i, int32_t *__restrict__ cand)
 {
+    __shared__ float fd[KNN_MAX];
+    __shared__ int32_t fi[KNN_MAX];
+    float ld[KNN_MAX];
+    int li[KNN_MAX];
+#pragma unroll
+    for (int j = 0; j < KNN_MAX; ++j) { ld[j] = INFINITY; li[j] = -1; }
+    for (int e = threadIdx.x; e < n_part; e += KNN_THREADS) {
+        const int32_t pi = __ldcg(part_i + e);
+        if (pi >= 0) knn_insert(ld, li, k, __ldcg(part_d + e), pi);
+    }
+    knn_block_select(ld, li, k, fd, fi);
+    if ((int)threadIdx.x < k) {
+        out_d[threadIdx.x] = fd[threadIdx.x];
+        out_i[threadIdx.x] = fi[threadIdx.x];
+        if (cand) cand[threadIdx.x] = fi[threadIdx.x] >= 0 ? fi[threadIdx.x] : (fi[0] >= 0 ? fi[0] : fallback);
+    }
+}
+
+__global__ void __launch_bounds__(KNN_THREADS)
+sc_knn_kernel(const float *__restrict__ rkeys, const float *__restrict__ query_key, const double *__restrict__ query_desc,
+              int first, int last, int k, float *__restrict__ part_d, int32_t *__restrict__ part_i,
+              unsigned int *__restrict__ ticket, float *__restrict__ out_d, int32_t *__restrict__ out_i,
+              int32_t *__restrict__ cand, float *__restrict__ key_out)
+{
+    __shared__ float skey[R];
+    __shared__ int is_last;
+    if (query_desc) {
+        if (threadIdx.x < R) {
+            const int r = threadIdx.x;
+            double acc[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = query_desc[i * R + r];
+            for (int i = 4; i < S; i += 4)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[j] += query_desc[(i + j) * R + r];
+            skey[r] = (float)(((acc[0] + acc[2]) + (acc[1] + acc[3])) / (double)S);
+            if (blockIdx.x == 0 && key_out) key_out[r] = skey[r];
+        }
+    } else if (threadIdx.x < R) {
+        skey[threadIdx.x] = query_key[threadIdx.x];
+    }
+    __syncthreads();
     float q[R];
 #pragma unroll
-    for (int i = 0; i < R; ++i) q[i] = query[i];
+    for (int i = 0; i < R; ++i) q[i] = skey[i];
     float ld[KNN_MAX];
     int li[KNN_MAX];
 #pragma unroll
@@ -759,43 +804,18 @@ sc_knn_scan_kernel(const float *__restrict__ rkeys, const float *__restrict__ qu
     for (int g = lo + threadIdx.x; g < hi; g += KNN_THREADS)
         knn_insert(ld, li, k, ringkey_l2(q, rkeys + (size_t)g * R), g);
     knn_block_select(ld, li, k, part_d + (size_t)blockIdx.x * k, part_i + (size_t)blockIdx.x * k);
-}
-
-// stage 2: one block merges the per-block lists; entries the scan could not fill (fewer than k valid
-// neighbours) repeat the best one, so that the candidate search below can run on exactly k ids
-__global__ void __launch_bounds__(KNN_THREADS)
-sc_knn_merge_kernel(const float *__restrict__ part_d, const int32_t *__restrict__ part_i, int n_part, int k,
-                    int fallback, float *__restrict__ out_d, int32_t *__restrict__ out_i, int32_t *__restrict__ cand)
-{
-    __shared__ float fd[KNN_MAX];
-    __shared__ int32_t fi[KNN_MAX];
-    float ld[KNN_MAX];
-    int li[KNN_MAX];
-#pragma unroll
-    for (int j = 0; j < KNN_MAX; ++j) { ld[j] = INFINITY; li[j] = -1; }
-    for (int e = threadIdx.x; e < n_part; e += KNN_THREADS)
-        if (part_i[e] >= 0) knn_insert(ld, li, k, part_d[e], part_i[e]);
-    knn_block_select(ld, li, k, fd, fi);
-    if ((int)threadIdx.x < k) {
-        out_d[threadIdx.x] = fd[threadIdx.x];
-        out_i[threadIdx.x] = fi[threadIdx.x];
-        if (cand) cand[threadIdx.x] = fi[threadIdx.x] >= 0 ? fi[threadIdx.x] : (fi[0] >= 0 ? fi[0] : fallback);
+    // last block done: merge
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int tk = atomicAdd(ticket, 1u);
+        is_last = (tk == gridDim.x - 1);
+        if (is_last) *ticket = 0u;
     }
-}
-
-// query ring key (f32) from a descriptor on the device: polarcontext_invkeys_mat_.back() (Scancontext.cpp:333)
-__global__ void __launch_bounds__(32)
-sc_query_ringkey_kernel(const double *__restrict__ desc, float *__restrict__ key)
-{
-    const int r = threadIdx.x;
-    if (r >= R) return;
-    double acc[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i] = desc[i * R + r];
-    for (int i = 4; i < S; i += 4)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] += desc[(i + j) * R + r];
-    key[r] = (float)(((acc[0] + acc[2]) + (acc[1] + acc[3])) / (double)S);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    knn_merge(part_d, part_i, (int)gridDim.x * k, k, first, out_d, out_i, cand);
 }
 
 // canonical 20x60 column-major descriptor(s) -> the three device records of a keyframe:
@@ -933,6 +953,7 @@ int init_bin_state(nrs_sc_db *db, cudaStream_t stream)
     NRS_CUDA(cudaMemcpyAsync(db->d_bstate, h.data(), h.size() * sizeof(SearchState), cudaMemcpyHostToDevice, stream));
     NRS_CUDA(cudaMemsetAsync(db->d_gticket, 0, sizeof(unsigned int), stream));
     NRS_CUDA(cudaMemsetAsync(db->d_ngen, 0, sizeof(unsigned int), stream));
+    NRS_CUDA(cudaMemsetAsync(db->d_knn_out, 0, 72 * sizeof(float), stream));        // incl. the k-NN kernel's ticket at [68]
     NRS_CUDA(cudaStreamSynchronize(stream));
     return NRS_OK;
 }
@@ -1073,7 +1094,7 @@ int nrs_sc_db_create(nrs_ctx *ctx, int capacity_hint, nrs_sc_db **out)
         (e = cudaMalloc(&db->d_state, sizeof(SearchState))) != cudaSuccess ||
         (e = cudaMalloc(&db->d_result, sizeof(nrs_sc_result))) != cudaSuccess ||
         (e = cudaMalloc(&db->d_query, DESC * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc(&db->d_knn_out, 68 * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&db->d_knn_out, 72 * sizeof(float))) != cudaSuccess ||
         (e = cudaMallocHost(&db->h_result, sizeof(nrs_sc_result))) != cudaSuccess ||
         (e = cudaMallocHost(&db->h_query, DESC * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&db->d_ngen, sizeof(unsigned int))) != cudaSuccess ||
@@ -1427,17 +1448,18 @@ int nrs_sc_xchg_set_timeout_ms(nrs_sc_db *db, int ms)
     return NRS_OK;
 }
 
-// enqueue the two k-NN kernels: d_key (20 floats, device) against ring keys [first, last)
-static int launch_knn(nrs_sc_db *db, const float *d_key, int first, int last, int k)
+// enqueue the k-NN kernel: ring keys [first, last) against d_key (20 floats, device) or, when d_desc is given,
+// against the ring key of that descriptor (derived in the kernel and also stored to d_knn_out + 48)
+static int launch_knn(nrs_sc_db *db, const float *d_key, const double *d_desc, int first, int last, int k)
 {
     nrs_ctx *ctx = db->ctx;
     const int n = std::max(0, last - first);
     const int blocks = std::max(1, (n + KNN_PER_BLOCK - 1) / KNN_PER_BLOCK);
     float *out_d = db->d_knn_out;
     int32_t *out_i = reinterpret_cast<int32_t *>(db->d_knn_out + 16), *cand = reinterpret_cast<int32_t *>(db->d_knn_out + 32);
-    sc_knn_scan_kernel<<<blocks, KNN_THREADS, 0, ctx->stream>>>(db->d_rkeys, d_key, first, last, k, db->d_knn_pd, db->d_knn_pi);
-    NRS_LAUNCHED();
-    sc_knn_merge_kernel<<<1, KNN_THREADS, 0, ctx->stream>>>(db->d_knn_pd, db->d_knn_pi, blocks * k, k, first, out_d, out_i, cand);
+    sc_knn_kernel<<<blocks, KNN_THREADS, 0, ctx->stream>>>(db->d_rkeys, d_key, d_desc, first, last, k, db->d_knn_pd, db->d_knn_pi,
+                                                          reinterpret_cast<unsigned int *>(db->d_knn_out + 68), out_d, out_i, cand,
+                                                          db->d_knn_out + 48);
     NRS_LAUNCHED();
     return NRS_OK;
 }
@@ -1453,7 +1475,7 @@ int nrs_sc_knn(nrs_sc_db *db, const float *ringkey20_host, int first, int last, 
     NRS_CUDA(cudaSetDevice(ctx->device));
     float *d_key = db->d_knn_out + 48;
     NRS_CUDA(cudaMemcpyAsync(d_key, ringkey20_host, R * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    int rc = launch_knn(db, d_key, first, last, k);
+    int rc = launch_knn(db, d_key, nullptr, first, last, k);
     if (rc) return rc;
     float h[32];
     NRS_CUDA(cudaMemcpyAsync(h, db->d_knn_out, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1484,10 +1506,7 @@ int nrs_sc_detect_knn(nrs_sc_db *db, const double *query_host, int first, int la
     }
     memcpy(db->h_query, query_host, DESC * sizeof(double));
     NRS_CUDA(cudaMemcpyAsync(db->d_query, db->h_query, DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    float *d_key = db->d_knn_out + 48;
-    sc_query_ringkey_kernel<<<1, 32, 0, ctx->stream>>>(db->d_query, d_key);
-    NRS_LAUNCHED();
-    int rc = launch_knn(db, d_key, first, last, k);
+    int rc = launch_knn(db, nullptr, db->d_query, first, last, k);
     if (rc) return rc;
     // the k ids stay on the device and feed the candidate search directly (Scancontext.cpp:380-396)
     const int32_t *d_cand = reinterpret_cast<const int32_t *>(db->d_knn_out + 32);

@@ -307,7 +307,6 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
             for (int i = 0; i < 15; ++i) W[i] = sm.win[lane & 3][i + (lane >> 2)];
             const bool hasB = lane < S - 32;
             const float cqf = (float)sm.cq;
-            const double cq = sm.cq;
             float my_ub = INFINITY;                    // warp-uniform
             bool parked = false;                       // warp-uniform
             for (int item = lo + warp; item < hi; item += BWARPS) {
@@ -476,7 +475,11 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
             const unsigned int n_list = *reinterpret_cast<volatile unsigned int *>(&stq->n_surv);
             const float bound = unord_f32(*reinterpret_cast<volatile unsigned int *>(&stq->gub));
             const double cq = sm.cq;
-            for (unsigned int base = warp * 32; base < n_list; base += BWARPS * 32) {
+            // Work items = (surviving keyframe, one of its candidate shifts), dealt round-robin to the CTA's warps:
+            // every warp walks the whole list (it is short) and certifies the items whose running number is its own.
+            // Order of the reference's scans: (dist, keyframe position, shift) lexicographic.
+            int wcount = 0;
+            for (unsigned int base = 0; base < n_list; base += 32) {
                 const unsigned int i = base + lane;
                 const int4 e = (i < n_list) ? __ldcg(reinterpret_cast<const int4 *>(survq + i)) : make_int4(0, 0, 0x7f800000, 0);
                 unsigned int todo = __ballot_sync(0xffffffffu, i < n_list && !(__int_as_float(e.z) - EPS_C > bound));
@@ -485,16 +488,28 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
                     todo &= todo - 1;
                     const int it = __shfl_sync(0xffffffffu, e.x, src), cd = __shfl_sync(0xffffffffu, e.y, src);
                     const float ckf = __int_as_float(__shfl_sync(0xffffffffu, e.w, src));
-                    const int kf = cand ? cand[it] : first + it;
-                    __syncwarp();
-                    *reinterpret_cast<uint2 *>(&ws.krec[2 * lane]) = __ldcg(reinterpret_cast<const uint2 *>(brec + (size_t)kf * BIN_WORDS + 2 * lane));
-                    __syncwarp();
-                    const unsigned long long kzero = (((unsigned long long)ws.krec[61] << 32) | ws.krec[60]) & MASK60;
-                    double dd;
-                    int ds;
-                    certify_dist_bin(sm.qcol, cq, ws.krec, (double)ckf, qzero, kzero, ws.scr, cd & 0xff, (unsigned int)(cd >> 8) & 0x7fu,
-                                     lane, dd, ds);
-                    if (better(dd, it, d, p)) { d = dd; p = it; ix = kf; sh = ds; }
+                    unsigned int bits = (unsigned int)(cd >> 8) & 0x7fu;
+                    bool loaded = false;
+                    int kf = 0;
+                    unsigned long long kzero = 0ull;
+                    while (bits) {
+                        const unsigned int one = bits & (0u - bits);
+                        bits &= bits - 1;
+                        if ((wcount++) % BWARPS != warp) continue;
+                        if (!loaded) {
+                            kf = cand ? cand[it] : first + it;
+                            __syncwarp();
+                            *reinterpret_cast<uint2 *>(&ws.krec[2 * lane]) =
+                                __ldcg(reinterpret_cast<const uint2 *>(brec + (size_t)kf * BIN_WORDS + 2 * lane));
+                            __syncwarp();
+                            kzero = (((unsigned long long)ws.krec[61] << 32) | ws.krec[60]) & MASK60;
+                            loaded = true;
+                        }
+                        double dd;
+                        int ds;
+                        certify_dist_bin(sm.qcol, cq, ws.krec, (double)ckf, qzero, kzero, ws.scr, cd & 0xff, one, lane, dd, ds);
+                        if (dd < d || (dd == d && (it < p || (it == p && ds < sh)))) { d = dd; p = it; ix = kf; sh = ds; }
+                    }
                 }
             }
         } else if (warp == 0) {
@@ -524,7 +539,7 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
                 const int op = __shfl_xor_sync(0xffffffffu, p, off);
                 const int oi = __shfl_xor_sync(0xffffffffu, ix, off);
                 const int os = __shfl_xor_sync(0xffffffffu, sh, off);
-                if (better(od, op, d, p)) { d = od; p = op; ix = oi; sh = os; }
+                if (od < d || (od == d && (op < p || (op == p && os < sh)))) { d = od; p = op; ix = oi; sh = os; }
             }
             ix = (d < SENTINEL) ? ix * idx_scale + idx_offset : 0;
             if (!(d < SENTINEL)) sh = 0;

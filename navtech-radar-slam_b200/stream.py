@@ -9,7 +9,7 @@ import time
 
 import numpy as np
 
-from . import orora, scancontext
+from . import orora, posemanager, scancontext
 
 
 def radar_files(datadir):
@@ -19,52 +19,69 @@ def radar_files(datadir):
 
 def run_odometry(datadir, dataset="mulran", keypoint_extraction="cen2018", voxel_size=0.6, use_voxelization=True,
                  frame_rate=4.0, loop_detection=False, sc_dist_thres=0.2, ctx=None, out_dir=None, end_idx=-1,
-                 noise_bound=0.75, noise_bound_radial=0.1, noise_bound_tangential_deg=9.0):
+                 noise_bound=0.75, noise_bound_radial=0.1, noise_bound_tangential_deg=9.0, gt_rel=None,
+                 check_stop_motion=True):
     """Returns a dict with the relative poses (n-1, 4, 4), the chained trajectory (n, 4, 4), per-pair wall times
-    and, with loop_detection, (frame, loop_id, yaw) triples.  Writes est_traj.txt / time_taken.txt / loops.txt
-    into out_dir when given (one row per frame: stamp and the row-major 3x4 pose, like writeTraj)."""
+    and, with loop_detection, (frame, loop_id, yaw) triples.  With out_dir, writes the reference node's own
+    evaluation files (posemanager.SE2PoseManager: <dataset>_ORORA_<extraction>_{eval_odom, rel_error_odom,
+    time_taken, est_traj, gt_traj}.txt, scorable by ORORA/scripts/evaluate_odometry.py) plus loops.txt.
+    gt_rel: per pair (x, y, yaw) relative ground-truth motion as the reference's getXYYawPose returns it
+    (odometry.cpp:253-259); None writes identity ground truth."""
     files = radar_files(datadir)
     if end_idx >= 0:
         files = files[:end_idx + 1]
     loader = orora.RadarLoader(dataset, keypoint_extraction, voxel_size, use_voxelization, False, ctx=ctx)
-    est = orora.ORORA(dataset, "rot", True, False, True, 700, 0.049, noise_bound_radial,
+    est = orora.ORORA(dataset, "rot", True, False, check_stop_motion, 700, 0.049, noise_bound_radial,
                       np.deg2rad(noise_bound_tangential_deg), ctx=loader.ctx)
     params = orora.setParams(noise_bound, 1.0, False, 100, 1.4, 1e-6)
     mgr = None
     if loop_detection:
         mgr = scancontext.SCManager(loader.ctx)
         mgr.setSCdistThres(sc_dist_thres)
-    rel, traj, times, loops = [], [np.eye(4)], [], []
+    rel, traj, times, loops, skipped = [], [np.eye(4)], [], [], []
+    pm_out = posemanager.SE2PoseManager(out_dir, dataset, "ORORA", keypoint_extraction) if out_dir else None
+    curr_gt = np.eye(4)
     prev = None
     for i, name in enumerate(files):
-        t0 = time.perf_counter()
         cur = loader.extractFeature(datadir, name)
         if prev is not None:
             pm, cm = loader.matchFeatures(prev, cur)
-            T = est.calcTransform(params, 1.0 / frame_rate, pm, cm)
+            t0 = time.perf_counter()                                   # the node times the estimator only (odometry.cpp:197-251)
+            try:
+                T = est.calcTransform(params, 1.0 / frame_rate, pm, cm)
+            except orora._lib.NrsError as e:
+                # more correspondences than the solver holds (1024; only reachable with check_stop_motion off): the
+                # pair is reported and skipped with an Identity motion, like the reference's stop-motion gate
+                if e.code != orora._lib.NRS_ECAPACITY:
+                    raise
+                T = np.eye(4)
+                skipped.append(i)
+            dt = time.perf_counter() - t0
             rel.append(T)
             traj.append(traj[-1] @ T)
-            times.append(time.perf_counter() - t0)
+            times.append(dt)
+            if pm_out is not None:
+                Tgt = posemanager.xyyaw2se2(gt_rel[i - 1], dataset) if gt_rel is not None else np.eye(4)
+                curr_gt = curr_gt @ Tgt
+                pm_out.writePoseError(Tgt, T)                          # odometry.cpp:281-285
+                pm_out.writePose(Tgt, T, prev.t_crietria_, cur.t_crietria_, loader.time_unit_denominator_)
+                pm_out.writeTraj(traj[-1], pm_out.est_traj_path_)
+                pm_out.writeTraj(curr_gt, pm_out.gt_traj_path_)
+                pm_out.writeTimeTaken(int(dt * 1e6), Tgt)
         prev = cur
         if mgr is not None:
-            # the node publishes the features with z = feat_in_cart_ row 2 (+1.0): odometry.cpp:305-316
-            z = cur.feat_in_cart_[2] + 1.0
-            cloud = np.column_stack([cur.feat_in_cart_[0], cur.feat_in_cart_[1], z]).astype(np.float32)
+            # the node zeroes z and publishes the local cloud with z = 1.0 whatever feat_in_cart_'s third row holds
+            # (eigen2pcl(..., true) then p.z = 1.0: odometry.cpp:305-316)
+            cloud = np.column_stack([cur.feat_in_cart_[0], cur.feat_in_cart_[1], np.ones(cur.feat_in_cart_.shape[1])]).astype(np.float32)
             mgr.makeAndSaveScancontextAndKeys(cloud)
             loop_id, yaw = mgr.detectLoopClosureID()
             if loop_id >= 0:
                 loops.append((i, loop_id, yaw))
     out = {"files": files, "relative": np.array(rel), "trajectory": np.array(traj), "seconds": np.array(times),
-           "loops": loops}
+           "loops": loops, "skipped_pairs": skipped}
     if out_dir:
-        os.makedirs(out_dir, exist_ok=True)
-        with open(os.path.join(out_dir, "est_traj.txt"), "w") as f:
-            for name, P in zip(files, traj):
-                f.write(name.split(".")[0] + " " + " ".join(f"{v:.9g}" for v in P[:3].reshape(-1)) + "\n")
-        with open(os.path.join(out_dir, "time_taken.txt"), "w") as f:
-            for s in times:
-                f.write(f"{int(s * 1e6)}\n")
         with open(os.path.join(out_dir, "loops.txt"), "w") as f:
             for i, l, y in loops:
                 f.write(f"{i} {l} {y:.9g}\n")
+        out["eval_odom"] = pm_out.output_pose_path_
     return out

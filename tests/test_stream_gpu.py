@@ -80,9 +80,19 @@ def test_png_directory_driver(nrs, ctx, synth, tmp_path):
     for k in range(6):
         raw = synth.radar_frame(world, (2.5 * k, 0.1 * k, np.deg2rad(1.0) * k), seed=900 + k, dataset="mulran")
         assert cv2.imwrite(str(tmp_path / f"{1560000000000000000 + k * 250000000}.png"), raw)
-    r = stream.run_odometry(str(tmp_path), "mulran", "cen2019", loop_detection=True, ctx=ctx, out_dir=str(tmp_path / "out"))
+    gt = [(2.5, 0.1, -np.deg2rad(1.0))] * 5          # MulRan-style ground truth: the reference negates its yaw (SE2posemanager.hpp:181-183)
+    r = stream.run_odometry(str(tmp_path), "mulran", "cen2019", loop_detection=True, ctx=ctx, out_dir=str(tmp_path / "out"), gt_rel=gt)
     assert r["relative"].shape == (5, 4, 4) and r["trajectory"].shape == (6, 4, 4)
     for T in r["relative"]:                                   # each step: ~2.5 m forward, ~1 degree
         assert abs(T[0, 3] - 2.5) < 0.6 and abs(np.arctan2(T[1, 0], T[0, 0]) - np.deg2rad(1.0)) < 2e-2
     assert abs(r["trajectory"][-1][0, 3] - 12.5) < 2.5
-    assert (tmp_path / "out" / "est_traj.txt").read_text().count("\n") == 6
+    # the node's own evaluation files (SE2posemanager.hpp:151-245), one row per scan pair
+    out = tmp_path / "out"
+    ev = np.loadtxt(out / "mulran_ORORA_cen2019_eval_odom.txt", delimiter=",")      # as evaluate_odometry.py reads it
+    assert ev.shape == (5, 8) and np.allclose(ev[:, 0], 2.5) and np.all(np.abs(ev[:, 3] - 2.5) < 0.6)
+    assert np.all(np.abs(ev[:, 5] - np.deg2rad(1.0)) < 2e-2) and np.all(np.abs(ev[:, 2] - np.deg2rad(1.0)) < 1e-5)
+    rel = np.loadtxt(out / "mulran_ORORA_cen2019_rel_error_odom.txt", delimiter=",")
+    assert rel.shape == (5, 5) and np.all(rel[:, 0] < 0.6) and np.all(rel[:, 1] < 1.5)
+    assert (out / "mulran_ORORA_cen2019_time_taken.txt").read_text().count("\n") == 5
+    assert (out / "mulran_ORORA_cen2019_est_traj.txt").read_text().count("\n") == 5
+    assert (out / "mulran_ORORA_cen2019_gt_traj.txt").read_text().count("\n") == 5
