@@ -361,6 +361,34 @@ int nrs_match(nrs_ctx *ctx, const nrs_frame *prev, const nrs_frame *curr, float 
               int32_t *query_idx, int32_t *train_idx, double *prev_2xN, double *curr_2xN,
               int64_t *prev_t, int64_t *curr_t, int *N);
 
+/* ---- loop verification behind the ScanContext detector (SC/../src/laserPosegraphOptimization.cpp:355-406) ---- */
+
+/* pcl::IterativeClosestPoint as doICPVirtualRelative configures it (:376-381) and its acceptance gate (:390-391) */
+typedef struct nrs_icp_params {
+    double  max_correspondence_distance;   /* 150 m (:377) */
+    int32_t max_iterations;                /* 100 (:378) */
+    double  transformation_epsilon;        /* 1e-6 (:379) */
+    double  euclidean_fitness_epsilon;     /* 1e-6 (:380) */
+    double  fitness_threshold;             /* loopFitnessScoreThreshold 0.3 (:390) */
+    int32_t min_correspondences;           /* 3 (pcl::Registration) */
+} nrs_icp_params;
+typedef struct nrs_icp_info {
+    int32_t converged;          /* icp.hasConverged() */
+    int32_t iterations;
+    int32_t state;              /* 1 iterations, 2 transform, 3 abs mse, 4 rel mse, 5 no correspondences */
+    int32_t n_correspondences;  /* of the last iteration */
+    double  fitness;            /* icp.getFitnessScore(): mean squared nearest-neighbour distance after alignment */
+    int32_t accepted;           /* converged && fitness <= fitness_threshold: the SC loop is kept */
+    int32_t pad_;
+} nrs_icp_info;
+void nrs_icp_default_params(nrs_icp_params *p);
+/* icp.setInputSource(src); icp.setInputTarget(tgt); icp.align(): point-to-point ICP of the current keyframe's
+ * cloud against the submap around the loop candidate (both in the loop keyframe's frame, float x,y,z per point,
+ * host).  T_out = icp.getFinalTransformation() as a column-major 4x4 (source -> target).  PCL is not vendored in
+ * the reference: this restates its published algorithm (icp_kernels.cu header), double-precision sums. */
+int nrs_icp_align(nrs_ctx *ctx, const float *src_xyz_Nsx3, int Ns, const float *tgt_xyz_Ntx3, int Nt,
+                  const nrs_icp_params *p, double T_out[16], nrs_icp_info *info);
+
 /* One iteration of the node's per-frame loop (odometry.cpp:153-284) in ONE call:
  *   curr = Loader.extractFeature(new frame); (prev_m, curr_m) = Loader.matchFeatures(prev, curr);
  *   T = orora_estimator.calcTransform(params, dt, prev_m, curr_m)

@@ -50,6 +50,19 @@ class ExtractParams(C.Structure):
                 ("keypoint_extraction", C.c_int32), ("zq", C.c_float), ("sigma_gauss", C.c_int32)]
 
 
+class IcpParams(C.Structure):
+    """nrs_icp_params (include/nrs_b200.h)."""
+    _fields_ = [("max_correspondence_distance", C.c_double), ("max_iterations", C.c_int32),
+                ("transformation_epsilon", C.c_double), ("euclidean_fitness_epsilon", C.c_double),
+                ("fitness_threshold", C.c_double), ("min_correspondences", C.c_int32)]
+
+
+class IcpInfo(C.Structure):
+    """nrs_icp_info (include/nrs_b200.h)."""
+    _fields_ = [("converged", C.c_int32), ("iterations", C.c_int32), ("state", C.c_int32), ("n_correspondences", C.c_int32),
+                ("fitness", C.c_double), ("accepted", C.c_int32), ("pad_", C.c_int32)]
+
+
 class FrameInfo(C.Structure):
     """nrs_frame_info (include/nrs_b200.h)."""
     _fields_ = [("n_candidates", C.c_int32), ("j_consumed", C.c_int32), ("l_regions", C.c_int32),
@@ -150,6 +163,9 @@ def _declare(L):
     L.nrs_frame_get.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.nrs_frame_get_stages.argtypes = [vp, vp, vp, vp, vp]
     L.nrs_match.argtypes = [vp, vp, vp, C.c_float, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.nrs_icp_default_params.restype = None
+    L.nrs_icp_default_params.argtypes = [vp]
+    L.nrs_icp_align.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp]
     L.nrs_orora_pair.argtypes = [vp, vp, vp, i32, i32, vp, C.c_int64, vp, f64, C.POINTER(vp), vp, vp, vp]
     for name in declared_symbols():
         fn = getattr(L, name, None)

@@ -326,3 +326,87 @@ def orora_calc_transform(prev, curr, vel_x, params=None, delta_t=0.25, beta=0.04
                            int(check_stop_motion), stop_thr, C.byref(v), _p(T), _p(clique), _p(fin), C.byref(info))
     return ({"T": T.reshape(4, 4).T.copy(), "clique": clique[:info.M].copy(),
              "final_inliers": fin[:info.n_final_inliers].copy(), "info": info, "valid": bool(info.valid)}, v.value)
+
+
+# -------------------------------------------------------------------------------------------------
+# loop verification: pcl::IterativeClosestPoint as doICPVirtualRelative configures it
+# (pgo/SC-A-LOAM/src/laserPosegraphOptimization.cpp:355-406).  PCL is not vendored in the reference and not
+# installed here: this restates its published algorithm (registration/impl/icp.hpp,
+# default_convergence_criteria.hpp, transformation_estimation_svd.hpp) -- PARITY UNPINNED against PCL itself.
+# Float points / distances, double sums; nearest neighbours exhaustively, lowest index on ties.
+# -------------------------------------------------------------------------------------------------
+def _nn(src, tgt):
+    best_d = np.full(src.shape[0], np.inf, dtype=np.float32)
+    best_i = np.zeros(src.shape[0], dtype=np.int64)
+    for a in range(0, tgt.shape[0], 4096):
+        t = tgt[a:a + 4096]
+        dx = src[:, None, 0] - t[None, :, 0]
+        dy = src[:, None, 1] - t[None, :, 1]
+        dz = src[:, None, 2] - t[None, :, 2]
+        d2 = (dx * dx + dy * dy + dz * dz).astype(np.float32)
+        j = np.argmin(d2, axis=1)
+        dj = d2[np.arange(src.shape[0]), j]
+        upd = dj < best_d
+        best_d[upd], best_i[upd] = dj[upd], j[upd] + a
+    return best_i, best_d
+
+
+def _xform32(T, p):
+    R, t = T[:3, :3].astype(np.float32), T[:3, 3].astype(np.float32)
+    x = R[0, 0] * p[:, 0] + R[0, 1] * p[:, 1] + R[0, 2] * p[:, 2] + t[0]
+    y = R[1, 0] * p[:, 0] + R[1, 1] * p[:, 1] + R[1, 2] * p[:, 2] + t[1]
+    z = R[2, 0] * p[:, 0] + R[2, 1] * p[:, 1] + R[2, 2] * p[:, 2] + t[2]
+    return np.stack([x, y, z], axis=1).astype(np.float32)
+
+
+def icp_align(src_xyz, tgt_xyz, max_corr_dist=150.0, max_iterations=100, transformation_epsilon=1e-6,
+              euclidean_fitness_epsilon=1e-6, fitness_threshold=0.3, min_correspondences=3):
+    """-> dict(T (4,4) source->target, converged, iterations, state, fitness, accepted)"""
+    src = np.ascontiguousarray(src_xyz, dtype=np.float32).reshape(-1, 3).copy()
+    tgt = np.ascontiguousarray(tgt_xyz, dtype=np.float32).reshape(-1, 3)
+    final = np.eye(4)
+    out = {"T": final, "converged": False, "iterations": 0, "state": 5, "fitness": float("inf"), "accepted": False, "n_corr": 0}
+    if src.shape[0] == 0 or tgt.shape[0] == 0:
+        return out
+    prev_mse, it, state, conv = np.finfo(np.float64).max, 0, 0, False
+    while True:
+        idx, d2 = _nn(src, tgt)
+        keep = d2.astype(np.float64) <= max_corr_dist * max_corr_dist
+        n = int(keep.sum())
+        out["n_corr"] = n
+        if n < min_correspondences:
+            state, conv = 5, False
+            break
+        s, t = src[keep].astype(np.float64), tgt[idx[keep]].astype(np.float64)
+        cs, ct = s.sum(0) / n, t.sum(0) / n
+        H = s.T @ t - n * np.outer(cs, ct)
+        U, _, Vt = np.linalg.svd(H)
+        V = Vt.T
+        D = np.diag([1.0, 1.0, -1.0 if np.linalg.det(U) * np.linalg.det(V) < 0 else 1.0])
+        R = V @ D @ U.T
+        T = np.eye(4)
+        T[:3, :3], T[:3, 3] = R, ct - R @ cs
+        src = _xform32(T, src)
+        final = T @ final
+        it += 1
+        if it >= max_iterations:
+            state, conv = 1, True
+            break
+        cos_angle = 0.5 * (T[0, 0] + T[1, 1] + T[2, 2] - 1.0)
+        tr2 = float(T[0, 3] ** 2 + T[1, 3] ** 2 + T[2, 3] ** 2)
+        if cos_angle >= 1.0 - transformation_epsilon and tr2 <= transformation_epsilon:
+            state, conv = 2, True
+            break
+        mse = float(d2[keep].astype(np.float64).sum() / n)
+        if abs(mse - prev_mse) < 1e-12:
+            state, conv = 3, True
+            break
+        if abs(mse - prev_mse) / prev_mse < euclidean_fitness_epsilon:
+            state, conv = 4, True
+            break
+        prev_mse = mse
+    _, d2 = _nn(src, tgt)
+    fitness = float(d2.astype(np.float64).sum() / src.shape[0])
+    out.update(T=final, converged=conv, iterations=it, state=state, fitness=fitness,
+               accepted=bool(conv and fitness <= fitness_threshold))
+    return out
