@@ -205,6 +205,74 @@ void fe_cen2018_sigma(const float *q, int rows, int cols, float *sigma_q)
     }
 }
 
+
+/* ---- exp() of a double, narrowed to float, INDEPENDENT OF THE PLATFORM'S libm --------------------------------
+ * The reference stores exp(double) into a float (features.cpp:98-99).  libm's exp is not correctly rounded (glibc:
+ * < 0.52 ulp, CUDA: <= 1 ulp), so two platforms can disagree in the last bit of the double -- which reaches the
+ * float only when the double lands within a couple of ulps of a float rounding boundary (a mid-point between two
+ * floats).  Exactly there, and for results in the float-subnormal range, the value is recomputed in double-double
+ * arithmetic (~100 bits: Cody-Waite reduction by ln2, x / 512, degree-8 Taylor series, nine squarings of
+ * (1 + s)^2 - 1) and rounded once: everywhere the result is float(correctly rounded double exp(x)).  The same
+ * operation sequence is compiled on the CPU (-ffp-contract=off) and on the GPU (--fmad=false), so both sides agree
+ * bit for bit by construction.  Valid for x <= 0 (the only use: x = -0.5 t^2). */
+typedef struct { double hi, lo; } dd_t;
+static dd_t dd_fast_two_sum(double a, double b) { dd_t r; r.hi = a + b; r.lo = b - (r.hi - a); return r; }
+static dd_t dd_two_sum(double a, double b)
+{
+    dd_t r; r.hi = a + b; const double bb = r.hi - a; r.lo = (a - (r.hi - bb)) + (b - bb); return r;
+}
+static dd_t dd_two_prod(double a, double b)
+{
+    const double ca = 134217729.0 * a, cb = 134217729.0 * b;
+    const double ah = ca - (ca - a), al = a - ah, bh = cb - (cb - b), bl = b - bh;
+    dd_t r; r.hi = a * b; r.lo = ((ah * bh - r.hi) + ah * bl + al * bh) + al * bl; return r;
+}
+static dd_t dd_add(dd_t a, dd_t b) { dd_t s = dd_two_sum(a.hi, b.hi); s.lo += a.lo + b.lo; return dd_fast_two_sum(s.hi, s.lo); }
+static dd_t dd_mul(dd_t a, dd_t b)
+{
+    dd_t p = dd_two_prod(a.hi, b.hi); p.lo += a.hi * b.lo + a.lo * b.hi; return dd_fast_two_sum(p.hi, p.lo);
+}
+static double exp_dd(double x)
+{
+    if (!(x > -800.0)) return 0.0;
+    if (x >= 0.0) return 1.0;
+    const double k = rint(x * 1.4426950408889634);
+    /* r = x - k ln2, ln2 = 0x1.62e42fefa39efp-1 + 0x1.abc9e3b39803fp-56 */
+    dd_t kl = dd_two_prod(k, 0.6931471805599453);
+    kl.lo += k * 2.3190468138462996e-17;
+    kl = dd_fast_two_sum(kl.hi, kl.lo);
+    dd_t neg; neg.hi = -kl.hi; neg.lo = -kl.lo;
+    dd_t xx; xx.hi = x; xx.lo = 0.0;
+    dd_t r = dd_add(xx, neg);
+    r.hi *= 0.001953125; r.lo *= 0.001953125;               /* / 512, exact */
+    /* s = exp(r) - 1 = r (1 + r/2 (1 + r/3 (... (1 + r/8)))) */
+    const double inv[9] = {0, 1.0, 0.5, 0.3333333333333333, 0.25, 0.2, 0.16666666666666666, 0.14285714285714285, 0.125};
+    const double invl[9] = {0, 0, 0, 1.850371707708594e-17, 0, -1.1102230246251566e-17, 9.25185853854297e-18, 7.93016446160826e-18, 0};
+    dd_t one; one.hi = 1.0; one.lo = 0.0;
+    dd_t acc = one;
+    for (int n = 8; n >= 2; --n) {
+        dd_t c; c.hi = inv[n]; c.lo = invl[n];
+        acc = dd_add(one, dd_mul(dd_mul(r, c), acc));
+    }
+    dd_t s = dd_mul(r, acc);
+    for (int i = 0; i < 9; ++i) {                            /* (1 + s)^2 - 1 = 2 s + s^2 */
+        dd_t s2 = dd_mul(s, s);
+        dd_t t; t.hi = 2.0 * s.hi; t.lo = 2.0 * s.lo;
+        s = dd_add(t, s2);
+    }
+    const dd_t e = dd_add(one, s);
+    return ldexp(e.hi, (int)k);                           /* |k| <= 1155: the scaling is exact above the double-subnormal range */
+}
+static float exp_to_float(double x)
+{
+    double e = exp(x);
+    unsigned long long b;
+    memcpy(&b, &e, sizeof(b));
+    const long long low = (long long)(b & 0x1fffffffull) - 0x10000000ll;      /* distance to the float mid-point, in double ulps */
+    if ((low >= -2 && low <= 2) || (e < 1.2e-38 && x > -110.0)) e = exp_dd(x);
+    return (float)e;
+}
+
 /* :94-113 peak centres per azimuth; y is also written out (nullable) for stage-wise comparison.
  * Returns the number of targets; out_a/out_r hold (azimuth, range bin) azimuth-major like :118-128. */
 int fe_cen2018_scan(const float *q, const float *p, const float *sigma_q, int rows, int cols, float zq,
@@ -218,8 +286,8 @@ int fe_cen2018_scan(const float *q, const float *p, const float *sigma_q, int ro
         for (int j = min_range; j < cols; ++j) {
             const float qv = q[(size_t)i * cols + j], pv = p[(size_t)i * cols + j];
             /* pow(float, int) promotes to double in C++11: the float quotient is squared exactly */
-            const float nqp = exp(-0.5 * pow((double)((qv - pv) / sigma_q[i]), 2));
-            const float npp = exp(-0.5 * pow((double)(pv / sigma_q[i]), 2));
+            const float nqp = exp_to_float(-0.5 * pow((double)((qv - pv) / sigma_q[i]), 2));
+            const float npp = exp_to_float(-0.5 * pow((double)(pv / sigma_q[i]), 2));
             const float b = nqp - npp;
             const float y = qv * (1 - nqp) + pv * b;
             if (y_out) y_out[(size_t)i * cols + j] = y;
@@ -239,3 +307,7 @@ int fe_cen2018_scan(const float *q, const float *p, const float *sigma_q, int ro
     free(peak);
     return k;
 }
+
+/* test hooks: the double-double exp and the float narrowing, checked against an arbitrary-precision exp */
+double oracle_exp_dd(double x) { return exp_dd(x); }
+float oracle_exp_to_float(double x) { return exp_to_float(x); }

@@ -282,3 +282,25 @@ def test_cen2018_c_loops_against_numpy_rederivation(F):
     y = (q * (np.float32(1) - nqp)).astype(np.float32) + (p * (nqp - npp).astype(np.float32)).astype(np.float32)
     d = np.abs(y[:, 58:].astype(np.float64) - st["y"][:, 58:])
     assert d.max() <= 2e-7 and (y[:, 58:].view(np.uint32) != st["y"][:, 58:].view(np.uint32)).mean() < 0.01
+
+
+def test_exp_to_float_is_libm_independent():
+    """cen2018's exp() narrowed to float (features.cpp:98-99): the double-double evaluation is the correctly
+    rounded double exp (against decimal's 60-digit exp), and exp_to_float equals float(correctly rounded exp)
+    on random, tiny, float-subnormal and squared-float arguments."""
+    import ctypes as C
+    import decimal
+    from oracle import pyoracle as O
+    O.build()
+    L = O.lib()
+    L.oracle_exp_dd.restype, L.oracle_exp_dd.argtypes = C.c_double, [C.c_double]
+    L.oracle_exp_to_float.restype, L.oracle_exp_to_float.argtypes = C.c_float, [C.c_double]
+    decimal.getcontext().prec = 60
+    rng = np.random.default_rng(1)
+    xs = np.concatenate([-rng.uniform(0, 110, 600), -10.0 ** rng.uniform(-12, 2, 300),
+                         -0.5 * (rng.standard_normal(600).astype(np.float32).astype(np.float64) ** 2),
+                         -rng.uniform(87.0, 104.0, 200), [0.0, -0.0, -745.2, -800.0, -1e-300]])
+    for x in xs:
+        cr = float(decimal.Decimal(float(x)).exp())
+        assert L.oracle_exp_dd(float(x)) == cr, x
+        assert np.float32(L.oracle_exp_to_float(float(x))) == np.float32(cr), x
