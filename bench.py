@@ -447,10 +447,21 @@ def run_ours(args, rank, world, local_rank):
             out["general_valued"] = general_block(d, q_dev, res_dev, n_local, n_rep, timed, peak, frec_bytes, qh)
             out["kdtree_mode"] = kdtree_block(sc, d, O, db, queries)
         if world == 1 and not args.no_orora:
-            try:
-                out["orora"] = orora_block(pkg, ctx)
-            except Exception as e:          # the headline line must still be printed
-                out["orora"] = {"error": repr(e)}
+            for name, fn in (("orora", orora_block), ("orora_oxford", orora_oxford_block)):
+                try:
+                    out[name] = fn(pkg, ctx)
+                except Exception as e:          # the headline line must still be printed
+                    out[name] = {"error": repr(e)}
+    # ---- BASELINE configs[4]: ORORA every frame + loop query against the growing (sharded) database -----------------
+    stream = None
+    if not args.no_orora:
+        try:
+            stream = stream_block(pkg, ctx, sc, rank, world, dev, args.stream_frames, db)
+        except Exception as e:
+            stream = {"error": repr(e)}
+    if rank == 0:
+        if stream is not None:
+            out["stream"] = stream
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
@@ -551,6 +562,125 @@ def orora_parity_gate(pkg, ctx, raws, dataset, cpu_res):
         g_prev = g_cur
     return (f"{len(cpu_res)} pairs vs oracle: cen2019 keypoints, Cartesian keypoints, ORB descriptors, match lists and cliques exact; "
             f"pose within {worst_t:.1e} m / {worst_r:.1e} rad (bar 1e-4 m / 1e-5 rad)")
+
+
+def orora_oxford_block(pkg, ctx, n_pairs=24, cpu_pairs=2):
+    """BASELINE configs[2]: the full pair on Oxford-format 400x3768 frames (uniform azimuths, CTS350), through the
+    fused entry point; parity gate and CPU baseline on the same pairs."""
+    import ctypes as C
+    import torch
+    L, orr = pkg.lib(), pkg.orora
+    raws_np = orora_frames("oxford", 6)
+    raws = [torch.from_numpy(r).pin_memory().numpy() for r in raws_np]
+    ep, sp = orr.extract_params("oxford"), orr.default_params()
+    T, info, n = np.zeros(16), orr.SolverInfo(), C.c_int()
+
+    def extract(k):
+        h = C.c_void_p()
+        pkg._lib.check(L.nrs_frame_extract(ctx.handle, raws[k % 6].ctypes.data_as(C.c_void_p), 400, raws[k % 6].shape[1], C.byref(ep), k, C.byref(h)))
+        return h
+
+    def pair(prev_h, k, vel):
+        cur, r = C.c_void_p(), raws[k % 6]
+        pkg._lib.check(L.nrs_orora_pair(ctx.handle, prev_h, r.ctypes.data_as(C.c_void_p), 400, r.shape[1], C.byref(ep), k, C.byref(sp), vel,
+                                        C.byref(cur), T.ctypes.data_as(C.c_void_p), C.byref(n), C.byref(info)))
+        L.nrs_frame_destroy(prev_h)
+        return cur, T[12] / 0.25
+
+    prev, vel = extract(0), 0.0
+    for k in range(1, 4):
+        prev, vel = pair(prev, k, vel)
+    ctx.sync()
+    t0 = time.perf_counter()
+    for k in range(4, 4 + n_pairs):
+        prev, vel = pair(prev, k, vel)
+    ctx.sync()
+    dt = (time.perf_counter() - t0) / n_pairs
+    L.nrs_frame_destroy(prev)
+    cpu_dt, cpu_res = orora_cpu_pairs(raws_np, "oxford", budget_s=8.0, max_pairs=cpu_pairs)
+    parity = orora_parity_gate(pkg, ctx, raws_np, "oxford", cpu_res)
+    frame_bytes = 400 * 3768 * 4
+    alg = frame_bytes + (frame_bytes + 964 * 964) + (964 * 964 + 32 * 2000)
+    return {"metric": "orora_scan_pairs_per_s", "value": 1.0 / dt, "unit": "pairs/s", "ms_per_pair": 1e3 * dt,
+            "workload": "synthetic Oxford-format 400x3768 frames (BASELINE configs[2]), cen2019 + remap + ORB + match + max-clique/GNC/COTE",
+            "matches": n.value, "clique": info.M, "parity_gate": parity,
+            "roofline": {"algorithmic_bytes_per_pair": alg, "frac_of_measured_peak": alg / dt / 1e9 / load_peaks()[0]},
+            "cpu_baseline": {"value": 1.0 / cpu_dt, "unit": "pairs/s", "kind": "port", "cores": len(os.sched_getaffinity(0)),
+                             "sample": f"{len(cpu_res)} pairs, oracle/frontend_ref.py (real cv2) + oracle/solver_ref.c"}}
+
+
+def stream_block(pkg, ctx, sc, rank, world, dev, n_frames, db_descs):
+    """BASELINE configs[4], the shape of a KAIST03 run: every frame goes through ORORA (extract + match + solve: the
+    fused pair call, on rank 0's GPU -- ORORA does not shard) and becomes a ScanContext keyframe that is
+    appended to the (keyframe-sharded) database and queried against it, newest 30 excluded like the node
+    (Scancontext.cpp:341-359).  Frames cycle through 8 synthetic radar frames (the cost does not depend on the
+    content); the keyframe descriptors are the seeded 10k set, one new descriptor per frame, so the database GROWS
+    from empty to n_frames.  Reports sustained frames/s and the loop query's latency against the database size."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    L, orr = pkg.lib(), pkg.orora
+    sdb = sc.ShardedSCDatabase(rank, world, ctx=ctx, exchange="auto")
+    raws, prev, ep, sp = None, None, None, None
+    T, info, n = np.zeros(16), orr.SolverInfo(), C.c_int()
+    ok = 1
+    if rank == 0:
+        try:
+            raws = [torch.from_numpy(r).pin_memory().numpy() for r in orora_frames("mulran", 8)]
+            ep, sp = orr.extract_params("mulran"), orr.default_params()
+            ep.keypoint_extraction = 1                  # cen2018: what the shipped launch file runs
+            h = C.c_void_p()
+            pkg._lib.check(L.nrs_frame_extract(ctx.handle, raws[0].ctypes.data_as(C.c_void_p), 400, raws[0].shape[1], C.byref(ep), 0, C.byref(h)))
+            prev = h
+        except Exception:
+            ok = 0
+    if world > 1:                                       # every rank proceeds, or none (a rank waiting in a broadcast would hang)
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = int(flag.item())
+    if not ok:
+        sdb.db.close()
+        return {"error": "stream block: front-end set-up failed on rank 0"}
+    desc_dev = torch.zeros(1200, dtype=torch.float64, device=dev)
+    vel, lat, sizes, loops = 0.0, [], [], 0
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for k in range(n_frames):
+        if rank == 0:
+            cur, r = C.c_void_p(), raws[(k + 1) % 8]
+            pkg._lib.check(L.nrs_orora_pair(ctx.handle, prev, r.ctypes.data_as(C.c_void_p), 400, r.shape[1], C.byref(ep), k + 1, C.byref(sp), vel,
+                                            C.byref(cur), T.ctypes.data_as(C.c_void_p), C.byref(n), C.byref(info)))
+            L.nrs_frame_destroy(prev)
+            prev, vel = cur, T[12] / 0.25
+        d = db_descs[k]
+        if world > 1:                                   # the new keyframe's descriptor reaches every rank (9.6 KB broadcast)
+            if rank == 0:
+                desc_dev.copy_(torch.from_numpy(d))
+            dist.broadcast(desc_dev, 0)
+            d = desc_dev.cpu().numpy()
+        sdb.append(d[None])
+        if k + 1 >= 31:                                 # detectLoopClosureID: too few keyframes before (:341-345)
+            tq = time.perf_counter()
+            res = sdb.query(d, 0, k + 1 - 30)
+            dtq = time.perf_counter() - tq
+            loops += res[0] < 0.2
+            if k % 50 == 0:
+                lat.append(dtq * 1e6); sizes.append(k + 1 - 30)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    if rank == 0:
+        L.nrs_frame_destroy(prev)
+    sdb.db.close()
+    return {"metric": "stream_frames_per_s", "value": n_frames / dt, "unit": "frames/s", "frames": n_frames, "n_gpus": world,
+            "what": "per frame: ORORA pair (cen2018, rank 0) + keyframe append + exhaustive loop query against the growing database "
+                    "(sharded over the ranks, newest 30 excluded)", "loops_found": int(loops),
+            "query_latency_us_vs_db_size": [[int(s_), round(l_, 1)] for s_, l_ in zip(sizes[::4], lat[::4])],
+            "query_latency_us_median": float(np.median(lat)) if lat else None,
+            "sensor_rate_hz": 4.0, "real_time_factor": (n_frames / dt) / 4.0}
 
 
 def orora_block(pkg, ctx, n_pairs=40, cpu_pairs=3):
@@ -728,7 +858,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-orora", action="store_true", help="skip the ORORA scan-pairs/s block")
+    ap.add_argument("--no-orora", action="store_true", help="skip the ORORA scan-pairs/s and stream blocks")
+    ap.add_argument("--stream-frames", type=int, default=1500, help="frames of the configs[4] stream block")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     rank = int(os.environ.get("RANK", "0"))
