@@ -44,17 +44,23 @@
 // Bound: with 256 B per keyframe the search is no longer HBM-bound; it is issue-bound (DP4A + POPC)
 // and, for a single query, launch/latency-bound.  Roofline figures are reported against both the
 // canonical 9600 B/keyframe and the 256 B actually streamed.
+#include <stdlib.h>
 #include <algorithm>
 
 #include "sc_common.cuh"
+
+#ifndef NRS_SC_BIN_REDUX_DEFAULT
+#define NRS_SC_BIN_REDUX_DEFAULT 0      // 1: REDUX.SUM fixed-point column sums, 0: shuffle tree (bench both: NRS_SC_BIN_REDUX)
+#endif
 
 using namespace nrs_sc;
 
 namespace nrs_sc {
 
-constexpr int BT = 512;                      // threads per CTA
+constexpr int BT = 384;                      // threads per CTA (2 CTAs per SM: 85 registers per thread, no spills in the hot loop)
 constexpr int BWARPS = BT / 32;
 constexpr int WIN_STRIDE = 36;               // words per byte-shifted copy of the doubled count vector
+constexpr int WORK_CAP = 192;                // certification work list (shared memory); longer lists are certified in place
 
 struct BinWarp {
     unsigned int nkb[16];                    // key column counts, one byte each (bytes 60..63 zero)
@@ -69,6 +75,9 @@ struct BinSmem {
     unsigned int  win[4][WIN_STRIDE];        // win[a] word w = counts of columns (4w + a + k) % 60, k = 0..3
     QCold         qc;                        // f64 sector key (and, for a non-binary query, norms)
     float         rtab[24];                  // 1 / sqrt(n), n = 0..20 (0 -> 0)
+    float         rcnt[64];                  // 1 / cnt, cnt = 0..60 (0 -> 0)
+    Survivor      work[WORK_CAP];            // certification: the entries the final bound could not rule out
+    unsigned int  n_work;
     unsigned int  qmask[64];
     unsigned char nqb[64];
     unsigned long long qzero;
@@ -82,9 +91,9 @@ struct BinSmem {
     BinWarp       w[BWARPS];
 };
 
-static __device__ __forceinline__ float u2f(unsigned int p)     // exact for p < 2^23, no I2F
+static __device__ __forceinline__ float u2f(unsigned int p)     // I2FP.F32.U32: one full-rate instruction on sm_100
 {
-    return __uint_as_float(p | 0x4B000000u) - 8388608.0f;
+    return __uint2float_rn(p);
 }
 static __device__ __forceinline__ bool c_ok(double c)            // see the header: <= 24 significant bits, sane range
 {
@@ -264,10 +273,11 @@ static __device__ __noinline__ void certify_dist_bin(const uint2 *__restrict__ q
     __syncwarp();
 }
 
+template <bool kRedux>
 __global__ void __launch_bounds__(BT, 2)
 sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__restrict__ desc, const double *__restrict__ keys,
                      const double *__restrict__ queries, int Q, const int32_t *__restrict__ cand, int first, int n_items,
-                     int n_chunks, int idx_scale, int idx_offset, Survivor *__restrict__ surv, size_t surv_stride,
+                     int n_chunks, int per, int idx_scale, int idx_offset, Survivor *__restrict__ surv, size_t surv_stride,
                      SearchState *__restrict__ st, BlockResult *__restrict__ block_results, unsigned int *__restrict__ gticket,
                      nrs_sc_result *__restrict__ results, XchgView xv)
 {
@@ -276,13 +286,13 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
     BinWarp &ws = sm.w[warp];
     if (t < 21) sm.rtab[t] = t ? (float)(1.0 / sqrt((double)t)) : 0.f;
 
+    if (t < 64) sm.rcnt[t] = t ? 1.0f / (float)t : 0.f;
     const int n_tiles = Q * n_chunks;
-    const int per = (n_items + n_chunks - 1) / n_chunks;
     const bool own = lane < S / 2;
     const int lb = own ? lane : 0;
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int q = tile / n_chunks, chunk = tile - q * n_chunks;
+        const int q = (Q == 1) ? 0 : tile / n_chunks, chunk = tile - q * n_chunks;
         const double *query = queries + (size_t)q * DESC;
         SearchState *stq = st + q;
         Survivor *survq = surv + (size_t)q * surv_stride;
@@ -306,6 +316,7 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
 #pragma unroll
             for (int i = 0; i < 15; ++i) W[i] = sm.win[lane & 3][i + (lane >> 2)];
             const bool hasB = lane < S - 32;
+            const unsigned int qz_any = (unsigned int)(qzero != 0ull);
             const float cqf = (float)sm.cq;
             float my_ub = INFINITY;                    // warp-uniform
             bool parked = false;                       // warp-uniform
@@ -368,33 +379,48 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
                 float dC = INFINITY;
                 int cntC = 0;
                 {
-                    float v4[4], v2[2], v1;
-                    const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
+                    float v;                                       // lane d (< 7): column sum of shift slot d
+                    if (kRedux) {
+                        // fixed point, 2^-24: a lane's partial is < 2 (two cosines), 30 lanes sum below 2^30; REDUX.SUM leaves
+                        // every slot's total in a uniform register (error <= 2^-25 per non-zero lane, cf. bound C)
+                        int tot[NSHIFT];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float hi_ = (i == 3) ? 0.f : part[4 + i];
-                        const float send = up16 ? part[i] : hi_, keep = up16 ? hi_ : part[i];
-                        v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                    }
+                        for (int d = 0; d < NSHIFT; ++d) tot[d] = __reduce_add_sync(0xffffffffu, __float2int_rn(part[d] * 16777216.0f));
+                        int mine = tot[0];
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const float send = up8 ? v4[i] : v4[2 + i], keep = up8 ? v4[2 + i] : v4[i];
-                        v2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                        for (int d = 1; d < NSHIFT; ++d) mine = (lane == d) ? tot[d] : mine;
+                        v = (float)mine * 5.9604644775390625e-08f;
+                    } else {
+                        float v4[4], v2[2], v1;
+                        const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float hi_ = (i == 3) ? 0.f : part[4 + i];
+                            const float send = up16 ? part[i] : hi_, keep = up16 ? hi_ : part[i];
+                            v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const float send = up8 ? v4[i] : v4[2 + i], keep = up8 ? v4[2 + i] : v4[i];
+                            v2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                        }
+                        {
+                            const float send = up4 ? v2[0] : v2[1], keep = up4 ? v2[1] : v2[0];
+                            v1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                        }
+                        v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+                        v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+                        const int srcl = (lane < 8) ? (((lane >> 2) & 1) << 4 | ((lane >> 1) & 1) << 3 | (lane & 1) << 2) : 0;
+                        v = __shfl_sync(0xffffffffu, v1, srcl);
                     }
-                    {
-                        const float send = up4 ? v2[0] : v2[1], keep = up4 ? v2[1] : v2[0];
-                        v1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                    }
-                    v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
-                    v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
-                    const int srcl = (lane < 8) ? (((lane >> 2) & 1) << 4 | ((lane >> 1) & 1) << 3 | (lane & 1) << 2) : 0;
-                    const float v = __shfl_sync(0xffffffffu, v1, srcl);
-                    if (lane < NSHIFT) {
+                    if ((kz_lo | kz_hi | qz_any) == 0u) {          // no empty column on either side (warp-uniform): 60 effective columns
+                        if (lane < NSHIFT) { cntC = S; dC = 1.0f - v * 0.016666668f; }
+                    } else if (lane < NSHIFT) {
                         const int s = wrap60(s0 + lane - RADIUS);
                         const unsigned long long kzero = (((unsigned long long)kz_hi << 32) | kz_lo) & MASK60;
                         const unsigned long long krot = s ? (((kzero << s) | (kzero >> (S - s))) & MASK60) : kzero;
                         cntC = S - __popcll((qzero | krot) & MASK60);
-                        dC = cntC ? 1.0f - v / (float)cntC : INFINITY;
+                        dC = cntC ? 1.0f - v * sm.rcnt[cntC] : INFINITY;     // the reciprocal's rounding is inside bound C
                     }
                 }
                 const float mC = warp_min_f(dC);
@@ -424,6 +450,8 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
                     parked = true;
                 }
             }
+            // the parked first keyframes are judged against the CTA's final bound (one entry per CTA survives, typically)
+            __syncthreads();
             if (lane == 0 && parked) {
                 const Survivor sv = ws.first;
                 const float bound = fminf(my_ub, unord_f32(*reinterpret_cast<volatile unsigned int *>(&sm.ub)));
@@ -475,40 +503,52 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
             const unsigned int n_list = *reinterpret_cast<volatile unsigned int *>(&stq->n_surv);
             const float bound = unord_f32(*reinterpret_cast<volatile unsigned int *>(&stq->gub));
             const double cq = sm.cq;
-            // Work items = (surviving keyframe, one of its candidate shifts), dealt round-robin to the CTA's warps:
-            // every warp walks the whole list (it is short) and certifies the items whose running number is its own.
+            // Phase 1, all warps in parallel: the entries the FINAL bound cannot rule out (typically a handful of the few
+            // hundred listed) are compacted into a shared work list.  Phase 2: work items = (entry, one of its candidate
+            // shifts), dealt round-robin to the warps.  A list longer than the work list's capacity (adversarial inputs:
+            // hundreds of near-ties) is certified in place, every warp taking the entries it filtered itself.
             // Order of the reference's scans: (dist, keyframe position, shift) lexicographic.
-            int wcount = 0;
-            for (unsigned int base = 0; base < n_list; base += 32) {
+            auto certify_one = [&](int it, int cd, float ckf, unsigned int bits) {
+                const int kf = cand ? cand[it] : first + it;
+                __syncwarp();
+                *reinterpret_cast<uint2 *>(&ws.krec[2 * lane]) = __ldcg(reinterpret_cast<const uint2 *>(brec + (size_t)kf * BIN_WORDS + 2 * lane));
+                __syncwarp();
+                const unsigned long long kzero = (((unsigned long long)ws.krec[61] << 32) | ws.krec[60]) & MASK60;
+                double dd;
+                int ds;
+                certify_dist_bin(sm.qcol, cq, ws.krec, (double)ckf, qzero, kzero, ws.scr, cd & 0xff, bits, lane, dd, ds);
+                if (dd < d || (dd == d && (it < p || (it == p && ds < sh)))) { d = dd; p = it; ix = kf; sh = ds; }
+            };
+            if (t == 0) sm.n_work = 0u;
+            __syncthreads();
+            const bool in_place = n_list > 8u * WORK_CAP;          // even the filtered list may not fit: skip the work list
+            for (unsigned int base = warp * 32; base < n_list; base += BWARPS * 32) {
                 const unsigned int i = base + lane;
                 const int4 e = (i < n_list) ? __ldcg(reinterpret_cast<const int4 *>(survq + i)) : make_int4(0, 0, 0x7f800000, 0);
-                unsigned int todo = __ballot_sync(0xffffffffu, i < n_list && !(__int_as_float(e.z) - EPS_C > bound));
+                const bool need = i < n_list && !(__int_as_float(e.z) - EPS_C > bound);
+                unsigned int slot = 0xffffffffu;
+                if (need && !in_place) slot = atomicAdd(&sm.n_work, 1u);
+                if (need && slot < WORK_CAP) { Survivor sv; sv.item = e.x; sv.code = e.y; sv.lo = __int_as_float(e.z); sv.pad = e.w; sm.work[slot] = sv; }
+                unsigned int todo = __ballot_sync(0xffffffffu, need && slot >= WORK_CAP);      // overflow / in place: certify here
                 while (todo) {
                     const int src = __ffs(todo) - 1;
                     todo &= todo - 1;
                     const int it = __shfl_sync(0xffffffffu, e.x, src), cd = __shfl_sync(0xffffffffu, e.y, src);
                     const float ckf = __int_as_float(__shfl_sync(0xffffffffu, e.w, src));
-                    unsigned int bits = (unsigned int)(cd >> 8) & 0x7fu;
-                    bool loaded = false;
-                    int kf = 0;
-                    unsigned long long kzero = 0ull;
+                    certify_one(it, cd, ckf, (unsigned int)(cd >> 8) & 0x7fu);
+                }
+            }
+            __syncthreads();
+            {
+                const int nw = (int)min(sm.n_work, (unsigned int)WORK_CAP);
+                int wcount = 0;
+                for (int w = 0; w < nw; ++w) {
+                    const Survivor sv = sm.work[w];
+                    unsigned int bits = (unsigned int)(sv.code >> 8) & 0x7fu;
                     while (bits) {
                         const unsigned int one = bits & (0u - bits);
                         bits &= bits - 1;
-                        if ((wcount++) % BWARPS != warp) continue;
-                        if (!loaded) {
-                            kf = cand ? cand[it] : first + it;
-                            __syncwarp();
-                            *reinterpret_cast<uint2 *>(&ws.krec[2 * lane]) =
-                                __ldcg(reinterpret_cast<const uint2 *>(brec + (size_t)kf * BIN_WORDS + 2 * lane));
-                            __syncwarp();
-                            kzero = (((unsigned long long)ws.krec[61] << 32) | ws.krec[60]) & MASK60;
-                            loaded = true;
-                        }
-                        double dd;
-                        int ds;
-                        certify_dist_bin(sm.qcol, cq, ws.krec, (double)ckf, qzero, kzero, ws.scr, cd & 0xff, one, lane, dd, ds);
-                        if (dd < d || (dd == d && (it < p || (it == p && ds < sh)))) { d = dd; p = it; ix = kf; sh = ds; }
+                        if ((wcount++) % BWARPS == warp) certify_one(sv.item, sv.code, __int_as_float(sv.pad), one);
                     }
                 }
             }
@@ -610,9 +650,16 @@ int nrs_sc::bin_launch(nrs_sc_db *db, const double *d_queries, int Q, const int3
     rc = db->bin_block.reserve((size_t)Q * n_chunks * sizeof(BlockResult));
     if (rc) return rc;
     const int grid = std::min(max_ctas, Q * n_chunks);
-    sc_search_bin_kernel<<<grid, BT, 0, ctx->stream>>>(db->d_brec, db->d_desc, db->d_keys, d_queries, Q, d_cand, first, n_items,
-                                                       n_chunks, idx_scale, idx_offset, db->bin_surv.as<Survivor>(), stride,
-                                                       db->d_bstate, db->bin_block.as<BlockResult>(), db->d_gticket, d_results, xv);
+    const int per = (n_items + n_chunks - 1) / n_chunks;
+    static const int use_redux = []() { const char *e = getenv("NRS_SC_BIN_REDUX"); return e ? atoi(e) : NRS_SC_BIN_REDUX_DEFAULT; }();
+    if (use_redux)
+        sc_search_bin_kernel<true><<<grid, BT, 0, ctx->stream>>>(db->d_brec, db->d_desc, db->d_keys, d_queries, Q, d_cand, first, n_items,
+                                                                 n_chunks, per, idx_scale, idx_offset, db->bin_surv.as<Survivor>(), stride,
+                                                                 db->d_bstate, db->bin_block.as<BlockResult>(), db->d_gticket, d_results, xv);
+    else
+        sc_search_bin_kernel<false><<<grid, BT, 0, ctx->stream>>>(db->d_brec, db->d_desc, db->d_keys, d_queries, Q, d_cand, first, n_items,
+                                                                  n_chunks, per, idx_scale, idx_offset, db->bin_surv.as<Survivor>(), stride,
+                                                                  db->d_bstate, db->bin_block.as<BlockResult>(), db->d_gticket, d_results, xv);
     NRS_LAUNCHED();
     return NRS_OK;
 }
