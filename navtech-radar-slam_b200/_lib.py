@@ -201,6 +201,8 @@ class Context:
     def adopt(self, obj):
         """Register a dependent (database, frame, ...) so close() tears it down first."""
         import weakref
+        if len(self._children) >= 64:                 # a long stream adopts one frame per scan: drop the dead ones
+            self._children = [r for r in self._children if r() is not None]
         self._children.append(weakref.ref(obj))
 
     @property

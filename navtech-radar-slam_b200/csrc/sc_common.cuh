@@ -116,6 +116,7 @@ struct XchgView {
     int world, rank;
     unsigned int epoch;
     long long timeout_cycles;            // a peer that never answers must not hang the GPU
+    int q_slot;                          // general-valued kernel: which of the launch group's query slots this launch fills
 };
 constexpr int XCHG_MAX_WORLD = 32;       // one lane per peer
 constexpr long long XCHG_TIMEOUT_CYCLES = 6000000000ll;   // default ~3 s (nrs_sc_xchg_set_timeout_ms)

@@ -481,14 +481,14 @@ sc_search_kernel(const float *__restrict__ frec, const double *__restrict__ desc
             const int par = (int)(xv.epoch & 1u);
             bool ok = true;
             if (lane < xv.world) {
-                // slot layout shared with the bit-mask kernel: [parity][query 0 of XCHG_QCAP][source rank]
-                XchgSlot *dst = xv.peers[lane] + (size_t)par * XCHG_QCAP * xv.world + xv.rank;
+                // slot layout shared with the bit-mask kernel: [parity][query slot of XCHG_QCAP][source rank]
+                XchgSlot *dst = xv.peers[lane] + ((size_t)par * XCHG_QCAP + xv.q_slot) * xv.world + xv.rank;
                 dst->dist = d;
                 dst->idx = ix;
                 dst->shift = sh;
                 st_release_sys(&dst->epoch, xv.epoch);
                 if (lane == 0) st->t_ns[2] = globaltimer_ns();
-                const XchgSlot *src = xv.peers[xv.rank] + (size_t)par * XCHG_QCAP * xv.world + lane;
+                const XchgSlot *src = xv.peers[xv.rank] + ((size_t)par * XCHG_QCAP + xv.q_slot) * xv.world + lane;
                 const long long t0 = clock64();
                 while (ld_acquire_sys(&src->epoch) != xv.epoch)
                     if (clock64() - t0 > xv.timeout_cycles) { ok = false; break; }
@@ -971,7 +971,7 @@ int init_state(SearchState *d_state, cudaStream_t stream)
 int launch_search(nrs_ctx *ctx, const DbView &v, const double *d_query, const int32_t *d_cand,
                   int first, int n_items, int idx_offset, double *d_dist_all, int32_t *d_shift_all,
                   BlockResult *d_block, SearchState *d_state, nrs_sc_result *d_result, int max_blocks,
-                  int idx_scale = 1, XchgView xv = XchgView{nullptr, 0, 0, 0u, 0ll})
+                  int idx_scale = 1, XchgView xv = XchgView{nullptr, 0, 0, 0u, 0ll, 0})
 {
     int rc = configure_search_kernel(ctx->device);
     if (rc) return rc;
@@ -1255,7 +1255,7 @@ static bool host_query_is_binary(const double *q)
     return (c > 0.0) && ((double)(float)c == c) && (c >= 7.888609052210118e-31) && (c <= 1.2676506002282294e30);
 }
 static inline bool db_bin_ok(const nrs_sc_db *db) { return db->search_mode == 0 && db->n_general == 0; }
-static const XchgView XV_NONE{nullptr, 0, 0, 0u, 0ll};
+static const XchgView XV_NONE{nullptr, 0, 0, 0u, 0ll, 0};
 
 static int sc_query_impl(nrs_sc_db *db, const double *query_host, int first, int last,
                          const int32_t *cand, int n_cand, double *dist_out, int32_t *shift_out,
@@ -1344,18 +1344,20 @@ int nrs_sc::batch_dev_locked(nrs_sc_db *db, const double *queries_dev, int Q, in
 {
     nrs_ctx *ctx = db->ctx;
     const int n_items = std::max(0, last - first);
+    // ONE exchange epoch per group of up to XCHG_QCAP queries on either kernel, so that ranks whose shards take different
+    // kernels (one holds a general-valued keyframe, another does not) stay in step: the bit-mask kernel fills the
+    // group's Q slots in one launch, the general-valued kernel one slot per launch
     for (int done = 0; done < Q; done += XCHG_QCAP) {
         const int q = std::min(XCHG_QCAP, Q - done);
+        XchgView xv = XV_NONE;
+        if (sharded) xv = XchgView{db->x_peers_dev, db->x_world, db->x_rank, ++db->x_epoch, db->x_timeout_cycles, 0};
         if (db_bin_ok(db)) {
-            XchgView xv = XV_NONE;
-            if (sharded) xv = XchgView{db->x_peers_dev, db->x_world, db->x_rank, ++db->x_epoch, db->x_timeout_cycles};
             int rc = nrs_sc::bin_launch(db, queries_dev + (size_t)done * DESC, q, nullptr, first, n_items, idx_scale, idx_offset,
                                         results_dev + done, xv);
             if (rc) return rc;
         } else {
             for (int i = 0; i < q; ++i) {
-                XchgView xv = XV_NONE;
-                if (sharded) xv = XchgView{db->x_peers_dev, db->x_world, db->x_rank, ++db->x_epoch, db->x_timeout_cycles};
+                xv.q_slot = i;
                 int rc = launch_search(ctx, view_of(db), queries_dev + (size_t)(done + i) * DESC, nullptr, first, n_items, idx_offset,
                                        nullptr, nullptr, db->d_block, db->d_state, results_dev + done + i, db->max_blocks,
                                        idx_scale, xv);
@@ -1385,7 +1387,13 @@ int nrs_sc_query_batch_dev_sharded(nrs_sc_db *db, const double *queries_dev, int
     NRS_CHECK_ARG(db && queries_dev && results_dev && Q >= 1, "bad argument");
     std::lock_guard<std::mutex> lk(db->mu);
     NRS_CHECK_ARG(db->x_ready, "exchange not opened (nrs_sc_xchg_create / nrs_sc_xchg_open)");
-    NRS_CHECK_ARG(first >= 0 && last <= db->size, "search range outside the database");
+    if (!(first >= 0 && last <= db->size)) {
+        // the peers consume one epoch per query group whatever happens here: stay in step with them (they report
+        // idx == -2 for these queries after the exchange timeout instead of waiting for ever on every later one)
+        db->x_epoch += (unsigned int)((Q + XCHG_QCAP - 1) / XCHG_QCAP);
+        nrs::set_error("nrs_sc_query_batch_dev_sharded: search range outside the database");
+        return NRS_EINVAL;
+    }
     std::lock_guard<std::mutex> lk2(db->ctx->mu);
     NRS_CUDA(cudaSetDevice(db->ctx->device));
     return batch_dev_locked(db, queries_dev, Q, first, last, db->x_world, db->x_rank, results_dev, true);

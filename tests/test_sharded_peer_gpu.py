@@ -39,7 +39,12 @@ def _worker(rank, world, port, out_q, binary=False):
     from oracle import pyoracle as O
     sc = nrs.scancontext
     ctx = nrs.Context(rank)
-    db, rev = synth.sc_database(3001, 200, seed=17, binary=binary)
+    db, rev = synth.sc_database(3001, 200, seed=17, binary=bool(binary))
+    if binary == 2:
+        # ONE general-valued keyframe: the rank that owns it searches with the f32-filter kernel, the others with the
+        # bit-mask kernel -- the exchange (one epoch per query group, one slot per query) must not care
+        gen, _ = synth.sc_database(4, 0, seed=5, binary=False)
+        db[1501] = gen[1]
     db[2500] = db[7]
     db[2601] = db[7]          # exact ties across shards: lowest global index must win on every rank
     sdb = sc.ShardedSCDatabase(rank, world, ctx=ctx, exchange="peer")
@@ -99,10 +104,10 @@ def _worker(rank, world, port, out_q, binary=False):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
-@pytest.mark.parametrize("binary", [False, True])
+@pytest.mark.parametrize("binary", [0, 1, 2])
 def test_peer_exchange_matches_single_scan(binary):
-    """binary=False: general-valued descriptors (f32-filter kernel); binary=True: {0,3.0} descriptors (bit-mask
-    kernel, batched launches with one exchange)."""
+    """binary=0: general-valued descriptors (f32-filter kernel); 1: {0,3.0} descriptors (bit-mask kernel, batched
+    launches with one exchange); 2: {0,3.0} except one keyframe, so the ranks run different kernels."""
     world = min(torch.cuda.device_count(), 4)
     mpc = mp.get_context("spawn")
     q = mpc.Queue()
