@@ -64,6 +64,12 @@ struct FrontendState {
     // cen2019 top-candidate subset: threshold on h carried from frame to frame (device), valid once a frame ran
     float *d_thresh = nullptr;
     bool   have_thresh = false;
+    // the extraction pipeline as CUDA graphs: ~35 launches on two streams replayed by one cudaGraphLaunch.  One
+    // executable graph per (frame block, extractor mode, azimuth count); node parameters are all device pointers of
+    // this state or of the frame block, so a graph stays valid while both live
+    struct ExtractGraph { unsigned char *block; int mode; int n_sorted; cudaGraphExec_t exec; int nodes; };
+    std::vector<ExtractGraph> graphs;
+    bool graphs_off = false;             // set when a capture failed once: plain stream launches from then on
     // voxel scratch
     unsigned int *d_vkey[2] = {nullptr, nullptr};
     unsigned int *d_vval[2] = {nullptr, nullptr};

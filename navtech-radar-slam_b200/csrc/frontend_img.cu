@@ -22,6 +22,7 @@
 #include <cub/cub.cuh>
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <string>
@@ -291,6 +292,8 @@ static void frontend_free(void *p)
                    S->d_blur, S->d_cub, S->d_az, S->d_azsort, S->d_azidx, S->d_cossin, S->d_times, S->d_counts,
                    S->d_vkey[0], S->d_vkey[1], S->d_vval[0], S->d_vval[1], S->d_pts32, S->d_rowcount, S->d_thresh};
     for (void *d : dev) if (d) cudaFree(d);
+    for (auto &g : S->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    S->graphs.clear();
     if (S->h_counts) cudaFreeHost(S->h_counts);
     if (S->st_img) { cudaStreamSynchronize(S->st_img); cudaStreamDestroy(S->st_img); }
     if (S->ev_fork) cudaEventDestroy(S->ev_fork);
@@ -615,6 +618,53 @@ int extract_enqueue(nrs_ctx *ctx, FrontendState *S, nrs_frame *f, int R, int C, 
     return NRS_OK;
 }
 
+// extract_enqueue through a cached CUDA graph (captured from the very same enqueue code on first use)
+int extract_run(nrs_ctx *ctx, FrontendState *S, nrs_frame *f, int R, int C, int row_pitch, const nrs_extract_params *p,
+                int n_sorted, bool force_full)
+{
+    static const bool env_off = getenv("NRS_NO_GRAPHS") != nullptr;
+    if (S->graphs_off || env_off) return extract_enqueue(ctx, S, f, R, C, row_pitch, p, n_sorted, force_full);
+    cudaStream_t st = ctx->stream;
+    const int mode = p->keypoint_extraction == 1 ? 2 : ((S->have_thresh && !force_full) ? 1 : 0);
+    for (auto &g : S->graphs)
+        if (g.block == f->d_block && g.mode == mode && g.n_sorted == n_sorted) {
+            NRS_CUDA(cudaGraphLaunch(g.exec, st));
+            g_launches.fetch_add((uint64_t)g.nodes, std::memory_order_relaxed);
+            if (mode != 2) S->have_thresh = true;
+            return NRS_OK;
+        }
+    // capture: the launches below are recorded, not run
+    const uint64_t launches_before = g_launches.load();
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        S->graphs_off = true;
+        return extract_enqueue(ctx, S, f, R, C, row_pitch, p, n_sorted, force_full);
+    }
+    const bool had_thresh = S->have_thresh;
+    const int rc = extract_enqueue(ctx, S, f, R, C, row_pitch, p, n_sorted, force_full);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &graph);
+    const int nodes = (int)(g_launches.load() - launches_before);      // this thread's launches were recorded, not run
+    g_launches.fetch_sub((uint64_t)nodes, std::memory_order_relaxed);
+    cudaGraphExec_t exec = nullptr;
+    if (rc != NRS_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        S->graphs_off = true;                        // plain launches from now on (and for this frame)
+        S->have_thresh = had_thresh;
+        return extract_enqueue(ctx, S, f, R, C, row_pitch, p, n_sorted, force_full);
+    }
+    cudaGraphDestroy(graph);
+    if (S->graphs.size() >= 12) {                    // frames recycle a handful of blocks; keep the cache small
+        cudaGraphExecDestroy(S->graphs.front().exec);
+        S->graphs.erase(S->graphs.begin());
+    }
+    S->graphs.push_back(FrontendState::ExtractGraph{f->d_block, mode, n_sorted, exec, nodes});
+    NRS_CUDA(cudaGraphLaunch(exec, st));
+    g_launches.fetch_add((uint64_t)nodes, std::memory_order_relaxed);
+    return NRS_OK;
+}
+
 int check_extract_args(nrs_ctx *ctx, const uint8_t *raw, int R, int row_pitch, const nrs_extract_params *p)
 {
     NRS_CHECK_ARG(ctx && raw && p, "bad argument");
@@ -674,7 +724,7 @@ int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw, int R, int row_pitch, co
     // a second pass with the full-frame sort only when cen2019's top-candidate subset could not vouch for the
     // marking loop's outcome (FrameCounts::need_full)
     for (int attempt = 0; attempt < 2; ++attempt) {
-        if ((rc = extract_enqueue(ctx, S, f, R, C, row_pitch, p, H.n_sorted, attempt == 1))) { frame_release_locked(f); return rc; }
+        if ((rc = extract_run(ctx, S, f, R, C, row_pitch, p, H.n_sorted, attempt == 1))) { frame_release_locked(f); return rc; }
         NRS_CUDA(cudaMemcpyAsync(S->h_counts, S->d_counts, sizeof(FrameCounts), cudaMemcpyDeviceToHost, st));
         NRS_CUDA(cudaStreamSynchronize(st));
         if (!S->h_counts->need_full) break;
@@ -721,7 +771,7 @@ int nrs_orora_pair(nrs_ctx *ctx, const nrs_frame *prev, const uint8_t *raw, int 
     if ((rc = match_carve(ctx, nq, cap, m))) { frame_release_locked(f); return rc; }
     int h_n = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        if ((rc = extract_enqueue(ctx, S, f, R, C, row_pitch, p, H.n_sorted, attempt == 1))) { frame_release_locked(f); return rc; }
+        if ((rc = extract_run(ctx, S, f, R, C, row_pitch, p, H.n_sorted, attempt == 1))) { frame_release_locked(f); return rc; }
         NRS_CUDA(cudaMemsetAsync(m.n, 0, 4, st));
         if (nq > 0) {
             fe_match_kernel<<<(nq * 32 + 255) / 256, 256, 0, st>>>(prev->d_desc, nq, f->d_desc, 0, S->d_counts, p->nndr, m.best, m.good);
