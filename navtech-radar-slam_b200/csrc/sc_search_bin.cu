@@ -50,7 +50,7 @@
 #include "sc_common.cuh"
 
 #ifndef NRS_SC_BIN_REDUX_DEFAULT
-#define NRS_SC_BIN_REDUX_DEFAULT 0      // 1: REDUX.SUM fixed-point column sums, 0: shuffle tree (bench both: NRS_SC_BIN_REDUX)
+#define NRS_SC_BIN_REDUX_DEFAULT 1      // 1: REDUX.SUM fixed-point column sums (measured 5 % faster), 0: shuffle tree; NRS_SC_BIN_REDUX overrides
 #endif
 
 using namespace nrs_sc;
