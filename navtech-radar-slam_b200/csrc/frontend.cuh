@@ -67,9 +67,13 @@ struct FrontendState {
     // the extraction pipeline as CUDA graphs: ~35 launches on two streams replayed by one cudaGraphLaunch.  One
     // executable graph per (frame block, extractor mode, azimuth count); node parameters are all device pointers of
     // this state or of the frame block, so a graph stays valid while both live
-    struct ExtractGraph { unsigned char *block; int mode; int n_sorted; cudaGraphExec_t exec; int nodes; };
+    struct ExtractGraph { unsigned char *block; int mode; int n_sorted; nrs_extract_params p; cudaGraphExec_t exec; int nodes; };
     std::vector<ExtractGraph> graphs;
     bool graphs_off = false;             // set when a capture failed once: plain stream launches from then on
+    // cen2018's Gaussian taps (host libm) live here, not on the stack: the upload is a node of the captured graph and
+    // reads this buffer at every replay
+    float h_taps[256] = {};
+    int   taps_sigma = -1;
     // voxel scratch
     unsigned int *d_vkey[2] = {nullptr, nullptr};
     unsigned int *d_vval[2] = {nullptr, nullptr};

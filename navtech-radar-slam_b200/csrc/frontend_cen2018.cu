@@ -317,12 +317,14 @@ int fe_cen2018_device(nrs_ctx *ctx, FrontendState &S, int R, int C, float zq, in
     cudaStream_t st = ctx->stream;
     FrameCounts *cnt = S.d_counts;
     if (reset_counts) NRS_CUDA(cudaMemsetAsync(cnt, 0, sizeof(FrameCounts), st));
-    float taps[FILT_MAX];
+    static_assert(FILT_MAX <= 256, "FrontendState::h_taps");
+    float *taps = S.h_taps;                                  // persistent: a captured graph re-reads it at every replay
     if (sigma_gauss < 1 || sigma_gauss * 3 > FILT_MAX || sigma_gauss % 2 != 1) {
         set_error("cen2018: sigma_gauss must be odd and 3 * sigma_gauss <= %d (features.cpp:63 asserts odd)", FILT_MAX);
         return NRS_EINVAL;
     }
-    const int fsize = fe_cen2018_taps_host(sigma_gauss, taps);
+    int fsize = sigma_gauss * 3;
+    if (S.taps_sigma != sigma_gauss) { fsize = fe_cen2018_taps_host(sigma_gauss, taps); S.taps_sigma = sigma_gauss; }
     float *d_q = S.d_h, *d_p = S.d_keys[0], *d_y = keep_y ? S.d_keys[1] : nullptr;
     unsigned char *d_flags = reinterpret_cast<unsigned char *>(S.d_claim);
     float *d_sigma = reinterpret_cast<float *>(S.d_incr);

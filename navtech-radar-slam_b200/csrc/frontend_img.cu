@@ -33,6 +33,7 @@ namespace nrs {
 
 int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_points, int min_range, int *d_polar,
                       bool reset_counts = true, bool force_full = false);
+int fe_cen2018_taps_host(int sigma_gauss, float *taps);
 int fe_cen2018_device(nrs_ctx *ctx, FrontendState &S, int R, int C, float zq, int sigma_gauss, int min_range,
                       int *d_polar, bool reset_counts, bool keep_y);
 int fe_points_voxel_bev_device(nrs_ctx *ctx, FrontendState &S, nrs_frame *f);
@@ -626,8 +627,13 @@ int extract_run(nrs_ctx *ctx, FrontendState *S, nrs_frame *f, int R, int C, int 
     if (S->graphs_off || env_off) return extract_enqueue(ctx, S, f, R, C, row_pitch, p, n_sorted, force_full);
     cudaStream_t st = ctx->stream;
     const int mode = p->keypoint_extraction == 1 ? 2 : ((S->have_thresh && !force_full) ? 1 : 0);
+    if (mode == 2 && S->taps_sigma != p->sigma_gauss && p->sigma_gauss >= 1 && p->sigma_gauss * 3 <= 256) {
+        // a cached cen2018 graph uploads S->h_taps at every replay: bring the taps back to this sigma first
+        fe_cen2018_taps_host(p->sigma_gauss, S->h_taps);
+        S->taps_sigma = p->sigma_gauss;
+    }
     for (auto &g : S->graphs)
-        if (g.block == f->d_block && g.mode == mode && g.n_sorted == n_sorted) {
+        if (g.block == f->d_block && g.mode == mode && g.n_sorted == n_sorted && !memcmp(&g.p, p, sizeof(*p))) {   // every by-value kernel argument
             NRS_CUDA(cudaGraphLaunch(g.exec, st));
             g_launches.fetch_add((uint64_t)g.nodes, std::memory_order_relaxed);
             if (mode != 2) S->have_thresh = true;
@@ -659,7 +665,7 @@ int extract_run(nrs_ctx *ctx, FrontendState *S, nrs_frame *f, int R, int C, int 
         cudaGraphExecDestroy(S->graphs.front().exec);
         S->graphs.erase(S->graphs.begin());
     }
-    S->graphs.push_back(FrontendState::ExtractGraph{f->d_block, mode, n_sorted, exec, nodes});
+    S->graphs.push_back(FrontendState::ExtractGraph{f->d_block, mode, n_sorted, *p, exec, nodes});
     NRS_CUDA(cudaGraphLaunch(exec, st));
     g_launches.fetch_add((uint64_t)nodes, std::memory_order_relaxed);
     return NRS_OK;

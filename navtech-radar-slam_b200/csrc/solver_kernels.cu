@@ -216,55 +216,6 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restri
     if (warp == 0) { s_key[0][lane] = -1; s_key[1][lane] = -1; s_min[0][lane] = 0x7fffffff; s_min[1][lane] = 0x7fffffff; }
     __syncthreads();
     int best_n = 0;
-    __shared__ int s_bestn;
-    if (nw <= 12) {
-        // Small graphs (N <= 384, the usual 300-odd matches): ONE warp runs the same rule without any CTA barrier --
-        // lane l looks after the vertices l, l + 32, ... (at most 12), the set lives in sPw[0], the maxima travel by
-        // REDUX.  A step costs ~|P| / 32 x nw AND+POPC per lane instead of a 12-warp barrier and a shared-memory round
-        // trip (0.41 us -> ~0.1 us per step at M = 135).
-        if (warp == 0) {
-            for (;;) {
-                int key = -1, cmin = 0x7fffffff, np = 0;
-                for (int j = 0; j < nw; ++j) {
-                    const uint32_t pw = sPw[0][j];
-                    np += (lane == 0) ? __popc(pw) : 0;
-                    if (!((pw >> lane) & 1u)) continue;
-                    const int v = j * 32 + lane;
-                    int c = 0;
-                    for (int w = 0; w < nw; ++w) c += __popc(sadj[v * SROW + w] & sPw[0][w]);
-                    key = max(key, (c << 10) | (1023 - v));
-                    cmin = min(cmin, c);
-                }
-                const int k2 = __reduce_max_sync(0xffffffffu, key);
-                if (k2 < 0) break;
-                const int m2 = __reduce_min_sync(0xffffffffu, cmin);
-                np = __shfl_sync(0xffffffffu, np, 0);
-                if (m2 == np - 1) {
-                    // the set is a clique: its vertices in ascending index (equal counts, lowest index first)
-                    const uint32_t pw = sPw[0][lane];
-                    int pre = __popc(pw);
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int up = __shfl_up_sync(0xffffffffu, pre, o);
-                        if (lane >= o) pre += up;
-                    }
-                    int pos = best_n + pre - __popc(pw);
-                    for (uint32_t x = pw; x; x &= x - 1) best[pos++] = lane * 32 + __ffs(x) - 1;
-                    best_n += np;
-                    break;
-                }
-                const int v = 1023 - (k2 & 1023);
-                if (lane == 0) best[best_n] = v;
-                ++best_n;
-                __syncwarp();
-                sPw[0][lane] &= sadj[v * SROW + lane];
-                __syncwarp();
-            }
-            if (lane == 0) s_bestn = best_n;
-        }
-        __syncthreads();
-        best_n = s_bestn;
-    } else
     for (int buf = 0;; buf ^= 1) {
         int key = -1, cmin = 0x7fffffff;
         if (tid < N && ((sPw[warp][warp] >> lane) & 1u)) {
@@ -632,6 +583,19 @@ __device__ void block_sum4(double &x0, double &x1, double &x2, double &x3, doubl
 }
 // five values, two barriers: the partials alternate between two halves of `red` (parity), so the barrier that
 // protected the buffer against the previous call's readers is not needed
+__device__ void block_sum5(double &x0, double &x1, double &x2, double &x3, double &x4, double *red, int nwl, int parity)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *buf = red + parity * 192;
+    x0 = warp_sum(x0); x1 = warp_sum(x1); x2 = warp_sum(x2); x3 = warp_sum(x3); x4 = warp_sum(x4);
+    if (lane == 0) { buf[warp] = x0; buf[32 + warp] = x1; buf[64 + warp] = x2; buf[96 + warp] = x3; buf[128 + warp] = x4; }
+    __syncthreads();
+    // every warp finishes the sum itself (same tree in every warp: identical results), no broadcast barrier
+    const bool on = lane < nwl;
+    double y0 = on ? buf[lane] : 0.0, y1 = on ? buf[32 + lane] : 0.0, y2 = on ? buf[64 + lane] : 0.0;
+    double y3 = on ? buf[96 + lane] : 0.0, y4 = on ? buf[128 + lane] : 0.0;
+    x0 = warp_sum(y0); x1 = warp_sum(y1); x2 = warp_sum(y2); x3 = warp_sum(y3); x4 = warp_sum(y4);
+}
 __device__ double block_max(double x, double *red, int nwl)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -819,102 +783,65 @@ orora_tail_kernel(const double *__restrict__ src, const double *__restrict__ tgt
     const double max_w = block_max(t < M ? w0 : 0.0, sm.red, nwl);
     w0 = w0 / max_w;
     STAMP(6);
-    // ---- GNC-TLS (:292-440), ONE warp: lane l carries the points l, l + 32, ... in shared memory, the five sums of
-    //      an iteration are warp shuffles -- no CTA barrier inside the loop (1.2 us -> ~0.3 us per iteration at M = 135).
-    //      As before the cost of iteration it-1 rides along with the correlation sums of iteration it, so its stopping
-    //      test is evaluated one pass later, before anything of iteration it is applied. ----------------------------------
+    // ---- GNC-TLS (:292-440) ------------------------------------------------------------------------
+    const double sx = t < M ? sm.a[t] : 0.0, sy = t < M ? sm.b[t] : 0.0;
+    const double dx = t < M ? sm.c[t] : 0.0, dy = t < M ? sm.d[t] : 0.0;
     double R[4];
-    double wgt = 1.0;
+    double nb2 = noise_bound * noise_bound;
+    if (nb2 < 1e-16) nb2 = 1e-2;
+    double wgt = 1.0, res;
     int iters = 0, early = 0;
-    double cost = INFINITY;
-    if (t < M) sm.w[t] = w0;
-    __syncthreads();
-    if ((t >> 5) == 0) {
-        const int lane = t;
-        double nb2 = noise_bound * noise_bound;
-        if (nb2 < 1e-16) nb2 = 1e-2;
-        double prev_cost = INFINITY;
+    double cost = INFINITY, prev_cost = INFINITY;
+    {
+        double h00 = sx * w0 * dx, h10 = sy * w0 * dx, h01 = sx * w0 * dy, h11 = sy * w0 * dy;
+        block_sum4(h00, h10, h01, h11, sm.red, nwl);
+        rot_from_H(h00, h10, h01, h11, R);                    // :333
+    }
+    {
+        const double ex = dx - (R[0] * sx + R[2] * sy), ey = dy - (R[1] * sx + R[3] * sy);
+        res = ex * ex + ey * ey;
+    }
+    const double max_res = block_max(t < M ? res : -INFINITY, sm.red, nwl);
+    if (max_res < nb2) nb2 = 0.01;                            // :342-344
+    double mu = 1 / (2 * max_res / nb2 - 1);
+    if (mu <= 0) {
+        early = 1;                                            // :348-352
+    } else {
         {
-            double h00 = 0, h10 = 0, h01 = 0, h11 = 0;
-            for (int i = lane; i < M; i += 32) {
-                const double wi = sm.w[i];
-                h00 += sm.a[i] * wi * sm.c[i]; h10 += sm.b[i] * wi * sm.c[i];
-                h01 += sm.a[i] * wi * sm.d[i]; h11 += sm.b[i] * wi * sm.d[i];
-            }
-            h00 = warp_sum(h00); h10 = warp_sum(h10); h01 = warp_sum(h01); h11 = warp_sum(h11);
-            rot_from_H(h00, h10, h01, h11, R);                // :333
+            const double th1 = (mu + 1) / mu * nb2, th2 = mu / (mu + 1) * nb2;
+            if (res >= th1) wgt = 0;
+            else if (res <= th2) wgt = 1;
+            else wgt = sqrt(nb2 * mu * (mu + 1) / res + 0.00000000000001) - mu;   // :368
+            mu = mu * gnc_factor;
         }
-        double max_res = -INFINITY;
-        for (int i = lane; i < M; i += 32) {
-            const double ex = sm.c[i] - (R[0] * sm.a[i] + R[2] * sm.b[i]), ey = sm.d[i] - (R[1] * sm.a[i] + R[3] * sm.b[i]);
-            const double r = ex * ex + ey * ey;
-            sm.key[i] = r;
-            max_res = fmax(max_res, r);
-        }
-        max_res = warp_max(max_res);
-        if (max_res < nb2) nb2 = 0.01;                        // :342-344
-        double mu = 1 / (2 * max_res / nb2 - 1);
-        if (mu <= 0) {
-            early = 1;                                        // :348-352
-        } else {
-            {
-                const double th1 = (mu + 1) / mu * nb2, th2 = mu / (mu + 1) * nb2;
-                for (int i = lane; i < M; i += 32) {
-                    const double r = sm.key[i];
-                    double wi;
-                    if (r >= th1) wi = 0;
-                    else if (r <= th2) wi = 1;
-                    else wi = sqrt(nb2 * mu * (mu + 1) / r + 0.00000000000001) - mu;      // :368
-                    sm.w[i] = wi;
-                    sm.s1[i] = 0.0;                           // cost term of "iteration -1"
-                }
-                mu = mu * gnc_factor;
+        // One CTA reduction per iteration: the cost of iteration it-1 rides along with the correlation sums
+        // of iteration it, so its stopping test is evaluated one pass later -- before anything of iteration
+        // it is applied.  Values and order of every sum are unchanged.
+        double cterm = 0.0;
+        for (int it = 0; it <= max_iter; ++it) {              // :376-433
+            double h00 = (t < M) ? sx * wgt * dx : 0.0, h10 = (t < M) ? sy * wgt * dx : 0.0;
+            double h01 = (t < M) ? sx * wgt * dy : 0.0, h11 = (t < M) ? sy * wgt * dy : 0.0;
+            double c0 = (t < M) ? cterm : 0.0;
+            block_sum5(h00, h10, h01, h11, c0, sm.red, nwl, (it + 1) & 1);   // first call: upper half (red[128] may still be read)
+            if (it > 0) {
+                cost = c0;
+                const double cost_diff = fabs(cost - prev_cost);
+                prev_cost = cost;
+                iters = it;
+                if (cost_diff < cost_thr) break;
             }
-            for (int it = 0; it <= max_iter; ++it) {          // :376-433
-                double h00 = 0, h10 = 0, h01 = 0, h11 = 0, c0 = 0;
-                for (int i = lane; i < M; i += 32) {
-                    const double wi = sm.w[i];
-                    h00 += sm.a[i] * wi * sm.c[i]; h10 += sm.b[i] * wi * sm.c[i];
-                    h01 += sm.a[i] * wi * sm.d[i]; h11 += sm.b[i] * wi * sm.d[i];
-                    c0 += sm.s1[i];
-                }
-                h00 = warp_sum(h00); h10 = warp_sum(h10); h01 = warp_sum(h01); h11 = warp_sum(h11); c0 = warp_sum(c0);
-                if (it > 0) {
-                    cost = c0;
-                    const double cost_diff = fabs(cost - prev_cost);
-                    prev_cost = cost;
-                    iters = it;
-                    if (cost_diff < cost_thr) break;
-                }
-                if (it == max_iter) break;
-                rot_from_H(h00, h10, h01, h11, R);
-                const double th1 = (mu + 1) / mu * nb2, th2 = mu / (mu + 1) * nb2;
-                for (int i = lane; i < M; i += 32) {
-                    const double ex = sm.c[i] - (R[0] * sm.a[i] + R[2] * sm.b[i]), ey = sm.d[i] - (R[1] * sm.a[i] + R[3] * sm.b[i]);
-                    const double r = ex * ex + ey * ey;
-                    const double wi = sm.w[i];
-                    sm.s1[i] = wi * r;
-                    double wn;
-                    if (r >= th1) wn = 0;
-                    else if (r <= th2) wn = 1;
-                    else wn = sqrt(nb2 * mu * (mu + 1) / r) - mu;      // :406
-                    sm.w[i] = wn;
-                }
-                mu = mu * gnc_factor;
-            }
-        }
-        if (lane == 0) {
-            sm.red[0] = R[0]; sm.red[1] = R[1]; sm.red[2] = R[2]; sm.red[3] = R[3];
-            sm.red[4] = cost;
-            sm.redi[0] = iters; sm.redi[1] = early;
+            if (it == max_iter) break;
+            rot_from_H(h00, h10, h01, h11, R);
+            const double ex = dx - (R[0] * sx + R[2] * sy), ey = dy - (R[1] * sx + R[3] * sy);
+            res = ex * ex + ey * ey;
+            cterm = wgt * res;
+            const double th1 = (mu + 1) / mu * nb2, th2 = mu / (mu + 1) * nb2;
+            if (res >= th1) wgt = 0;
+            else if (res <= th2) wgt = 1;
+            else wgt = sqrt(nb2 * mu * (mu + 1) / res) - mu;  // :406
+            mu = mu * gnc_factor;
         }
     }
-    __syncthreads();
-    R[0] = sm.red[0]; R[1] = sm.red[1]; R[2] = sm.red[2]; R[3] = sm.red[3];
-    cost = sm.red[4];
-    iters = sm.redi[0]; early = sm.redi[1];
-    wgt = (t < M) ? sm.w[t] : 0.0;
-    __syncthreads();                                          // sm.red / sm.w are reused below
     STAMP(7);
     if (t < M) sm.rot_inl[t] = early ? 0 : (wgt >= 0.4);      // :435-439
     __syncthreads();
