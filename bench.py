@@ -24,6 +24,10 @@ import time
 
 import numpy as np
 
+# NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; the contract is ONE JSON line there
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 PKG = "navtech-radar-slam_b200"

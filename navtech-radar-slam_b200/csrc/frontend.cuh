@@ -29,6 +29,7 @@ struct FrameCounts {
     int   n_sub;         // top-candidate subset: pixels with h >= the carried threshold (0 in full-sort mode)
     int   n_sorted;      // candidates in the sorted list the marking loop walked (== n_cand in full-sort mode)
     int   need_full;     // the subset could not prove the marking loop's outcome: redo with the full sort
+    unsigned int ticket[2];   // last-block tickets of fe_stats_kernel / fe_h_kernel (zeroed with the counts)
     int   pad_;
 };
 
@@ -75,9 +76,8 @@ struct FrontendState {
     float h_taps[256] = {};
     int   taps_sigma = -1;
     // voxel scratch
-    unsigned int *d_vkey[2] = {nullptr, nullptr};
-    unsigned int *d_vval[2] = {nullptr, nullptr};
     float *d_pts32 = nullptr;            // 2 * KP_CAP float x,y
+    int *d_stage = nullptr;              // R x C: one staging row of keypoint range bins per azimuth
     int   *d_rowcount = nullptr;         // per-row keypoint counts / offsets
     int    R = 0, C = 0, pitch = 0;
     // the Cartesian-image branch of extractFeature (remap, 8-bit conversion, ORB's blur) does not depend on

@@ -248,17 +248,17 @@ fe18_flags_kernel(const float *__restrict__ q, const float *__restrict__ p, cons
 
 // :102-112 one CTA per azimuth: a run starts at a flagged column whose left neighbour (from min_range on) is
 // not flagged; it emits column start + len / 2.  Emission stays ordered through per-warp ballots.
-template <bool EMIT>
 __global__ void __launch_bounds__(256)
 fe18_runs_kernel(const unsigned char *__restrict__ flags, int R, int C, int min_range, int *__restrict__ rowcount,
-                 int *__restrict__ polar, int cap)
+                 int *__restrict__ stage)
 {
     __shared__ int wsum[8];
     __shared__ int running;
     const int i = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned char *fr = flags + (size_t)i * C;
-    if (threadIdx.x == 0) running = EMIT ? rowcount[i] : 0;
+    int *srow = stage + (size_t)i * C;                       // this azimuth's staging row (fe_tail_kernel strings them)
+    if (threadIdx.x == 0) running = 0;
     __syncthreads();
     for (int j0 = min_range; j0 < C; j0 += 256) {
         const int j = j0 + threadIdx.x;
@@ -277,21 +277,17 @@ fe18_runs_kernel(const unsigned char *__restrict__ flags, int R, int C, int min_
 #pragma unroll
         for (int w = 0; w < 8; ++w) { const int c = wsum[w]; if (w < warp) before += c; total += c; }
         const int base = running;
-        if (EMIT && emit) {
-            const int pos = base + before + __popc(mask & ((1u << lane) - 1u));
-            if (pos < cap) { polar[2 * pos] = i; polar[2 * pos + 1] = centre; }
-        }
+        if (emit) srow[base + before + __popc(mask & ((1u << lane) - 1u))] = centre;
         __syncthreads();
         if (threadIdx.x == 0) running = base + total;
         __syncthreads();
     }
-    if (!EMIT && threadIdx.x == 0) rowcount[i] = running;
+    if (threadIdx.x == 0) rowcount[i] = running;
 }
 
 }  // namespace
 
-// exclusive scan of the per-azimuth counts, total -> cnt->K0 (defined in frontend_cen2019.cu)
-int fe_launch_rowscan(cudaStream_t st, int *rowcount, int R, FrameCounts *cnt, int cap);
+int fe_gather_rows_device(nrs_ctx *ctx, FrontendState &S, int *d_polar);   // frontend_cen2019.cu
 
 // host libm taps, the reference's expression (:62-73); returns the number of taps
 int fe_cen2018_taps_host(int sigma_gauss, float *taps)
@@ -309,7 +305,7 @@ int fe_cen2018_taps_host(int sigma_gauss, float *taps)
     return fsize;
 }
 
-// d_fft (S.d_fft) -> d_polar + cnt->K0.  Scratch reuse: q in S.d_h, p in d_keys[0], flags in d_claim (bytes),
+// d_fft (S.d_fft) -> the azimuths' staging rows (S.d_stage, S.d_rowcount); with d_polar also -> d_polar + cnt->K0.  Scratch reuse: q in S.d_h, p in d_keys[0], flags in d_claim (bytes),
 // y (optional, tests) in d_keys[1], sigma_q + taps in d_partial's neighbour d_incr.
 int fe_cen2018_device(nrs_ctx *ctx, FrontendState &S, int R, int C, float zq, int sigma_gauss, int min_range,
                       int *d_polar, bool reset_counts, bool keep_y)
@@ -353,12 +349,9 @@ int fe_cen2018_device(nrs_ctx *ctx, FrontendState &S, int R, int C, float zq, in
     dim3 gp((C + 255) / 256, R);
     fe18_flags_kernel<<<gp, 256, 0, st>>>(d_q, d_p, d_sigma, R, C, zq, min_range, d_flags, d_y);
     NRS_LAUNCHED();
-    fe18_runs_kernel<false><<<R, 256, 0, st>>>(d_flags, R, C, min_range, S.d_rowcount, nullptr, 0);
+    fe18_runs_kernel<<<R, 256, 0, st>>>(d_flags, R, C, min_range, S.d_rowcount, S.d_stage);
     NRS_LAUNCHED();
-    int rc = fe_launch_rowscan(st, S.d_rowcount, R, cnt, FE_KP_CAP);
-    if (rc) return rc;
-    fe18_runs_kernel<true><<<R, 256, 0, st>>>(d_flags, R, C, min_range, S.d_rowcount, d_polar, FE_KP_CAP);
-    NRS_LAUNCHED();
+    if (d_polar) return fe_gather_rows_device(ctx, S, d_polar);        // standalone detector call; else fe_tail_kernel does it
     return NRS_OK;
 }
 

@@ -24,6 +24,7 @@
 //                                       test against the neighbouring azimuths (wrap-around),
 //                                       getMaxInRegion's int-truncated running max, ordered emission.
 // Bound: HBM (R*C*4 = 5.4 MB per frame plus the sort's passes); DESIGN.md gives the byte counts.
+#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <float.h>
@@ -59,11 +60,32 @@ __device__ __forceinline__ float prewitt_abs(const float *__restrict__ row, int 
 
 constexpr int RED_THREADS = 256;
 
+// cv::mean = sum * (1.0 / N) in f64, truncated to float by the reference (features.cpp:211,214).  Called by thread 0
+// of every block after it stored its partial sum; the block that draws the last ticket reduces all partials in one
+// fixed order (lane l sums partial[l], partial[l + 32], ... then a fixed shuffle tree), whichever block it is.
+__device__ __forceinline__ void last_block_mean(unsigned int *ticket, const double *partial, double inv_n,
+                                                float *mean_out, bool *is_last)
+{
+    if (threadIdx.x == 0) {
+        __threadfence();
+        *is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (*is_last && threadIdx.x < 32) {
+        __threadfence();
+        double s = 0.0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) s += __ldcg(partial + b);
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) *mean_out = (float)(s * inv_n);
+    }
+}
+
 // sum(f) in f64 (exact for k/255 data: every partial sum is a multiple of 2^-31 below 2^21) and max(g)
 __global__ void __launch_bounds__(RED_THREADS)
 fe_stats_kernel(const float *__restrict__ fft, int R, int C, double *__restrict__ partial,
-                int *__restrict__ maxg_bits)
+                FrameCounts *__restrict__ cnt)
 {
+    __shared__ bool is_last;
     const size_t N = (size_t)R * C;
     double s = 0.0;
     float mg = 0.0f;
@@ -84,26 +106,17 @@ fe_stats_kernel(const float *__restrict__ fft, int R, int C, double *__restrict_
         float m = 0.0f;
         for (int w = 0; w < RED_THREADS / 32; ++w) m = fmaxf(m, smax[w]);
         partial[blockIdx.x] = bs;
-        atomicMax(maxg_bits, __float_as_int(m));      // g >= 0: int order == float order
+        atomicMax(reinterpret_cast<int *>(&cnt->maxg), __float_as_int(m));      // g >= 0: int order == float order
     }
-}
-
-// cv::mean = sum * (1.0 / N) in f64, truncated to float by the reference (features.cpp:211,214)
-__global__ void fe_mean_kernel(const double *__restrict__ partial, int nblocks, double inv_n,
-                               float *__restrict__ mean_out)
-{
-    // one warp, fixed order: lane l sums partial[l], partial[l+32], ... then a fixed shuffle tree
-    double s = 0.0;
-    for (int b = threadIdx.x; b < nblocks; b += 32) s += partial[b];
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) *mean_out = (float)(s * inv_n);
+    last_block_mean(&cnt->ticket[0], partial, 1.0 / (double)N, &cnt->mean, &is_last);
 }
 
 // h = s .* (1 - g / maxg) (features.cpp:206-213), all f32; Mat /= double multiplies by (float)(1/maxg)
 __global__ void __launch_bounds__(RED_THREADS)
-fe_h_kernel(const float *__restrict__ fft, int R, int C, const FrameCounts *__restrict__ cnt,
+fe_h_kernel(const float *__restrict__ fft, int R, int C, FrameCounts *__restrict__ cnt,
             float *__restrict__ h, double *__restrict__ partial)
 {
+    __shared__ bool is_last;
     const size_t N = (size_t)R * C;
     const float mean = cnt->mean;
     const float inv = (float)(1.0 / (double)cnt->maxg);
@@ -121,6 +134,7 @@ fe_h_kernel(const float *__restrict__ fft, int R, int C, const FrameCounts *__re
     __shared__ typename BR::TempStorage tmp;
     const double bs = BR(tmp).Sum(s);
     if (threadIdx.x == 0) partial[blockIdx.x] = bs;
+    last_block_mean(&cnt->ticket[1], partial, 1.0 / (double)N, &cnt->mean_h, &is_last);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -263,24 +277,127 @@ fe_prep_sub_kernel(const float *__restrict__ h, size_t N, FrameCounts *__restric
     if (threadIdx.x == 0 && bc) atomicAdd(&cnt->n_cand, bc);
 }
 
-__global__ void fe_sub_keys_kernel(const float *__restrict__ h, FrameCounts *__restrict__ cnt, float *__restrict__ keys,
-                                   unsigned int *__restrict__ vals)
+// The subset's sort as ONE launch: a thread-block cluster of 8 CTAs holds the <= 64k (key, pixel) pairs in its
+// distributed shared memory (8192 pairs per CTA, two buffers) and runs a stable LSD radix sort over them -- 8-bit
+// digits, per-warp private histograms over contiguous segments (ranks inside a 32-group from match.any, like
+// fe_tail_kernel), per-digit CTA totals exchanged through DSMEM, the scatter written straight into the owning
+// CTA's shared memory (st.shared::cluster).  Two cluster barriers per pass; a pass whose digit is the same for every
+// key is skipped.  Keys are h mapped to descending-sortable integers (-0.0 == +0.0 like the reference's compare),
+// so equal h keep pixel order exactly as cub::DeviceRadixSort::SortPairsDescending over the same list would.
+// Replaces fe_sub_keys_kernel + six CUB launches (histogram, scan, four onesweep passes) on the subset path.
+namespace cg = cooperative_groups;
+constexpr int SS_CL = 8, SS_T = 1024, SS_PER = FE_SUB_CAP / SS_CL;
+static_assert(SS_PER == 8192, "rank -> (CTA, slot) uses shifts");
+struct SubSortSmem {
+    unsigned int key[2][SS_PER];
+    unsigned int val[2][SS_PER];
+    unsigned short hist[32][256];        // [warp][digit]: counts, then exclusive offsets among this CTA's warps
+    unsigned int tot[256];               // this CTA's items per digit (read by the whole cluster)
+    unsigned int base[256];              // global rank of this CTA's first item with the digit
+    int skip;
+};
+
+__global__ void __cluster_dims__(SS_CL, 1, 1) __launch_bounds__(SS_T)
+fe_subsort_kernel(const float *__restrict__ h, const unsigned int *__restrict__ sel, FrameCounts *__restrict__ cnt,
+                  float *__restrict__ keys_out, unsigned int *__restrict__ vals_out)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= FE_SUB_CAP) return;
+    typedef cub::BlockScan<unsigned int, SS_T> BS;
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ typename BS::TempStorage tmp;
+    SubSortSmem &sm = *reinterpret_cast<SubSortSmem *>(dyn);
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = (int)cluster.block_rank();
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int n_sub = cnt->n_sub;
-    if (k == 0) {
-        cnt->n_sorted = min(n_sub, FE_SUB_CAP);
-        if (n_sub > FE_SUB_CAP) cnt->need_full = 1;         // the first 64k in pixel order are not the top 64k
+    const int n = min(n_sub, FE_SUB_CAP);
+    if (c == 0 && t == 0) {
+        cnt->n_sorted = n;
+        if (n_sub > FE_SUB_CAP) cnt->need_full = 1;          // the first 64k in pixel order are not the top 64k
     }
-    if (k < n_sub) {
-        const float hv = h[vals[k]];
-        keys[k] = (hv == 0.0f) ? 0.0f : hv;
-    } else {
-        keys[k] = -FLT_MAX;
-        vals[k] = 0xffffffffu;
+    const int my_n = max(0, min(SS_PER, n - c * SS_PER));
+    for (int i = t; i < my_n; i += SS_T) {
+        const unsigned int e = sel[c * SS_PER + i];
+        const float hv = h[e];
+        const unsigned int b = (hv == 0.0f) ? 0u : __float_as_uint(hv);
+        const unsigned int u = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);      // ascending-sortable
+        sm.key[0][i] = ~u;                                                        // descending
+        sm.val[0][i] = e;
+    }
+    const int seg = ((my_n + SS_T - 1) / SS_T) * 32;          // whole 32-groups per warp, contiguous in order
+    const int g0 = min(warp * seg, my_n), g1 = min(g0 + seg, my_n);
+    unsigned short *hw = sm.hist[warp];
+    const unsigned int lt = (1u << lane) - 1u;
+    int cur = 0;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 8 * pass;
+        const unsigned int *sk = sm.key[cur];
+        const unsigned int *sv = sm.val[cur];
+        for (int i = t; i < 32 * 256 / 2; i += SS_T) reinterpret_cast<unsigned int *>(&sm.hist[0][0])[i] = 0u;
+        if (t == 0) sm.skip = 0;
+        __syncthreads();
+        for (int gb = g0; gb < g1; gb += 32) {
+            const int k = gb + lane;
+            const bool ok = k < g1;
+            const unsigned int dig = ok ? ((sk[k] >> shift) & 255u) : 0xffffffffu;
+            const unsigned int peers = __match_any_sync(0xffffffffu, dig);
+            if (ok && !(peers & lt)) hw[dig] += (unsigned short)__popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        if (t < 256) {
+            unsigned int run = 0;
+#pragma unroll 8
+            for (int w = 0; w < 32; ++w) { const unsigned int v = sm.hist[w][t]; sm.hist[w][t] = (unsigned short)run; run += v; }
+            sm.tot[t] = run;
+        }
+        cluster.sync();
+        unsigned int all = 0, before = 0;
+        if (t < 256) {
+#pragma unroll
+            for (int cc = 0; cc < SS_CL; ++cc) {
+                const unsigned int v = *cluster.map_shared_rank(&sm.tot[t], cc);
+                all += v;
+                if (cc < c) before += v;
+            }
+            if (all == (unsigned int)n && n > 0) sm.skip = 1;       // every key has this digit: the pass is the identity
+        }
+        unsigned int ex;
+        BS(tmp).ExclusiveSum(all, ex);
+        if (t < 256) sm.base[t] = ex + before;
+        __syncthreads();
+        const bool skip = sm.skip != 0;                        // the same verdict in every CTA (global counts)
+        if (!skip) {
+            unsigned int *dk = sm.key[cur ^ 1], *dv = sm.val[cur ^ 1];
+            for (int gb = g0; gb < g1; gb += 32) {
+                const int k = gb + lane;
+                const bool ok = k < g1;
+                const unsigned int key = ok ? sk[k] : 0u;
+                const unsigned int dig = ok ? ((key >> shift) & 255u) : 0xffffffffu;
+                const unsigned int peers = __match_any_sync(0xffffffffu, dig);
+                const int rank = __popc(peers & lt);
+                const unsigned int loc = ok ? hw[dig] : 0u;
+                __syncwarp();
+                if (ok && rank == 0) hw[dig] = (unsigned short)(loc + __popc(peers));
+                __syncwarp();
+                if (ok) {
+                    const unsigned int dst = sm.base[dig] + loc + rank;            // rank in the whole list
+                    const unsigned int dc = dst >> 13, di = dst & (SS_PER - 1);
+                    *cluster.map_shared_rank(&dk[di], dc) = key;
+                    *cluster.map_shared_rank(&dv[di], dc) = sv[k];
+                }
+            }
+            cur ^= 1;
+        }
+        cluster.sync();                                        // remote stores landed; tot / base free for the next pass
+    }
+    for (int i = t; i < my_n; i += SS_T) {
+        const unsigned int u = ~sm.key[cur][i];
+        const unsigned int b = (u >> 31) ? (u ^ 0x80000000u) : ~u;
+        keys_out[c * SS_PER + i] = __uint_as_float(b);
+        vals_out[c * SS_PER + i] = sm.val[cur][i];
     }
 }
+
 __global__ void fe_set_sorted_full_kernel(FrameCounts *__restrict__ cnt)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) cnt->n_sorted = cnt->n_cand;
@@ -289,14 +406,14 @@ __global__ void fe_set_sorted_full_kernel(FrameCounts *__restrict__ cnt)
 // ------------------------------------------------------------------------------------------------
 // K3: per-azimuth scan (features.cpp:251-278), one warp per azimuth
 // ------------------------------------------------------------------------------------------------
-template <bool EMIT>
 __global__ void __launch_bounds__(256)
 fe_scan_rows_kernel(const unsigned int *__restrict__ claim, const float *__restrict__ h, int R, int C,
                     int min_range, const FrameCounts *__restrict__ cnt, int *__restrict__ rowcount,
-                    int *__restrict__ polar, int cap)
+                    int *__restrict__ stage)
 {
-    // one 256-thread block per azimuth, one column per thread per step; emission stays ordered by
-    // column through per-warp ballots and a running base
+    // one 256-thread block per azimuth, one column per thread per step; the azimuth's range bins go to its own
+    // staging row (at most one per closed run, so fewer than C), ordered by column through per-warp ballots and a
+    // running base; fe_tail_kernel strings the rows together
     __shared__ int wsum[8];
     __shared__ int running;
     const int i = blockIdx.x;
@@ -307,7 +424,8 @@ fe_scan_rows_kernel(const unsigned int *__restrict__ claim, const float *__restr
     const int below = (i == 0) ? R - 1 : i - 1, above = (i + 1 >= R) ? 0 : i + 1;     // :173-178
     const unsigned int *cb = claim + (size_t)below * C, *ca = claim + (size_t)above * C;
     const float *hrow = h + (size_t)i * C;
-    if (threadIdx.x == 0) running = EMIT ? rowcount[i] : 0;
+    int *srow = stage + (size_t)i * C;
+    if (threadIdx.x == 0) running = 0;
     __syncthreads();
     for (int j0 = min_range; j0 < C; j0 += 256) {
         const int j = j0 + threadIdx.x;
@@ -343,156 +461,244 @@ fe_scan_rows_kernel(const unsigned int *__restrict__ claim, const float *__restr
 #pragma unroll
         for (int w = 0; w < 8; ++w) { const int c = wsum[w]; if (w < warp) before += c; total += c; }
         const int base = running;
-        if (EMIT && emit) {
-            const int pos = base + before + __popc(mask & ((1u << lane) - 1u));
-            if (pos < cap) { polar[2 * pos] = i; polar[2 * pos + 1] = max_r; }
-        }
+        if (emit) srow[base + before + __popc(mask & ((1u << lane) - 1u))] = max_r;
         __syncthreads();
         if (threadIdx.x == 0) running = base + total;
         __syncthreads();
     }
-    if (!EMIT && threadIdx.x == 0) rowcount[i] = running;
+    if (threadIdx.x == 0) rowcount[i] = running;
 }
 
-// exclusive scan of the per-azimuth counts (R <= 1024), total -> K0
+// The standalone detector entry points (nrs_cen2019 / nrs_cen2018) have no tail kernel behind them: the same
+// stringing of the staging rows on its own, (azimuth, range bin) pairs -> polar, total -> K0.
 __global__ void __launch_bounds__(1024)
-fe_rowscan_kernel(int *__restrict__ rowcount, int R, FrameCounts *__restrict__ cnt, int cap)
+fe_gather_rows_kernel(const int *__restrict__ rowcount, const int *__restrict__ stage, int R, int C,
+                      FrameCounts *__restrict__ cnt, int *__restrict__ polar, int cap)
 {
     typedef cub::BlockScan<int, 1024> BS;
     __shared__ typename BS::TempStorage tmp;
-    const int t = threadIdx.x;
-    int v = (t < R) ? rowcount[t] : 0, ex, total;
+    __shared__ int rowoff[FE_MAX_AZ];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int v = (t < R) ? rowcount[t] : 0;
+    int ex, total;
     BS(tmp).ExclusiveSum(v, ex, total);
-    if (t < R) rowcount[t] = ex;
+    if (t < R) rowoff[t] = ex;
     if (t == 0) {
         cnt->K0 = min(total, cap);
         if (total > cap) cnt->overflow = 1;
     }
+    __syncthreads();
+    for (int a = warp; a < R; a += 32) {
+        const int c = rowcount[a], off = rowoff[a];
+        for (int e = lane; e < c && off + e < cap; e += 32) {
+            polar[2 * (off + e)] = a;
+            polar[2 * (off + e) + 1] = stage[(size_t)a * C + e];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
-// polar_to_cartesian_points (radar_utils.cpp:329-341); cos/sin come from the host's libm table
-// ------------------------------------------------------------------------------------------------
-__global__ void fe_points_kernel(const int *__restrict__ polar, const FrameCounts *__restrict__ cnt,
-                                 const double *__restrict__ cossin, const long long *__restrict__ times,
-                                 float radar_resolution, double *__restrict__ cart_pre,
-                                 long long *__restrict__ t_pre)
-{
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= cnt->K0) return;
-    const int a = polar[2 * k], rb = polar[2 * k + 1];
-    const double r = (double)rb * (double)radar_resolution + (double)(radar_resolution / 2);
-    cart_pre[2 * k] = r * cossin[2 * a];
-    cart_pre[2 * k + 1] = r * cossin[2 * a + 1];
-    t_pre[k] = times[a];
-}
-
-// ------------------------------------------------------------------------------------------------
-// voxelize (radar_loader.hpp:207-222 -> pcl::VoxelGrid<PointXYZ>::applyFilter), float32 like PCL
+// K3 tail: polar_to_cartesian_points (radar_utils.cpp:329-341; cos/sin from the host's libm table), voxelize
+// (radar_loader.hpp:207-222 -> pcl::VoxelGrid<PointXYZ>::applyFilter, float32 like PCL), convert_to_bev
+// (radar_utils.cpp:382-403) and ORB's border filter in ONE single-CTA launch.  At most FE_KP_CAP points: the
+// voxel sort is a stable LSD radix sort held entirely in shared memory (8-bit digits, one private histogram per
+// warp over a contiguous segment, ranks inside a 32-group from match.any), as many passes as the largest voxel
+// index has bytes.  The keypoints arrive as one staging row of range bins per azimuth (fe_scan_rows_kernel /
+// fe18_runs_kernel): the kernel scans the row counts and strings the rows together (K0, d_polar) itself.
+// Replaces eight launches plus a three-pass cub::DeviceRadixSort.
 // ------------------------------------------------------------------------------------------------
 struct VoxGrid { int min_bx, min_by, div_x; float inv; };
+constexpr int TAIL_T = 1024;
+constexpr size_t FE_TAIL_SMEM = (size_t)FE_KP_CAP * (2 * 4 + 2 * 2) + 32 * 256 * 2;
 
-__global__ void __launch_bounds__(1024)
-fe_vox_keys_kernel(const double *__restrict__ cart_pre, const FrameCounts *__restrict__ cnt,
-                   float leaf, int cap, unsigned int *__restrict__ keys, unsigned int *__restrict__ vals,
-                   float *__restrict__ pts32)
+__global__ void __launch_bounds__(TAIL_T)
+fe_tail_kernel(const int *__restrict__ rowcount, const int *__restrict__ stage, int R, int C,
+               int *__restrict__ polar, FrameCounts *__restrict__ cnt, const double *__restrict__ cossin,
+               const long long *__restrict__ times, float radar_resolution, int use_vox, float leaf, int cap,
+               double *__restrict__ cart_pre, long long *__restrict__ t_pre, float *__restrict__ pts32,
+               double *__restrict__ vox_xy, float cart_resolution, int width, int patch,
+               double *__restrict__ feat, float *__restrict__ kp, long long *__restrict__ t_out,
+               float *__restrict__ kp_orb)
 {
+    typedef cub::BlockScan<int, TAIL_T> BS;
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ typename BS::TempStorage tmp;
     __shared__ float smin[2][32], smax[2][32];
     __shared__ VoxGrid g;
-    const int t = threadIdx.x, K0 = cnt->K0;
-    float mnx = FLT_MAX, mny = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX;
-    for (int k = t; k < K0; k += blockDim.x) {
-        const float x = (float)cart_pre[2 * k], y = (float)cart_pre[2 * k + 1];   // eigen2pcl: double -> float
-        pts32[2 * k] = x; pts32[2 * k + 1] = y;
-        mnx = fminf(mnx, x); mxx = fmaxf(mxx, x);
-        mny = fminf(mny, y); mxy = fmaxf(mxy, y);
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-    }
-    if ((t & 31) == 0) { smin[0][t >> 5] = mnx; smin[1][t >> 5] = mny; smax[0][t >> 5] = mxx; smax[1][t >> 5] = mxy; }
-    __syncthreads();
-    if (t == 0) {
-        for (int w = 1; w < 32; ++w) {
-            mnx = fminf(mnx, smin[0][w]); mny = fminf(mny, smin[1][w]);
-            mxx = fmaxf(mxx, smax[0][w]); mxy = fmaxf(mxy, smax[1][w]);
+    __shared__ unsigned int maxkey;
+    __shared__ int carry;
+    __shared__ int rowoff[FE_MAX_AZ];
+    unsigned int *kbuf[2] = {reinterpret_cast<unsigned int *>(dyn), reinterpret_cast<unsigned int *>(dyn) + cap};
+    unsigned short *vbuf[2] = {reinterpret_cast<unsigned short *>(kbuf[1] + cap), reinterpret_cast<unsigned short *>(kbuf[1] + cap) + cap};
+    unsigned short *hist = vbuf[1] + cap;                           // [warp][digit]
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    // ---- the azimuths' staging rows, strung together in azimuth order (features.cpp:251-278 pushes them in
+    // this order); more than cap keypoints is reported, not truncated silently ----
+    int K0;
+    {
+        const int v = (t < R) ? rowcount[t] : 0;
+        int ex, total;
+        BS(tmp).ExclusiveSum(v, ex, total);
+        if (t < R) rowoff[t] = ex;
+        K0 = min(total, cap);
+        if (t == 0) {
+            cnt->K0 = K0;
+            if (total > cap) cnt->overflow = 1;
         }
-        const float inv = 1.0f / leaf;                          // inverse_leaf_size_
-        g.inv = inv;
-        g.min_bx = (int)floorf(mnx * inv);
-        g.min_by = (int)floorf(mny * inv);
-        g.div_x = (int)floorf(mxx * inv) - g.min_bx + 1;        // div_b_[0]; z is constant -> ijk2 = 0
+        __syncthreads();
     }
-    __syncthreads();
-    for (int k = t; k < cap; k += blockDim.x) {
-        unsigned int key = 0xffffffffu;
-        if (k < K0) {
+
+    // ---- polar_to_cartesian_points; PCL's float copy and its bounding box ----
+    float mnx = FLT_MAX, mny = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX;
+    for (int a = warp; a < R; a += TAIL_T / 32) {
+        const int c = rowcount[a], off = rowoff[a];
+        const double ca = cossin[2 * a], sa = cossin[2 * a + 1];
+        const long long ta = times[a];
+        for (int e = lane; e < c; e += 32) {
+            const int k = off + e;
+            if (k >= cap) break;
+            const int rb = stage[(size_t)a * C + e];
+            polar[2 * k] = a;
+            polar[2 * k + 1] = rb;
+            const double r = (double)rb * (double)radar_resolution + (double)(radar_resolution / 2);
+            const double cx = r * ca, cy = r * sa;
+            cart_pre[2 * k] = cx;
+            cart_pre[2 * k + 1] = cy;
+            t_pre[k] = ta;
+            if (use_vox) {
+                const float x = (float)cx, y = (float)cy;            // eigen2pcl: double -> float
+                pts32[2 * k] = x; pts32[2 * k + 1] = y;
+                mnx = fminf(mnx, x); mxx = fmaxf(mxx, x);
+                mny = fminf(mny, y); mxy = fmaxf(mxy, y);
+            }
+        }
+    }
+    __syncthreads();                                                 // pts32 is read by other threads below
+    int n = K0;
+    const double *pts_xy = cart_pre;
+    if (use_vox) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+            mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        }
+        if (lane == 0) { smin[0][warp] = mnx; smin[1][warp] = mny; smax[0][warp] = mxx; smax[1][warp] = mxy; }
+        __syncthreads();
+        if (t == 0) {
+            for (int w = 1; w < 32; ++w) {
+                mnx = fminf(mnx, smin[0][w]); mny = fminf(mny, smin[1][w]);
+                mxx = fmaxf(mxx, smax[0][w]); mxy = fmaxf(mxy, smax[1][w]);
+            }
+            const float inv = 1.0f / leaf;                          // inverse_leaf_size_
+            g.inv = inv;
+            g.min_bx = (int)floorf(mnx * inv);
+            g.min_by = (int)floorf(mny * inv);
+            g.div_x = (int)floorf(mxx * inv) - g.min_bx + 1;        // div_b_[0]; z is constant -> ijk2 = 0
+            maxkey = 0u;
+        }
+        __syncthreads();
+        unsigned int mk = 0u;
+        for (int k = t; k < K0; k += TAIL_T) {
             const int i0 = (int)(floorf(pts32[2 * k] * g.inv) - (float)g.min_bx);
             const int i1 = (int)(floorf(pts32[2 * k + 1] * g.inv) - (float)g.min_by);
-            key = (unsigned int)(i0 + i1 * g.div_x);
+            const unsigned int key = (unsigned int)(i0 + i1 * g.div_x);
+            kbuf[0][k] = key;
+            vbuf[0][k] = (unsigned short)k;
+            mk = max(mk, key);
         }
-        keys[k] = key;
-        vals[k] = (unsigned int)k;
-    }
-}
-
-// centroids in ascending voxel index, f32 running sums in (stable) point order, / float(count)
-__global__ void __launch_bounds__(1024)
-fe_vox_centroid_kernel(const unsigned int *__restrict__ skeys, const unsigned int *__restrict__ svals,
-                       const float *__restrict__ pts32, FrameCounts *__restrict__ cnt, int cap,
-                       double *__restrict__ vox_xy)
-{
-    typedef cub::BlockScan<int, 1024> BS;
-    __shared__ typename BS::TempStorage tmp;
-    __shared__ int carry;
-    const int t = threadIdx.x, K0 = cnt->K0;
-    if (t == 0) carry = 0;
-    __syncthreads();
-    for (int base = 0; base < cap; base += 1024) {
-        const int k = base + t;
-        const bool head = (k < K0) && (k == 0 || skeys[k] != skeys[k - 1]);
-        int ex, total;
-        BS(tmp).ExclusiveSum(head ? 1 : 0, ex, total);
-        const int c0 = carry;
-        if (head) {
-            float sx = 0.0f, sy = 0.0f;
-            int n = 0;
-            for (int q = k; q < K0 && skeys[q] == skeys[k]; ++q) {
-                const unsigned int p = svals[q];
-                sx += pts32[2 * p];
-                sy += pts32[2 * p + 1];
-                ++n;
+        mk = __reduce_max_sync(0xffffffffu, mk);
+        if (lane == 0 && mk) atomicMax(&maxkey, mk);
+        __syncthreads();
+        const int passes = (32 - __clz(maxkey) + 7) >> 3;
+        const int seg = ((K0 + TAIL_T - 1) / TAIL_T) * 32;           // whole 32-groups per warp, contiguous in order
+        const int g0 = warp * seg, g1 = min(g0 + seg, K0);
+        unsigned short *hw = hist + warp * 256;
+        const unsigned int lt = (1u << lane) - 1u;
+        int cur = 0;
+        for (int pass = 0; pass < passes; ++pass) {
+            const int shift = 8 * pass;
+            const unsigned int *sk = kbuf[cur];
+            const unsigned short *sv = vbuf[cur];
+            unsigned int *dk = kbuf[cur ^ 1];
+            unsigned short *dv = vbuf[cur ^ 1];
+            for (int i = t; i < 32 * 256 / 2; i += TAIL_T) reinterpret_cast<unsigned int *>(hist)[i] = 0u;
+            __syncthreads();
+            for (int gb = g0; gb < g1; gb += 32) {
+                const int k = gb + lane;
+                const bool ok = k < K0;
+                const unsigned int dig = ok ? ((sk[k] >> shift) & 255u) : 0xffffffffu;
+                const unsigned int peers = __match_any_sync(0xffffffffu, dig);
+                if (ok && !(peers & lt)) hw[dig] += (unsigned short)__popc(peers);
+                __syncwarp();
             }
-            const float fn = (float)n;
-            vox_xy[2 * (c0 + ex)] = (double)(sx / fn);
-            vox_xy[2 * (c0 + ex) + 1] = (double)(sy / fn);
+            __syncthreads();
+            {   // exclusive offsets in (digit, warp) order: thread t owns digit t / 4, warps 8 * (t % 4) .. + 7
+                const int d = t >> 2, w0 = (t & 3) * 8;
+                int c[8], sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { c[j] = hist[(w0 + j) * 256 + d]; sum += c[j]; }
+                int ex;
+                BS(tmp).ExclusiveSum(sum, ex);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { hist[(w0 + j) * 256 + d] = (unsigned short)ex; ex += c[j]; }
+            }
+            __syncthreads();
+            for (int gb = g0; gb < g1; gb += 32) {
+                const int k = gb + lane;
+                const bool ok = k < K0;
+                const unsigned int key = ok ? sk[k] : 0u;
+                const unsigned int dig = ok ? ((key >> shift) & 255u) : 0xffffffffu;
+                const unsigned int peers = __match_any_sync(0xffffffffu, dig);
+                const int rank = __popc(peers & lt);
+                const int base = ok ? hw[dig] : 0;
+                __syncwarp();
+                if (ok && rank == 0) hw[dig] = (unsigned short)(base + __popc(peers));
+                __syncwarp();
+                if (ok) { dk[base + rank] = key; dv[base + rank] = sv[k]; }
+            }
+            __syncthreads();
+            cur ^= 1;
         }
+        // centroids in ascending voxel index, f32 running sums in (stable) point order, / float(count)
+        const unsigned int *skeys = kbuf[cur];
+        const unsigned short *svals = vbuf[cur];
+        if (t == 0) carry = 0;
         __syncthreads();
-        if (t == 0) carry = c0 + total;
+        for (int base = 0; base < K0; base += TAIL_T) {
+            const int k = base + t;
+            const bool head = (k < K0) && (k == 0 || skeys[k] != skeys[k - 1]);
+            int ex, total;
+            BS(tmp).ExclusiveSum(head ? 1 : 0, ex, total);
+            const int c0 = carry;
+            if (head) {
+                float sx = 0.0f, sy = 0.0f;
+                int m = 0;
+                for (int q = k; q < K0 && skeys[q] == skeys[k]; ++q) {
+                    const unsigned int p = svals[q];
+                    sx += pts32[2 * p];
+                    sy += pts32[2 * p + 1];
+                    ++m;
+                }
+                const float fn = (float)m;
+                vox_xy[2 * (c0 + ex)] = (double)(sx / fn);
+                vox_xy[2 * (c0 + ex) + 1] = (double)(sy / fn);
+            }
+            __syncthreads();
+            if (t == 0) carry = c0 + total;
+            __syncthreads();
+        }
+        n = carry;
+        pts_xy = vox_xy;
         __syncthreads();
+        if (t == 0) cnt->Kv = n;
     }
-    if (t == 0) cnt->Kv = carry;
-}
 
-// convert_to_bev (radar_utils.cpp:382-403): ordered compaction, keypoints (u, v), stamps with the
-// reference's pre-voxelisation indexing quirk (radar_loader.hpp:123-124)
-__global__ void __launch_bounds__(1024)
-fe_bev_kernel(const double *__restrict__ pts_xy, const long long *__restrict__ t_pre,
-              FrameCounts *__restrict__ cnt, int use_vox, float cart_resolution, int width, int patch,
-              int cap, double *__restrict__ feat, float *__restrict__ kp, long long *__restrict__ t_out,
-              float *__restrict__ kp_orb)
-{
-    typedef cub::BlockScan<int, 1024> BS;
-    __shared__ typename BS::TempStorage tmp;
-    __shared__ int carry;
-    const int t = threadIdx.x;
-    const int n = use_vox ? cnt->Kv : cnt->K0;
+    // ---- convert_to_bev: ordered compaction, keypoints (u, v), stamps with the reference's pre-voxelisation
+    // indexing quirk (radar_loader.hpp:123-124) ----
     float cmr = (width / 2) * cart_resolution;
     if (width % 2 == 0) cmr = (float)((width / 2 - 0.5) * cart_resolution);
     if (t == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < cap; base += 1024) {
+    for (int base = 0; base < n; base += TAIL_T) {
         const int i = base + t;
         bool keep = false;
         double x = 0, y = 0, u = 0, v = 0;
@@ -515,7 +721,6 @@ fe_bev_kernel(const double *__restrict__ pts_xy, const long long *__restrict__ t
         if (t == 0) carry = c0 + total;
         __syncthreads();
     }
-    __syncthreads();
     const int K = carry;
     __syncthreads();
     if (t == 0) { cnt->K = K; carry = 0; }
@@ -524,7 +729,7 @@ fe_bev_kernel(const double *__restrict__ pts_xy, const long long *__restrict__ t
     // edgeThreshold = patch): Rect(Point(b,b), Point(W-b,W-b)).contains(Point(cvRound(u), cvRound(v))).
     // Keypoints with cvRound(u|v) == W - patch are dropped from kp_/desc_ while feat_in_cart_ keeps its
     // columns -- the reference's index misalignment is reproduced, not repaired.
-    for (int base = 0; base < K; base += 1024) {
+    for (int base = 0; base < K; base += TAIL_T) {
         const int j = base + t;
         bool keep = false;
         float u = 0.f, v = 0.f;
@@ -549,9 +754,9 @@ fe_bev_kernel(const double *__restrict__ pts_xy, const long long *__restrict__ t
 // ------------------------------------------------------------------------------------------------
 static int stats_blocks(const nrs_ctx *ctx) { return ctx->sm_count * 8; }
 
-int fe_launch_rowscan(cudaStream_t st, int *rowcount, int R, FrameCounts *cnt, int cap)
+int fe_gather_rows_device(nrs_ctx *ctx, FrontendState &S, int *d_polar)
 {
-    fe_rowscan_kernel<<<1, 1024, 0, st>>>(rowcount, R, cnt, cap);
+    fe_gather_rows_kernel<<<1, 1024, 0, ctx->stream>>>(S.d_rowcount, S.d_stage, S.R, S.C, S.d_counts, d_polar, FE_KP_CAP);
     NRS_LAUNCHED();
     return NRS_OK;
 }
@@ -564,13 +769,9 @@ int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_poin
     const int nb = stats_blocks(ctx);
     FrameCounts *cnt = S.d_counts;
     if (reset_counts) NRS_CUDA(cudaMemsetAsync(cnt, 0, sizeof(FrameCounts), st));
-    fe_stats_kernel<<<nb, RED_THREADS, 0, st>>>(S.d_fft, R, C, S.d_partial, (int *)&cnt->maxg);
+    fe_stats_kernel<<<nb, RED_THREADS, 0, st>>>(S.d_fft, R, C, S.d_partial, cnt);       // -> maxg, mean (last block)
     NRS_LAUNCHED();
-    fe_mean_kernel<<<1, 32, 0, st>>>(S.d_partial, nb, 1.0 / (double)N, &cnt->mean);
-    NRS_LAUNCHED();
-    fe_h_kernel<<<nb, RED_THREADS, 0, st>>>(S.d_fft, R, C, cnt, S.d_h, S.d_partial);
-    NRS_LAUNCHED();
-    fe_mean_kernel<<<1, 32, 0, st>>>(S.d_partial, nb, 1.0 / (double)N, &cnt->mean_h);
+    fe_h_kernel<<<nb, RED_THREADS, 0, st>>>(S.d_fft, R, C, cnt, S.d_h, S.d_partial);     // -> h, mean_h (last block)
     NRS_LAUNCHED();
     const bool sub = S.have_thresh && !force_full;
     const size_t n_walk = sub ? (size_t)FE_SUB_CAP : N;       // length of the sorted list the marking kernels cover
@@ -581,7 +782,17 @@ int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_poin
         thrust::counting_iterator<unsigned int> ids(0u);
         NRS_CUDA(cub::DeviceSelect::If(S.d_cub, need, ids, S.d_vals[0], &cnt->n_sub, (int)N, SubSelect{S.d_h, S.d_thresh, cnt}, st));
         g_launches.fetch_add(1, std::memory_order_relaxed);
-        fe_sub_keys_kernel<<<FE_SUB_CAP / 256, 256, 0, st>>>(S.d_h, cnt, S.d_keys[0], S.d_vals[0]);
+        {   // opt in to the cluster sort's 146 KB of dynamic shared memory once per device
+            static std::mutex cfg_mu;
+            static bool configured[64] = {};
+            std::lock_guard<std::mutex> lk(cfg_mu);
+            const int dv = (ctx->device >= 0 && ctx->device < 64) ? ctx->device : -1;
+            if (dv < 0 || !configured[dv]) {
+                NRS_CUDA(cudaFuncSetAttribute(fe_subsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SubSortSmem)));
+                if (dv >= 0) configured[dv] = true;
+            }
+        }
+        fe_subsort_kernel<<<SS_CL, SS_T, sizeof(SubSortSmem), st>>>(S.d_h, S.d_vals[0], cnt, S.d_keys[1], S.d_vals[1]);
         NRS_LAUNCHED();
     } else {
         fe_keys_kernel<<<nb, RED_THREADS, 0, st>>>(S.d_h, N, cnt, S.d_keys[0], S.d_vals[0], S.d_claim);
@@ -589,10 +800,12 @@ int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_poin
         fe_set_sorted_full_kernel<<<1, 32, 0, st>>>(cnt);
         NRS_LAUNCHED();
     }
-    need = S.cub_bytes;
-    NRS_CUDA(cub::DeviceRadixSort::SortPairsDescending(S.d_cub, need, S.d_keys[0], S.d_keys[1], S.d_vals[0],
-                                                       S.d_vals[1], (int)n_walk, 0, 32, st));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!sub) {
+        need = S.cub_bytes;
+        NRS_CUDA(cub::DeviceRadixSort::SortPairsDescending(S.d_cub, need, S.d_keys[0], S.d_keys[1], S.d_vals[0],
+                                                           S.d_vals[1], (int)n_walk, 0, 32, st));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
     const int tb = 256;
     const unsigned int gb = (unsigned int)((n_walk + tb - 1) / tb);
     fe_claim_kernel<<<gb, tb, 0, st>>>(S.d_vals[1], S.d_fft, R, C, cnt, S.d_claim);
@@ -609,45 +822,32 @@ int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_poin
     NRS_LAUNCHED();
     S.have_thresh = true;
     const int sb = R;
-    fe_scan_rows_kernel<false><<<sb, 256, 0, st>>>(S.d_claim, S.d_h, R, C, min_range, cnt, S.d_rowcount, nullptr, 0);
+    fe_scan_rows_kernel<<<sb, 256, 0, st>>>(S.d_claim, S.d_h, R, C, min_range, cnt, S.d_rowcount, S.d_stage);
     NRS_LAUNCHED();
-    fe_rowscan_kernel<<<1, 1024, 0, st>>>(S.d_rowcount, R, cnt, FE_KP_CAP);
-    NRS_LAUNCHED();
-    fe_scan_rows_kernel<true><<<sb, 256, 0, st>>>(S.d_claim, S.d_h, R, C, min_range, cnt, S.d_rowcount, d_polar, FE_KP_CAP);
-    NRS_LAUNCHED();
+    if (d_polar) return fe_gather_rows_device(ctx, S, d_polar);        // standalone detector call; else fe_tail_kernel does it
     return NRS_OK;
 }
 
 int fe_points_voxel_bev_device(nrs_ctx *ctx, FrontendState &S, nrs_frame *f)
 {
     cudaStream_t st = ctx->stream;
-    FrameCounts *cnt = S.d_counts;
     const nrs_extract_params &p = S.p;
-    fe_points_kernel<<<(FE_KP_CAP + 255) / 256, 256, 0, st>>>(f->d_polar, cnt, S.d_cossin, S.d_times,
-                                                             p.radar_resolution, f->d_cart_pre, f->d_t_pre);
-    NRS_LAUNCHED();
-    const double *pts = f->d_cart_pre;
-    if (p.use_voxelization) {
-        fe_vox_keys_kernel<<<1, 1024, 0, st>>>(f->d_cart_pre, cnt, (float)p.voxel_size, FE_KP_CAP, S.d_vkey[0],
-                                               S.d_vval[0], S.d_pts32);
-        NRS_LAUNCHED();
-        size_t need = S.cub_bytes;
-        // voxel keys are i0 + i1 * div_x with both indices below extent / leaf + 2 (the points lie within the
-        // sensor range): when that product stays under 2^24 three radix passes suffice.  The padding key
-        // 0xffffffff has its low 24 bits set, so it still sorts behind every real key.
-        const double cells = 2.0 * S.C * p.radar_resolution / p.voxel_size + 4.0;
-        const int end_bit = (cells * cells < 16777214.0) ? 24 : 32;
-        NRS_CUDA(cub::DeviceRadixSort::SortPairs(S.d_cub, need, S.d_vkey[0], S.d_vkey[1], S.d_vval[0], S.d_vval[1],
-                                                 FE_KP_CAP, 0, end_bit, st));
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        // voxel centroids are staged in d_partial's neighbour: reuse d_keys[0] (free after the sort)
-        double *vox = reinterpret_cast<double *>(S.d_keys[0]);
-        fe_vox_centroid_kernel<<<1, 1024, 0, st>>>(S.d_vkey[1], S.d_vval[1], S.d_pts32, cnt, FE_KP_CAP, vox);
-        NRS_LAUNCHED();
-        pts = vox;
+    {   // opt in to the 208 KB of dynamic shared memory once per device (contexts on several GPUs may share the process)
+        static std::mutex cfg_mu;
+        static bool configured[64] = {};
+        std::lock_guard<std::mutex> lk(cfg_mu);
+        const int dv = (ctx->device >= 0 && ctx->device < 64) ? ctx->device : -1;
+        if (dv < 0 || !configured[dv]) {
+            NRS_CUDA(cudaFuncSetAttribute(fe_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FE_TAIL_SMEM));
+            if (dv >= 0) configured[dv] = true;
+        }
     }
-    fe_bev_kernel<<<1, 1024, 0, st>>>(pts, f->d_t_pre, cnt, p.use_voxelization, p.cart_resolution,
-                                      p.cart_pixel_width, p.patch_size, FE_KP_CAP, f->d_feat, f->d_kp, f->d_t, f->d_kp_orb);
+    // voxel centroids are staged in d_keys[0] (free once the keypoints are known)
+    double *vox = reinterpret_cast<double *>(S.d_keys[0]);
+    fe_tail_kernel<<<1, TAIL_T, FE_TAIL_SMEM, st>>>(S.d_rowcount, S.d_stage, S.R, S.C, f->d_polar, S.d_counts, S.d_cossin, S.d_times, p.radar_resolution,
+                                                   p.use_voxelization, (float)p.voxel_size, FE_KP_CAP, f->d_cart_pre,
+                                                   f->d_t_pre, S.d_pts32, vox, p.cart_resolution, p.cart_pixel_width,
+                                                   p.patch_size, f->d_feat, f->d_kp, f->d_t, f->d_kp_orb);
     NRS_LAUNCHED();
     return NRS_OK;
 }
@@ -666,8 +866,6 @@ size_t fe_cub_bytes(size_t N)
     cub::DeviceRadixSort::SortPairsDescending(nullptr, a, (float *)nullptr, (float *)nullptr, (unsigned int *)nullptr,
                                               (unsigned int *)nullptr, (int)N);
     cub::DeviceScan::InclusiveSum(nullptr, b, (unsigned int *)nullptr, (unsigned int *)nullptr, (int)N);
-    cub::DeviceRadixSort::SortPairs(nullptr, c, (unsigned int *)nullptr, (unsigned int *)nullptr, (unsigned int *)nullptr,
-                                    (unsigned int *)nullptr, FE_KP_CAP);
     size_t d = 0;
     thrust::counting_iterator<unsigned int> ids(0u);
     cub::DeviceSelect::If(nullptr, d, ids, (unsigned int *)nullptr, (int *)nullptr, (int)N, SubSelect{nullptr, nullptr, nullptr});

@@ -291,7 +291,7 @@ static void frontend_free(void *p)
     void *dev[] = {S->d_theta, S->d_sx, S->d_pattern, S->d_raw, S->d_fft, S->d_h, S->d_keys[0], S->d_keys[1],
                    S->d_vals[0], S->d_vals[1], S->d_claim, S->d_incr, S->d_partial, S->d_cart, S->d_rowbuf,
                    S->d_blur, S->d_cub, S->d_az, S->d_azsort, S->d_azidx, S->d_cossin, S->d_times, S->d_counts,
-                   S->d_vkey[0], S->d_vkey[1], S->d_vval[0], S->d_vval[1], S->d_pts32, S->d_rowcount, S->d_thresh};
+                   S->d_pts32, S->d_rowcount, S->d_thresh, S->d_stage};
     for (void *d : dev) if (d) cudaFree(d);
     for (auto &g : S->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     S->graphs.clear();
@@ -345,10 +345,8 @@ static int frontend_state(nrs_ctx *ctx, const nrs_extract_params *p, int R, int 
     rc |= dmalloc((unsigned char **)&S->d_cub, S->cub_bytes);
     rc |= dmalloc(&S->d_az, FE_MAX_AZ); rc |= dmalloc(&S->d_azsort, FE_MAX_AZ); rc |= dmalloc(&S->d_azidx, FE_MAX_AZ);
     rc |= dmalloc(&S->d_cossin, 2 * FE_MAX_AZ); rc |= dmalloc(&S->d_times, FE_MAX_AZ); rc |= dmalloc(&S->d_counts, 1);
-    rc |= dmalloc(&S->d_vkey[0], FE_KP_CAP); rc |= dmalloc(&S->d_vkey[1], FE_KP_CAP);
-    rc |= dmalloc(&S->d_vval[0], FE_KP_CAP); rc |= dmalloc(&S->d_vval[1], FE_KP_CAP);
     rc |= dmalloc(&S->d_pts32, 2 * FE_KP_CAP); rc |= dmalloc(&S->d_rowcount, FE_MAX_AZ);
-    rc |= dmalloc(&S->d_thresh, 1);
+    rc |= dmalloc(&S->d_thresh, 1); rc |= dmalloc(&S->d_stage, N);
     if (rc) return rc;
     NRS_CUDA(cudaMallocHost((void **)&S->h_counts, sizeof(FrameCounts)));
 
@@ -609,8 +607,8 @@ int extract_enqueue(nrs_ctx *ctx, FrontendState *S, nrs_frame *f, int R, int C, 
     NRS_CUDA(cudaEventRecord(S->ev_join, si));
     // keypoint branch on the context stream
     rc = (p->keypoint_extraction == 1)
-             ? fe_cen2018_device(ctx, *S, R, C, p->zq, p->sigma_gauss, p->min_range, f->d_polar, false, false)
-             : fe_cen2019_device(ctx, *S, R, C, p->max_points, p->min_range, f->d_polar, false, force_full);
+             ? fe_cen2018_device(ctx, *S, R, C, p->zq, p->sigma_gauss, p->min_range, nullptr, false, false)
+             : fe_cen2019_device(ctx, *S, R, C, p->max_points, p->min_range, nullptr, false, force_full);
     if (rc) { cudaStreamSynchronize(si); return rc; }
     if ((rc = fe_points_voxel_bev_device(ctx, *S, f))) { cudaStreamSynchronize(si); return rc; }
     NRS_CUDA(cudaStreamWaitEvent(st, S->ev_join, 0));           // join
