@@ -29,8 +29,16 @@ struct FrameCounts {
     int   n_sub;         // top-candidate subset: pixels with h >= the carried threshold (0 in full-sort mode)
     int   n_sorted;      // candidates in the sorted list the marking loop walked (== n_cand in full-sort mode)
     int   need_full;     // the subset could not prove the marking loop's outcome: redo with the full sort
-    unsigned int ticket[2];   // last-block tickets of fe_stats_kernel / fe_h_kernel (zeroed with the counts)
-    int   pad_;
+    unsigned int ticket[3];   // last-block tickets of fe_stats_kernel / fe_h_kernel / fe_incr_kernel (zeroed with the counts)
+};
+
+// per-frame azimuth tables, device layout == pinned host layout: ONE host-to-device copy per frame
+struct AzTables {
+    double az[FE_MAX_AZ];                // azimuths (R)
+    double azs[FE_MAX_AZ];               // sorted distinct azimuth values
+    double cossin[2 * FE_MAX_AZ];        // host libm cos / sin of each azimuth
+    long long times[FE_MAX_AZ];          // row stamps
+    int azi[FE_MAX_AZ];                  // lowest original index of each sorted distinct value
 };
 
 struct FrontendState {
@@ -55,6 +63,7 @@ struct FrontendState {
     void *d_cub = nullptr;               // CUB temp storage
     size_t cub_bytes = 0;
     // per-frame small tables
+    AzTables *d_tables = nullptr, *h_tables = nullptr;   // h_tables pinned; the five pointers below alias d_tables
     double *d_az = nullptr;              // azimuths (R)
     double *d_azsort = nullptr;          // sorted distinct azimuth values
     int    *d_azidx = nullptr;           // their (lowest) original index

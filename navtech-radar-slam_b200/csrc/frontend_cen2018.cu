@@ -248,39 +248,46 @@ fe18_flags_kernel(const float *__restrict__ q, const float *__restrict__ p, cons
 
 // :102-112 one CTA per azimuth: a run starts at a flagged column whose left neighbour (from min_range on) is
 // not flagged; it emits column start + len / 2.  Emission stays ordered through per-warp ballots.
-__global__ void __launch_bounds__(256)
+constexpr int RN_WARPS = 8, RN_SPAN = 512;       // columns per warp and round: at most RN_SPAN / 2 runs start in them
+
+__global__ void __launch_bounds__(RN_WARPS * 32)
 fe18_runs_kernel(const unsigned char *__restrict__ flags, int R, int C, int min_range, int *__restrict__ rowcount,
                  int *__restrict__ stage)
 {
-    __shared__ int wsum[8];
-    __shared__ int running;
+    // every warp walks its own span of columns and keeps a private list; two barriers per round of 8 x 512
+    // columns string the lists into this azimuth's staging row (fe_tail_kernel strings the rows)
+    __shared__ int wl[RN_WARPS][RN_SPAN / 2];
+    __shared__ int wn[RN_WARPS];
     const int i = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned char *fr = flags + (size_t)i * C;
-    int *srow = stage + (size_t)i * C;                       // this azimuth's staging row (fe_tail_kernel strings them)
-    if (threadIdx.x == 0) running = 0;
-    __syncthreads();
-    for (int j0 = min_range; j0 < C; j0 += 256) {
-        const int j = j0 + threadIdx.x;
-        bool emit = false;
-        int centre = 0;
-        if (j < C && fr[j] && (j == min_range || !fr[j - 1])) {
-            int end = j;
-            while (end + 1 < C && fr[end + 1]) ++end;
-            centre = j + (end - j + 1) / 2;                 // peak_points[peak_points.size() / 2]
-            emit = true;
+    int *srow = stage + (size_t)i * C;
+    int running = 0;
+    for (int base0 = min_range; base0 < C; base0 += RN_WARPS * RN_SPAN) {
+        const int w0 = base0 + warp * RN_SPAN, w1 = min(w0 + RN_SPAN, C);
+        int mine = 0;
+        for (int j0 = w0; j0 < w1; j0 += 32) {
+            const int j = j0 + lane;
+            bool emit = false;
+            int centre = 0;
+            if (j < w1 && fr[j] && (j == min_range || !fr[j - 1])) {
+                int end = j;
+                while (end + 1 < C && fr[end + 1]) ++end;
+                centre = j + (end - j + 1) / 2;                 // peak_points[peak_points.size() / 2]
+                emit = true;
+            }
+            const unsigned int mask = __ballot_sync(0xffffffffu, emit);
+            if (emit) wl[warp][mine + __popc(mask & ((1u << lane) - 1u))] = centre;
+            mine += __popc(mask);
         }
-        const unsigned int mask = __ballot_sync(0xffffffffu, emit);
-        if (lane == 0) wsum[warp] = __popc(mask);
+        if (lane == 0) wn[warp] = mine;
         __syncthreads();
         int before = 0, total = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { const int c = wsum[w]; if (w < warp) before += c; total += c; }
-        const int base = running;
-        if (emit) srow[base + before + __popc(mask & ((1u << lane) - 1u))] = centre;
-        __syncthreads();
-        if (threadIdx.x == 0) running = base + total;
-        __syncthreads();
+        for (int w = 0; w < RN_WARPS; ++w) { const int c = wn[w]; if (w < warp) before += c; total += c; }
+        for (int e = lane; e < mine; e += 32) srow[running + before + e] = wl[warp][e];
+        running += total;
+        __syncthreads();                                        // wn / wl are rewritten by the next round
     }
     if (threadIdx.x == 0) rowcount[i] = running;
 }
@@ -349,7 +356,7 @@ int fe_cen2018_device(nrs_ctx *ctx, FrontendState &S, int R, int C, float zq, in
     dim3 gp((C + 255) / 256, R);
     fe18_flags_kernel<<<gp, 256, 0, st>>>(d_q, d_p, d_sigma, R, C, zq, min_range, d_flags, d_y);
     NRS_LAUNCHED();
-    fe18_runs_kernel<<<R, 256, 0, st>>>(d_flags, R, C, min_range, S.d_rowcount, S.d_stage);
+    fe18_runs_kernel<<<R, RN_WARPS * 32, 0, st>>>(d_flags, R, C, min_range, S.d_rowcount, S.d_stage);
     NRS_LAUNCHED();
     if (d_polar) return fe_gather_rows_device(ctx, S, d_polar);        // standalone detector call; else fe_tail_kernel does it
     return NRS_OK;

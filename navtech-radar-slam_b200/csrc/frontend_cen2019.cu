@@ -192,55 +192,83 @@ __global__ void fe_claim_kernel(const unsigned int *__restrict__ sorted_vals,
     for (int i = lo; i <= hi; ++i) atomicMin(&crow[i], k);
 }
 
-__global__ void fe_incr_kernel(const unsigned int *__restrict__ sorted_vals,
-                               const float *__restrict__ fft, int R, int C,
-                               const FrameCounts *__restrict__ cnt,
-                               const unsigned int *__restrict__ claim, unsigned int *__restrict__ incr,
-                               size_t N)
+// Second half of the marking loop (features.cpp:227-249), after every candidate claimed its range: candidate k
+// opens a fresh region iff it still owns its whole range.  The flags go out as one bit per candidate (warp
+// ballots); the block that draws the last ticket then replays the loop's bookkeeping on them -- the loop exits
+// right after the increment that makes l == max_points (:231), so j_star is the position of the max_points-th
+// set bit -- and settles what used to be four more launches (an inclusive scan, the j_star search, its fix-up):
+//   * fewer than max_points regions in the whole list: every candidate was consumed, which the top-candidate
+//     subset can only vouch for when it held them all (else need_full);
+//   * the threshold carried to the next frame: the h value at rank ~4x the candidates this frame consumed (at
+//     least 16k, at most 48k of the 64k capacity).
+constexpr int INCR_T = 256;
+__global__ void __launch_bounds__(INCR_T)
+fe_incr_kernel(const unsigned int *__restrict__ sorted_vals, const float *__restrict__ fft, int R, int C,
+               FrameCounts *__restrict__ cnt, const unsigned int *__restrict__ claim,
+               unsigned int *__restrict__ bits, int max_points, const float *__restrict__ sorted_keys,
+               float *__restrict__ thresh)
 {
+    typedef cub::BlockScan<int, INCR_T> BS;
+    __shared__ typename BS::TempStorage tmp;
+    __shared__ bool is_last;
+    __shared__ int s_carry, s_jstar;
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= N) return;
-    unsigned int fresh = 0;
-    if (k < (size_t)cnt->n_sorted) {
+    const int n_sorted = cnt->n_sorted;
+    bool fresh = false;
+    if (k < (size_t)n_sorted) {
         const unsigned int e = sorted_vals[k];
         const int a = e / C, r = e - a * C;
         const float *row = fft + (size_t)a * C;
         int lo, hi;
         range_bounds(row, cnt->mean, R, C, r, lo, hi);
         const unsigned int *crow = claim + (size_t)a * C;
-        fresh = 1;
+        fresh = true;
         for (int i = lo; i <= hi; ++i)
-            if (crow[i] != (unsigned int)k) { fresh = 0; break; }
+            if (crow[i] != (unsigned int)k) { fresh = false; break; }
     }
-    incr[k] = fresh;
-}
-
-// the marking loop exits right after the increment that makes l == max_points (features.cpp:231)
-__global__ void fe_jstar_kernel(const unsigned int *__restrict__ incr, const unsigned int *__restrict__ cums,
-                                size_t N, int max_points, FrameCounts *__restrict__ cnt)
-{
-    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= N) return;
-    if (k < (size_t)cnt->n_sorted && incr[k] && cums[k] == (unsigned int)max_points) cnt->j_star = (int)k;
-    if (k == N - 1) cnt->l_regions = min((int)cums[k], max_points);
-}
-// the loop ran out of candidates before max_points regions: every candidate was consumed -- which the
-// top-candidate subset can only vouch for when it held them all.  Also carries the threshold to the next frame:
-// the h value at rank ~4x the candidates this frame consumed (at least 16k, at most 48k of the 64k capacity).
-__global__ void fe_jstar_fix_kernel(FrameCounts *__restrict__ cnt, const float *__restrict__ sorted_keys,
-                                    float *__restrict__ thresh)
-{
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (cnt->j_star < 0) {
-        if (cnt->n_sorted == cnt->n_cand) cnt->j_star = cnt->n_cand - 1;
+    const unsigned int word = __ballot_sync(0xffffffffu, fresh);
+    if ((threadIdx.x & 31) == 0) bits[k >> 5] = word;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = atomicAdd(&cnt->ticket[2], 1u) == gridDim.x - 1;
+        s_carry = 0;
+        s_jstar = -1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int nwords = (n_sorted + 31) >> 5;                 // every word below was written (the grid covers n_sorted)
+    for (int base = 0; base < nwords; base += INCR_T) {
+        const int w = base + threadIdx.x;
+        const unsigned int x = (w < nwords) ? __ldcg(bits + w) : 0u;
+        const int c = __popc(x);
+        int ex, total;
+        BS(tmp).ExclusiveSum(c, ex, total);
+        const int before = s_carry + ex;                     // fresh regions ahead of this word
+        if (before < max_points && before + c >= max_points) {
+            unsigned int y = x;                              // the (max_points - before)-th set bit
+            for (int q = max_points - before - 1; q > 0; --q) y &= y - 1;
+            s_jstar = w * 32 + __ffs(y) - 1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += total;
+        __syncthreads();
+        if (s_jstar >= 0) break;                             // uniform: written before the barrier above
+    }
+    if (threadIdx.x != 0) return;
+    int j_star = s_jstar;
+    cnt->l_regions = (j_star >= 0) ? max_points : s_carry;
+    if (j_star < 0) {
+        if (n_sorted == cnt->n_cand) j_star = cnt->n_cand - 1;
         else cnt->need_full = 1;
     }
-    if (cnt->need_full || cnt->n_sorted <= 0) return;
-    const int want = min(max(4 * (cnt->j_star + 1), 16384), 49152);
-    if (cnt->n_sorted > want) *thresh = sorted_keys[want];
-    else if (cnt->n_sorted == cnt->n_cand) *thresh = sorted_keys[cnt->n_sorted - 1];           // everything fits: keep it all
-    else if (cnt->n_sorted >= 2 * (cnt->j_star + 1)) *thresh = sorted_keys[cnt->n_sorted - 1]; // comfortable margin: keep
-    else *thresh = cnt->mean_h + 0.5f * (sorted_keys[cnt->n_sorted - 1] - cnt->mean_h);        // thin margin: loosen
+    cnt->j_star = j_star;
+    if (cnt->need_full || n_sorted <= 0) return;
+    const int want = min(max(4 * (j_star + 1), 16384), 49152);
+    if (n_sorted > want) *thresh = sorted_keys[want];
+    else if (n_sorted == cnt->n_cand) *thresh = sorted_keys[n_sorted - 1];           // everything fits: keep it all
+    else if (n_sorted >= 2 * (j_star + 1)) *thresh = sorted_keys[n_sorted - 1];      // comfortable margin: keep
+    else *thresh = cnt->mean_h + 0.5f * (sorted_keys[n_sorted - 1] - cnt->mean_h);   // thin margin: loosen
 }
 
 // ---- top-candidate subset (replaces the full-frame sort when a threshold is known) -----------------------------
@@ -406,16 +434,19 @@ __global__ void fe_set_sorted_full_kernel(FrameCounts *__restrict__ cnt)
 // ------------------------------------------------------------------------------------------------
 // K3: per-azimuth scan (features.cpp:251-278), one warp per azimuth
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int SR_WARPS = 8, SR_SPAN = 512;       // columns per warp and round: at most SR_SPAN / 2 runs start in them
+
+__global__ void __launch_bounds__(SR_WARPS * 32)
 fe_scan_rows_kernel(const unsigned int *__restrict__ claim, const float *__restrict__ h, int R, int C,
                     int min_range, const FrameCounts *__restrict__ cnt, int *__restrict__ rowcount,
                     int *__restrict__ stage)
 {
-    // one 256-thread block per azimuth, one column per thread per step; the azimuth's range bins go to its own
-    // staging row (at most one per closed run, so fewer than C), ordered by column through per-warp ballots and a
-    // running base; fe_tail_kernel strings the rows together
-    __shared__ int wsum[8];
-    __shared__ int running;
+    // one block per azimuth; every warp walks its own contiguous span of columns 32 at a time and appends the
+    // range bins it finds to a private list (ordered by column through ballots), two barriers per round of
+    // 8 x 512 columns string the lists together into the azimuth's staging row (at most one bin per closed run,
+    // so fewer than C); fe_tail_kernel strings the rows together
+    __shared__ int wl[SR_WARPS][SR_SPAN / 2];
+    __shared__ int wn[SR_WARPS];
     const int i = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int J = (unsigned int)cnt->j_star;
@@ -425,46 +456,49 @@ fe_scan_rows_kernel(const unsigned int *__restrict__ claim, const float *__restr
     const unsigned int *cb = claim + (size_t)below * C, *ca = claim + (size_t)above * C;
     const float *hrow = h + (size_t)i * C;
     int *srow = stage + (size_t)i * C;
-    if (threadIdx.x == 0) running = 0;
-    __syncthreads();
-    for (int j0 = min_range; j0 < C; j0 += 256) {
-        const int j = j0 + threadIdx.x;
-        bool emit = false;
-        int max_r = 0;
-        if (j < C && !none) {
-            const bool m = crow[j] <= J;
-            const bool prev = (j > min_range) && (crow[j - 1] <= J);
-            if (m && !prev) {                      // a run starts here
-                int end = j;
-                while (end + 1 < C && crow[end + 1] <= J) ++end;
-                if (end + 1 < C) {                 // closed by an unmarked pixel; else never emitted
-                    bool adj = false;              // checkAdjacentMarked :172-184
-                    for (int r = j; r <= end; ++r)
-                        if (cb[r] <= J || ca[r] <= J) { adj = true; break; }
-                    if (adj) {
-                        // getMaxInRegion :186-194 with its int-typed running max
-                        int mx = -1000;
-                        max_r = j;
-                        for (int r = j; r <= end; ++r) {
-                            const float hv = hrow[r];
-                            if (hv > (float)mx) { mx = (int)hv; max_r = r; }
+    int running = 0;
+    for (int base0 = min_range; base0 < C; base0 += SR_WARPS * SR_SPAN) {
+        const int w0 = base0 + warp * SR_SPAN, w1 = min(w0 + SR_SPAN, C);
+        int mine = 0;
+        for (int j0 = w0; j0 < w1 && !none; j0 += 32) {
+            const int j = j0 + lane;
+            bool emit = false;
+            int max_r = 0;
+            if (j < w1) {
+                const bool m = crow[j] <= J;
+                const bool prev = (j > min_range) && (crow[j - 1] <= J);
+                if (m && !prev) {                      // a run starts here
+                    int end = j;
+                    while (end + 1 < C && crow[end + 1] <= J) ++end;
+                    if (end + 1 < C) {                 // closed by an unmarked pixel; else never emitted
+                        bool adj = false;              // checkAdjacentMarked :172-184
+                        for (int r = j; r <= end; ++r)
+                            if (cb[r] <= J || ca[r] <= J) { adj = true; break; }
+                        if (adj) {
+                            // getMaxInRegion :186-194 with its int-typed running max
+                            int mx = -1000;
+                            max_r = j;
+                            for (int r = j; r <= end; ++r) {
+                                const float hv = hrow[r];
+                                if (hv > (float)mx) { mx = (int)hv; max_r = r; }
+                            }
+                            emit = true;
                         }
-                        emit = true;
                     }
                 }
             }
+            const unsigned int mask = __ballot_sync(0xffffffffu, emit);
+            if (emit) wl[warp][mine + __popc(mask & ((1u << lane) - 1u))] = max_r;
+            mine += __popc(mask);
         }
-        const unsigned int mask = __ballot_sync(0xffffffffu, emit);
-        if (lane == 0) wsum[warp] = __popc(mask);
+        if (lane == 0) wn[warp] = mine;
         __syncthreads();
         int before = 0, total = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { const int c = wsum[w]; if (w < warp) before += c; total += c; }
-        const int base = running;
-        if (emit) srow[base + before + __popc(mask & ((1u << lane) - 1u))] = max_r;
-        __syncthreads();
-        if (threadIdx.x == 0) running = base + total;
-        __syncthreads();
+        for (int w = 0; w < SR_WARPS; ++w) { const int c = wn[w]; if (w < warp) before += c; total += c; }
+        for (int e = lane; e < mine; e += 32) srow[running + before + e] = wl[warp][e];
+        running += total;
+        __syncthreads();                               // wn / wl are rewritten by the next round
     }
     if (threadIdx.x == 0) rowcount[i] = running;
 }
@@ -810,19 +844,11 @@ int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_poin
     const unsigned int gb = (unsigned int)((n_walk + tb - 1) / tb);
     fe_claim_kernel<<<gb, tb, 0, st>>>(S.d_vals[1], S.d_fft, R, C, cnt, S.d_claim);
     NRS_LAUNCHED();
-    fe_incr_kernel<<<gb, tb, 0, st>>>(S.d_vals[1], S.d_fft, R, C, cnt, S.d_claim, S.d_incr, n_walk);
-    NRS_LAUNCHED();
-    need = S.cub_bytes;
-    NRS_CUDA(cub::DeviceScan::InclusiveSum(S.d_cub, need, S.d_incr, S.d_vals[0], (int)n_walk, st));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    NRS_CUDA(cudaMemsetAsync(&cnt->j_star, 0xff, sizeof(int), st));      // -1
-    fe_jstar_kernel<<<gb, tb, 0, st>>>(S.d_incr, S.d_vals[0], n_walk, max_points, cnt);
-    NRS_LAUNCHED();
-    fe_jstar_fix_kernel<<<1, 32, 0, st>>>(cnt, S.d_keys[1], S.d_thresh);
+    fe_incr_kernel<<<gb, INCR_T, 0, st>>>(S.d_vals[1], S.d_fft, R, C, cnt, S.d_claim, S.d_incr, max_points, S.d_keys[1], S.d_thresh);
     NRS_LAUNCHED();
     S.have_thresh = true;
     const int sb = R;
-    fe_scan_rows_kernel<<<sb, 256, 0, st>>>(S.d_claim, S.d_h, R, C, min_range, cnt, S.d_rowcount, S.d_stage);
+    fe_scan_rows_kernel<<<sb, SR_WARPS * 32, 0, st>>>(S.d_claim, S.d_h, R, C, min_range, cnt, S.d_rowcount, S.d_stage);
     NRS_LAUNCHED();
     if (d_polar) return fe_gather_rows_device(ctx, S, d_polar);        // standalone detector call; else fe_tail_kernel does it
     return NRS_OK;

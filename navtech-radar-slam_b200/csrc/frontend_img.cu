@@ -290,12 +290,13 @@ static void frontend_free(void *p)
     FrontendState *S = static_cast<FrontendState *>(p);
     void *dev[] = {S->d_theta, S->d_sx, S->d_pattern, S->d_raw, S->d_fft, S->d_h, S->d_keys[0], S->d_keys[1],
                    S->d_vals[0], S->d_vals[1], S->d_claim, S->d_incr, S->d_partial, S->d_cart, S->d_rowbuf,
-                   S->d_blur, S->d_cub, S->d_az, S->d_azsort, S->d_azidx, S->d_cossin, S->d_times, S->d_counts,
+                   S->d_blur, S->d_cub, S->d_tables, S->d_counts,
                    S->d_pts32, S->d_rowcount, S->d_thresh, S->d_stage};
     for (void *d : dev) if (d) cudaFree(d);
     for (auto &g : S->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     S->graphs.clear();
     if (S->h_counts) cudaFreeHost(S->h_counts);
+    if (S->h_tables) cudaFreeHost(S->h_tables);
     if (S->st_img) { cudaStreamSynchronize(S->st_img); cudaStreamDestroy(S->st_img); }
     if (S->ev_fork) cudaEventDestroy(S->ev_fork);
     if (S->ev_join) cudaEventDestroy(S->ev_join);
@@ -343,12 +344,14 @@ static int frontend_state(nrs_ctx *ctx, const nrs_extract_params *p, int R, int 
     rc |= dmalloc(&S->d_cart, WW); rc |= dmalloc(&S->d_rowbuf, WW); rc |= dmalloc(&S->d_blur, WW);
     S->cub_bytes = fe_cub_bytes(N);
     rc |= dmalloc((unsigned char **)&S->d_cub, S->cub_bytes);
-    rc |= dmalloc(&S->d_az, FE_MAX_AZ); rc |= dmalloc(&S->d_azsort, FE_MAX_AZ); rc |= dmalloc(&S->d_azidx, FE_MAX_AZ);
-    rc |= dmalloc(&S->d_cossin, 2 * FE_MAX_AZ); rc |= dmalloc(&S->d_times, FE_MAX_AZ); rc |= dmalloc(&S->d_counts, 1);
+    rc |= dmalloc(&S->d_tables, 1); rc |= dmalloc(&S->d_counts, 1);
     rc |= dmalloc(&S->d_pts32, 2 * FE_KP_CAP); rc |= dmalloc(&S->d_rowcount, FE_MAX_AZ);
     rc |= dmalloc(&S->d_thresh, 1); rc |= dmalloc(&S->d_stage, N);
     if (rc) return rc;
     NRS_CUDA(cudaMallocHost((void **)&S->h_counts, sizeof(FrameCounts)));
+    NRS_CUDA(cudaMallocHost((void **)&S->h_tables, sizeof(AzTables)));
+    S->d_az = S->d_tables->az; S->d_azsort = S->d_tables->azs; S->d_azidx = S->d_tables->azi;      // address arithmetic only
+    S->d_cossin = S->d_tables->cossin; S->d_times = S->d_tables->times;
 
     // ---- static maps (radar_utils.cpp:257-291), computed with the host's libm like the reference ----
     std::vector<float> theta(WW);
@@ -536,45 +539,65 @@ namespace {
 
 // row headers (radar_utils.cpp:121-123) and the libm tables derived from them, uploaded with the raw rows
 struct HostTables {
-    double az[FE_MAX_AZ], cossin[2 * FE_MAX_AZ], azs[FE_MAX_AZ];
-    long long times[FE_MAX_AZ];
-    int azi[FE_MAX_AZ];
     int n_sorted = 0;
     long long tmin = 0, tmax = 0;
 };
 
+// cos / sin of the 5600 azimuths a Navtech encoder can report (radar_utils.cpp:117-123: enc * 2 pi / 5600), host
+// libm like the reference, evaluated once
+struct EncoderTable { double az[5600], c[5600], s[5600]; };
+const EncoderTable &encoder_table()
+{
+    static const EncoderTable *tab = [] {
+        EncoderTable *t = new EncoderTable();
+        for (int e = 0; e < 5600; ++e) {
+            t->az[e] = e * 2 * M_PI / double(5600);
+            t->c[e] = cos(t->az[e]);
+            t->s[e] = sin(t->az[e]);
+        }
+        return t;
+    }();
+    return *tab;
+}
+
 int extract_upload(nrs_ctx *ctx, FrontendState *S, const uint8_t *raw, int R, int row_pitch, HostTables &H)
 {
     cudaStream_t st = ctx->stream;
+    const EncoderTable &E = encoder_table();
+    AzTables &T = *S->h_tables;          // pinned; the previous frame's copy finished before its call returned
+    bool increasing = true;
     for (int i = 0; i < R; ++i) {
         const uint8_t *row = raw + (size_t)i * row_pitch;
         int64_t stamp; uint16_t enc;
         memcpy(&stamp, row, 8);
         memcpy(&enc, row + 8, 2);
-        H.times[i] = stamp;
-        H.az[i] = enc * 2 * M_PI / double(5600);
-        H.cossin[2 * i] = cos(H.az[i]);
-        H.cossin[2 * i + 1] = sin(H.az[i]);
+        T.times[i] = stamp;
+        if (enc < 5600) { T.az[i] = E.az[enc]; T.cossin[2 * i] = E.c[enc]; T.cossin[2 * i + 1] = E.s[enc]; }
+        else {                           // not an encoder value the sensor produces; same expression all the same
+            T.az[i] = enc * 2 * M_PI / double(5600);
+            T.cossin[2 * i] = cos(T.az[i]);
+            T.cossin[2 * i + 1] = sin(T.az[i]);
+        }
+        if (i && !(T.az[i] > T.az[i - 1])) increasing = false;
         if (i == 0 || stamp < H.tmin) H.tmin = stamp;
         if (i == 0 || stamp > H.tmax) H.tmax = stamp;
     }
     H.n_sorted = 0;
-    {
-        std::vector<int> order(R);
+    if (increasing) {                    // one sweep without a wrap: already sorted and distinct
+        for (int i = 0; i < R; ++i) { T.azs[i] = T.az[i]; T.azi[i] = i; }
+        H.n_sorted = R;
+    } else {
+        int order[FE_MAX_AZ];
         for (int i = 0; i < R; ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return H.az[a] < H.az[b]; });
+        std::stable_sort(order, order + R, [&](int a, int b) { return T.az[a] < T.az[b]; });
         for (int k = 0; k < R; ++k) {
             const int i = order[k];
-            if (H.n_sorted && H.azs[H.n_sorted - 1] == H.az[i]) continue;     // duplicates: keep the lowest index
-            H.azs[H.n_sorted] = H.az[i]; H.azi[H.n_sorted] = i; ++H.n_sorted;
+            if (H.n_sorted && T.azs[H.n_sorted - 1] == T.az[i]) continue;     // duplicates: keep the lowest index
+            T.azs[H.n_sorted] = T.az[i]; T.azi[H.n_sorted] = i; ++H.n_sorted;
         }
     }
     NRS_CUDA(cudaMemcpyAsync(S->d_raw, raw, (size_t)R * row_pitch, cudaMemcpyHostToDevice, st));
-    NRS_CUDA(cudaMemcpyAsync(S->d_az, H.az, R * sizeof(double), cudaMemcpyHostToDevice, st));
-    NRS_CUDA(cudaMemcpyAsync(S->d_azsort, H.azs, H.n_sorted * sizeof(double), cudaMemcpyHostToDevice, st));
-    NRS_CUDA(cudaMemcpyAsync(S->d_azidx, H.azi, H.n_sorted * sizeof(int), cudaMemcpyHostToDevice, st));
-    NRS_CUDA(cudaMemcpyAsync(S->d_cossin, H.cossin, 2 * R * sizeof(double), cudaMemcpyHostToDevice, st));
-    NRS_CUDA(cudaMemcpyAsync(S->d_times, H.times, R * sizeof(long long), cudaMemcpyHostToDevice, st));
+    NRS_CUDA(cudaMemcpyAsync(S->d_tables, S->h_tables, sizeof(AzTables), cudaMemcpyHostToDevice, st));
     return NRS_OK;
 }
 

@@ -209,52 +209,59 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restri
     //      set (ties: lowest index), shrink the set to its neighbourhood (oracle/solver_ref.c).  Every warp
     //      keeps its own copy of the set, so one CTA barrier per step suffices: warp maxima by REDUX on a
     //      packed (count, 1023 - index) key, exchanged through a double-buffered shared array ---------------
+    //      A vertex adjacent to every other vertex of the set ("universal") is what the rule takes next, lowest
+    //      index first, and taking it changes nothing but the counts (all drop by one): the universal vertices
+    //      are emitted in one go together with the best of the rest, so a step costs one barrier per SHRINK of
+    //      the set, not one per clique vertex ------------------------------------------------------------------
     __shared__ uint32_t sPw[32][WORDS];
-    __shared__ int s_key[2][32], s_min[2][32];
+    __shared__ int s_key[2][32];
+    __shared__ uint32_t s_uni[2][32];
     const int nw = (N + 31) >> 5;
     sPw[warp][lane] = full;
-    if (warp == 0) { s_key[0][lane] = -1; s_key[1][lane] = -1; s_min[0][lane] = 0x7fffffff; s_min[1][lane] = 0x7fffffff; }
+    if (warp == 0) { s_key[0][lane] = -1; s_key[1][lane] = -1; s_uni[0][lane] = 0u; s_uni[1][lane] = 0u; }
     __syncthreads();
-    int best_n = 0;
+    int best_n = 0, np = N;
+    int greedy_steps = 0;
     for (int buf = 0;; buf ^= 1) {
-        int key = -1, cmin = 0x7fffffff;
+        int key = -1;
+        bool uni = false;
         if (tid < N && ((sPw[warp][warp] >> lane) & 1u)) {
             int c = 0;
             for (int w = 0; w < nw; ++w) c += __popc(sadj[tid * SROW + w] & sPw[warp][w]);
-            key = (c << 10) | (1023 - tid);
-            cmin = c;
+            uni = (c == np - 1);
+            if (!uni) key = (c << 10) | (1023 - tid);
         }
         key = __reduce_max_sync(0xffffffffu, key);
-        cmin = __reduce_min_sync(0xffffffffu, cmin);
-        if (lane == 0) { s_key[buf][warp] = key; s_min[buf][warp] = cmin; }
+        const uint32_t ub = __ballot_sync(0xffffffffu, uni);            // warp w owns word w of the vertex set
+        if (lane == 0) { s_key[buf][warp] = key; s_uni[buf][warp] = ub; }
         __syncthreads();
+        ++greedy_steps;
         const int k2 = __reduce_max_sync(0xffffffffu, s_key[buf][lane]);
-        if (k2 < 0) break;
-        const int np = __reduce_add_sync(0xffffffffu, __popc(sPw[warp][lane]));
-        const int m2 = __reduce_min_sync(0xffffffffu, s_min[buf][lane]);
-        if (m2 == np - 1) {
-            // the set is a clique: the remaining steps would take its vertices one by one in ascending index
-            // (equal counts, lowest index first) -- emit them all at once
-            if (warp == 0) {
-                const uint32_t pw = sPw[0][lane];
-                int pre = __popc(pw);
+        const uint32_t uw = s_uni[buf][lane];
+        const int nu = __reduce_add_sync(0xffffffffu, __popc(uw));
+        if (nu) {
+            if (warp == 0) {                                            // ascending index, like one-by-one picks
+                int pre = __popc(uw);
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const int up = __shfl_up_sync(0xffffffffu, pre, o);
                     if (lane >= o) pre += up;
                 }
-                int pos = best_n + pre - __popc(pw);
-                for (uint32_t x = pw; x; x &= x - 1) best[pos++] = lane * 32 + __ffs(x) - 1;
+                int pos = best_n + pre - __popc(uw);
+                for (uint32_t x = uw; x; x &= x - 1) best[pos++] = lane * 32 + __ffs(x) - 1;
             }
-            best_n += np;
-            break;
+            best_n += nu;
         }
+        if (k2 < 0) break;                                              // nothing but universal vertices was left
         const int v = 1023 - (k2 & 1023);
         if (tid == 0) best[best_n] = v;
         ++best_n;
-        sPw[warp][lane] &= sadj[v * SROW + lane];
+        const uint32_t pw = sPw[warp][lane] & ~uw & sadj[v * SROW + lane];
+        sPw[warp][lane] = pw;
+        np = __reduce_add_sync(0xffffffffu, __popc(pw));
         __syncwarp();
     }
+    if (tid == 0) info->t_ns[10] = (unsigned long long)greedy_steps;
     STAMP(2);
     // ---- peel to the best_n-core (Jacobi sweeps; the fixpoint does not depend on the order) ---------
     if (warp == 0) sP[lane] = full;
