@@ -131,6 +131,13 @@ int nrs_sc_knn(nrs_sc_db *db, const float *ringkey20_host, int first, int last, 
  * device; cand_out (nullable, k ids) reports the candidates. */
 int nrs_sc_detect_knn(nrs_sc_db *db, const double *query_host, int first, int last, int k,
                       int32_t *cand_out, nrs_sc_result *result_host);
+/* The same for Q queries in one call (Q descriptors in, Q results and, nullable, Q x k candidate
+ * ids out): the k-NN kernel takes the query as its second grid dimension, the candidate search
+ * runs over every query's own k ids -- two launches for the whole batch.  Results equal Q calls
+ * of nrs_sc_detect_knn over the same [first, last) (offline / between-session use; the online
+ * node asks one query per keyframe). */
+int nrs_sc_detect_knn_batch(nrs_sc_db *db, const double *queries_host, int Q, int first, int last,
+                            int k, int32_t *cand_out, nrs_sc_result *results_host);
 /* bytes per keyframe that an exhaustive query streams from HBM: the f32 filter record of the
  * general-valued search, and the 256-byte bit-mask record of the {0,c} search (below) */
 int nrs_sc_filter_record_bytes(void);
@@ -309,7 +316,8 @@ typedef struct nrs_frame_info {
     int32_t K_voxel;        /* after voxelisation */
     int32_t K;              /* after the BEV border filter = feat_in_cart_.cols() = t_.size() */
     int32_t K_desc;         /* kp_.size() = desc_.rows after cv::ORB::compute's own border filter (<= K) */
-    int32_t pad_;
+    int32_t n_sorted;       /* candidates the marking loop had sorted before it: the top-candidate subset's size,
+                             * or n_candidates when the full-frame sort ran (diagnostic; never changes a result) */
     float   maxg, mean, mean_h, cart_max;
     int64_t t_criteria;
 } nrs_frame_info;

@@ -67,7 +67,7 @@ class FrameInfo(C.Structure):
     """nrs_frame_info (include/nrs_b200.h)."""
     _fields_ = [("n_candidates", C.c_int32), ("j_consumed", C.c_int32), ("l_regions", C.c_int32),
                 ("K_polar", C.c_int32), ("K_voxel", C.c_int32), ("K", C.c_int32), ("K_desc", C.c_int32),
-                ("pad_", C.c_int32), ("maxg", C.c_float),
+                ("n_sorted", C.c_int32), ("maxg", C.c_float),
                 ("mean", C.c_float), ("mean_h", C.c_float), ("cart_max", C.c_float), ("t_criteria", C.c_int64)]
 
 
@@ -131,6 +131,7 @@ def _declare(L):
     L.nrs_orora_last_timings.argtypes = [vp]
     L.nrs_sc_knn.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.nrs_sc_detect_knn.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    L.nrs_sc_detect_knn_batch.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
     L.nrs_sc_xchg_create.argtypes = [vp, i32, i32, vp]
     L.nrs_sc_xchg_open.argtypes = [vp, vp]
     L.nrs_sc_query_dev_sharded.argtypes = [vp, vp, i32, i32, vp]

@@ -32,6 +32,51 @@ struct FrameCounts {
     unsigned int ticket[3];   // last-block tickets of fe_stats_kernel / fe_h_kernel / fe_incr_kernel (zeroed with the counts)
 };
 
+// ---- bit rows: the per-azimuth run scans (cen2019's marked regions, cen2018's peaks) first turn the azimuth's
+// columns into one bit per column in shared memory (coalesced, independent loads) and then find run starts, run
+// ends and neighbour tests with word operations instead of walking global memory column by column ----
+constexpr int FE_ROW_WORDS = 256;        // => range_bins <= 8192
+// first clear bit at or after position p (32 * nwords when there is none)
+__device__ __forceinline__ int fe_first_zero(const unsigned int *mw, int nwords, int p)
+{
+    int w = p >> 5;
+    unsigned int z = ~mw[w] & (0xffffffffu << (p & 31));
+    while (!z) {
+        if (++w >= nwords) return nwords * 32;
+        z = ~mw[w];
+    }
+    return w * 32 + __ffs(z) - 1;
+}
+// any set bit in [lo, hi]
+__device__ __forceinline__ bool fe_any_set(const unsigned int *aw, int lo, int hi)
+{
+    const int w0 = lo >> 5, w1 = hi >> 5;
+    const unsigned int first = 0xffffffffu << (lo & 31), last = 0xffffffffu >> (31 - (hi & 31));
+    if (w0 == w1) return (aw[w0] & first & last) != 0u;
+    if (aw[w0] & first) return true;
+    for (int w = w0 + 1; w < w1; ++w)
+        if (aw[w]) return true;
+    return (aw[w1] & last) != 0u;
+}
+// exclusive prefix of one count per thread over a 256-thread block (total in `total`); wsum: 8 ints of shared memory
+__device__ __forceinline__ int fe_block256_exscan(int c, int *wsum, int &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += up;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int before = 0;
+    total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const int v = wsum[w]; if (w < warp) before += v; total += v; }
+    return before + inc - c;
+}
+
 // per-frame azimuth tables, device layout == pinned host layout: ONE host-to-device copy per frame
 struct AzTables {
     double az[FE_MAX_AZ];                // azimuths (R)

@@ -248,48 +248,40 @@ fe18_flags_kernel(const float *__restrict__ q, const float *__restrict__ p, cons
 
 // :102-112 one CTA per azimuth: a run starts at a flagged column whose left neighbour (from min_range on) is
 // not flagged; it emits column start + len / 2.  Emission stays ordered through per-warp ballots.
-constexpr int RN_WARPS = 8, RN_SPAN = 512;       // columns per warp and round: at most RN_SPAN / 2 runs start in them
-
-__global__ void __launch_bounds__(RN_WARPS * 32)
+__global__ void __launch_bounds__(256)
 fe18_runs_kernel(const unsigned char *__restrict__ flags, int R, int C, int min_range, int *__restrict__ rowcount,
                  int *__restrict__ stage)
 {
-    // every warp walks its own span of columns and keeps a private list; two barriers per round of 8 x 512
-    // columns string the lists into this azimuth's staging row (fe_tail_kernel strings the rows)
-    __shared__ int wl[RN_WARPS][RN_SPAN / 2];
-    __shared__ int wn[RN_WARPS];
-    const int i = blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // pass 1: the azimuth's flags (from min_range on) as one bit per column in shared memory; pass 2: thread t owns
+    // word t, run starts = set bits with a clear left neighbour, run end = before the next clear bit (or the last
+    // column); the staging row takes start + len / 2 in column order (fe_tail_kernel strings the rows)
+    __shared__ unsigned int mw[FE_ROW_WORDS];
+    __shared__ int wsum[8];
+    const int i = blockIdx.x, t = threadIdx.x, lane = t & 31;
     const unsigned char *fr = flags + (size_t)i * C;
-    int *srow = stage + (size_t)i * C;
-    int running = 0;
-    for (int base0 = min_range; base0 < C; base0 += RN_WARPS * RN_SPAN) {
-        const int w0 = base0 + warp * RN_SPAN, w1 = min(w0 + RN_SPAN, C);
-        int mine = 0;
-        for (int j0 = w0; j0 < w1; j0 += 32) {
-            const int j = j0 + lane;
-            bool emit = false;
-            int centre = 0;
-            if (j < w1 && fr[j] && (j == min_range || !fr[j - 1])) {
-                int end = j;
-                while (end + 1 < C && fr[end + 1]) ++end;
-                centre = j + (end - j + 1) / 2;                 // peak_points[peak_points.size() / 2]
-                emit = true;
-            }
-            const unsigned int mask = __ballot_sync(0xffffffffu, emit);
-            if (emit) wl[warp][mine + __popc(mask & ((1u << lane) - 1u))] = centre;
-            mine += __popc(mask);
-        }
-        if (lane == 0) wn[warp] = mine;
-        __syncthreads();
-        int before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < RN_WARPS; ++w) { const int c = wn[w]; if (w < warp) before += c; total += c; }
-        for (int e = lane; e < mine; e += 32) srow[running + before + e] = wl[warp][e];
-        running += total;
-        __syncthreads();                                        // wn / wl are rewritten by the next round
+    const int nwords = (C + 31) >> 5;
+#pragma unroll 4
+    for (int j0 = (t >> 5) * 32; j0 < nwords * 32; j0 += 256) {
+        const int j = j0 + lane;
+        const bool m = (j < C) && (j >= min_range) && fr[j];
+        const unsigned int mb = __ballot_sync(0xffffffffu, m);
+        if (lane == 0) mw[j0 >> 5] = mb;
     }
-    if (threadIdx.x == 0) rowcount[i] = running;
+    __syncthreads();
+    unsigned int starts = 0u;
+    if (t < nwords) {
+        const unsigned int m = mw[t];
+        starts = m & ~((m << 1) | (t ? mw[t - 1] >> 31 : 0u));
+    }
+    int total;
+    int pos = fe_block256_exscan(__popc(starts), wsum, total);
+    int *srow = stage + (size_t)i * C;
+    for (unsigned int x = starts; x; x &= x - 1) {
+        const int j = 32 * t + __ffs(x) - 1;
+        const int end = min(fe_first_zero(mw, nwords, j), C) - 1;
+        srow[pos++] = j + (end - j + 1) / 2;                        // peak_points[peak_points.size() / 2]
+    }
+    if (t == 0) rowcount[i] = total;
 }
 
 }  // namespace
@@ -356,7 +348,7 @@ int fe_cen2018_device(nrs_ctx *ctx, FrontendState &S, int R, int C, float zq, in
     dim3 gp((C + 255) / 256, R);
     fe18_flags_kernel<<<gp, 256, 0, st>>>(d_q, d_p, d_sigma, R, C, zq, min_range, d_flags, d_y);
     NRS_LAUNCHED();
-    fe18_runs_kernel<<<R, RN_WARPS * 32, 0, st>>>(d_flags, R, C, min_range, S.d_rowcount, S.d_stage);
+    fe18_runs_kernel<<<R, 256, 0, st>>>(d_flags, R, C, min_range, S.d_rowcount, S.d_stage);
     NRS_LAUNCHED();
     if (d_polar) return fe_gather_rows_device(ctx, S, d_polar);        // standalone detector call; else fe_tail_kernel does it
     return NRS_OK;

@@ -434,73 +434,64 @@ __global__ void fe_set_sorted_full_kernel(FrameCounts *__restrict__ cnt)
 // ------------------------------------------------------------------------------------------------
 // K3: per-azimuth scan (features.cpp:251-278), one warp per azimuth
 // ------------------------------------------------------------------------------------------------
-constexpr int SR_WARPS = 8, SR_SPAN = 512;       // columns per warp and round: at most SR_SPAN / 2 runs start in them
-
-__global__ void __launch_bounds__(SR_WARPS * 32)
+__global__ void __launch_bounds__(256)
 fe_scan_rows_kernel(const unsigned int *__restrict__ claim, const float *__restrict__ h, int R, int C,
                     int min_range, const FrameCounts *__restrict__ cnt, int *__restrict__ rowcount,
                     int *__restrict__ stage)
 {
-    // one block per azimuth; every warp walks its own contiguous span of columns 32 at a time and appends the
-    // range bins it finds to a private list (ordered by column through ballots), two barriers per round of
-    // 8 x 512 columns string the lists together into the azimuth's staging row (at most one bin per closed run,
-    // so fewer than C); fe_tail_kernel strings the rows together
-    __shared__ int wl[SR_WARPS][SR_SPAN / 2];
-    __shared__ int wn[SR_WARPS];
-    const int i = blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // one block per azimuth.  Pass 1 (streaming, no dependent loads): one bit per column for "marked"
+    // (claim <= j_star, from min_range on) and one for "a vertical neighbour is marked" (checkAdjacentMarked
+    // :172-184, rows wrap).  Pass 2: thread t owns word t of the row: a run starts at a marked bit whose left
+    // neighbour is clear, ends before the next clear bit (a run that reaches the last column is never closed and
+    // never emitted), counts if any neighbour bit is set inside it; the survivors take getMaxInRegion's bin
+    // (:186-194, int-typed running max) and go to the azimuth's staging row in column order.
+    __shared__ unsigned int mw[FE_ROW_WORDS], aw[FE_ROW_WORDS];
+    __shared__ int wsum[8];
+    const int i = blockIdx.x, t = threadIdx.x;
+    const int lane = t & 31;
     const unsigned int J = (unsigned int)cnt->j_star;
     const bool none = cnt->j_star < 0;
     const unsigned int *crow = claim + (size_t)i * C;
     const int below = (i == 0) ? R - 1 : i - 1, above = (i + 1 >= R) ? 0 : i + 1;     // :173-178
     const unsigned int *cb = claim + (size_t)below * C, *ca = claim + (size_t)above * C;
+    const int nwords = (C + 31) >> 5;
+#pragma unroll 4
+    for (int j0 = (t >> 5) * 32; j0 < nwords * 32; j0 += 256) {
+        const int j = j0 + lane;
+        bool m = false, a = false;
+        if (j < C && !none) {
+            m = (j >= min_range) && (crow[j] <= J);
+            a = (cb[j] <= J) || (ca[j] <= J);
+        }
+        const unsigned int mb = __ballot_sync(0xffffffffu, m), ab = __ballot_sync(0xffffffffu, a);
+        if (lane == 0) { mw[j0 >> 5] = mb; aw[j0 >> 5] = ab; }
+    }
+    __syncthreads();
+    unsigned int emit = 0u;
+    if (t < nwords) {
+        const unsigned int m = mw[t];
+        const unsigned int starts = m & ~((m << 1) | (t ? mw[t - 1] >> 31 : 0u));
+        for (unsigned int x = starts; x; x &= x - 1) {
+            const int b = __ffs(x) - 1, j = 32 * t + b;
+            const int p = fe_first_zero(mw, nwords, j);                // the unmarked pixel that closes the run
+            if (p < C && fe_any_set(aw, j, p - 1)) emit |= 1u << b;
+        }
+    }
+    int total;
+    int pos = fe_block256_exscan(__popc(emit), wsum, total);
     const float *hrow = h + (size_t)i * C;
     int *srow = stage + (size_t)i * C;
-    int running = 0;
-    for (int base0 = min_range; base0 < C; base0 += SR_WARPS * SR_SPAN) {
-        const int w0 = base0 + warp * SR_SPAN, w1 = min(w0 + SR_SPAN, C);
-        int mine = 0;
-        for (int j0 = w0; j0 < w1 && !none; j0 += 32) {
-            const int j = j0 + lane;
-            bool emit = false;
-            int max_r = 0;
-            if (j < w1) {
-                const bool m = crow[j] <= J;
-                const bool prev = (j > min_range) && (crow[j - 1] <= J);
-                if (m && !prev) {                      // a run starts here
-                    int end = j;
-                    while (end + 1 < C && crow[end + 1] <= J) ++end;
-                    if (end + 1 < C) {                 // closed by an unmarked pixel; else never emitted
-                        bool adj = false;              // checkAdjacentMarked :172-184
-                        for (int r = j; r <= end; ++r)
-                            if (cb[r] <= J || ca[r] <= J) { adj = true; break; }
-                        if (adj) {
-                            // getMaxInRegion :186-194 with its int-typed running max
-                            int mx = -1000;
-                            max_r = j;
-                            for (int r = j; r <= end; ++r) {
-                                const float hv = hrow[r];
-                                if (hv > (float)mx) { mx = (int)hv; max_r = r; }
-                            }
-                            emit = true;
-                        }
-                    }
-                }
-            }
-            const unsigned int mask = __ballot_sync(0xffffffffu, emit);
-            if (emit) wl[warp][mine + __popc(mask & ((1u << lane) - 1u))] = max_r;
-            mine += __popc(mask);
+    for (unsigned int x = emit; x; x &= x - 1) {
+        const int j = 32 * t + __ffs(x) - 1;
+        const int end = fe_first_zero(mw, nwords, j) - 1;
+        int mx = -1000, max_r = j;
+        for (int r = j; r <= end; ++r) {
+            const float hv = hrow[r];
+            if (hv > (float)mx) { mx = (int)hv; max_r = r; }
         }
-        if (lane == 0) wn[warp] = mine;
-        __syncthreads();
-        int before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < SR_WARPS; ++w) { const int c = wn[w]; if (w < warp) before += c; total += c; }
-        for (int e = lane; e < mine; e += 32) srow[running + before + e] = wl[warp][e];
-        running += total;
-        __syncthreads();                               // wn / wl are rewritten by the next round
+        srow[pos++] = max_r;
     }
-    if (threadIdx.x == 0) rowcount[i] = running;
+    if (t == 0) rowcount[i] = total;
 }
 
 // The standalone detector entry points (nrs_cen2019 / nrs_cen2018) have no tail kernel behind them: the same
@@ -554,7 +545,7 @@ fe_tail_kernel(const int *__restrict__ rowcount, const int *__restrict__ stage, 
                double *__restrict__ feat, float *__restrict__ kp, long long *__restrict__ t_out,
                float *__restrict__ kp_orb)
 {
-    typedef cub::BlockScan<int, TAIL_T> BS;
+    typedef cub::BlockScan<int, TAIL_T, cub::BLOCK_SCAN_WARP_SCANS> BS;
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ typename BS::TempStorage tmp;
     __shared__ float smin[2][32], smax[2][32];
@@ -584,27 +575,27 @@ fe_tail_kernel(const int *__restrict__ rowcount, const int *__restrict__ stage, 
 
     // ---- polar_to_cartesian_points; PCL's float copy and its bounding box ----
     float mnx = FLT_MAX, mny = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX;
-    for (int a = warp; a < R; a += TAIL_T / 32) {
-        const int c = rowcount[a], off = rowoff[a];
-        const double ca = cossin[2 * a], sa = cossin[2 * a + 1];
-        const long long ta = times[a];
-        for (int e = lane; e < c; e += 32) {
-            const int k = off + e;
-            if (k >= cap) break;
-            const int rb = stage[(size_t)a * C + e];
-            polar[2 * k] = a;
-            polar[2 * k + 1] = rb;
-            const double r = (double)rb * (double)radar_resolution + (double)(radar_resolution / 2);
-            const double cx = r * ca, cy = r * sa;
-            cart_pre[2 * k] = cx;
-            cart_pre[2 * k + 1] = cy;
-            t_pre[k] = ta;
-            if (use_vox) {
-                const float x = (float)cx, y = (float)cy;            // eigen2pcl: double -> float
-                pts32[2 * k] = x; pts32[2 * k + 1] = y;
-                mnx = fminf(mnx, x); mxx = fmaxf(mxx, x);
-                mny = fminf(mny, y); mxy = fmaxf(mxy, y);
-            }
+    for (int k = t; k < K0; k += TAIL_T) {
+        // the keypoint's azimuth: the last row whose offset is <= k (empty rows share their successor's offset)
+        int lo = 0, hi = R;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (rowoff[mid] <= k) lo = mid + 1; else hi = mid;
+        }
+        const int a = lo - 1;
+        const int rb = stage[(size_t)a * C + (k - rowoff[a])];
+        polar[2 * k] = a;
+        polar[2 * k + 1] = rb;
+        const double r = (double)rb * (double)radar_resolution + (double)(radar_resolution / 2);
+        const double cx = r * cossin[2 * a], cy = r * cossin[2 * a + 1];
+        cart_pre[2 * k] = cx;
+        cart_pre[2 * k + 1] = cy;
+        t_pre[k] = times[a];
+        if (use_vox) {
+            const float x = (float)cx, y = (float)cy;                // eigen2pcl: double -> float
+            pts32[2 * k] = x; pts32[2 * k + 1] = y;
+            mnx = fminf(mnx, x); mxx = fmaxf(mxx, x);
+            mny = fminf(mny, y); mxy = fmaxf(mxy, y);
         }
     }
     __syncthreads();                                                 // pts32 is read by other threads below
@@ -727,60 +718,48 @@ fe_tail_kernel(const int *__restrict__ rowcount, const int *__restrict__ stage, 
     }
 
     // ---- convert_to_bev: ordered compaction, keypoints (u, v), stamps with the reference's pre-voxelisation
-    // indexing quirk (radar_loader.hpp:123-124) ----
+    // indexing quirk (radar_loader.hpp:123-124).  In the same sweep the keypoints cv::ORB::compute keeps
+    // (radar_loader.hpp:126): it first runs KeyPointsFilter::runByImageBorder(kps, size, edgeThreshold = patch):
+    // Rect(Point(b,b), Point(W-b,W-b)).contains(Point(cvRound(u), cvRound(v))).  Keypoints with
+    // cvRound(u|v) == W - patch are dropped from kp_/desc_ while feat_in_cart_ keeps its columns -- the
+    // reference's index misalignment is reproduced, not repaired.  Both running counts ride in one scan
+    // (low / high half of an int; at most 16384 each) ----
     float cmr = (width / 2) * cart_resolution;
     if (width % 2 == 0) cmr = (float)((width / 2 - 0.5) * cart_resolution);
     if (t == 0) carry = 0;
     __syncthreads();
     for (int base = 0; base < n; base += TAIL_T) {
         const int i = base + t;
-        bool keep = false;
-        double x = 0, y = 0, u = 0, v = 0;
+        bool keep = false, keep_orb = false;
+        double x = 0, y = 0;
+        float uf = 0.f, vf = 0.f;
         if (i < n) {
             x = pts_xy[2 * i]; y = pts_xy[2 * i + 1];
-            u = ((double)cmr + y) / (double)cart_resolution;
-            v = ((double)cmr - x) / (double)cart_resolution;
+            const double u = ((double)cmr + y) / (double)cart_resolution;
+            const double v = ((double)cmr - x) / (double)cart_resolution;
             keep = (0 < u - patch) && (u + patch < width) && (0 < v - patch) && (v + patch < width);
+            uf = (float)u; vf = (float)v;
+            const int ru = __float2int_rn(uf), rv = __float2int_rn(vf);
+            keep_orb = keep && ru >= patch && ru < width - patch && rv >= patch && rv < width - patch;
         }
         int ex, total;
-        BS(tmp).ExclusiveSum(keep ? 1 : 0, ex, total);
+        BS(tmp).ExclusiveSum((keep ? 1 : 0) | (keep_orb ? 0x10000 : 0), ex, total);
         const int c0 = carry;
         if (keep) {
-            const int j = c0 + ex;
+            const int j = (c0 + ex) & 0xffff;
             feat[2 * j] = x; feat[2 * j + 1] = y;
-            kp[2 * j] = (float)u; kp[2 * j + 1] = (float)v;
+            kp[2 * j] = uf; kp[2 * j + 1] = vf;
             t_out[j] = t_pre[i];
         }
-        __syncthreads();
-        if (t == 0) carry = c0 + total;
-        __syncthreads();
-    }
-    const int K = carry;
-    __syncthreads();
-    if (t == 0) { cnt->K = K; carry = 0; }
-    __syncthreads();
-    // cv::ORB::compute (radar_loader.hpp:126) first runs KeyPointsFilter::runByImageBorder(kps, size,
-    // edgeThreshold = patch): Rect(Point(b,b), Point(W-b,W-b)).contains(Point(cvRound(u), cvRound(v))).
-    // Keypoints with cvRound(u|v) == W - patch are dropped from kp_/desc_ while feat_in_cart_ keeps its
-    // columns -- the reference's index misalignment is reproduced, not repaired.
-    for (int base = 0; base < K; base += TAIL_T) {
-        const int j = base + t;
-        bool keep = false;
-        float u = 0.f, v = 0.f;
-        if (j < K) {
-            u = kp[2 * j]; v = kp[2 * j + 1];
-            const int ru = __float2int_rn(u), rv = __float2int_rn(v);
-            keep = ru >= patch && ru < width - patch && rv >= patch && rv < width - patch;
+        if (keep_orb) {
+            const int j = (c0 + ex) >> 16;
+            kp_orb[2 * j] = uf; kp_orb[2 * j + 1] = vf;
         }
-        int ex, total;
-        BS(tmp).ExclusiveSum(keep ? 1 : 0, ex, total);
-        const int c0 = carry;
-        if (keep) { kp_orb[2 * (c0 + ex)] = u; kp_orb[2 * (c0 + ex) + 1] = v; }
         __syncthreads();
         if (t == 0) carry = c0 + total;
         __syncthreads();
     }
-    if (t == 0) cnt->Kd = carry;
+    if (t == 0) { cnt->K = carry & 0xffff; cnt->Kd = carry >> 16; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -848,7 +827,7 @@ int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_poin
     NRS_LAUNCHED();
     S.have_thresh = true;
     const int sb = R;
-    fe_scan_rows_kernel<<<sb, SR_WARPS * 32, 0, st>>>(S.d_claim, S.d_h, R, C, min_range, cnt, S.d_rowcount, S.d_stage);
+    fe_scan_rows_kernel<<<sb, 256, 0, st>>>(S.d_claim, S.d_h, R, C, min_range, cnt, S.d_rowcount, S.d_stage);
     NRS_LAUNCHED();
     if (d_polar) return fe_gather_rows_device(ctx, S, d_polar);        // standalone detector call; else fe_tail_kernel does it
     return NRS_OK;

@@ -468,7 +468,7 @@ int nrs_extract_default_params(const char *dataset, nrs_extract_params *p)
 int nrs_cen2018(nrs_ctx *ctx, const float *fft, int R, int C, float zq, int sigma_gauss, int min_range,
                 double *targets, int Kcap, int *K, float *y_out)
 {
-    NRS_CHECK_ARG(ctx && fft && K && R >= 2 && R <= FE_MAX_AZ && C >= 3 && min_range >= 0 &&
+    NRS_CHECK_ARG(ctx && fft && K && R >= 2 && R <= FE_MAX_AZ && C >= 3 && C <= 32 * FE_ROW_WORDS && min_range >= 0 &&
                   (targets || Kcap == 0), "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     NRS_CUDA(cudaSetDevice(ctx->device));
@@ -502,7 +502,7 @@ int nrs_cen2018(nrs_ctx *ctx, const float *fft, int R, int C, float zq, int sigm
 int nrs_cen2019(nrs_ctx *ctx, const float *fft, int R, int C, int max_points, int min_range,
                 double *targets, int Kcap, int *K)
 {
-    NRS_CHECK_ARG(ctx && fft && K && R >= 2 && R <= FE_MAX_AZ && C >= 3 && max_points > 0 && min_range >= 0 &&
+    NRS_CHECK_ARG(ctx && fft && K && R >= 2 && R <= FE_MAX_AZ && C >= 3 && C <= 32 * FE_ROW_WORDS && max_points > 0 && min_range >= 0 &&
                   (targets || Kcap == 0), "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     NRS_CUDA(cudaSetDevice(ctx->device));
@@ -696,6 +696,7 @@ int check_extract_args(nrs_ctx *ctx, const uint8_t *raw, int R, int row_pitch, c
 {
     NRS_CHECK_ARG(ctx && raw && p, "bad argument");
     NRS_CHECK_ARG(R >= 2 && R <= FE_MAX_AZ, "number of azimuths out of range");
+    NRS_CHECK_ARG(p->range_bins >= 3 && p->range_bins <= 32 * FE_ROW_WORDS, "range_bins out of range (3..8192)");
     NRS_CHECK_ARG(row_pitch >= p->range_bins + 11, "row pitch smaller than 11 + range_bins");
     NRS_CHECK_ARG(p->cart_pixel_width >= 64 && p->patch_size >= 3 && p->patch_size <= 63 && p->max_points <= FE_KP_CAP, "bad parameters");
     NRS_CHECK_ARG(p->keypoint_extraction == 0 || p->keypoint_extraction == 1, "keypoint_extraction must be 0 (cen2019) or 1 (cen2018)");
@@ -850,6 +851,7 @@ int nrs_frame_info_get(const nrs_frame *f, nrs_frame_info *info)
     info->K_voxel = f->counts.Kv;
     info->K = f->counts.K;
     info->K_desc = f->counts.Kd;
+    info->n_sorted = f->counts.n_sorted;
     info->maxg = f->counts.maxg; info->mean = f->counts.mean; info->mean_h = f->counts.mean_h;
     info->cart_max = f->counts.cart_max;
     info->t_criteria = f->t_criteria;

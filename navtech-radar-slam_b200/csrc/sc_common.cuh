@@ -280,6 +280,8 @@ struct nrs_sc_db {
     nrs_sc::SearchState *d_bstate = nullptr;      // XCHG_QCAP entries
     unsigned int  *d_gticket = nullptr;
     nrs::DevBuf    bin_surv, bin_block;
+    nrs::DevBuf    knn_rec, knn_part;   // batched k-NN: one 72-float record per query, per-block partial lists
+    nrs::PinBuf    knn_host;            // ... and the records' pinned landing zone
     double        *d_queries = nullptr;  // batch staging: XCHG_QCAP x 1200 doubles (device) ...
     double        *h_queries = nullptr;  // ... and pinned host
     nrs_sc_result *d_results = nullptr;  // XCHG_QCAP records
@@ -305,7 +307,7 @@ namespace nrs_sc {
 // enqueue the bit-mask search of Q queries (device, Q x 1200 doubles) over keyframes [first, first + n_items)
 // (or the candidate list) on the database's stream; every keyframe in range must be {0,c} (db->n_general == 0)
 int bin_launch(nrs_sc_db *db, const double *d_queries, int Q, const int32_t *d_cand, int first, int n_items,
-               int idx_scale, int idx_offset, nrs_sc_result *d_results, XchgView xv);
+               int idx_scale, int idx_offset, nrs_sc_result *d_results, XchgView xv, int cand_stride = 0);
 // Q searches enqueued on the context stream (db->mu and ctx->mu held by the caller): reported index =
 // local slot * idx_scale + idx_offset; sharded = exchange the per-query records over peer memory in-kernel
 int batch_dev_locked(nrs_sc_db *db, const double *queries_dev, int Q, int first, int last, int idx_scale,

@@ -768,14 +768,24 @@ __device__ void knn_merge(const float *__restrict__ part_d, const int32_t *__res
     }
 }
 
+// Batched: blockIdx.y is the query; its descriptor, partial lists and 72-float record ([0,16) distances, [16,32)
+// ids, [32,48) the k candidate ids, [48,68) its ring key, [68] the ticket) sit at multiples of the strides.
+constexpr int KNN_REC = 72;
 __global__ void __launch_bounds__(KNN_THREADS)
 sc_knn_kernel(const float *__restrict__ rkeys, const float *__restrict__ query_key, const double *__restrict__ query_desc,
-              int first, int last, int k, float *__restrict__ part_d, int32_t *__restrict__ part_i,
-              unsigned int *__restrict__ ticket, float *__restrict__ out_d, int32_t *__restrict__ out_i,
-              int32_t *__restrict__ cand, float *__restrict__ key_out)
+              int first, int last, int k, int per_block, float *__restrict__ part_d, int32_t *__restrict__ part_i,
+              size_t part_stride, float *__restrict__ rec)
 {
     __shared__ float skey[R];
     __shared__ int is_last;
+    const int y = blockIdx.y;
+    if (query_desc) query_desc += (size_t)y * DESC;
+    part_d += (size_t)y * part_stride;
+    part_i += (size_t)y * part_stride;
+    rec += (size_t)y * KNN_REC;
+    float *out_d = rec, *key_out = rec + 48;
+    int32_t *out_i = reinterpret_cast<int32_t *>(rec + 16), *cand = reinterpret_cast<int32_t *>(rec + 32);
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(rec + 68);
     if (query_desc) {
         if (threadIdx.x < R) {
             const int r = threadIdx.x;
@@ -799,8 +809,8 @@ sc_knn_kernel(const float *__restrict__ rkeys, const float *__restrict__ query_k
     int li[KNN_MAX];
 #pragma unroll
     for (int j = 0; j < KNN_MAX; ++j) { ld[j] = INFINITY; li[j] = -1; }
-    const int lo = first + blockIdx.x * KNN_PER_BLOCK;
-    const int hi = min(last, lo + KNN_PER_BLOCK);
+    const int lo = first + blockIdx.x * per_block;
+    const int hi = min(last, lo + per_block);
     for (int g = lo + threadIdx.x; g < hi; g += KNN_THREADS)
         knn_insert(ld, li, k, ringkey_l2(q, rkeys + (size_t)g * R), g);
     knn_block_select(ld, li, k, part_d + (size_t)blockIdx.x * k, part_i + (size_t)blockIdx.x * k);
@@ -1132,6 +1142,7 @@ int nrs_sc_db_destroy(nrs_sc_db *db)
     cudaFree(db->d_brec); cudaFree(db->d_ngen); cudaFree(db->d_bstate); cudaFree(db->d_gticket);
     cudaFree(db->d_queries); cudaFree(db->d_results);
     db->bin_surv.release(); db->bin_block.release();
+    db->knn_rec.release(); db->knn_part.release(); db->knn_host.release();
     if (db->h_result) cudaFreeHost(db->h_result);
     if (db->h_query) cudaFreeHost(db->h_query);
     if (db->h_ngen) cudaFreeHost(db->h_ngen);
@@ -1463,11 +1474,8 @@ static int launch_knn(nrs_sc_db *db, const float *d_key, const double *d_desc, i
     nrs_ctx *ctx = db->ctx;
     const int n = std::max(0, last - first);
     const int blocks = std::max(1, (n + KNN_PER_BLOCK - 1) / KNN_PER_BLOCK);
-    float *out_d = db->d_knn_out;
-    int32_t *out_i = reinterpret_cast<int32_t *>(db->d_knn_out + 16), *cand = reinterpret_cast<int32_t *>(db->d_knn_out + 32);
-    sc_knn_kernel<<<blocks, KNN_THREADS, 0, ctx->stream>>>(db->d_rkeys, d_key, d_desc, first, last, k, db->d_knn_pd, db->d_knn_pi,
-                                                          reinterpret_cast<unsigned int *>(db->d_knn_out + 68), out_d, out_i, cand,
-                                                          db->d_knn_out + 48);
+    sc_knn_kernel<<<blocks, KNN_THREADS, 0, ctx->stream>>>(db->d_rkeys, d_key, d_desc, first, last, k, KNN_PER_BLOCK, db->d_knn_pd,
+                                                          db->d_knn_pi, 0, db->d_knn_out);
     NRS_LAUNCHED();
     return NRS_OK;
 }
@@ -1531,6 +1539,68 @@ int nrs_sc_detect_knn(nrs_sc_db *db, const double *query_host, int first, int la
     *result_host = *db->h_result;
     if (cand_out)
         for (int j = 0; j < k; ++j) memcpy(&cand_out[j], &h[16 + j], sizeof(int32_t));
+    return NRS_OK;
+}
+
+// detectLoopClosureID's tree branch (Scancontext.cpp:364-410) for Q queries at once, two launches in all: the k-NN
+// kernel with the query as its second grid dimension (ring keys derived from the descriptors on the device, per-query
+// tickets and merges), then the candidate search over every query's own k ids.  Results are those of Q calls of
+// nrs_sc_detect_knn over the same [first, last).
+int nrs_sc_detect_knn_batch(nrs_sc_db *db, const double *queries_host, int Q, int first, int last, int k,
+                            int32_t *cand_out, nrs_sc_result *results_host)
+{
+    NRS_CHECK_ARG(db && queries_host && results_host && Q >= 1, "bad argument");
+    NRS_CHECK_ARG(k >= 1 && k <= KNN_MAX, "k must be 1..16");
+    std::lock_guard<std::mutex> lk(db->mu);
+    NRS_CHECK_ARG(first >= 0 && last <= db->size && first <= last, "search range outside the database");
+    nrs_ctx *ctx = db->ctx;
+    std::lock_guard<std::mutex> lk2(ctx->mu);
+    NRS_CUDA(cudaSetDevice(ctx->device));
+    if (last == first) {                       // empty tree: nothing found
+        for (int q = 0; q < Q; ++q) { results_host[q].dist = SENTINEL; results_host[q].idx = 0; results_host[q].shift = 0; }
+        if (cand_out) for (int j = 0; j < Q * k; ++j) cand_out[j] = -1;
+        return NRS_OK;
+    }
+    const int n = last - first;
+    // at most 64 blocks per query, each a multiple of the block width
+    int per_block = 4 * KNN_THREADS;
+    while ((n + per_block - 1) / per_block > 64) per_block *= 2;
+    const int blocks = (n + per_block - 1) / per_block;
+    const size_t part_stride = (size_t)blocks * KNN_MAX;
+    for (int done = 0; done < Q; done += XCHG_QCAP) {
+        const int q = std::min(XCHG_QCAP, Q - done);
+        const double *src = queries_host + (size_t)done * DESC;
+        int rc = db->knn_rec.reserve((size_t)q * KNN_REC * sizeof(float));
+        if (!rc) rc = db->knn_part.reserve((size_t)q * part_stride * (sizeof(float) + sizeof(int32_t)));
+        if (!rc) rc = db->knn_host.reserve((size_t)q * KNN_REC * sizeof(float));
+        if (rc) return rc;
+        float *rec = db->knn_rec.as<float>();
+        float *pd = db->knn_part.as<float>();
+        int32_t *pi = reinterpret_cast<int32_t *>(pd + (size_t)q * part_stride);
+        NRS_CUDA(cudaMemcpyAsync(db->d_queries, src, (size_t)q * DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        NRS_CUDA(cudaMemsetAsync(rec, 0, (size_t)q * KNN_REC * sizeof(float), ctx->stream));          // tickets
+        sc_knn_kernel<<<dim3(blocks, q), KNN_THREADS, 0, ctx->stream>>>(db->d_rkeys, nullptr, db->d_queries, first, last, k, per_block,
+                                                                      pd, pi, part_stride, rec);
+        NRS_LAUNCHED();
+        bool all_bin = db_bin_ok(db);
+        for (int i = 0; all_bin && i < q; ++i) all_bin = host_query_is_binary(src + (size_t)i * DESC);
+        const int32_t *d_cand = reinterpret_cast<const int32_t *>(rec + 32);
+        if (all_bin) {
+            rc = nrs_sc::bin_launch(db, db->d_queries, q, d_cand, 0, k, 1, 0, db->d_results, XV_NONE, KNN_REC);
+        } else {
+            for (int i = 0; i < q && !rc; ++i)
+                rc = launch_search(ctx, view_of(db), db->d_queries + (size_t)i * DESC, d_cand + (size_t)i * KNN_REC, 0, k, 0, nullptr,
+                                   nullptr, db->d_block, db->d_state, db->d_results + i, db->max_blocks);
+        }
+        if (rc) return rc;
+        NRS_CUDA(cudaMemcpyAsync(results_host + done, db->d_results, (size_t)q * sizeof(nrs_sc_result), cudaMemcpyDeviceToHost, ctx->stream));
+        float *h = db->knn_host.as<float>();
+        if (cand_out) NRS_CUDA(cudaMemcpyAsync(h, rec, (size_t)q * KNN_REC * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        NRS_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (cand_out)
+            for (int i = 0; i < q; ++i)
+                for (int j = 0; j < k; ++j) memcpy(&cand_out[(size_t)(done + i) * k + j], &h[(size_t)i * KNN_REC + 16 + j], sizeof(int32_t));
+    }
     return NRS_OK;
 }
 

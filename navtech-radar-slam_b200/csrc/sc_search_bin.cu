@@ -276,8 +276,8 @@ static __device__ __noinline__ void certify_dist_bin(const uint2 *__restrict__ q
 template <bool kRedux>
 __global__ void __launch_bounds__(BT, 2)
 sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__restrict__ desc, const double *__restrict__ keys,
-                     const double *__restrict__ queries, int Q, const int32_t *__restrict__ cand, int first, int n_items,
-                     int n_chunks, int per, int idx_scale, int idx_offset, Survivor *__restrict__ surv, size_t surv_stride,
+                     const double *__restrict__ queries, int Q, const int32_t *__restrict__ cand_base, int cand_stride,
+                     int first, int n_items, int n_chunks, int per, int idx_scale, int idx_offset, Survivor *__restrict__ surv, size_t surv_stride,
                      SearchState *__restrict__ st, BlockResult *__restrict__ block_results, unsigned int *__restrict__ gticket,
                      nrs_sc_result *__restrict__ results, XchgView xv)
 {
@@ -294,6 +294,7 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int q = (Q == 1) ? 0 : tile / n_chunks, chunk = tile - q * n_chunks;
         const double *query = queries + (size_t)q * DESC;
+        const int32_t *cand = cand_base ? cand_base + (size_t)q * cand_stride : nullptr;     // this query's own candidate list
         SearchState *stq = st + q;
         Survivor *survq = surv + (size_t)q * surv_stride;
         const int lo = chunk * per, hi = min(n_items, lo + per);
@@ -636,7 +637,7 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
 // host side: launch on the context stream (no synchronisation)
 // -------------------------------------------------------------------------------------------------
 int nrs_sc::bin_launch(nrs_sc_db *db, const double *d_queries, int Q, const int32_t *d_cand, int first, int n_items,
-                       int idx_scale, int idx_offset, nrs_sc_result *d_results, XchgView xv)
+                       int idx_scale, int idx_offset, nrs_sc_result *d_results, XchgView xv, int cand_stride)
 {
     nrs_ctx *ctx = db->ctx;
     if (Q < 1 || Q > XCHG_QCAP) { nrs::set_error("sc batch: 1 <= Q <= %d", XCHG_QCAP); return NRS_EINVAL; }
@@ -653,11 +654,11 @@ int nrs_sc::bin_launch(nrs_sc_db *db, const double *d_queries, int Q, const int3
     const int per = (n_items + n_chunks - 1) / n_chunks;
     static const int use_redux = []() { const char *e = getenv("NRS_SC_BIN_REDUX"); return e ? atoi(e) : NRS_SC_BIN_REDUX_DEFAULT; }();
     if (use_redux)
-        sc_search_bin_kernel<true><<<grid, BT, 0, ctx->stream>>>(db->d_brec, db->d_desc, db->d_keys, d_queries, Q, d_cand, first, n_items,
+        sc_search_bin_kernel<true><<<grid, BT, 0, ctx->stream>>>(db->d_brec, db->d_desc, db->d_keys, d_queries, Q, d_cand, cand_stride, first, n_items,
                                                                  n_chunks, per, idx_scale, idx_offset, db->bin_surv.as<Survivor>(), stride,
                                                                  db->d_bstate, db->bin_block.as<BlockResult>(), db->d_gticket, d_results, xv);
     else
-        sc_search_bin_kernel<false><<<grid, BT, 0, ctx->stream>>>(db->d_brec, db->d_desc, db->d_keys, d_queries, Q, d_cand, first, n_items,
+        sc_search_bin_kernel<false><<<grid, BT, 0, ctx->stream>>>(db->d_brec, db->d_desc, db->d_keys, d_queries, Q, d_cand, cand_stride, first, n_items,
                                                                   n_chunks, per, idx_scale, idx_offset, db->bin_surv.as<Survivor>(), stride,
                                                                   db->d_bstate, db->bin_block.as<BlockResult>(), db->d_gticket, d_results, xv);
     NRS_LAUNCHED();

@@ -156,6 +156,16 @@ class SCDatabase:
         check(lib().nrs_sc_detect_knn(self._h, ptr(q), first, last, k, ptr(cand), C.byref(res)))
         return (res.dist, res.idx, res.shift), cand
 
+    def detect_knn_batch(self, queries, first=0, last=None, k=3):
+        """nrs_sc_detect_knn_batch: detect_knn for Q queries (Q,1200) in two launches
+        -> ([(dist, idx, shift)] * Q, candidate ids (Q, k) int32)"""
+        q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, DESC)
+        last = len(self) if last is None else last
+        cand = np.empty((q.shape[0], k), dtype=np.int32)
+        res = (ScResult * q.shape[0])()
+        check(lib().nrs_sc_detect_knn_batch(self._h, ptr(q), q.shape[0], first, last, k, ptr(cand), res))
+        return [(r.dist, r.idx, r.shift) for r in res], cand
+
     def query_batch(self, queries, first=0, last=None):
         """nrs_sc_query_batch: Q queries (Q,1200) against keyframes [first,last) -> [(dist, idx, shift)] * Q,
         each exactly what query() returns; one kernel launch on a {0,c} database."""

@@ -30,5 +30,5 @@ for rep in range(2):
         t = [int(x) for x in t]
         i = r["info"]
         ph = " ".join(f"{n}={(t[j + 1] - t[j]) / 1e3:.1f}" for j, n in enumerate(names))
-        print(k, "N", pm.feat_in_cart_.shape[1], "M", i.M, "nodes", i.clique_nodes, "iters", i.gnc_iters, f"{dt * 1e3:.2f} ms |", ph, flush=True)
+        print(k, "N", pm.feat_in_cart_.shape[1], "M", i.M, "nodes", i.clique_nodes, "iters", i.gnc_iters, f"{dt * 1e3:.2f} ms |", ph, "greedy_steps", t[10], flush=True)
         vel = r["T"][0, 3] / 0.25

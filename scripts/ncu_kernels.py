@@ -36,7 +36,7 @@ def val(r, name):
 
 agg = collections.OrderedDict()
 for r in data:
-    name = re.sub(r"\(.*", "", r[col["Kernel Name"]].replace("(anonymous namespace)::", "")).replace("void ", "")
+    name = re.sub(r"\(.*", "", r[col["Kernel Name"]].replace("(anonymous namespace)::", "").replace("<unnamed>::", "")).replace("void ", "")
     name = re.sub(r"<.*", "", name).split("::")[-1][:60]
     a = agg.setdefault(name, {"launches": 0, "us": 0.0, "rd": 0.0, "wr": 0.0, "dram_pct": 0.0, "sm_pct": 0.0, "regs": 0, "grid": 0, "block": 0})
     a["launches"] += 1

@@ -2,7 +2,8 @@
 """Workload for ncu captures of the ORORA kernels (run under gpurun):
     ncu --set full --clock-control none -s <skip> -c <n> -o gpurun_out/x python scripts/prof_orora.py [cen2019|cen2018] [mulran|oxford]
 Runs 5 scan pairs through the fused entry point (extract + match + solve); the first 3 warm everything up
-(incl. cen2019's carried threshold), so a capture should skip their launches."""
+(incl. cen2019's carried threshold).  cudaProfilerStart / Stop bracket the last two pairs: capture with
+`--profile-from-start off` to get exactly their kernels."""
 import ctypes as C
 import importlib
 import os
@@ -27,11 +28,20 @@ h = C.c_void_p()
 pkg._lib.check(L.nrs_frame_extract(ctx.handle, raws[0].ctypes.data_as(C.c_void_p), 400, raws[0].shape[1], C.byref(ep), 0, C.byref(h)))
 prev, vel = h, 0.0
 print("launches after first extract:", L.nrs_kernel_launches())
+import torch  # noqa: E402  (cudart handle for the profiler range)
 for k in range(1, 6):
+    if k == 4:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
     cur = C.c_void_p()
     pkg._lib.check(L.nrs_orora_pair(ctx.handle, prev, raws[k].ctypes.data_as(C.c_void_p), 400, raws[k].shape[1], C.byref(ep), k,
                                     C.byref(sp), vel, C.byref(cur), T.ctypes.data_as(C.c_void_p), C.byref(n), C.byref(info)))
     L.nrs_frame_destroy(prev)
     prev, vel = cur, T[12] / 0.25
-    print("pair", k, "matches", n.value, "clique", info.M, "launches so far:", L.nrs_kernel_launches())
+    fi = pkg._lib.FrameInfo()
+    L.nrs_frame_info_get(cur, C.byref(fi))
+    print("pair", k, "matches", n.value, "clique", info.M, "launches so far:", L.nrs_kernel_launches(),
+          "| candidates", fi.n_candidates, "consumed", fi.j_consumed, "sorted", fi.n_sorted, "K0", fi.K_polar, "Kv", fi.K_voxel, "Kd", fi.K_desc)
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
 L.nrs_frame_destroy(prev)

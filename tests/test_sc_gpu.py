@@ -362,6 +362,32 @@ def test_detect_flow_kdtree_mode(sc, ctx, oracle, synth):
     assert checked > 300
 
 
+@pytest.mark.parametrize("binary", [True, False])
+def test_detect_knn_batch_equals_single_calls(sc, ctx, oracle, synth, binary):
+    """nrs_sc_detect_knn_batch (query = second grid dimension of the k-NN kernel, per-query candidate lists in
+    the search kernel) against Q single calls and against the oracle fed with the reference nanoflann's ids;
+    {0,c} and general-valued databases, ragged ranges, fewer keyframes than k."""
+    db, rev = synth.sc_database(700, 150, seed=33, binary=binary)
+    d = sc.SCDatabase(ctx, 1024)
+    d.append(db)
+    qs = np.ascontiguousarray(db[[rev[i][0] for i in range(40)]] if len(rev) >= 40 else db[:40])
+    ref = oracle.ref_kdtree()
+    for first, last, k in ((0, 700, 3), (13, 650, 3), (0, 700, 10), (5, 7, 3), (100, 100, 3)):
+        resb, candb = d.detect_knn_batch(qs, first, last, k)
+        for i in range(len(qs)):
+            res1, cand1 = d.detect_knn(qs[i], first, last, k)
+            assert resb[i] == res1 and np.array_equal(candb[i], cand1), (first, last, k, i)
+        if last - first >= k:
+            keys = np.stack([oracle.sc_ringkey_f32(x) for x in db[first:last]])
+            for i in range(0, len(qs), 7):
+                qk = oracle.sc_ringkey_f32(qs[i])
+                cand = (oracle.ref_knn(keys, qk, k)[0] if ref is not None else oracle.sc_knn_bruteforce(keys, qk, k)[0]) + first
+                assert np.array_equal(candb[i], cand)
+                eloop, eyaw, emd, enn = oracle.sc_detect_from_candidates(qs[i], db, cand, 0.2)
+                assert (resb[i][0], resb[i][1]) == (emd, enn)
+    d.close()
+
+
 def test_between_session_flow(sc, ctx, oracle, synth):
     """detectLoopClosureIDBetweenSession (Scancontext.cpp:267-328): the batch tree is made once, over the keys
     stored at the FIRST call; later calls search exactly those keyframes.  Both modes against the oracle: the
