@@ -392,12 +392,12 @@ def run_ours(args, rank, world, local_rank):
     #      Q records out ---------------------------------------------------------------------------------------------
     q_pin = torch.from_numpy(queries).pin_memory().numpy()
     for w in range(args.warmup):
-        sharded.query_batch(q_pin, (w % n_rep) * D_KEYFRAMES, (w % n_rep + 1) * D_KEYFRAMES)
+        sharded.query_batch(q_pin, (w % n_rep) * D_KEYFRAMES, (w % n_rep + 1) * D_KEYFRAMES, as_array=True)
     barrier()
     t0 = time.perf_counter()
     for s in range(args.steps):
         r = s % n_rep
-        sharded.query_batch(q_pin, r * D_KEYFRAMES, (r + 1) * D_KEYFRAMES)
+        sharded.query_batch(q_pin, r * D_KEYFRAMES, (r + 1) * D_KEYFRAMES, as_array=True)
     barrier()
     dt = time.perf_counter() - t0
     tt = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -442,8 +442,9 @@ def run_ours(args, rank, world, local_rank):
                               f"{n_rep * n_local * 16.4e3 / 1e9:.1f} GB of database per GPU > 126 MB L2)",
                            parity_gate=parity),
             "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": Q * DESC_BYTES, "d2h_bytes_per_step": Q * 16,
-                    "api": ("ShardedSCDatabase.query_batch -> nrs_sc_query_batch_dev" + ("_sharded" if peer else "") if world > 1
-                            else "ShardedSCDatabase.query_batch -> nrs_sc_query_batch") + ", pinned host queries in, host records out"},
+                    "api": ("ShardedSCDatabase.query_batch -> " + ("nrs_sc_query_batch_sharded" if peer else "nrs_sc_query_batch_dev + all_gather")
+                            if world > 1 else "ShardedSCDatabase.query_batch -> nrs_sc_query_batch")
+                           + ", pinned host queries in (no host staging copy), Q host records out as one structured array"},
             "single_query": {"device_us": single_us, "device_queries_per_s": 1e6 / single_us,
                              "e2e_us": single_e2e_us, "e2e_queries_per_s": 1e6 / single_e2e_us,
                              "what": "one query per launch (Q = 1): latency of a loop query, device-resident and through "

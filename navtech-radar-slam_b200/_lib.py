@@ -161,6 +161,7 @@ def _declare(L):
     L.nrs_frame_extract.argtypes = [vp, vp, i32, i32, vp, C.c_int64, C.POINTER(vp)]
     L.nrs_frame_destroy.argtypes = [vp]
     L.nrs_frame_info_get.argtypes = [vp, vp]
+    L.nrs_frontend_tail_times.argtypes = [vp, vp]
     L.nrs_frame_get.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.nrs_frame_get_stages.argtypes = [vp, vp, vp, vp, vp]
     L.nrs_match.argtypes = [vp, vp, vp, C.c_float, i32, vp, vp, vp, vp, vp, vp, vp]

@@ -29,6 +29,7 @@ struct FrameCounts {
     int   n_sub;         // top-candidate subset: pixels with h >= the carried threshold (0 in full-sort mode)
     int   n_sorted;      // candidates in the sorted list the marking loop walked (== n_cand in full-sort mode)
     int   need_full;     // the subset could not prove the marking loop's outcome: redo with the full sort
+    unsigned long long t_tail[8];   // %globaltimer stamps of fe_tail_kernel's phases (diagnostics: nrs_frontend_tail_times)
     unsigned int ticket[3];   // last-block tickets of fe_stats_kernel / fe_h_kernel / fe_incr_kernel (zeroed with the counts)
 };
 
@@ -76,6 +77,35 @@ __device__ __forceinline__ int fe_block256_exscan(int c, int *wsum, int &total)
     for (int w = 0; w < 8; ++w) { const int v = wsum[w]; if (w < warp) before += v; total += v; }
     return before + inc - c;
 }
+
+// exclusive prefix of one value per thread over a 1024-thread block, total in `total`: warp scans by shuffles, the 32
+// warp totals through `wtot` (32 entries of shared memory), every warp scans those itself -- one barrier, ~30
+// instructions per thread (cub::BlockScan's warp-scans variant walks the 32 warp aggregates one by one in every
+// thread).  The caller keeps a barrier between two calls that share `wtot` (every call site has one anyway).
+template <class T>
+__device__ __forceinline__ T fe_block1024_exscan(T v, T *wtot, T &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const T up = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += up;
+    }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    const T wt = wtot[lane];
+    T winc = wt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const T up = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += up;
+    }
+    total = __shfl_sync(0xffffffffu, winc, 31);
+    return __shfl_sync(0xffffffffu, winc - wt, warp) + inc - v;
+}
+
+struct SubPair { unsigned int e; float h; };   // cen2019 top-candidate subset: (pixel, h) as the compaction emits them
 
 // per-frame azimuth tables, device layout == pinned host layout: ONE host-to-device copy per frame
 struct AzTables {
@@ -131,6 +161,8 @@ struct FrontendState {
     int   taps_sigma = -1;
     // voxel scratch
     float *d_pts32 = nullptr;            // 2 * KP_CAP float x,y
+    SubPair *d_sel = nullptr;            // R x C: the compacted candidate subset (at most every pixel)
+    float *d_lut = nullptr;              // 256: (float)(b / 255.0), load_radar's sample values (radar_utils.cpp:117-126)
     int *d_stage = nullptr;              // R x C: one staging row of keypoint range bins per azimuth
     int   *d_rowcount = nullptr;         // per-row keypoint counts / offsets
     int    R = 0, C = 0, pitch = 0;

@@ -27,6 +27,7 @@
 #include <cooperative_groups.h>
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 #include <float.h>
 #include <math.h>
 #include <string.h>
@@ -60,21 +61,22 @@ __device__ __forceinline__ float prewitt_abs(const float *__restrict__ row, int 
 
 constexpr int RED_THREADS = 256;
 
-// cv::mean = sum * (1.0 / N) in f64, truncated to float by the reference (features.cpp:211,214).  Called by thread 0
-// of every block after it stored its partial sum; the block that draws the last ticket reduces all partials in one
+// cv::mean = sum * (1.0 / N) in f64, truncated to float by the reference (features.cpp:211,214).  Called by every
+// thread of every block after thread 0 stored the block's partial sum; the block that draws the last ticket reduces all partials in one
 // fixed order (lane l sums partial[l], partial[l + 32], ... then a fixed shuffle tree), whichever block it is.
 __device__ __forceinline__ void last_block_mean(unsigned int *ticket, const double *partial, double inv_n,
                                                 float *mean_out, bool *is_last)
 {
+    const unsigned int nblocks = gridDim.x * gridDim.y;
     if (threadIdx.x == 0) {
         __threadfence();
-        *is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        *is_last = atomicAdd(ticket, 1u) == nblocks - 1;
     }
     __syncthreads();
     if (*is_last && threadIdx.x < 32) {
         __threadfence();
         double s = 0.0;
-        for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) s += __ldcg(partial + b);
+        for (int b = threadIdx.x; b < (int)nblocks; b += 32) s += __ldcg(partial + b);
         for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
         if (threadIdx.x == 0) *mean_out = (float)(s * inv_n);
     }
@@ -109,6 +111,49 @@ fe_stats_kernel(const float *__restrict__ fft, int R, int C, double *__restrict_
         atomicMax(reinterpret_cast<int *>(&cnt->maxg), __float_as_int(m));      // g >= 0: int order == float order
     }
     last_block_mean(&cnt->ticket[0], partial, 1.0 / (double)N, &cnt->mean, &is_last);
+}
+
+// K1 of the extraction pipeline in one pass over the raw PNG rows: load_radar's decode (fft written for the image
+// branch and fe_h_kernel) and fe_stats_kernel's sum(f) / max(g) taken from the bytes directly.  The 256 possible
+// sample values (float)(b / 255.0) come from a table computed once on the host (IEEE f64 division and narrowing:
+// the same bits as the device's), so no division is left in the kernel.  One block per azimuth; the partial sums
+// are exact (see fe_stats_kernel), so the mean does not depend on how the frame is cut into blocks.
+__global__ void __launch_bounds__(RED_THREADS)
+fe_decode_stats_kernel(const unsigned char *__restrict__ raw, int pitch, int R, int C, const float *__restrict__ lut_g,
+                       float *__restrict__ fft, double *__restrict__ partial, FrameCounts *__restrict__ cnt)
+{
+    __shared__ float lut[256];
+    __shared__ float smax[RED_THREADS / 32];
+    __shared__ bool is_last;
+    typedef cub::BlockReduce<double, RED_THREADS> BR;
+    __shared__ typename BR::TempStorage tmp;
+    lut[threadIdx.x] = lut_g[threadIdx.x];
+    __syncthreads();
+    const int i = blockIdx.x;
+    const unsigned char *row = raw + (size_t)i * pitch + 11;
+    float *frow = fft + (size_t)i * C;
+    double s = 0.0;
+    float mg = 0.0f;
+#pragma unroll 4
+    for (int j = threadIdx.x; j < C; j += RED_THREADS) {
+        const int jl = (j == 0) ? 1 : j - 1, jr = (j == C - 1) ? C - 2 : j + 1;       // BORDER_REFLECT101
+        const float v = (j >= 42) ? lut[row[j]] : 0.0f;
+        const float vl = (jl >= 42) ? lut[row[jl]] : 0.0f, vr = (jr >= 42) ? lut[row[jr]] : 0.0f;
+        frow[j] = v;
+        s += (double)v;
+        mg = fmaxf(mg, fabsf(vr - vl));
+    }
+    const double bs = BR(tmp).Sum(s);
+    for (int o = 16; o > 0; o >>= 1) mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, o));
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mg;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = 0.0f;
+        for (int w = 0; w < RED_THREADS / 32; ++w) m = fmaxf(m, smax[w]);
+        partial[blockIdx.x] = bs;
+        atomicMax(reinterpret_cast<int *>(&cnt->maxg), __float_as_int(m));      // g >= 0: int order == float order
+    }
+    last_block_mean(&cnt->ticket[0], partial, 1.0 / (double)((size_t)R * C), &cnt->mean, &is_last);
 }
 
 // h = s .* (1 - g / maxg) (features.cpp:206-213), all f32; Mat /= double multiplies by (float)(1/maxg)
@@ -199,8 +244,9 @@ __global__ void fe_claim_kernel(const unsigned int *__restrict__ sorted_vals,
 // set bit -- and settles what used to be four more launches (an inclusive scan, the j_star search, its fix-up):
 //   * fewer than max_points regions in the whole list: every candidate was consumed, which the top-candidate
 //     subset can only vouch for when it held them all (else need_full);
-//   * the threshold carried to the next frame: the h value at rank ~4x the candidates this frame consumed (at
-//     least 16k, at most 48k of the 64k capacity).
+//   * the threshold carried to the next frame: the h value at rank ~1.5x the candidates this frame consumed (at
+//     least 8k, at most 48k of the 64k capacity) -- small enough for the single-CTA sort in the usual case; a
+//     frame that needs more than the subset holds raises need_full and is redone with the full sort.
 constexpr int INCR_T = 256;
 __global__ void __launch_bounds__(INCR_T)
 fe_incr_kernel(const unsigned int *__restrict__ sorted_vals, const float *__restrict__ fft, int R, int C,
@@ -264,10 +310,10 @@ fe_incr_kernel(const unsigned int *__restrict__ sorted_vals, const float *__rest
     }
     cnt->j_star = j_star;
     if (cnt->need_full || n_sorted <= 0) return;
-    const int want = min(max(4 * (j_star + 1), 16384), 49152);
-    if (n_sorted > want) *thresh = sorted_keys[want];
+    const int want = min(max(3 * (j_star + 1) / 2, 8192), 49152);
+    if (n_sorted > want) *thresh = sorted_keys[want];                                 // shrink to the target
     else if (n_sorted == cnt->n_cand) *thresh = sorted_keys[n_sorted - 1];           // everything fits: keep it all
-    else if (n_sorted >= 2 * (j_star + 1)) *thresh = sorted_keys[n_sorted - 1];      // comfortable margin: keep
+    else if (4 * n_sorted >= 5 * (j_star + 1)) *thresh = sorted_keys[n_sorted - 1];  // 1.25x margin or better: keep
     else *thresh = cnt->mean_h + 0.5f * (sorted_keys[n_sorted - 1] - cnt->mean_h);   // thin margin: loosen
 }
 
@@ -279,16 +325,18 @@ fe_incr_kernel(const unsigned int *__restrict__ sorted_vals, const float *__rest
 // the full order, so claims, regions and j_star are identical -- provided the loop terminates inside the subset
 // (or the subset holds every candidate).  Otherwise need_full is raised and the host redoes the frame with the
 // full sort; the result never depends on T.
-struct SubSelect {
+// The compaction carries (pixel, h) pairs: the sort that follows reads its keys in one coalesced sweep instead of
+// gathering h[pixel] pixel by pixel.
+struct SubLoad {
     const float *h;
+    __device__ __forceinline__ SubPair operator()(unsigned int e) const { return SubPair{e, h[e]}; }
+};
+struct SubSelect {
     const float *thresh;
     const FrameCounts *cnt;
-    __device__ __forceinline__ bool operator()(const unsigned int &e) const
-    {
-        const float hv = h[e];
-        return hv > cnt->mean_h && hv >= *thresh;
-    }
+    __device__ __forceinline__ bool operator()(const SubPair &p) const { return p.h > cnt->mean_h && p.h >= *thresh; }
 };
+typedef thrust::transform_iterator<SubLoad, thrust::counting_iterator<unsigned int>> SubPairIn;
 
 __global__ void __launch_bounds__(RED_THREADS)
 fe_prep_sub_kernel(const float *__restrict__ h, size_t N, FrameCounts *__restrict__ cnt, unsigned int *__restrict__ claim)
@@ -305,63 +353,29 @@ fe_prep_sub_kernel(const float *__restrict__ h, size_t N, FrameCounts *__restric
     if (threadIdx.x == 0 && bc) atomicAdd(&cnt->n_cand, bc);
 }
 
-// The subset's sort as ONE launch: a thread-block cluster of 8 CTAs holds the <= 64k (key, pixel) pairs in its
-// distributed shared memory (8192 pairs per CTA, two buffers) and runs a stable LSD radix sort over them -- 8-bit
-// digits, per-warp private histograms over contiguous segments (ranks inside a 32-group from match.any, like
-// fe_tail_kernel), per-digit CTA totals exchanged through DSMEM, the scatter written straight into the owning
-// CTA's shared memory (st.shared::cluster).  Two cluster barriers per pass; a pass whose digit is the same for every
-// key is skipped.  Keys are h mapped to descending-sortable integers (-0.0 == +0.0 like the reference's compare),
-// so equal h keep pixel order exactly as cub::DeviceRadixSort::SortPairsDescending over the same list would.
-// Replaces fe_sub_keys_kernel + six CUB launches (histogram, scan, four onesweep passes) on the subset path.
-namespace cg = cooperative_groups;
-constexpr int SS_CL = 8, SS_T = 1024, SS_PER = FE_SUB_CAP / SS_CL;
-static_assert(SS_PER == 8192, "rank -> (CTA, slot) uses shifts");
-struct SubSortSmem {
-    unsigned int key[2][SS_PER];
-    unsigned int val[2][SS_PER];
-    unsigned short hist[32][256];        // [warp][digit]: counts, then exclusive offsets among this CTA's warps
-    unsigned int tot[256];               // this CTA's items per digit (read by the whole cluster)
-    unsigned int base[256];              // global rank of this CTA's first item with the digit
-    int skip;
-};
-
-__global__ void __cluster_dims__(SS_CL, 1, 1) __launch_bounds__(SS_T)
-fe_subsort_kernel(const float *__restrict__ h, const unsigned int *__restrict__ sel, FrameCounts *__restrict__ cnt,
-                  float *__restrict__ keys_out, unsigned int *__restrict__ vals_out)
+// Stable LSD radix sort of n <= 16384 (key, 16-bit payload) pairs held in shared memory by ONE 1024-thread CTA:
+// 8-bit digits, `passes` of them from the least significant; every warp owns a contiguous segment of whole
+// 32-groups and a private histogram (hist: [32 warps][256] u16), ranks inside a 32-group come from match.any, the
+// (digit, warp) offsets from one block scan.  Returns the buffer (0 / 1) that holds the result.
+constexpr int SORT_T = 1024;
+__device__ __forceinline__ int fe_block_sort16(unsigned int *k0, unsigned int *k1, unsigned short *v0, unsigned short *v1,
+                                               unsigned short *hist, int n, int passes, int *wtot)
 {
-    typedef cub::BlockScan<unsigned int, SS_T> BS;
-    extern __shared__ __align__(16) unsigned char dyn[];
-    __shared__ typename BS::TempStorage tmp;
-    SubSortSmem &sm = *reinterpret_cast<SubSortSmem *>(dyn);
-    cg::cluster_group cluster = cg::this_cluster();
-    const int c = (int)cluster.block_rank();
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int n_sub = cnt->n_sub;
-    const int n = min(n_sub, FE_SUB_CAP);
-    if (c == 0 && t == 0) {
-        cnt->n_sorted = n;
-        if (n_sub > FE_SUB_CAP) cnt->need_full = 1;          // the first 64k in pixel order are not the top 64k
-    }
-    const int my_n = max(0, min(SS_PER, n - c * SS_PER));
-    for (int i = t; i < my_n; i += SS_T) {
-        const unsigned int e = sel[c * SS_PER + i];
-        const float hv = h[e];
-        const unsigned int b = (hv == 0.0f) ? 0u : __float_as_uint(hv);
-        const unsigned int u = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);      // ascending-sortable
-        sm.key[0][i] = ~u;                                                        // descending
-        sm.val[0][i] = e;
-    }
-    const int seg = ((my_n + SS_T - 1) / SS_T) * 32;          // whole 32-groups per warp, contiguous in order
-    const int g0 = min(warp * seg, my_n), g1 = min(g0 + seg, my_n);
-    unsigned short *hw = sm.hist[warp];
+    unsigned int *kbuf[2] = {k0, k1};
+    unsigned short *vbuf[2] = {v0, v1};
+    const int seg = ((n + SORT_T - 1) / SORT_T) * 32;             // whole 32-groups per warp, contiguous in order
+    const int g0 = min(warp * seg, n), g1 = min(g0 + seg, n);
+    unsigned short *hw = hist + warp * 256;
     const unsigned int lt = (1u << lane) - 1u;
     int cur = 0;
-    for (int pass = 0; pass < 4; ++pass) {
+    for (int pass = 0; pass < passes; ++pass) {
         const int shift = 8 * pass;
-        const unsigned int *sk = sm.key[cur];
-        const unsigned int *sv = sm.val[cur];
-        for (int i = t; i < 32 * 256 / 2; i += SS_T) reinterpret_cast<unsigned int *>(&sm.hist[0][0])[i] = 0u;
-        if (t == 0) sm.skip = 0;
+        const unsigned int *sk = kbuf[cur];
+        const unsigned short *sv = vbuf[cur];
+        unsigned int *dk = kbuf[cur ^ 1];
+        unsigned short *dv = vbuf[cur ^ 1];
+        for (int i = t; i < 32 * 256 / 2; i += SORT_T) reinterpret_cast<unsigned int *>(hist)[i] = 0u;
         __syncthreads();
         for (int gb = g0; gb < g1; gb += 32) {
             const int k = gb + lane;
@@ -372,11 +386,136 @@ fe_subsort_kernel(const float *__restrict__ h, const unsigned int *__restrict__ 
             __syncwarp();
         }
         __syncthreads();
-        if (t < 256) {
-            unsigned int run = 0;
-#pragma unroll 8
-            for (int w = 0; w < 32; ++w) { const unsigned int v = sm.hist[w][t]; sm.hist[w][t] = (unsigned short)run; run += v; }
-            sm.tot[t] = run;
+        {   // exclusive offsets in (digit, warp) order: thread t owns digit t / 4, warps 8 * (t % 4) .. + 7
+            const int d = t >> 2, w0 = (t & 3) * 8;
+            int c[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { c[j] = hist[(w0 + j) * 256 + d]; sum += c[j]; }
+            int total;
+            int ex = fe_block1024_exscan(sum, wtot, total);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { hist[(w0 + j) * 256 + d] = (unsigned short)ex; ex += c[j]; }
+        }
+        __syncthreads();
+        for (int gb = g0; gb < g1; gb += 32) {
+            const int k = gb + lane;
+            const bool ok = k < g1;
+            const unsigned int key = ok ? sk[k] : 0u;
+            const unsigned int dig = ok ? ((key >> shift) & 255u) : 0xffffffffu;
+            const unsigned int peers = __match_any_sync(0xffffffffu, dig);
+            const int rank = __popc(peers & lt);
+            const int base = ok ? hw[dig] : 0;
+            __syncwarp();
+            if (ok && rank == 0) hw[dig] = (unsigned short)(base + __popc(peers));
+            __syncwarp();
+            if (ok) { dk[base + rank] = key; dv[base + rank] = sv[k]; }
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    return cur;
+}
+
+// The subset's sort as ONE launch: a thread-block cluster of 8 CTAs holds the <= 64k (key, pixel) pairs in its
+// distributed shared memory -- dealt EVENLY, ceil(n / 8) consecutive ranks per CTA, so that eight SMs' shared-memory
+// pipes work on a pass whatever n is -- and runs a stable LSD radix sort over them: 8-bit digits, per-warp private
+// histograms over contiguous segments (ranks inside a 32-group from match.any, like fe_block_sort16), per-digit CTA
+// totals exchanged through DSMEM, the scatter written straight into the owning CTA's shared memory
+// (st.shared::cluster).  Keys: h mapped to an ascending-sortable integer u (-0.0 == +0.0 like the reference's
+// compare), then re-based to umax - u over the whole subset: descending h = ascending key, and the passes cover only
+// the bytes the subset's value range needs (3 of 4 for a range below 2^24 ulps).  Equal h keep pixel order exactly as
+// cub::DeviceRadixSort::SortPairsDescending over the same list would.  Two cluster barriers per pass plus one for
+// the range.  Replaces fe_sub_keys_kernel + six CUB launches (histogram, scan, four onesweep passes).
+namespace cg = cooperative_groups;
+constexpr int SS_CL = 8, SS_T = 1024, SS_PER = FE_SUB_CAP / SS_CL;
+struct SubSortSmem {
+    unsigned int key[2][SS_PER];
+    unsigned int val[2][SS_PER];
+    unsigned short hist[32][256];        // [warp][digit]: counts, then exclusive offsets among this CTA's warps
+    unsigned int tot[256];               // this CTA's items per digit (read by the whole cluster)
+    unsigned int base[256];              // global rank of this CTA's first item with the digit
+    unsigned int umax, umin;             // this CTA's key range (read by the whole cluster)
+};
+constexpr size_t SS_SMEM = sizeof(SubSortSmem);
+
+__global__ void __cluster_dims__(SS_CL, 1, 1) __launch_bounds__(SS_T)
+fe_subsort_kernel(const SubPair *__restrict__ sel, FrameCounts *__restrict__ cnt,
+                  float *__restrict__ keys_out, unsigned int *__restrict__ vals_out)
+{
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ unsigned int wtot[32];
+    SubSortSmem &sm = *reinterpret_cast<SubSortSmem *>(dyn);
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = (int)cluster.block_rank();
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int n_sub = cnt->n_sub;
+    const int n = min(n_sub, FE_SUB_CAP);
+    if (c == 0 && t == 0) {
+        cnt->n_sorted = n;
+        if (n_sub > FE_SUB_CAP) cnt->need_full = 1;          // the first 64k in pixel order are not the top 64k
+    }
+    const int per = max(32, ((n + SS_CL * 32 - 1) / (SS_CL * 32)) * 32);      // ranks per CTA (whole 32-groups, <= SS_PER)
+    const int my_n = max(0, min(per, n - c * per));
+    if (t == 0) { sm.umax = 0u; sm.umin = 0xffffffffu; }
+    __syncthreads();
+    {
+        unsigned int mx = 0u, mn = 0xffffffffu;
+        for (int i = t; i < my_n; i += SS_T) {
+            const SubPair p = sel[c * per + i];
+            const unsigned int b = (p.h == 0.0f) ? 0u : __float_as_uint(p.h);
+            const unsigned int u = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);  // ascending-sortable
+            sm.key[0][i] = u;
+            sm.val[0][i] = p.e;
+            mx = max(mx, u); mn = min(mn, u);
+        }
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        if (lane == 0 && my_n > 0) { atomicMax(&sm.umax, mx); atomicMin(&sm.umin, mn); }
+    }
+    cluster.sync();
+    unsigned int umax = 0u, umin = 0xffffffffu;
+#pragma unroll
+    for (int cc = 0; cc < SS_CL; ++cc) {
+        umax = max(umax, *cluster.map_shared_rank(&sm.umax, cc));
+        umin = min(umin, *cluster.map_shared_rank(&sm.umin, cc));
+    }
+    for (int i = t; i < my_n; i += SS_T) sm.key[0][i] = umax - sm.key[0][i];      // own items: no barrier needed
+    const int passes = (n > 0) ? ((32 - __clz(umax - umin)) + 7) >> 3 : 0;
+    if (passes == 0) cluster.sync();                          // nobody leaves while its range is still being read
+    const int seg = ((my_n + SS_T - 1) / SS_T) * 32;          // whole 32-groups per warp, contiguous in order
+    const int g0 = min(warp * seg, my_n), g1 = min(g0 + seg, my_n);
+    unsigned short *hw = sm.hist[warp];
+    const unsigned int lt = (1u << lane) - 1u;
+    int cur = 0;
+    for (int pass = 0; pass < passes; ++pass) {
+        const int shift = 8 * pass;
+        const unsigned int *sk = sm.key[cur];
+        const unsigned int *sv = sm.val[cur];
+        for (int i = t; i < 32 * 256 / 2; i += SS_T) reinterpret_cast<unsigned int *>(&sm.hist[0][0])[i] = 0u;
+        __syncthreads();
+        for (int gb = g0; gb < g1; gb += 32) {
+            const int k = gb + lane;
+            const bool ok = k < g1;
+            const unsigned int dig = ok ? ((sk[k] >> shift) & 255u) : 0xffffffffu;
+            const unsigned int peers = __match_any_sync(0xffffffffu, dig);
+            if (ok && !(peers & lt)) hw[dig] += (unsigned short)__popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        {   // exclusive offsets among this CTA's warps, digit totals: thread t owns digit t / 4, warps 8 * (t % 4) .. + 7
+            const int d = t >> 2, w0 = (t & 3) * 8;
+            unsigned int cw[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { cw[j] = sm.hist[w0 + j][d]; sum += cw[j]; }
+            unsigned int inc = sum;                            // inclusive scan over the digit's four threads
+            unsigned int up = __shfl_up_sync(0xffffffffu, inc, 1);
+            if ((t & 3) >= 1) inc += up;
+            up = __shfl_up_sync(0xffffffffu, inc, 2);
+            if ((t & 3) >= 2) inc += up;
+            unsigned int ex = inc - sum;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { sm.hist[w0 + j][d] = (unsigned short)ex; ex += cw[j]; }
+            if ((t & 3) == 3) sm.tot[d] = inc;
         }
         cluster.sync();
         unsigned int all = 0, before = 0;
@@ -387,42 +526,38 @@ fe_subsort_kernel(const float *__restrict__ h, const unsigned int *__restrict__ 
                 all += v;
                 if (cc < c) before += v;
             }
-            if (all == (unsigned int)n && n > 0) sm.skip = 1;       // every key has this digit: the pass is the identity
         }
-        unsigned int ex;
-        BS(tmp).ExclusiveSum(all, ex);
+        unsigned int all_total;
+        const unsigned int ex = fe_block1024_exscan(all, wtot, all_total);
         if (t < 256) sm.base[t] = ex + before;
         __syncthreads();
-        const bool skip = sm.skip != 0;                        // the same verdict in every CTA (global counts)
-        if (!skip) {
-            unsigned int *dk = sm.key[cur ^ 1], *dv = sm.val[cur ^ 1];
-            for (int gb = g0; gb < g1; gb += 32) {
-                const int k = gb + lane;
-                const bool ok = k < g1;
-                const unsigned int key = ok ? sk[k] : 0u;
-                const unsigned int dig = ok ? ((key >> shift) & 255u) : 0xffffffffu;
-                const unsigned int peers = __match_any_sync(0xffffffffu, dig);
-                const int rank = __popc(peers & lt);
-                const unsigned int loc = ok ? hw[dig] : 0u;
-                __syncwarp();
-                if (ok && rank == 0) hw[dig] = (unsigned short)(loc + __popc(peers));
-                __syncwarp();
-                if (ok) {
-                    const unsigned int dst = sm.base[dig] + loc + rank;            // rank in the whole list
-                    const unsigned int dc = dst >> 13, di = dst & (SS_PER - 1);
-                    *cluster.map_shared_rank(&dk[di], dc) = key;
-                    *cluster.map_shared_rank(&dv[di], dc) = sv[k];
-                }
+        unsigned int *dk = sm.key[cur ^ 1], *dv = sm.val[cur ^ 1];
+        for (int gb = g0; gb < g1; gb += 32) {
+            const int k = gb + lane;
+            const bool ok = k < g1;
+            const unsigned int key = ok ? sk[k] : 0u;
+            const unsigned int dig = ok ? ((key >> shift) & 255u) : 0xffffffffu;
+            const unsigned int peers = __match_any_sync(0xffffffffu, dig);
+            const int rank = __popc(peers & lt);
+            const unsigned int loc = ok ? hw[dig] : 0u;
+            __syncwarp();
+            if (ok && rank == 0) hw[dig] = (unsigned short)(loc + __popc(peers));
+            __syncwarp();
+            if (ok) {
+                const unsigned int dst = sm.base[dig] + loc + rank;            // rank in the whole list
+                const unsigned int dc = dst / (unsigned int)per, di = dst - dc * (unsigned int)per;
+                *cluster.map_shared_rank(&dk[di], dc) = key;
+                *cluster.map_shared_rank(&dv[di], dc) = sv[k];
             }
-            cur ^= 1;
         }
+        cur ^= 1;
         cluster.sync();                                        // remote stores landed; tot / base free for the next pass
     }
     for (int i = t; i < my_n; i += SS_T) {
-        const unsigned int u = ~sm.key[cur][i];
+        const unsigned int u = umax - sm.key[cur][i];
         const unsigned int b = (u >> 31) ? (u ^ 0x80000000u) : ~u;
-        keys_out[c * SS_PER + i] = __uint_as_float(b);
-        vals_out[c * SS_PER + i] = sm.val[cur][i];
+        keys_out[c * per + i] = __uint_as_float(b);
+        vals_out[c * per + i] = sm.val[cur][i];
     }
 }
 
@@ -541,29 +676,30 @@ fe_tail_kernel(const int *__restrict__ rowcount, const int *__restrict__ stage, 
                int *__restrict__ polar, FrameCounts *__restrict__ cnt, const double *__restrict__ cossin,
                const long long *__restrict__ times, float radar_resolution, int use_vox, float leaf, int cap,
                double *__restrict__ cart_pre, long long *__restrict__ t_pre, float *__restrict__ pts32,
-               double *__restrict__ vox_xy, float cart_resolution, int width, int patch,
+               float cart_resolution, int width, int patch,
                double *__restrict__ feat, float *__restrict__ kp, long long *__restrict__ t_out,
                float *__restrict__ kp_orb)
 {
-    typedef cub::BlockScan<int, TAIL_T, cub::BLOCK_SCAN_WARP_SCANS> BS;
     extern __shared__ __align__(16) unsigned char dyn[];
-    __shared__ typename BS::TempStorage tmp;
+    __shared__ int wtot[32];
+    __shared__ unsigned long long wtot3[32];
     __shared__ float smin[2][32], smax[2][32];
     __shared__ VoxGrid g;
     __shared__ unsigned int maxkey;
-    __shared__ int carry;
     __shared__ int rowoff[FE_MAX_AZ];
     unsigned int *kbuf[2] = {reinterpret_cast<unsigned int *>(dyn), reinterpret_cast<unsigned int *>(dyn) + cap};
     unsigned short *vbuf[2] = {reinterpret_cast<unsigned short *>(kbuf[1] + cap), reinterpret_cast<unsigned short *>(kbuf[1] + cap) + cap};
     unsigned short *hist = vbuf[1] + cap;                           // [warp][digit]
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+#define TAIL_STAMP(i) do { if (t == 0) { unsigned long long ts_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts_)); cnt->t_tail[i] = ts_; } } while (0)
+    TAIL_STAMP(0);
     // ---- the azimuths' staging rows, strung together in azimuth order (features.cpp:251-278 pushes them in
     // this order); more than cap keypoints is reported, not truncated silently ----
     int K0;
     {
         const int v = (t < R) ? rowcount[t] : 0;
-        int ex, total;
-        BS(tmp).ExclusiveSum(v, ex, total);
+        int total;
+        const int ex = fe_block1024_exscan(v, wtot, total);
         if (t < R) rowoff[t] = ex;
         K0 = min(total, cap);
         if (t == 0) {
@@ -573,6 +709,7 @@ fe_tail_kernel(const int *__restrict__ rowcount, const int *__restrict__ stage, 
         __syncthreads();
     }
 
+    TAIL_STAMP(1);
     // ---- polar_to_cartesian_points; PCL's float copy and its bounding box ----
     float mnx = FLT_MAX, mny = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX;
     for (int k = t; k < K0; k += TAIL_T) {
@@ -599,8 +736,8 @@ fe_tail_kernel(const int *__restrict__ rowcount, const int *__restrict__ stage, 
         }
     }
     __syncthreads();                                                 // pts32 is read by other threads below
-    int n = K0;
-    const double *pts_xy = cart_pre;
+    TAIL_STAMP(2);
+    int sorted_in = 0;
     if (use_vox) {
         for (int o = 16; o > 0; o >>= 1) {
             mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
@@ -633,133 +770,89 @@ fe_tail_kernel(const int *__restrict__ rowcount, const int *__restrict__ stage, 
         mk = __reduce_max_sync(0xffffffffu, mk);
         if (lane == 0 && mk) atomicMax(&maxkey, mk);
         __syncthreads();
+        TAIL_STAMP(3);
         const int passes = (32 - __clz(maxkey) + 7) >> 3;
-        const int seg = ((K0 + TAIL_T - 1) / TAIL_T) * 32;           // whole 32-groups per warp, contiguous in order
-        const int g0 = warp * seg, g1 = min(g0 + seg, K0);
-        unsigned short *hw = hist + warp * 256;
-        const unsigned int lt = (1u << lane) - 1u;
-        int cur = 0;
-        for (int pass = 0; pass < passes; ++pass) {
-            const int shift = 8 * pass;
-            const unsigned int *sk = kbuf[cur];
-            const unsigned short *sv = vbuf[cur];
-            unsigned int *dk = kbuf[cur ^ 1];
-            unsigned short *dv = vbuf[cur ^ 1];
-            for (int i = t; i < 32 * 256 / 2; i += TAIL_T) reinterpret_cast<unsigned int *>(hist)[i] = 0u;
-            __syncthreads();
-            for (int gb = g0; gb < g1; gb += 32) {
-                const int k = gb + lane;
-                const bool ok = k < K0;
-                const unsigned int dig = ok ? ((sk[k] >> shift) & 255u) : 0xffffffffu;
-                const unsigned int peers = __match_any_sync(0xffffffffu, dig);
-                if (ok && !(peers & lt)) hw[dig] += (unsigned short)__popc(peers);
-                __syncwarp();
-            }
-            __syncthreads();
-            {   // exclusive offsets in (digit, warp) order: thread t owns digit t / 4, warps 8 * (t % 4) .. + 7
-                const int d = t >> 2, w0 = (t & 3) * 8;
-                int c[8], sum = 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { c[j] = hist[(w0 + j) * 256 + d]; sum += c[j]; }
-                int ex;
-                BS(tmp).ExclusiveSum(sum, ex);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { hist[(w0 + j) * 256 + d] = (unsigned short)ex; ex += c[j]; }
-            }
-            __syncthreads();
-            for (int gb = g0; gb < g1; gb += 32) {
-                const int k = gb + lane;
-                const bool ok = k < K0;
-                const unsigned int key = ok ? sk[k] : 0u;
-                const unsigned int dig = ok ? ((key >> shift) & 255u) : 0xffffffffu;
-                const unsigned int peers = __match_any_sync(0xffffffffu, dig);
-                const int rank = __popc(peers & lt);
-                const int base = ok ? hw[dig] : 0;
-                __syncwarp();
-                if (ok && rank == 0) hw[dig] = (unsigned short)(base + __popc(peers));
-                __syncwarp();
-                if (ok) { dk[base + rank] = key; dv[base + rank] = sv[k]; }
-            }
-            __syncthreads();
-            cur ^= 1;
-        }
-        // centroids in ascending voxel index, f32 running sums in (stable) point order, / float(count)
-        const unsigned int *skeys = kbuf[cur];
-        const unsigned short *svals = vbuf[cur];
-        if (t == 0) carry = 0;
-        __syncthreads();
-        for (int base = 0; base < K0; base += TAIL_T) {
-            const int k = base + t;
-            const bool head = (k < K0) && (k == 0 || skeys[k] != skeys[k - 1]);
-            int ex, total;
-            BS(tmp).ExclusiveSum(head ? 1 : 0, ex, total);
-            const int c0 = carry;
-            if (head) {
-                float sx = 0.0f, sy = 0.0f;
-                int m = 0;
-                for (int q = k; q < K0 && skeys[q] == skeys[k]; ++q) {
-                    const unsigned int p = svals[q];
-                    sx += pts32[2 * p];
-                    sy += pts32[2 * p + 1];
-                    ++m;
-                }
-                const float fn = (float)m;
-                vox_xy[2 * (c0 + ex)] = (double)(sx / fn);
-                vox_xy[2 * (c0 + ex) + 1] = (double)(sy / fn);
-            }
-            __syncthreads();
-            if (t == 0) carry = c0 + total;
-            __syncthreads();
-        }
-        n = carry;
-        pts_xy = vox_xy;
-        __syncthreads();
-        if (t == 0) cnt->Kv = n;
+        const int cur = fe_block_sort16(kbuf[0], kbuf[1], vbuf[0], vbuf[1], hist, K0, passes, wtot);
+        sorted_in = cur;
     }
+    TAIL_STAMP(4);
 
-    // ---- convert_to_bev: ordered compaction, keypoints (u, v), stamps with the reference's pre-voxelisation
-    // indexing quirk (radar_loader.hpp:123-124).  In the same sweep the keypoints cv::ORB::compute keeps
-    // (radar_loader.hpp:126): it first runs KeyPointsFilter::runByImageBorder(kps, size, edgeThreshold = patch):
-    // Rect(Point(b,b), Point(W-b,W-b)).contains(Point(cvRound(u), cvRound(v))).  Keypoints with
-    // cvRound(u|v) == W - patch are dropped from kp_/desc_ while feat_in_cart_ keeps its columns -- the
-    // reference's index misalignment is reproduced, not repaired.  Both running counts ride in one scan
-    // (low / high half of an int; at most 16384 each) ----
+    // ---- one sweep over the (voxel-sorted) points does the rest:
+    //   * voxel centroids in ascending voxel index: the thread at the head of a run of equal keys sums the run's
+    //     points in f32, in (stable) point order, and divides by float(count) like PCL;
+    //   * convert_to_bev (radar_utils.cpp:382-403): ordered compaction, keypoints (u, v), stamps with the
+    //     reference's pre-voxelisation indexing quirk (radar_loader.hpp:123-124: t_pre at the VOXEL's index);
+    //   * the keypoints cv::ORB::compute keeps (radar_loader.hpp:126): it first runs KeyPointsFilter::
+    //     runByImageBorder(kps, size, edgeThreshold = patch): Rect(Point(b,b), Point(W-b,W-b)).contains(
+    //     Point(cvRound(u), cvRound(v))).  Keypoints with cvRound(u|v) == W - patch are dropped from kp_/desc_ while
+    //     feat_in_cart_ keeps its columns -- the reference's index misalignment is reproduced, not repaired.
+    // The three running counts (voxels, BEV keypoints, ORB keypoints; at most 16384 each) ride in one 64-bit scan.
+    __shared__ unsigned long long carry3;
+    const unsigned int *skeys = kbuf[sorted_in];
+    const unsigned short *svals = vbuf[sorted_in];
     float cmr = (width / 2) * cart_resolution;
     if (width % 2 == 0) cmr = (float)((width / 2 - 0.5) * cart_resolution);
-    if (t == 0) carry = 0;
+    if (t == 0) carry3 = 0ull;
     __syncthreads();
-    for (int base = 0; base < n; base += TAIL_T) {
-        const int i = base + t;
-        bool keep = false, keep_orb = false;
+    for (int base = 0; base < K0; base += TAIL_T) {
+        const int k = base + t;
+        bool valid = false, keep = false, keep_orb = false;
         double x = 0, y = 0;
         float uf = 0.f, vf = 0.f;
-        if (i < n) {
-            x = pts_xy[2 * i]; y = pts_xy[2 * i + 1];
-            const double u = ((double)cmr + y) / (double)cart_resolution;
-            const double v = ((double)cmr - x) / (double)cart_resolution;
-            keep = (0 < u - patch) && (u + patch < width) && (0 < v - patch) && (v + patch < width);
-            uf = (float)u; vf = (float)v;
-            const int ru = __float2int_rn(uf), rv = __float2int_rn(vf);
-            keep_orb = keep && ru >= patch && ru < width - patch && rv >= patch && rv < width - patch;
+        if (k < K0) {
+            if (use_vox) {
+                valid = (k == 0) || (skeys[k] != skeys[k - 1]);
+                if (valid) {
+                    float sx = 0.0f, sy = 0.0f;
+                    int m = 0;
+                    for (int q = k; q < K0 && skeys[q] == skeys[k]; ++q) {
+                        const unsigned int p = svals[q];
+                        sx += pts32[2 * p];
+                        sy += pts32[2 * p + 1];
+                        ++m;
+                    }
+                    const float fn = (float)m;
+                    x = (double)(sx / fn);
+                    y = (double)(sy / fn);
+                }
+            } else {
+                valid = true;
+                x = cart_pre[2 * k]; y = cart_pre[2 * k + 1];
+            }
+            if (valid) {
+                const double u = ((double)cmr + y) / (double)cart_resolution;
+                const double v = ((double)cmr - x) / (double)cart_resolution;
+                keep = (0 < u - patch) && (u + patch < width) && (0 < v - patch) && (v + patch < width);
+                uf = (float)u; vf = (float)v;
+                const int ru = __float2int_rn(uf), rv = __float2int_rn(vf);
+                keep_orb = keep && ru >= patch && ru < width - patch && rv >= patch && rv < width - patch;
+            }
         }
-        int ex, total;
-        BS(tmp).ExclusiveSum((keep ? 1 : 0) | (keep_orb ? 0x10000 : 0), ex, total);
-        const int c0 = carry;
+        unsigned long long total;
+        const unsigned long long ex = fe_block1024_exscan((valid ? 1ull : 0ull) | (keep ? 1ull << 21 : 0ull) | (keep_orb ? 1ull << 42 : 0ull),
+                                                          wtot3, total);
+        const unsigned long long c0 = carry3, at = c0 + ex;
         if (keep) {
-            const int j = (c0 + ex) & 0xffff;
+            const int i = (int)(at & 0x1fffffull), j = (int)((at >> 21) & 0x1fffffull);
             feat[2 * j] = x; feat[2 * j + 1] = y;
             kp[2 * j] = uf; kp[2 * j + 1] = vf;
             t_out[j] = t_pre[i];
         }
         if (keep_orb) {
-            const int j = (c0 + ex) >> 16;
+            const int j = (int)(at >> 42);
             kp_orb[2 * j] = uf; kp_orb[2 * j + 1] = vf;
         }
         __syncthreads();
-        if (t == 0) carry = c0 + total;
+        if (t == 0) carry3 = c0 + total;
         __syncthreads();
     }
-    if (t == 0) { cnt->K = carry & 0xffff; cnt->Kd = carry >> 16; }
+    TAIL_STAMP(5);
+#undef TAIL_STAMP
+    if (t == 0) {
+        if (use_vox) cnt->Kv = (int)(carry3 & 0x1fffffull);
+        cnt->K = (int)((carry3 >> 21) & 0x1fffffull);
+        cnt->Kd = (int)(carry3 >> 42);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -775,15 +868,17 @@ int fe_gather_rows_device(nrs_ctx *ctx, FrontendState &S, int *d_polar)
 }
 
 int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_points, int min_range,
-                      int *d_polar, bool reset_counts, bool force_full)
+                      int *d_polar, bool reset_counts, bool force_full, bool stats_done)
 {
     cudaStream_t st = ctx->stream;
     const size_t N = (size_t)R * C;
     const int nb = stats_blocks(ctx);
     FrameCounts *cnt = S.d_counts;
     if (reset_counts) NRS_CUDA(cudaMemsetAsync(cnt, 0, sizeof(FrameCounts), st));
-    fe_stats_kernel<<<nb, RED_THREADS, 0, st>>>(S.d_fft, R, C, S.d_partial, cnt);       // -> maxg, mean (last block)
-    NRS_LAUNCHED();
+    if (!stats_done) {                       // the extraction pipeline's decode has them already (fe_decode_stats_kernel)
+        fe_stats_kernel<<<nb, RED_THREADS, 0, st>>>(S.d_fft, R, C, S.d_partial, cnt);   // -> maxg, mean (last block)
+        NRS_LAUNCHED();
+    }
     fe_h_kernel<<<nb, RED_THREADS, 0, st>>>(S.d_fft, R, C, cnt, S.d_h, S.d_partial);     // -> h, mean_h (last block)
     NRS_LAUNCHED();
     const bool sub = S.have_thresh && !force_full;
@@ -792,8 +887,8 @@ int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_poin
     if (sub) {
         fe_prep_sub_kernel<<<nb, RED_THREADS, 0, st>>>(S.d_h, N, cnt, S.d_claim);
         NRS_LAUNCHED();
-        thrust::counting_iterator<unsigned int> ids(0u);
-        NRS_CUDA(cub::DeviceSelect::If(S.d_cub, need, ids, S.d_vals[0], &cnt->n_sub, (int)N, SubSelect{S.d_h, S.d_thresh, cnt}, st));
+        SubPairIn pairs(thrust::counting_iterator<unsigned int>(0u), SubLoad{S.d_h});
+        NRS_CUDA(cub::DeviceSelect::If(S.d_cub, need, pairs, S.d_sel, &cnt->n_sub, (int)N, SubSelect{S.d_thresh, cnt}, st));
         g_launches.fetch_add(1, std::memory_order_relaxed);
         {   // opt in to the cluster sort's 146 KB of dynamic shared memory once per device
             static std::mutex cfg_mu;
@@ -801,11 +896,11 @@ int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_poin
             std::lock_guard<std::mutex> lk(cfg_mu);
             const int dv = (ctx->device >= 0 && ctx->device < 64) ? ctx->device : -1;
             if (dv < 0 || !configured[dv]) {
-                NRS_CUDA(cudaFuncSetAttribute(fe_subsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SubSortSmem)));
+                NRS_CUDA(cudaFuncSetAttribute(fe_subsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
                 if (dv >= 0) configured[dv] = true;
             }
         }
-        fe_subsort_kernel<<<SS_CL, SS_T, sizeof(SubSortSmem), st>>>(S.d_h, S.d_vals[0], cnt, S.d_keys[1], S.d_vals[1]);
+        fe_subsort_kernel<<<SS_CL, SS_T, SS_SMEM, st>>>(S.d_sel, cnt, S.d_keys[1], S.d_vals[1]);
         NRS_LAUNCHED();
     } else {
         fe_keys_kernel<<<nb, RED_THREADS, 0, st>>>(S.d_h, N, cnt, S.d_keys[0], S.d_vals[0], S.d_claim);
@@ -847,20 +942,19 @@ int fe_points_voxel_bev_device(nrs_ctx *ctx, FrontendState &S, nrs_frame *f)
             if (dv >= 0) configured[dv] = true;
         }
     }
-    // voxel centroids are staged in d_keys[0] (free once the keypoints are known)
-    double *vox = reinterpret_cast<double *>(S.d_keys[0]);
     fe_tail_kernel<<<1, TAIL_T, FE_TAIL_SMEM, st>>>(S.d_rowcount, S.d_stage, S.R, S.C, f->d_polar, S.d_counts, S.d_cossin, S.d_times, p.radar_resolution,
                                                    p.use_voxelization, (float)p.voxel_size, FE_KP_CAP, f->d_cart_pre,
-                                                   f->d_t_pre, S.d_pts32, vox, p.cart_resolution, p.cart_pixel_width,
+                                                   f->d_t_pre, S.d_pts32, p.cart_resolution, p.cart_pixel_width,
                                                    p.patch_size, f->d_feat, f->d_kp, f->d_t, f->d_kp_orb);
     NRS_LAUNCHED();
     return NRS_OK;
 }
 
-int fe_decode_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int pitch)
+int fe_decode_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int pitch, bool with_stats)
 {
     dim3 grid((C + 255) / 256, R);
-    fe_decode_kernel<<<grid, 256, 0, ctx->stream>>>(S.d_raw, pitch, R, C, S.d_fft);
+    if (with_stats) fe_decode_stats_kernel<<<R, RED_THREADS, 0, ctx->stream>>>(S.d_raw, pitch, R, C, S.d_lut, S.d_fft, S.d_partial, S.d_counts);
+    else fe_decode_kernel<<<grid, 256, 0, ctx->stream>>>(S.d_raw, pitch, R, C, S.d_fft);
     NRS_LAUNCHED();
     return NRS_OK;
 }
@@ -872,8 +966,8 @@ size_t fe_cub_bytes(size_t N)
                                               (unsigned int *)nullptr, (int)N);
     cub::DeviceScan::InclusiveSum(nullptr, b, (unsigned int *)nullptr, (unsigned int *)nullptr, (int)N);
     size_t d = 0;
-    thrust::counting_iterator<unsigned int> ids(0u);
-    cub::DeviceSelect::If(nullptr, d, ids, (unsigned int *)nullptr, (int *)nullptr, (int)N, SubSelect{nullptr, nullptr, nullptr});
+    SubPairIn pairs(thrust::counting_iterator<unsigned int>(0u), SubLoad{nullptr});
+    cub::DeviceSelect::If(nullptr, d, pairs, (SubPair *)nullptr, (int *)nullptr, (int)N, SubSelect{nullptr, nullptr});
     return std::max(std::max(a, d), std::max(b, c)) + 256;
 }
 

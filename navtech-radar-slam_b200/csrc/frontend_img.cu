@@ -32,12 +32,12 @@
 namespace nrs {
 
 int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_points, int min_range, int *d_polar,
-                      bool reset_counts = true, bool force_full = false);
+                      bool reset_counts = true, bool force_full = false, bool stats_done = false);
 int fe_cen2018_taps_host(int sigma_gauss, float *taps);
 int fe_cen2018_device(nrs_ctx *ctx, FrontendState &S, int R, int C, float zq, int sigma_gauss, int min_range,
                       int *d_polar, bool reset_counts, bool keep_y);
 int fe_points_voxel_bev_device(nrs_ctx *ctx, FrontendState &S, nrs_frame *f);
-int fe_decode_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int pitch);
+int fe_decode_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int pitch, bool with_stats);
 size_t fe_cub_bytes(size_t N);
 
 // cv::getGaussianKernel(7, 2, CV_32F) of OpenCV 4.13 (bit patterns; bit-exact softdouble evaluation)
@@ -200,43 +200,71 @@ __global__ void fe_brief_kernel(const unsigned char *__restrict__ blur, int W, c
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool lex_less(int d1, int i1, int d2, int i2) { return d1 < d2 || (d1 == d2 && i1 < i2); }
 
+constexpr int MATCH_PARTS = 4;           // warps that share one query descriptor (each scans a quarter of the train set)
+constexpr int MATCH_QPB = 8 / MATCH_PARTS;   // queries per 256-thread block
+
 __global__ void __launch_bounds__(256)
 fe_match_kernel(const unsigned char *__restrict__ qdesc, int nq, const unsigned char *__restrict__ tdesc, int nt_host,
                 const FrameCounts *__restrict__ tcnt, float nndr, int *__restrict__ best_train,
                 unsigned char *__restrict__ good)
 {
-    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (q >= nq) return;
+    // BFMatcher(NORM_HAMMING).knnMatch(k = 2) of one query row: the two smallest (distance, train index) pairs.
+    // Four warps scan a quarter of the train descriptors each (the scan is a chain of dependent loads: shorter
+    // chains, four times the warps in flight), lane 0..3 of the first warp then merge the four partial answers.
+    __shared__ int4 part_res[MATCH_QPB][MATCH_PARTS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ql = warp / MATCH_PARTS, part = warp % MATCH_PARTS;
+    const int q = blockIdx.x * MATCH_QPB + ql;
     const int nt = tcnt ? tcnt->Kd : nt_host;            // fused pair call: the train frame's counts are still on the device
-    const uint4 *qp = reinterpret_cast<const uint4 *>(qdesc + (size_t)q * 32);
-    const uint4 qa = qp[0], qb = qp[1];
-    int d0 = 0x7fffffff, i0 = 0x7fffffff, d1 = 0x7fffffff, i1 = 0x7fffffff;
-    for (int t = lane; t < nt; t += 32) {
-        const uint4 *tp = reinterpret_cast<const uint4 *>(tdesc + (size_t)t * 32);
-        const uint4 ta = tp[0], tb = tp[1];
-        const int d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
-                      __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
-        if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = t; }
-        else if (d < d1) { d1 = d; i1 = t; }
+    if (q < nq) {
+        const uint4 *qp = reinterpret_cast<const uint4 *>(qdesc + (size_t)q * 32);
+        const uint4 qa = qp[0], qb = qp[1];
+        const int chunk = (((nt + MATCH_PARTS - 1) / MATCH_PARTS) + 31) & ~31;
+        const int t0 = part * chunk, t1 = min(nt, t0 + chunk);
+        int d0 = 0x7fffffff, i0 = 0x7fffffff, d1 = 0x7fffffff, i1 = 0x7fffffff;
+        for (int t = t0 + lane; t < t1; t += 32) {
+            const uint4 *tp = reinterpret_cast<const uint4 *>(tdesc + (size_t)t * 32);
+            const uint4 ta = tp[0], tb = tp[1];
+            const int d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
+                          __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+            if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = t; }
+            else if (d < d1) { d1 = d; i1 = t; }
+        }
+        // the part's best, then its second = best of (every lane's best except the winner's) U (the winner's second)
+        int bd = d0, bi = i0;
+        for (int o = 16; o > 0; o >>= 1) {
+            const int od = __shfl_xor_sync(0xffffffffu, bd, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (lex_less(od, oi, bd, bi)) { bd = od; bi = oi; }
+        }
+        const bool winner = (i0 == bi);
+        int sd = winner ? d1 : d0, si = winner ? i1 : i0;
+        for (int o = 16; o > 0; o >>= 1) {
+            const int od = __shfl_xor_sync(0xffffffffu, sd, o), oi = __shfl_xor_sync(0xffffffffu, si, o);
+            if (lex_less(od, oi, sd, si)) { sd = od; si = oi; }
+        }
+        if (lane == 0) part_res[ql][part] = make_int4(bd, bi, sd, si);
     }
-    // global best, then global second = best of (everyone's best except the winner's) U (winner's second)
-    int bd = d0, bi = i0;
-    for (int o = 16; o > 0; o >>= 1) {
-        const int od = __shfl_xor_sync(0xffffffffu, bd, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (lex_less(od, oi, bd, bi)) { bd = od; bi = oi; }
-    }
-    const bool winner = (i0 == bi);
-    int sd = winner ? d1 : d0, si = winner ? i1 : i0;
-    for (int o = 16; o > 0; o >>= 1) {
-        const int od = __shfl_xor_sync(0xffffffffu, sd, o), oi = __shfl_xor_sync(0xffffffffu, si, o);
-        if (lex_less(od, oi, sd, si)) { sd = od; si = oi; }
-    }
-    if (lane == 0) {
-        best_train[q] = bi;
-        // radar_loader.hpp:159-167; rows with fewer than two neighbours are skipped (the reference
-        // dereferences knn_matches[j][1] -- undefined behaviour -- when curr has a single keypoint)
-        good[q] = (nt >= 2) && ((float)bd < nndr * (float)sd);
+    __syncthreads();
+    if (q < nq && part == 0 && lane < MATCH_PARTS) {
+        const int4 r = part_res[ql][lane];
+        const unsigned int m = (1u << MATCH_PARTS) - 1u;
+        int bd = r.x, bi = r.y;
+        for (int o = MATCH_PARTS / 2; o > 0; o >>= 1) {
+            const int od = __shfl_xor_sync(m, bd, o), oi = __shfl_xor_sync(m, bi, o);
+            if (lex_less(od, oi, bd, bi)) { bd = od; bi = oi; }
+        }
+        const bool winner = (r.y == bi);
+        int sd = winner ? r.z : r.x, si = winner ? r.w : r.y;
+        for (int o = MATCH_PARTS / 2; o > 0; o >>= 1) {
+            const int od = __shfl_xor_sync(m, sd, o), oi = __shfl_xor_sync(m, si, o);
+            if (lex_less(od, oi, sd, si)) { sd = od; si = oi; }
+        }
+        if (lane == 0) {
+            best_train[q] = bi;
+            // radar_loader.hpp:159-167; rows with fewer than two neighbours are skipped (the reference
+            // dereferences knn_matches[j][1] -- undefined behaviour -- when curr has a single keypoint)
+            good[q] = (nt >= 2) && ((float)bd < nndr * (float)sd);
+        }
     }
 }
 
@@ -291,7 +319,7 @@ static void frontend_free(void *p)
     void *dev[] = {S->d_theta, S->d_sx, S->d_pattern, S->d_raw, S->d_fft, S->d_h, S->d_keys[0], S->d_keys[1],
                    S->d_vals[0], S->d_vals[1], S->d_claim, S->d_incr, S->d_partial, S->d_cart, S->d_rowbuf,
                    S->d_blur, S->d_cub, S->d_tables, S->d_counts,
-                   S->d_pts32, S->d_rowcount, S->d_thresh, S->d_stage};
+                   S->d_pts32, S->d_rowcount, S->d_thresh, S->d_stage, S->d_sel, S->d_lut};
     for (void *d : dev) if (d) cudaFree(d);
     for (auto &g : S->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     S->graphs.clear();
@@ -340,16 +368,21 @@ static int frontend_state(nrs_ctx *ctx, const nrs_extract_params *p, int R, int 
     rc |= dmalloc(&S->d_raw, (size_t)R * pitch); rc |= dmalloc(&S->d_fft, N); rc |= dmalloc(&S->d_h, N);
     rc |= dmalloc(&S->d_keys[0], N); rc |= dmalloc(&S->d_keys[1], N); rc |= dmalloc(&S->d_vals[0], N);
     rc |= dmalloc(&S->d_vals[1], N); rc |= dmalloc(&S->d_claim, N); rc |= dmalloc(&S->d_incr, N);
-    rc |= dmalloc(&S->d_partial, (size_t)ctx->sm_count * 8 + 8);
+    rc |= dmalloc(&S->d_partial, std::max((size_t)ctx->sm_count * 8, (size_t)R) + 8);
     rc |= dmalloc(&S->d_cart, WW); rc |= dmalloc(&S->d_rowbuf, WW); rc |= dmalloc(&S->d_blur, WW);
     S->cub_bytes = fe_cub_bytes(N);
     rc |= dmalloc((unsigned char **)&S->d_cub, S->cub_bytes);
     rc |= dmalloc(&S->d_tables, 1); rc |= dmalloc(&S->d_counts, 1);
     rc |= dmalloc(&S->d_pts32, 2 * FE_KP_CAP); rc |= dmalloc(&S->d_rowcount, FE_MAX_AZ);
-    rc |= dmalloc(&S->d_thresh, 1); rc |= dmalloc(&S->d_stage, N);
+    rc |= dmalloc(&S->d_thresh, 1); rc |= dmalloc(&S->d_stage, N); rc |= dmalloc(&S->d_sel, N); rc |= dmalloc(&S->d_lut, 256);
     if (rc) return rc;
     NRS_CUDA(cudaMallocHost((void **)&S->h_counts, sizeof(FrameCounts)));
     NRS_CUDA(cudaMallocHost((void **)&S->h_tables, sizeof(AzTables)));
+    {
+        float lut[256];
+        for (int b = 0; b < 256; ++b) lut[b] = (float)((double)b / 255.0);
+        NRS_CUDA(cudaMemcpy(S->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+    }
     S->d_az = S->d_tables->az; S->d_azsort = S->d_tables->azs; S->d_azidx = S->d_tables->azi;      // address arithmetic only
     S->d_cossin = S->d_tables->cossin; S->d_times = S->d_tables->times;
 
@@ -610,7 +643,8 @@ int extract_enqueue(nrs_ctx *ctx, FrontendState *S, nrs_frame *f, int R, int C, 
     const int W = p->cart_pixel_width;
     int rc;
     NRS_CUDA(cudaMemsetAsync(S->d_counts, 0, sizeof(FrameCounts), st));
-    if ((rc = fe_decode_device(ctx, *S, R, C, row_pitch))) return rc;
+    const bool cen2019 = p->keypoint_extraction != 1;
+    if ((rc = fe_decode_device(ctx, *S, R, C, row_pitch, cen2019))) return rc;      // cen2019: sum(f), max(g) in the same pass
     // fork: Cartesian image branch (radar_utils.cpp:227-316 + ORB's blur) on the second stream
     cudaStream_t si = S->st_img;
     NRS_CUDA(cudaEventRecord(S->ev_fork, st));
@@ -631,7 +665,7 @@ int extract_enqueue(nrs_ctx *ctx, FrontendState *S, nrs_frame *f, int R, int C, 
     // keypoint branch on the context stream
     rc = (p->keypoint_extraction == 1)
              ? fe_cen2018_device(ctx, *S, R, C, p->zq, p->sigma_gauss, p->min_range, nullptr, false, false)
-             : fe_cen2019_device(ctx, *S, R, C, p->max_points, p->min_range, nullptr, false, force_full);
+             : fe_cen2019_device(ctx, *S, R, C, p->max_points, p->min_range, nullptr, false, force_full, true);
     if (rc) { cudaStreamSynchronize(si); return rc; }
     if ((rc = fe_points_voxel_bev_device(ctx, *S, f))) { cudaStreamSynchronize(si); return rc; }
     NRS_CUDA(cudaStreamWaitEvent(st, S->ev_join, 0));           // join
@@ -802,7 +836,7 @@ int nrs_orora_pair(nrs_ctx *ctx, const nrs_frame *prev, const uint8_t *raw, int 
         if ((rc = extract_run(ctx, S, f, R, C, row_pitch, p, H.n_sorted, attempt == 1))) { frame_release_locked(f); return rc; }
         NRS_CUDA(cudaMemsetAsync(m.n, 0, 4, st));
         if (nq > 0) {
-            fe_match_kernel<<<(nq * 32 + 255) / 256, 256, 0, st>>>(prev->d_desc, nq, f->d_desc, 0, S->d_counts, p->nndr, m.best, m.good);
+            fe_match_kernel<<<(nq + MATCH_QPB - 1) / MATCH_QPB, 256, 0, st>>>(prev->d_desc, nq, f->d_desc, 0, S->d_counts, p->nndr, m.best, m.good);
             NRS_LAUNCHED();
             fe_match_gather_kernel<<<1, 1024, 0, st>>>(m.best, m.good, nq, prev->d_feat, f->d_feat, prev->d_t, f->d_t, cap, m.q, m.t,
                                                        m.p, m.c, m.pt, m.ct, m.n);
@@ -838,6 +872,16 @@ int nrs_frame_destroy(nrs_frame *f)
         else { cudaSetDevice(f->ctx->device); cudaFree(f->d_block); }
     }
     delete f;
+    return NRS_OK;
+}
+
+int nrs_frontend_tail_times(nrs_ctx *ctx, uint64_t *t_ns8)
+{
+    NRS_CHECK_ARG(ctx && t_ns8, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    FrontendState *S = static_cast<FrontendState *>(ctx->frontend);
+    NRS_CHECK_ARG(S && S->h_counts, "no extraction ran on this context yet");
+    for (int i = 0; i < 8; ++i) t_ns8[i] = S->h_counts->t_tail[i];
     return NRS_OK;
 }
 
@@ -939,7 +983,7 @@ int nrs_match(nrs_ctx *ctx, const nrs_frame *prev, const nrs_frame *curr, float 
     if (rc) return rc;
     unsigned char *b = ctx->scratch[5].as<unsigned char>();
     cudaStream_t st = ctx->stream;
-    fe_match_kernel<<<(nq * 32 + 255) / 256, 256, 0, st>>>(prev->d_desc, nq, curr->d_desc, nt, nullptr, nndr,
+    fe_match_kernel<<<(nq + MATCH_QPB - 1) / MATCH_QPB, 256, 0, st>>>(prev->d_desc, nq, curr->d_desc, nt, nullptr, nndr,
                                                           (int *)(b + o_best), b + o_good);
     NRS_LAUNCHED();
     fe_match_gather_kernel<<<1, 1024, 0, st>>>((int *)(b + o_best), b + o_good, nq, prev->d_feat, curr->d_feat,

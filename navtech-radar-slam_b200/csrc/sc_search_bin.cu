@@ -18,17 +18,18 @@
 // database is 2.56 MB of records instead of 96 MB of f64 (or 55 MB of f32 filter records).
 //
 // Kernel sc_search_bin_kernel, ONE launch for Q >= 1 queries.  Work is cut into tiles
-// (query, chunk of keyframes); a 16-warp CTA prepares the tile's query in shared memory (masks,
-// 1/sqrt(n) per column, the count vector as byte-packed sliding windows) and its warps take one
-// keyframe each:
+// (query, chunk of keyframes); a 12-warp CTA (BT = 384, two CTAs per SM) prepares the tile's query in
+// shared memory (masks, 1/sqrt(n) per column, the count vector as four byte-shifted copies of the
+// byte-packed, doubled window) and its warps take one keyframe each:
 //   fastAlignUsingVkey (:93-113): argmin_s |vq - shift(vk, s)| == argmax_s sum_j n_k[j] n_q[(j+s)%60];
-//        lane l holds the query windows of shifts 2l, 2l+1 in registers and runs 2 x 15 DP4A against
-//        the keyframe's counts (broadcast from shared memory).  Integer, exact; shifts that tie on the
-//        integer score are re-evaluated in the reference's f64 order (certify_shift_bin), because
+//        lane l scores shifts l and l + 32 (the latter for l < 28) from ONE 15-word register window of
+//        the query counts -- the two shifts read the same words, rotated by 8 -- with 2 x 15 DP4A
+//        against the keyframe's byte-packed counts (broadcast from shared memory).  Integer, exact;
+//        shifts that tie on the integer score are re-evaluated in the reference's f64 order (certify_shift_bin), because
 //        rounding decides between them there.
 //   distDirectSC x 7 shifts (:69-90,123-146): lane l owns key columns 2l, 2l+1; per shift slot and
-//        column one AND + POPC + two multiplies by the tabulated 1/sqrt(n); 9 shuffles reduce the 7
-//        partial sums.  f32, error <= 12 * 2^-24 per distance (terms are <= 1, see bound C in
+//        column one AND + POPC + two multiplies by the tabulated 1/sqrt(n); the 7 partial sums are
+//        reduced by REDUX.SUM on 2^-24 fixed point (NRS_SC_BIN_REDUX=0: a shuffle tree).  f32, error <= 12 * 2^-24 per distance (terms are <= 1, see bound C in
 //        sc_kernels.cu; the same 2^-17 margins are used).
 //   arg-min over keyframes: pruned exactly like the general kernel -- a keyframe whose lower bound
 //        exceeds the smallest upper bound seen (CTA-wide in shared memory, per query in global memory)

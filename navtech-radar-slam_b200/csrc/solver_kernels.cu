@@ -33,6 +33,7 @@ namespace {
 
 constexpr int MAXN = 1024;      // one 32-bit adjacency word per lane
 constexpr int WORDS = 32;
+constexpr int FUSE_ORDER_MAXN = 512;   // largest N whose raw + permuted adjacency matrices share one CTA's shared memory
 constexpr int SROW = 33;        // shared-memory row stride of the adjacency matrix (words): thread u reads row u,
                                 // an odd stride spreads a warp's 32 rows over 32 banks
 
@@ -77,24 +78,26 @@ __global__ void __launch_bounds__(256)
 orora_adjacency_kernel(const double *__restrict__ src, const double *__restrict__ tgt, int N,
                        double beta, uint32_t *__restrict__ adj)
 {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = gid / WORDS, w = gid % WORDS;
+    // one warp per (row i, word w), one pair (i, j = 32 w + lane) per thread, the word assembled by a ballot:
+    // the f64 square roots and divisions of the ~N^2 tests run on N * ceil(N/32) * 32 threads instead of N * 32
+    const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int i = wg / WORDS, w = wg % WORDS;
     if (i >= N) return;
-    uint32_t bits = 0;
-    const double six = src[2 * i], siy = src[2 * i + 1], tix = tgt[2 * i], tiy = tgt[2 * i + 1];
-    for (int b = 0; b < 32; ++b) {
-        const int j = w * 32 + b;
-        if (j >= N || j == i) continue;
+    const int j = w * 32 + lane;
+    bool ok = false;
+    if (j < N && j != i) {
         // nonminimal_solver.hpp:185-222 TIM (sign is irrelevant for the norms), :233-264 test
-        const double sx = src[2 * j] - six, sy = src[2 * j + 1] - siy;
-        const double tx = tgt[2 * j] - tix, ty = tgt[2 * j + 1] - tiy;
+        const double sx = src[2 * j] - src[2 * i], sy = src[2 * j + 1] - src[2 * i + 1];
+        const double tx = tgt[2 * j] - tgt[2 * i], ty = tgt[2 * j + 1] - tgt[2 * i + 1];
         const double v1 = sqrt(sx * sx + sy * sy + 0.0);
         const double v2 = sqrt(tx * tx + ty * ty + 0.0);
         const bool in_f = fabs(v2 / v1 - 1.0) <= beta * (1.0 / v1);
         const bool in_r = fabs(v1 / v2 - 1.0) <= beta * (1.0 / v2);
-        if (in_f && in_r) bits |= 1u << b;
+        ok = in_f && in_r;
     }
-    adj[i * WORDS + w] = bits;
+    const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) adj[i * WORDS + w] = bits;
 }
 
 // ---- K8 ---------------------------------------------------------------------------------------
@@ -183,7 +186,8 @@ __device__ void take_clique(const uint16_t *__restrict__ ord, int n, int *__rest
 constexpr int CLQ_THREADS = 1024;
 
 __global__ void __launch_bounds__(CLQ_THREADS)
-orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restrict__ stackP,
+orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, int fuse_order, int *__restrict__ perm_out,
+                    int *__restrict__ inv_out, int *__restrict__ n_edges, uint32_t *__restrict__ stackP,
                     uint16_t *__restrict__ ordS, uint16_t *__restrict__ colS, int *__restrict__ cur,
                     int *__restrict__ best, int *__restrict__ idxS, SolverInfoDev *__restrict__ info,
                     long long node_limit, uint32_t *__restrict__ misStack)
@@ -194,7 +198,85 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, uint32_t *__restri
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     STAMP(0);
     const int nthr = blockDim.x;
-    for (int i = tid; i < N * WORDS; i += nthr) sadj[(i >> 5) * SROW + (i & 31)] = adjp[i];
+    if (fuse_order) {
+        // `adjp` is the raw adjacency matrix: search order (non-increasing degree, ties by index:
+        // oracle/solver_ref.c orora_max_clique) and the permuted matrix are made here, thread per vertex, the raw
+        // rows staged behind sadj (N <= FUSE_ORDER_MAXN) -- what orora_order_kernel + orora_permute_kernel do in two
+        // more launches for larger N
+        uint32_t *raw = sadj + N * SROW;
+        __shared__ unsigned short s_cnt[FUSE_ORDER_MAXN / 32][FUSE_ORDER_MAXN];   // [warp of vertices][degree]
+        __shared__ int s_base[FUSE_ORDER_MAXN];                                  // vertices of larger degree
+        __shared__ unsigned short s_perm[FUSE_ORDER_MAXN];
+        __shared__ int s_wtot[32];
+        __shared__ int s_esum;
+        const int nwr = (N + 31) >> 5;
+        if (tid == 0) s_esum = 0;
+        for (int i = tid; i < N * nwr; i += nthr) { const int r = i / nwr, w = i - r * nwr; raw[r * SROW + w] = adjp[r * WORDS + w]; }
+        for (int i = tid; i < nwr * FUSE_ORDER_MAXN / 2; i += nthr) reinterpret_cast<uint32_t *>(&s_cnt[0][0])[i] = 0u;
+        __syncthreads();
+        // rank = (vertices of larger degree) + (vertices of equal degree and lower index): a stable counting sort by
+        // degree -- per-warp counts of every degree value (match.any inside the warp), running sums over the warps,
+        // one block scan over the degree values in descending order
+        int d = 0, in_warp = 0;
+        if (tid < nwr * 32) {
+            if (tid < N)
+                for (int w = 0; w < nwr; ++w) d += __popc(raw[tid * SROW + w]);
+            const unsigned int peers = __match_any_sync(0xffffffffu, tid < N ? d : -1);
+            in_warp = __popc(peers & ((1u << lane) - 1u));
+            if (tid < N && in_warp == 0) s_cnt[warp][d] = (unsigned short)__popc(peers);
+            int dsum = (tid < N) ? d : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+            if (lane == 0 && dsum) atomicAdd(&s_esum, dsum);
+        }
+        __syncthreads();
+        int tot = 0;
+        const int dd = N - 1 - tid;                               // thread k looks after degree N - 1 - k (descending)
+        if (tid < N) {
+            for (int w = 0; w < nwr; ++w) { const int c = s_cnt[w][dd]; s_cnt[w][dd] = (unsigned short)tot; tot += c; }
+        }
+        {   // exclusive prefix of tot over the block (warp shuffles, 32 warp totals through shared memory)
+            int inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int up = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += up; }
+            if (lane == 31) s_wtot[warp] = inc;
+            __syncthreads();
+            const int wt = (lane < (nthr >> 5)) ? s_wtot[lane] : 0;
+            int winc = wt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int up = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += up; }
+            const int ex = __shfl_sync(0xffffffffu, winc - wt, warp) + inc - tot;
+            if (tid < N) s_base[dd] = ex;
+        }
+        __syncthreads();
+        if (tid < N) {
+            const int rank = s_base[d] + s_cnt[warp][d] + in_warp;
+            s_perm[rank] = (unsigned short)tid;
+            perm_out[rank] = tid;
+            inv_out[tid] = rank;
+        }
+        if (tid == 0) *n_edges = s_esum / 2;
+        __syncthreads();
+        // permuted matrix: one warp per row, lane l makes bit l of every word -- bit perm[32 w + l] of the raw row --
+        // and a ballot assembles the word
+        for (int ip = warp; ip < N; ip += nthr >> 5) {
+            const uint32_t *ri = raw + (int)s_perm[ip] * SROW;
+            for (int w = 0; w < nwr; ++w) {
+                const int jp = w * 32 + lane;
+                bool bit = false;
+                if (jp < N) { const int j = s_perm[jp]; bit = (ri[j >> 5] >> (j & 31)) & 1u; }
+                const uint32_t word = __ballot_sync(0xffffffffu, bit);
+                if (lane == 0) sadj[ip * SROW + w] = word;
+            }
+            if (lane >= nwr) sadj[ip * SROW + lane] = 0u;           // the words beyond N stay empty
+        }
+    } else {
+        for (int i = tid; i < N * WORDS; i += nthr) sadj[(i >> 5) * SROW + (i & 31)] = adjp[i];
+    }
+    // the launch carries CLQ_THREADS threads for the load phase; the search keeps one thread per vertex (whole warps,
+    // at least two), the rest leave here (CTA barriers count the remaining threads only)
+    __syncthreads();                                          // the matrix is complete before anyone leaves
+    if (tid >= max(64, (N + 31) & ~31)) return;
     // all-vertices mask, word `lane`
     uint32_t full = 0;
     {
@@ -745,6 +827,132 @@ __device__ double cote_axis(TailSmem &sm, int M, unsigned char *inl_and, int TT)
     return est;
 }
 
+// Both axes at once for M <= COTE2_MAXM (the usual case: a few hundred clique members): axis 1 lives in the upper
+// halves of the endpoint arrays (X, alpha in sm.c / sm.d), every phase handles the two axes side by side -- the
+// barriers, the sequential running-sum loop and the block reductions are paid once instead of twice.  Values and
+// orders of all sums are those of cote_axis.
+constexpr int COTE2_MAXM = MAXN / 2;
+__device__ void cote_axes2(TailSmem &sm, int M, unsigned char *inl_and, int TT, double &est_x, double &est_y)
+{
+    const int t = threadIdx.x;
+    const int nwl = TT >> 5;
+    const int n2 = 2 * M;
+    constexpr int O = MAXN;                // offset of axis 1 in the 2 * MAXN arrays
+    for (int e = t; e < n2; e += TT) {
+        const int i = e >> 1;
+        const bool lo = (e & 1) == 0;
+        sm.key[e] = lo ? sm.a[i] - sm.b[i] : sm.a[i] + sm.b[i];
+        sm.key[O + e] = lo ? sm.c[i] - sm.d[i] : sm.c[i] + sm.d[i];
+    }
+    __syncthreads();
+    int rk0[2], rk1[2];
+    {
+        int cnt = 0;
+        for (int e = t; e < n2; e += TT, ++cnt) {
+            const double k0 = sm.key[e], k1 = sm.key[O + e];
+            int r0 = 0, r1 = 0;
+            for (int j = 0; j < n2; ++j) {
+                const double a0 = sm.key[j], a1 = sm.key[O + j];
+                r0 += (a0 < k0) || (a0 == k0 && j < e);
+                r1 += (a1 < k1) || (a1 == k1 && j < e);
+            }
+            rk0[cnt] = r0; rk1[cnt] = r1;
+        }
+    }
+    double tot0, tot1;
+    {
+        double x0 = (t < M) ? sm.b[t] : 0.0, x1 = (t < M) ? sm.d[t] : 0.0, x2 = 0, x3 = 0;
+        block_sum4(x0, x1, x2, x3, sm.red, nwl);
+        tot0 = x0; tot1 = x1;             // ranges.sum() (:566), per axis
+    }
+    {
+        int cnt = 0;
+        for (int e = t; e < n2; e += TT, ++cnt) {
+            const int i = e >> 1;
+            const bool lo = (e & 1) == 0;
+            const double eps = lo ? 1.0 : -1.0;
+            {
+                const double r = sm.b[i], x = sm.a[i];
+                const double wgt = 1.0 / (r * r);
+                const int d = rk0[cnt];
+                sm.s1[d] = eps * wgt; sm.s2[d] = eps * wgt * x; sm.s3[d] = eps * r; sm.s4[d] = eps * x; sm.s5[d] = eps * x * x;
+                sm.si[d] = lo ? 1 : -1;
+            }
+            {
+                const double r = sm.d[i], x = sm.c[i];
+                const double wgt = 1.0 / (r * r);
+                const int d = O + rk1[cnt];
+                sm.s1[d] = eps * wgt; sm.s2[d] = eps * wgt * x; sm.s3[d] = eps * r; sm.s4[d] = eps * x; sm.s5[d] = eps * x * x;
+                sm.si[d] = lo ? 1 : -1;
+            }
+        }
+    }
+    __syncthreads();
+    // running sums in sorted order, sequentially like the reference's loop: ten f64 chains and two int chains
+    if (t < 12) {
+        const int ax = t / 6, q = t % 6, o = ax * O;
+        if (q == 5) {
+            int acc = 0;
+            for (int e = 0; e < n2; ++e) { acc += sm.si[o + e]; sm.si[o + e] = acc; }
+        } else {
+            double *arr = (q == 0 ? sm.s1 : q == 1 ? sm.s2 : q == 2 ? sm.s3 : q == 3 ? sm.s4 : sm.s5) + o;
+            double acc = 0.0;
+            for (int e = 0; e < n2; ++e) { acc = acc + arr[e]; arr[e] = acc; }
+        }
+    }
+    __syncthreads();
+    double bc[2] = {INFINITY, INFINITY}, bh[2] = {0.0, 0.0};
+    int bi[2] = {0x7fffffff, 0x7fffffff};
+    for (int e = t; e < n2; e += TT) {
+#pragma unroll
+        for (int ax = 0; ax < 2; ++ax) {
+            const int o = ax * O + e;
+            const double x_hat = sm.s2[o] / sm.s1[o];
+            const double residual = sm.si[o] * x_hat * x_hat + sm.s5[o] - 2 * sm.s4[o] * x_hat;
+            const double cost = residual + ((ax ? tot1 : tot0) - sm.s3[o]);
+            if (cost < bc[ax] || (e == 0 && !(cost >= cost))) { bc[ax] = cost; bh[ax] = x_hat; bi[ax] = e; }
+        }
+    }
+    {
+        const int lane = t & 31, warp = t >> 5;
+#pragma unroll
+        for (int ax = 0; ax < 2; ++ax)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double oc = __shfl_xor_sync(0xffffffffu, bc[ax], o);
+                const double oh = __shfl_xor_sync(0xffffffffu, bh[ax], o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi[ax], o);
+                if (oc < bc[ax] || (oc == bc[ax] && oi < bi[ax])) { bc[ax] = oc; bh[ax] = oh; bi[ax] = oi; }
+            }
+        __syncthreads();
+        if (lane == 0) {
+            sm.red[warp] = bc[0]; sm.red[32 + warp] = bh[0]; sm.redi[warp] = bi[0];
+            sm.red[64 + warp] = bc[1]; sm.red[96 + warp] = bh[1]; sm.tag[warp] = bi[1];
+        }
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int ax = 0; ax < 2; ++ax) {
+                double c = lane < nwl ? sm.red[64 * ax + lane] : INFINITY, hh = lane < nwl ? sm.red[64 * ax + 32 + lane] : 0.0;
+                int ii = lane < nwl ? (ax ? sm.tag[lane] : sm.redi[lane]) : 0x7fffffff;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double oc = __shfl_xor_sync(0xffffffffu, c, o);
+                    const double oh = __shfl_xor_sync(0xffffffffu, hh, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, ii, o);
+                    if (oc < c || (oc == c && oi < ii)) { c = oc; hh = oh; ii = oi; }
+                }
+                if (lane == 0) sm.red[160 + ax] = hh;
+            }
+        }
+        __syncthreads();
+    }
+    est_x = sm.red[160];
+    est_y = sm.red[161];
+    if (t < M) inl_and[t] = inl_and[t] && (fabs(sm.a[t] - est_x) <= sm.b[t]) && (fabs(sm.c[t] - est_y) <= sm.d[t]);   // :658
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(TT_MAX)
 orora_tail_kernel(const double *__restrict__ src, const double *__restrict__ tgt, int N,
                   const int *__restrict__ perm, const int *__restrict__ best,
@@ -829,6 +1037,8 @@ orora_tail_kernel(const double *__restrict__ src, const double *__restrict__ tgt
             double h00 = (t < M) ? sx * wgt * dx : 0.0, h10 = (t < M) ? sy * wgt * dx : 0.0;
             double h01 = (t < M) ? sx * wgt * dy : 0.0, h11 = (t < M) ? sy * wgt * dy : 0.0;
             double c0 = (t < M) ? cterm : 0.0;
+            // this iteration's thresholds depend on mu only: issued ahead of the reduction, they overlap with it
+            const double th1 = (mu + 1) / mu * nb2, th2 = mu / (mu + 1) * nb2, wnum = nb2 * mu * (mu + 1);
             block_sum5(h00, h10, h01, h11, c0, sm.red, nwl, (it + 1) & 1);   // first call: upper half (red[128] may still be read)
             if (it > 0) {
                 cost = c0;
@@ -842,10 +1052,9 @@ orora_tail_kernel(const double *__restrict__ src, const double *__restrict__ tgt
             const double ex = dx - (R[0] * sx + R[2] * sy), ey = dy - (R[1] * sx + R[3] * sy);
             res = ex * ex + ey * ey;
             cterm = wgt * res;
-            const double th1 = (mu + 1) / mu * nb2, th2 = mu / (mu + 1) * nb2;
             if (res >= th1) wgt = 0;
             else if (res <= th2) wgt = 1;
-            else wgt = sqrt(nb2 * mu * (mu + 1) / res) - mu;  // :406
+            else wgt = sqrt(wnum / res) - mu;                 // :406 sqrt(nb2 * mu * (mu + 1) / res) - mu
             mu = mu * gnc_factor;
         }
     }
@@ -876,13 +1085,21 @@ orora_tail_kernel(const double *__restrict__ src, const double *__restrict__ tgt
         sm.inl[t] = 1;
     }
     __syncthreads();
-    if (t < M) { sm.a[t] = X0; sm.b[t] = ax; }
-    __syncthreads();
-    const double tx = cote_axis(sm, M, sm.inl, TT);
-    STAMP(8);
-    if (t < M) { sm.a[t] = X1; sm.b[t] = ay; }
-    __syncthreads();
-    const double ty = cote_axis(sm, M, sm.inl, TT);
+    double tx, ty;
+    if (M <= COTE2_MAXM) {
+        if (t < M) { sm.a[t] = X0; sm.b[t] = ax; sm.c[t] = X1; sm.d[t] = ay; }
+        __syncthreads();
+        cote_axes2(sm, M, sm.inl, TT, tx, ty);
+        STAMP(8);
+    } else {
+        if (t < M) { sm.a[t] = X0; sm.b[t] = ax; }
+        __syncthreads();
+        tx = cote_axis(sm, M, sm.inl, TT);
+        STAMP(8);
+        if (t < M) { sm.a[t] = X1; sm.b[t] = ay; }
+        __syncthreads();
+        ty = cote_axis(sm, M, sm.inl, TT);
+    }
     STAMP(9);
     // ---- final inliers (:807-818), compose (:820-824) -------------------------------------------
     if (t == 0) {
@@ -1013,15 +1230,19 @@ int nrs::orora_solve_locked(nrs_ctx *ctx, const double *prev_2xN, const double *
     NRS_LAUNCHED();
     const double beta = 2 * p->noise_bound * sqrt(p->cbar2);
     const int nthreads = N * WORDS;
-    orora_adjacency_kernel<<<(nthreads + 255) / 256, 256, 0, st>>>(b.d_src, b.d_tgt, N, beta, b.d_adj);
-    NRS_LAUNCHED();
-    orora_order_kernel<<<1, 1024, 0, st>>>(b.d_adj, N, b.d_perm, b.d_inv, b.d_edges);
-    NRS_LAUNCHED();
-    orora_permute_kernel<<<(nthreads + 255) / 256, 256, 0, st>>>(b.d_adj, b.d_perm, N, b.d_adjp);
+    orora_adjacency_kernel<<<(nthreads * 32 + 255) / 256, 256, 0, st>>>(b.d_src, b.d_tgt, N, beta, b.d_adj);
     NRS_LAUNCHED();
     const long long node_limit = p->clique_node_limit > 0 ? p->clique_node_limit : 2000000;
-    orora_clique_kernel<<<1, std::max(64, (N + 31) & ~31), (size_t)N * SROW * 4, st>>>(b.d_adjp, N, b.d_stackP, b.d_ord, b.d_col, b.d_cur,
-                                                             b.d_best, b.d_idx, b.d_info, node_limit, b.d_mis);
+    const bool fuse_order = N <= FUSE_ORDER_MAXN;   // two copies of the adjacency matrix fit the CTA's shared memory
+    if (!fuse_order) {
+        orora_order_kernel<<<1, 1024, 0, st>>>(b.d_adj, N, b.d_perm, b.d_inv, b.d_edges);
+        NRS_LAUNCHED();
+        orora_permute_kernel<<<(nthreads + 255) / 256, 256, 0, st>>>(b.d_adj, b.d_perm, N, b.d_adjp);
+        NRS_LAUNCHED();
+    }
+    orora_clique_kernel<<<1, CLQ_THREADS, (size_t)N * SROW * 4 * (fuse_order ? 2 : 1), st>>>(
+        fuse_order ? b.d_adj : b.d_adjp, N, fuse_order ? 1 : 0, b.d_perm, b.d_inv, b.d_edges, b.d_stackP, b.d_ord, b.d_col, b.d_cur,
+        b.d_best, b.d_idx, b.d_info, node_limit, b.d_mis);
     NRS_LAUNCHED();
     orora_tail_kernel<<<1, TT_MAX, sizeof(TailSmem), st>>>(b.d_src, b.d_tgt, N, b.d_perm, b.d_best, p->noise_bound,
                                                        p->rotation_max_iterations, p->rotation_gnc_factor,

@@ -24,6 +24,8 @@ import numpy as np
 from . import _lib
 from ._lib import ScResult, check, f64, lib, ptr
 
+REC_DTYPE = np.dtype([("dist", "<f8"), ("idx", "<i4"), ("shift", "<i4")])   # nrs_sc_result (16 bytes)
+
 RINGS, SECTORS, DESC = 20, 60, 1200
 SENTINEL = 10000000.0
 
@@ -166,14 +168,15 @@ class SCDatabase:
         check(lib().nrs_sc_detect_knn_batch(self._h, ptr(q), q.shape[0], first, last, k, ptr(cand), res))
         return [(r.dist, r.idx, r.shift) for r in res], cand
 
-    def query_batch(self, queries, first=0, last=None):
+    def query_batch(self, queries, first=0, last=None, as_array=False):
         """nrs_sc_query_batch: Q queries (Q,1200) against keyframes [first,last) -> [(dist, idx, shift)] * Q,
-        each exactly what query() returns; one kernel launch on a {0,c} database."""
+        each exactly what query() returns; one kernel launch on a {0,c} database.  as_array: the Q records as
+        one structured array (dist f8, idx i4, shift i4) instead of a list of tuples."""
         q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, DESC)
         last = len(self) if last is None else last
-        res = (ScResult * q.shape[0])()
-        check(lib().nrs_sc_query_batch(self._h, ptr(q), q.shape[0], first, last, res))
-        return [(r.dist, r.idx, r.shift) for r in res]
+        res = np.empty(q.shape[0], dtype=REC_DTYPE)
+        check(lib().nrs_sc_query_batch(self._h, ptr(q), q.shape[0], first, last, ptr(res)))
+        return res if as_array else [(float(r[0]), int(r[1]), int(r[2])) for r in res.tolist()]
 
     def query_batch_dev(self, queries_dev_ptr, Q, first, last, idx_offset, results_dev_ptr):
         check(lib().nrs_sc_query_batch_dev(self._h, C.c_void_p(queries_dev_ptr), Q, first, last, idx_offset,
@@ -551,9 +554,9 @@ class ShardedSCDatabase:
             self._rb_pin = torch.zeros(cap * self.RECORD * max(1, self.world), dtype=torch.uint8).pin_memory()
             self._rb_all = torch.zeros(cap * self.RECORD * max(1, self.world), dtype=torch.uint8, device=self.dev)
 
-    def query_batch(self, queries, first=0, last=None):
+    def query_batch(self, queries, first=0, last=None, as_array=False):
         """[(dist, idx, shift)] * Q over keyframes [first,last), each identical to query(); identical on every
-        rank.  One GPU: nrs_sc_query_batch.  Sharded on GPUs: nrs_sc_query_batch_dev_sharded (one launch, the
+        rank (as_array: one structured array (dist f8, idx i4, shift i4) instead of the list).  One GPU: nrs_sc_query_batch.  Sharded on GPUs: nrs_sc_query_batch_dev_sharded (one launch, the
         per-query records exchanged in-kernel over peer memory, merged once).  Otherwise one all_gather of
         the Q records per rank and best_of() per query."""
         torch, dist = self._torch, self._dist
@@ -562,7 +565,7 @@ class ShardedSCDatabase:
         Q = qs.shape[0]
         rec_t = [("dist", "<f8"), ("idx", "<i4"), ("shift", "<i4")]
         if self.world == 1 and self.db is not None:
-            return self.db.query_batch(qs, max(first, 0), max(first, min(last, self._local_n)))
+            return self.db.query_batch(qs, max(first, 0), max(first, min(last, self._local_n)), as_array)
         lo, hi = local_range(first, last, self.rank, self.world)
         hi = min(hi, self._local_n)
         if self.db is None:
@@ -576,21 +579,19 @@ class ShardedSCDatabase:
             allr = [o.numpy().view(rec_t) for o in outs]
             return [best_of([(float(allr[r]["dist"][k]), int(allr[r]["idx"][k]) * self.world + r, int(allr[r]["shift"][k]))
                              for r in range(self.world)]) for k in range(Q)]
+        if self.exchange == "peer":
+            # nrs_sc_query_batch_sharded: the caller's buffer goes to the device as it is (DMA when it is pinned), one
+            # launch with the in-kernel exchange, the Q records come back -- no staging copy on the host
+            r = np.empty(Q, dtype=REC_DTYPE)
+            check(lib().nrs_sc_query_batch_sharded(self.db._h, ptr(qs), Q, lo, hi, ptr(r)))
+            if np.any(r["idx"] == -2):
+                raise RuntimeError("sharded ScanContext batch: a peer rank did not answer within the exchange timeout")
+            return r if as_array else [(float(x[0]), int(x[1]), int(x[2])) for x in r.tolist()]
         self._batch_buffers(Q)
         self._qb_pin[:Q].copy_(torch.from_numpy(qs))
         nb = Q * self.RECORD
         with torch.cuda.stream(self._nrs_stream):
             self._qb_dev[:Q].copy_(self._qb_pin[:Q], non_blocking=True)
-            if self.exchange == "peer":
-                self.db.query_batch_dev_sharded(self._qb_dev.data_ptr(), Q, lo, hi, self._rb_dev.data_ptr())
-                self._rb_pin[:nb].copy_(self._rb_dev[:nb], non_blocking=True)
-        if self.exchange == "peer":
-            self._nrs_stream.synchronize()
-            r = self._rb_pin[:nb].numpy().view(rec_t)
-            if np.any(r["idx"] == -2):
-                raise RuntimeError("sharded ScanContext batch: a peer rank did not answer within the exchange timeout")
-            return [(float(r["dist"][k]), int(r["idx"][k]), int(r["shift"][k])) for k in range(Q)]
-        with torch.cuda.stream(self._nrs_stream):
             self.db.query_batch_dev(self._qb_dev.data_ptr(), Q, lo, hi, 0, self._rb_dev.data_ptr())
         cur = torch.cuda.current_stream(self.dev)
         cur.wait_stream(self._nrs_stream)

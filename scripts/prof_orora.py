@@ -28,6 +28,12 @@ h = C.c_void_p()
 pkg._lib.check(L.nrs_frame_extract(ctx.handle, raws[0].ctypes.data_as(C.c_void_p), 400, raws[0].shape[1], C.byref(ep), 0, C.byref(h)))
 prev, vel = h, 0.0
 print("launches after first extract:", L.nrs_kernel_launches())
+def tail_phases():
+    t = (C.c_uint64 * 8)()
+    L.nrs_frontend_tail_times(ctx.handle, t)
+    return [round((int(t[i + 1]) - int(t[i])) / 1e3, 1) for i in range(5)]
+
+
 import torch  # noqa: E402  (cudart handle for the profiler range)
 for k in range(1, 6):
     if k == 4:
@@ -41,6 +47,7 @@ for k in range(1, 6):
     fi = pkg._lib.FrameInfo()
     L.nrs_frame_info_get(cur, C.byref(fi))
     print("pair", k, "matches", n.value, "clique", info.M, "launches so far:", L.nrs_kernel_launches(),
+          "| tail us", tail_phases(),
           "| candidates", fi.n_candidates, "consumed", fi.j_consumed, "sorted", fi.n_sorted, "K0", fi.K_polar, "Kv", fi.K_voxel, "Kd", fi.K_desc)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
