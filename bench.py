@@ -24,9 +24,17 @@ import time
 
 import numpy as np
 
-# NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; the contract is ONE JSON line there
-if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# The contract is ONE JSON line on stdout, and libraries write there too (NCCL's version banner at init, for one):
+# file descriptor 1 is pointed at stderr for the whole run, the JSON line goes out through a private copy of the
+# original stdout.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit_json(obj):
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -175,7 +183,7 @@ def run_reference(args, rank, world):
     }
     if out_orora is not None:
         out["orora"] = out_orora
-    print(json.dumps(out), flush=True)
+    emit_json(out)
 
 
 def kdtree_block(sc, d, O, db, queries, n=400):
@@ -484,7 +492,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         if stream is not None:
             out["stream"] = stream
-        print(json.dumps(out), flush=True)
+        emit_json(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

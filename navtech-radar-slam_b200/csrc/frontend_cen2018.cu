@@ -26,7 +26,7 @@ namespace nrs {
 
 namespace {
 
-constexpr int ROWS_PB = 3;       // azimuths per CTA in the bias / noise kernel (134 CTAs for 400 azimuths)
+constexpr int ROWS_PB = 1;       // azimuths per CTA in the bias / noise kernel (one CTA per azimuth: the staging and the q pass of a row spread over 256 threads, the two add chains are the floor)
 
 // :49-59 + :77-91.  q = f - mean(row), sigma_q(row); both sums are sequential in column order, so the
 // floor is two dependent chains of C float adds per azimuth.  Each CTA stages its rows whole in shared

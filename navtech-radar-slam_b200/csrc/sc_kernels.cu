@@ -1252,13 +1252,19 @@ int nrs_sc_filter_record_bytes(void) { return FREC_BYTES; }
 // {0,c} query?  (the host-side twin of prep_query's classification in sc_search_bin.cu)
 static bool host_query_is_binary(const double *q)
 {
-    unsigned long long pa = ~0ull, po = 0ull;
-    for (int i = 0; i < DESC; ++i)
-        if (!(q[i] == 0.0)) {
+    // branch-free, four independent accumulator pairs (the compiler vectorises it): this runs on the host between the
+    // enqueue of a batch's upload and its launch, 1200 values per query
+    unsigned long long pa4[4] = {~0ull, ~0ull, ~0ull, ~0ull}, po4[4] = {0ull, 0ull, 0ull, 0ull};
+    static_assert(DESC % 4 == 0, "unrolled by four");
+    for (int i = 0; i < DESC; i += 4)
+        for (int k = 0; k < 4; ++k) {
             unsigned long long b;
-            memcpy(&b, &q[i], sizeof(b));
-            pa &= b; po |= b;
+            memcpy(&b, &q[i + k], sizeof(b));
+            const unsigned long long m = (b << 1) ? ~0ull : 0ull;        // +-0.0 -> not counted (q == 0.0), NaN counted
+            pa4[k] &= b | ~m;
+            po4[k] |= b & m;
         }
+    const unsigned long long pa = pa4[0] & pa4[1] & pa4[2] & pa4[3], po = po4[0] | po4[1] | po4[2] | po4[3];
     if (po == 0ull) return true;
     if (pa != po) return false;
     double c;

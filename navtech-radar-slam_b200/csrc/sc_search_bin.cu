@@ -274,7 +274,7 @@ static __device__ __noinline__ void certify_dist_bin(const uint2 *__restrict__ q
     __syncwarp();
 }
 
-template <bool kRedux>
+template <bool kRedux, bool kCand>
 __global__ void __launch_bounds__(BT, 2)
 sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__restrict__ desc, const double *__restrict__ keys,
                      const double *__restrict__ queries, int Q, const int32_t *__restrict__ cand_base, int cand_stride,
@@ -295,7 +295,7 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int q = (Q == 1) ? 0 : tile / n_chunks, chunk = tile - q * n_chunks;
         const double *query = queries + (size_t)q * DESC;
-        const int32_t *cand = cand_base ? cand_base + (size_t)q * cand_stride : nullptr;     // this query's own candidate list
+        const int32_t *cand = kCand ? cand_base + (size_t)q * cand_stride : nullptr;         // this query's own candidate list (compiled out of the exhaustive search)
         SearchState *stq = st + q;
         Survivor *survq = surv + (size_t)q * surv_stride;
         const int lo = chunk * per, hi = min(n_items, lo + per);
@@ -303,7 +303,7 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
         // this warp's first record is in flight while the CTA prepares the query
         uint2 cur = make_uint2(0u, 0u);
         if (lo + warp < hi) {
-            const int kf = cand ? cand[lo + warp] : first + lo + warp;
+            const int kf = kCand ? cand[lo + warp] : first + lo + warp;
             cur = ldg_u2(brec + (size_t)kf * BIN_WORDS + 2 * lane);
         }
         prep_query(sm, query, stq);
@@ -325,7 +325,7 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
             for (int item = lo + warp; item < hi; item += BWARPS) {
                 const uint2 km = cur;
                 if (item + BWARPS < hi) {
-                    const int kf2 = cand ? cand[item + BWARPS] : first + item + BWARPS;
+                    const int kf2 = kCand ? cand[item + BWARPS] : first + item + BWARPS;
                     cur = ldg_u2(brec + (size_t)kf2 * BIN_WORDS + 2 * lane);
                 }
                 const unsigned int kz_lo = __shfl_sync(0xffffffffu, km.x, 30), kz_hi = __shfl_sync(0xffffffffu, km.y, 30);
@@ -464,7 +464,7 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
             double bd = SENTINEL;
             int bp = 0x7fffffff, bi = 0, bs = 0;
             for (int item = lo + warp; item < hi; item += BWARPS) {
-                const int kf = cand ? cand[item] : first + item;
+                const int kf = kCand ? cand[item] : first + item;
                 const uint2 kzw = *reinterpret_cast<const uint2 *>(brec + (size_t)kf * BIN_WORDS + 60);
                 const unsigned long long kzero = (((unsigned long long)kzw.y << 32) | kzw.x) & MASK60;
                 const int s0 = certify_shift(&sm.qc, ws.scr, keys + (size_t)kf * KEYS_D, 0x3fffffffu, 0x3fffffffu, lane);
@@ -511,7 +511,7 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
             // hundreds of near-ties) is certified in place, every warp taking the entries it filtered itself.
             // Order of the reference's scans: (dist, keyframe position, shift) lexicographic.
             auto certify_one = [&](int it, int cd, float ckf, unsigned int bits) {
-                const int kf = cand ? cand[it] : first + it;
+                const int kf = kCand ? cand[it] : first + it;
                 __syncwarp();
                 *reinterpret_cast<uint2 *>(&ws.krec[2 * lane]) = __ldcg(reinterpret_cast<const uint2 *>(brec + (size_t)kf * BIN_WORDS + 2 * lane));
                 __syncwarp();
@@ -645,7 +645,20 @@ int nrs_sc::bin_launch(nrs_sc_db *db, const double *d_queries, int Q, const int3
     const int max_ctas = 2 * ctx->sm_count;
     int n_chunks;
     if (Q == 1) n_chunks = std::max(1, std::min(max_ctas, (n_items + BWARPS - 1) / BWARPS));
-    else n_chunks = std::max(1, std::min((4 * max_ctas + Q - 1) / Q, (n_items + 8 * BWARPS - 1) / (8 * BWARPS)));
+    else {
+        // tiles are dealt round-robin to a persistent grid: the launch lasts ceil(tiles / grid) rounds, so among the
+        // chunk counts from "~4 tiles per CTA" up to twice that, take the one that wastes the least of the last round
+        // (256 queries on 296 CTAs: 8 chunks = 2048 tiles = 6.92 rounds instead of 5 chunks = 4.32 rounds paid as 5)
+        const int cmax = std::max(1, (n_items + 8 * BWARPS - 1) / (8 * BWARPS));
+        const int c0 = std::max(1, std::min((4 * max_ctas + Q - 1) / Q, cmax));
+        double best = -1.0;
+        n_chunks = c0;
+        for (int c = c0; c <= std::min(cmax, 2 * c0 + 2); ++c) {
+            const long long tiles = (long long)Q * c, g = std::min<long long>(max_ctas, tiles);
+            const double eff = (double)tiles / (double)(((tiles + g - 1) / g) * g);
+            if (eff > best + 1e-9) { best = eff; n_chunks = c; }
+        }
+    }
     const size_t stride = (size_t)n_items + 64;
     int rc = db->bin_surv.reserve((size_t)Q * stride * sizeof(Survivor));
     if (rc) return rc;
@@ -654,14 +667,14 @@ int nrs_sc::bin_launch(nrs_sc_db *db, const double *d_queries, int Q, const int3
     const int grid = std::min(max_ctas, Q * n_chunks);
     const int per = (n_items + n_chunks - 1) / n_chunks;
     static const int use_redux = []() { const char *e = getenv("NRS_SC_BIN_REDUX"); return e ? atoi(e) : NRS_SC_BIN_REDUX_DEFAULT; }();
-    if (use_redux)
-        sc_search_bin_kernel<true><<<grid, BT, 0, ctx->stream>>>(db->d_brec, db->d_desc, db->d_keys, d_queries, Q, d_cand, cand_stride, first, n_items,
-                                                                 n_chunks, per, idx_scale, idx_offset, db->bin_surv.as<Survivor>(), stride,
-                                                                 db->d_bstate, db->bin_block.as<BlockResult>(), db->d_gticket, d_results, xv);
-    else
-        sc_search_bin_kernel<false><<<grid, BT, 0, ctx->stream>>>(db->d_brec, db->d_desc, db->d_keys, d_queries, Q, d_cand, cand_stride, first, n_items,
-                                                                  n_chunks, per, idx_scale, idx_offset, db->bin_surv.as<Survivor>(), stride,
-                                                                  db->d_bstate, db->bin_block.as<BlockResult>(), db->d_gticket, d_results, xv);
+#define NRS_BIN_LAUNCH(R_, C_)                                                                                               \
+    sc_search_bin_kernel<R_, C_><<<grid, BT, 0, ctx->stream>>>(db->d_brec, db->d_desc, db->d_keys, d_queries, Q, d_cand, cand_stride, \
+                                                               first, n_items, n_chunks, per, idx_scale, idx_offset,          \
+                                                               db->bin_surv.as<Survivor>(), stride, db->d_bstate,              \
+                                                               db->bin_block.as<BlockResult>(), db->d_gticket, d_results, xv)
+    if (use_redux) { if (d_cand) NRS_BIN_LAUNCH(true, true); else NRS_BIN_LAUNCH(true, false); }
+    else           { if (d_cand) NRS_BIN_LAUNCH(false, true); else NRS_BIN_LAUNCH(false, false); }
+#undef NRS_BIN_LAUNCH
     NRS_LAUNCHED();
     return NRS_OK;
 }
