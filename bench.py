@@ -865,7 +865,7 @@ def orora_block(pkg, ctx, n_pairs=40, cpu_pairs=3):
             "parity_gate": parity,
             "workload": "synthetic MulRan-format 400x3360 frames, cen2019 + remap + ORB + match + max-clique/GNC/COTE",
             "e2e": "pinned host PNG rows in (1.35 MB H2D per frame), 4x4 pose out; value == e2e (the path starts on the host)",
-            "api": "nrs_orora_pair (extract + match + solve in one call, two host synchronisations per pair)",
+            "api": "nrs_orora_pair (extract + match + solve in one call; the solver is enqueued behind the matcher with the match count still on the device: ONE host synchronisation per pair)",
             "separate_calls": {"value": n_pairs / dt_sep, "ms_per_pair": 1e3 * dt_sep / n_pairs,
                                "api": "nrs_frame_extract + nrs_match + nrs_orora_solve (four synchronisations, matches through host memory)"},
             "h2d_bytes_per_pair": int(raws[0].nbytes), "d2h_bytes_per_pair": 128 + 40 * max(n_matches, 1),

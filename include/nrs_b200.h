@@ -405,8 +405,10 @@ int nrs_icp_align(nrs_ctx *ctx, const float *src_xyz_Nsx3, int Ns, const float *
  *   T = orora_estimator.calcTransform(params, dt, prev_m, curr_m)
  * with the same results as nrs_frame_extract + nrs_match + nrs_orora_solve, but the matcher is enqueued behind the
  * extraction without waiting for it and the matched points reach the solver without a round trip through host
- * memory (two host synchronisations per scan pair instead of four).  prev: the previous frame's handle (same
- * context); *curr_out: the new frame's handle (caller destroys); vel_x as in nrs_orora_solve;
+ * memory, and the solver is enqueued speculatively with the match count still on the device (ONE host
+ * synchronisation per scan pair instead of four; the stop-motion gate and the capacity rule are applied by the host
+ * once it sees the count, counts above the speculative launch's 512 are solved again with the host-sized launch).
+ * prev: the previous frame's handle (same context); *curr_out: the new frame's handle (caller destroys); vel_x as in nrs_orora_solve;
  * *n_matches (nullable): matches fed to the solver. */
 int nrs_orora_pair(nrs_ctx *ctx, const nrs_frame *prev, const uint8_t *raw_rows, int R, int row_pitch,
                    const nrs_extract_params *p, int64_t t_criteria, const nrs_solver_params *sp, double vel_x,

@@ -67,6 +67,12 @@ struct PinBuf {
 int orora_solve_locked(nrs_ctx *ctx, const double *prev_2xN, const double *curr_2xN, bool points_on_device, int N,
                        const nrs_solver_params *p, double vel_x, double T_out[16], int32_t *clique_out,
                        int32_t *final_inliers_out, nrs_solver_info *info_out);
+// the same solve enqueued behind the matcher with the match count still on the device (d_n); no synchronisation.
+// orora_pair_finish reads the result after the caller's synchronisation, given the count it read back.
+int orora_pair_enqueue(nrs_ctx *ctx, const double *d_prev, const double *d_curr, const int *d_n,
+                       const nrs_solver_params *p, double vel_x);
+int orora_pair_finish(nrs_ctx *ctx, const double *d_prev, const double *d_curr, int N, const nrs_solver_params *p,
+                      double vel_x, double T_out[16], nrs_solver_info *info_out);
 
 }  // namespace nrs
 

@@ -146,6 +146,7 @@ struct FrontendState {
     long long *d_times = nullptr;        // R
     FrameCounts *d_counts = nullptr;
     FrameCounts *h_counts = nullptr;     // pinned
+    int *h_n = nullptr;                  // pinned: the fused pair call's match count
     // cen2019 top-candidate subset: threshold on h carried from frame to frame (device), valid once a frame ran
     float *d_thresh = nullptr;
     bool   have_thresh = false;

@@ -324,6 +324,7 @@ static void frontend_free(void *p)
     for (auto &g : S->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     S->graphs.clear();
     if (S->h_counts) cudaFreeHost(S->h_counts);
+    if (S->h_n) cudaFreeHost(S->h_n);
     if (S->h_tables) cudaFreeHost(S->h_tables);
     if (S->st_img) { cudaStreamSynchronize(S->st_img); cudaStreamDestroy(S->st_img); }
     if (S->ev_fork) cudaEventDestroy(S->ev_fork);
@@ -377,6 +378,7 @@ static int frontend_state(nrs_ctx *ctx, const nrs_extract_params *p, int R, int 
     rc |= dmalloc(&S->d_thresh, 1); rc |= dmalloc(&S->d_stage, N); rc |= dmalloc(&S->d_sel, N); rc |= dmalloc(&S->d_lut, 256);
     if (rc) return rc;
     NRS_CUDA(cudaMallocHost((void **)&S->h_counts, sizeof(FrameCounts)));
+    NRS_CUDA(cudaMallocHost((void **)&S->h_n, sizeof(int)));
     NRS_CUDA(cudaMallocHost((void **)&S->h_tables, sizeof(AzTables)));
     {
         float lut[256];
@@ -804,7 +806,8 @@ int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw, int R, int row_pitch, co
 // One iteration of the node's loop (odometry.cpp:153-284) in ONE call: extractFeature(new frame),
 // matchFeatures(prev, curr), ORORA::calcTransform -- the matcher is enqueued behind the extraction without
 // waiting for it (the new frame's keypoint count stays on the device), the matched points go to the solver
-// without a round trip through host memory: two host synchronisations per scan pair instead of four.
+// without a round trip through host memory, and it is enqueued before the match count is known to the host (the
+// kernels read it on the device and gate themselves): ONE host synchronisation per scan pair instead of four.
 int nrs_orora_pair(nrs_ctx *ctx, const nrs_frame *prev, const uint8_t *raw, int R, int row_pitch,
                    const nrs_extract_params *p, int64_t t_criteria, const nrs_solver_params *sp, double vel_x,
                    nrs_frame **curr_out, double T_out[16], int *n_matches, nrs_solver_info *info_out)
@@ -842,9 +845,13 @@ int nrs_orora_pair(nrs_ctx *ctx, const nrs_frame *prev, const uint8_t *raw, int 
                                                        m.p, m.c, m.pt, m.ct, m.n);
             NRS_LAUNCHED();
         }
+        // the solver goes in behind the matcher without waiting for the match count (it stays on the device): ONE host
+        // synchronisation per scan pair
+        if ((rc = nrs::orora_pair_enqueue(ctx, m.p, m.c, m.n, sp, vel_x))) { frame_release_locked(f); return rc; }
         NRS_CUDA(cudaMemcpyAsync(S->h_counts, S->d_counts, sizeof(FrameCounts), cudaMemcpyDeviceToHost, st));
-        NRS_CUDA(cudaMemcpyAsync(&h_n, m.n, 4, cudaMemcpyDeviceToHost, st));
+        NRS_CUDA(cudaMemcpyAsync(S->h_n, m.n, 4, cudaMemcpyDeviceToHost, st));
         NRS_CUDA(cudaStreamSynchronize(st));
+        h_n = *S->h_n;
         if (!S->h_counts->need_full) break;
     }
     f->counts = *S->h_counts;
@@ -855,7 +862,7 @@ int nrs_orora_pair(nrs_ctx *ctx, const nrs_frame *prev, const uint8_t *raw, int 
     }
     if (f->counts.Kd == 0) h_n = 0;                  // the matcher saw an empty train set
     if (n_matches) *n_matches = h_n;
-    rc = nrs::orora_solve_locked(ctx, m.p, m.c, true, h_n, sp, vel_x, T_out, nullptr, nullptr, info_out);
+    rc = nrs::orora_pair_finish(ctx, m.p, m.c, h_n, sp, vel_x, T_out, info_out);
     if (rc) { frame_release_locked(f); return rc; }
     *curr_out = f;
     return NRS_OK;

@@ -54,10 +54,24 @@ __device__ __forceinline__ unsigned long long gtimer()
 
 // ---- K7 ---------------------------------------------------------------------------------------
 // ORORA.hpp:139-151 Doppler compensation fused in front: p.x += beta*v*x*x/rsq; p.y += beta*v*x'*y/rsq
+// Device-resident problem size (the fused pair call enqueues the solver behind the matcher without reading the
+// match count back): with d_n the kernels take N from there and do nothing unless 2 <= N <= gate -- the host sees
+// the count after its one synchronisation and applies the stop-motion gate / capacity rules (or redoes the solve
+// with the host-sized launch for counts the speculative launch geometry does not cover).
+__device__ __forceinline__ bool solver_size(const int *__restrict__ d_n, int gate, int &N)
+{
+    if (d_n) {
+        N = *d_n;
+        return N >= 2 && N <= gate;
+    }
+    return true;
+}
+
 __global__ void orora_prep_kernel(const double *__restrict__ prev, const double *__restrict__ curr,
                                   int N, double beta_v, int use_doppler, double *__restrict__ src,
-                                  double *__restrict__ tgt)
+                                  double *__restrict__ tgt, const int *__restrict__ d_n, int gate)
 {
+    if (!solver_size(d_n, gate, N)) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     // src = curr frame (setInputSource), tgt = prev frame (setInputTarget): ORORA.hpp:83-84
@@ -76,8 +90,9 @@ __global__ void orora_prep_kernel(const double *__restrict__ prev, const double 
 
 __global__ void __launch_bounds__(256)
 orora_adjacency_kernel(const double *__restrict__ src, const double *__restrict__ tgt, int N,
-                       double beta, uint32_t *__restrict__ adj)
+                       double beta, uint32_t *__restrict__ adj, const int *__restrict__ d_n, int gate)
 {
+    if (!solver_size(d_n, gate, N)) return;
     // one warp per (row i, word w), one pair (i, j = 32 w + lane) per thread, the word assembled by a ballot:
     // the f64 square roots and divisions of the ~N^2 tests run on N * ceil(N/32) * 32 threads instead of N * 32
     const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -190,8 +205,9 @@ orora_clique_kernel(const uint32_t *__restrict__ adjp, int N, int fuse_order, in
                     int *__restrict__ inv_out, int *__restrict__ n_edges, uint32_t *__restrict__ stackP,
                     uint16_t *__restrict__ ordS, uint16_t *__restrict__ colS, int *__restrict__ cur,
                     int *__restrict__ best, int *__restrict__ idxS, SolverInfoDev *__restrict__ info,
-                    long long node_limit, uint32_t *__restrict__ misStack)
+                    long long node_limit, uint32_t *__restrict__ misStack, const int *__restrict__ d_n, int gate)
 {
+    if (!solver_size(d_n, gate, N)) return;
     extern __shared__ uint32_t sadj[];
     __shared__ uint32_t sP[WORDS];          // current vertex set, one word per entry
     __shared__ int s_changed;
@@ -1178,6 +1194,26 @@ int configure_solver_kernels(int device)
 
 }  // namespace
 
+namespace {
+void read_solver_result(const SolverInfoDev *h_info, const double *h_T, int h_edges, double T_out[16], nrs_solver_info *info_out)
+{
+    for (int i = 0; i < 16; ++i) T_out[i] = h_T[i];
+    info_out->valid = h_info->valid;
+    info_out->n_edges = h_edges;
+    info_out->M = h_info->M;
+    info_out->gnc_iters = h_info->gnc_iters;
+    info_out->gnc_early_return = h_info->gnc_early_return;
+    info_out->n_rot_inliers = h_info->n_rot_inliers;
+    info_out->n_final_inliers = h_info->n_final_inliers;
+    info_out->clique_exact = h_info->clique_exact;
+    info_out->clique_nodes = h_info->nodes;
+    for (int i = 0; i < 12; ++i) g_last_t_ns[i] = h_info->t_ns[i];
+    for (int i = 0; i < 4; ++i) info_out->R[i] = h_info->R[i];
+    info_out->t[0] = h_info->t[0]; info_out->t[1] = h_info->t[1];
+    info_out->cost = h_info->cost;
+}
+}  // namespace
+
 extern "C" {
 
 int nrs_orora_solve(nrs_ctx *ctx, const double *prev_2xN, const double *curr_2xN, int N,
@@ -1197,19 +1233,20 @@ int nrs::orora_solve_locked(nrs_ctx *ctx, const double *prev_2xN, const double *
                             const nrs_solver_params *p, double vel_x, double T_out[16], int32_t *clique_out,
                             int32_t *final_inliers_out, nrs_solver_info *info_out)
 {
-    if (N > MAXN) {
-        nrs::set_error("nrs_orora_solve: N = %d exceeds the %d correspondences one warp-wide bitset holds "
-                       "(the reference skips estimation above num_feat_thr_for_stop_motion = 700)", N, MAXN);
-        return NRS_ECAPACITY;
-    }
     memset(info_out, 0, sizeof(*info_out));
     for (int i = 0; i < 16; ++i) T_out[i] = (i % 5 == 0) ? 1.0 : 0.0;
     info_out->R[0] = info_out->R[3] = 1.0;
     info_out->clique_exact = 1;
-    // stop-motion gate (ORORA.hpp:74-79) and the degenerate sizes are host decisions
+    // stop-motion gate (ORORA.hpp:74-79) and the degenerate sizes are host decisions; the gate comes first, like in
+    // the reference: a pair it skips is never a capacity error
     if ((p->check_stop_motion && N > p->num_feat_thr_for_stop_motion) || N < 2) {
         info_out->stop_motion = (p->check_stop_motion && N > p->num_feat_thr_for_stop_motion) ? 1 : 0;
         return NRS_OK;
+    }
+    if (N > MAXN) {
+        nrs::set_error("nrs_orora_solve: N = %d exceeds the %d correspondences one warp-wide bitset holds "
+                       "(the reference's default stop-motion gate skips estimation above 700)", N, MAXN);
+        return NRS_ECAPACITY;
     }
     int rc = configure_solver_kernels(ctx->device);
     if (rc) return rc;
@@ -1226,11 +1263,11 @@ int nrs::orora_solve_locked(nrs_ctx *ctx, const double *prev_2xN, const double *
     NRS_CUDA(cudaMemsetAsync(b.d_info, 0, sizeof(SolverInfoDev), st));
     const double beta_v = p->doppler_beta * fabs(vel_x);
     orora_prep_kernel<<<(N + 255) / 256, 256, 0, st>>>(d_prev_in, d_curr_in, N, beta_v, p->use_doppler_compensation,
-                                                      b.d_src, b.d_tgt);
+                                                      b.d_src, b.d_tgt, nullptr, 0);
     NRS_LAUNCHED();
     const double beta = 2 * p->noise_bound * sqrt(p->cbar2);
     const int nthreads = N * WORDS;
-    orora_adjacency_kernel<<<(nthreads * 32 + 255) / 256, 256, 0, st>>>(b.d_src, b.d_tgt, N, beta, b.d_adj);
+    orora_adjacency_kernel<<<(nthreads * 32 + 255) / 256, 256, 0, st>>>(b.d_src, b.d_tgt, N, beta, b.d_adj, nullptr, 0);
     NRS_LAUNCHED();
     const long long node_limit = p->clique_node_limit > 0 ? p->clique_node_limit : 2000000;
     const bool fuse_order = N <= FUSE_ORDER_MAXN;   // two copies of the adjacency matrix fit the CTA's shared memory
@@ -1242,7 +1279,7 @@ int nrs::orora_solve_locked(nrs_ctx *ctx, const double *prev_2xN, const double *
     }
     orora_clique_kernel<<<1, CLQ_THREADS, (size_t)N * SROW * 4 * (fuse_order ? 2 : 1), st>>>(
         fuse_order ? b.d_adj : b.d_adjp, N, fuse_order ? 1 : 0, b.d_perm, b.d_inv, b.d_edges, b.d_stackP, b.d_ord, b.d_col, b.d_cur,
-        b.d_best, b.d_idx, b.d_info, node_limit, b.d_mis);
+        b.d_best, b.d_idx, b.d_info, node_limit, b.d_mis, nullptr, 0);
     NRS_LAUNCHED();
     orora_tail_kernel<<<1, TT_MAX, sizeof(TailSmem), st>>>(b.d_src, b.d_tgt, N, b.d_perm, b.d_best, p->noise_bound,
                                                        p->rotation_max_iterations, p->rotation_gnc_factor,
@@ -1257,29 +1294,78 @@ int nrs::orora_solve_locked(nrs_ctx *ctx, const double *prev_2xN, const double *
     double *h_T = (double *)(h + align_up(sizeof(SolverInfoDev)));
     int *h_clique = (int *)(h_T + 16);
     int *h_final = h_clique + N;
-    int h_edges = 0;
+    int *h_edges = h_final + N;
     NRS_CUDA(cudaMemcpyAsync(h_info, b.d_info, sizeof(SolverInfoDev), cudaMemcpyDeviceToHost, st));
     NRS_CUDA(cudaMemcpyAsync(h_T, b.d_T, 16 * 8, cudaMemcpyDeviceToHost, st));
-    NRS_CUDA(cudaMemcpyAsync(&h_edges, b.d_edges, 4, cudaMemcpyDeviceToHost, st));
+    NRS_CUDA(cudaMemcpyAsync(h_edges, b.d_edges, 4, cudaMemcpyDeviceToHost, st));
     if (clique_out) NRS_CUDA(cudaMemcpyAsync(h_clique, b.d_clique, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
     if (final_inliers_out) NRS_CUDA(cudaMemcpyAsync(h_final, b.d_final, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
     NRS_CUDA(cudaStreamSynchronize(st));
-    for (int i = 0; i < 16; ++i) T_out[i] = h_T[i];
-    info_out->valid = h_info->valid;
-    info_out->n_edges = h_edges;
-    info_out->M = h_info->M;
-    info_out->gnc_iters = h_info->gnc_iters;
-    info_out->gnc_early_return = h_info->gnc_early_return;
-    info_out->n_rot_inliers = h_info->n_rot_inliers;
-    info_out->n_final_inliers = h_info->n_final_inliers;
-    info_out->clique_exact = h_info->clique_exact;
-    info_out->clique_nodes = h_info->nodes;
-    for (int i = 0; i < 12; ++i) g_last_t_ns[i] = h_info->t_ns[i];
-    for (int i = 0; i < 4; ++i) info_out->R[i] = h_info->R[i];
-    info_out->t[0] = h_info->t[0]; info_out->t[1] = h_info->t[1];
-    info_out->cost = h_info->cost;
+    read_solver_result(h_info, h_T, *h_edges, T_out, info_out);
     if (clique_out) memcpy(clique_out, h_clique, (size_t)h_info->M * 4);
     if (final_inliers_out) memcpy(final_inliers_out, h_final, (size_t)h_info->n_final_inliers * 4);
+    return NRS_OK;
+}
+
+// ---- the solver enqueued SPECULATIVELY behind the matcher (fused pair call): the match count stays on the device
+// (d_n), the launch geometry covers N <= FUSE_ORDER_MAXN, the kernels gate themselves (solver_size).  Results land in
+// the context's pinned buffer; nothing is synchronised here.
+int nrs::orora_pair_enqueue(nrs_ctx *ctx, const double *d_prev, const double *d_curr, const int *d_n,
+                            const nrs_solver_params *p, double vel_x)
+{
+    int rc = configure_solver_kernels(ctx->device);
+    if (rc) return rc;
+    const int NB = FUSE_ORDER_MAXN;
+    SolverBufs b;
+    rc = carve(ctx, NB, b);
+    if (rc) return rc;
+    rc = ctx->pin[0].reserve(sizeof(SolverInfoDev) + 16 * 8 + 2 * (size_t)MAXN * 4 + 64);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    const int gate = (p->check_stop_motion && p->num_feat_thr_for_stop_motion < NB) ? std::max(0, p->num_feat_thr_for_stop_motion) : NB;
+    NRS_CUDA(cudaMemsetAsync(b.d_info, 0, sizeof(SolverInfoDev), st));
+    const double beta_v = p->doppler_beta * fabs(vel_x);
+    orora_prep_kernel<<<(NB + 255) / 256, 256, 0, st>>>(d_prev, d_curr, NB, beta_v, p->use_doppler_compensation, b.d_src, b.d_tgt, d_n, gate);
+    NRS_LAUNCHED();
+    const double beta = 2 * p->noise_bound * sqrt(p->cbar2);
+    orora_adjacency_kernel<<<(NB * WORDS * 32 + 255) / 256, 256, 0, st>>>(b.d_src, b.d_tgt, NB, beta, b.d_adj, d_n, gate);
+    NRS_LAUNCHED();
+    const long long node_limit = p->clique_node_limit > 0 ? p->clique_node_limit : 2000000;
+    orora_clique_kernel<<<1, CLQ_THREADS, (size_t)NB * SROW * 4 * 2, st>>>(b.d_adj, NB, 1, b.d_perm, b.d_inv, b.d_edges, b.d_stackP, b.d_ord,
+                                                                         b.d_col, b.d_cur, b.d_best, b.d_idx, b.d_info, node_limit, b.d_mis,
+                                                                         d_n, gate);
+    NRS_LAUNCHED();
+    orora_tail_kernel<<<1, TT_MAX, sizeof(TailSmem), st>>>(b.d_src, b.d_tgt, NB, b.d_perm, b.d_best, p->noise_bound,
+                                                       p->rotation_max_iterations, p->rotation_gnc_factor,
+                                                       p->rotation_cost_threshold, p->noise_bound_radial,
+                                                       p->noise_bound_tangential, b.d_info, b.d_T, b.d_clique,
+                                                       b.d_final);
+    NRS_LAUNCHED();
+    unsigned char *h = ctx->pin[0].as<unsigned char>();
+    SolverInfoDev *h_info = (SolverInfoDev *)h;
+    double *h_T = (double *)(h + align_up(sizeof(SolverInfoDev)));
+    int *h_edges = (int *)(h_T + 16) + 2 * MAXN;
+    NRS_CUDA(cudaMemcpyAsync(h_info, b.d_info, sizeof(SolverInfoDev), cudaMemcpyDeviceToHost, st));
+    NRS_CUDA(cudaMemcpyAsync(h_T, b.d_T, 16 * 8, cudaMemcpyDeviceToHost, st));
+    NRS_CUDA(cudaMemcpyAsync(h_edges, b.d_edges, 4, cudaMemcpyDeviceToHost, st));
+    return NRS_OK;
+}
+
+// after the caller's synchronisation: N = the match count it read back.  Applies the host rules of
+// orora_solve_locked; counts the speculative launch did not cover are solved again with the host-sized launch.
+int nrs::orora_pair_finish(nrs_ctx *ctx, const double *d_prev, const double *d_curr, int N, const nrs_solver_params *p,
+                           double vel_x, double T_out[16], nrs_solver_info *info_out)
+{
+    const bool gated = (p->check_stop_motion && N > p->num_feat_thr_for_stop_motion) || N < 2;
+    if (N > MAXN || gated || N > FUSE_ORDER_MAXN)
+        return orora_solve_locked(ctx, d_prev, d_curr, true, N, p, vel_x, T_out, nullptr, nullptr, info_out);
+    memset(info_out, 0, sizeof(*info_out));
+    info_out->clique_exact = 1;
+    unsigned char *h = ctx->pin[0].as<unsigned char>();
+    const SolverInfoDev *h_info = (const SolverInfoDev *)h;
+    const double *h_T = (const double *)(h + align_up(sizeof(SolverInfoDev)));
+    const int *h_edges = (const int *)(h_T + 16) + 2 * MAXN;
+    read_solver_result(h_info, h_T, *h_edges, T_out, info_out);
     return NRS_OK;
 }
 

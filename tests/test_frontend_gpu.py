@@ -241,3 +241,44 @@ def test_fused_pair_equals_separate_calls(nrs, ctx, synth, world, extraction):
         assert np.array_equal(d["img"], feats[k].img_) and np.array_equal(d["polar"], feats[k].feat_in_polar_)
         vel = T[0, 3] / 0.25
         prev = fr
+
+
+def test_fused_pair_size_rules(nrs, ctx, synth, world):
+    """The fused call enqueues the solver before it knows the match count: the host-side rules must come out the
+    same as through nrs_orora_solve -- the stop-motion gate (identical frames: ~1900 matches > 700), the capacity
+    error above 1024 matches without the gate, the host-sized second solve for counts between 512 and 1024 (coarse
+    voxels on identical frames), and a pair with too few matches (unrelated frame)."""
+    orr = nrs.orora
+    raw = synth.radar_frame(world, (0.0, 0.0, 0.0), seed=900)
+    # 1. stop-motion gate and capacity
+    loader = orr.RadarLoader("mulran", "cen2019", 0.6, True, False, ctx=ctx)
+    f0 = loader.extractFeatureFromRows(raw, 0)
+    pm, cm = loader.matchFeatures(f0, f0)
+    n_same = pm.feat_in_cart_.shape[1]
+    assert n_same > 1024
+    sp = orr.default_params()
+    fr, T, n, info = orr.pair(ctx, f0.handle, raw, loader.params, sp, 0.0, t_criteria=1)
+    assert n == n_same and info.stop_motion == 1 and np.array_equal(T, np.eye(4))
+    sp.check_stop_motion = 0
+    with pytest.raises(nrs._lib.NrsError) as e:
+        orr.pair(ctx, f0.handle, raw, loader.params, sp, 0.0, t_criteria=1)
+    assert e.value.code == nrs._lib.NRS_ECAPACITY
+    # 2. between the speculative launch's 512 and the solver's 1024: solved again with the host-sized launch
+    for leaf in (2.5, 3.0, 3.5, 4.0, 5.0):
+        lc = orr.RadarLoader("mulran", "cen2019", leaf, True, False, ctx=ctx)
+        g0 = lc.extractFeatureFromRows(raw, 0)
+        pm, cm = lc.matchFeatures(g0, g0)
+        n_mid = pm.feat_in_cart_.shape[1]
+        if 512 < n_mid <= 1024:
+            break
+    assert 512 < n_mid <= 1024, n_mid
+    r = orr.solve(ctx, pm.feat_in_cart_, cm.feat_in_cart_, sp, 0.0)
+    fr, T, n, info = orr.pair(ctx, g0.handle, raw, lc.params, sp, 0.0, t_criteria=1)
+    assert n == n_mid and info.M == r["info"].M and info.n_edges == r["info"].n_edges and np.array_equal(T, r["T"])
+    # 3. (almost) no matches: a frame of another world
+    other = synth.radar_frame(synth.radar_world(seed=4321), (0.0, 0.0, 0.0), seed=901)
+    h0 = loader.extractFeatureFromRows(other, 0)
+    pm, cm = loader.matchFeatures(f0, h0)
+    r = orr.solve(ctx, pm.feat_in_cart_, cm.feat_in_cart_, sp, 0.0)
+    fr, T, n, info = orr.pair(ctx, f0.handle, other, loader.params, sp, 0.0, t_criteria=1)
+    assert n == pm.feat_in_cart_.shape[1] and info.M == r["info"].M and np.array_equal(T, r["T"])
