@@ -142,6 +142,10 @@ int nrs_sc_detect_knn_batch(nrs_sc_db *db, const double *queries_host, int Q, in
  * general-valued search, and the 256-byte bit-mask record of the {0,c} search (below) */
 int nrs_sc_filter_record_bytes(void);
 int nrs_sc_bin_record_bytes(void);
+/* 1 when a 20x60 descriptor (host memory, no GPU involved) is {0, c} with a c the bit-mask kernel accepts (finite,
+ * positive, exact in float, moderate magnitude) -- the host-side test that routes a query to the bit-mask or the
+ * general-valued kernel; +-0.0 count as empty bins, NaN as a value. */
+int nrs_sc_descriptor_is_binary(const double *desc1200);
 
 /* {0,c} descriptors.  In this pipeline every occupied bin holds the same value (ORORA publishes
  * z = 1.0, ORORA/src/odometry.cpp:305-316; makeScancontext adds LIDAR_HEIGHT, Scancontext.cpp:168),

@@ -132,6 +132,7 @@ def _declare(L):
     L.nrs_sc_knn.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.nrs_sc_detect_knn.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.nrs_sc_detect_knn_batch.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    L.nrs_sc_descriptor_is_binary.argtypes = [vp]
     L.nrs_sc_xchg_create.argtypes = [vp, i32, i32, vp]
     L.nrs_sc_xchg_open.argtypes = [vp, vp]
     L.nrs_sc_query_dev_sharded.argtypes = [vp, vp, i32, i32, vp]

@@ -23,6 +23,7 @@
 // the last CTA also exchanges the per-rank records over peer memory (XchgView).
 // Bound: HBM by design; algorithmic bytes per keyframe = 9600 (f64 20x60, the reference's
 // MatrixXd), per query = 9600*D + 9600 + 16; bytes actually streamed = 5536*D + survivors.
+#include <immintrin.h>
 #include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1250,21 +1251,44 @@ const double *nrs_sc_db_device_ptr(nrs_sc_db *db) { return db ? db->d_desc : nul
 int nrs_sc_filter_record_bytes(void) { return FREC_BYTES; }
 
 // {0,c} query?  (the host-side twin of prep_query's classification in sc_search_bin.cu)
+static_assert(DESC % 4 == 0, "the host classification walks the descriptor four values at a time");
+__attribute__((target("avx2"))) static void query_bits_avx2(const double *q, unsigned long long &pa, unsigned long long &po)
+{
+    __m256i A = _mm256_set1_epi64x(-1), O = _mm256_setzero_si256();
+    const __m256i zero = _mm256_setzero_si256();
+    for (int i = 0; i < DESC; i += 4) {
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(q + i));
+        const __m256i z = _mm256_cmpeq_epi64(_mm256_slli_epi64(b, 1), zero);    // all ones where the value is +-0.0
+        A = _mm256_and_si256(A, _mm256_or_si256(b, z));
+        O = _mm256_or_si256(O, _mm256_andnot_si256(z, b));
+    }
+    alignas(32) unsigned long long a[4], o[4];
+    _mm256_store_si256(reinterpret_cast<__m256i *>(a), A);
+    _mm256_store_si256(reinterpret_cast<__m256i *>(o), O);
+    pa = a[0] & a[1] & a[2] & a[3];
+    po = o[0] | o[1] | o[2] | o[3];
+}
+
 static bool host_query_is_binary(const double *q)
 {
-    // branch-free, four independent accumulator pairs (the compiler vectorises it): this runs on the host between the
-    // enqueue of a batch's upload and its launch, 1200 values per query
-    unsigned long long pa4[4] = {~0ull, ~0ull, ~0ull, ~0ull}, po4[4] = {0ull, 0ull, 0ull, 0ull};
-    static_assert(DESC % 4 == 0, "unrolled by four");
-    for (int i = 0; i < DESC; i += 4)
-        for (int k = 0; k < 4; ++k) {
-            unsigned long long b;
-            memcpy(&b, &q[i + k], sizeof(b));
-            const unsigned long long m = (b << 1) ? ~0ull : 0ull;        // +-0.0 -> not counted (q == 0.0), NaN counted
-            pa4[k] &= b | ~m;
-            po4[k] |= b & m;
-        }
-    const unsigned long long pa = pa4[0] & pa4[1] & pa4[2] & pa4[3], po = po4[0] | po4[1] | po4[2] | po4[3];
+    // this runs on the host between the enqueue of a batch's upload and its launch, 1200 values per query: AND / OR of
+    // the bit patterns of the non-zero entries, branch-free, 4 values per step with AVX2 where the CPU has it
+    unsigned long long pa, po;
+    static const bool has_avx2 = __builtin_cpu_supports("avx2");
+    if (has_avx2) {
+        query_bits_avx2(q, pa, po);
+    } else {
+        unsigned long long pa4[4] = {~0ull, ~0ull, ~0ull, ~0ull}, po4[4] = {0ull, 0ull, 0ull, 0ull};
+        for (int i = 0; i < DESC; i += 4)
+            for (int k = 0; k < 4; ++k) {
+                unsigned long long b;
+                memcpy(&b, &q[i + k], sizeof(b));
+                const unsigned long long m = (b << 1) ? ~0ull : 0ull;    // +-0.0 -> not counted (q == 0.0), NaN counted
+                pa4[k] &= b | ~m;
+                po4[k] |= b & m;
+            }
+        pa = pa4[0] & pa4[1] & pa4[2] & pa4[3]; po = po4[0] | po4[1] | po4[2] | po4[3];
+    }
     if (po == 0ull) return true;
     if (pa != po) return false;
     double c;
@@ -1464,6 +1488,12 @@ int nrs_sc_db_is_binary(nrs_sc_db *db)
 }
 
 int nrs_sc_bin_record_bytes(void) { return BIN_WORDS * (int)sizeof(unsigned int); }
+
+int nrs_sc_descriptor_is_binary(const double *desc)
+{
+    if (!desc) return NRS_EINVAL;
+    return host_query_is_binary(desc) ? 1 : 0;
+}
 
 int nrs_sc_xchg_set_timeout_ms(nrs_sc_db *db, int ms)
 {

@@ -368,6 +368,9 @@ sc_search_bin_kernel(const unsigned int *__restrict__ brec, const double *__rest
                 {
                     const int e0 = 2 * lb + wrap60(s0 - RADIUS);        // <= 58 + 59; + 7 < 128
                     const float rk0 = sm.rtab[n0], rk1 = sm.rtab[n1];
+                    // (eight 8-byte loads at a 16-byte lane stride: twice the minimal shared-memory wavefronts, yet measured
+                    // 2 % faster than four aligned 16-byte loads from two staggered copies of the list -- the kernel is
+                    // issue-bound, not LSU-bound, and the wide loads lengthen the dependent chain)
                     uint2 qe[NSHIFT + 1];
 #pragma unroll
                     for (int i = 0; i < NSHIFT + 1; ++i) qe[i] = sm.qcol[e0 + i];

@@ -110,3 +110,41 @@ def test_every_symbol_has_a_ctypes_signature(nrs):
 def importlib_lib(nrs):
     import importlib
     return importlib.import_module("navtech-radar-slam_b200._lib")
+
+
+def test_host_descriptor_classification(nrs):
+    """nrs_sc_descriptor_is_binary (the host-side routing test between the bit-mask and the general-valued kernel; AVX2
+    where the CPU has it) against a plain numpy statement of the rule: all non-zero entries carry the same bit
+    pattern c, c finite, positive, exact in float and of moderate magnitude; +-0.0 are empty bins; NaN is a value."""
+    import ctypes as C
+    import numpy as np
+    L = nrs.lib()
+    rng = np.random.default_rng(5)
+
+    def rule(d):
+        nz = d[~(d == 0.0)]                     # NaN counts as a value, -0.0 does not
+        if nz.size == 0:
+            return 1
+        bits = nz.view(np.uint64)
+        if not np.all(bits == bits[0]):
+            return 0
+        c = float(nz[0])
+        return int(c > 0.0 and float(np.float32(c)) == c and 7.888609052210118e-31 <= c <= 1.2676506002282294e30)
+
+    cases = []
+    for _ in range(40):
+        d = np.where(rng.random(1200) < rng.uniform(0.0, 0.6), 3.0, 0.0)
+        cases.append(d)
+    d = cases[0].copy(); d[rng.integers(1200)] = 3.0000000000000004; cases.append(d)        # one ulp off in one bin
+    d = cases[1].copy(); d[d == 0.0][:0] = 0.0; d[7] = -0.0; d[8] = -0.0; cases.append(d)   # negative zeros are empty bins
+    d = cases[2].copy(); d[1199] = np.nan; cases.append(d)                                   # NaN in the last lane
+    d = np.zeros(1200); cases.append(d)                                                      # empty descriptor
+    d = np.zeros(1200); d[::7] = 0.1; cases.append(d)                                        # c not exact in float
+    d = np.zeros(1200); d[::7] = -2.0; cases.append(d)                                       # negative c
+    d = np.zeros(1200); d[3] = 2.5; d[1197] = 2.5; cases.append(d)                           # sparse, first / last vector lanes
+    d = np.zeros(1200); d[5] = 1e-40; cases.append(d)                                        # tiny c
+    d = np.zeros(1200); d[0] = np.inf; cases.append(d)
+    d = rng.uniform(0.5, 4.0, 1200); cases.append(d)                                         # general-valued
+    for k, d in enumerate(cases):
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        assert L.nrs_sc_descriptor_is_binary(d.ctypes.data_as(C.c_void_p)) == rule(d), k
