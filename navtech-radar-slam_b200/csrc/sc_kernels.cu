@@ -1143,6 +1143,8 @@ int nrs_sc_db_destroy(nrs_sc_db *db)
     cudaFree(db->d_brec); cudaFree(db->d_ngen); cudaFree(db->d_bstate); cudaFree(db->d_gticket);
     cudaFree(db->d_queries); cudaFree(db->d_results);
     db->bin_surv.release(); db->bin_block.release();
+    if (db->up_stream) cudaStreamDestroy(db->up_stream);
+    for (cudaEvent_t e : db->up_event) if (e) cudaEventDestroy(e);
     db->knn_rec.release(); db->knn_part.release(); db->knn_host.release();
     if (db->h_result) cudaFreeHost(db->h_result);
     if (db->h_query) cudaFreeHost(db->h_query);
@@ -1450,22 +1452,39 @@ int nrs_sc_query_batch(nrs_sc_db *db, const double *queries_host, int Q, int fir
     std::lock_guard<std::mutex> lk2(ctx->mu);
     NRS_CUDA(cudaSetDevice(ctx->device));
     const int n_items = std::max(0, last - first);
+    if (!db->up_stream) {
+        NRS_CUDA(cudaStreamCreateWithFlags(&db->up_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t &e : db->up_event) NRS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     for (int done = 0; done < Q; done += XCHG_QCAP) {
         const int q = std::min(XCHG_QCAP, Q - done);
         const double *src = queries_host + (size_t)done * DESC;
-        // straight from the caller's buffer (true DMA when it is pinned, driver-staged when pageable)
-        NRS_CUDA(cudaMemcpyAsync(db->d_queries, src, (size_t)q * DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        bool all_bin = db_bin_ok(db);
-        for (int i = 0; all_bin && i < q; ++i) all_bin = host_query_is_binary(src + (size_t)i * DESC);
-        int rc = NRS_OK;
-        if (all_bin) {
-            rc = nrs_sc::bin_launch(db, db->d_queries, q, nullptr, first, n_items, 1, 0, db->d_results, XV_NONE);
-        } else {
-            for (int i = 0; i < q && !rc; ++i)
-                rc = launch_search(ctx, view_of(db), db->d_queries + (size_t)i * DESC, nullptr, first, n_items, 0, nullptr, nullptr,
-                                   db->d_block, db->d_state, db->d_results + i, db->max_blocks);
+        // A large group goes up in (at most) four slices on a second stream, straight from the caller's buffer (true DMA
+        // when it is pinned, driver-staged when pageable): slice k's upload and its host-side classification overlap
+        // the search of slice k - 1, so only the first slice's copy stays on the critical path.
+        const int n_sl = (q >= 128 && db_bin_ok(db)) ? 4 : 1;
+        const int per = ((q + n_sl - 1) / n_sl + 31) & ~31;
+        NRS_CUDA(cudaEventRecord(db->up_event[0], ctx->stream));                 // d_queries / d_results are free again
+        NRS_CUDA(cudaStreamWaitEvent(db->up_stream, db->up_event[0], 0));
+        int rc = NRS_OK, k = 0;
+        for (int off = 0; off < q && !rc; off += per, ++k) {
+            const int qs = std::min(per, q - off);
+            const double *ssrc = src + (size_t)off * DESC;
+            double *dq = db->d_queries + (size_t)off * DESC;
+            NRS_CUDA(cudaMemcpyAsync(dq, ssrc, (size_t)qs * DESC * sizeof(double), cudaMemcpyHostToDevice, db->up_stream));
+            NRS_CUDA(cudaEventRecord(db->up_event[k & 3], db->up_stream));
+            bool all_bin = db_bin_ok(db);
+            for (int i = 0; all_bin && i < qs; ++i) all_bin = host_query_is_binary(ssrc + (size_t)i * DESC);
+            NRS_CUDA(cudaStreamWaitEvent(ctx->stream, db->up_event[k & 3], 0));
+            if (all_bin) {
+                rc = nrs_sc::bin_launch(db, dq, qs, nullptr, first, n_items, 1, 0, db->d_results + off, XV_NONE);
+            } else {
+                for (int i = 0; i < qs && !rc; ++i)
+                    rc = launch_search(ctx, view_of(db), dq + (size_t)i * DESC, nullptr, first, n_items, 0, nullptr, nullptr,
+                                       db->d_block, db->d_state, db->d_results + off + i, db->max_blocks);
+            }
         }
-        if (rc) return rc;
+        if (rc) { cudaStreamSynchronize(db->up_stream); cudaStreamSynchronize(ctx->stream); return rc; }
         NRS_CUDA(cudaMemcpyAsync(results_host + done, db->d_results, (size_t)q * sizeof(nrs_sc_result), cudaMemcpyDeviceToHost, ctx->stream));
         NRS_CUDA(cudaStreamSynchronize(ctx->stream));
     }

@@ -282,3 +282,28 @@ def test_fused_pair_size_rules(nrs, ctx, synth, world):
     r = orr.solve(ctx, pm.feat_in_cart_, cm.feat_in_cart_, sp, 0.0)
     fr, T, n, info = orr.pair(ctx, f0.handle, other, loader.params, sp, 0.0, t_criteria=1)
     assert n == pm.feat_in_cart_.shape[1] and info.M == r["info"].M and np.array_equal(T, r["T"])
+
+
+@pytest.mark.parametrize("extraction", ["cen2019", "cen2018"])
+def test_extract_degenerate_frames(nrs, ctx, synth, world, extraction):
+    """The fused kernels on frames with nothing (or almost nothing) in them: an all-zero frame gives an empty feature
+    set without tripping the staging rows, the in-shared-memory sorts or the cluster sort (zero items, zero passes);
+    a frame with one bright blob gives a handful of keypoints; and a normal frame right after is unaffected by the
+    threshold the empty frames carried over (the extraction never depends on it)."""
+    orr = nrs.orora
+    loader = orr.RadarLoader("mulran", extraction, 0.6, True, False, ctx=ctx)
+    normal = synth.radar_frame(world, (0.0, 0.0, 0.0), seed=77)
+    ref = loader.extractFeatureFromRows(normal, 0)
+    blank = normal.copy()
+    blank[:, 11:] = 0
+    for rep in range(2):                                              # twice: the second run replays the cached graph
+        f = loader.extractFeatureFromRows(blank, 1 + rep)
+        assert f.feat_in_cart_.shape[1] == 0 and f.desc_.shape[0] == 0
+    blob = blank.copy()
+    blob[100:104, 11 + 800:11 + 806] = 255
+    blob[300:303, 11 + 1500:11 + 1504] = 200
+    f = loader.extractFeatureFromRows(blob, 3)
+    assert f.feat_in_polar_.shape[1] <= 200 and f.feat_in_cart_.shape[1] <= f.feat_in_polar_.shape[1]
+    again = loader.extractFeatureFromRows(normal, 4)
+    assert np.array_equal(again.feat_in_polar_, ref.feat_in_polar_) and np.array_equal(again.desc_, ref.desc_)
+    assert np.array_equal(again.feat_in_cart_, ref.feat_in_cart_)
