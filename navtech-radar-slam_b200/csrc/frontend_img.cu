@@ -598,11 +598,15 @@ const EncoderTable &encoder_table()
 int extract_upload(nrs_ctx *ctx, FrontendState *S, const uint8_t *raw, int R, int row_pitch, HostTables &H)
 {
     cudaStream_t st = ctx->stream;
+    // the frame goes first: its 1.35 MB are on the wire while the host walks the row headers (one cache-cold line per
+    // azimuth) and builds the tables
+    NRS_CUDA(cudaMemcpyAsync(S->d_raw, raw, (size_t)R * row_pitch, cudaMemcpyHostToDevice, st));
     const EncoderTable &E = encoder_table();
     AzTables &T = *S->h_tables;          // pinned; the previous frame's copy finished before its call returned
     bool increasing = true;
     for (int i = 0; i < R; ++i) {
         const uint8_t *row = raw + (size_t)i * row_pitch;
+        if (i + 8 < R) __builtin_prefetch(row + (size_t)8 * row_pitch);
         int64_t stamp; uint16_t enc;
         memcpy(&stamp, row, 8);
         memcpy(&enc, row + 8, 2);
@@ -631,7 +635,6 @@ int extract_upload(nrs_ctx *ctx, FrontendState *S, const uint8_t *raw, int R, in
             T.azs[H.n_sorted] = T.az[i]; T.azi[H.n_sorted] = i; ++H.n_sorted;
         }
     }
-    NRS_CUDA(cudaMemcpyAsync(S->d_raw, raw, (size_t)R * row_pitch, cudaMemcpyHostToDevice, st));
     NRS_CUDA(cudaMemcpyAsync(S->d_tables, S->h_tables, sizeof(AzTables), cudaMemcpyHostToDevice, st));
     return NRS_OK;
 }

@@ -280,8 +280,6 @@ struct nrs_sc_db {
     nrs_sc::SearchState *d_bstate = nullptr;      // XCHG_QCAP entries
     unsigned int  *d_gticket = nullptr;
     nrs::DevBuf    bin_surv, bin_block;
-    cudaStream_t   up_stream = nullptr;   // host batches: a batch's upload is cut in slices that overlap the search of the slice before
-    cudaEvent_t    up_event[4] = {nullptr, nullptr, nullptr, nullptr};
     nrs::DevBuf    knn_rec, knn_part;   // batched k-NN: one 72-float record per query, per-block partial lists
     nrs::PinBuf    knn_host;            // ... and the records' pinned landing zone
     double        *d_queries = nullptr;  // batch staging: XCHG_QCAP x 1200 doubles (device) ...

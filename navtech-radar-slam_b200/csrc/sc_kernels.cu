@@ -1143,8 +1143,6 @@ int nrs_sc_db_destroy(nrs_sc_db *db)
     cudaFree(db->d_brec); cudaFree(db->d_ngen); cudaFree(db->d_bstate); cudaFree(db->d_gticket);
     cudaFree(db->d_queries); cudaFree(db->d_results);
     db->bin_surv.release(); db->bin_block.release();
-    if (db->up_stream) cudaStreamDestroy(db->up_stream);
-    for (cudaEvent_t e : db->up_event) if (e) cudaEventDestroy(e);
     db->knn_rec.release(); db->knn_part.release(); db->knn_host.release();
     if (db->h_result) cudaFreeHost(db->h_result);
     if (db->h_query) cudaFreeHost(db->h_query);
@@ -1254,11 +1252,11 @@ int nrs_sc_filter_record_bytes(void) { return FREC_BYTES; }
 
 // {0,c} query?  (the host-side twin of prep_query's classification in sc_search_bin.cu)
 static_assert(DESC % 4 == 0, "the host classification walks the descriptor four values at a time");
-__attribute__((target("avx2"))) static void query_bits_avx2(const double *q, unsigned long long &pa, unsigned long long &po)
+__attribute__((target("avx2"))) static void query_bits_avx2(const double *q, int n, unsigned long long &pa, unsigned long long &po)
 {
     __m256i A = _mm256_set1_epi64x(-1), O = _mm256_setzero_si256();
     const __m256i zero = _mm256_setzero_si256();
-    for (int i = 0; i < DESC; i += 4) {
+    for (int i = 0; i < n; i += 4) {
         const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(q + i));
         const __m256i z = _mm256_cmpeq_epi64(_mm256_slli_epi64(b, 1), zero);    // all ones where the value is +-0.0
         A = _mm256_and_si256(A, _mm256_or_si256(b, z));
@@ -1271,17 +1269,17 @@ __attribute__((target("avx2"))) static void query_bits_avx2(const double *q, uns
     po = o[0] | o[1] | o[2] | o[3];
 }
 
-static bool host_query_is_binary(const double *q)
+// the {0, c} rule over the first n (multiple of 4) values of a descriptor
+static bool host_values_are_binary(const double *q, int n)
 {
-    // this runs on the host between the enqueue of a batch's upload and its launch, 1200 values per query: AND / OR of
-    // the bit patterns of the non-zero entries, branch-free, 4 values per step with AVX2 where the CPU has it
+    // AND / OR of the bit patterns of the non-zero entries, branch-free, 4 values per step with AVX2 where the CPU has it
     unsigned long long pa, po;
     static const bool has_avx2 = __builtin_cpu_supports("avx2");
     if (has_avx2) {
-        query_bits_avx2(q, pa, po);
+        query_bits_avx2(q, n, pa, po);
     } else {
         unsigned long long pa4[4] = {~0ull, ~0ull, ~0ull, ~0ull}, po4[4] = {0ull, 0ull, 0ull, 0ull};
-        for (int i = 0; i < DESC; i += 4)
+        for (int i = 0; i < n; i += 4)
             for (int k = 0; k < 4; ++k) {
                 unsigned long long b;
                 memcpy(&b, &q[i + k], sizeof(b));
@@ -1297,6 +1295,14 @@ static bool host_query_is_binary(const double *q)
     memcpy(&c, &po, sizeof(c));
     return (c > 0.0) && ((double)(float)c == c) && (c >= 7.888609052210118e-31) && (c <= 1.2676506002282294e30);
 }
+static bool host_query_is_binary(const double *q) { return host_values_are_binary(q, DESC); }
+// Batches: reading every byte of 256 descriptors (2.4 MB, cache-cold behind the DMA) costs a host core ~0.2 ms per
+// launch, more than the upload itself.  The routing test therefore looks at the first twelve columns only: a query it
+// lets through although it is general-valued further on is still answered exactly -- the bit-mask kernel classifies
+// every query itself and evaluates such a one in f64 from the canonical descriptors -- only slower than the general
+// kernel would have been.
+constexpr int ROUTE_SAMPLE = 12 * R;
+static bool host_query_looks_binary(const double *q) { return host_values_are_binary(q, ROUTE_SAMPLE); }
 static inline bool db_bin_ok(const nrs_sc_db *db) { return db->search_mode == 0 && db->n_general == 0; }
 static const XchgView XV_NONE{nullptr, 0, 0, 0u, 0ll, 0};
 
@@ -1452,39 +1458,24 @@ int nrs_sc_query_batch(nrs_sc_db *db, const double *queries_host, int Q, int fir
     std::lock_guard<std::mutex> lk2(ctx->mu);
     NRS_CUDA(cudaSetDevice(ctx->device));
     const int n_items = std::max(0, last - first);
-    if (!db->up_stream) {
-        NRS_CUDA(cudaStreamCreateWithFlags(&db->up_stream, cudaStreamNonBlocking));
-        for (cudaEvent_t &e : db->up_event) NRS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
     for (int done = 0; done < Q; done += XCHG_QCAP) {
         const int q = std::min(XCHG_QCAP, Q - done);
         const double *src = queries_host + (size_t)done * DESC;
-        // A large group goes up in (at most) four slices on a second stream, straight from the caller's buffer (true DMA
-        // when it is pinned, driver-staged when pageable): slice k's upload and its host-side classification overlap
-        // the search of slice k - 1, so only the first slice's copy stays on the critical path.
-        const int n_sl = (q >= 128 && db_bin_ok(db)) ? 4 : 1;
-        const int per = ((q + n_sl - 1) / n_sl + 31) & ~31;
-        NRS_CUDA(cudaEventRecord(db->up_event[0], ctx->stream));                 // d_queries / d_results are free again
-        NRS_CUDA(cudaStreamWaitEvent(db->up_stream, db->up_event[0], 0));
-        int rc = NRS_OK, k = 0;
-        for (int off = 0; off < q && !rc; off += per, ++k) {
-            const int qs = std::min(per, q - off);
-            const double *ssrc = src + (size_t)off * DESC;
-            double *dq = db->d_queries + (size_t)off * DESC;
-            NRS_CUDA(cudaMemcpyAsync(dq, ssrc, (size_t)qs * DESC * sizeof(double), cudaMemcpyHostToDevice, db->up_stream));
-            NRS_CUDA(cudaEventRecord(db->up_event[k & 3], db->up_stream));
-            bool all_bin = db_bin_ok(db);
-            for (int i = 0; all_bin && i < qs; ++i) all_bin = host_query_is_binary(ssrc + (size_t)i * DESC);
-            NRS_CUDA(cudaStreamWaitEvent(ctx->stream, db->up_event[k & 3], 0));
-            if (all_bin) {
-                rc = nrs_sc::bin_launch(db, dq, qs, nullptr, first, n_items, 1, 0, db->d_results + off, XV_NONE);
-            } else {
-                for (int i = 0; i < qs && !rc; ++i)
-                    rc = launch_search(ctx, view_of(db), dq + (size_t)i * DESC, nullptr, first, n_items, 0, nullptr, nullptr,
-                                       db->d_block, db->d_state, db->d_results + off + i, db->max_blocks);
-            }
+        // straight from the caller's buffer (true DMA when it is pinned, driver-staged when pageable); the routing test
+        // below runs on the host while the copy is in flight.  (Cutting the group into slices whose uploads overlap the
+        // search of the slice before was measured and is slower: 64-query launches lose more than the 57 us copy costs.)
+        NRS_CUDA(cudaMemcpyAsync(db->d_queries, src, (size_t)q * DESC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        bool all_bin = db_bin_ok(db);
+        for (int i = 0; all_bin && i < q; ++i) all_bin = host_query_looks_binary(src + (size_t)i * DESC);
+        int rc = NRS_OK;
+        if (all_bin) {
+            rc = nrs_sc::bin_launch(db, db->d_queries, q, nullptr, first, n_items, 1, 0, db->d_results, XV_NONE);
+        } else {
+            for (int i = 0; i < q && !rc; ++i)
+                rc = launch_search(ctx, view_of(db), db->d_queries + (size_t)i * DESC, nullptr, first, n_items, 0, nullptr, nullptr,
+                                   db->d_block, db->d_state, db->d_results + i, db->max_blocks);
         }
-        if (rc) { cudaStreamSynchronize(db->up_stream); cudaStreamSynchronize(ctx->stream); return rc; }
+        if (rc) return rc;
         NRS_CUDA(cudaMemcpyAsync(results_host + done, db->d_results, (size_t)q * sizeof(nrs_sc_result), cudaMemcpyDeviceToHost, ctx->stream));
         NRS_CUDA(cudaStreamSynchronize(ctx->stream));
     }
@@ -1638,7 +1629,7 @@ int nrs_sc_detect_knn_batch(nrs_sc_db *db, const double *queries_host, int Q, in
                                                                       pd, pi, part_stride, rec);
         NRS_LAUNCHED();
         bool all_bin = db_bin_ok(db);
-        for (int i = 0; all_bin && i < q; ++i) all_bin = host_query_is_binary(src + (size_t)i * DESC);
+        for (int i = 0; all_bin && i < q; ++i) all_bin = host_query_looks_binary(src + (size_t)i * DESC);
         const int32_t *d_cand = reinterpret_cast<const int32_t *>(rec + 32);
         if (all_bin) {
             rc = nrs_sc::bin_launch(db, db->d_queries, q, d_cand, 0, k, 1, 0, db->d_results, XV_NONE, KNN_REC);

@@ -104,14 +104,22 @@ def test_bin_batch(sc, ctx, oracle, synth):
     for g, q in zip(got[::37], many[::37]):
         assert same(g, oracle.sc_search(q, small, want_all=False)[2])
     assert same(got[1099], oracle.sc_search(many[1099], small, want_all=False)[2])
-    # a host batch goes up in slices that overlap the search of the slice before (ragged last slice: 300 = 96 + 96 +
-    # 96 + 12); a slice that holds a general-valued query takes the general kernel, the others the bit-mask kernel
+    # host batches are routed by a test of the first twelve columns only: a batch with visibly general-valued queries
+    # takes the general kernel; a query that is general-valued only further on reaches the bit-mask kernel, which
+    # classifies every query itself and answers such a one exactly from the canonical descriptors
     mixed = small[rng.integers(0, 40, 300)].copy()
     for k in (5, 100, 299):
         mixed[k] = mixed[k] * rng.uniform(0.5, 1.5, 1200)
     got = d.query_batch(mixed)
     for k in list(range(0, 300, 23)) + [5, 100, 299]:
         assert same(got[k], oracle.sc_search(mixed[k], small, want_all=False)[2]), k
+    late = small[rng.integers(0, 40, 200)].copy()
+    for k in (0, 77, 199):
+        late[k, 700:] = late[k, 700:] * rng.uniform(0.5, 1.5, 500)      # columns 35..59 only
+        late[k, :240] = small[3, :240]
+    got = d.query_batch(late)
+    for k in list(range(0, 200, 19)) + [0, 77, 199]:
+        assert same(got[k], oracle.sc_search(late[k], small, want_all=False)[2]), k
     d.close()
 
 
