@@ -352,7 +352,8 @@ int nrs_frame_extract(nrs_ctx *ctx, const uint8_t *raw_rows, int R, int row_pitc
 int nrs_frame_destroy(nrs_frame *f);
 int nrs_frame_info_get(const nrs_frame *f, nrs_frame_info *info);
 /* diagnostics: %globaltimer (ns) stamps of the most recent extraction's tail kernel on this context:
- * [0] entered, [1] row offsets scanned, [2] points made, [3] voxel keys made, [4] sorted, [5] centroids + BEV done */
+ * [0] entered, [1] row offsets scanned, [2] points made, [3] voxel keys made, [4] sorted, [5] centroids + BEV done;
+ * [6], [7] are not stamps: the radix passes the candidate-subset sort and the voxel sort took */
 int nrs_frontend_tail_times(nrs_ctx *ctx, uint64_t *t_ns8);
 /* copy products to host; any pointer may be NULL.  Sizes: polar 3 x K_polar doubles (col-major),
  * feat_in_cart 3 x K doubles (row 2 = 0 with voxelisation, 1 without), t K int64, t_norm K doubles,

@@ -9,21 +9,28 @@
 // cen2019 is NOT purely per-azimuth in the reference: it has three global reductions, a global
 // descending sort of every pixel with h > mean(h) and a sequential region-marking loop that
 // stops after max_points fresh regions.  The loop is parallelised EXACTLY:
-//   K1  fe_decode / fe_stats / fe_h     elementwise f32 passes in the reference's operation order
-//                                       (Prewitt |f[j+1]-f[j-1]|, /max, s = f-mean, h = s*(1-g)),
-//                                       f64 block sums combined in a fixed order, max by atomics.
-//   K2  sort + claim                    all R*C (key = h or -FLT_MAX, value = pixel) pairs are radix
-//                                       sorted descending (stable -> ties keep pixel order, which is
-//                                       how the oracle restates std::sort); candidate k claims its
-//                                       region [rlow, rhigh] (findRangeBoundaries incl. the s.rows
-//                                       quirk) with atomicMin(rank); a region counts as fresh iff it
-//                                       owns all of its pixels; an inclusive scan finds the rank J at
-//                                       which the max_points-th fresh region appears; the marked matrix
-//                                       R is { pixel : claim <= J }.
-//   K3  fe_scan_rows                    one warp per azimuth: maximal marked runs (ballot), adjacency
-//                                       test against the neighbouring azimuths (wrap-around),
-//                                       getMaxInRegion's int-truncated running max, ordered emission.
-// Bound: HBM (R*C*4 = 5.4 MB per frame plus the sort's passes); DESIGN.md gives the byte counts.
+//   K1  fe_decode_stats / fe_h          the decode and the reference's elementwise f32 passes in its operation order
+//                                       (Prewitt |f[j+1]-f[j-1]|, /max, s = f-mean, h = s*(1-g)), one CTA per azimuth;
+//                                       f64 block sums combined in a fixed order by the CTA that draws the last
+//                                       ticket, max by atomics.  (fe_decode / fe_stats: the standalone operators.)
+//   K2  sort + claim                    (key = h, value = pixel) pairs sorted descending, stable -> ties keep pixel
+//                                       order, which is how the oracle restates std::sort.  Steady state: only the
+//                                       pixels above a threshold carried from the previous frame are compacted
+//                                       (cub::DeviceSelect) and sorted by fe_subsort_kernel -- a thread-block cluster
+//                                       holding the pairs in distributed shared memory; first frame / fallback: all
+//                                       R*C pairs through cub::DeviceRadixSort.  Candidate k claims its region
+//                                       [rlow, rhigh] (findRangeBoundaries incl. the s.rows quirk) with
+//                                       atomicMin(rank); a region counts as fresh iff it owns all of its pixels;
+//                                       the last CTA of fe_incr_kernel finds the rank J at which the max_points-th
+//                                       fresh region appears; the marked matrix R is { pixel : claim <= J }.
+//   K3  fe_scan_rows / fe_tail          one CTA per azimuth: the row as one bit per column, maximal marked runs,
+//                                       adjacency test against the neighbouring azimuths (wrap-around),
+//                                       getMaxInRegion's int-truncated running max, into the azimuth's staging row;
+//                                       fe_tail_kernel (one CTA) strings the rows together and does everything
+//                                       from polar_to_cartesian_points to the BEV / ORB border filters, incl. the
+//                                       voxel grid's sort in shared memory.
+// Bound: a frame is 5.4 MB (1-2 us of HBM time per pass): every kernel here is launch / latency-bound, which is why the
+// work of this file went into fewer launches and shorter serial chains; DESIGN.md gives the byte counts and times.
 #include <cooperative_groups.h>
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
@@ -156,30 +163,35 @@ fe_decode_stats_kernel(const unsigned char *__restrict__ raw, int pitch, int R, 
     last_block_mean(&cnt->ticket[0], partial, 1.0 / (double)((size_t)R * C), &cnt->mean, &is_last);
 }
 
-// h = s .* (1 - g / maxg) (features.cpp:206-213), all f32; Mat /= double multiplies by (float)(1/maxg)
+// h = s .* (1 - g / maxg) (features.cpp:206-213), all f32; Mat /= double multiplies by (float)(1/maxg).  One CTA per
+// azimuth (no index division, four independent columns in flight per thread); the pass also resets the claim map the
+// marking kernels use, so no later pass has to write 5 MB for that.
 __global__ void __launch_bounds__(RED_THREADS)
 fe_h_kernel(const float *__restrict__ fft, int R, int C, FrameCounts *__restrict__ cnt,
-            float *__restrict__ h, double *__restrict__ partial)
+            float *__restrict__ h, double *__restrict__ partial, unsigned int *__restrict__ claim)
 {
     __shared__ bool is_last;
-    const size_t N = (size_t)R * C;
     const float mean = cnt->mean;
     const float inv = (float)(1.0 / (double)cnt->maxg);
+    const int i = blockIdx.x;
+    const float *row = fft + (size_t)i * C;
+    float *hrow = h + (size_t)i * C;
+    unsigned int *crow = claim + (size_t)i * C;
     double s = 0.0;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < N; e += (size_t)gridDim.x * blockDim.x) {
-        const int i = (int)(e / C), j = (int)(e - (size_t)i * C);
-        const float *row = fft + (size_t)i * C;
+#pragma unroll 4
+    for (int j = threadIdx.x; j < C; j += RED_THREADS) {
         const float g = prewitt_abs(row, j, C) * inv;
         const float sv = row[j] - mean;
         const float hv = sv * (1.0f - g);
-        h[e] = hv;
+        hrow[j] = hv;
+        crow[j] = 0xffffffffu;
         s += (double)hv;
     }
     typedef cub::BlockReduce<double, RED_THREADS> BR;
     __shared__ typename BR::TempStorage tmp;
     const double bs = BR(tmp).Sum(s);
     if (threadIdx.x == 0) partial[blockIdx.x] = bs;
-    last_block_mean(&cnt->ticket[1], partial, 1.0 / (double)N, &cnt->mean_h, &is_last);
+    last_block_mean(&cnt->ticket[1], partial, 1.0 / (double)((size_t)R * C), &cnt->mean_h, &is_last);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -339,14 +351,19 @@ struct SubSelect {
 typedef thrust::transform_iterator<SubLoad, thrust::counting_iterator<unsigned int>> SubPairIn;
 
 __global__ void __launch_bounds__(RED_THREADS)
-fe_prep_sub_kernel(const float *__restrict__ h, size_t N, FrameCounts *__restrict__ cnt, unsigned int *__restrict__ claim)
+fe_prep_sub_kernel(const float *__restrict__ h, size_t N, FrameCounts *__restrict__ cnt)
 {
+    // the candidate count (features.cpp:220) -- read-only: fe_h_kernel has reset the claim map
     const float mean_h = cnt->mean_h;
     int c = 0;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < N; e += (size_t)gridDim.x * blockDim.x) {
-        c += h[e] > mean_h;                                  // features.cpp:220
-        claim[e] = 0xffffffffu;
+    const size_t n4 = N >> 2;
+    const float4 *h4 = reinterpret_cast<const float4 *>(h);
+#pragma unroll 2
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = h4[e];
+        c += (v.x > mean_h) + (v.y > mean_h) + (v.z > mean_h) + (v.w > mean_h);
     }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(N & 3)) c += h[(n4 << 2) + threadIdx.x] > mean_h;
     typedef cub::BlockReduce<int, RED_THREADS> BR;
     __shared__ typename BR::TempStorage tmp;
     const int bc = BR(tmp).Sum(c);
@@ -418,22 +435,23 @@ __device__ __forceinline__ int fe_block_sort16(unsigned int *k0, unsigned int *k
 
 // The subset's sort as ONE launch: a thread-block cluster of 8 CTAs holds the <= 64k (key, pixel) pairs in its
 // distributed shared memory -- dealt EVENLY, ceil(n / 8) consecutive ranks per CTA, so that eight SMs' shared-memory
-// pipes work on a pass whatever n is -- and runs a stable LSD radix sort over them: 8-bit digits, per-warp private
+// pipes work on a pass whatever n is -- and runs a stable LSD radix sort over them: 9-bit digits, per-warp private
 // histograms over contiguous segments (ranks inside a 32-group from match.any, like fe_block_sort16), per-digit CTA
 // totals exchanged through DSMEM, the scatter written straight into the owning CTA's shared memory
 // (st.shared::cluster).  Keys: h mapped to an ascending-sortable integer u (-0.0 == +0.0 like the reference's
 // compare), then re-based to umax - u over the whole subset: descending h = ascending key, and the passes cover only
-// the bytes the subset's value range needs (3 of 4 for a range below 2^24 ulps).  Equal h keep pixel order exactly as
+// the digits the subset's value range needs (3 passes for a range below 2^27 ulps, i.e. max(h) < ~16 x the threshold).  Equal h keep pixel order exactly as
 // cub::DeviceRadixSort::SortPairsDescending over the same list would.  Two cluster barriers per pass plus one for
 // the range.  Replaces fe_sub_keys_kernel + six CUB launches (histogram, scan, four onesweep passes).
 namespace cg = cooperative_groups;
 constexpr int SS_CL = 8, SS_T = 1024, SS_PER = FE_SUB_CAP / SS_CL;
+constexpr int SS_DIG = 9, SS_NB = 1 << SS_DIG;   // digit width / bins: 512 bins x 32 warps of u16 counters = 32 KB
 struct SubSortSmem {
     unsigned int key[2][SS_PER];
     unsigned int val[2][SS_PER];
-    unsigned short hist[32][256];        // [warp][digit]: counts, then exclusive offsets among this CTA's warps
-    unsigned int tot[256];               // this CTA's items per digit (read by the whole cluster)
-    unsigned int base[256];              // global rank of this CTA's first item with the digit
+    unsigned short hist[32][SS_NB];      // [warp][digit]: counts, then exclusive offsets among this CTA's warps
+    unsigned int tot[SS_NB];             // this CTA's items per digit (read by the whole cluster)
+    unsigned int base[SS_NB];            // global rank of this CTA's first item with the digit
     unsigned int umax, umin;             // this CTA's key range (read by the whole cluster)
 };
 constexpr size_t SS_SMEM = sizeof(SubSortSmem);
@@ -480,7 +498,8 @@ fe_subsort_kernel(const SubPair *__restrict__ sel, FrameCounts *__restrict__ cnt
         umin = min(umin, *cluster.map_shared_rank(&sm.umin, cc));
     }
     for (int i = t; i < my_n; i += SS_T) sm.key[0][i] = umax - sm.key[0][i];      // own items: no barrier needed
-    const int passes = (n > 0) ? ((32 - __clz(umax - umin)) + 7) >> 3 : 0;
+    const int passes = (n > 0) ? ((32 - __clz(umax - umin)) + SS_DIG - 1) / SS_DIG : 0;
+    if (c == 0 && t == 0) cnt->t_tail[6] = (unsigned long long)passes;     // diagnostics (nrs_frontend_tail_times)
     if (passes == 0) cluster.sync();                          // nobody leaves while its range is still being read
     const int seg = ((my_n + SS_T - 1) / SS_T) * 32;          // whole 32-groups per warp, contiguous in order
     const int g0 = min(warp * seg, my_n), g1 = min(g0 + seg, my_n);
@@ -488,22 +507,23 @@ fe_subsort_kernel(const SubPair *__restrict__ sel, FrameCounts *__restrict__ cnt
     const unsigned int lt = (1u << lane) - 1u;
     int cur = 0;
     for (int pass = 0; pass < passes; ++pass) {
-        const int shift = 8 * pass;
+        const int shift = SS_DIG * pass;
         const unsigned int *sk = sm.key[cur];
         const unsigned int *sv = sm.val[cur];
-        for (int i = t; i < 32 * 256 / 2; i += SS_T) reinterpret_cast<unsigned int *>(&sm.hist[0][0])[i] = 0u;
+        for (int i = t; i < 32 * SS_NB / 2; i += SS_T) reinterpret_cast<unsigned int *>(&sm.hist[0][0])[i] = 0u;
         __syncthreads();
         for (int gb = g0; gb < g1; gb += 32) {
             const int k = gb + lane;
             const bool ok = k < g1;
-            const unsigned int dig = ok ? ((sk[k] >> shift) & 255u) : 0xffffffffu;
+            const unsigned int dig = ok ? ((sk[k] >> shift) & (SS_NB - 1)) : 0xffffffffu;
             const unsigned int peers = __match_any_sync(0xffffffffu, dig);
             if (ok && !(peers & lt)) hw[dig] += (unsigned short)__popc(peers);
             __syncwarp();
         }
         __syncthreads();
-        {   // exclusive offsets among this CTA's warps, digit totals: thread t owns digit t / 4, warps 8 * (t % 4) .. + 7
-            const int d = t >> 2, w0 = (t & 3) * 8;
+        for (int d = t >> 2; d < SS_NB; d += SS_T / 4) {
+            // exclusive offsets among this CTA's warps, digit totals: four threads per digit, warps 8 * (t % 4) .. + 7
+            const int w0 = (t & 3) * 8;
             unsigned int cw[8], sum = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) { cw[j] = sm.hist[w0 + j][d]; sum += cw[j]; }
@@ -519,7 +539,7 @@ fe_subsort_kernel(const SubPair *__restrict__ sel, FrameCounts *__restrict__ cnt
         }
         cluster.sync();
         unsigned int all = 0, before = 0;
-        if (t < 256) {
+        if (t < SS_NB) {
 #pragma unroll
             for (int cc = 0; cc < SS_CL; ++cc) {
                 const unsigned int v = *cluster.map_shared_rank(&sm.tot[t], cc);
@@ -529,14 +549,14 @@ fe_subsort_kernel(const SubPair *__restrict__ sel, FrameCounts *__restrict__ cnt
         }
         unsigned int all_total;
         const unsigned int ex = fe_block1024_exscan(all, wtot, all_total);
-        if (t < 256) sm.base[t] = ex + before;
+        if (t < SS_NB) sm.base[t] = ex + before;
         __syncthreads();
         unsigned int *dk = sm.key[cur ^ 1], *dv = sm.val[cur ^ 1];
         for (int gb = g0; gb < g1; gb += 32) {
             const int k = gb + lane;
             const bool ok = k < g1;
             const unsigned int key = ok ? sk[k] : 0u;
-            const unsigned int dig = ok ? ((key >> shift) & 255u) : 0xffffffffu;
+            const unsigned int dig = ok ? ((key >> shift) & (SS_NB - 1)) : 0xffffffffu;
             const unsigned int peers = __match_any_sync(0xffffffffu, dig);
             const int rank = __popc(peers & lt);
             const unsigned int loc = ok ? hw[dig] : 0u;
@@ -772,6 +792,7 @@ fe_tail_kernel(const int *__restrict__ rowcount, const int *__restrict__ stage, 
         __syncthreads();
         TAIL_STAMP(3);
         const int passes = (32 - __clz(maxkey) + 7) >> 3;
+        if (t == 0) cnt->t_tail[7] = (unsigned long long)passes;         // diagnostics
         const int cur = fe_block_sort16(kbuf[0], kbuf[1], vbuf[0], vbuf[1], hist, K0, passes, wtot);
         sorted_in = cur;
     }
@@ -879,13 +900,13 @@ int fe_cen2019_device(nrs_ctx *ctx, FrontendState &S, int R, int C, int max_poin
         fe_stats_kernel<<<nb, RED_THREADS, 0, st>>>(S.d_fft, R, C, S.d_partial, cnt);   // -> maxg, mean (last block)
         NRS_LAUNCHED();
     }
-    fe_h_kernel<<<nb, RED_THREADS, 0, st>>>(S.d_fft, R, C, cnt, S.d_h, S.d_partial);     // -> h, mean_h (last block)
+    fe_h_kernel<<<R, RED_THREADS, 0, st>>>(S.d_fft, R, C, cnt, S.d_h, S.d_partial, S.d_claim);   // -> h, mean_h (last block), claim reset
     NRS_LAUNCHED();
     const bool sub = S.have_thresh && !force_full;
     const size_t n_walk = sub ? (size_t)FE_SUB_CAP : N;       // length of the sorted list the marking kernels cover
     size_t need = S.cub_bytes;
     if (sub) {
-        fe_prep_sub_kernel<<<nb, RED_THREADS, 0, st>>>(S.d_h, N, cnt, S.d_claim);
+        fe_prep_sub_kernel<<<nb, RED_THREADS, 0, st>>>(S.d_h, N, cnt);
         NRS_LAUNCHED();
         SubPairIn pairs(thrust::counting_iterator<unsigned int>(0u), SubLoad{S.d_h});
         NRS_CUDA(cub::DeviceSelect::If(S.d_cub, need, pairs, S.d_sel, &cnt->n_sub, (int)N, SubSelect{S.d_thresh, cnt}, st));

@@ -4,22 +4,24 @@
 // it (reference: outlier-robust-radar-odometry/include/solver/nonminimal_solver.hpp:171-264,
 // 266-440, 480-661, 678-825, 844-859; include/ORORA.hpp:37-93,139-151; src/graph.cc:12-130).
 //
-//   K7  orora_adjacency_kernel   all N(N-1)/2 translation-invariant measurements (TIMs) and the
-//                                scale-consistency test of solveForScale, written directly as an
-//                                N x 32-word bit adjacency matrix (replaces computeTIMs' 3 x N^2/2
-//                                f64 temporaries and Graph::addEdge's O(N^3) linear finds).
-//   K8  orora_order_kernel /     degree ordering, permuted adjacency, then an exact maximum-clique
-//       orora_permute_kernel /   search in one CTA of ceil(N/32) warps with the adjacency matrix in shared
-//       orora_clique_kernel      memory: greedy bound (one CTA barrier per step, REDUX-packed warp maxima,
-//                                finishes at once when the candidate set is a clique), Jacobi core pruning,
-//                                then maximum independent set on the sparse complement or, for sparse cores,
-//                                bitset branch and bound with greedy colouring on warp 0.  PMC (un-vendored
-//                                in the reference) is replaced by this exact solver.
+//   K7  orora_adjacency_kernel   all N(N-1) ordered pairs' translation-invariant measurements (TIMs) and the
+//                                scale-consistency test of solveForScale, one pair per thread, the words of an
+//                                N x 32-word bit adjacency matrix assembled by ballots (replaces computeTIMs'
+//                                3 x N^2/2 f64 temporaries and Graph::addEdge's O(N^3) linear finds).
+//   K8  orora_clique_kernel      one CTA.  Load phase (1024 threads; N <= 512): degree ordering by a stable counting
+//       (orora_order_kernel /    sort, permuted adjacency by warp-per-row ballots, all in shared memory -- for
+//        orora_permute_kernel    larger N the two separate kernels do it.  Then one thread per vertex: greedy bound
+//        for N > 512)            (one CTA barrier per SHRINK of the candidate set: all universal vertices are taken
+//                                in one step; REDUX-packed warp maxima), Jacobi core pruning, then maximum
+//                                independent set on the sparse complement or, for sparse cores, bitset branch and
+//                                bound with greedy colouring on warp 0.  PMC (un-vendored in the reference) is
+//                                replaced by this exact solver.
 //   K9  orora_tail_kernel        launched with 1024 threads, keeps nextpow2(M) alive: clique sort, chain TIMs +
 //                                initial weights, GNC-TLS rotation (one warp-shuffle CTA reduction per
-//                                iteration, closed-form 2-D Kabsch), anisotropic COTE translation (rank
-//                                counting instead of a sorting network, running sums in sorted order like
-//                                the reference's loop, first-minimum argmin).
+//                                iteration, closed-form 2-D Kabsch), anisotropic COTE translation on both axes
+//                                side by side (rank counting instead of a sorting network, running sums in sorted
+//                                order like the reference's loop, first-minimum argmin).
+//   The fused pair call enqueues K7-K9 before the host knows the match count (solver_size / orora_pair_enqueue).
 //
 // All of it is latency-bound on <= 1024 correspondences (22 KB of input): it sits far below the
 // HBM roofline by construction and DESIGN.md reports it that way.  Built with --fmad=false so the

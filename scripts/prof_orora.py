@@ -31,7 +31,7 @@ print("launches after first extract:", L.nrs_kernel_launches())
 def tail_phases():
     t = (C.c_uint64 * 8)()
     L.nrs_frontend_tail_times(ctx.handle, t)
-    return [round((int(t[i + 1]) - int(t[i])) / 1e3, 1) for i in range(5)]
+    return [round((int(t[i + 1]) - int(t[i])) / 1e3, 1) for i in range(5)] + ["passes subset/voxel", int(t[6]), int(t[7])]
 
 
 import torch  # noqa: E402  (cudart handle for the profiler range)
