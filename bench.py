@@ -418,11 +418,21 @@ def run_ours(args, rank, world, local_rank):
         alg_bytes = Q * (DESC_BYTES * n_local + DESC_BYTES + 16)            # SURVEY 8d per-query figure x Q queries per launch
         achieved = alg_bytes / (kern_us * 1e-6) / 1e9
         streamed = bin_bytes * n_local + Q * DESC_BYTES                     # unique bytes one launch touches
-        traffic = None
+        traffic = issue = None
         summ = os.path.join(ROOT, "profiles", "sc_search_bin_ncu.json")
         if os.path.exists(summ) and world == 1:
             try:
-                traffic = json.load(open(summ)).get("dram_bytes_per_launch")
+                ncu = json.load(open(summ))
+                traffic = ncu.get("dram_bytes_per_launch")
+                # the bound that does hold for this kernel: warp-instruction issue.  Instruction count per launch from the
+                # committed ncu capture of this very workload (smsp__inst_executed.sum), issue peak = 148 SMs x 4
+                # schedulers x 1 warp instruction per cycle at the SM clock sampled under load, time measured live
+                inst = float(ncu["launches"][0]["smsp__inst_executed.sum"][0])
+                sm_hz = float((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+                issue = {"bound": "warp-instruction issue", "warp_inst_per_launch": inst,
+                         "peak_warp_inst_per_s": 148 * 4 * sm_hz,
+                         "frac": inst / (kern_us * 1e-6) / (148 * 4 * sm_hz),
+                         "source": "profiles/sc_search_bin_ncu.json (ncu --set full of the same launch) / live kernel_us"}
             except Exception:
                 traffic = None
         # bounded CPU baseline on this box's host cores (oracle port, all threads)
@@ -468,7 +478,8 @@ def run_ours(args, rank, world, local_rank):
                                  "queries, so it is issue-bound (DP4A/POPC/FFMA), not HBM-bound: frac > 1 means the canonical bytes were "
                                  "never moved; frac_streamed is against the bytes really touched",
                          "streamed_bytes_per_launch": streamed,
-                         "frac_streamed": streamed / (kern_us * 1e-6) / 1e9 / peak},
+                         "frac_streamed": streamed / (kern_us * 1e-6) / 1e9 / peak,
+                         "issue": issue},
             "cpu_baseline": {"value": cpu_v, "unit": "queries/s", "cores": cores, "kind": "port",
                              "value_1_thread": cpu_v1,
                              "sample": f"{n_cpu} full queries vs the same 10k DB in ~10 s (oracle/sc_ref.c, OpenMP, -O3 -march=native)"},

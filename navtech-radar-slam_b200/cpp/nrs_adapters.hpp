@@ -40,9 +40,16 @@
 
 namespace nrs {
 
+// NRS_ECAPACITY as its own type: a caller's buffer or a fixed device-side capacity was too small (the one the
+// reference does not have: more than 1024 correspondences in one solve, reachable only with the stop-motion gate off)
+struct CapacityError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
 inline void check(int rc)
 {
     if (rc == NRS_EINVAL) throw std::invalid_argument(nrs_last_error());
+    if (rc == NRS_ECAPACITY) throw CapacityError(std::string("nrs_b200: ") + nrs_last_error());
     if (rc < 0) throw std::runtime_error(std::string("nrs_b200: ") + nrs_last_error());
 }
 

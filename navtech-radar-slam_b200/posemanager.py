@@ -31,15 +31,20 @@ def euler_yaw(T):
 
 
 def xyyaw2se2(xyyaw_rel, dataset):
-    """XYYaw2SE2 (:176-188): the MulRan ground truth enters with its yaw negated, like the reference"""
+    """XYYaw2SE2 (:176-188): the MulRan ground truth enters with its yaw negated, like the reference.  The yaw goes
+    through tf::createQuaternionFromYaw (double: z = sin(yaw/2), w = cos(yaw/2), x = y = 0), is narrowed to an
+    Eigen::Quaternionf and becomes a float rotation matrix (Quaternion::toRotationMatrix) that is widened again."""
+    f32 = np.float32
     T = np.eye(4)
-    T[0, 3], T[1, 3] = float(np.float32(xyyaw_rel[0])), float(np.float32(xyyaw_rel[1]))
-    yaw = float(np.float32(xyyaw_rel[2]))
+    T[0, 3], T[1, 3] = float(f32(xyyaw_rel[0])), float(f32(xyyaw_rel[1]))
+    yaw = float(f32(xyyaw_rel[2]))
     if dataset == "mulran":
         yaw = -yaw
-    c, s = math.cos(yaw), math.sin(yaw)
-    # tf quaternion -> Eigen::Quaternionf -> rotation matrix: single precision on the way (:186-187)
-    T[0, 0], T[0, 1], T[1, 0], T[1, 1] = float(np.float32(c)), float(np.float32(-s)), float(np.float32(s)), float(np.float32(c))
+    z, w = f32(math.sin(yaw * 0.5)), f32(math.cos(yaw * 0.5))
+    tz = f32(2.0) * z
+    twz, tzz = tz * w, tz * z
+    T[0, 0] = T[1, 1] = float(f32(1.0) - (f32(0.0) + tzz))
+    T[0, 1], T[1, 0] = float(f32(0.0) - twz), float(f32(0.0) + twz)
     return T
 
 

@@ -12,24 +12,36 @@ import numpy as np
 from . import orora, posemanager, scancontext
 
 
+def stamp_of(name):
+    """getTimestamp / less_than_img (radar_utils.cpp:70-83): the integer before the first '.'"""
+    return int(name.split(".")[0])
+
+
 def radar_files(datadir):
-    """get_file_names (radar_utils.cpp:88-102): the PNGs of the directory, sorted by name (= timestamp)."""
-    return sorted(f for f in os.listdir(datadir) if f.endswith(".png"))
+    """get_file_names (radar_utils.cpp:85-102): the directory's regular files whose last '.'-part is "png", in
+    ascending order of the time stamp in the name."""
+    return sorted((f for f in os.listdir(datadir) if f.split(".")[-1] == "png" and os.path.isfile(os.path.join(datadir, f))),
+                  key=stamp_of)
 
 
 def run_odometry(datadir, dataset="mulran", keypoint_extraction="cen2018", voxel_size=0.6, use_voxelization=True,
                  frame_rate=4.0, loop_detection=False, sc_dist_thres=0.2, ctx=None, out_dir=None, end_idx=-1,
                  noise_bound=0.75, noise_bound_radial=0.1, noise_bound_tangential_deg=9.0, gt_rel=None,
                  check_stop_motion=True):
-    """Returns a dict with the relative poses (n-1, 4, 4), the chained trajectory (n, 4, 4), per-pair wall times
+    """n files give n - 2 scan pairs, like the node (below).  Returns a dict with the relative poses (n-2, 4, 4),
+    the chained trajectory (n-1, 4, 4: Identity first), per-pair wall times
     and, with loop_detection, (frame, loop_id, yaw) triples.  With out_dir, writes the reference node's own
     evaluation files (posemanager.SE2PoseManager: <dataset>_ORORA_<extraction>_{eval_odom, rel_error_odom,
     time_taken, est_traj, gt_traj}.txt, scorable by ORORA/scripts/evaluate_odometry.py) plus loops.txt.
     gt_rel: per pair (x, y, yaw) relative ground-truth motion as the reference's getXYYawPose returns it
     (odometry.cpp:253-259); None writes identity ground truth."""
     files = radar_files(datadir)
-    if end_idx >= 0:
-        files = files[:end_idx + 1]
+    # the node stops one file short of the list -- pair i is written with the stamps of files i and i + 1
+    # (odometry.cpp:157-158: `if (end_idx < 0) end_idx = radar_files.size() - 1; for (i = start_idx; i < end_idx; ++i)`,
+    # :180-185) -- so n files give n - 2 scan pairs
+    end_idx = len(files) - 1 if end_idx < 0 else min(end_idx, len(files) - 1)
+    next_stamp = [stamp_of(f) for f in files[1:end_idx + 1]]
+    files = files[:max(end_idx, 0)]
     loader = orora.RadarLoader(dataset, keypoint_extraction, voxel_size, use_voxelization, False, ctx=ctx)
     est = orora.ORORA(dataset, "rot", True, False, check_stop_motion, 700, 0.049, noise_bound_radial,
                       np.deg2rad(noise_bound_tangential_deg), ctx=loader.ctx)
@@ -64,7 +76,7 @@ def run_odometry(datadir, dataset="mulran", keypoint_extraction="cen2018", voxel
                 Tgt = posemanager.xyyaw2se2(gt_rel[i - 1], dataset) if gt_rel is not None else np.eye(4)
                 curr_gt = curr_gt @ Tgt
                 pm_out.writePoseError(Tgt, T)                          # odometry.cpp:281-285
-                pm_out.writePose(Tgt, T, prev.t_crietria_, cur.t_crietria_, loader.time_unit_denominator_)
+                pm_out.writePose(Tgt, T, stamp_of(name), next_stamp[i], loader.time_unit_denominator_)   # time1, time2 (:183-185)
                 pm_out.writeTraj(traj[-1], pm_out.est_traj_path_)
                 pm_out.writeTraj(curr_gt, pm_out.gt_traj_path_)
                 pm_out.writeTimeTaken(int(dt * 1e6), Tgt)

@@ -77,7 +77,7 @@ def test_png_directory_driver(nrs, ctx, synth, tmp_path):
     import cv2
     stream = importlib.import_module("navtech-radar-slam_b200.stream")
     world = synth.radar_world(seed=1234)
-    for k in range(6):
+    for k in range(7):                                 # n files give n - 2 scan pairs (the node stops one file short)
         raw = synth.radar_frame(world, (2.5 * k, 0.1 * k, np.deg2rad(1.0) * k), seed=900 + k, dataset="mulran")
         assert cv2.imwrite(str(tmp_path / f"{1560000000000000000 + k * 250000000}.png"), raw)
     gt = [(2.5, 0.1, -np.deg2rad(1.0))] * 5          # MulRan-style ground truth: the reference negates its yaw (SE2posemanager.hpp:181-183)
