@@ -14,7 +14,10 @@
 //              [--gt FILE] [--voxel-size 0.6] [--no-voxelization] [--frame-rate 4] [--end-idx N] [--loops]
 //              [--sc-dist-thres 0.2] [--noise-bound 0.75] [--noise-bound-radial 0.1] [--noise-bound-tangential 9]
 //              [--no-stop-motion] [--no-doppler] [--device 0]
+//   orora_odom --seq-dir SEQ ...        the node's own layout (run_orora.launch's seq_dir): frames from
+//              SEQ/polar_oxford_form/, ground truth from SEQ/gt/radar_odometry.csv, files into SEQ/outputs/
 //   orora_odom --decode-only in.png out.raw            (no GPU: rows, cols as two int32, then the bytes)
+//   orora_odom --gt-lookup SEQ DATASET T1 T2           (no GPU: prints getXYYawPose's x y yaw with %.9g)
 //   orora_odom --posefile-selftest in.bin OUTDIR DATASET EXTRACTION   (no GPU: see tests/test_cpp_driver.py)
 //
 // --gt FILE: one "x,y,yaw" line per scan pair, the relative ground-truth motion getXYYawPose would return
@@ -127,7 +130,7 @@ int posefile_selftest(const char *in, const std::string &out_dir, const std::str
 }
 
 struct Options {
-    std::string datadir, dataset = "mulran", extractor = "cen2018", out_dir, gt_path;
+    std::string datadir, seq_dir, dataset = "mulran", extractor = "cen2018", out_dir, gt_path;
     double voxel_size = 0.6, frame_rate = 4.0, sc_dist_thres = 0.2;
     double noise_bound = 0.75, noise_bound_radial = 0.1, noise_bound_tangential_deg = 9.0;
     bool use_voxelization = true, loops = false, check_stop_motion = true, use_doppler = true;
@@ -143,6 +146,7 @@ bool parse(int argc, char **argv, Options &o)
         else if (a == "--extractor") o.extractor = val();
         else if (a == "--out") o.out_dir = val();
         else if (a == "--gt") o.gt_path = val();
+        else if (a == "--seq-dir") o.seq_dir = val();
         else if (a == "--voxel-size") o.voxel_size = std::atof(val());
         else if (a == "--no-voxelization") o.use_voxelization = false;
         else if (a == "--frame-rate") o.frame_rate = std::atof(val());
@@ -157,6 +161,11 @@ bool parse(int argc, char **argv, Options &o)
         else if (a == "--device") o.device = std::atoi(val());
         else if (!a.empty() && a[0] != '-' && o.datadir.empty()) o.datadir = a;
         else throw std::invalid_argument("unknown argument " + a);
+    }
+    if (!o.seq_dir.empty()) {
+        if (!o.datadir.empty() || !o.out_dir.empty() || !o.gt_path.empty())
+            throw std::invalid_argument("--seq-dir fixes the frame directory, the ground truth and the output directory");
+        o.datadir = o.seq_dir + "/polar_oxford_form/";                               // odometry.cpp:141
     }
     return !o.datadir.empty();
 }
@@ -190,10 +199,13 @@ int run(const Options &o)
     ORORA orora_estimator(o.dataset, "rot", o.use_doppler, false, o.check_stop_motion, 700, 0.049, o.noise_bound_radial,
                           o.noise_bound_tangential_deg * M_PI / 180.0, ctx);
     std::vector<std::string> radar_files = get_file_names(o.datadir);
-    const bool write = !o.out_dir.empty();
-    if (write) mkdir(o.out_dir.c_str(), 0777);
+    const bool from_seq = !o.seq_dir.empty();
+    const bool write = from_seq || !o.out_dir.empty();
+    const std::string out_dir = from_seq ? o.seq_dir + "/outputs" : o.out_dir;
+    if (write && !from_seq) mkdir(o.out_dir.c_str(), 0777);
     nrs::SE2PoseManager PoseManager;
-    if (write) PoseManager = nrs::SE2PoseManager(o.out_dir, o.dataset, "ORORA", o.extractor);
+    if (from_seq) PoseManager = nrs::SE2PoseManager::from_seq_dir(o.seq_dir, o.dataset, "ORORA", o.extractor);   // odometry.cpp:143-144
+    else if (write) PoseManager = nrs::SE2PoseManager(o.out_dir, o.dataset, "ORORA", o.extractor);
     RadarLoader Loader(o.dataset, o.extractor, o.voxel_size, o.use_voxelization, false, ctx);
     const double time_unit_denominator = Loader.getTimeDenominator();
     std::vector<std::vector<float>> gt;
@@ -201,7 +213,7 @@ int run(const Options &o)
     std::unique_ptr<SCManager> sc;
     if (o.loops) { sc.reset(new SCManager(ctx)); sc->setSCdistThres(o.sc_dist_thres); }
     std::ofstream loops_file;
-    if (write && o.loops) loops_file.open(o.out_dir + "/loops.txt");
+    if (write && o.loops) loops_file.open(out_dir + "/loops.txt");
 
     RadarFeature prev_feat, curr_feat;
     nrs::Mat4 curr_gt, curr_odom;
@@ -247,9 +259,13 @@ int run(const Options &o)
         const auto end = std::chrono::steady_clock::now();
         const int time_taken = (int)std::chrono::duration_cast<std::chrono::microseconds>(end - start).count();
         solve_s += time_taken * 1e-6;
-        if (!gt.empty()) {
+        PoseManager.dataset_name_ = o.dataset;
+        if (from_seq) {                                                            // odometry.cpp:253-259
+            const std::vector<float> xyyaw_rel = o.dataset == "oxford" ? PoseManager.getXYYawPose(time1, time2)
+                                                                       : PoseManager.getXYYawPose(time1);
+            PoseManager.XYYaw2SE2(xyyaw_rel, Tgt);
+        } else if (!gt.empty()) {
             if ((size_t)(i - 1) >= gt.size()) throw std::invalid_argument("The corresponding time is not inserted!... exiting.");
-            PoseManager.dataset_name_ = o.dataset;
             PoseManager.XYYaw2SE2(gt[i - 1], Tgt);
         }
         curr_gt = curr_gt * Tgt;
@@ -276,6 +292,16 @@ int main(int argc, char **argv)
 {
     try {
         if (argc == 4 && !std::strcmp(argv[1], "--decode-only")) return decode_only(argv[2], argv[3]);
+        if (argc == 6 && !std::strcmp(argv[1], "--gt-lookup")) {
+            nrs::SE2PoseManager pm;
+            pm.dataset_name_ = argv[3];
+            pm.gt_path_ = std::string(argv[2]) + "/gt/radar_odometry.csv";
+            if (pm.dataset_name_ == "mulran") nrs::loadGTPoses(pm.gt_path_, pm.gt_rel_);
+            const std::vector<float> g = pm.dataset_name_ == "oxford" ? pm.getXYYawPose(std::atoll(argv[4]), std::atoll(argv[5]))
+                                                                      : pm.getXYYawPose(std::atoll(argv[4]));
+            std::printf("%.9g %.9g %.9g\n", g[0], g[1], g[2]);
+            return 0;
+        }
         if (argc == 6 && !std::strcmp(argv[1], "--posefile-selftest")) return posefile_selftest(argv[2], argv[3], argv[4], argv[5]);
         Options o;
         if (!parse(argc, argv, o)) {

@@ -6,7 +6,9 @@
 //     <prefix>eval_odom.txt        tsx_gt,tsy_gt,yaw_gt,tsx_test,tsy_test,yaw_test,time1/den,time2/den (:216-229)
 //     <prefix>time_taken.txt       time_taken[us],is_stopped                                         (:231-245)
 //     <prefix>est_traj.txt / gt_traj.txt   x,y,yaw                                                   (:247-259)
-// Ground-truth LOADING (the reader half, :27-93) is the caller's business: relative motions are passed in.
+// and the reader half the node uses for the ground-truth columns: loadGTPoses (:17-36, MulRan:
+// <seq_dir>/gt/radar_odometry.csv keyed by time stamp) and get_groundtruth_odometry (radar_utils.cpp:483-501, Oxford:
+// the row whose two stamps match), behind getXYYawPose (:137-140,159-166) -- quirks kept (see loadGTPoses).
 // The Python twin is navtech-radar-slam_b200/posemanager.py; tests/test_cpp_driver.py compares the two byte for byte.
 // Host-side bookkeeping only.
 #ifndef NRS_SE2_POSEMANAGER_HPP
@@ -14,10 +16,64 @@
 #include <cmath>
 #include <cstdint>
 #include <fstream>
+#include <sstream>
+#include <stdexcept>
 #include <string>
+#include <sys/stat.h>
+#include <unordered_map>
 #include <vector>
 
 namespace nrs {
+
+namespace gt_detail {
+inline std::vector<std::string> split_commas(const std::string &line)        // boost::split(.., is_any_of(","))
+{
+    std::vector<std::string> parts;
+    size_t a = 0;
+    for (;;) {
+        const size_t b = line.find(',', a);
+        parts.push_back(line.substr(a, b == std::string::npos ? std::string::npos : b - a));
+        if (b == std::string::npos) break;
+        a = b + 1;
+    }
+    return parts;
+}
+}  // namespace gt_detail
+
+// loadGTPoses (SE2posemanager.hpp:17-36): "(Time, x, y, yaw)" rows without a header line.  Kept as written there:
+// the y entry is read from column 3 like the yaw (`{stof(words[1]), stof(words[3]), stof(words[3])}`), so the
+// relative ground truth the node writes and scores against has y == yaw.
+inline void loadGTPoses(const std::string &gt_path, std::unordered_map<int64_t, std::vector<float>> &gt_rel)
+{
+    gt_rel.clear();
+    std::ifstream ifs(gt_path);
+    std::string line;
+    while (std::getline(ifs, line)) {
+        const std::vector<std::string> words = gt_detail::split_commas(line);
+        if (words.size() < 4) throw std::invalid_argument("loadGTPoses: a row of " + gt_path + " has fewer than 4 columns");
+        gt_rel[std::stoll(words[0])] = {std::stof(words[1]), std::stof(words[3]), std::stof(words[3])};
+    }
+    if (gt_rel.empty()) throw std::invalid_argument("Some parameters seem to be wrong! Load GT failed!");
+}
+
+// get_groundtruth_odometry (radar_utils.cpp:483-501): Oxford's radar_odometry.csv, first line = header; the row with
+// parts[9] == t1 and parts[8] == t2 gives parts[2..7] = x, y, z, roll, pitch, yaw
+inline bool get_groundtruth_odometry(const std::string &gtfile, int64_t t1, int64_t t2, std::vector<float> &gt)
+{
+    std::ifstream ifs(gtfile);
+    std::string line;
+    std::getline(ifs, line);
+    gt.clear();
+    while (std::getline(ifs, line)) {
+        const std::vector<std::string> parts = gt_detail::split_commas(line);
+        if (parts.size() < 10) continue;
+        if (std::stoll(parts[9]) == t1 && std::stoll(parts[8]) == t2) {
+            for (int i = 2; i < 8; ++i) gt.push_back(std::stof(parts[i]));
+            return true;
+        }
+    }
+    return false;
+}
 
 // 4x4 double, column-major like Eigen::Matrix4d (only what the node's bookkeeping needs)
 struct Mat4 {
@@ -79,6 +135,33 @@ public:
         for (const std::string *p : {&output_pose_error_path_, &output_pose_path_, &output_time_path_, &est_traj_path_,
                                      &gt_traj_path_})
             clearOutputFile(*p);
+    }
+
+    // the node's form (:73-135 with ANALYZE_PARAM off): ground truth from <seq_dir>/gt/radar_odometry.csv (loaded up
+    // front for MulRan, searched per pair for Oxford), files under <seq_dir>/outputs/, truncated (is_overwrite_available)
+    static SE2PoseManager from_seq_dir(const std::string &seq_dir, const std::string &dataset_name,
+                                       const std::string &algorithm_name, const std::string &keypoint_extraction)
+    {
+        const std::string output_dir = seq_dir + "/outputs";
+        struct stat st;
+        if (stat(output_dir.c_str(), &st) != 0) mkdir(output_dir.c_str(), 0777);
+        SE2PoseManager pm(output_dir, dataset_name, algorithm_name, keypoint_extraction);
+        pm.gt_path_ = seq_dir + "/gt/radar_odometry.csv";
+        if (dataset_name == "mulran") loadGTPoses(pm.gt_path_, pm.gt_rel_);
+        return pm;
+    }
+
+    std::vector<float> getXYYawPose(const int64_t t)             // MulRan (:137-142)
+    {
+        const auto it = gt_rel_.find(t);
+        if (it == gt_rel_.end()) throw std::invalid_argument("The corresponding time is not inserted!... exiting.");
+        return it->second;
+    }
+    std::vector<float> getXYYawPose(const int64_t time1, const int64_t time2)     // Oxford (:159-166)
+    {
+        std::vector<float> gtvec;
+        if (!get_groundtruth_odometry(gt_path_, time1, time2, gtvec)) throw std::invalid_argument("Stop!!");
+        return {gtvec[0], gtvec[1], gtvec[5]};
     }
 
     void setFilenames(std::string common_dir)                   // :151-157
@@ -143,7 +226,8 @@ public:
         f << Tf4x4(0, 3) << "," << Tf4x4(1, 3) << "," << euler_yaw(Tf4x4) << "\n";
     }
 
-    std::string dataset_name_;
+    std::string dataset_name_, gt_path_;
+    std::unordered_map<int64_t, std::vector<float>> gt_rel_;
     std::string output_pose_error_path_, output_pose_path_, output_time_path_, est_traj_path_, gt_traj_path_;
 };
 

@@ -48,9 +48,62 @@ def xyyaw2se2(xyyaw_rel, dataset):
     return T
 
 
+def loadGTPoses(gt_path):
+    """loadGTPoses (:17-36): "(Time, x, y, yaw)" rows without a header -> {stamp: [x, y, yaw]} as float32.  Kept as
+    written there: the y entry is read from column 3 like the yaw (`{stof(words[1]), stof(words[3]), stof(words[3])}`),
+    so the relative ground truth the node writes and scores against has y == yaw."""
+    gt_rel = {}
+    with open(gt_path) as f:
+        for line in f.read().splitlines():
+            words = line.split(",")
+            if len(words) < 4:
+                raise ValueError(f"loadGTPoses: a row of {gt_path} has fewer than 4 columns")
+            gt_rel[int(words[0])] = [float(np.float32(words[1])), float(np.float32(words[3])), float(np.float32(words[3]))]
+    if not gt_rel:
+        raise ValueError("Some parameters seem to be wrong! Load GT failed!")
+    return gt_rel
+
+
+def get_groundtruth_odometry(gtfile, t1, t2):
+    """get_groundtruth_odometry (radar_utils.cpp:483-501): Oxford's radar_odometry.csv, first line = header; the row with
+    parts[9] == t1 and parts[8] == t2 gives parts[2..7] = x, y, z, roll, pitch, yaw (float32), else None."""
+    with open(gtfile) as f:
+        f.readline()
+        for line in f:
+            parts = line.rstrip("\n").split(",")
+            if len(parts) < 10:
+                continue
+            if int(parts[9]) == t1 and int(parts[8]) == t2:
+                return [float(np.float32(v)) for v in parts[2:8]]
+    return None
+
+
 class SE2PoseManager:
-    """Writer half of the reference's SE2PoseManager (ground-truth loading is the caller's business: pass the
-    relative ground-truth motions in)."""
+    """The reference's SE2PoseManager: the five output files and, with from_seq_dir, the ground-truth reader the node
+    uses for their ground-truth columns (otherwise the caller passes the relative ground-truth motions in)."""
+    gt_path_ = None
+    gt_rel_ = None
+
+    @classmethod
+    def from_seq_dir(cls, seq_dir, dataset_name="mulran", algorithm_name="ORORA", keypoint_extraction="cen2018"):
+        """The node's form (:73-135 with ANALYZE_PARAM off): ground truth from <seq_dir>/gt/radar_odometry.csv (loaded
+        up front for MulRan, searched per pair for Oxford), files under <seq_dir>/outputs/, truncated."""
+        pm = cls(os.path.join(seq_dir, "outputs"), dataset_name, algorithm_name, keypoint_extraction)
+        pm.gt_path_ = os.path.join(seq_dir, "gt", "radar_odometry.csv")
+        if dataset_name == "mulran":
+            pm.gt_rel_ = loadGTPoses(pm.gt_path_)
+        return pm
+
+    def getXYYawPose(self, time1, time2=None):
+        """MulRan: getXYYawPose(t) (:137-142); Oxford: getXYYawPose(time1, time2) (:159-166)"""
+        if time2 is None:
+            if time1 not in self.gt_rel_:
+                raise ValueError("The corresponding time is not inserted!... exiting.")
+            return self.gt_rel_[time1]
+        gtvec = get_groundtruth_odometry(self.gt_path_, time1, time2)
+        if gtvec is None:
+            raise ValueError("Stop!!")
+        return [gtvec[0], gtvec[1], gtvec[5]]
 
     def __init__(self, out_dir, dataset_name="mulran", algorithm_name="ORORA", keypoint_extraction="cen2018"):
         os.makedirs(out_dir, exist_ok=True)

@@ -27,14 +27,20 @@ def radar_files(datadir):
 def run_odometry(datadir, dataset="mulran", keypoint_extraction="cen2018", voxel_size=0.6, use_voxelization=True,
                  frame_rate=4.0, loop_detection=False, sc_dist_thres=0.2, ctx=None, out_dir=None, end_idx=-1,
                  noise_bound=0.75, noise_bound_radial=0.1, noise_bound_tangential_deg=9.0, gt_rel=None,
-                 check_stop_motion=True):
+                 check_stop_motion=True, seq_dir=None):
     """n files give n - 2 scan pairs, like the node (below).  Returns a dict with the relative poses (n-2, 4, 4),
     the chained trajectory (n-1, 4, 4: Identity first), per-pair wall times
     and, with loop_detection, (frame, loop_id, yaw) triples.  With out_dir, writes the reference node's own
     evaluation files (posemanager.SE2PoseManager: <dataset>_ORORA_<extraction>_{eval_odom, rel_error_odom,
     time_taken, est_traj, gt_traj}.txt, scorable by ORORA/scripts/evaluate_odometry.py) plus loops.txt.
     gt_rel: per pair (x, y, yaw) relative ground-truth motion as the reference's getXYYawPose returns it
-    (odometry.cpp:253-259); None writes identity ground truth."""
+    (odometry.cpp:253-259); None writes identity ground truth.
+    seq_dir (datadir = None): the node's own layout -- frames from <seq_dir>/polar_oxford_form/, ground truth from
+    <seq_dir>/gt/radar_odometry.csv through SE2PoseManager.getXYYawPose, files into <seq_dir>/outputs/."""
+    if seq_dir is not None:
+        if datadir is not None or out_dir is not None or gt_rel is not None:
+            raise ValueError("seq_dir fixes the frame directory, the ground truth and the output directory")
+        datadir, out_dir = os.path.join(seq_dir, "polar_oxford_form"), os.path.join(seq_dir, "outputs")
     files = radar_files(datadir)
     # the node stops one file short of the list -- pair i is written with the stamps of files i and i + 1
     # (odometry.cpp:157-158: `if (end_idx < 0) end_idx = radar_files.size() - 1; for (i = start_idx; i < end_idx; ++i)`,
@@ -51,7 +57,10 @@ def run_odometry(datadir, dataset="mulran", keypoint_extraction="cen2018", voxel
         mgr = scancontext.SCManager(loader.ctx)
         mgr.setSCdistThres(sc_dist_thres)
     rel, traj, times, loops, skipped = [], [np.eye(4)], [], [], []
-    pm_out = posemanager.SE2PoseManager(out_dir, dataset, "ORORA", keypoint_extraction) if out_dir else None
+    if seq_dir is not None:
+        pm_out = posemanager.SE2PoseManager.from_seq_dir(seq_dir, dataset, "ORORA", keypoint_extraction)      # odometry.cpp:143-144
+    else:
+        pm_out = posemanager.SE2PoseManager(out_dir, dataset, "ORORA", keypoint_extraction) if out_dir else None
     curr_gt = np.eye(4)
     prev = None
     for i, name in enumerate(files):
@@ -73,7 +82,12 @@ def run_odometry(datadir, dataset="mulran", keypoint_extraction="cen2018", voxel
             traj.append(traj[-1] @ T)
             times.append(dt)
             if pm_out is not None:
-                Tgt = posemanager.xyyaw2se2(gt_rel[i - 1], dataset) if gt_rel is not None else np.eye(4)
+                if seq_dir is not None:                                # odometry.cpp:253-259
+                    xyyaw = (pm_out.getXYYawPose(stamp_of(name), next_stamp[i]) if dataset == "oxford"
+                             else pm_out.getXYYawPose(stamp_of(name)))
+                    Tgt = posemanager.xyyaw2se2(xyyaw, dataset)
+                else:
+                    Tgt = posemanager.xyyaw2se2(gt_rel[i - 1], dataset) if gt_rel is not None else np.eye(4)
                 curr_gt = curr_gt @ Tgt
                 pm_out.writePoseError(Tgt, T)                          # odometry.cpp:281-285
                 pm_out.writePose(Tgt, T, stamp_of(name), next_stamp[i], loader.time_unit_denominator_)   # time1, time2 (:183-185)

@@ -192,6 +192,45 @@ def test_pose_files_equal_python_twin(tmp_path, dataset):
         assert not diff, (name, diff[:3])
 
 
+def test_ground_truth_reader(tmp_path):
+    """loadGTPoses / get_groundtruth_odometry behind getXYYawPose (SE2posemanager.hpp:17-36,137-166,
+    radar_utils.cpp:483-501): C++ and Python agree, MulRan's y column is the yaw column (the reference's own indexing),
+    Oxford rows are found by their two stamps, a missing stamp is an error in both."""
+    need_exe()
+    pmod = importlib.import_module("navtech-radar-slam_b200.posemanager")
+    rng = np.random.default_rng(21)
+    for dataset in ("mulran", "oxford"):
+        seq = tmp_path / dataset
+        (seq / "gt").mkdir(parents=True)
+        stamps = [1560000000000000000 + 250000000 * k for k in range(40)]
+        vals = rng.normal(0, 1, (40, 6))
+        with open(seq / "gt" / "radar_odometry.csv", "w") as f:
+            if dataset == "mulran":
+                for t, v in zip(stamps, vals):
+                    f.write(f"{t},{v[0]:.9g},{v[1]:.9g},{v[5]:.9g}\n")
+            else:
+                f.write("source_timestamp,destination_timestamp,x,y,z,roll,pitch,yaw,source_radar_timestamp,destination_radar_timestamp\n")
+                for k, v in enumerate(vals[:-1]):
+                    f.write(f"{k},{k + 1}," + ",".join(f"{x:.9g}" for x in v) + f",{stamps[k + 1]},{stamps[k]}\n")
+        pm = pmod.SE2PoseManager.from_seq_dir(str(seq), dataset, "ORORA", "cen2018")
+        assert os.path.isdir(seq / "outputs") and os.path.exists(pm.output_pose_path_)
+        for k in (0, 7, 38):
+            t1, t2 = stamps[k], stamps[k + 1]
+            want = pm.getXYYawPose(t1, t2) if dataset == "oxford" else pm.getXYYawPose(t1)
+            f32 = lambda x: float(np.float32(float(f"{x:.9g}")))
+            if dataset == "mulran":
+                assert want == [f32(vals[k][0]), f32(vals[k][5]), f32(vals[k][5])]          # y := column 3 (:31)
+            else:
+                assert want == [f32(vals[k][0]), f32(vals[k][1]), f32(vals[k][5])]
+            r = subprocess.run([EXE, "--gt-lookup", str(seq), dataset, str(t1), str(t2)], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            assert [float(x) for x in r.stdout.split()] == [float(f"{v:.9g}") for v in want]
+        r = subprocess.run([EXE, "--gt-lookup", str(seq), dataset, "12345", "67890"], capture_output=True, text=True)
+        assert r.returncode == 1
+        with pytest.raises(ValueError):
+            pm.getXYYawPose(12345, 67890) if dataset == "oxford" else pm.getXYYawPose(12345)
+
+
 def test_driver_without_gpu_or_input(tmp_path):
     """No CPU fallback in the C++ host either: without a device the driver says so and exits 77; a bad directory or
     flag is an error (1), not a crash."""
@@ -237,3 +276,26 @@ def test_cpp_node_equals_python_driver(nrs, ctx, synth, tmp_path):
         tb = (pdir / f"mulran_ORORA_{extractor}_time_taken.txt").read_text().splitlines()
         assert [x.split(",")[1] for x in ta] == [x.split(",")[1] for x in tb] and len(ta) == 6
         assert (cdir / "loops.txt").read_text() == (pdir / "loops.txt").read_text()
+    # the node's own layout (seq_dir with polar_oxford_form/, gt/radar_odometry.csv, outputs/): two copies of the
+    # sequence directory sharing the frames, one per driver
+    seqs = []
+    for who in ("c", "p"):
+        seq = tmp_path / f"seq_{who}"
+        (seq / "gt").mkdir(parents=True)
+        os.symlink(d, seq / "polar_oxford_form")
+        with open(seq / "gt" / "radar_odometry.csv", "w") as f:
+            for k in range(8):
+                f.write(f"{1560000000000000000 + k * 250000000},{2.0 + 0.01 * k:.9g},0.05,{-0.0139 - 0.001 * k:.9g}\n")
+        seqs.append(seq)
+    r = subprocess.run([EXE, "--seq-dir", str(seqs[0]), "--dataset", "mulran", "--extractor", "cen2018"], capture_output=True, text=True)
+    assert r.returncode == 0 and "6 pairs (0 skipped)" in r.stdout, (r.stdout, r.stderr)
+    stream.run_odometry(None, "mulran", "cen2018", ctx=ctx, seq_dir=str(seqs[1]))
+    for name in ("rel_error_odom", "eval_odom", "est_traj", "gt_traj"):
+        a = (seqs[0] / "outputs" / f"mulran_ORORA_cen2018_{name}.txt").read_text()
+        b = (seqs[1] / "outputs" / f"mulran_ORORA_cen2018_{name}.txt").read_text()
+        assert a == b and a.count("\n") == 6, name
+    ev = np.loadtxt(seqs[0] / "outputs" / "mulran_ORORA_cen2018_eval_odom.txt", delimiter=",")
+    # ground-truth columns: x of pair i = the row of file i's stamp; y = yaw = -(column 3) through XYYaw2SE2's -yaw
+    assert np.allclose(ev[:, 0], [2.0 + 0.01 * k for k in range(1, 7)], atol=1e-5)
+    assert np.allclose(ev[:, 1], [-0.0139 - 0.001 * k for k in range(1, 7)], atol=1e-6)
+    assert np.allclose(ev[:, 2], [0.0139 + 0.001 * k for k in range(1, 7)], atol=1e-6)
