@@ -197,7 +197,7 @@ int run(const Options &o)
     nrs_solver_params params;
     nrs::setParams(o.noise_bound, 1.0, false, 100, 1.4, 1e-6, params);
     ORORA orora_estimator(o.dataset, "rot", o.use_doppler, false, o.check_stop_motion, 700, 0.049, o.noise_bound_radial,
-                          o.noise_bound_tangential_deg * M_PI / 180.0, ctx);
+                          o.noise_bound_tangential_deg * (M_PI / 180.0), ctx);     // DEG2RAD
     std::vector<std::string> radar_files = get_file_names(o.datadir);
     const bool from_seq = !o.seq_dir.empty();
     const bool write = from_seq || !o.out_dir.empty();
