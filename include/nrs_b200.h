@@ -292,9 +292,13 @@ int nrs_orora_solve(nrs_ctx *ctx, const double *prev_2xN, const double *curr_2xN
 
 typedef struct nrs_frame nrs_frame;   /* device-resident RadarFeature (radar_loader.hpp:16-33) */
 
+/* the reference's own values (`#define CTS350 0`, `#define CIR204 1`, radar_utils.hpp:25-26) */
+#define NRS_NAVTECH_CTS350 0
+#define NRS_NAVTECH_CIR204 1
+
 /* RadarLoader's dataset constants (radar_loader.hpp:48-62) and extractor knobs (:283-297). */
 typedef struct nrs_extract_params {
-    int32_t navtech_version;        /* 0 = CIR204 (MulRan, 3360 bins), 1 = CTS350 (Oxford, 3768 bins) */
+    int32_t navtech_version;        /* NRS_NAVTECH_CTS350 (Oxford, 3768 bins) or NRS_NAVTECH_CIR204 (MulRan, 3360 bins) */
     int32_t range_bins;
     float   radar_resolution;       /* m / bin: 0.05952 (mulran), 0.0432 (oxford) */
     float   cart_resolution;        /* 0.2592 m / px */

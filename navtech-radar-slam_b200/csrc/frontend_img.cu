@@ -486,9 +486,9 @@ int nrs_extract_default_params(const char *dataset, nrs_extract_params *p)
     NRS_CHECK_ARG(dataset && p, "bad argument");
     memset(p, 0, sizeof(*p));
     if (!strcmp(dataset, "oxford")) {                 // radar_loader.hpp:48-54
-        p->navtech_version = 1; p->range_bins = 3768; p->radar_resolution = 0.0432f;
+        p->navtech_version = NRS_NAVTECH_CTS350; p->range_bins = 3768; p->radar_resolution = 0.0432f;
     } else if (!strcmp(dataset, "mulran")) {          // :55-61
-        p->navtech_version = 0; p->range_bins = 3360; p->radar_resolution = 0.05952f;
+        p->navtech_version = NRS_NAVTECH_CIR204; p->range_bins = 3360; p->radar_resolution = 0.05952f;
     } else {
         set_error("nrs_extract_default_params: dataset '%s' not implemented (radar_loader.hpp:62)", dataset);
         return NRS_EINVAL;
@@ -655,7 +655,7 @@ int extract_enqueue(nrs_ctx *ctx, FrontendState *S, nrs_frame *f, int R, int C, 
     NRS_CUDA(cudaEventRecord(S->ev_fork, st));
     NRS_CUDA(cudaStreamWaitEvent(si, S->ev_fork, 0));
     fe_remap_kernel<<<(W * W + 255) / 256, 256, 0, si>>>(S->d_fft, R, C, S->d_theta, S->d_sx, S->d_az, S->d_azsort,
-                                                        S->d_azidx, n_sorted, p->navtech_version == 0,
+                                                        S->d_azidx, n_sorted, p->navtech_version == NRS_NAVTECH_CIR204,
                                                         p->interpolate_crossover, W, S->d_cart,
                                                         (int *)&S->d_counts->cart_max);
     NRS_LAUNCHED();

@@ -41,6 +41,9 @@ static double get_azimuth_index(const double *azimuths, int M, double azimuth)
     return closest;
 }
 
+/* the restatement above, callable on its own (pinned against the reference's compiled get_azimuth_index) */
+double fe_get_azimuth_index(const double *azimuths, int M, double azimuth) { return get_azimuth_index(azimuths, M, azimuth); }
+
 /* radar_utils.cpp:257-298: the static part (x, y, range, theta) and the per-frame angle map.
  * range/angle/theta are width*width float32, row-major.  cir204 selects the MulRan branch
  * (:292-293) vs the uniform-step branch (:295). */

@@ -31,7 +31,7 @@ import numpy as np
 
 from . import pyoracle
 
-CIR204, CTS350 = 0, 1      # radar_utils.hpp navtech versions (MulRan uses CIR204)
+CTS350, CIR204 = 0, 1      # radar_utils.hpp:25-26 navtech versions (MulRan uses CIR204)
 ENCODER_SIZE = 5600
 
 
@@ -100,8 +100,27 @@ def load_radar(raw, navtech_version=CTS350):
 
 
 # ---- features.cpp:197-299 -------------------------------------------------------------------------
-def cen2019_stages(fft, max_points=10000, min_range=58):
-    """Returns a dict with every intermediate the GPU stages are compared against."""
+_stdsort = None
+
+
+def _std_sort_desc(hv, ca, cr):
+    """The candidate order this toolchain's std::sort (libstdc++ introsort) gives the reference (oracle/stdsort.cpp)."""
+    global _stdsort
+    if _stdsort is None:
+        _stdsort = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "libstdsort.so"))
+    hv = np.ascontiguousarray(hv, dtype=np.float32)
+    ca = np.ascontiguousarray(ca, dtype=np.int32).copy()
+    cr = np.ascontiguousarray(cr, dtype=np.int32).copy()
+    _stdsort.oracle_std_sort_desc(_p(hv), _p(ca), _p(cr), len(hv))
+    return ca, cr
+
+
+def cen2019_stages(fft, max_points=10000, min_range=58, order="stable"):
+    """Returns a dict with every intermediate the GPU stages are compared against.
+    order: how candidates of EQUAL response are ordered by the reference's unstable std::sort (features.cpp:224):
+    "stable" = row-major among ties (the oracle's definition, what the GPU path implements); "libstdc++" = the
+    permutation this toolchain's introsort produces, i.e. what the reference compiled here does (pinned exactly against
+    oracle/_ref/libref_frontend.so in tests/test_ref_frontend.py)."""
     fft = np.ascontiguousarray(fft, dtype=np.float32)
     rows, cols = fft.shape
     prewitt = np.zeros((1, 3), dtype=np.float32)
@@ -109,7 +128,8 @@ def cen2019_stages(fft, max_points=10000, min_range=58):
     g = cv2.filter2D(fft, -1, prewitt, anchor=(-1, -1), delta=0, borderType=cv2.BORDER_REFLECT101)
     g = np.abs(g)
     ming, maxg, _, _ = cv2.minMaxLoc(g)
-    g = g * np.float32(1.0 / maxg)                    # Mat /= double == convertTo(-1, 1./s)
+    with np.errstate(all="ignore"):                   # a constant frame has maxg = 0: 1./0 = inf and 0 * inf = NaN, like in C++
+        g = g * np.float32(np.float64(1.0) / np.float64(maxg))      # Mat /= double == convertTo(-1, 1./s)
     mean = np.float32(cv2.mean(fft)[0])
     s = fft - mean
     h = s * (np.float32(1) - g)
@@ -117,9 +137,13 @@ def cen2019_stages(fft, max_points=10000, min_range=58):
     # candidates in row-major order, then stable descending sort on h
     ca, cr = np.nonzero(h > mean_h)
     hv = h[ca, cr]
-    order = np.argsort(-hv, kind="stable")
-    ca = np.ascontiguousarray(ca[order], dtype=np.int32)
-    cr = np.ascontiguousarray(cr[order], dtype=np.int32)
+    if order == "libstdc++":
+        ca, cr = _std_sort_desc(hv, ca, cr)
+    else:
+        assert order == "stable"
+        perm = np.argsort(-hv, kind="stable")
+        ca = np.ascontiguousarray(ca[perm], dtype=np.int32)
+        cr = np.ascontiguousarray(cr[perm], dtype=np.int32)
     R = np.zeros((rows, cols), dtype=np.uint8)
     j = C.c_int()
     L = _lib()
@@ -138,8 +162,8 @@ def cen2019_stages(fft, max_points=10000, min_range=58):
             "cand_a": ca, "cand_r": cr, "R": R, "j_consumed": j.value, "l_regions": l, "targets": targets}
 
 
-def cen2019features(fft, max_points=10000, min_range=58):
-    return cen2019_stages(fft, max_points, min_range)["targets"]
+def cen2019features(fft, max_points=10000, min_range=58, order="stable"):
+    return cen2019_stages(fft, max_points, min_range, order)["targets"]
 
 
 def cen2018_stages(fft, zq=3.0, sigma_gauss=17, min_range=58):
@@ -172,6 +196,15 @@ def cen2018_stages(fft, zq=3.0, sigma_gauss=17, min_range=58):
 
 def cen2018features(fft, zq=3.0, sigma_gauss=17, min_range=58):
     return cen2018_stages(fft, zq, sigma_gauss, min_range)["targets"]
+
+
+def get_azimuth_index(azimuths, azimuth):
+    """radar_utils.cpp:227-250"""
+    az = np.ascontiguousarray(azimuths, dtype=np.float64)
+    fn = _lib().fe_get_azimuth_index
+    fn.restype = C.c_double
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    return fn(_p(az), len(az), float(azimuth))
 
 
 # ---- radar_utils.cpp:252-316 -------------------------------------------------------------------------

@@ -30,13 +30,15 @@ def _cpu_id():
 
 
 def build(force=False):
-    """Compile the C restatement (gcc, seconds).  Also builds oracle/_ref when /root/reference
-    exists (this container); on the GPU box the prebuilt _ref files are used as they travelled."""
+    """Compile the C restatement (gcc, seconds).  Also builds oracle/_ref (the reference's own nanoflann, and its
+    features.cpp / radar_utils.cpp against oracle/refshim/) when /root/reference exists (this container); on the GPU
+    box the prebuilt _ref files are used as they travelled."""
     stamp = os.path.join(_HERE, "_build", ".cpu")
     same_cpu = os.path.exists(stamp) and open(stamp).read() == _cpu_id()
     if force or not same_cpu or not os.path.exists(_LIB) or any(
             os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB)
-            for f in os.listdir(_HERE) if f.endswith(".c") or f == "Makefile"):
+            for f in os.listdir(_HERE) if f.endswith(".c") or f == "stdsort.cpp" or f == "Makefile") or not os.path.exists(
+                os.path.join(_HERE, "_build", "libstdsort.so")):
         if not same_cpu:
             subprocess.call(["make", "-s", "-C", _HERE, "clean"])
         subprocess.check_call(["make", "-s", "-C", _HERE, "all"])

@@ -1,0 +1,152 @@
+"""PINNING the front-end oracle on the reference itself: oracle/_ref/libref_frontend.so is the reference's own
+outlier-robust-radar-odometry/src/features.cpp and src/radar_utils.cpp, compiled unmodified from /root/reference
+against the stand-in headers of oracle/refshim/ (recipe: oracle/Makefile `ref`), with every OpenCV algorithm call served
+by the real cv2 (oracle/refbridge.py).  Every function of those two files that is on the hot path is compared with the
+oracle's restatement (oracle/frontend_ref.*), exactly:
+
+    load_radar                      radar_utils.cpp:104-129      (A1)
+    cen2019features                 features.cpp:133-299         (A2)   -- incl. the std::sort tie order, below
+    cen2018features                 features.cpp:44-131          (A2')
+    get_azimuth_index               radar_utils.cpp:227-250      (A3)
+    polar_to_cartesian_radar_img    radar_utils.cpp:252-316      (A3)
+    polar_to_cartesian_points       radar_utils.cpp:329-341      (A4)
+    convert_to_bev                  radar_utils.cpp:382-403      (A6)
+
+cen2019features sorts its candidates with an unstable std::sort on the response alone (features.cpp:224); equal
+responses are common (u8 samples), so which members of the tie group at the max_points cut-off get marked is decided by
+the toolchain's introsort.  The oracle therefore has two orders: "libstdc++" (oracle/stdsort.cpp: this toolchain's
+std::sort) -- identical to the compiled reference on every frame below -- and "stable" (row-major among ties), the
+definition the GPU path implements and tests/test_frontend_gpu.py holds it to.  test_cen2019_tie_sensitivity measures
+what separates the two.  Runs on CPU; skipped where the library is absent (no /root/reference and no prebuilt copy)."""
+import importlib
+
+import numpy as np
+import pytest
+
+R = importlib.import_module("oracle.refbridge")
+F = importlib.import_module("oracle.frontend_ref")
+
+pytestmark = pytest.mark.skipif(not R.available(), reason="oracle/_ref/libref_frontend.so not built (needs /root/reference)")
+
+
+def frames(synth, dataset, n, seed):
+    world = synth.radar_world(seed=seed)
+    out = []
+    for k in range(n):
+        raw = synth.radar_frame(world, (2.5 * k, 0.1 * k, 0.017 * k), seed=seed + 1 + k, dataset=dataset)
+        out.append(raw)
+    return out
+
+
+def small_fft(seed, rows=48, cols=700, levels=256):
+    """a small frame with heavy ties: few distinct sample values, blobs and a noisy floor"""
+    rng = np.random.default_rng(seed)
+    u8 = np.clip(rng.normal(30, 8, (rows, cols)), 0, 255)
+    for _ in range(60):
+        a, r, w = rng.integers(0, rows), rng.integers(60, cols - 8), rng.integers(2, 6)
+        u8[a:a + rng.integers(1, 4), r:r + w] = rng.integers(120, 250)
+    u8 = (np.round(u8 / (256 // levels)) * (256 // levels)).clip(0, 255).astype(np.uint8)
+    fft = (u8.astype(np.float64) / 255.0).astype(np.float32)
+    fft[:, :42] = 0
+    return fft
+
+
+def test_load_radar(tmp_path, synth):
+    import cv2
+    for dataset, ver in (("mulran", F.CIR204), ("oxford", F.CTS350)):
+        raw = frames(synth, dataset, 1, 40)[0]
+        p = tmp_path / f"{dataset}.png"
+        assert cv2.imwrite(str(p), raw)
+        t, az, valid, fft = R.load_radar(p, ver)
+        ot, oaz, ovalid, offt = F.load_radar(raw, ver)
+        assert np.array_equal(t, ot) and np.array_equal(az, oaz) and np.array_equal(valid, ovalid)
+        assert fft.shape == offt.shape and np.array_equal(fft, offt)
+
+
+@pytest.mark.parametrize("dataset", ["mulran", "oxford"])
+def test_cen2019_and_cen2018_full_frames(synth, dataset):
+    ver = F.CIR204 if dataset == "mulran" else F.CTS350
+    for raw in frames(synth, dataset, 3, 1234 if dataset == "mulran" else 77):
+        _, _, _, fft = F.load_radar(raw, ver)
+        ref = R.cen2019features(fft, 10000, 58)
+        assert ref.shape[1] > 500
+        assert np.array_equal(F.cen2019features(fft, 10000, 58, order="libstdc++"), ref)
+        ref18 = R.cen2018features(fft, 3.0, 17, 58)
+        assert ref18.shape[1] > 500
+        assert np.array_equal(F.cen2018features(fft, 3.0, 17, 58), ref18)
+
+
+def test_cen2019_small_frames_heavy_ties():
+    """few grey levels -> thousands of equal responses; every max_points, min_range; still identical in libstdc++ order"""
+    for seed in range(6):
+        fft = small_fft(seed, levels=(256, 32, 8)[seed % 3])
+        for max_points, min_range in ((10000, 58), (300, 58), (37, 0), (1, 58), (5000, 100)):
+            ref = R.cen2019features(fft, max_points, min_range)
+            got = F.cen2019features(fft, max_points, min_range, order="libstdc++")
+            assert np.array_equal(got, ref), (seed, max_points, min_range)
+        assert np.array_equal(F.cen2018features(fft, 3.0, 17, 58), R.cen2018features(fft, 3.0, 17, 58))
+        assert np.array_equal(F.cen2018features(fft, 1.5, 5, 10), R.cen2018features(fft, 1.5, 5, 10))
+    z = np.zeros((16, 300), dtype=np.float32)                    # degenerate frames: nothing above the mean / all equal
+    z[3, 100] = 1.0
+    for fft in (z, np.full((16, 300), 0.25, dtype=np.float32)):
+        with np.errstate(all="ignore"):
+            assert np.array_equal(F.cen2019features(fft, 100, 58, order="libstdc++"), R.cen2019features(fft, 100, 58))
+
+
+def test_cen2019_tie_sensitivity(synth):
+    """The oracle's stable order (what the GPU implements) against the reference compiled here: the two can differ only
+    through the members of ONE tie group (the one the max_points cut-off falls into), so at most that many keypoints move.
+    With the cut placed between two distinct responses the stable order gives the reference's result exactly."""
+    moved = []
+    for raw in frames(synth, "mulran", 4, 1234):
+        _, _, _, fft = F.load_radar(raw, F.CIR204)
+        st = F.cen2019_stages(fft, 10000, 58)
+        ref = R.cen2019features(fft, 10000, 58)
+        a = set(map(tuple, st["targets"][:2].T.astype(int)))
+        b = set(map(tuple, ref[:2].T.astype(int)))
+        j, h = st["j_consumed"], st["h"]
+        hv = h[st["cand_a"], st["cand_r"]]
+        tie = int((hv == hv[j - 1]).sum()) if j < len(hv) and hv[j] == hv[j - 1] else 0
+        moved.append(len(a ^ b) // 2)
+        assert len(a ^ b) // 2 <= max(tie, 0), (len(a ^ b), tie)
+        assert abs(st["targets"].shape[1] - ref.shape[1]) <= tie
+        if st["l_regions"] == j:
+            # every consumed candidate opened a fresh region: cut the list where the response changes -> no tie at the cut
+            cut = j
+            while cut > 1 and hv[cut] == hv[cut - 1]:
+                cut -= 1
+            assert np.array_equal(F.cen2019features(fft, cut, 58), R.cen2019features(fft, cut, 58))
+    assert sum(moved) <= 8, moved                                 # measured here: [1, 0, 0, 0] keypoints of ~2450 per frame
+
+
+def test_azimuth_index_and_cartesian_image(synth):
+    for dataset, ver in (("mulran", F.CIR204), ("oxford", F.CTS350)):
+        P = F.DatasetParams(dataset)
+        raw = frames(synth, dataset, 1, 9)[0]
+        _, az, _, fft = F.load_radar(raw, ver)
+        rng = np.random.default_rng(3)
+        for a in list(rng.uniform(-0.2, 2 * np.pi + 0.2, 400)) + [az[0], az[-1], az[17], 0.0, 2 * np.pi]:
+            assert R.get_azimuth_index(az, a) == F.get_azimuth_index(az, a), a
+        for as_u8 in (True, False):
+            ref, rows_after = R.polar_to_cartesian_radar_img(az, fft, P.radar_resolution, P.cart_resolution, P.cart_pixel_width,
+                                                             True, ver, as_u8)
+            assert rows_after == fft.shape[0] + 2                 # the function stacks the wrap-around rows into its argument
+            got = F.polar_to_cartesian_radar_img(az, fft, P.radar_resolution, P.cart_resolution, P.cart_pixel_width, True, ver, as_u8)
+            assert got.dtype == ref.dtype and np.array_equal(got, ref), (dataset, as_u8)
+
+
+def test_points_and_bev(synth):
+    for dataset, ver in (("mulran", F.CIR204), ("oxford", F.CTS350)):
+        P = F.DatasetParams(dataset)
+        raw = frames(synth, dataset, 1, 21)[0]
+        times, az, _, fft = F.load_radar(raw, ver)
+        polar = F.cen2018features(fft, 3.0, 17, 58)
+        cart_ref, t_ref = R.polar_to_cartesian_points(az, times, polar, P.radar_resolution)
+        cart, t = F.polar_to_cartesian_points(az, times, polar, P.radar_resolution)
+        assert np.array_equal(cart, cart_ref) and np.array_equal(t, t_ref)
+        c_ref, kp_ref, pt_ref = R.convert_to_bev(cart, P.cart_resolution, P.cart_pixel_width, P.patch_size, t)
+        c, kp, pt = F.convert_to_bev(cart, P.cart_resolution, P.cart_pixel_width, P.patch_size, t)
+        assert 0 < c.shape[1] < cart.shape[1]                      # some points fall outside the 964-pixel image
+        assert np.array_equal(c, c_ref) and np.array_equal(np.asarray(kp, dtype=np.float32).reshape(-1, 2), kp_ref) and np.array_equal(pt, pt_ref)
+        c0_ref, kp0_ref, pt0_ref = R.convert_to_bev(np.zeros((3, 0)), P.cart_resolution, P.cart_pixel_width, P.patch_size, np.zeros(0, np.int64))
+        assert c0_ref.shape == (3, 0) and len(kp0_ref) == 0
