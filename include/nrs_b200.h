@@ -298,8 +298,10 @@ typedef struct nrs_frame nrs_frame;   /* device-resident RadarFeature (radar_loa
 
 /* RadarLoader's dataset constants (radar_loader.hpp:48-62) and extractor knobs (:283-297). */
 typedef struct nrs_extract_params {
-    int32_t navtech_version;        /* NRS_NAVTECH_CTS350 (Oxford, 3768 bins) or NRS_NAVTECH_CIR204 (MulRan, 3360 bins) */
-    int32_t range_bins;
+    int32_t navtech_version;        /* what polar_to_cartesian_radar_img is given (radar_utils.cpp:292-296): NRS_NAVTECH_CTS350 =
+                                     * uniform azimuth step, NRS_NAVTECH_CIR204 = get_azimuth_index.  RadarLoader::extractFeature
+                                     * passes none, i.e. CTS350, for BOTH datasets (radar_loader.hpp:105-107) -- the default here */
+    int32_t range_bins;             /* load_radar's navtech_version: 3768 (CTS350, oxford) / 3360 (CIR204, mulran) */
     float   radar_resolution;       /* m / bin: 0.05952 (mulran), 0.0432 (oxford) */
     float   cart_resolution;        /* 0.2592 m / px */
     int32_t cart_pixel_width;       /* 964 */

@@ -488,7 +488,11 @@ int nrs_extract_default_params(const char *dataset, nrs_extract_params *p)
     if (!strcmp(dataset, "oxford")) {                 // radar_loader.hpp:48-54
         p->navtech_version = NRS_NAVTECH_CTS350; p->range_bins = 3768; p->radar_resolution = 0.0432f;
     } else if (!strcmp(dataset, "mulran")) {          // :55-61
-        p->navtech_version = NRS_NAVTECH_CIR204; p->range_bins = 3360; p->radar_resolution = 0.05952f;
+        // load_radar gets CIR204 here (radar_loader.hpp:82-84: 3360 range bins), but extractFeature hands
+        // polar_to_cartesian_radar_img no version at all (:105-107), i.e. its default CTS350: the node's Cartesian image
+        // uses the uniform-step azimuth mapping (radar_utils.cpp:295) for MulRan too; get_azimuth_index (:293) is only
+        // reached by a caller that sets NRS_NAVTECH_CIR204 here itself
+        p->navtech_version = NRS_NAVTECH_CTS350; p->range_bins = 3360; p->radar_resolution = 0.05952f;
     } else {
         set_error("nrs_extract_default_params: dataset '%s' not implemented (radar_loader.hpp:62)", dataset);
         return NRS_EINVAL;

@@ -342,16 +342,21 @@ def match_features(desc_prev, desc_curr, nndr=np.float32(0.8)):
 
 
 # ---- radar_loader.hpp:74-141 ---------------------------------------------------------------------------------
-def extract_feature(raw, dataset="mulran", voxel_size=0.6, use_voxelization=True, keypoint_extraction="cen2019"):
+def extract_feature(raw, dataset="mulran", voxel_size=0.6, use_voxelization=True, keypoint_extraction="cen2019",
+                    polar_override=None):
+    """polar_override: keypoints to run the rest of the chain on (tests/test_ref_frontend.py hands in cen2019's
+    keypoints in the libstdc++ tie order when comparing with the compiled RadarLoader)."""
     P = DatasetParams(dataset)
     times, azimuths, valid, fft = load_radar(raw, P.navtech_version)
     if keypoint_extraction == "cen2018":                  # radar_loader.hpp:95-99, zq_ / sigma_gauss_ :284-285
         st = cen2018_stages(fft, 3.0, 17, P.min_range)
     else:
         st = cen2019_stages(fft, P.max_points, P.min_range)
-    polar = st["targets"]
+    polar = st["targets"] if polar_override is None else polar_override
+    # radar_loader.hpp:105-107 passes no navtech_version: polar_to_cartesian_radar_img runs with its default CTS350
+    # (uniform azimuth step) for MulRan too -- pinned against the compiled RadarLoader in tests/test_ref_frontend.py
     img = polar_to_cartesian_radar_img(azimuths, fft, P.radar_resolution, P.cart_resolution,
-                                       P.cart_pixel_width, True, P.navtech_version)
+                                       P.cart_pixel_width, True, CTS350)
     cart, t = polar_to_cartesian_points(azimuths, times, polar, P.radar_resolution)
     cart_pre_voxel = cart
     if use_voxelization:

@@ -1,5 +1,6 @@
 // ref_frontend_wrap.cpp -- extern "C" doors into the REFERENCE's own front-end functions, compiled from the sources
-// where they lie (outlier-robust-radar-odometry/src/features.cpp and src/radar_utils.cpp, unmodified) against the
+// where they lie (outlier-robust-radar-odometry/src/features.cpp, src/radar_utils.cpp and the header-only
+// include/radar_loader.hpp, unmodified) against the
 // stand-in headers of oracle/refshim/ (Eigen / OpenCV / Boost / PCL are not in this image; every OpenCV algorithm call
 // is forwarded to the real cv2 through g_ref_cv -- see oracle/refshim/README.md).  Recipe: oracle/Makefile `ref`;
 // output oracle/_ref/libref_frontend.so.  TEST INFRASTRUCTURE ONLY: the oracle (oracle/frontend_ref.*) is checked
@@ -7,6 +8,7 @@
 #include <cstring>
 
 #include "features.hpp"          // the reference's header (declares cen2018features / cen2019features, pulls radar_utils.hpp)
+#include "radar_loader.hpp"      // the reference's RadarLoader (header-only): extractFeature / matchFeatures as the node calls them
 
 extern "C" {
 
@@ -110,6 +112,58 @@ int ref_convert_to_bev(double *cart_3xN, int N, float cart_resolution, int cart_
     if (K) std::memcpy(cart_3xN, cart.data(), sizeof(double) * 3 * (size_t)K);
     for (int i = 0; i < K; ++i) { kp_uv_Nx2[2 * i] = kp[i].pt.x; kp_uv_Nx2[2 * i + 1] = kp[i].pt.y; point_times[i] = pt[i]; }
     return K;
+}
+
+// ---- RadarLoader (radar_loader.hpp:35-308): the chain and the matcher exactly as the node drives them ----
+void *ref_loader_create(const char *dataset, const char *keypoint_extraction, double voxel_size, int use_voxelization)
+{
+    try {
+        return new RadarLoader(dataset, keypoint_extraction, voxel_size, use_voxelization != 0, false);
+    } catch (const std::exception &) {
+        return nullptr;
+    }
+}
+void ref_loader_destroy(void *l) { delete (RadarLoader *)l; }
+
+// radar_loader.hpp:74-141 (cv::imread, cv::ORB through the bridge; pcl::VoxelGrid is the stand-in, see refshim)
+void *ref_extract_feature(void *loader, const char *datadir, const char *radar_file)
+{
+    return new RadarFeature(((RadarLoader *)loader)->extractFeature(datadir, radar_file));
+}
+void ref_feature_destroy(void *f) { delete (RadarFeature *)f; }
+
+// sizes: [0] feat_in_cart_ cols, [1] feat_in_cart_ rows, [2] feat_in_polar_ cols, [3] kp_, [4] desc_ rows, [5] t_, [6] t_norm_,
+// [7] img_ rows, [8] img_ cols
+void ref_feature_sizes(void *fp, int *sizes9)
+{
+    const RadarFeature &f = *(RadarFeature *)fp;
+    sizes9[0] = (int)f.feat_in_cart_.cols(); sizes9[1] = (int)f.feat_in_cart_.rows(); sizes9[2] = (int)f.feat_in_polar_.cols();
+    sizes9[3] = (int)f.kp_.size(); sizes9[4] = f.desc_.rows; sizes9[5] = (int)f.t_.size(); sizes9[6] = (int)f.t_norm_.size();
+    sizes9[7] = f.img_.rows; sizes9[8] = f.img_.cols;
+}
+
+// any pointer may be NULL; cart / polar column-major
+void ref_feature_get(void *fp, double *cart, double *polar, float *kp_xy, uint8_t *desc, int64_t *t, double *t_norm, uint8_t *img,
+                     int64_t *t_criteria, double *time_unit_denominator)
+{
+    const RadarFeature &f = *(RadarFeature *)fp;
+    if (cart && f.feat_in_cart_.size()) std::memcpy(cart, f.feat_in_cart_.data(), sizeof(double) * (size_t)f.feat_in_cart_.size());
+    if (polar && f.feat_in_polar_.size()) std::memcpy(polar, f.feat_in_polar_.data(), sizeof(double) * (size_t)f.feat_in_polar_.size());
+    if (kp_xy) for (size_t i = 0; i < f.kp_.size(); ++i) { kp_xy[2 * i] = f.kp_[i].pt.x; kp_xy[2 * i + 1] = f.kp_[i].pt.y; }
+    if (desc && f.desc_.rows) std::memcpy(desc, f.desc_.data, 32 * (size_t)f.desc_.rows);
+    if (t) for (size_t i = 0; i < f.t_.size(); ++i) t[i] = f.t_[i];
+    if (t_norm) for (size_t i = 0; i < f.t_norm_.size(); ++i) t_norm[i] = f.t_norm_[i];
+    if (img && f.img_.rows) std::memcpy(img, f.img_.data, (size_t)f.img_.rows * f.img_.cols);
+    if (t_criteria) *t_criteria = f.t_crietria_;
+    if (time_unit_denominator) *time_unit_denominator = f.time_unit_denominator_;
+}
+
+// radar_loader.hpp:143-205 -> two new features (prev_matched, curr_matched)
+void ref_match_features(void *loader, void *prev, void *curr, void **prev_matched, void **curr_matched)
+{
+    auto [pm, cm] = ((RadarLoader *)loader)->matchFeatures(*(RadarFeature *)prev, *(RadarFeature *)curr);
+    *prev_matched = new RadarFeature(pm);
+    *curr_matched = new RadarFeature(cm);
 }
 
 }  // extern "C"

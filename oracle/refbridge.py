@@ -25,11 +25,15 @@ _REMAP = C.CFUNCTYPE(None, C.POINTER(C.c_float), C.c_int, C.c_int, C.POINTER(C.c
                      C.POINTER(C.c_float))
 _TO_U8 = C.CFUNCTYPE(None, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_double, C.POINTER(C.c_uint8))
 _IMREAD = C.CFUNCTYPE(C.c_int, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint8), C.c_long)
+_ORB = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_float,
+                   C.POINTER(C.c_uint8))
+_KNN = C.CFUNCTYPE(None, C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                   C.POINTER(C.c_float))
 
 
 class _Callbacks(C.Structure):
     _fields_ = [("filter2D", _FILTER2D), ("mean", _MEAN), ("minmax", _MINMAX), ("remap", _REMAP), ("to_u8", _TO_U8),
-                ("imread_gray", _IMREAD)]
+                ("imread_gray", _IMREAD), ("orb_compute", _ORB), ("knn_match", _KNN)]
 
 
 def _arr(p, rows, cols, dtype=np.float32):
@@ -77,6 +81,36 @@ def _cb_imread(path, rows, cols, buf, cap):
     return 0
 
 
+def _cb_orb(img, rows, cols, patch_size, edge_threshold, kp_xy, n, kp_size, desc):
+    orb = cv2.ORB_create()
+    orb.setPatchSize(patch_size)
+    orb.setEdgeThreshold(edge_threshold)
+    xy = np.ctypeslib.as_array(kp_xy, shape=(max(n, 1), 2))
+    kps = [cv2.KeyPoint(float(xy[i, 0]), float(xy[i, 1]), float(kp_size)) for i in range(n)]
+    kps2, d = orb.compute(np.ctypeslib.as_array(img, shape=(rows, cols)), kps)
+    m = len(kps2)
+    for i, k in enumerate(kps2):
+        xy[i, 0], xy[i, 1] = k.pt
+    if m:
+        np.ctypeslib.as_array(desc, shape=(max(n, 1), 32))[:m] = d
+    return m
+
+
+def _cb_knn(q, nq, t, nt, counts, idx, dist):
+    cnt = np.ctypeslib.as_array(counts, shape=(max(nq, 1),))
+    cnt[:] = 0
+    if nq == 0 or nt == 0:
+        return
+    ii = np.ctypeslib.as_array(idx, shape=(nq, 2))
+    dd = np.ctypeslib.as_array(dist, shape=(nq, 2))
+    knn = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(np.ctypeslib.as_array(q, shape=(nq, 32)), np.ctypeslib.as_array(t, shape=(nt, 32)), k=2)
+    for j, m in enumerate(knn):
+        cnt[j] = len(m)
+        for c, mm in enumerate(m):
+            assert mm.queryIdx == j
+            ii[j, c], dd[j, c] = mm.trainIdx, mm.distance
+
+
 _lib = None
 _keep = None
 
@@ -90,10 +124,19 @@ def lib():
     if _lib is None:
         L = C.CDLL(_PATH)
         _keep = _Callbacks(_FILTER2D(_cb_filter2d), _MEAN(_cb_mean), _MINMAX(_cb_minmax), _REMAP(_cb_remap), _TO_U8(_cb_to_u8),
-                           _IMREAD(_cb_imread))
+                           _IMREAD(_cb_imread), _ORB(_cb_orb), _KNN(_cb_knn))
         L.ref_set_callbacks(C.byref(_keep))
         L.ref_get_azimuth_index.restype = C.c_double
         L.ref_get_azimuth_index.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.ref_loader_create.restype = C.c_void_p
+        L.ref_loader_create.argtypes = [C.c_char_p, C.c_char_p, C.c_double, C.c_int]
+        L.ref_extract_feature.restype = C.c_void_p
+        L.ref_extract_feature.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        for name in ("ref_loader_destroy", "ref_feature_destroy"):
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.ref_feature_sizes.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_feature_get.argtypes = [C.c_void_p] * 10
+        L.ref_match_features.argtypes = [C.c_void_p] * 3 + [C.POINTER(C.c_void_p)] * 2
         _lib = L
     return _lib
 
@@ -178,3 +221,48 @@ def convert_to_bev(cart, cart_resolution, width, patch_size, point_times):
         pt = np.zeros(1, dtype=np.int64)
     k = lib().ref_convert_to_bev(_p(c), n, C.c_float(cart_resolution), int(width), int(patch_size), _p(kp), _p(pt))
     return np.ascontiguousarray(c[:, :k]), kp[:k].copy(), pt[:k].copy()
+
+
+class RadarLoader:
+    """The reference's RadarLoader (radar_loader.hpp:35-308), compiled: extractFeature(datadir, file) and matchFeatures
+    return dicts of plain arrays.  pcl::VoxelGrid inside is the stand-in (oracle/refshim/pcl/filters/voxel_grid.h: the
+    oracle's own recalled restatement, NOT a pin of A5); everything else is the reference's code + the real cv2."""
+
+    def __init__(self, dataset, keypoint_extraction, voxel_size=0.6, use_voxelization=True):
+        self.h = lib().ref_loader_create(dataset.encode(), keypoint_extraction.encode(), float(voxel_size), int(bool(use_voxelization)))
+        if not self.h:
+            raise ValueError("RadarLoader: the reference threw std::invalid_argument")
+
+    def close(self):
+        if self.h:
+            lib().ref_loader_destroy(self.h)
+            self.h = None
+
+    @staticmethod
+    def _unpack(f):
+        L = lib()
+        sz = np.zeros(9, dtype=np.int32)
+        L.ref_feature_sizes(f, _p(sz))
+        kc, rc, kp0, nkp, nd, nt, ntn, ir, ic = (int(v) for v in sz)
+        cart = np.zeros((rc, kc), order="F")
+        polar = np.zeros((3, kp0), order="F")
+        kp = np.zeros((max(nkp, 1), 2), dtype=np.float32)
+        desc = np.zeros((max(nd, 1), 32), dtype=np.uint8)
+        t = np.zeros(max(nt, 1), dtype=np.int64)
+        tn = np.zeros(max(ntn, 1))
+        img = np.zeros((max(ir, 1), max(ic, 1)), dtype=np.uint8)
+        tc, den = C.c_int64(), C.c_double()
+        L.ref_feature_get(f, _p(cart), _p(polar), _p(kp), _p(desc), _p(t), _p(tn), _p(img),
+                          C.cast(C.byref(tc), C.c_void_p), C.cast(C.byref(den), C.c_void_p))
+        return {"feat_in_cart": np.ascontiguousarray(cart), "polar": np.ascontiguousarray(polar), "kp": kp[:nkp].copy(),
+                "desc": desc[:nd].copy(), "t": t[:nt].copy(), "t_norm": tn[:ntn].copy(), "img": img if ir else img[:0],
+                "t_criteria": tc.value, "time_unit_denominator": den.value, "_handle": f}
+
+    def extractFeature(self, datadir, radar_file):
+        f = lib().ref_extract_feature(self.h, str(datadir).encode(), str(radar_file).encode())
+        return self._unpack(f)
+
+    def matchFeatures(self, prev, curr):
+        pm, cm = C.c_void_p(), C.c_void_p()
+        lib().ref_match_features(self.h, prev["_handle"], curr["_handle"], C.byref(pm), C.byref(cm))
+        return self._unpack(pm.value), self._unpack(cm.value)

@@ -46,6 +46,13 @@ struct RefCvCallbacks {
     void (*to_u8)(const float *src, int rows, int cols, double alpha, uint8_t *dst);        // src.convertTo(dst, CV_8UC1, alpha)
     // cv::imread(path, IMREAD_GRAYSCALE): returns 0 on success; buf == NULL asks for the size only
     int (*imread_gray)(const char *path, int *rows, int *cols, uint8_t *buf, long cap);
+    // cv::ORB::create() + setPatchSize + setEdgeThreshold, then compute(img, keypoints, descriptors): kp_xy holds n (x, y)
+    // pairs of size kp_size on entry and the m kept ones on return; desc has room for n x 32 bytes; returns m
+    int (*orb_compute)(const uint8_t *img, int rows, int cols, int patch_size, int edge_threshold, float *kp_xy, int n, float kp_size,
+                       uint8_t *desc);
+    // cv::DescriptorMatcher::create(BRUTEFORCE_HAMMING)->knnMatch(query, train, matches, 2): per query the number of
+    // matches returned (0..2) and their (trainIdx, distance)
+    void (*knn_match)(const uint8_t *q, int nq, const uint8_t *t, int nt, int32_t *counts, int32_t *train_idx_nqx2, float *dist_nqx2);
 };
 extern RefCvCallbacks g_ref_cv;
 }
@@ -263,6 +270,75 @@ inline void vconcat(const Mat &a, const Mat &b, Mat &dst)
     std::memcpy(out.data + na, b.data, nb);
     dst = out;
 }
+
+// ---- features2d: the real OpenCV ----
+template <class T> class Ptr {
+public:
+    Ptr() {}
+    Ptr(std::shared_ptr<T> p) : p_(p) {}
+    T *operator->() const { return p_.get(); }
+    T &operator*() const { return *p_; }
+    explicit operator bool() const { return (bool)p_; }
+private:
+    std::shared_ptr<T> p_;
+};
+
+class ORB {
+public:
+    static Ptr<ORB> create() { return Ptr<ORB>(std::make_shared<ORB>()); }
+    void setPatchSize(int p) { patch_ = p; }
+    void setEdgeThreshold(int e) { edge_ = e; }
+    // Feature2D::compute: keypoints the extractor cannot describe are REMOVED from the vector (the reference relies on it)
+    void compute(const Mat &image, std::vector<KeyPoint> &keypoints, Mat &descriptors)
+    {
+        if (image.type() != CV_8UC1) refshim_unreached("ORB::compute on a non-8-bit image");
+        const int n = (int)keypoints.size();
+        std::vector<float> xy(2 * (size_t)std::max(n, 1));
+        float size = 31;
+        for (int i = 0; i < n; ++i) {
+            xy[2 * i] = keypoints[i].pt.x; xy[2 * i + 1] = keypoints[i].pt.y;
+            if (i == 0) size = keypoints[i].size;
+            else if (keypoints[i].size != size) refshim_unreached("ORB::compute with keypoints of different sizes");
+        }
+        Mat d(std::max(n, 1), 32, CV_8UC1);
+        const int m = g_ref_cv.orb_compute(image.data, image.rows, image.cols, patch_, edge_, xy.data(), n, size, d.data);
+        keypoints.resize((size_t)m);
+        for (int i = 0; i < m; ++i) keypoints[i] = KeyPoint(xy[2 * i], xy[2 * i + 1], size);
+        Mat out(m, 32, CV_8UC1);
+        if (m) std::memcpy(out.data, d.data, 32 * (size_t)m);
+        descriptors = out;
+    }
+private:
+    int patch_ = 31, edge_ = 31;
+};
+
+class DescriptorMatcher {
+public:
+    enum { FLANNBASED = 1, BRUTEFORCE = 2, BRUTEFORCE_L1 = 3, BRUTEFORCE_HAMMING = 4 };
+    static Ptr<DescriptorMatcher> create(int type)
+    {
+        if (type != BRUTEFORCE_HAMMING) refshim_unreached("DescriptorMatcher other than BRUTEFORCE_HAMMING");
+        return Ptr<DescriptorMatcher>(std::make_shared<DescriptorMatcher>());
+    }
+    void knnMatch(const Mat &query, const Mat &train, std::vector<std::vector<DMatch>> &matches, int k) const
+    {
+        if (k != 2) refshim_unreached("knnMatch with k != 2");
+        const int nq = query.rows, nt = train.rows;
+        std::vector<int32_t> counts((size_t)std::max(nq, 1)), idx(2 * (size_t)std::max(nq, 1));
+        std::vector<float> dist(2 * (size_t)std::max(nq, 1));
+        g_ref_cv.knn_match(query.data, nq, train.data, nt, counts.data(), idx.data(), dist.data());
+        matches.assign((size_t)nq, std::vector<DMatch>());
+        for (int i = 0; i < nq; ++i)
+            for (int c = 0; c < counts[i]; ++c) {
+                DMatch m;
+                m.queryIdx = i; m.trainIdx = idx[2 * i + c]; m.distance = dist[2 * i + c];
+                matches[i].push_back(m);
+            }
+    }
+};
+
+inline void imshow(const std::string &, const Mat &) { refshim_unreached("imshow"); }
+inline int waitKey(int = 0) { refshim_unreached("waitKey"); }
 
 // ---- never reached by the pinned functions ----
 inline void hconcat(const Mat &, const Mat &, Mat &) { refshim_unreached("hconcat"); }

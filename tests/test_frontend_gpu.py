@@ -77,6 +77,28 @@ def test_extract_match_solve_parity(nrs, ctx, oracle, synth, F, world, dataset):
         assert g0.handle.info.K_desc < g0.handle.info.K or g1.handle.info.K_desc < g1.handle.info.K
 
 
+def test_remap_get_azimuth_index_branch(nrs, ctx, synth, F, world):
+    """RadarLoader::extractFeature never hands polar_to_cartesian_radar_img a navtech_version (radar_loader.hpp:105-107),
+    so the node's image uses the uniform-step mapping for MulRan too -- the default of nrs_extract_default_params and what
+    every other test here runs.  A caller may still ask for the CIR204 branch (get_azimuth_index over the frame's own,
+    non-uniform azimuths, radar_utils.cpp:227-250,293): same kernel, the other mapping, against the oracle."""
+    loader = nrs.orora.RadarLoader("mulran", "cen2019", 0.6, True, False, ctx=ctx)
+    assert loader.params.navtech_version == F.CTS350 and loader.params.range_bins == 3360
+    raw = synth.radar_frame(world, (1.0, 0.2, 0.03), seed=4242, dataset="mulran")
+    _, az, _, fft = F.load_radar(raw, F.CIR204)
+    uniform = loader.extractFeatureFromRows(raw, 1).handle.stages(*fft.shape)["cart_f32"]
+    assert np.array_equal(uniform, F.polar_to_cartesian_radar_img(az, fft, loader.params.radar_resolution,
+                                                                   loader.params.cart_resolution, 964, True, F.CTS350, as_u8=False))
+    loader.params.navtech_version = F.CIR204
+    g = loader.extractFeatureFromRows(raw, 2)
+    indexed = g.handle.stages(*fft.shape)["cart_f32"]
+    want = F.polar_to_cartesian_radar_img(az, fft, loader.params.radar_resolution, loader.params.cart_resolution, 964, True,
+                                          F.CIR204, as_u8=False)
+    assert np.array_equal(indexed, want) and not np.array_equal(indexed, uniform)
+    assert np.array_equal(g.img_, F.polar_to_cartesian_radar_img(az, fft, loader.params.radar_resolution,
+                                                                 loader.params.cart_resolution, 964, True, F.CIR204, as_u8=True))
+
+
 def test_cen2019_operator_small_and_adversarial(nrs, ctx, F):
     """cen2019features as a stand-alone operator on small frames: random, heavily tied (few grey
     levels), nearly empty, and one where fewer than max_points regions exist."""
@@ -125,9 +147,9 @@ def test_cen2018_operator_stagewise(nrs, ctx, F, synth, world):
     rng = np.random.default_rng(5)
     frames = []
     raw = synth.radar_frame(world, (0, 0, 0), seed=1234, dataset="mulran")
-    frames.append((F.load_radar(raw, 0)[3], 3.0, 17, 58))
+    frames.append((F.load_radar(raw, F.CIR204)[3], 3.0, 17, 58))
     raw = synth.radar_frame(world, (1.0, 0.5, 0.1), seed=99, dataset="oxford")
-    frames.append((F.load_radar(raw, 1)[3], 3.0, 17, 58))
+    frames.append((F.load_radar(raw, F.CTS350)[3], 3.0, 17, 58))
     f = (rng.integers(0, 24, (37, 701)) / 255.0).astype(np.float32)
     hot = rng.random(f.shape) < 0.03
     f[hot] = (rng.integers(120, 256, int(hot.sum())) / 255.0).astype(np.float32)
