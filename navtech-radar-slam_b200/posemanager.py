@@ -30,6 +30,39 @@ def euler_yaw(T):
     return math.atan2(T[1, 0], T[1, 1])
 
 
+def mul4(a, b):
+    """4 x 4 product in plain index order (k ascending, no fused multiply-add), the arithmetic of the C++ twin's Mat4 --
+    numpy's matmul goes through BLAS kernels whose last bit depends on the host"""
+    r = np.zeros((4, 4))
+    for i in range(4):
+        for j in range(4):
+            s = 0.0
+            for k in range(4):
+                s += float(a[i, k]) * float(b[k, j])
+            r[i, j] = s
+    return r
+
+
+def inverse_affine(a):
+    """inverse of [A t; 0 0 0 1] by cofactors, the same expression order as the C++ twin's Mat4::inverse_affine"""
+    f = lambda i, j: float(a[i, j])
+    c00 = f(1, 1) * f(2, 2) - f(1, 2) * f(2, 1)
+    c01 = f(1, 2) * f(2, 0) - f(1, 0) * f(2, 2)
+    c02 = f(1, 0) * f(2, 1) - f(1, 1) * f(2, 0)
+    det = f(0, 0) * c00 + f(0, 1) * c01 + f(0, 2) * c02
+    r = np.eye(4)
+    r[0, 0], r[1, 0], r[2, 0] = c00 / det, c01 / det, c02 / det
+    r[0, 1] = (f(0, 2) * f(2, 1) - f(0, 1) * f(2, 2)) / det
+    r[1, 1] = (f(0, 0) * f(2, 2) - f(0, 2) * f(2, 0)) / det
+    r[2, 1] = (f(0, 1) * f(2, 0) - f(0, 0) * f(2, 1)) / det
+    r[0, 2] = (f(0, 1) * f(1, 2) - f(0, 2) * f(1, 1)) / det
+    r[1, 2] = (f(0, 2) * f(1, 0) - f(0, 0) * f(1, 2)) / det
+    r[2, 2] = (f(0, 0) * f(1, 1) - f(0, 1) * f(1, 0)) / det
+    for i in range(3):
+        r[i, 3] = -(r[i, 0] * f(0, 3) + r[i, 1] * f(1, 3) + r[i, 2] * f(2, 3))
+    return r
+
+
 def xyyaw2se2(xyyaw_rel, dataset):
     """XYYaw2SE2 (:176-188): the MulRan ground truth enters with its yaw negated, like the reference.  The yaw goes
     through tf::createQuaternionFromYaw (double: z = sin(yaw/2), w = cos(yaw/2), x = y = 0), is narrowed to an
@@ -120,9 +153,9 @@ class SE2PoseManager:
 
     def writePoseError(self, Tgt, Test):
         """writePose(Tgt, Test) :194-214 -> [ts_error, rot_error]"""
-        Trel = np.linalg.inv(Tgt) @ Test
+        Trel = mul4(inverse_affine(Tgt), Test)
         ts_error = math.sqrt(Trel[0, 3] ** 2 + Trel[1, 3] ** 2)
-        x = (np.trace(Trel[:3, :3]) - 1) / 2 + EPSILON_ROT
+        x = (Trel[0, 0] + Trel[1, 1] + Trel[2, 2] - 1) / 2 + EPSILON_ROT
         rot_error = math.degrees(math.acos(x)) if -1.0 <= x <= 1.0 else 0.0      # isnan -> 0 (:200-203)
         ts_abs = math.sqrt(Tgt[0, 3] ** 2 + Tgt[1, 3] ** 2)
         ts_perc = 0 if ts_abs < EPSILON_TRANS else ts_error / ts_abs * 100.0

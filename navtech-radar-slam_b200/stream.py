@@ -79,7 +79,7 @@ def run_odometry(datadir, dataset="mulran", keypoint_extraction="cen2018", voxel
                 skipped.append(i)
             dt = time.perf_counter() - t0
             rel.append(T)
-            traj.append(traj[-1] @ T)
+            traj.append(posemanager.mul4(traj[-1], T))                 # curr_odom = curr_odom * Test (odometry.cpp:264)
             times.append(dt)
             if pm_out is not None:
                 if seq_dir is not None:                                # odometry.cpp:253-259
@@ -88,7 +88,7 @@ def run_odometry(datadir, dataset="mulran", keypoint_extraction="cen2018", voxel
                     Tgt = posemanager.xyyaw2se2(xyyaw, dataset)
                 else:
                     Tgt = posemanager.xyyaw2se2(gt_rel[i - 1], dataset) if gt_rel is not None else np.eye(4)
-                curr_gt = curr_gt @ Tgt
+                curr_gt = posemanager.mul4(curr_gt, Tgt)
                 pm_out.writePoseError(Tgt, T)                          # odometry.cpp:281-285
                 pm_out.writePose(Tgt, T, stamp_of(name), next_stamp[i], loader.time_unit_denominator_)   # time1, time2 (:183-185)
                 pm_out.writeTraj(traj[-1], pm_out.est_traj_path_)

@@ -178,7 +178,7 @@ def test_pose_files_equal_python_twin(tmp_path, dataset):
     curr_gt, curr = np.eye(4), np.eye(4)
     for g, T, t1, t2, us in pairs:
         Tgt = pmod.xyyaw2se2(g, dataset)
-        curr_gt, curr = curr_gt @ Tgt, curr @ T
+        curr_gt, curr = pmod.mul4(curr_gt, Tgt), pmod.mul4(curr, T)
         pm.writePoseError(Tgt, T)
         pm.writePose(Tgt, T, t1, t2, den)
         pm.writeTraj(curr, pm.est_traj_path_)
