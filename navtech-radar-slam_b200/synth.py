@@ -137,6 +137,10 @@ def radar_frame(world, pose=(0.0, 0.0, 0.0), seed=1234, dataset="mulran", t0=1_5
     rngm = np.hypot(lx, ly)
     az = np.arctan2(ly, lx) % (2 * np.pi)
     jit = rng.integers(0, 2, n_azimuths) if cfg["jitter"] else np.zeros(n_azimuths, dtype=np.int64)
+    # the first two azimuths keep the nominal 14-tick step: the node derives the azimuth step of its Cartesian image from
+    # exactly these two (radar_utils.cpp:279, reached with the default CTS350 for MulRan too: radar_loader.hpp:105-107),
+    # so a jittered pair would warp the whole image by 7 % -- real scans start regular
+    jit[:2] = 0
     enc = ((np.arange(n_azimuths) * 14 + jit) % 5600).astype(np.uint16)
     az_table = enc.astype(np.float64) * 2 * np.pi / 5600.0
     img = np.clip(rng.normal(30, 8, size=(n_azimuths, bins)), 0, 255)
