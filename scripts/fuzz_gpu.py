@@ -1,0 +1,120 @@
+"""Randomised GPU-vs-oracle sweep through the C ABI (run on a B200: python scripts/fuzz_gpu.py SEED SECONDS [out.json]).
+Solver: the problem families of scripts/fuzz_ref_solver.py (duplicates, near-collinear clouds, far points, heavy noise)
+-- edge count, clique, rotation-inlier count and final inliers must be identical, the pose within north_star's
+1e-4 m / 1e-5 rad.  ScanContext: databases of binary, general-valued, tie-heavy, extreme-magnitude and near-empty
+descriptors -- per-keyframe (distance bits, shift) through nrs_sc_query_all and the winner through nrs_sc_query /
+nrs_sc_query_batch must equal the oracle exactly.  The oracle itself is pinned on the reference's compiled code
+(tests/test_ref_*.py), so this closes the chain reference -> oracle -> GPU on random inputs."""
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as O  # noqa: E402
+
+nrs = importlib.import_module("navtech-radar-slam_b200")
+synth = importlib.import_module("navtech-radar-slam_b200.synth")
+
+
+def rand_desc(rng, kind):
+    if kind == 0:
+        d = (rng.random((60, 20)) < rng.uniform(0.02, 0.6)) * 3.0
+    elif kind == 1:
+        d = (rng.random((60, 20)) < rng.uniform(0.1, 0.9)) * rng.uniform(0.5, 8.0, (60, 20))
+    elif kind == 2:
+        cols = (rng.random((3, 20)) < 0.4) * 3.0
+        d = cols[rng.integers(0, 3, 60)]
+    elif kind == 3:
+        d = (rng.random((60, 20)) < 0.3) * (10.0 ** rng.uniform(-6, 6, (60, 20)))
+    else:
+        d = np.zeros((60, 20))
+        d[rng.integers(0, 60, 3), rng.integers(0, 20, 3)] = 3.0
+    return d.reshape(-1).astype(np.float64)
+
+
+def main():
+    seed, seconds = int(sys.argv[1]), float(sys.argv[2])
+    rng = np.random.default_rng(seed)
+    ctx = nrs.Context(0)
+    out = {"seed": seed, "solver_cases": 0, "solver_mismatch": 0, "solver_max_dt_m": 0.0, "solver_max_dyaw_rad": 0.0,
+           "sc_databases": 0, "sc_pairs": 0, "sc_mismatch": 0, "notes": []}
+    t_end = time.time() + seconds / 2
+    it = 0
+    while time.time() < t_end:
+        N = int(rng.integers(3, 600))
+        prev, curr, _, _ = synth.correspondences(N, float(rng.uniform(0.15, 1.0)), int(rng.integers(0, 1 << 30)))
+        mode = it % 5
+        it += 1
+        if mode == 1:
+            k = rng.integers(0, N, N // 4)
+            prev[:, :len(k)], curr[:, :len(k)] = prev[:, k], curr[:, k]
+        if mode == 2:
+            prev[1] *= 1e-3
+            curr[1] *= 1e-3
+        if mode == 3:
+            prev, curr = prev * 3.0, curr * 3.0
+        if mode == 4:
+            curr = curr + rng.normal(0, 0.4, curr.shape)
+        P = O.OroraParams(float(rng.choice([0.5, 0.75, 1.0])), 1.0, int(rng.choice([50, 100])), float(rng.choice([1.39, 1.4])),
+                          float(rng.choice([1e-6, 1e-4])), float(rng.choice([0.1, 0.3536])), np.deg2rad(9.0))
+        o = O.orora_solve(curr, prev, P)
+        p = nrs.orora.default_params()
+        p.noise_bound, p.cbar2, p.rotation_max_iterations = P.noise_bound, P.cbar2, P.max_iter
+        p.rotation_gnc_factor, p.rotation_cost_threshold = P.gnc_factor, P.cost_thr
+        p.noise_bound_radial, p.noise_bound_tangential = P.nb_radial, P.nb_tangential
+        p.check_stop_motion, p.use_doppler_compensation = 0, 0
+        g = nrs.orora.solve(ctx, prev, curr, p)
+        dt = float(np.hypot(g["T"][0, 3] - o["T"][0, 3], g["T"][1, 3] - o["T"][1, 3]))
+        dy = np.arctan2(g["T"][1, 0], g["T"][0, 0]) - np.arctan2(o["T"][1, 0], o["T"][0, 0])
+        dy = float(abs((dy + np.pi) % (2 * np.pi) - np.pi))
+        same = (g["info"].n_edges == o["info"].n_edges and np.array_equal(g["clique"], o["clique"]) and
+                g["info"].n_rot_inliers == o["info"].n_rot_inliers and np.array_equal(g["final_inliers"], o["final_inliers"]) and
+                g["valid"] == o["valid"] and dt <= 1e-4 and dy <= 1e-5)
+        out["solver_cases"] += 1
+        out["solver_max_dt_m"], out["solver_max_dyaw_rad"] = max(out["solver_max_dt_m"], dt), max(out["solver_max_dyaw_rad"], dy)
+        if not same:
+            out["solver_mismatch"] += 1
+            if len(out["notes"]) < 20:
+                out["notes"].append(f"solver it {it} N {N} mode {mode}: edges {g['info'].n_edges}/{o['info'].n_edges} clique "
+                                    f"{len(g['clique'])}/{len(o['clique'])} eq {np.array_equal(g['clique'], o['clique'])} rot "
+                                    f"{g['info'].n_rot_inliers}/{o['info'].n_rot_inliers} final {len(g['final_inliers'])}/"
+                                    f"{len(o['final_inliers'])} dt {dt:.3g} dyaw {dy:.3g}")
+    t_end = time.time() + seconds / 2
+    while time.time() < t_end:
+        kind = int(rng.integers(0, 5))
+        mixed = rng.random() < 0.3
+        D = int(rng.integers(40, 400))
+        db = np.stack([rand_desc(rng, int(rng.integers(0, 5)) if mixed else kind) for _ in range(D)])
+        d = nrs.scancontext.SCDatabase(ctx)
+        d.append(db)
+        qs = [rand_desc(rng, kind), db[int(rng.integers(0, D))], synth.shift_desc(db[int(rng.integers(0, D))], int(rng.integers(0, 60))),
+              rand_desc(rng, int(rng.integers(0, 5)))]
+        first, last = int(rng.integers(0, D // 3)), int(rng.integers(2 * D // 3, D + 1))
+        batch = d.query_batch(np.stack(qs), first, last)
+        for q, b in zip(qs, batch):
+            od, os_, best = O.sc_search(q, db, first, last)
+            gd, gs, gbest = d.query_all(q, first, last)
+            eq = (np.array_equal(gd.view(np.uint64), od.view(np.uint64)) or np.array_equal(np.isnan(gd), np.isnan(od)) and
+                  np.array_equal(gd[~np.isnan(gd)], od[~np.isnan(od)])) and np.array_equal(gs, os_)
+            eq = eq and tuple(gbest) == tuple(best) and tuple(d.query(q, first, last)) == tuple(best) and tuple(b) == tuple(best)
+            out["sc_pairs"] += last - first
+            if not eq:
+                out["sc_mismatch"] += 1
+                if len(out["notes"]) < 20:
+                    out["notes"].append(f"sc kind {kind} mixed {mixed} D {D} [{first},{last}): best gpu {gbest} single {d.query(q, first, last)} "
+                                        f"batch {b} oracle {best}; per-keyframe dist differ at {int((gd != od).sum())}, shift at {int((gs != os_).sum())}")
+        out["sc_databases"] += 1
+        d.close()
+    print(json.dumps(out))
+    if len(sys.argv) > 3:
+        with open(sys.argv[3], "w") as f:
+            json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
