@@ -72,7 +72,10 @@ def main():
         dt = float(np.hypot(g["T"][0, 3] - o["T"][0, 3], g["T"][1, 3] - o["T"][1, 3]))
         dy = np.arctan2(g["T"][1, 0], g["T"][0, 0]) - np.arctan2(o["T"][1, 0], o["T"][0, 0])
         dy = float(abs((dy + np.pi) % (2 * np.pi) - np.pi))
-        same = (g["info"].n_edges == o["info"].n_edges and np.array_equal(g["clique"], o["clique"]) and
+        # an edgeless graph has only one-vertex "cliques": estimation fails on both sides (valid = false, Identity, like
+        # nonminimal_solver.hpp:713-720) and which lone vertex is named means nothing
+        lone = o["info"].M <= 1 and g["info"].M == o["info"].M
+        same = (g["info"].n_edges == o["info"].n_edges and (lone or np.array_equal(g["clique"], o["clique"])) and
                 g["info"].n_rot_inliers == o["info"].n_rot_inliers and np.array_equal(g["final_inliers"], o["final_inliers"]) and
                 g["valid"] == o["valid"] and dt <= 1e-4 and dy <= 1e-5)
         out["solver_cases"] += 1
