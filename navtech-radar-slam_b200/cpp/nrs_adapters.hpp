@@ -420,13 +420,43 @@ double cen2018features(const float *fft_data, int rows, int cols, float zq, int 
 // ================================================================================================
 // RadarFeature / RadarLoader (radar_loader.hpp:16-33, 35-308)
 // ================================================================================================
-template <class MatrixXd>
+// Mat / KeyPoint: the node's own types where OpenCV is around -- RadarFeatureT<Eigen::MatrixXd, cv::Mat, cv::KeyPoint> has
+// the reference's exact members (cv::Mat img_ / desc_, std::vector<cv::KeyPoint> kp_), so its visualisation branch
+// (odometry.cpp:335-339,362) compiles against it unchanged.  The defaults are plain buffers: img_ = W*W bytes,
+// desc_ = K_desc*32 bytes, kp_ = K_desc (u, v) float pairs.
+struct RawKeyPoint { float u, v; };
+
+namespace detail {
+// 8-bit single-channel matrix <- bytes: std::vector<uint8_t>, or anything with cv::Mat's create(rows, cols, type) / data
+inline void fill_bytes(std::vector<uint8_t> &dst, const uint8_t *src, int rows, int cols) { dst.assign(src, src + (size_t)rows * cols); }
+template <class Mat>
+auto fill_bytes(Mat &dst, const uint8_t *src, int rows, int cols) -> decltype(dst.create(rows, cols, 0), void())
+{
+    dst.create(rows, cols, 0 /* CV_8UC1 */);
+    if (rows && cols) std::memcpy(dst.data, src, (size_t)rows * cols);
+}
+// keypoints <- K (u, v) pairs: RawKeyPoint keeps the pair, anything else is built like cv::KeyPoint(x, y, size)
+inline void fill_keypoints(std::vector<RawKeyPoint> &dst, const float *uv, int n, float)
+{
+    dst.resize((size_t)n);
+    for (int i = 0; i < n; ++i) dst[(size_t)i] = RawKeyPoint{uv[2 * i], uv[2 * i + 1]};
+}
+template <class KeyPoint>
+void fill_keypoints(std::vector<KeyPoint> &dst, const float *uv, int n, float size)
+{
+    dst.clear();
+    dst.reserve((size_t)n);
+    for (int i = 0; i < n; ++i) dst.emplace_back(uv[2 * i], uv[2 * i + 1], size);
+}
+}  // namespace detail
+
+template <class MatrixXd, class Mat = std::vector<uint8_t>, class KeyPoint = RawKeyPoint>
 struct RadarFeatureT {
-    std::vector<uint8_t> img_;                 // 964 x 964 (cv::Mat CV_8UC1 data)
+    Mat img_;                                  // 964 x 964 (CV_8UC1)
     std::vector<int64_t> t_;
     double time_unit_denominator_ = 1.0;
-    std::vector<uint8_t> desc_;                // K_desc x 32
-    std::vector<float> kp_;                    // K_desc x 2 (u, v)
+    Mat desc_;                                 // K_desc x 32 (CV_8UC1)
+    std::vector<KeyPoint> kp_;                 // K_desc keypoints (u, v), size = patch_size
     MatrixXd feat_in_cart_;
     MatrixXd feat_in_polar_;
     MatrixXd feat_compensated_;
@@ -435,10 +465,10 @@ struct RadarFeatureT {
     std::shared_ptr<nrs_frame> frame_;         // device-resident copy used by matchFeatures
 };
 
-template <class MatrixXd>
+template <class MatrixXd, class Mat = std::vector<uint8_t>, class KeyPoint = RawKeyPoint>
 class RadarLoaderT {
 public:
-    using RadarFeature = RadarFeatureT<MatrixXd>;
+    using RadarFeature = RadarFeatureT<MatrixXd, Mat, KeyPoint>;
     using FeatureMatching = std::tuple<RadarFeature, RadarFeature>;
 
     RadarLoaderT(const std::string &dataset, const std::string keypoint_extraction, const double voxel_size,
@@ -465,13 +495,16 @@ public:
         check(nrs_frame_info_get(f, &info));
         r.feat_in_polar_.resize(3, info.K_polar);
         r.feat_in_cart_.resize(3, info.K);
-        r.kp_.resize(2 * (size_t)info.K_desc);
         r.t_.resize(info.K);
         r.t_norm_.resize(info.K);
-        r.desc_.resize(32 * (size_t)info.K_desc);
-        r.img_.resize((size_t)p_.cart_pixel_width * p_.cart_pixel_width);
-        check(nrs_frame_get(f, r.feat_in_polar_.data(), r.feat_in_cart_.data(), r.kp_.data(), r.t_.data(),
-                            r.t_norm_.data(), r.desc_.data(), r.img_.data()));
+        const int W = p_.cart_pixel_width;
+        std::vector<float> kp(2 * (size_t)info.K_desc + 2);
+        std::vector<uint8_t> desc(32 * (size_t)info.K_desc + 32), img((size_t)W * W);
+        check(nrs_frame_get(f, r.feat_in_polar_.data(), r.feat_in_cart_.data(), kp.data(), r.t_.data(),
+                            r.t_norm_.data(), desc.data(), img.data()));
+        detail::fill_bytes(r.img_, img.data(), W, W);
+        detail::fill_bytes(r.desc_, desc.data(), info.K_desc, 32);
+        detail::fill_keypoints(r.kp_, kp.data(), info.K_desc, (float)p_.patch_size);    // cv::KeyPoint(u, v, patch_size): radar_utils.cpp:393
         r.t_crietria_ = t_criteria;
         r.time_unit_denominator_ = time_unit_denominator_;
         return r;
@@ -480,7 +513,7 @@ public:
     FeatureMatching matchFeatures(const RadarFeature &prev_feat, const RadarFeature &curr_feat)
     {
         RadarFeature prev_matched = prev_feat, curr_matched = curr_feat;           // :144-146
-        const int cap = (int)(prev_feat.kp_.size() / 2) + 1;
+        const int cap = (int)prev_feat.kp_.size() + 1;
         std::vector<int32_t> q(cap), t(cap);
         std::vector<double> pxy(2 * (size_t)cap), cxy(2 * (size_t)cap);
         std::vector<int64_t> pt(cap), ct(cap);
@@ -495,9 +528,15 @@ public:
         curr_matched.t_.assign(ct.begin(), ct.begin() + n);
         prev_matched.t_norm_.resize(n);
         curr_matched.t_norm_.resize(n);
+        prev_matched.kp_.resize(n);
+        curr_matched.kp_.resize(n);
         for (int j = 0; j < n; ++j) {
             prev_matched.t_norm_[j] = prev_feat.t_norm_[q[j]];
             curr_matched.t_norm_[j] = curr_feat.t_norm_[t[j]];
+            // "For visualization" (:189-191): BOTH come from prev_feat.kp_ in the reference, the second indexed with the train
+            // index -- out of range there when the current frame has more keypoints; clamped here
+            prev_matched.kp_[j] = prev_feat.kp_[q[j]];
+            curr_matched.kp_[j] = prev_feat.kp_[std::min<size_t>((size_t)t[j], prev_feat.kp_.size() - 1)];
         }
         return {prev_matched, curr_matched};
     }
@@ -621,7 +660,7 @@ private:
 template <class MatrixXd, class Cloud = SimpleCloud>
 class ORORAT {
 public:
-    using RadarFeature = RadarFeatureT<MatrixXd>;
+    using RadarFeature = RadarFeatureT<MatrixXd>;              // calcTransform takes any RadarFeatureT<MatrixXd, Mat, KeyPoint>
     using Solver = NonMinimalSolverT<MatrixXd, MatrixXd, Cloud>;
     using InlierSetPairs = typename Solver::InlierSetPairs;
 
@@ -637,8 +676,8 @@ public:
     }
 
     // returns the 4x4 transform, column-major like Eigen (ORORA.hpp:37-93)
-    MatrixXd calcTransform(const nrs_solver_params params, const double delta_t, RadarFeature &prev_matched,
-                           RadarFeature &curr_matched)
+    template <class Feature>
+    MatrixXd calcTransform(const nrs_solver_params params, const double delta_t, Feature &prev_matched, Feature &curr_matched)
     {
         const double prev_vel_x = curr_vel_x_;                                      // prev_vel_se3_ = curr_vel_se3_ (:42)
         // feat_compensated_ is a public product of the call (the node draws it, odometry.cpp:344-345)

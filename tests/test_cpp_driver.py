@@ -231,6 +231,27 @@ def test_ground_truth_reader(tmp_path):
             pm.getXYYawPose(12345, 67890) if dataset == "oxford" else pm.getXYYawPose(12345)
 
 
+def test_adapters_with_cv_and_eigen_types(tmp_path):
+    """RadarFeatureT<Eigen::MatrixXd, cv::Mat, cv::KeyPoint> -- the reference's exact RadarFeature members -- RadarLoaderT,
+    ORORAT and SCManagerT compiled and linked against OpenCV- / Eigen- / PCL-shaped types (tests/cpp/cv_types_check.cpp).
+    Neither library exists in this image: the interface stand-ins of oracle/refshim supply the shapes (cv::Mat::create /
+    data / rows / cols, cv::KeyPoint(x, y, size), MatrixXd::resize / data / operator(), PointCloud::points).  Without a GPU
+    the program must stop at nrs_ctx_create (77); with one it extracts, matches and solves through these types (0;
+    profiles/tests/r02_cpp_host_check.log holds a run on a B200)."""
+    shim = os.path.join(ROOT, "oracle", "refshim")
+    lib = os.path.join(ROOT, "navtech-radar-slam_b200")
+    if not os.path.exists(os.path.join(lib, "libnrs_b200.so")):
+        pytest.skip("libnrs_b200.so not built")
+    exe = str(tmp_path / "cv_types_check")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I" + shim, "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(lib, "cpp"),
+                        os.path.join(ROOT, "tests", "cpp", "cv_types_check.cpp"), "-L" + lib, "-lnrs_b200", "-Wl,-rpath," + lib, "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode in (0, 77), (r.returncode, r.stdout, r.stderr)
+    assert "adapters" in r.stdout
+
+
 def test_driver_without_gpu_or_input(tmp_path):
     """No CPU fallback in the C++ host either: without a device the driver says so and exits 77; a bad directory or
     flag is an error (1), not a crash."""
