@@ -88,3 +88,35 @@ def test_orora_sequence_with_doppler(oracle, synth):
     assert np.array_equal(pc, prev) and np.array_equal(cc, curr)
     assert pose_close(Tr, oracle.orora_calc_transform(prev, curr, 3.0, use_doppler=False)[0]["T"])
     off.close()
+
+
+def test_whole_reference_pipeline_four_frames(tmp_path, oracle, synth):
+    """The node's loop body end to end in the reference's own compiled code -- RadarLoader::extractFeature ->
+    RadarLoader::matchFeatures (libref_frontend.so) -> ORORA::calcTransform with the velocity carried (libref_solver.so) -- on
+    four MulRan-format PNGs, against the oracle chain: identical matched pairs, poses to 1e-12."""
+    import cv2
+    RB = importlib.import_module("oracle.refbridge")
+    F = importlib.import_module("oracle.frontend_ref")
+    if not RB.available():
+        pytest.skip("oracle/_ref/libref_frontend.so not built")
+    world = synth.radar_world(seed=808)
+    names, raws = [], []
+    for k in range(4):
+        raws.append(synth.radar_frame(world, (2.2 * k, -0.08 * k, np.deg2rad(0.7) * k), seed=810 + k, dataset="mulran"))
+        names.append(f"{1560000000000000000 + k * 250000000}.png")
+        assert cv2.imwrite(str(tmp_path / names[-1]), raws[-1])
+    loader = RB.RadarLoader("mulran", "cen2018", 0.6, True)
+    est = RS.ORORA("mulran", "rot", True, False, True, 700, 0.049, 0.1, np.deg2rad(9.0))
+    fr = [loader.extractFeature(tmp_path, n) for n in names]
+    fo = [F.extract_feature(raw, "mulran", 0.6, True, "cen2018") for raw in raws]
+    vel = 0.0
+    for k in range(1, 4):
+        pm, cm = loader.matchFeatures(fr[k - 1], fr[k])
+        po, co, _, _ = F.match_frames(fo[k - 1], fo[k])
+        assert np.array_equal(pm["feat_in_cart"], po) and np.array_equal(cm["feat_in_cart"], co)
+        Tr, _, _ = est.calcTransform(pm["feat_in_cart"], cm["feat_in_cart"], 0.25)
+        ro, vel = oracle.orora_calc_transform(po, co, vel, delta_t=0.25)
+        assert pose_close(Tr, ro["T"], 1e-12, 1e-12), (k, np.abs(Tr - ro["T"]).max())
+        assert abs(Tr[0, 3] - 2.2) < 0.5                      # and it is the planted motion
+    loader.close()
+    est.close()
