@@ -183,6 +183,30 @@ def run_reference(args, rank, world):
     }
     if out_orora is not None:
         out["orora"] = out_orora
+    # for information: the reference's OWN distanceBtnScanContext loop, compiled in place (oracle/_ref/libref_sc.so, built
+    # here from pgo/SC-A-LOAM/include/scancontext/Scancontext.cpp against oracle/refshim -- its Eigen is a stand-in, so this
+    # is not Eigen's speed; one thread like the node).  `value` above stays the oracle port: the faster, stronger baseline.
+    try:
+        from oracle import refsc
+        if refsc.available():
+            m = refsc.SCManager()
+            n_pairs = 600
+            best = (1e7, 0, 0)
+            t0 = time.perf_counter()
+            for i in range(n_pairs):
+                d_, s_ = m.distanceBtnScanContext(queries[0], db[i])
+                if d_ < best[0]:
+                    best = (d_, i, s_)
+            per_pair = (time.perf_counter() - t0) / n_pairs
+            m.close()
+            _, _, port_best = O.sc_search(queries[0], db, 0, n_pairs, want_all=False)
+            out["reference_compiled"] = {
+                "value": 1.0 / (per_pair * D_KEYFRAMES), "unit": "queries/s", "cores": 1, "kind": "reference",
+                "sample": f"{n_pairs} keyframes scored by the reference's compiled SCManager::distanceBtnScanContext "
+                          f"({1e6 * per_pair:.0f} us per keyframe), scaled to the 10k DB; Eigen stand-in (oracle/refshim)",
+                "agrees_with_port": bool(tuple(best) == tuple(port_best))}
+    except Exception as e:                                   # informative block only
+        out["reference_compiled"] = {"error": repr(e)}
     emit_json(out)
 
 
