@@ -117,8 +117,9 @@ struct Mat4 {
 };
 
 // rot.eulerAngles(0, 1, 2)(2) of a rotation about z (Eigen/src/Geometry/EulerAngles.h with i,j,k = 0,1,2: the first
-// angle atan2(R(1,2), R(2,2)) is 0, so s1 = 0, c1 = 1 and the third is -atan2(-R(1,0), R(1,1)))
-inline double euler_yaw(const Mat4 &T) { return -std::atan2(-T(1, 0), T(1, 1)); }
+// angle atan2(R(1,2), R(2,2)) is 0, so s1 = 0, c1 = 1 and the third is -atan2(s1 R(2,0) - c1 R(1,0), c1 R(1,1) - s1 R(2,1))
+// = -atan2(0 - R(1,0), R(1,1)); the subtraction is kept so that an exact R(1,0) = +0 gives -0 like there)
+inline double euler_yaw(const Mat4 &T) { return -std::atan2(0.0 - T(1, 0), T(1, 1)); }
 
 class SE2PoseManager {
 public:

@@ -26,8 +26,12 @@ def _g(v):
 
 
 def euler_yaw(T):
-    """rot.eulerAngles(0, 1, 2)(2) of a planar rotation (Eigen's convention: first angle in [0, pi])"""
-    return math.atan2(T[1, 0], T[1, 1])
+    """rot.eulerAngles(0, 1, 2)(2) of a rotation about z, as Eigen/src/Geometry/EulerAngles.h evaluates it with
+    i, j, k = 0, 1, 2: the first angle atan2(R(1,2), R(2,2)) is 0, so s1 = 0, c1 = 1 and the third angle is
+    -atan2(s1 R(2,0) - c1 R(1,0), c1 R(1,1) - s1 R(2,1)) = -atan2(0 - R(1,0), R(1,1)) -- written with the subtraction so
+    that an exact R(1,0) = +0 gives -0 like there (the node's est_traj.txt starts "0,0,-0"; pinned against the compiled
+    reference in tests/test_ref_posemanager.py)"""
+    return -math.atan2(0.0 - float(T[1, 0]), float(T[1, 1]))
 
 
 def mul4(a, b):
